@@ -1,0 +1,117 @@
+/* srk.h -- C ABI of libsrk.so, the B200 (sm_100a) fused window-attention kernels.
+ *
+ * The reference (ViacheslavTimofeev/tpu_superresolution) has no FFI layer: its boundary for this
+ * path is the nn.Module surface.  The drop-in modules in
+ * tpu_superresolution_b200/swinir.py keep that surface and call the entry points below through
+ * ctypes.  Each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every device pointer is BORROWED for the duration of the
+ *    enqueue (PyTorch owns all memory); nothing is allocated or freed on the device;
+ *  - functions only enqueue work on `stream` (a cudaStream_t), no implicit synchronisation;
+ *  - return 0 on success, non-zero on error (srk_last_error_string() describes it);
+ *    unsupported configurations are errors -- there is no CPU or eager fallback;
+ *  - activations are fp32 token rows [token][ld] (ld floats per token, ld % 4 == 0, ld >= 180),
+ *    i.e. exactly the reference's (B, H*W, C) tensors; GEMM operands are bf16 with fp32
+ *    accumulation; weights arrive pre-packed by tpu_superresolution_b200/packing.py.
+ */
+#ifndef SRK_H_
+#define SRK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRK_ABI_VERSION 1
+
+/* Fixed geometry of the SwinIR/HAT/DAT "M" family served by these kernels. */
+#define SRK_DIM 180        /* embed_dim                      (finetune_swinir.py:276) */
+#define SRK_DIM_PAD 192    /* padded to a multiple of the UMMA K-atom (64) */
+#define SRK_HEADS 6        /* num_heads                      (finetune_swinir.py:277) */
+#define SRK_HEAD_DIM 30    /* 180 / 6 */
+#define SRK_HEAD_PAD 32    /* head_dim padded to the UMMA K step */
+#define SRK_WINDOW 8       /* window_size                    (finetune_swinir.py:273) */
+#define SRK_HIDDEN 360     /* int(dim * mlp_ratio), mlp_ratio 2 (finetune_swinir.py:278) */
+#define SRK_HIDDEN_PAD 384
+
+/* byte sizes of the packed weight streams (see packing.py for the slab order) */
+#define SRK_ATTN_WSTREAM_BYTES (15 * 16384 + 3 * 24576)
+#define SRK_MLP_WSTREAM_BYTES (12 * 24576)
+/* float offsets inside the packed per-block vectors */
+#define SRK_AV_LN_W 0
+#define SRK_AV_LN_B 192
+#define SRK_AV_BIAS_V 384          /* 256: v bias in padded head layout (h*32+d) */
+#define SRK_AV_BIAS_QK 640         /* 3 x 128: per head pair [q(2p) q(2p+1) k(2p) k(2p+1)], q pre-scaled */
+#define SRK_AV_BIAS_PROJ 1024      /* 192 */
+#define SRK_AV_RPB 1216            /* 6 x 232: relative-position-bias table per head, * log2(e) */
+#define SRK_AV_RPB_STRIDE 232
+#define SRK_ATTN_VEC_FLOATS (1216 + 6 * 232)
+#define SRK_MV_LN_W 0
+#define SRK_MV_LN_B 192
+#define SRK_MV_B1 384              /* 384 */
+#define SRK_MV_B2 768              /* 192 */
+#define SRK_MLP_VEC_FLOATS 960
+
+/* Attention half of a Swin block:  y = x + proj(softmax(q k^T * scale + rpb + mask) v),
+ * q,k,v = qkv(LN1(x)) on cyclically shifted 8x8 windows.
+ * Replaces network_swinir.py:244-276 (SwinTransformerBlock.forward up to the first residual) and,
+ * with mode = SRK_MODE_WINDOWS, network_swinir.py:114-145 (WindowAttention.forward). */
+enum { SRK_MODE_IMAGE = 0, SRK_MODE_WINDOWS = 1 };
+enum { SRK_MASK_NONE = 0, SRK_MASK_SHIFT = 1, SRK_MASK_EXPLICIT = 2 };
+
+typedef struct SrkSwinAttnDesc {
+    int32_t mode;          /* SRK_MODE_IMAGE: x is (batch, height*width, ld); SRK_MODE_WINDOWS: x is (num_windows, 64, ld) */
+    int32_t batch;         /* images (mode IMAGE) */
+    int32_t height, width; /* feature-map size, multiples of 8 (mode IMAGE) */
+    int32_t num_windows;   /* B_ = nW*B (mode WINDOWS) */
+    int32_t ld_in, ld_out; /* floats per token row of x and y */
+    int32_t shift;         /* 0 or 4: cyclic shift, torch.roll(-shift,-shift) (network_swinir.py:249-250) */
+    int32_t apply_ln;      /* 1: LayerNorm(x) first (network_swinir.py:245) */
+    int32_t add_residual;  /* 1: y = x + attn (network_swinir.py:276); 0: y = attn */
+    int32_t mask_mode;     /* SRK_MASK_SHIFT: closed form of calculate_mask (network_swinir.py:216-237) */
+    int32_t mask_nw;       /* SRK_MASK_EXPLICIT: mask is (mask_nw, 64, 64) fp32, window w uses mask[w % mask_nw] */
+} SrkSwinAttnDesc;
+
+int srk_swin_attn_fwd(const SrkSwinAttnDesc* desc, const float* x, float* y, const void* wstream /* SRK_ATTN_WSTREAM_BYTES */,
+                      const float* vec /* SRK_ATTN_VEC_FLOATS */, const float* mask /* or NULL */, void* stream);
+
+/* MLP half:  y = x + fc2(gelu_erf(fc1(LN2(x)))).  Replaces network_swinir.py:277 + Mlp.forward :24-30. */
+typedef struct SrkMlpDesc {
+    int64_t num_tokens;
+    int32_t ld_in, ld_out;
+    int32_t apply_ln;      /* 1: LayerNorm first */
+    int32_t add_residual;  /* 1: y = x + mlp(LN(x)); 0: y = mlp(LN(x)) */
+} SrkMlpDesc;
+
+int srk_swin_mlp_fwd(const SrkMlpDesc* desc, const float* x, float* y, const void* wstream /* SRK_MLP_WSTREAM_BYTES */,
+                     const float* vec /* SRK_MLP_VEC_FLOATS */, void* stream);
+
+/* Row LayerNorm over the 180 channels of token rows (patch_embed.norm / final norm,
+ * network_swinir.py:526-527, :800). */
+int srk_layernorm_fwd(const float* x, float* y, const float* w, const float* b, int64_t num_tokens, int32_t ld_in,
+                      int32_t ld_out, void* stream);
+
+/* PixelShuffle(r) on channels-last activations, optional fused LeakyReLU:
+ * out[b, h*r+i, w*r+j, c] = in[b, h, w, c*r*r + i*r + j].  Replaces nn.PixelShuffle in Upsample
+ * (network_swinir.py:580-588). */
+int srk_pixelshuffle_nhwc_fwd(const float* x, float* y, int32_t batch, int32_t height, int32_t width,
+                              int32_t out_channels, int32_t r, void* stream);
+
+/* Weighted tile accumulation for the overlapping-tile stitcher (BASELINE.json configs[4]):
+ * E[:, y0:y0+th, x0:x0+tw] += tile, Wt[y0:.., x0:..] += 1  (tiles of one launch must not overlap). */
+int srk_stitch_accumulate(const float* tiles, float* E, float* Wt, const int32_t* tile_yx, int32_t num_tiles,
+                          int32_t channels, int32_t tile_h, int32_t tile_w, int32_t out_h, int32_t out_w, void* stream);
+int srk_stitch_normalize(float* E, const float* Wt, int32_t channels, int64_t pixels, void* stream);
+
+int srk_abi_version(void);
+const char* srk_last_error_string(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t srk_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRK_H_ */

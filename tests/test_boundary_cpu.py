@@ -1,0 +1,151 @@
+"""CPU-side checks of the drop-in boundary: state_dict contract, weight packing, C-ABI exports."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import tpu_superresolution_b200 as srk
+from tpu_superresolution_b200 import _lib as L
+from tpu_superresolution_b200 import packing
+from oracle import synth
+from oracle import swinir_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.mark.parametrize("name", ["swinir_x2", "swinir_x4"])
+def test_state_dict_keys_match_reference_manifest(name):
+    """Same keys / shapes / dtypes as the reference's state_dict (finetune_swinir.py:283-285 strict=True)."""
+    with open(os.path.join(GOLDEN, f"{name}_manifest.json")) as f:
+        man = json.load(f)
+    model = srk.SwinIR(**synth.CONFIGS[name].as_kwargs())
+    sd = model.state_dict()
+    assert [m[0] for m in man] == list(sd.keys())
+    for k, shape, dtype in man:
+        assert list(sd[k].shape) == shape and str(sd[k].dtype).replace("torch.", "") == dtype, k
+
+
+def test_strict_load_roundtrip_and_buffers():
+    cfg = synth.CONFIGS["swinir_x2_d2"]
+    sd = synth.make_swinir_state_dict(cfg, seed=5, kind="stress")
+    model = srk.SwinIR(**cfg.as_kwargs())
+    model.load_state_dict(sd, strict=True)
+    out = model.state_dict()
+    for k, v in sd.items():
+        assert torch.equal(out[k], v), k
+    g = np.load(os.path.join(GOLDEN, "kat_buffers.npz"))
+    blk = srk.SwinTransformerBlock(180, (64, 64), 6, window_size=8, shift_size=4, mlp_ratio=2.0)
+    assert np.array_equal(blk.attn.relative_position_index.numpy(), g["rpi"])
+    assert np.array_equal(blk.attn_mask.numpy().astype(np.int8), g["mask_64"])
+    assert np.array_equal(blk.calculate_mask((48, 40)).numpy().astype(np.int8), g["mask_48x40"])
+    assert srk.SwinTransformerBlock(180, (64, 64), 6, window_size=8, shift_size=0).attn_mask is None
+
+
+def test_swizzle_is_an_involution_and_matches_device_formula():
+    m = torch.arange(128 * 64, dtype=torch.float32).reshape(128, 64)
+    s = packing.swizzle_slab(m)
+    assert torch.equal(packing.unswizzle_slab(s), m)
+    # device side: 16-byte chunk c of row r lives at byte r*128 + ((c ^ (r & 7)) << 4)   (csrc/umma.cuh sw128_off)
+    flat = s.reshape(-1)
+    for r, c in [(0, 0), (1, 0), (5, 3), (77, 7), (127, 2)]:
+        off_elems = (r * 128 + ((c ^ (r & 7)) << 4)) // 2          # bf16 elements
+        assert torch.equal(flat[off_elems:off_elems + 8], m[r, 8 * c:8 * c + 8])
+
+
+def _unpack_slabs(stream_u8, specs):
+    """specs: list of row counts; returns list of (rows, 64) float tensors (un-swizzled)."""
+    bf = stream_u8.view(torch.bfloat16)
+    out, off = [], 0
+    for rows in specs:
+        out.append(packing.unswizzle_slab(bf[off:off + rows * 64].reshape(rows, 64)).float())
+        off += rows * 64
+    assert off == bf.numel()
+    return out
+
+
+def test_pack_attention_reconstructs_reference_math():
+    """Emulate the kernel's dataflow on the CPU from the packed stream alone and compare with the oracle."""
+    cfg = synth.CONFIGS["swinir_x2_d2"]
+    sd = synth.make_swinir_state_dict(cfg, seed=99, kind="stress")
+    pre = "layers.0.residual_group.blocks.1.attn."
+    w, vec = packing.pack_attention(sd[pre + "qkv.weight"], sd[pre + "qkv.bias"], sd[pre + "proj.weight"], sd[pre + "proj.bias"],
+                                    sd[pre + "relative_position_bias_table"])
+    assert w.numel() == L.ATTN_WSTREAM_BYTES and vec.numel() == L.ATTN_VEC_FLOATS
+    slabs = _unpack_slabs(w, [128] * 15 + [192] * 3)
+    wv = torch.cat([torch.cat(slabs[0:3], 1), torch.cat(slabs[3:6], 1)], 0)           # (256, 192)
+    wqk = [torch.cat(slabs[6 + 3 * p:9 + 3 * p], 1) for p in range(3)]                  # 3 x (128, 192)
+    wp = torch.cat(slabs[15:18], 1)                                                      # (192, 192)
+    xw = synth.make_tokens(4, 8, 8, 180, seed=5)
+    xb = torch.zeros(4, 64, 192)
+    xb[..., :180] = xw.bfloat16().float()
+    v = xb @ wv.T + vec[L.AV_BIAS_V:L.AV_BIAS_V + 256]                                   # (4, 64, 256) padded head layout
+    o = torch.zeros(4, 64, 192)
+    rpb = vec[L.AV_RPB:].view(6, L.AV_RPB_STRIDE)
+    idx = O.relative_position_index(8)
+    for h in range(6):
+        p, j = divmod(h, 2)
+        qk = xb @ wqk[p].T + vec[L.AV_BIAS_QK + 128 * p:L.AV_BIAS_QK + 128 * p + 128]
+        q, k = qk[..., 32 * j:32 * j + 32], qk[..., 64 + 32 * j:64 + 32 * j + 32]
+        s = q @ k.transpose(-1, -2) + rpb[h][idx]                                        # log2 domain
+        pm = torch.exp2(s - s.max(-1, keepdim=True).values)
+        o[..., 32 * h:32 * h + 32] = (pm / pm.sum(-1, keepdim=True)) @ v[..., 32 * h:32 * h + 32]
+    y = o @ wp.T + vec[L.AV_BIAS_PROJ:L.AV_BIAS_PROJ + 192]
+    ref = O.window_attention(xw, sd, pre, 6, 8, None)
+    assert (y[..., 180:].abs().max() == 0) and (v[..., 30:32].abs().max() == 0)
+    err = (y[..., :180] - ref).abs().max().item()
+    assert err < 3e-2 * ref.abs().max().item(), err       # bf16 weights/inputs only
+
+
+def test_pack_mlp_reconstructs_reference_math():
+    cfg = synth.CONFIGS["swinir_x2_d2"]
+    sd = synth.make_swinir_state_dict(cfg, seed=99, kind="stress")
+    pre = "layers.0.residual_group.blocks.0.mlp."
+    w, vec = packing.pack_mlp(sd[pre + "fc1.weight"], sd[pre + "fc1.bias"], sd[pre + "fc2.weight"], sd[pre + "fc2.bias"])
+    slabs = _unpack_slabs(w, [192] * 12)
+    w1 = torch.cat([torch.cat(slabs[0:3], 1), torch.cat(slabs[3:6], 1)], 0)             # (384, 192)
+    w2 = torch.cat(slabs[6:12], 1)                                                       # (192, 384)
+    x = synth.make_tokens(1, 8, 8, 180, seed=7)[0]
+    xb = torch.zeros(64, 192)
+    xb[:, :180] = x
+    y = O.gelu(xb @ w1.T + vec[L.MV_B1:L.MV_B1 + 384]) @ w2.T + vec[L.MV_B2:L.MV_B2 + 192]
+    ref = O.mlp(x, sd, pre)
+    assert (y[:, :180] - ref).abs().max() < 2e-2 * ref.abs().max()
+    with pytest.raises(RuntimeError):
+        packing.pack_mlp(torch.zeros(720, 180), None, torch.zeros(180, 720), None)
+
+
+def test_header_constants_match_python_mirror():
+    hdr = open(os.path.join(ROOT, "include", "srk.h")).read()
+    defs = dict(re.findall(r"#define\s+(SRK_\w+)\s+\(?([0-9+* ]+)\)?\s", hdr))
+    ev = lambda k: eval(defs[k])
+    assert ev("SRK_ATTN_WSTREAM_BYTES") == L.ATTN_WSTREAM_BYTES and ev("SRK_MLP_WSTREAM_BYTES") == L.MLP_WSTREAM_BYTES
+    assert ev("SRK_ATTN_VEC_FLOATS") == L.ATTN_VEC_FLOATS and ev("SRK_MLP_VEC_FLOATS") == L.MLP_VEC_FLOATS
+    for k, v in [("SRK_AV_BIAS_V", L.AV_BIAS_V), ("SRK_AV_BIAS_QK", L.AV_BIAS_QK), ("SRK_AV_BIAS_PROJ", L.AV_BIAS_PROJ),
+                 ("SRK_AV_RPB", L.AV_RPB), ("SRK_AV_RPB_STRIDE", L.AV_RPB_STRIDE), ("SRK_MV_B1", L.MV_B1), ("SRK_MV_B2", L.MV_B2),
+                 ("SRK_ABI_VERSION", L.ABI_VERSION)]:
+        assert ev(k) == v, k
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    """The C-ABI library must exist in-tree and export everything include/srk.h declares (no compute here)."""
+    assert os.path.isfile(L.LIB_PATH), "build with __graft_entry__.build()"
+    lib = ctypes.CDLL(L.LIB_PATH)
+    hdr = open(os.path.join(ROOT, "include", "srk.h")).read()
+    declared = set(re.findall(r"\b(srk_\w+)\s*\(", hdr))
+    assert declared == set(L.EXPORTS)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert L.load().srk_abi_version() == L.ABI_VERSION
+
+
+def test_no_cpu_fallback():
+    blk = srk.SwinTransformerBlock(180, (16, 16), 6, window_size=8, shift_size=0, mlp_ratio=2.0).eval()
+    with torch.no_grad(), pytest.raises(RuntimeError):
+        blk(torch.zeros(1, 256, 180), (16, 16))
+    with torch.no_grad(), pytest.raises(RuntimeError):
+        srk.WindowAttention(96, (7, 7), 3)._packed()

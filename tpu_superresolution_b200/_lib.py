@@ -1,0 +1,132 @@
+"""ctypes binding of libsrk.so (include/srk.h).  No fallback: a missing library is an error."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_int32, c_int64, c_void_p, c_char_p, POINTER, Structure
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsrk.so")
+
+# mirrors of the #defines in include/srk.h
+ABI_VERSION = 1
+DIM, DIM_PAD, HEADS, HEAD_DIM, HEAD_PAD, WINDOW, HIDDEN, HIDDEN_PAD = 180, 192, 6, 30, 32, 8, 360, 384
+ATTN_WSTREAM_BYTES = 15 * 16384 + 3 * 24576
+MLP_WSTREAM_BYTES = 12 * 24576
+AV_LN_W, AV_LN_B, AV_BIAS_V, AV_BIAS_QK, AV_BIAS_PROJ, AV_RPB, AV_RPB_STRIDE = 0, 192, 384, 640, 1024, 1216, 232
+ATTN_VEC_FLOATS = 1216 + 6 * 232
+MV_LN_W, MV_LN_B, MV_B1, MV_B2, MLP_VEC_FLOATS = 0, 192, 384, 768, 960
+MODE_IMAGE, MODE_WINDOWS = 0, 1
+MASK_NONE, MASK_SHIFT, MASK_EXPLICIT = 0, 1, 2
+
+
+class SwinAttnDesc(Structure):
+    _fields_ = [(n, c_int32) for n in ("mode", "batch", "height", "width", "num_windows", "ld_in", "ld_out", "shift",
+                                       "apply_ln", "add_residual", "mask_mode", "mask_nw")]
+
+
+class MlpDesc(Structure):
+    _fields_ = [("num_tokens", c_int64), ("ld_in", c_int32), ("ld_out", c_int32), ("apply_ln", c_int32),
+                ("add_residual", c_int32)]
+
+
+_lib = None
+
+
+def load():
+    """Load libsrk.so (built in-tree by __graft_entry__.build()); raise if it is missing or stale."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                           "There is no CPU / eager fallback for this path.")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.srk_abi_version.restype = c_int32
+    lib.srk_last_error_string.restype = c_char_p
+    lib.srk_launch_count.restype = c_int64
+    lib.srk_swin_attn_fwd.argtypes = [POINTER(SwinAttnDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.srk_swin_mlp_fwd.argtypes = [POINTER(MlpDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.srk_layernorm_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]
+    lib.srk_pixelshuffle_nhwc_fwd.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
+    lib.srk_stitch_accumulate.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                          c_int32, c_int32, c_void_p]
+    lib.srk_stitch_normalize.argtypes = [c_void_p, c_void_p, c_int32, c_int64, c_void_p]
+    for f in ("srk_swin_attn_fwd", "srk_swin_mlp_fwd", "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd",
+              "srk_stitch_accumulate", "srk_stitch_normalize"):
+        getattr(lib, f).restype = c_int32
+    if lib.srk_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"libsrk.so ABI {lib.srk_abi_version()} != expected {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+EXPORTS = ("srk_abi_version", "srk_last_error_string", "srk_launch_count", "srk_swin_attn_fwd", "srk_swin_mlp_fwd",
+           "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd", "srk_stitch_accumulate", "srk_stitch_normalize")
+
+
+def _check(rc: int, lib) -> None:
+    if rc != 0:
+        raise RuntimeError("libsrk: " + lib.srk_last_error_string().decode())
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda_f32(*tensors) -> None:
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("tpu_superresolution_b200 kernels need CUDA tensors (no CPU fallback)")
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"expected float32 activations, got {t.dtype}")
+
+
+def launch_count() -> int:
+    return int(load().srk_launch_count())
+
+
+def swin_attn(x, y, wstream, vec, *, mode, batch=0, height=0, width=0, num_windows=0, ld_in, ld_out, shift=0,
+              apply_ln=True, add_residual=True, mask_mode=MASK_NONE, mask=None) -> None:
+    lib = load()
+    _require_cuda_f32(x, y, vec, mask)
+    d = SwinAttnDesc(mode, batch, height, width, num_windows, ld_in, ld_out, shift, int(apply_ln), int(add_residual),
+                     mask_mode, 0 if mask is None else mask.shape[0])
+    _check(lib.srk_swin_attn_fwd(ctypes.byref(d), x.data_ptr(), y.data_ptr(), wstream.data_ptr(), vec.data_ptr(),
+                                 0 if mask is None else mask.data_ptr(), _stream()), lib)
+
+
+def swin_mlp(x, y, wstream, vec, *, num_tokens, ld_in, ld_out, apply_ln=True, add_residual=True) -> None:
+    lib = load()
+    _require_cuda_f32(x, y, vec)
+    d = MlpDesc(num_tokens, ld_in, ld_out, int(apply_ln), int(add_residual))
+    _check(lib.srk_swin_mlp_fwd(ctypes.byref(d), x.data_ptr(), y.data_ptr(), wstream.data_ptr(), vec.data_ptr(), _stream()), lib)
+
+
+def layernorm(x, y, w, b, *, num_tokens, ld_in, ld_out) -> None:
+    lib = load()
+    _require_cuda_f32(x, y, w, b)
+    _check(lib.srk_layernorm_fwd(x.data_ptr(), y.data_ptr(), w.data_ptr(), b.data_ptr(), num_tokens, ld_in, ld_out, _stream()), lib)
+
+
+def pixelshuffle_nhwc(x, y, *, batch, height, width, out_channels, r) -> None:
+    lib = load()
+    _require_cuda_f32(x, y)
+    _check(lib.srk_pixelshuffle_nhwc_fwd(x.data_ptr(), y.data_ptr(), batch, height, width, out_channels, r, _stream()), lib)
+
+
+def stitch_accumulate(tiles, E, Wt, tile_yx, *, channels, tile_h, tile_w, out_h, out_w) -> None:
+    lib = load()
+    _require_cuda_f32(tiles, E, Wt)
+    _check(lib.srk_stitch_accumulate(tiles.data_ptr(), E.data_ptr(), Wt.data_ptr(), tile_yx.data_ptr(), tile_yx.shape[0],
+                                     channels, tile_h, tile_w, out_h, out_w, _stream()), lib)
+
+
+def stitch_normalize(E, Wt, *, channels, pixels) -> None:
+    lib = load()
+    _require_cuda_f32(E, Wt)
+    _check(lib.srk_stitch_normalize(E.data_ptr(), Wt.data_ptr(), channels, pixels, _stream()), lib)

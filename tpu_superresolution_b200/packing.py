@@ -1,0 +1,137 @@
+"""Weight repack: reference state_dict tensors -> the bf16 slab streams and fp32 vectors the kernels read.
+
+A "slab" is one k-atom of a UMMA B (or A) operand: R rows x 64 K-elements of bf16 = R x 128 bytes, stored
+with the 128-byte swizzle (16-byte chunk c of row r at chunk position c ^ (r & 7)), so that one 1-D bulk
+TMA copy drops it into shared memory ready for tcgen05.mma (csrc/umma.cuh).  Slabs are concatenated in
+the exact order the kernel's producer warp streams them (csrc/swin_kernels.cu).
+
+Folded at pack time: q scale (head_dim**-0.5, network_swinir.py:86,124) and log2(e) for the
+exp2-domain softmax into Wq/bq; log2(e) into the relative-position-bias table; head_dim 30 -> 32 and
+C 180 -> 192 zero padding; W_proj columns re-indexed to the padded head layout.
+"""
+from __future__ import annotations
+
+import math
+from typing import Tuple
+
+import torch
+
+from . import _lib as L
+
+LOG2E = 1.4426950408889634
+
+
+def swizzle_slab(mat: torch.Tensor) -> torch.Tensor:
+    """(R, 64) -> (R, 64) with the 8-element (16-byte) chunks of each row permuted by c ^ (r & 7)."""
+    R = mat.shape[0]
+    assert mat.shape[1] == 64 and R % 8 == 0
+    chunks = mat.reshape(R, 8, 8)
+    r = torch.arange(R, device=mat.device)[:, None]
+    c = torch.arange(8, device=mat.device)[None, :]
+    out = torch.empty_like(chunks)
+    out[r.expand(R, 8), c ^ (r & 7)] = chunks
+    return out.reshape(R, 64)
+
+
+def unswizzle_slab(slab: torch.Tensor) -> torch.Tensor:
+    """Inverse of swizzle_slab (the permutation is an involution per row)."""
+    return swizzle_slab(slab)
+
+
+def _slabs(mat: torch.Tensor) -> list:
+    """(R, K) with K % 64 == 0 -> list of K/64 swizzled bf16 slabs in k order."""
+    mat = mat.to(torch.bfloat16)
+    return [swizzle_slab(mat[:, k:k + 64].contiguous()) for k in range(0, mat.shape[1], 64)]
+
+
+def _pad_heads(w: torch.Tensor) -> torch.Tensor:
+    """(180, ...) rows in head layout h*30+d -> (192, ...) rows in padded layout h*32+d."""
+    out = w.new_zeros((L.HEADS * L.HEAD_PAD,) + tuple(w.shape[1:]))
+    out.view(L.HEADS, L.HEAD_PAD, *w.shape[1:])[:, :L.HEAD_DIM] = w.view(L.HEADS, L.HEAD_DIM, *w.shape[1:])
+    return out
+
+
+def _pad_cols(w: torch.Tensor, cols: int) -> torch.Tensor:
+    out = w.new_zeros(w.shape[0], cols)
+    out[:, :w.shape[1]] = w
+    return out
+
+
+@torch.no_grad()
+def pack_attention(qkv_w, qkv_b, proj_w, proj_b, rpb_table, ln_w=None, ln_b=None, scale=None
+                   ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """-> (wstream uint8[ATTN_WSTREAM_BYTES], vec float32[ATTN_VEC_FLOATS]) on qkv_w's device.
+
+    qkv_w (540,180), qkv_b (540) or None, proj_w (180,180), proj_b (180), rpb_table (225, 6);
+    ln_w/ln_b (180) or None for the identity (WindowAttention used stand-alone).
+    """
+    dev = qkv_w.device
+    C = L.DIM
+    if tuple(qkv_w.shape) != (3 * C, C) or tuple(proj_w.shape) != (C, C) or tuple(rpb_table.shape) != (225, L.HEADS):
+        raise RuntimeError(f"unsupported attention geometry qkv {tuple(qkv_w.shape)} proj {tuple(proj_w.shape)} "
+                           f"rpb {tuple(rpb_table.shape)}: kernels serve dim 180 / 6 heads / window 8 only")
+    scale = (L.HEAD_DIM ** -0.5) if scale is None else float(scale)
+    qkv_w = qkv_w.detach().float()
+    qkv_b = torch.zeros(3 * C, device=dev) if qkv_b is None else qkv_b.detach().float()
+    wq = _pad_cols(_pad_heads(qkv_w[:C] * (scale * LOG2E)), L.DIM_PAD)          # (192, 192)
+    wk = _pad_cols(_pad_heads(qkv_w[C:2 * C]), L.DIM_PAD)
+    wv = _pad_cols(_pad_heads(qkv_w[2 * C:]), L.DIM_PAD)
+    bq, bk, bv = _pad_heads(qkv_b[:C] * (scale * LOG2E)), _pad_heads(qkv_b[C:2 * C]), _pad_heads(qkv_b[2 * C:])
+
+    slabs = []
+    wv256 = wv.new_zeros(256, L.DIM_PAD)
+    wv256[:192] = wv
+    for m in range(2):                                   # V^T pass: A operand = 128 v-dims per half
+        slabs += _slabs(wv256[128 * m:128 * (m + 1)])
+    for p in range(3):                                   # head pair p: [q(2p) q(2p+1) k(2p) k(2p+1)] rows
+        rows = torch.cat([wq[64 * p:64 * p + 64], wk[64 * p:64 * p + 64]], 0)
+        slabs += _slabs(rows)
+    # proj: K index is the padded head layout of O
+    wp = proj_w.detach().float().view(C, L.HEADS, L.HEAD_DIM)
+    wp_pad = wp.new_zeros(L.DIM_PAD, L.HEADS, L.HEAD_PAD)
+    wp_pad[:C, :, :L.HEAD_DIM] = wp
+    slabs += _slabs(wp_pad.reshape(L.DIM_PAD, L.DIM_PAD))
+    wstream = torch.cat([s.reshape(-1) for s in slabs]).contiguous().view(torch.uint8)
+    assert wstream.numel() == L.ATTN_WSTREAM_BYTES
+
+    vec = torch.zeros(L.ATTN_VEC_FLOATS, device=dev, dtype=torch.float32)
+    vec[L.AV_LN_W:L.AV_LN_W + C] = 1.0 if ln_w is None else ln_w.detach().float()
+    if ln_b is not None:
+        vec[L.AV_LN_B:L.AV_LN_B + C] = ln_b.detach().float()
+    vec[L.AV_BIAS_V:L.AV_BIAS_V + 192] = bv
+    for p in range(3):
+        vec[L.AV_BIAS_QK + 128 * p:L.AV_BIAS_QK + 128 * p + 64] = bq[64 * p:64 * p + 64]
+        vec[L.AV_BIAS_QK + 128 * p + 64:L.AV_BIAS_QK + 128 * p + 128] = bk[64 * p:64 * p + 64]
+    vec[L.AV_BIAS_PROJ:L.AV_BIAS_PROJ + C] = proj_b.detach().float()
+    rpb = vec[L.AV_RPB:L.AV_RPB + L.HEADS * L.AV_RPB_STRIDE].view(L.HEADS, L.AV_RPB_STRIDE)
+    rpb[:, :225] = rpb_table.detach().float().t() * LOG2E
+    return wstream, vec
+
+
+@torch.no_grad()
+def pack_mlp(fc1_w, fc1_b, fc2_w, fc2_b, ln_w=None, ln_b=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """fc1 (360,180), fc2 (180,360) -> (wstream uint8[MLP_WSTREAM_BYTES], vec float32[MLP_VEC_FLOATS])."""
+    dev = fc1_w.device
+    C, Hd = L.DIM, L.HIDDEN
+    if tuple(fc1_w.shape) != (Hd, C) or tuple(fc2_w.shape) != (C, Hd):
+        raise RuntimeError(f"unsupported MLP geometry fc1 {tuple(fc1_w.shape)} fc2 {tuple(fc2_w.shape)}: "
+                           "kernels serve dim 180 / mlp_ratio 2 only")
+    w1 = fc1_w.new_zeros(L.HIDDEN_PAD, L.DIM_PAD, dtype=torch.float32)
+    w1[:Hd, :C] = fc1_w.detach().float()
+    w2 = fc2_w.new_zeros(L.DIM_PAD, L.HIDDEN_PAD, dtype=torch.float32)
+    w2[:C, :Hd] = fc2_w.detach().float()
+    slabs = []
+    for nh in range(2):
+        slabs += _slabs(w1[192 * nh:192 * (nh + 1)])
+    slabs += _slabs(w2)
+    wstream = torch.cat([s.reshape(-1) for s in slabs]).contiguous().view(torch.uint8)
+    assert wstream.numel() == L.MLP_WSTREAM_BYTES
+    vec = torch.zeros(L.MLP_VEC_FLOATS, device=dev, dtype=torch.float32)
+    vec[L.MV_LN_W:L.MV_LN_W + C] = 1.0 if ln_w is None else ln_w.detach().float()
+    if ln_b is not None:
+        vec[L.MV_LN_B:L.MV_LN_B + C] = ln_b.detach().float()
+    if fc1_b is not None:
+        vec[L.MV_B1:L.MV_B1 + Hd] = fc1_b.detach().float()
+    if fc2_b is not None:
+        vec[L.MV_B2:L.MV_B2 + C] = fc2_b.detach().float()
+    return wstream, vec

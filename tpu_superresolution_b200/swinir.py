@@ -1,0 +1,483 @@
+"""Drop-in SwinIR modules backed by the sm_100a kernels in libsrk.so.
+
+Same constructor arguments, forward signatures and state_dict keys as the reference's
+``modules/network_swinir.py``, so a reference checkpoint loads with
+``strict=True`` (finetune_swinir.py:283-285) and the classes can be swapped into the reference
+containers.  Inference only: Dropout / DropPath are the identity in eval mode
+(network_swinir.py:22, :204), autograd is not supported, and there is no CPU or eager fallback --
+a CPU tensor, a missing libsrk.so or an unsupported geometry raises.
+
+What runs where
+  * attention half of a block (LN1, shift, partition, qkv, softmax(qk^T+bias+mask)v, proj, residual,
+    reverse/un-shift)                       -> srk_swin_attn_fwd   (one kernel, csrc/swin_kernels.cu)
+  * MLP half (LN2, fc1, GELU, fc2, residual) -> srk_swin_mlp_fwd    (one kernel)
+  * patch_embed.norm / final norm            -> srk_layernorm_fwd
+  * PixelShuffle                             -> srk_pixelshuffle_nhwc_fwd
+  * 3x3 convolutions                         -> cuDNN through torch, channels-last (library call; the
+    tcgen05 implicit-GEMM replacement is SURVEY.md §8f rank 1)
+The residual stream is the reference's own (B, H*W, 180) fp32 tensor; kernels gather/scatter window
+tokens with index math, so no roll / partition / reverse copies exist.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib as L
+from . import packing
+
+
+def _to_2tuple(v):
+    return tuple(v) if isinstance(v, (tuple, list)) else (v, v)
+
+
+def _inference_only(mod: nn.Module) -> None:
+    if torch.is_grad_enabled() and any(p.requires_grad for p in mod.parameters(recurse=False)):
+        # the kernels have no backward; refuse silently-wrong training instead of detaching
+        raise RuntimeError(f"{type(mod).__name__}: fused kernels are inference-only; call under torch.no_grad()")
+
+
+class _PackedCache:
+    """Packed weight images keyed on (data_ptr, _version, device) of the source parameters."""
+
+    def __init__(self):
+        self.key = None
+        self.value = None
+
+    def get(self, params, build):
+        key = tuple((p.data_ptr(), p._version, str(p.device)) for p in params if p is not None)
+        if key != self.key:
+            self.value = build()
+            self.key = key
+        return self.value
+
+
+class Mlp(nn.Module):
+    """network_swinir.py:14-30.  forward(x: (..., 180)) -> fc2(gelu(fc1(x)))."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        if act_layer is not nn.GELU:
+            raise RuntimeError("Mlp: only the exact-erf nn.GELU activation is implemented")
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = act_layer()
+        self.fc2 = nn.Linear(hidden_features, out_features)
+        self.drop = nn.Dropout(drop)
+        self._cache = _PackedCache()
+
+    def _packed(self, norm: Optional[nn.LayerNorm] = None):
+        ps = [self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias] + \
+             ([norm.weight, norm.bias] if norm is not None else [])
+        return self._cache.get(ps, lambda: packing.pack_mlp(
+            self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias,
+            None if norm is None else norm.weight, None if norm is None else norm.bias))
+
+    def forward(self, x):
+        _inference_only(self)
+        shape = x.shape
+        x2 = x.reshape(-1, shape[-1]).contiguous()
+        y = torch.empty_like(x2)
+        w, v = self._packed()
+        L.swin_mlp(x2, y, w, v, num_tokens=x2.shape[0], ld_in=x2.shape[1], ld_out=x2.shape[1], apply_ln=False,
+                   add_residual=False)
+        return y.reshape(shape)
+
+
+class WindowAttention(nn.Module):
+    """network_swinir.py:65-161.  forward(x: (nW*B, 64, 180), mask: (nW, 64, 64) | None)."""
+
+    def __init__(self, dim, window_size, num_heads, qkv_bias=True, qk_scale=None, attn_drop=0., proj_drop=0.):
+        super().__init__()
+        self.dim, self.window_size, self.num_heads = dim, tuple(window_size), num_heads
+        head_dim = dim // num_heads
+        self.scale = qk_scale or head_dim ** -0.5
+        wh, ww = self.window_size
+        self.relative_position_bias_table = nn.Parameter(torch.zeros((2 * wh - 1) * (2 * ww - 1), num_heads))
+        # closed form of network_swinir.py:93-102: (yi-yj+wh-1)*(2ww-1) + (xi-xj+ww-1)
+        t = torch.arange(wh * ww)
+        ty, tx = t // ww, t % ww
+        idx = (ty[:, None] - ty[None, :] + wh - 1) * (2 * ww - 1) + (tx[:, None] - tx[None, :] + ww - 1)
+        self.register_buffer("relative_position_index", idx)
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop)
+        nn.init.trunc_normal_(self.relative_position_bias_table, std=.02)
+        self.softmax = nn.Softmax(dim=-1)
+        self._cache = _PackedCache()
+
+    def _packed(self, norm: Optional[nn.LayerNorm] = None):
+        if self.window_size != (L.WINDOW, L.WINDOW) or self.num_heads != L.HEADS or self.dim != L.DIM:
+            raise RuntimeError(f"WindowAttention(dim={self.dim}, window={self.window_size}, heads={self.num_heads}): "
+                               "kernels serve dim 180 / window 8 / 6 heads only")
+        ps = [self.qkv.weight, self.qkv.bias, self.proj.weight, self.proj.bias, self.relative_position_bias_table] + \
+             ([norm.weight, norm.bias] if norm is not None else [])
+        return self._cache.get(ps, lambda: packing.pack_attention(
+            self.qkv.weight, self.qkv.bias, self.proj.weight, self.proj.bias, self.relative_position_bias_table,
+            None if norm is None else norm.weight, None if norm is None else norm.bias, self.scale))
+
+    def forward(self, x, mask=None):
+        _inference_only(self)
+        B_, N, C = x.shape
+        if N != L.WINDOW * L.WINDOW:
+            raise RuntimeError(f"WindowAttention: expected {L.WINDOW * L.WINDOW} tokens per window, got {N}")
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        w, v = self._packed()
+        if mask is not None:
+            if B_ % mask.shape[0] != 0:
+                raise RuntimeError("WindowAttention: B_ must be a multiple of mask.shape[0]")
+            mask = mask.to(device=x.device, dtype=torch.float32).contiguous()
+        L.swin_attn(x, y, w, v, mode=L.MODE_WINDOWS, num_windows=B_, ld_in=C, ld_out=C, apply_ln=False,
+                    add_residual=False, mask_mode=L.MASK_NONE if mask is None else L.MASK_EXPLICIT, mask=mask)
+        return y
+
+    def extra_repr(self) -> str:
+        return f'dim={self.dim}, window_size={self.window_size}, num_heads={self.num_heads}'
+
+
+def calculate_mask(x_size, window_size: int, shift_size: int) -> torch.Tensor:
+    """(nW, N, N) 0 / -100 mask of SW-MSA (network_swinir.py:216-237), closed form.
+
+    Only used to populate the ``attn_mask`` state_dict buffer; the kernel evaluates the same region ids
+    in registers and never reads this tensor.
+    """
+    H, W = x_size
+    ws, s = window_size, shift_size
+
+    def region(p, Ln):
+        return (p >= Ln - ws).long() + (p >= Ln - s).long()
+
+    ids = 3 * region(torch.arange(H), H)[:, None] + region(torch.arange(W), W)[None, :]
+    ids = ids.view(H // ws, ws, W // ws, ws).permute(0, 2, 1, 3).reshape(-1, ws * ws)
+    diff = ids[:, None, :] != ids[:, :, None]
+    return torch.zeros(diff.shape).masked_fill(diff, -100.0)
+
+
+class SwinTransformerBlock(nn.Module):
+    """network_swinir.py:164-297.  forward(x: (B, H*W, 180), x_size=(H, W)) -> (B, H*W, 180)."""
+
+    def __init__(self, dim, input_resolution, num_heads, window_size=7, shift_size=0, mlp_ratio=4., qkv_bias=True,
+                 qk_scale=None, drop=0., attn_drop=0., drop_path=0., act_layer=nn.GELU, norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.dim, self.input_resolution, self.num_heads = dim, input_resolution, num_heads
+        self.window_size, self.shift_size, self.mlp_ratio = window_size, shift_size, mlp_ratio
+        if min(self.input_resolution) <= self.window_size:      # :193-196
+            self.shift_size = 0
+            self.window_size = min(self.input_resolution)
+        assert 0 <= self.shift_size < self.window_size, "shift_size must in 0-window_size"
+        if norm_layer is not nn.LayerNorm:
+            raise RuntimeError("SwinTransformerBlock: only nn.LayerNorm is implemented")
+        self.norm1 = norm_layer(dim)
+        self.attn = WindowAttention(dim, window_size=_to_2tuple(self.window_size), num_heads=num_heads,
+                                    qkv_bias=qkv_bias, qk_scale=qk_scale, attn_drop=attn_drop, proj_drop=drop)
+        self.drop_path = nn.Identity()      # DropPath is the identity in eval mode (:204)
+        self.norm2 = norm_layer(dim)
+        self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
+        self.register_buffer("attn_mask", calculate_mask(self.input_resolution, self.window_size, self.shift_size)
+                             if self.shift_size > 0 else None)
+
+    def calculate_mask(self, x_size):
+        return calculate_mask(x_size, self.window_size, self.shift_size)
+
+    def forward_into(self, x: torch.Tensor, x_size: Tuple[int, int], out: torch.Tensor) -> torch.Tensor:
+        """out = block(x); ``out`` may be ``x`` itself (in place)."""
+        _inference_only(self)
+        H, W = x_size
+        B, Ltok, C = x.shape
+        if Ltok != H * W:
+            raise RuntimeError("input feature has wrong size")
+        if self.shift_size not in (0, L.WINDOW // 2):
+            raise RuntimeError(f"shift_size {self.shift_size} unsupported (0 or {L.WINDOW // 2})")
+        if H % L.WINDOW or W % L.WINDOW:
+            raise RuntimeError(f"x_size {x_size} must be a multiple of the window size {L.WINDOW}")
+        aw, av = self.attn._packed(self.norm1)
+        mw, mv = self.mlp._packed(self.norm2)
+        L.swin_attn(x, out, aw, av, mode=L.MODE_IMAGE, batch=B, height=H, width=W, ld_in=C, ld_out=C,
+                    shift=self.shift_size, apply_ln=True, add_residual=True,
+                    mask_mode=L.MASK_SHIFT if self.shift_size > 0 else L.MASK_NONE)
+        L.swin_mlp(out, out, mw, mv, num_tokens=B * Ltok, ld_in=C, ld_out=C, apply_ln=True, add_residual=True)
+        return out
+
+    def forward(self, x, x_size):
+        x = x.contiguous()
+        return self.forward_into(x, x_size, torch.empty_like(x))
+
+    def extra_repr(self) -> str:
+        return (f"dim={self.dim}, input_resolution={self.input_resolution}, num_heads={self.num_heads}, "
+                f"window_size={self.window_size}, shift_size={self.shift_size}, mlp_ratio={self.mlp_ratio}")
+
+
+class BasicLayer(nn.Module):
+    """network_swinir.py:349-416: `depth` blocks alternating shift 0 / window_size // 2."""
+
+    def __init__(self, dim, input_resolution, depth, num_heads, window_size, mlp_ratio=4., qkv_bias=True, qk_scale=None,
+                 drop=0., attn_drop=0., drop_path=0., norm_layer=nn.LayerNorm, downsample=None, use_checkpoint=False):
+        super().__init__()
+        self.dim, self.input_resolution, self.depth, self.use_checkpoint = dim, input_resolution, depth, use_checkpoint
+        self.blocks = nn.ModuleList([
+            SwinTransformerBlock(dim=dim, input_resolution=input_resolution, num_heads=num_heads, window_size=window_size,
+                                 shift_size=0 if (i % 2 == 0) else window_size // 2, mlp_ratio=mlp_ratio,
+                                 qkv_bias=qkv_bias, qk_scale=qk_scale, drop=drop, attn_drop=attn_drop,
+                                 drop_path=drop_path[i] if isinstance(drop_path, list) else drop_path,
+                                 norm_layer=norm_layer)
+            for i in range(depth)])
+        if downsample is not None:
+            raise RuntimeError("BasicLayer: downsample (PatchMerging) is never used by SwinIR and is not implemented")
+        self.downsample = None
+
+    def forward(self, x, x_size):
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        src = x
+        for blk in self.blocks:          # first block out of place (x is the group's residual), the rest in place
+            blk.forward_into(src, x_size, out)
+            src = out
+        return out if len(self.blocks) else x
+
+    def extra_repr(self) -> str:
+        return f"dim={self.dim}, input_resolution={self.input_resolution}, depth={self.depth}"
+
+
+class PatchEmbed(nn.Module):
+    """network_swinir.py:495-535: (B,C,H,W) -> (B, H*W, C) (+ LayerNorm)."""
+
+    def __init__(self, img_size=224, patch_size=4, in_chans=3, embed_dim=96, norm_layer=None):
+        super().__init__()
+        self.img_size, self.patch_size = _to_2tuple(img_size), _to_2tuple(patch_size)
+        self.patches_resolution = [self.img_size[0] // self.patch_size[0], self.img_size[1] // self.patch_size[1]]
+        self.num_patches = self.patches_resolution[0] * self.patches_resolution[1]
+        self.in_chans, self.embed_dim = in_chans, embed_dim
+        self.norm = norm_layer(embed_dim) if norm_layer is not None else None
+
+    def forward(self, x):
+        B, C = x.shape[:2]
+        t = x.permute(0, 2, 3, 1).reshape(B, -1, C)       # a view when x is channels-last
+        if self.norm is None:
+            return t
+        t = t.contiguous()
+        y = torch.empty_like(t)
+        L.layernorm(t, y, self.norm.weight, self.norm.bias, num_tokens=t.shape[0] * t.shape[1], ld_in=C, ld_out=C)
+        return y
+
+
+class PatchUnEmbed(nn.Module):
+    """network_swinir.py:538-569: (B, H*W, C) -> (B,C,H,W) (a channels-last view, no copy)."""
+
+    def __init__(self, img_size=224, patch_size=4, in_chans=3, embed_dim=96, norm_layer=None):
+        super().__init__()
+        self.img_size, self.patch_size = _to_2tuple(img_size), _to_2tuple(patch_size)
+        self.patches_resolution = [self.img_size[0] // self.patch_size[0], self.img_size[1] // self.patch_size[1]]
+        self.num_patches = self.patches_resolution[0] * self.patches_resolution[1]
+        self.in_chans, self.embed_dim = in_chans, embed_dim
+
+    def forward(self, x, x_size):
+        B, HW, C = x.shape
+        return x.reshape(B, x_size[0], x_size[1], C).permute(0, 3, 1, 2)
+
+
+class RSTB(nn.Module):
+    """network_swinir.py:419-492: blocks -> 3x3 conv -> + input."""
+
+    def __init__(self, dim, input_resolution, depth, num_heads, window_size, mlp_ratio=4., qkv_bias=True, qk_scale=None,
+                 drop=0., attn_drop=0., drop_path=0., norm_layer=nn.LayerNorm, downsample=None, use_checkpoint=False,
+                 img_size=224, patch_size=4, resi_connection='1conv'):
+        super().__init__()
+        self.dim, self.input_resolution = dim, input_resolution
+        self.residual_group = BasicLayer(dim=dim, input_resolution=input_resolution, depth=depth, num_heads=num_heads,
+                                         window_size=window_size, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias,
+                                         qk_scale=qk_scale, drop=drop, attn_drop=attn_drop, drop_path=drop_path,
+                                         norm_layer=norm_layer, downsample=downsample, use_checkpoint=use_checkpoint)
+        if resi_connection == '1conv':
+            self.conv = nn.Conv2d(dim, dim, 3, 1, 1)
+        elif resi_connection == '3conv':
+            self.conv = nn.Sequential(nn.Conv2d(dim, dim // 4, 3, 1, 1), nn.LeakyReLU(negative_slope=0.2, inplace=True),
+                                      nn.Conv2d(dim // 4, dim // 4, 1, 1, 0), nn.LeakyReLU(negative_slope=0.2, inplace=True),
+                                      nn.Conv2d(dim // 4, dim, 3, 1, 1))
+        else:
+            raise ValueError(resi_connection)
+        self.patch_embed = PatchEmbed(img_size=img_size, patch_size=patch_size, in_chans=0, embed_dim=dim, norm_layer=None)
+        self.patch_unembed = PatchUnEmbed(img_size=img_size, patch_size=patch_size, in_chans=0, embed_dim=dim,
+                                          norm_layer=None)
+
+    def forward(self, x, x_size):
+        y = self.patch_unembed(self.residual_group(x, x_size), x_size)
+        return self.patch_embed(self.conv(y)) + x
+
+
+class PixelShuffle(nn.Module):
+    """nn.PixelShuffle drop-in; channels-last CUDA fp32 inputs go through srk_pixelshuffle_nhwc_fwd."""
+
+    def __init__(self, upscale_factor: int):
+        super().__init__()
+        self.upscale_factor = upscale_factor
+
+    def forward(self, x):
+        r = self.upscale_factor
+        B, C, H, W = x.shape
+        oc = C // (r * r)
+        xin = x.permute(0, 2, 3, 1)
+        if not xin.is_contiguous():
+            xin = xin.contiguous()
+        y = torch.empty((B, H * r, W * r, oc), device=x.device, dtype=x.dtype)
+        L.pixelshuffle_nhwc(xin, y, batch=B, height=H, width=W, out_channels=oc, r=r)
+        return y.permute(0, 3, 1, 2)          # logical NCHW, channels-last memory
+
+    def extra_repr(self) -> str:
+        return f"upscale_factor={self.upscale_factor}"
+
+
+class Upsample(nn.Sequential):
+    """network_swinir.py:572-591: [conv 3x3 nf -> 4nf, PixelShuffle(2)] * log2(scale), or one x3 stage."""
+
+    def __init__(self, scale, num_feat):
+        m = []
+        if (scale & (scale - 1)) == 0:
+            for _ in range(int(math.log(scale, 2))):
+                m += [nn.Conv2d(num_feat, 4 * num_feat, 3, 1, 1), PixelShuffle(2)]
+        elif scale == 3:
+            m += [nn.Conv2d(num_feat, 9 * num_feat, 3, 1, 1), PixelShuffle(3)]
+        else:
+            raise ValueError(f'scale {scale} is not supported. Supported scales: 2^n and 3.')
+        super().__init__(*m)
+
+
+class UpsampleOneStep(nn.Sequential):
+    """network_swinir.py:594-615 (lightweight SR tail)."""
+
+    def __init__(self, scale, num_feat, num_out_ch, input_resolution=None):
+        self.num_feat, self.input_resolution = num_feat, input_resolution
+        super().__init__(nn.Conv2d(num_feat, (scale ** 2) * num_out_ch, 3, 1, 1), PixelShuffle(scale))
+
+
+class SwinIR(nn.Module):
+    """network_swinir.py:618-851.  forward(x: (B, 3, H, W) in [0, img_range]) -> (B, 3, H*s, W*s)."""
+
+    def __init__(self, img_size=64, patch_size=1, in_chans=3, embed_dim=96, depths=[6, 6, 6, 6], num_heads=[6, 6, 6, 6],
+                 window_size=7, mlp_ratio=4., qkv_bias=True, qk_scale=None, drop_rate=0., attn_drop_rate=0.,
+                 drop_path_rate=0.1, norm_layer=nn.LayerNorm, ape=False, patch_norm=True, use_checkpoint=False, upscale=2,
+                 img_range=1., upsampler='', resi_connection='1conv', **kwargs):
+        super().__init__()
+        num_in_ch = num_out_ch = in_chans
+        num_feat = 64
+        self.img_range = img_range
+        self.mean = torch.Tensor((0.4488, 0.4371, 0.4040)).view(1, 3, 1, 1) if in_chans == 3 else torch.zeros(1, 1, 1, 1)
+        self.upscale, self.upsampler, self.window_size = upscale, upsampler, window_size
+        self.conv_first = nn.Conv2d(num_in_ch, embed_dim, 3, 1, 1)
+        self.num_layers, self.embed_dim, self.ape, self.patch_norm = len(depths), embed_dim, ape, patch_norm
+        self.num_features, self.mlp_ratio = embed_dim, mlp_ratio
+        self.patch_embed = PatchEmbed(img_size=img_size, patch_size=patch_size, in_chans=embed_dim, embed_dim=embed_dim,
+                                      norm_layer=norm_layer if patch_norm else None)
+        self.patches_resolution = self.patch_embed.patches_resolution
+        self.patch_unembed = PatchUnEmbed(img_size=img_size, patch_size=patch_size, in_chans=embed_dim,
+                                          embed_dim=embed_dim, norm_layer=norm_layer if patch_norm else None)
+        if ape:
+            self.absolute_pos_embed = nn.Parameter(torch.zeros(1, self.patch_embed.num_patches, embed_dim))
+            nn.init.trunc_normal_(self.absolute_pos_embed, std=.02)
+        self.pos_drop = nn.Dropout(p=drop_rate)
+        res = (self.patches_resolution[0], self.patches_resolution[1])
+        self.layers = nn.ModuleList([
+            RSTB(dim=embed_dim, input_resolution=res, depth=depths[i], num_heads=num_heads[i], window_size=window_size,
+                 mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, qk_scale=qk_scale, drop=drop_rate, attn_drop=attn_drop_rate,
+                 drop_path=0., norm_layer=norm_layer, downsample=None, use_checkpoint=use_checkpoint, img_size=img_size,
+                 patch_size=patch_size, resi_connection=resi_connection)
+            for i in range(self.num_layers)])
+        self.norm = norm_layer(self.num_features)
+        if resi_connection == '1conv':
+            self.conv_after_body = nn.Conv2d(embed_dim, embed_dim, 3, 1, 1)
+        elif resi_connection == '3conv':
+            self.conv_after_body = nn.Sequential(
+                nn.Conv2d(embed_dim, embed_dim // 4, 3, 1, 1), nn.LeakyReLU(negative_slope=0.2, inplace=True),
+                nn.Conv2d(embed_dim // 4, embed_dim // 4, 1, 1, 0), nn.LeakyReLU(negative_slope=0.2, inplace=True),
+                nn.Conv2d(embed_dim // 4, embed_dim, 3, 1, 1))
+        if upsampler == 'pixelshuffle':
+            self.conv_before_upsample = nn.Sequential(nn.Conv2d(embed_dim, num_feat, 3, 1, 1), nn.LeakyReLU(inplace=True))
+            self.upsample = Upsample(upscale, num_feat)
+            self.conv_last = nn.Conv2d(num_feat, num_out_ch, 3, 1, 1)
+        elif upsampler == 'pixelshuffledirect':
+            self.upsample = UpsampleOneStep(upscale, embed_dim, num_out_ch, res)
+        elif upsampler == 'nearest+conv':
+            self.conv_before_upsample = nn.Sequential(nn.Conv2d(embed_dim, num_feat, 3, 1, 1), nn.LeakyReLU(inplace=True))
+            self.conv_up1 = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
+            if upscale == 4:
+                self.conv_up2 = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
+            self.conv_hr = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
+            self.conv_last = nn.Conv2d(num_feat, num_out_ch, 3, 1, 1)
+            self.lrelu = nn.LeakyReLU(negative_slope=0.2, inplace=True)
+        else:
+            self.conv_last = nn.Conv2d(embed_dim, num_out_ch, 3, 1, 1)
+        self.apply(self._init_weights)
+        self._channels_last_done = None
+
+    def _init_weights(self, m):
+        if isinstance(m, nn.Linear):          # network_swinir.py:766-773
+            nn.init.trunc_normal_(m.weight, std=.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    def check_image_size(self, x):
+        _, _, h, w = x.size()
+        ph = (self.window_size - h % self.window_size) % self.window_size
+        pw = (self.window_size - w % self.window_size) % self.window_size
+        return F.pad(x, (0, pw, 0, ph), 'reflect') if (ph or pw) else x
+
+    def _prepare(self, device):
+        if self._channels_last_done != str(device):
+            for m in self.modules():
+                if isinstance(m, nn.Conv2d):
+                    m.weight.data = m.weight.data.contiguous(memory_format=torch.channels_last)
+            self._channels_last_done = str(device)
+
+    def forward_features(self, x):
+        x_size = (x.shape[2], x.shape[3])
+        x = self.patch_embed(x)
+        if self.ape:
+            x = x + self.absolute_pos_embed
+        for layer in self.layers:
+            x = layer(x, x_size)
+        x = x.contiguous()
+        B, Ltok, C = x.shape
+        L.layernorm(x, x, self.norm.weight, self.norm.bias, num_tokens=B * Ltok, ld_in=C, ld_out=C)   # :800, in place
+        return self.patch_unembed(x, x_size)
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("SwinIR: CUDA input required (no CPU fallback)")
+        _inference_only(self.conv_first)
+        self._prepare(x.device)
+        H, W = x.shape[2:]
+        x = self.check_image_size(x)
+        self.mean = self.mean.type_as(x)
+        x = ((x - self.mean) * self.img_range).contiguous(memory_format=torch.channels_last)
+        if self.upsampler == 'pixelshuffle':
+            x = self.conv_first(x)
+            x = self.conv_after_body(self.forward_features(x)) + x
+            x = self.conv_before_upsample(x)
+            x = self.conv_last(self.upsample(x))
+        elif self.upsampler == 'pixelshuffledirect':
+            x = self.conv_first(x)
+            x = self.conv_after_body(self.forward_features(x)) + x
+            x = self.upsample(x)
+        elif self.upsampler == 'nearest+conv':
+            x = self.conv_first(x)
+            x = self.conv_after_body(self.forward_features(x)) + x
+            x = self.conv_before_upsample(x)
+            x = self.lrelu(self.conv_up1(F.interpolate(x, scale_factor=2, mode='nearest')))
+            if self.upscale == 4:
+                x = self.lrelu(self.conv_up2(F.interpolate(x, scale_factor=2, mode='nearest')))
+            x = self.conv_last(self.lrelu(self.conv_hr(x)))
+        else:
+            x_first = self.conv_first(x)
+            res = self.conv_after_body(self.forward_features(x_first)) + x_first
+            x = x + self.conv_last(res)
+        x = x / self.img_range + self.mean
+        return x[:, :, :H * self.upscale, :W * self.upscale]
