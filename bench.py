@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""Benchmark of the fused window-attention SR path (BASELINE.json: "SwinIR/HAT x4 output Mpix/s").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch of synthetic input: BASELINE.json configs[1],
+SwinIR classical x4 on a batch of 16 LR tiles of 64x64 per GPU (16 x 3 x 256 x 256 = 1.049 output Mpix).
+With N > 1 (torchrun, one rank per GPU) every rank runs its own batch -- tiles are independent, there is
+no collective on the data path -- so scaling is "weak" and `value` is the sum over ranks divided by the
+slowest rank's time.  JSON keys follow the driver contract; see DESIGN.md "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+TILES_PER_STEP = 16
+TILE = 64
+SCALE = 4
+MODEL = "swinir_x4"
+# algorithmic FLOPs, 2/MAC, un-padded dims
+FLOP_PER_TOKEN_ATTN = 305_280          # qkv + qk^T + pv + proj per token (one swin_attn_kernel launch covers B*4096 tokens)
+FLOP_PER_TOKEN_MLP = 259_200           # fc1 + fc2
+GFLOP_PER_TILE_MODEL = 107.113         # whole SwinIR x4 forward, one 64x64 tile
+WORKLOAD = "SwinIR classical x4 (embed 180, 6 RSTB x 6, window 8, 6 heads, mlp_ratio 2), batch 16 of 64x64 LR tiles per GPU"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained bf16, 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = max((int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()), default=None)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm)}
+
+
+def _dist_setup(n_gpus: int):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return world, rank, local
+
+
+def _max_over_ranks(x: float, world: int) -> float:
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _barrier(world: int):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def cpu_oracle_rate(tiles: int, reps: int = 1, warm: bool = True):
+    """Reference algorithm on the host cores (oracle port, fp32): output Mpix/s on `tiles` tiles of the workload."""
+    from oracle import synth
+    from oracle import swinir_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = synth.CONFIGS[MODEL]
+    sd = synth.make_swinir_state_dict(cfg, seed=1234, kind="init")
+    lr = synth.make_lr_batch(tiles, TILE, TILE, seed=2)
+    with torch.no_grad():
+        if warm:
+            O.swinir_forward(lr[:1], sd, cfg)
+        best = float("inf")
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            O.swinir_forward(lr, sd, cfg)
+            best = min(best, time.perf_counter() - t0)
+    return tiles * (TILE * SCALE) ** 2 / best / 1e6, cores, best
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the reference is pure Python and cannot be
+    compiled into oracle/_ref) on all host cores; each step is a bounded 2-tile sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import synth
+    from oracle import swinir_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_tiles = 2
+    cfg = synth.CONFIGS[MODEL]
+    sd = synth.make_swinir_state_dict(cfg, seed=1234, kind="init")
+    lr = synth.make_lr_batch(sample_tiles, TILE, TILE, seed=2)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            O.swinir_forward(lr, sd, cfg)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.swinir_forward(lr, sd, cfg)
+        dt = time.perf_counter() - t0
+    mpix = sample_tiles * (TILE * SCALE) ** 2 / 1e6
+    value = mpix * args.steps / dt
+    sample = f"{sample_tiles} of the {TILES_PER_STEP} tiles of one step per timed step, fp32, torch CPU ops, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "SwinIR x4 output Mpix/s", "value": value, "unit": "Mpix/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours(args):
+    from oracle import synth                      # synthetic weights / inputs only (numpy RNG), not the checker
+    import tpu_superresolution_b200 as srk
+    from tpu_superresolution_b200 import _lib as L
+
+    world, rank, local = _dist_setup(args.gpus)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    L.load()
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True
+
+    cfg = synth.CONFIGS[MODEL]
+    model = srk.SwinIR(**cfg.as_kwargs()).eval()
+    model.load_state_dict(synth.make_swinir_state_dict(cfg, seed=1234, kind="init"), strict=True)
+    model.to(dev)
+    n_in = 4                                        # rotate distinct input batches
+    host_in = [synth.make_lr_batch(TILES_PER_STEP, TILE, TILE, seed=100 + rank * n_in + i).pin_memory() for i in range(n_in)]
+    dev_in = [h.to(dev) for h in host_in]
+    host_out = torch.empty(TILES_PER_STEP, 3, TILE * SCALE, TILE * SCALE).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    mpix_step = TILES_PER_STEP * (TILE * SCALE) ** 2 / 1e6
+    stream = torch.cuda.current_stream()
+
+    def step_resident(i):
+        return model(dev_in[i % n_in])
+
+    def step_e2e(i):
+        x = host_in[i % n_in].to(dev, non_blocking=True)
+        y = model(x)
+        host_out.copy_(y, non_blocking=True)
+        return y
+
+    def timed(fn, steps, warmup):
+        with torch.no_grad():
+            for i in range(warmup):
+                fn(i)
+            _barrier(world)
+            evs = []
+            for i in range(steps):
+                flush.zero_()                                          # L2 flush, outside the timed events
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                fn(i)
+                e1.record(stream)
+                evs.append((e0, e1))
+            _barrier(world)
+            return sum(a.elapsed_time(b) for a, b in evs) / 1e3        # seconds of device time in the K steps
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.launch_count()
+    t_res = _max_over_ranks(timed(step_resident, args.steps, args.warmup), world)
+    launches = (L.launch_count() - launches0) * args.steps // (args.steps + args.warmup)
+    t_e2e = _max_over_ranks(timed(step_e2e, args.steps, max(1, args.warmup // 2)), world)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-kernel timing pass (CUDA events around every libsrk launch) for the roofline of the dominant kernel
+    prof = {}
+    L.PROFILE = prof
+    with torch.no_grad():
+        for i in range(3):
+            flush.zero_()
+            step_resident(i)
+    torch.cuda.synchronize()
+    L.PROFILE = None
+    kstats = {k: (sum(a.elapsed_time(b) for a, b in v) / len(v), len(v)) for k, v in prof.items()}
+
+    if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return
+
+    peak_tf, peak_gbs, peak_src = _peaks()
+    tokens = TILES_PER_STEP * TILE * TILE
+    attn_ms, attn_n = kstats.get("swin_attn", (float("nan"), 0))
+    mlp_ms, mlp_n = kstats.get("swin_mlp", (float("nan"), 0))
+    attn_tf = FLOP_PER_TOKEN_ATTN * tokens / (attn_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.isfile(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("swin_attn_kernel_dram_bytes_per_launch")
+
+    cpu_val, cores, cpu_s = cpu_oracle_rate(tiles=TILES_PER_STEP if (os.cpu_count() or 1) >= 16 else 4)
+    cpu_tiles = TILES_PER_STEP if (os.cpu_count() or 1) >= 16 else 4
+
+    ms_step = t_res / args.steps * 1e3
+    value = world * mpix_step * args.steps / t_res
+    model_tf = world * GFLOP_PER_TILE_MODEL * TILES_PER_STEP * args.steps / t_res / 1e3
+    out = {
+        "metric": "SwinIR x4 output Mpix/s", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "tiles_per_step_per_gpu": TILES_PER_STEP, "parallelism": f"tile-sharded x{world}, no collective",
+                   "precision": "bf16 MMA operands, fp32 accumulate, fp32 residual stream; convs cuDNN TF32",
+                   "l2": "flushed between steps (256 MiB memset outside the timed events)",
+                   "whole_model_tflops": model_tf, "whole_model_frac_of_peak": model_tf / world / peak_tf},
+        "e2e": {"value": world * mpix_step * args.steps / t_e2e, "unit": "Mpix/s",
+                "h2d_bytes_per_step": host_in[0].numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4,
+                "ms_per_step": t_e2e / args.steps * 1e3},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"kernel": "swin_attn_kernel", "bound": "tensor", "achieved": attn_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": attn_tf / peak_tf, "traffic": traffic, "peak_source": peak_src,
+                     "avg_launch_ms": attn_ms, "launches_timed": attn_n,
+                     "algorithmic_flop_per_launch": FLOP_PER_TOKEN_ATTN * tokens,
+                     "other_kernels": {"swin_mlp_kernel": {"avg_launch_ms": mlp_ms, "launches_timed": mlp_n,
+                                                           "achieved": FLOP_PER_TOKEN_MLP * tokens / (mlp_ms * 1e-3) / 1e12,
+                                                           "frac": FLOP_PER_TOKEN_MLP * tokens / (mlp_ms * 1e-3) / 1e12 / peak_tf}},
+                     "libsrk_ms_per_step": sum(v[0] * v[1] for v in kstats.values()) / 3.0},
+        "cpu_baseline": {"value": cpu_val, "unit": "Mpix/s", "cores": cores, "kind": "port",
+                         "sample": f"{cpu_tiles} of the {TILES_PER_STEP} tiles of one step, fp32 oracle port (torch CPU ops), {cpu_s:.1f} s"},
+    }
+    print(json.dumps(out))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -38,8 +38,8 @@ extern "C" {
 #define SRK_HIDDEN_PAD 384
 
 /* byte sizes of the packed weight streams (see packing.py for the slab order) */
-#define SRK_ATTN_WSTREAM_BYTES (15 * 16384 + 3 * 24576)
-#define SRK_MLP_WSTREAM_BYTES (12 * 24576)
+#define SRK_ATTN_WSTREAM_BYTES (6 * 16384 + 18 * 8192 + 3 * 24576)
+#define SRK_MLP_WSTREAM_BYTES (9 * 16384 + 6 * 24576)
 /* float offsets inside the packed per-block vectors */
 #define SRK_AV_LN_W 0
 #define SRK_AV_LN_B 192

@@ -76,10 +76,10 @@ def test_pack_attention_reconstructs_reference_math():
     w, vec = packing.pack_attention(sd[pre + "qkv.weight"], sd[pre + "qkv.bias"], sd[pre + "proj.weight"], sd[pre + "proj.bias"],
                                     sd[pre + "relative_position_bias_table"])
     assert w.numel() == L.ATTN_WSTREAM_BYTES and vec.numel() == L.ATTN_VEC_FLOATS
-    slabs = _unpack_slabs(w, [128] * 15 + [192] * 3)
+    slabs = _unpack_slabs(w, [128] * 6 + [64] * 18 + [192] * 3)
     wv = torch.cat([torch.cat(slabs[0:3], 1), torch.cat(slabs[3:6], 1)], 0)           # (256, 192)
-    wqk = [torch.cat(slabs[6 + 3 * p:9 + 3 * p], 1) for p in range(3)]                  # 3 x (128, 192)
-    wp = torch.cat(slabs[15:18], 1)                                                      # (192, 192)
+    wqk = [torch.cat(slabs[6 + 3 * h:9 + 3 * h], 1) for h in range(6)]                  # 6 x (64, 192): [q_h | k_h]
+    wp = torch.cat(slabs[24:27], 1)                                                      # (192, 192)
     xw = synth.make_tokens(4, 8, 8, 180, seed=5)
     xb = torch.zeros(4, 64, 192)
     xb[..., :180] = xw.bfloat16().float()
@@ -89,8 +89,9 @@ def test_pack_attention_reconstructs_reference_math():
     idx = O.relative_position_index(8)
     for h in range(6):
         p, j = divmod(h, 2)
-        qk = xb @ wqk[p].T + vec[L.AV_BIAS_QK + 128 * p:L.AV_BIAS_QK + 128 * p + 128]
-        q, k = qk[..., 32 * j:32 * j + 32], qk[..., 64 + 32 * j:64 + 32 * j + 32]
+        bias = vec[L.AV_BIAS_QK + 128 * p:L.AV_BIAS_QK + 128 * p + 128]
+        qk = xb @ wqk[h].T
+        q, k = qk[..., :32] + bias[32 * j:32 * j + 32], qk[..., 32:] + bias[64 + 32 * j:64 + 32 * j + 32]
         s = q @ k.transpose(-1, -2) + rpb[h][idx]                                        # log2 domain
         pm = torch.exp2(s - s.max(-1, keepdim=True).values)
         o[..., 32 * h:32 * h + 32] = (pm / pm.sum(-1, keepdim=True)) @ v[..., 32 * h:32 * h + 32]
@@ -106,9 +107,9 @@ def test_pack_mlp_reconstructs_reference_math():
     sd = synth.make_swinir_state_dict(cfg, seed=99, kind="stress")
     pre = "layers.0.residual_group.blocks.0.mlp."
     w, vec = packing.pack_mlp(sd[pre + "fc1.weight"], sd[pre + "fc1.bias"], sd[pre + "fc2.weight"], sd[pre + "fc2.bias"])
-    slabs = _unpack_slabs(w, [192] * 12)
-    w1 = torch.cat([torch.cat(slabs[0:3], 1), torch.cat(slabs[3:6], 1)], 0)             # (384, 192)
-    w2 = torch.cat(slabs[6:12], 1)                                                       # (192, 384)
+    slabs = _unpack_slabs(w, [128] * 9 + [192] * 6)
+    w1 = torch.cat([torch.cat(slabs[3 * c:3 * c + 3], 1) for c in range(3)], 0)         # (384, 192)
+    w2 = torch.cat(slabs[9:15], 1)                                                       # (192, 384)
     x = synth.make_tokens(1, 8, 8, 180, seed=7)[0]
     xb = torch.zeros(64, 192)
     xb[:, :180] = x

@@ -13,8 +13,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libsrk.so")
 # mirrors of the #defines in include/srk.h
 ABI_VERSION = 1
 DIM, DIM_PAD, HEADS, HEAD_DIM, HEAD_PAD, WINDOW, HIDDEN, HIDDEN_PAD = 180, 192, 6, 30, 32, 8, 360, 384
-ATTN_WSTREAM_BYTES = 15 * 16384 + 3 * 24576
-MLP_WSTREAM_BYTES = 12 * 24576
+ATTN_WSTREAM_BYTES = 6 * 16384 + 18 * 8192 + 3 * 24576
+MLP_WSTREAM_BYTES = 9 * 16384 + 6 * 24576
 AV_LN_W, AV_LN_B, AV_BIAS_V, AV_BIAS_QK, AV_BIAS_PROJ, AV_RPB, AV_RPB_STRIDE = 0, 192, 384, 640, 1024, 1216, 232
 ATTN_VEC_FLOATS = 1216 + 6 * 232
 MV_LN_W, MV_LN_B, MV_B1, MV_B2, MLP_VEC_FLOATS = 0, 192, 384, 768, 960
@@ -33,6 +33,24 @@ class MlpDesc(Structure):
 
 
 _lib = None
+# bench.py sets this to a dict to get CUDA-event timings of every launch: {"swin_attn": [(ev0, ev1), ...], ...}
+PROFILE = None
+
+
+class _timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record(torch.cuda.current_stream())
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e1.record(torch.cuda.current_stream())
+            PROFILE.setdefault(self.name, []).append((self.e0, self.e1))
+        return False
 
 
 def load():
@@ -96,27 +114,31 @@ def swin_attn(x, y, wstream, vec, *, mode, batch=0, height=0, width=0, num_windo
     _require_cuda_f32(x, y, vec, mask)
     d = SwinAttnDesc(mode, batch, height, width, num_windows, ld_in, ld_out, shift, int(apply_ln), int(add_residual),
                      mask_mode, 0 if mask is None else mask.shape[0])
-    _check(lib.srk_swin_attn_fwd(ctypes.byref(d), x.data_ptr(), y.data_ptr(), wstream.data_ptr(), vec.data_ptr(),
-                                 0 if mask is None else mask.data_ptr(), _stream()), lib)
+    with _timed("swin_attn"):
+        _check(lib.srk_swin_attn_fwd(ctypes.byref(d), x.data_ptr(), y.data_ptr(), wstream.data_ptr(), vec.data_ptr(),
+                                     0 if mask is None else mask.data_ptr(), _stream()), lib)
 
 
 def swin_mlp(x, y, wstream, vec, *, num_tokens, ld_in, ld_out, apply_ln=True, add_residual=True) -> None:
     lib = load()
     _require_cuda_f32(x, y, vec)
     d = MlpDesc(num_tokens, ld_in, ld_out, int(apply_ln), int(add_residual))
-    _check(lib.srk_swin_mlp_fwd(ctypes.byref(d), x.data_ptr(), y.data_ptr(), wstream.data_ptr(), vec.data_ptr(), _stream()), lib)
+    with _timed("swin_mlp"):
+        _check(lib.srk_swin_mlp_fwd(ctypes.byref(d), x.data_ptr(), y.data_ptr(), wstream.data_ptr(), vec.data_ptr(), _stream()), lib)
 
 
 def layernorm(x, y, w, b, *, num_tokens, ld_in, ld_out) -> None:
     lib = load()
     _require_cuda_f32(x, y, w, b)
-    _check(lib.srk_layernorm_fwd(x.data_ptr(), y.data_ptr(), w.data_ptr(), b.data_ptr(), num_tokens, ld_in, ld_out, _stream()), lib)
+    with _timed("layernorm"):
+        _check(lib.srk_layernorm_fwd(x.data_ptr(), y.data_ptr(), w.data_ptr(), b.data_ptr(), num_tokens, ld_in, ld_out, _stream()), lib)
 
 
 def pixelshuffle_nhwc(x, y, *, batch, height, width, out_channels, r) -> None:
     lib = load()
     _require_cuda_f32(x, y)
-    _check(lib.srk_pixelshuffle_nhwc_fwd(x.data_ptr(), y.data_ptr(), batch, height, width, out_channels, r, _stream()), lib)
+    with _timed("pixelshuffle"):
+        _check(lib.srk_pixelshuffle_nhwc_fwd(x.data_ptr(), y.data_ptr(), batch, height, width, out_channels, r, _stream()), lib)
 
 
 def stitch_accumulate(tiles, E, Wt, tile_yx, *, channels, tile_h, tile_w, out_h, out_w) -> None:

@@ -83,8 +83,8 @@ def pack_attention(qkv_w, qkv_b, proj_w, proj_b, rpb_table, ln_w=None, ln_b=None
     wv256[:192] = wv
     for m in range(2):                                   # V^T pass: A operand = 128 v-dims per half
         slabs += _slabs(wv256[128 * m:128 * (m + 1)])
-    for p in range(3):                                   # head pair p: [q(2p) q(2p+1) k(2p) k(2p+1)] rows
-        rows = torch.cat([wq[64 * p:64 * p + 64], wk[64 * p:64 * p + 64]], 0)
+    for h in range(L.HEADS):                             # head h: [q_h | k_h] rows (B operand, N = 64)
+        rows = torch.cat([wq[32 * h:32 * h + 32], wk[32 * h:32 * h + 32]], 0)
         slabs += _slabs(rows)
     # proj: K index is the padded head layout of O
     wp = proj_w.detach().float().view(C, L.HEADS, L.HEAD_DIM)
@@ -121,8 +121,8 @@ def pack_mlp(fc1_w, fc1_b, fc2_w, fc2_b, ln_w=None, ln_b=None) -> Tuple[torch.Te
     w2 = fc2_w.new_zeros(L.DIM_PAD, L.HIDDEN_PAD, dtype=torch.float32)
     w2[:C, :Hd] = fc2_w.detach().float()
     slabs = []
-    for nh in range(2):
-        slabs += _slabs(w1[192 * nh:192 * (nh + 1)])
+    for c in range(3):                                   # fc1 in three 128-unit hidden chunks
+        slabs += _slabs(w1[128 * c:128 * (c + 1)])
     slabs += _slabs(w2)
     wstream = torch.cat([s.reshape(-1) for s in slabs]).contiguous().view(torch.uint8)
     assert wstream.numel() == L.MLP_WSTREAM_BYTES
