@@ -40,17 +40,14 @@ extern "C" {
 /* byte sizes of the packed weight streams (see packing.py for the slab order) */
 #define SRK_ATTN_WSTREAM_BYTES (6 * 16384 + 18 * 8192 + 3 * 24576)
 #define SRK_MLP_WSTREAM_BYTES (9 * 16384 + 6 * 24576)
-/* float offsets inside the packed per-block vectors */
-#define SRK_AV_LN_W 0
-#define SRK_AV_LN_B 192
-#define SRK_AV_BIAS_V 384          /* 256: v bias in padded head layout (h*32+d) */
-#define SRK_AV_BIAS_QK 640         /* 3 x 128: per head pair [q(2p) q(2p+1) k(2p) k(2p+1)], q pre-scaled */
+/* float offsets inside the packed per-block vectors.  LayerNorm's affine, the k bias and the v bias do not appear:
+ * packing.py folds gamma/beta into the following GEMM, drops the k bias (softmax-invariant) and moves the v bias
+ * into the proj bias (softmax rows sum to one). */
+#define SRK_AV_BIAS_Q 384          /* 192: q bias in padded head layout (h*32+d), pre-scaled by head_dim^-0.5 * log2(e) */
 #define SRK_AV_BIAS_PROJ 1024      /* 192 */
 #define SRK_AV_RPB 1216            /* 6 x 232: relative-position-bias table per head, * log2(e) */
 #define SRK_AV_RPB_STRIDE 232
 #define SRK_ATTN_VEC_FLOATS (1216 + 6 * 232)
-#define SRK_MV_LN_W 0
-#define SRK_MV_LN_B 192
 #define SRK_MV_B1 384              /* 384 */
 #define SRK_MV_B2 768              /* 192 */
 #define SRK_MLP_VEC_FLOATS 960
@@ -78,7 +75,7 @@ typedef struct SrkSwinAttnDesc {
 int srk_swin_attn_fwd(const SrkSwinAttnDesc* desc, const float* x, float* y, const void* wstream /* SRK_ATTN_WSTREAM_BYTES */,
                       const float* vec /* SRK_ATTN_VEC_FLOATS */, const float* mask /* or NULL */, void* stream);
 
-/* MLP half:  y = x + fc2(gelu_erf(fc1(LN2(x)))).  Replaces network_swinir.py:277 + Mlp.forward :24-30. */
+/* MLP half:  y = x + fc2(gelu(fc1(LN2(x)))), gelu = the exact-erf form evaluated to 2.6e-5 (see swin_kernels.cu).  Replaces network_swinir.py:277 + Mlp.forward :24-30. */
 typedef struct SrkMlpDesc {
     int64_t num_tokens;
     int32_t ld_in, ld_out;
@@ -110,6 +107,10 @@ int srk_abi_version(void);
 const char* srk_last_error_string(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t srk_launch_count(void);
+/* debug: device buffer of >= 512 uint64 receiving CTA 0's clock64() timeline of later launches (NULL = off) */
+void srk_debug_set_timeline(void* device_buf);
+/* tuning: start skew (cycles per CTA index mod 4) of the attention / MLP kernels, see stagger_start() */
+void srk_debug_set_stagger(int attn_cycles, int mlp_cycles);
 
 #ifdef __cplusplus
 }

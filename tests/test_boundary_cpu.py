@@ -68,56 +68,71 @@ def _unpack_slabs(stream_u8, specs):
     return out
 
 
-def test_pack_attention_reconstructs_reference_math():
+@pytest.mark.parametrize("with_ln", [False, True])
+def test_pack_attention_reconstructs_reference_math(with_ln):
     """Emulate the kernel's dataflow on the CPU from the packed stream alone and compare with the oracle."""
     cfg = synth.CONFIGS["swinir_x2_d2"]
     sd = synth.make_swinir_state_dict(cfg, seed=99, kind="stress")
-    pre = "layers.0.residual_group.blocks.1.attn."
+    blk = "layers.0.residual_group.blocks.1."
+    pre = blk + "attn."
+    ln = (sd[blk + "norm1.weight"], sd[blk + "norm1.bias"]) if with_ln else (None, None)
     w, vec = packing.pack_attention(sd[pre + "qkv.weight"], sd[pre + "qkv.bias"], sd[pre + "proj.weight"], sd[pre + "proj.bias"],
-                                    sd[pre + "relative_position_bias_table"])
+                                    sd[pre + "relative_position_bias_table"], *ln)
     assert w.numel() == L.ATTN_WSTREAM_BYTES and vec.numel() == L.ATTN_VEC_FLOATS
     slabs = _unpack_slabs(w, [128] * 6 + [64] * 18 + [192] * 3)
     wv = torch.cat([torch.cat(slabs[0:3], 1), torch.cat(slabs[3:6], 1)], 0)           # (256, 192)
     wqk = [torch.cat(slabs[6 + 3 * h:9 + 3 * h], 1) for h in range(6)]                  # 6 x (64, 192): [q_h | k_h]
     wp = torch.cat(slabs[24:27], 1)                                                      # (192, 192)
     xw = synth.make_tokens(4, 8, 8, 180, seed=5)
+    xhat = (xw - xw.mean(-1, keepdim=True)) / torch.sqrt(xw.var(-1, unbiased=False, keepdim=True) + 1e-5) if with_ln else xw
     xb = torch.zeros(4, 64, 192)
-    xb[..., :180] = xw.bfloat16().float()
-    v = xb @ wv.T + vec[L.AV_BIAS_V:L.AV_BIAS_V + 256]                                   # (4, 64, 256) padded head layout
+    xb[..., :180] = xhat.bfloat16().float()
+    v = xb @ wv.T                                                                        # (4, 64, 256) padded head layout, no bias
     o = torch.zeros(4, 64, 192)
     rpb = vec[L.AV_RPB:].view(6, L.AV_RPB_STRIDE)
     idx = O.relative_position_index(8)
     for h in range(6):
-        p, j = divmod(h, 2)
-        bias = vec[L.AV_BIAS_QK + 128 * p:L.AV_BIAS_QK + 128 * p + 128]
         qk = xb @ wqk[h].T
-        q, k = qk[..., :32] + bias[32 * j:32 * j + 32], qk[..., 32:] + bias[64 + 32 * j:64 + 32 * j + 32]
+        q, k = qk[..., :32] + vec[L.AV_BIAS_Q + 32 * h:L.AV_BIAS_Q + 32 * h + 32], qk[..., 32:]
         s = q @ k.transpose(-1, -2) + rpb[h][idx]                                        # log2 domain
         pm = torch.exp2(s - s.max(-1, keepdim=True).values)
         o[..., 32 * h:32 * h + 32] = (pm / pm.sum(-1, keepdim=True)) @ v[..., 32 * h:32 * h + 32]
     y = o @ wp.T + vec[L.AV_BIAS_PROJ:L.AV_BIAS_PROJ + 192]
-    ref = O.window_attention(xw, sd, pre, 6, 8, None)
+    xin = O.layer_norm(xw, *ln) if with_ln else xw
+    ref = O.window_attention(xin, sd, pre, 6, 8, None)
     assert (y[..., 180:].abs().max() == 0) and (v[..., 30:32].abs().max() == 0)
     err = (y[..., :180] - ref).abs().max().item()
     assert err < 3e-2 * ref.abs().max().item(), err       # bf16 weights/inputs only
 
 
-def test_pack_mlp_reconstructs_reference_math():
+@pytest.mark.parametrize("with_ln", [False, True])
+def test_pack_mlp_reconstructs_reference_math(with_ln):
     cfg = synth.CONFIGS["swinir_x2_d2"]
     sd = synth.make_swinir_state_dict(cfg, seed=99, kind="stress")
-    pre = "layers.0.residual_group.blocks.0.mlp."
-    w, vec = packing.pack_mlp(sd[pre + "fc1.weight"], sd[pre + "fc1.bias"], sd[pre + "fc2.weight"], sd[pre + "fc2.bias"])
+    blk = "layers.0.residual_group.blocks.0."
+    pre = blk + "mlp."
+    ln = (sd[blk + "norm2.weight"], sd[blk + "norm2.bias"]) if with_ln else (None, None)
+    w, vec = packing.pack_mlp(sd[pre + "fc1.weight"], sd[pre + "fc1.bias"], sd[pre + "fc2.weight"], sd[pre + "fc2.bias"], *ln)
     slabs = _unpack_slabs(w, [128] * 9 + [192] * 6)
     w1 = torch.cat([torch.cat(slabs[3 * c:3 * c + 3], 1) for c in range(3)], 0)         # (384, 192)
     w2 = torch.cat(slabs[9:15], 1)                                                       # (192, 384)
     x = synth.make_tokens(1, 8, 8, 180, seed=7)[0]
+    xhat = (x - x.mean(-1, keepdim=True)) / torch.sqrt(x.var(-1, unbiased=False, keepdim=True) + 1e-5) if with_ln else x
     xb = torch.zeros(64, 192)
-    xb[:, :180] = x
+    xb[:, :180] = xhat
     y = O.gelu(xb @ w1.T + vec[L.MV_B1:L.MV_B1 + 384]) @ w2.T + vec[L.MV_B2:L.MV_B2 + 192]
-    ref = O.mlp(x, sd, pre)
+    ref = O.mlp(O.layer_norm(x, *ln) if with_ln else x, sd, pre)
     assert (y[:, :180] - ref).abs().max() < 2e-2 * ref.abs().max()
     with pytest.raises(RuntimeError):
         packing.pack_mlp(torch.zeros(720, 180), None, torch.zeros(180, 720), None)
+
+
+def test_gelu_tanh_polynomial_matches_exact_erf_gelu():
+    """csrc/swin_kernels.cu gelu_fast: 0.5 x (1 + tanh(x (c1 + c3 u + c5 u^2))), u = min(x^2, 64)."""
+    x = torch.linspace(-30, 30, 240001, dtype=torch.float64)
+    u = torch.clamp(x * x, max=64.0)
+    g = 0.5 * x * (1 + torch.tanh(x * (7.97507881e-01 + u * (3.70056486e-02 + u * -3.51517176e-04))))
+    assert (g - O.gelu(x)).abs().max() < 2.6e-5
 
 
 def test_header_constants_match_python_mirror():
@@ -126,7 +141,7 @@ def test_header_constants_match_python_mirror():
     ev = lambda k: eval(defs[k])
     assert ev("SRK_ATTN_WSTREAM_BYTES") == L.ATTN_WSTREAM_BYTES and ev("SRK_MLP_WSTREAM_BYTES") == L.MLP_WSTREAM_BYTES
     assert ev("SRK_ATTN_VEC_FLOATS") == L.ATTN_VEC_FLOATS and ev("SRK_MLP_VEC_FLOATS") == L.MLP_VEC_FLOATS
-    for k, v in [("SRK_AV_BIAS_V", L.AV_BIAS_V), ("SRK_AV_BIAS_QK", L.AV_BIAS_QK), ("SRK_AV_BIAS_PROJ", L.AV_BIAS_PROJ),
+    for k, v in [("SRK_AV_BIAS_Q", L.AV_BIAS_Q), ("SRK_AV_BIAS_PROJ", L.AV_BIAS_PROJ),
                  ("SRK_AV_RPB", L.AV_RPB), ("SRK_AV_RPB_STRIDE", L.AV_RPB_STRIDE), ("SRK_MV_B1", L.MV_B1), ("SRK_MV_B2", L.MV_B2),
                  ("SRK_ABI_VERSION", L.ABI_VERSION)]:
         assert ev(k) == v, k

@@ -1,0 +1,49 @@
+"""Print CTA 0's phase timeline (clock64 deltas) of one swin_attn / swin_mlp launch at the bench workload size."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import tpu_superresolution_b200 as srk
+from tpu_superresolution_b200 import _lib as L
+from oracle import synth
+
+torch.set_grad_enabled(False)
+sd = synth.make_swinir_state_dict(synth.CONFIGS["swinir_x2_d2"], seed=99, kind="init")
+pre = "layers.0.residual_group.blocks.1."
+blk = srk.SwinTransformerBlock(180, (64, 64), 6, window_size=8, shift_size=4, mlp_ratio=2.0).eval()
+st = {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}
+st["attn_mask"] = blk.attn_mask.clone()
+blk.load_state_dict(st, strict=True)
+blk.cuda()
+x = synth.make_tokens(16, 64, 64, 180, seed=1).cuda()
+y = torch.empty_like(x)
+for _ in range(3):
+    blk.forward_into(x, (64, 64), y)
+lib = L.load()
+buf = torch.zeros(512, dtype=torch.int64, device="cuda")
+aw, av = blk.attn._packed(blk.norm1)
+mw, mv = blk.mlp._packed(blk.norm2)
+names1 = {0: "tile start", 1: "LN done", 2: "VTF seen", 3: "VT epi done", 4: "QKep0,1 done", 23: "OF seen", 24: "O epi done", 25: "PJF seen", 26: "store done",
+          32: "MMA tile start", 33: "MMA XA seen", 34: "MMA VT issued", 41: "MMA PV5 issued", 42: "MMA OR seen", 43: "MMA proj issued"}
+for h in range(6):
+    names1[5 + 3 * h] = f"SF{h} seen"; names1[6 + 3 * h] = f"softmax{h} done"; names1[7 + 3 * h] = f"QKep{h+2} done"; names1[35 + h] = f"MMA QKR{h} seen"
+names2 = {0: "tile start", 1: "F1c0 seen", 2: "gelu0 done", 3: "F1c1 seen", 4: "gelu1 done", 5: "F1c2 seen", 6: "gelu2 done", 7: "LN next done", 8: "F2 seen", 9: "store done"}
+for which, names in (("attn", names1), ("mlp", names2)):
+    buf.zero_()
+    lib.srk_debug_set_timeline(buf.data_ptr())
+    if which == "attn":
+        L.swin_attn(x, y, aw, av, mode=L.MODE_IMAGE, batch=16, height=64, width=64, ld_in=180, ld_out=180, shift=4, mask_mode=L.MASK_SHIFT)
+    else:
+        L.swin_mlp(y, y, mw, mv, num_tokens=16 * 4096, ld_in=180, ld_out=180)
+    torch.cuda.synchronize()
+    lib.srk_debug_set_timeline(0)
+    t = buf.cpu().view(8, 64)
+    for it in range(4):
+        ev = sorted((int(t[it, i]), i) for i in names if int(t[it, i]) != 0)
+        if not ev:
+            continue
+        t0 = ev[0][0]
+        print(f"--- {which} CTA0 tile iteration {it}")
+        prev = t0
+        for c, i in ev:
+            print(f"  {c - t0:8d} (+{c - prev:6d})  {names[i]}")
+            prev = c

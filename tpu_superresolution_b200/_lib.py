@@ -15,9 +15,9 @@ ABI_VERSION = 1
 DIM, DIM_PAD, HEADS, HEAD_DIM, HEAD_PAD, WINDOW, HIDDEN, HIDDEN_PAD = 180, 192, 6, 30, 32, 8, 360, 384
 ATTN_WSTREAM_BYTES = 6 * 16384 + 18 * 8192 + 3 * 24576
 MLP_WSTREAM_BYTES = 9 * 16384 + 6 * 24576
-AV_LN_W, AV_LN_B, AV_BIAS_V, AV_BIAS_QK, AV_BIAS_PROJ, AV_RPB, AV_RPB_STRIDE = 0, 192, 384, 640, 1024, 1216, 232
+AV_BIAS_Q, AV_BIAS_PROJ, AV_RPB, AV_RPB_STRIDE = 384, 1024, 1216, 232
 ATTN_VEC_FLOATS = 1216 + 6 * 232
-MV_LN_W, MV_LN_B, MV_B1, MV_B2, MLP_VEC_FLOATS = 0, 192, 384, 768, 960
+MV_B1, MV_B2, MLP_VEC_FLOATS = 384, 768, 960
 MODE_IMAGE, MODE_WINDOWS = 0, 1
 MASK_NONE, MASK_SHIFT, MASK_EXPLICIT = 0, 1, 2
 
@@ -72,6 +72,10 @@ def load():
     lib.srk_stitch_accumulate.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                           c_int32, c_int32, c_void_p]
     lib.srk_stitch_normalize.argtypes = [c_void_p, c_void_p, c_int32, c_int64, c_void_p]
+    lib.srk_debug_set_timeline.argtypes = [c_void_p]
+    lib.srk_debug_set_timeline.restype = None
+    lib.srk_debug_set_stagger.argtypes = [c_int32, c_int32]
+    lib.srk_debug_set_stagger.restype = None
     for f in ("srk_swin_attn_fwd", "srk_swin_mlp_fwd", "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd",
               "srk_stitch_accumulate", "srk_stitch_normalize"):
         getattr(lib, f).restype = c_int32
@@ -82,7 +86,7 @@ def load():
 
 
 EXPORTS = ("srk_abi_version", "srk_last_error_string", "srk_launch_count", "srk_swin_attn_fwd", "srk_swin_mlp_fwd",
-           "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd", "srk_stitch_accumulate", "srk_stitch_normalize")
+           "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd", "srk_stitch_accumulate", "srk_stitch_normalize", "srk_debug_set_timeline", "srk_debug_set_stagger")
 
 
 def _check(rc: int, lib) -> None:

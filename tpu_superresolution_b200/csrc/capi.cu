@@ -32,6 +32,8 @@ extern "C" {
 
 int srk_abi_version(void) { return SRK_ABI_VERSION; }
 const char* srk_last_error_string(void) { return g_err; }
+void srk_debug_set_stagger(int attn_cycles, int mlp_cycles) { srk::g_stagger_attn = attn_cycles; srk::g_stagger_mlp = mlp_cycles; }
+void srk_debug_set_timeline(void* buf) { srk::g_timeline = static_cast<unsigned long long*>(buf); }
 int64_t srk_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int srk_swin_attn_fwd(const SrkSwinAttnDesc* d, const float* x, float* y, const void* wstream, const float* vec,
@@ -76,6 +78,8 @@ int srk_swin_attn_fwd(const SrkSwinAttnDesc* d, const float* x, float* y, const 
     if (d->mask_mode == SRK_MASK_SHIFT && d->shift == 0 && d->mode == SRK_MODE_IMAGE) p.mask_mode = SRK_MASK_NONE;
     if (d->mask_mode == SRK_MASK_SHIFT && d->mode == SRK_MODE_WINDOWS) p.shift = SRK_WINDOW / 2;   // regions of the shifted grid
     p.n_tiles = (p.total_windows + 1) / 2;
+    p.dbg = srk::g_timeline;
+    p.stagger = p.n_tiles >= 2 * 148 ? srk::g_stagger_attn : 0;
     return check(srk::launch_swin_attn(p, static_cast<cudaStream_t>(stream)), "srk_swin_attn_fwd");
 }
 
@@ -90,6 +94,8 @@ int srk_swin_mlp_fwd(const SrkMlpDesc* d, const float* x, float* y, const void* 
     p.x = x; p.y = y; p.wstream = static_cast<const uint8_t*>(wstream); p.vec = vec;
     p.num_tokens = d->num_tokens; p.n_tiles = static_cast<int>((d->num_tokens + 127) / 128);
     p.ld_in = d->ld_in; p.ld_out = d->ld_out; p.apply_ln = d->apply_ln; p.add_residual = d->add_residual;
+    p.dbg = srk::g_timeline;
+    p.stagger = p.n_tiles >= 2 * 148 ? srk::g_stagger_mlp : 0;
     return check(srk::launch_swin_mlp(p, static_cast<cudaStream_t>(stream)), "srk_swin_mlp_fwd");
 }
 

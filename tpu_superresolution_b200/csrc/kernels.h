@@ -17,6 +17,8 @@ struct AttnParams {
     int total_windows, n_tiles;
     int ld_in, ld_out;
     int apply_ln, add_residual, mask_mode, mask_nw;
+    unsigned long long* dbg;   // optional timeline buffer (srk_debug_set_timeline), else nullptr
+    int stagger;               // start skew in cycles per (CTA index mod 4)
 };
 
 struct MlpParams {
@@ -28,8 +30,12 @@ struct MlpParams {
     int n_tiles;
     int ld_in, ld_out;
     int apply_ln, add_residual;
+    unsigned long long* dbg;
+    int stagger;
 };
 
+extern unsigned long long* g_timeline;
+extern int g_stagger_attn, g_stagger_mlp;
 cudaError_t launch_swin_attn(const AttnParams& p, cudaStream_t stream);
 cudaError_t launch_swin_mlp(const MlpParams& p, cudaStream_t stream);
 cudaError_t launch_layernorm(const float* x, float* y, const float* w, const float* b, int64_t num_tokens, int ld_in,

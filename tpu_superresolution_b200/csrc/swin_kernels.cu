@@ -32,7 +32,7 @@ constexpr uint32_t VT_ATOM = 24576;     // 192 rows x 128 B: one k-atom (64 keys
 constexpr uint32_t RING_STAGE = 24576;  // largest weight slab (192 rows x 64 k)
 constexpr int RING_N = 3;
 constexpr int STAGE_LD = 36;            // fp32 words per row of the store transposer (conflict-free float4)
-constexpr uint32_t STAGE_BYTES = 128 * STAGE_LD * 4;
+constexpr uint32_t STAGE_WARP_BYTES = 32 * STAGE_LD * 4;   // warp-private 32 x 32 fp32 transposer
 
 constexpr uint32_t IDESC_128x128 = umma_idesc_bf16(128, 128);
 constexpr uint32_t IDESC_128x192 = umma_idesc_bf16(128, 192);
@@ -40,172 +40,194 @@ constexpr uint32_t IDESC_128x64 = umma_idesc_bf16(128, 64);
 constexpr uint32_t IDESC_128x32 = umma_idesc_bf16(128, 32);
 constexpr float LOG2E = 1.4426950408889634f;
 
+// Optional per-CTA timeline (debug): CTA 0 writes clock64() at event `id` of its `it`-th tile.
+#define SRK_TL(dbgptr, it, id) do { if ((dbgptr) != nullptr && blockIdx.x == 0 && (it) < 8) (dbgptr)[(it) * 64 + (id)] = clock64(); } while (0)
+unsigned long long* g_timeline = nullptr;
+int g_stagger_attn = 0, g_stagger_mlp = 0;
+
+// All CTAs of a launch run the same phase sequence; started together they hit their memory phases (tile load, tile
+// store) at the same time and leave HBM / L2 idle in between.  Skewing the start of CTA i by (i mod 4) * `cycles`
+// spreads the memory phases of neighbouring SMs over the tile period.
+__device__ __forceinline__ void stagger_start(int cycles) {
+    const long long wait = static_cast<long long>(blockIdx.x & 3) * cycles;
+    if (wait > 0) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < wait) {}
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // shared helpers for the 256 row threads
 // ------------------------------------------------------------------------------------------------
-// LayerNorm (optional) of 16 token rows per warp -> bf16 SW128 image at `xa` (3 k-atoms).
+// (x - mean) * rstd of 16 token rows per warp -> bf16 SW128 image at `xa` (3 k-atoms).  LayerNorm's affine
+// (gamma, beta) is folded into the following GEMM's weights / bias at pack time (packing.py).
 // Half-warp per token: 16 lanes x 3 float4 cover the 180 channels (45 float4) fully coalesced.  All 24 loads
 // of a lane are issued before the first use (one exposed memory latency per tile).
 template <typename TokFn>
-__device__ __forceinline__ void ln_rows_to_image(const float* __restrict__ x, int ld, const float* s_w, const float* s_b,
-                                                 int apply_ln, uint32_t xa, int cw8, int lane, TokFn tok_of_row) {
+__device__ __forceinline__ void ln_rows_to_image(const float* __restrict__ x, int ld, int apply_ln, uint32_t xa, int cw8,
+                                                 int lane, TokFn tok_of_row) {
     const int l16 = lane & 15;
+    const bool live2 = l16 < 13;            // float4 index l16 + 32 < 45
     float4 v[8][3];
 #pragma unroll
     for (int pass = 0; pass < 8; ++pass) {
         const int r = cw8 * 16 + pass * 2 + (lane >> 4);
         const int64_t tok = tok_of_row(r);
-#pragma unroll
-        for (int jj = 0; jj < 3; ++jj) {
-            const int f = l16 + 16 * jj;
-            v[pass][jj] = (tok >= 0 && f < SRK_DIM / 4) ? __ldg(reinterpret_cast<const float4*>(x + tok * ld) + f)
-                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        const float4* src = reinterpret_cast<const float4*>(x + (tok >= 0 ? tok : 0) * ld) + l16;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        v[pass][0] = tok >= 0 ? __ldg(src) : z;
+        v[pass][1] = tok >= 0 ? __ldg(src + 16) : z;
+        v[pass][2] = (tok >= 0 && live2) ? __ldg(src + 32) : z;
     }
+    // statistics of all 8 passes first, then the 4 butterfly rounds over all passes at once: the 16 shuffles of a
+    // round are independent, so their latency overlaps instead of serialising 8 x 4 dependent steps
+    float s[8], q[8];
 #pragma unroll
     for (int pass = 0; pass < 8; ++pass) {
-        const int r = cw8 * 16 + pass * 2 + (lane >> 4);
+        float4(&w)[3] = v[pass];
+        s[pass] = 0.f; q[pass] = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 3; ++jj) {
+            s[pass] += (w[jj].x + w[jj].y) + (w[jj].z + w[jj].w);
+            q[pass] = fmaf(w[jj].x, w[jj].x, q[pass]); q[pass] = fmaf(w[jj].y, w[jj].y, q[pass]);
+            q[pass] = fmaf(w[jj].z, w[jj].z, q[pass]); q[pass] = fmaf(w[jj].w, w[jj].w, q[pass]);
+        }
+    }
+    if (apply_ln) {
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+#pragma unroll
+            for (int pass = 0; pass < 8; ++pass) {
+                s[pass] += __shfl_xor_sync(0xffffffffu, s[pass], o);
+                q[pass] += __shfl_xor_sync(0xffffffffu, q[pass], o);
+            }
+        }
+    }
+    const uint32_t r0 = cw8 * 16 + (lane >> 4);
+#pragma unroll
+    for (int pass = 0; pass < 8; ++pass) {
         float4(&w)[3] = v[pass];
         if (apply_ln) {
-            float s = 0.f;
-#pragma unroll
-            for (int jj = 0; jj < 3; ++jj) s += (w[jj].x + w[jj].y) + (w[jj].z + w[jj].w);
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            const float mean = s * (1.0f / SRK_DIM);
-            float q = 0.f;
+            const float mean = s[pass] * (1.0f / SRK_DIM);
+            const float var = fmaxf(fmaf(-mean, mean, q[pass] * (1.0f / SRK_DIM)), 0.f);
+            const float rstd = rsqrtf(var + 1e-5f);
+            const float nm = -mean * rstd;
 #pragma unroll
             for (int jj = 0; jj < 3; ++jj) {
-                if (l16 + 16 * jj < SRK_DIM / 4) {
-                    w[jj].x -= mean; w[jj].y -= mean; w[jj].z -= mean; w[jj].w -= mean;
-                    q += (w[jj].x * w[jj].x + w[jj].y * w[jj].y) + (w[jj].z * w[jj].z + w[jj].w * w[jj].w);
-                }
+                w[jj].x = fmaf(w[jj].x, rstd, nm); w[jj].y = fmaf(w[jj].y, rstd, nm);
+                w[jj].z = fmaf(w[jj].z, rstd, nm); w[jj].w = fmaf(w[jj].w, rstd, nm);
             }
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-            const float rstd = rsqrtf(q * (1.0f / SRK_DIM) + 1e-5f);
-#pragma unroll
-            for (int jj = 0; jj < 3; ++jj) {
-                const int f = l16 + 16 * jj;
-                if (f < SRK_DIM / 4) {
-                    const float4 g = reinterpret_cast<const float4*>(s_w)[f];
-                    const float4 b = reinterpret_cast<const float4*>(s_b)[f];
-                    w[jj].x = w[jj].x * rstd * g.x + b.x; w[jj].y = w[jj].y * rstd * g.y + b.y;
-                    w[jj].z = w[jj].z * rstd * g.z + b.z; w[jj].w = w[jj].w * rstd * g.w + b.w;
-                }
-            }
+            if (!live2) w[2] = make_float4(0.f, 0.f, 0.f, 0.f);      // padded channels 180..191 stay exactly zero
         }
+        const uint32_t r = r0 + 2 * pass;
+        const uint32_t off = xa + sw128_off(r, l16 >> 1) + (l16 & 1) * 8;
 #pragma unroll
-        for (int jj = 0; jj < 3; ++jj) {   // channel 4f = 64*jj + 4*l16 -> atom jj, chunk l16>>1, byte (l16&1)*8
-            const uint32_t addr = xa + jj * ATOM_A + sw128_off(r, l16 >> 1) + (l16 & 1) * 8;
-            st_shared_v2(addr, pack_bf16x2(w[jj].x, w[jj].y), pack_bf16x2(w[jj].z, w[jj].w));
-        }
+        for (int jj = 0; jj < 3; ++jj)      // channel 4f = 64*jj + 4*l16 -> atom jj, chunk l16>>1, byte (l16&1)*8
+            st_shared_v2(off + jj * ATOM_A, pack_bf16x2(w[jj].x, w[jj].y), pack_bf16x2(w[jj].z, w[jj].w));
     }
 }
 
-// 32 fp32 accumulators (+ per-column bias from smem, * scale) -> 4 x 16-byte bf16 chunks of one image row.
+// 32 fp32 accumulators (+ per-column bias from smem | * scale) -> 4 x 16-byte bf16 chunks of one image row.
+template <bool HAS_BIAS, bool HAS_SCALE>
 __device__ __forceinline__ void store_row_chunks(uint32_t img_atom, uint32_t row, uint32_t c16base, const uint32_t (&v)[32],
                                                  const float* bias, float scale) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        uint32_t w[4];
+        float f[8];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int i = 8 * k + 2 * e;
-            const float a = (__uint_as_float(v[i]) + (bias ? bias[i] : 0.f)) * scale;
-            const float b = (__uint_as_float(v[i + 1]) + (bias ? bias[i + 1] : 0.f)) * scale;
-            w[e] = pack_bf16x2(a, b);
+        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * k + e]);
+        if (HAS_BIAS) {
+            const float4 b0 = reinterpret_cast<const float4*>(bias)[2 * k], b1 = reinterpret_cast<const float4*>(bias)[2 * k + 1];
+            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
         }
-        st_shared_v4(img_atom + sw128_off(row, c16base + k), w[0], w[1], w[2], w[3]);
+        if (HAS_SCALE) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] *= scale;
+        }
+        st_shared_v4(img_atom + sw128_off(row, c16base + k), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                     pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
     }
 }
 
-// Final epilogue shared by K1/K2.  Group g owns accumulator columns [96 g, 96 g + 96) (three 32-column chunks):
-// TMEM -> (+bias) -> per-group shared-memory transposer -> coalesced (+ shortcut) global store, 4 rows x 128 B
-// per warp instruction.  The shortcut loads of chunk c+1 are in flight while chunk c is processed; the first
-// ones are issued before `wait_acc()` so their latency hides behind the last GEMM.
+// Final epilogue shared by K1/K2.  Each warp owns the 32 accumulator rows of its TMEM lane quadrant and the columns
+// [96 g, 96 g + 96) of its group: TMEM -> (+bias) -> warp-private shared-memory transposer (32 x 32 fp32, only
+// __syncwarp) -> coalesced (+ shortcut) global store, 4 rows x 128 B per warp instruction.  The shortcut loads of
+// whole 96-column slice are issued before `wait_acc()` so their latency hides behind the last GEMM.
 template <typename TokFn, typename WaitFn>
-__device__ __forceinline__ void store_rows_coalesced(uint32_t tmem_acc, uint32_t lanebase, float* stage, uint32_t bar_id,
-                                                     const float* s_bias, const float* __restrict__ x, int ld_in,
-                                                     float* __restrict__ y, int ld_out, int add_residual, int row, int wg,
-                                                     int g, int lane, TokFn tok_of_row, WaitFn wait_acc) {
+__device__ __forceinline__ void store_rows_coalesced(uint32_t tmem_acc, uint32_t lanebase, float* stage, const float* s_bias,
+                                                     const float* __restrict__ x, int ld_in, float* __restrict__ y, int ld_out,
+                                                     int add_residual, int q, int g, int lane, TokFn tok_of_row, WaitFn wait_acc) {
     int64_t toks[8];
 #pragma unroll
-    for (int it = 0; it < 8; ++it) toks[it] = tok_of_row(wg * 32 + it * 4 + (lane >> 3));
+    for (int it = 0; it < 8; ++it) toks[it] = tok_of_row(q * 32 + it * 4 + (lane >> 3));
     const int c4 = lane & 7;
-    float4 sc_next[8];
-    auto prefetch = [&](int c) {
-        const int ch = 32 * c + 4 * c4;
+    float4 sc[3][8];
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) {
+        const int ch = 32 * (3 * g + ci) + 4 * c4;
 #pragma unroll
         for (int it = 0; it < 8; ++it)
-            sc_next[it] = (add_residual && ch < SRK_DIM && toks[it] >= 0)
-                              ? __ldg(reinterpret_cast<const float4*>(x + toks[it] * ld_in + ch))
-                              : make_float4(0.f, 0.f, 0.f, 0.f);
-    };
-    prefetch(3 * g);
+            sc[ci][it] = (add_residual && ch < SRK_DIM && toks[it] >= 0)
+                             ? __ldg(reinterpret_cast<const float4*>(x + toks[it] * ld_in + ch))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     wait_acc();
-#pragma unroll 1
+#pragma unroll
     for (int ci = 0; ci < 3; ++ci) {
         const int c = 3 * g + ci;
-        float4 sc[8];
-#pragma unroll
-        for (int it = 0; it < 8; ++it) sc[it] = sc_next[it];
-        if (ci < 2) prefetch(c + 1);
         uint32_t v[32];
         tmem_ld32(tmem_acc + lanebase + 32 * c, v);
         tmem_ld_wait();
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
+            const float4 b = reinterpret_cast<const float4*>(s_bias + 32 * c)[k];
             float4 o;
-            o.x = __uint_as_float(v[4 * k + 0]) + s_bias[32 * c + 4 * k + 0];
-            o.y = __uint_as_float(v[4 * k + 1]) + s_bias[32 * c + 4 * k + 1];
-            o.z = __uint_as_float(v[4 * k + 2]) + s_bias[32 * c + 4 * k + 2];
-            o.w = __uint_as_float(v[4 * k + 3]) + s_bias[32 * c + 4 * k + 3];
-            *reinterpret_cast<float4*>(stage + row * STAGE_LD + 4 * k) = o;
+            o.x = __uint_as_float(v[4 * k + 0]) + b.x;
+            o.y = __uint_as_float(v[4 * k + 1]) + b.y;
+            o.z = __uint_as_float(v[4 * k + 2]) + b.z;
+            o.w = __uint_as_float(v[4 * k + 3]) + b.w;
+            *reinterpret_cast<float4*>(stage + lane * STAGE_LD + 4 * k) = o;
         }
-        named_bar_sync(bar_id, 128);
+        __syncwarp();
         const int ch = 32 * c + 4 * c4;
         if (ch < SRK_DIM) {
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
-                const int rr = wg * 32 + it * 4 + (lane >> 3);
                 if (toks[it] >= 0) {
-                    float4 o = *reinterpret_cast<const float4*>(stage + rr * STAGE_LD + 4 * c4);
-                    o.x += sc[it].x; o.y += sc[it].y; o.z += sc[it].z; o.w += sc[it].w;
+                    float4 o = *reinterpret_cast<const float4*>(stage + (it * 4 + (lane >> 3)) * STAGE_LD + 4 * c4);
+                    o.x += sc[ci][it].x; o.y += sc[ci][it].y; o.z += sc[ci][it].z; o.w += sc[ci][it].w;
                     *reinterpret_cast<float4*>(y + toks[it] * ld_out + ch) = o;
                 }
             }
         }
-        named_bar_sync(bar_id, 128);
+        __syncwarp();
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // K1: attention half
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t A_XA = 0;                          // LN1(x) image [128 x 192]; later the O image
-constexpr uint32_t A_VT = A_XA + 3 * ATOM_A;          // V^T image [192 x 128 keys]; later group-1 transposer
-constexpr uint32_t A_QKI = A_VT + 2 * VT_ATOM;        // 2 x [q_h | k_h] images [128 x (32+32)]; later group-0 transposer
+constexpr uint32_t A_XA = 0;                          // normalised x image [128 x 192]
+constexpr uint32_t A_VT = A_XA + 3 * ATOM_A;          // V^T image [192 x 128 keys]; then the O image; then the transposers
+constexpr uint32_t A_QKI = A_VT + 2 * VT_ATOM;        // 2 x [q_h | k_h] images [128 x (32+32)] (one per softmax group)
 constexpr uint32_t A_RING = A_QKI + 2 * ATOM_A;       // weight ring
 constexpr uint32_t A_VEC = A_RING + RING_N * RING_STAGE;
-constexpr uint32_t A_SUM = A_VEC + ((SRK_ATTN_VEC_FLOATS * 4 + 127) / 128) * 128;   // float [2][6][128] partial row sums
-constexpr uint32_t A_MAX = A_SUM + 2 * 6 * 128 * 4;                                  // float [2][2][128] partial row maxima
-constexpr uint32_t A_BAR = A_MAX + 2 * 2 * 128 * 4;
+constexpr uint32_t A_BAR = A_VEC + ((SRK_ATTN_VEC_FLOATS * 4 + 127) / 128) * 128;
 constexpr uint32_t A_END = A_BAR + 256;
 constexpr uint32_t K1_SMEM = A_END + 1024;            // + alignment slack
 static_assert(K1_SMEM <= 232448, "K1 shared memory exceeds 227 KB");
-static_assert(STAGE_BYTES <= 2 * ATOM_A && STAGE_BYTES <= 2 * VT_ATOM, "transposers must fit");
+static_assert(8 * STAGE_WARP_BYTES <= 2 * VT_ATOM && 3 * ATOM_A <= 2 * VT_ATOM, "O image / transposers must fit in the V^T image");
 
 // TMEM columns (fp32, 128 lanes)
-constexpr uint32_t TC_O = 0;                          // O accumulator, 6 heads x 32
+constexpr uint32_t TC_O = 0;                          // O accumulator, 6 heads x 32; later the proj accumulator (192)
 constexpr uint32_t TC_S0 = 192, TC_S1 = 320;          // S = q k^T (128 x 128, block diagonal used); P (bf16) aliases cols 0..63
 constexpr uint32_t TC_QK = 448;                       // [q_h | k_h] accumulator of one head (64 cols)
-constexpr uint32_t TC_VT0 = 192, TC_VT1 = 320;        // V^T accumulators (before the first S)
-constexpr uint32_t TC_PROJ = 192;                     // proj accumulator (after the last P v), 192 cols
+constexpr uint32_t TC_VT0 = 192, TC_VT1 = 320;        // V^T accumulators (before the first S of the tile)
+constexpr uint32_t TC_PROJ = 0;
 
 enum {  // K1 barrier slots
-    B_FULL = 0, B_EMPTY = 3, B_XA = 6, B_VTF = 7, B_VTD = 8, B_QKF = 9, B_QKR = 10, B_SF0 = 11, B_SF1 = 12,
-    B_PR0 = 13, B_PR1 = 14, B_OF = 15, B_OR = 16, B_PJF = 17, B_COUNT = 18
+    B_FULL = 0, B_EMPTY = 3, B_XA = 6, B_VTF = 7, B_VTD = 8, B_QKF0 = 9, B_QKF1 = 10, B_QKR0 = 11, B_QKR1 = 12, B_SF0 = 13,
+    B_SF1 = 14, B_PR0 = 15, B_PR1 = 16, B_OF = 17, B_OR = 18, B_PJF = 19, B_COUNT = 20
 };
 
 struct TileGeom {
@@ -220,8 +242,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_attn_kernel(const AttnParams
     const uint32_t sbase = (raw + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (sbase - raw);
     float* s_vec = reinterpret_cast<float*>(sm + A_VEC);
-    float* s_sum = reinterpret_cast<float*>(sm + A_SUM);
-    float* s_max = reinterpret_cast<float*>(sm + A_MAX);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + A_BAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT + 1);
 
@@ -230,10 +250,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_attn_kernel(const AttnParams
     for (int i = threadIdx.x; i < SRK_ATTN_VEC_FLOATS; i += blockDim.x) s_vec[i] = p.vec[i];
     if (threadIdx.x == 0) {
         for (int i = 0; i < RING_N; ++i) { mbar_init(&bars[B_FULL + i], 1); mbar_init(&bars[B_EMPTY + i], 1); }
-        mbar_init(&bars[B_XA], NROWTHREADS);  mbar_init(&bars[B_VTF], 1);           mbar_init(&bars[B_VTD], NROWTHREADS);
-        mbar_init(&bars[B_QKF], 1);           mbar_init(&bars[B_QKR], NROWTHREADS); mbar_init(&bars[B_SF0], 1);
-        mbar_init(&bars[B_SF1], 1);           mbar_init(&bars[B_PR0], NROWTHREADS); mbar_init(&bars[B_PR1], NROWTHREADS);
-        mbar_init(&bars[B_OF], 1);            mbar_init(&bars[B_OR], NROWTHREADS);  mbar_init(&bars[B_PJF], 1);
+        mbar_init(&bars[B_XA], NROWTHREADS); mbar_init(&bars[B_VTF], 1);    mbar_init(&bars[B_VTD], NROWTHREADS);
+        mbar_init(&bars[B_QKF0], 1);         mbar_init(&bars[B_QKF1], 1);   mbar_init(&bars[B_QKR0], 128);
+        mbar_init(&bars[B_QKR1], 128);       mbar_init(&bars[B_SF0], 1);    mbar_init(&bars[B_SF1], 1);
+        mbar_init(&bars[B_PR0], 128);        mbar_init(&bars[B_PR1], 128);  mbar_init(&bars[B_OF], 1);
+        mbar_init(&bars[B_OR], NROWTHREADS); mbar_init(&bars[B_PJF], 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -263,7 +284,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_attn_kernel(const AttnParams
         // ===================================================== MMA issuer
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            uint32_t ph_xa = 0, ph_vtd = 0, ph_qkr = 0, ph_pr[2] = {0, 0}, ph_or = 0;
+            uint32_t ph_xa = 0, ph_vtd = 0, ph_qkr[2] = {0, 0}, ph_pr[2] = {0, 0}, ph_or = 0;
             const uint32_t xa = sbase + A_XA, vt = sbase + A_VT, qki = sbase + A_QKI, ring = sbase + A_RING;
             // one GEMM over K = 192: 3 ring slabs x 4 k-steps
             auto gemm_k192 = [&](uint32_t d_tmem, uint32_t img, bool img_is_a, uint32_t idesc) {
@@ -286,24 +307,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_attn_kernel(const AttnParams
                     umma_ts(tmem + TC_O + 32 * h, tmem + pcol + 8 * kk,
                             umma_desc_sw128(vt + (kk >> 2) * VT_ATOM + h * 4096 + (kk & 3) * 32), IDESC_128x32, kk != 0);
             };
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+                SRK_TL(p.dbg, it, 32);
                 mbar_wait(&bars[B_XA], ph_xa); ph_xa ^= 1;
                 tc_fence_after();
-                // ---- V^T = Wv * LN(x)^T : A = Wv slab (128 v-dims), B = x image (128 tokens)
+                SRK_TL(p.dbg, it, 33);
+                // ---- V^T = Wv * xhat^T : A = Wv slab (128 v-dims), B = x image (128 tokens)
                 gemm_k192(tmem + TC_VT0, xa, false, IDESC_128x128);
                 gemm_k192(tmem + TC_VT1, xa, false, IDESC_128x128);
                 umma_commit(&bars[B_VTF]);
+                SRK_TL(p.dbg, it, 34);
                 // ---- [q_0 | k_0]
                 gemm_k192(tmem + TC_QK, xa, true, IDESC_128x64);
-                umma_commit(&bars[B_QKF]);
+                umma_commit(&bars[B_QKF0]);
                 for (int h = 0; h < 6; ++h) {
-                    mbar_wait(&bars[B_QKR], ph_qkr); ph_qkr ^= 1;          // image h written, QK accumulator drained
+                    mbar_wait(&bars[B_QKR0 + (h & 1)], ph_qkr[h & 1]); ph_qkr[h & 1] ^= 1;   // image h written, QK accumulator drained
                     tc_fence_after();
-                    if (h < 5) {                                           // next head's q|k GEMM overlaps softmax(h)
-                        gemm_k192(tmem + TC_QK, xa, true, IDESC_128x64);
-                        umma_commit(&bars[B_QKF]);
-                    }
-                    if (h == 0) {                                          // V^T accumulators drained (S columns free)
+                    SRK_TL(p.dbg, it, 35 + h);
+                    if (h == 0) {                                          // V^T accumulators drained (S columns free), V^T image ready
                         mbar_wait(&bars[B_VTD], ph_vtd); ph_vtd ^= 1;
                         tc_fence_after();
                     }
@@ -313,9 +335,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_attn_kernel(const AttnParams
                     for (int ks = 0; ks < 2; ++ks)
                         umma_ss(tmem + ((h & 1) ? TC_S1 : TC_S0), umma_desc_sw128(img + ks * 32), umma_desc_sw128(img + 64 + ks * 32),
                                 IDESC_128x128, ks != 0);
-                    umma_commit(&bars[(h & 1) ? B_SF1 : B_SF0]);
+                    umma_commit(&bars[B_SF0 + (h & 1)]);
+                    if (h < 5) {                                           // next head's q|k GEMM overlaps softmax(h)
+                        gemm_k192(tmem + TC_QK, xa, true, IDESC_128x64);
+                        umma_commit(&bars[B_QKF0 + ((h + 1) & 1)]);
+                    }
                     if (h >= 1) {
-                        mbar_wait(&bars[((h - 1) & 1) ? B_PR1 : B_PR0], ph_pr[(h - 1) & 1]); ph_pr[(h - 1) & 1] ^= 1;
+                        mbar_wait(&bars[B_PR0 + ((h - 1) & 1)], ph_pr[(h - 1) & 1]); ph_pr[(h - 1) & 1] ^= 1;
                         tc_fence_after();
                         issue_pv(h - 1);
                     }
@@ -324,30 +350,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_attn_kernel(const AttnParams
                 tc_fence_after();
                 issue_pv(5);
                 umma_commit(&bars[B_OF]);
+                SRK_TL(p.dbg, it, 41);
                 mbar_wait(&bars[B_OR], ph_or); ph_or ^= 1;
                 tc_fence_after();
-                // ---- proj: A = O image, B = Wproj slab (192 rows)
-                gemm_k192(tmem + TC_PROJ, xa, true, IDESC_128x192);
+                SRK_TL(p.dbg, it, 42);
+                // ---- proj: A = O image (in the V^T region), B = Wproj slab (192 rows)
+                gemm_k192(tmem + TC_PROJ, vt, true, IDESC_128x192);
                 umma_commit(&bars[B_PJF]);
+                SRK_TL(p.dbg, it, 43);
             }
         }
         __syncwarp();
     } else {
         // ===================================================== 256 row threads
         const int cw8 = warp - 2;                   // 0..7: 16-row slice this warp loads in the LN phase
-        const int g = cw8 >> 2;                     // column group
-        const int wg = cw8 & 3;                     // warp within the group: 32-row slice for coalesced stores
+        const int g = cw8 >> 2;                     // group: softmax of heads h = g (mod 2); column half elsewhere
         const int q = warp & 3;                     // TMEM lane quadrant this warp may access
         const int row = q * 32 + lane;              // accumulator row == token row of the tile
         const uint32_t lanebase = static_cast<uint32_t>(q * 32) << 16;
-        const uint32_t xa = sbase + A_XA, vt = sbase + A_VT, qki = sbase + A_QKI;
-        float* stage_buf = reinterpret_cast<float*>(sm + (g == 0 ? A_QKI : A_VT));
+        const uint32_t xa = sbase + A_XA, vt = sbase + A_VT, qki = sbase + A_QKI + g * ATOM_A;
+        float* stage_buf = reinterpret_cast<float*>(sm + A_VT + cw8 * STAGE_WARP_BYTES);
         const int half = row >> 6, t = row & 63;
-        const int rpb_base = (t >> 3) * 15 + (t & 7) + 112 - 60 * g;      // keys 32 g .. 32 g + 31 of the window
-        uint32_t ph_vtf = 0, ph_qkf = 0, ph_sf[2] = {0, 0}, ph_of = 0, ph_pjf = 0;
+        const int rpb_base = (t >> 3) * 15 + (t & 7) + 112;
+        uint32_t ph_vtf = 0, ph_qkf = 0, ph_sf = 0, ph_of = 0, ph_pjf = 0;
+        uint64_t* const bar_qkf = &bars[B_QKF0 + g];
+        uint64_t* const bar_qkr = &bars[B_QKR0 + g];
+        uint64_t* const bar_sf = &bars[B_SF0 + g];
+        uint64_t* const bar_pr = &bars[B_PR0 + g];
+        const uint32_t scol = g ? TC_S1 : TC_S0;
 
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            TileGeom geo;
+        TileGeom geo;
+        auto set_geom = [&](int tile) {
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
                 const int gw = tile * 2 + hf;
@@ -361,21 +394,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_attn_kernel(const AttnParams
                     geo.y0[hf] = wy * 8 + p.shift; geo.x0[hf] = wx * 8 + p.shift;
                 }
             }
-            auto tok_of_row = [&](int r) -> int64_t {
-                const int hf = r >> 6, tt = r & 63;
-                if (!geo.valid[hf]) return static_cast<int64_t>(-1);
-                if (p.mode == SRK_MODE_WINDOWS) return geo.base[hf] + tt;
-                int yy = geo.y0[hf] + (tt >> 3);
-                if (yy >= p.H) yy -= p.H;
-                int xx = geo.x0[hf] + (tt & 7);
-                if (xx >= p.W) xx -= p.W;
-                return geo.base[hf] + static_cast<int64_t>(yy) * p.W + xx;
-            };
-            // ---- phase 0: gather + LN1 -> x image
-            ln_rows_to_image(p.x, p.ld_in, s_vec + SRK_AV_LN_W, s_vec + SRK_AV_LN_B, p.apply_ln, xa, cw8, lane, tok_of_row);
+        };
+        auto tok_of_row = [&](int r) -> int64_t {
+            const int hf = r >> 6, tt = r & 63;
+            if (!geo.valid[hf]) return static_cast<int64_t>(-1);
+            if (p.mode == SRK_MODE_WINDOWS) return geo.base[hf] + tt;
+            int yy = geo.y0[hf] + (tt >> 3);
+            if (yy >= p.H) yy -= p.H;
+            int xx = geo.x0[hf] + (tt & 7);
+            if (xx >= p.W) xx -= p.W;
+            return geo.base[hf] + static_cast<int64_t>(yy) * p.W + xx;
+        };
+        auto ln_tile = [&](int tile) {               // gather + normalise -> x image
+            set_geom(tile);
+            ln_rows_to_image(p.x, p.ld_in, p.apply_ln, xa, cw8, lane, tok_of_row);
             fence_proxy_async_smem();
             mbar_arrive(&bars[B_XA]);
+        };
+        stagger_start(p.stagger);
+        if (static_cast<int>(blockIdx.x) < p.n_tiles) ln_tile(blockIdx.x);
 
+        int it = 0;
+        unsigned long long* dbg = threadIdx.x == 64 ? p.dbg : nullptr;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            SRK_TL(dbg, it, 0);
+            set_geom(tile);
             // mask bits of this row (closed form of calculate_mask, network_swinir.py:216-237)
             const int gw_row = tile * 2 + half;
             uint32_t mh = 0xffu, mw = 0xffu;
@@ -392,125 +435,138 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_attn_kernel(const AttnParams
                 }
             }
             const bool masked = (mh & mw) != 0xffu;
-            const uint32_t mh_g = mh >> (4 * g);
             const float* emask = nullptr;
             if (p.mask_mode == SRK_MASK_EXPLICIT && gw_row < p.total_windows)
-                emask = p.mask + (static_cast<int64_t>(gw_row % p.mask_nw) * 64 + t) * 64 + 32 * g;
+                emask = p.mask + (static_cast<int64_t>(gw_row % p.mask_nw) * 64 + t) * 64;
 
-            // ---- phase 1: V^T accumulators -> V^T image (thread = v-dim row, group g = tokens 64 g .. 64 g + 63)
+            // ---- phase 1: V^T accumulators -> V^T image (thread = v-dim row, group g = tokens 64 g .. 64 g + 63).
+            //      The v bias is folded into the proj bias at pack time (softmax rows sum to one).
             mbar_wait(&bars[B_VTF], ph_vtf); ph_vtf ^= 1;
             tc_fence_after();
+            SRK_TL(dbg, it, 2);
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
                 if (m == 0 || q < 2) {      // v-dims 192..255 are padding
                     const int vrow = m * 128 + row;
-                    const float bv = s_vec[SRK_AV_BIAS_V + vrow];
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
                         uint32_t v[32];
                         tmem_ld32(tmem + lanebase + (m ? TC_VT1 : TC_VT0) + 64 * g + 32 * c, v);
                         tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + bv);
-                        store_row_chunks(vt + g * VT_ATOM, vrow, c * 4, v, nullptr, 1.0f);
+                        store_row_chunks<false, false>(vt + g * VT_ATOM, vrow, c * 4, v, nullptr, 1.0f);
                     }
                 }
             }
             tc_fence_before();
             fence_proxy_async_smem();
             mbar_arrive(&bars[B_VTD]);
+            SRK_TL(dbg, it, 3);
 
-            // q (group 0) / k (group 1) accumulators of head h -> [q_h | k_h] image (h & 1)
-            auto qk_epilogue = [&](int h) {
-                mbar_wait(&bars[B_QKF], ph_qkf); ph_qkf ^= 1;
+            float inv_sum[3];
+#pragma unroll
+            for (int hh = 0; hh < 3; ++hh) {
+                const int h = 2 * hh + g;
+                // ---- q,k accumulators of head h -> [q_h | k_h] image of this group.  The k bias is dropped: it shifts
+                //      every logit of a row by the same amount, which the softmax cancels.
+                mbar_wait(bar_qkf, ph_qkf); ph_qkf ^= 1;
                 tc_fence_after();
-                uint32_t v[32];
-                tmem_ld32(tmem + lanebase + TC_QK + 32 * g, v);
-                tmem_ld_wait();
-                store_row_chunks(qki + (h & 1) * ATOM_A, row, g * 4, v,
-                                 s_vec + SRK_AV_BIAS_QK + (h >> 1) * 128 + 64 * g + 32 * (h & 1), 1.0f);
+                {
+                    uint32_t v[32];
+                    tmem_ld32(tmem + lanebase + TC_QK, v);
+                    tmem_ld_wait();
+                    store_row_chunks<true, false>(qki, row, 0, v, s_vec + SRK_AV_BIAS_Q + 32 * h, 1.0f);
+                    tmem_ld32(tmem + lanebase + TC_QK + 32, v);
+                    tmem_ld_wait();
+                    store_row_chunks<false, false>(qki, row, 4, v, nullptr, 1.0f);
+                }
                 tc_fence_before();
                 fence_proxy_async_smem();
-                mbar_arrive(&bars[B_QKR]);
-            };
-            qk_epilogue(0);
-            qk_epilogue(1);
+                mbar_arrive(bar_qkr);
+                SRK_TL(dbg, it, 4 + 3 * hh);
 
-#pragma unroll 1
-            for (int h = 0; h < 6; ++h) {
-                // ---- softmax of this row over keys 32 g .. 32 g + 31 of its own window; merged with the other group
-                const uint32_t scol = (h & 1) ? TC_S1 : TC_S0;
-                mbar_wait(&bars[(h & 1) ? B_SF1 : B_SF0], ph_sf[h & 1]); ph_sf[h & 1] ^= 1;
+                // ---- softmax of this row over the 64 keys of its own window (exp2 domain; log2 e folded into Wq, rpb)
+                mbar_wait(bar_sf, ph_sf); ph_sf ^= 1;
                 tc_fence_after();
-                uint32_t v[32];
-                tmem_ld32(tmem + lanebase + scol + 64 * half + 32 * g, v);
+                SRK_TL(dbg, it, 5 + 3 * hh);
+                uint32_t v0[32], v1[32];
+                tmem_ld32(tmem + lanebase + scol + 64 * half, v0);
+                tmem_ld32(tmem + lanebase + scol + 64 * half + 32, v1);
                 tmem_ld_wait();
                 const float* rpb = s_vec + SRK_AV_RPB + h * SRK_AV_RPB_STRIDE + rpb_base;
-                float s[32];
-                float mx = -INFINITY;
+                float s[64];
 #pragma unroll
-                for (int jx = 0; jx < 32; ++jx) s[jx] = __uint_as_float(v[jx]) + rpb[-(15 * (jx >> 3) + (jx & 7))];
+                for (int jx = 0; jx < 64; ++jx)
+                    s[jx] = __uint_as_float(jx < 32 ? v0[jx] : v1[jx - 32]) + rpb[-(15 * (jx >> 3) + (jx & 7))];
                 if (masked) {
 #pragma unroll
-                    for (int jx = 0; jx < 32; ++jx)
-                        if (!(((mh_g >> (jx >> 3)) & (mw >> (jx & 7))) & 1u)) s[jx] += -100.0f * LOG2E;
+                    for (int jx = 0; jx < 64; ++jx)
+                        if (!(((mh >> (jx >> 3)) & (mw >> (jx & 7))) & 1u)) s[jx] += -100.0f * LOG2E;
                 }
                 if (emask) {
 #pragma unroll
-                    for (int jx = 0; jx < 32; jx += 4) {
+                    for (int jx = 0; jx < 64; jx += 4) {
                         const float4 mk = __ldg(reinterpret_cast<const float4*>(emask + jx));
-                        s[jx] += mk.x * LOG2E; s[jx + 1] += mk.y * LOG2E; s[jx + 2] += mk.z * LOG2E; s[jx + 3] += mk.w * LOG2E;
+                        s[jx] = fmaf(mk.x, LOG2E, s[jx]); s[jx + 1] = fmaf(mk.y, LOG2E, s[jx + 1]);
+                        s[jx + 2] = fmaf(mk.z, LOG2E, s[jx + 2]); s[jx + 3] = fmaf(mk.w, LOG2E, s[jx + 3]);
                     }
                 }
+                float mx = s[0];
 #pragma unroll
-                for (int jx = 0; jx < 32; ++jx) mx = fmaxf(mx, s[jx]);
-                s_max[((h & 1) * 2 + g) * 128 + row] = mx;
-                named_bar_sync(2 + q, 64);                       // the two warps (groups) of this lane quadrant
-                mx = fmaxf(mx, s_max[((h & 1) * 2 + (1 - g)) * 128 + row]);
-                float sum = 0.f;
-                uint32_t pw[16];
+                for (int jx = 1; jx < 64; ++jx) mx = fmaxf(mx, s[jx]);
+                float sum0 = 0.f, sum1 = 0.f;
+                uint32_t pw[32];
 #pragma unroll
-                for (int jx = 0; jx < 32; jx += 2) {
+                for (int jx = 0; jx < 64; jx += 2) {
                     const float e0 = ex2_approx(s[jx] - mx), e1 = ex2_approx(s[jx + 1] - mx);
-                    sum += e0 + e1;
+                    sum0 += e0; sum1 += e1;
                     pw[jx >> 1] = pack_bf16x2(e0, e1);
                 }
-                s_sum[(g * 6 + h) * 128 + row] = sum;
-                uint32_t zeros[16];
+                inv_sum[hh] = __frcp_rn(sum0 + sum1);
+                uint32_t zeros[32];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) zeros[i] = 0u;
-                tmem_st16(tmem + lanebase + scol + 32 * half + 16 * g, pw);          // P aliases the S columns
-                tmem_st16(tmem + lanebase + scol + 32 * (1 - half) + 16 * g, zeros); // other window's keys
+                for (int i = 0; i < 32; ++i) zeros[i] = 0u;
+                tmem_st32(tmem + lanebase + scol + 32 * half, pw);            // P aliases the S columns
+                tmem_st32(tmem + lanebase + scol + 32 * (1 - half), zeros);   // the other window's keys
                 tmem_st_wait();
                 tc_fence_before();
-                mbar_arrive(&bars[(h & 1) ? B_PR1 : B_PR0]);
-                if (h + 2 < 6) qk_epilogue(h + 2);
+                mbar_arrive(bar_pr);
+                SRK_TL(dbg, it, 6 + 3 * hh);
             }
 
-            // ---- phase 4: O accumulators / row sums -> O image (overwrites the x image); group g = heads 3g..3g+2
-            named_bar_sync(2 + q, 64);                            // partial sums of the other group visible
+            // ---- phase 4: O accumulators / row sums -> O image (in the V^T region); this group's own heads
             mbar_wait(&bars[B_OF], ph_of); ph_of ^= 1;
             tc_fence_after();
+            SRK_TL(dbg, it, 23);
 #pragma unroll
             for (int hh = 0; hh < 3; ++hh) {
-                const int h = 3 * g + hh;
-                const float inv = 1.0f / (s_sum[h * 128 + row] + s_sum[(6 + h) * 128 + row]);
+                const int h = 2 * hh + g;
                 uint32_t v[32];
                 tmem_ld32(tmem + lanebase + TC_O + 32 * h, v);
                 tmem_ld_wait();
-                store_row_chunks(xa + (h >> 1) * ATOM_A, row, (h & 1) * 4, v, nullptr, inv);
+                store_row_chunks<false, true>(vt + (h >> 1) * ATOM_A, row, (h & 1) * 4, v, nullptr, inv_sum[hh]);
             }
             tc_fence_before();
             fence_proxy_async_smem();
             mbar_arrive(&bars[B_OR]);
+            SRK_TL(dbg, it, 24);
+
+            // ---- every GEMM that reads the x image is complete: normalise the next tile while proj runs, so that the
+            //      next tile's V^T / q|k GEMMs overlap this tile's store phase
+            int64_t toks_cur[8];
+#pragma unroll
+            for (int i8 = 0; i8 < 8; ++i8) toks_cur[i8] = tok_of_row(q * 32 + i8 * 4 + (lane >> 3));
+            if (tile + static_cast<int>(gridDim.x) < p.n_tiles) ln_tile(tile + gridDim.x);
+            SRK_TL(dbg, it, 25);
 
             // ---- phase 5: proj accumulators + bias + shortcut -> y (window reverse + un-shift in the store)
-            store_rows_coalesced(tmem + TC_PROJ, lanebase, stage_buf, 6 + g, s_vec + SRK_AV_BIAS_PROJ, p.x, p.ld_in, p.y, p.ld_out,
-                                 p.add_residual, row, wg, g, lane, tok_of_row, [&]() {
+            store_rows_coalesced(tmem + TC_PROJ, lanebase, stage_buf, s_vec + SRK_AV_BIAS_PROJ, p.x, p.ld_in, p.y, p.ld_out,
+                                 p.add_residual, q, g, lane, [&](int r) { return toks_cur[((r - q * 32) >> 2)]; }, [&]() {
                                      mbar_wait(&bars[B_PJF], ph_pjf); ph_pjf ^= 1;
                                      tc_fence_after();
+                                     SRK_TL(dbg, it, 26);
                                  });
             tc_fence_before();
+            SRK_TL(dbg, it, 27);
         }
     }
     tc_fence_before();
@@ -521,7 +577,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_attn_kernel(const AttnParams
 // ------------------------------------------------------------------------------------------------
 // K2: MLP half
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t M_XA = 0;                           // LN2(x) image [128 x 192]
+constexpr uint32_t M_XA = 0;                           // normalised x image [128 x 192]
 constexpr uint32_t M_H = M_XA + 3 * ATOM_A;            // gelu(fc1) image [128 x 384] = 6 k-atoms; later the transposers
 constexpr uint32_t M_RING = M_H + 6 * ATOM_A;
 constexpr uint32_t M_VEC = M_RING + RING_N * RING_STAGE;
@@ -533,13 +589,12 @@ constexpr uint32_t TC_F1A = 0, TC_F1B = 128;   // fc1 accumulators of one 128-un
 constexpr uint32_t TC_F2 = 256;                // fc2 accumulator, 192 cols
 enum { MB_FULL = 0, MB_EMPTY = 3, MB_XA = 6, MB_F1A = 7, MB_F1B = 8, MB_HR0 = 9, MB_HR1 = 10, MB_HR2 = 11, MB_F2 = 12, MB_COUNT = 13 };
 
-// gelu(x) = x Phi(x).  Phi(x) = 0.5 (1 + erf(x / sqrt 2)) is evaluated as 0.5 (1 + tanh(u (c1 + c3 u^2 + c5 u^4))),
-// u = clamp(x, +-8): minimax fit, |error| <= 2.6e-5 on the GELU output for all x, plus the MUFU.TANH error (2^-11 rel.)
+// gelu(x) = x Phi(x).  Phi(x) = 0.5 (1 + erf(x / sqrt 2)) is evaluated as 0.5 (1 + tanh(x (c1 + c3 u + c5 u^2))),
+// u = min(x^2, 64): minimax fit, |error| <= 2.6e-5 on the GELU output for all x, plus the MUFU.TANH error (2^-11 rel.)
 // -- both far below the bf16 rounding (2^-9 rel.) applied to the result right after.  One MUFU per element.
 __device__ __forceinline__ float gelu_fast(float x) {
-    const float u = fminf(fmaxf(x, -8.0f), 8.0f);
-    const float u2 = u * u;
-    const float qv = u * fmaf(u2, fmaf(u2, -3.51517176e-04f, 3.70056486e-02f), 7.97507881e-01f);
+    const float u2 = fminf(x * x, 64.0f);
+    const float qv = x * fmaf(u2, fmaf(u2, -3.51517176e-04f, 3.70056486e-02f), 7.97507881e-01f);
     const float hx = 0.5f * x;
     return fmaf(hx, tanh_approx(qv), hx);
 }
@@ -622,22 +677,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_mlp_kernel(const MlpParams p
         }
         __syncwarp();
     } else {
-        const int cw8 = warp - 2, g = cw8 >> 2, wg = cw8 & 3, q = warp & 3, row = q * 32 + lane;
+        const int cw8 = warp - 2, g = cw8 >> 2, q = warp & 3, row = q * 32 + lane;
         const uint32_t lanebase = static_cast<uint32_t>(q * 32) << 16;
         const uint32_t xa = sbase + M_XA, hi = sbase + M_H;
-        float* stage_buf = reinterpret_cast<float*>(sm + M_H + g * (3 * ATOM_A));
+        float* stage_buf = reinterpret_cast<float*>(sm + M_H + cw8 * STAGE_WARP_BYTES);
         uint32_t ph_f1[2] = {0, 0}, ph_f2 = 0, nchunk = 0;
         auto ln_tile = [&](int tile) {
             auto tok_of_row = [&](int r) -> int64_t {
                 const int64_t tk = static_cast<int64_t>(tile) * 128 + r;
                 return tk < p.num_tokens ? tk : static_cast<int64_t>(-1);
             };
-            ln_rows_to_image(p.x, p.ld_in, s_vec + SRK_MV_LN_W, s_vec + SRK_MV_LN_B, p.apply_ln, xa, cw8, lane, tok_of_row);
+            ln_rows_to_image(p.x, p.ld_in, p.apply_ln, xa, cw8, lane, tok_of_row);
             fence_proxy_async_smem();
             mbar_arrive(&bars[MB_XA]);
         };
+        stagger_start(p.stagger);
         if (static_cast<int>(blockIdx.x) < p.n_tiles) ln_tile(blockIdx.x);
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        int it = 0;
+        unsigned long long* dbg = threadIdx.x == 64 ? p.dbg : nullptr;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            SRK_TL(dbg, it, 0);
             auto tok_of_row = [&](int r) -> int64_t {
                 const int64_t tk = static_cast<int64_t>(tile) * 128 + r;
                 return tk < p.num_tokens ? tk : static_cast<int64_t>(-1);
@@ -649,29 +708,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_mlp_kernel(const MlpParams p
                 ++nchunk;
                 mbar_wait(&bars[buf ? MB_F1B : MB_F1A], ph_f1[buf]); ph_f1[buf] ^= 1;
                 tc_fence_after();
+                SRK_TL(dbg, it, 1 + 2 * c);
 #pragma unroll
                 for (int cc = 0; cc < 2; ++cc) {
                     uint32_t v[32];
                     tmem_ld32(tmem + lanebase + (buf ? TC_F1B : TC_F1A) + 64 * g + 32 * cc, v);
                     tmem_ld_wait();
-                    const float* b1 = s_vec + SRK_MV_B1 + 128 * c + 64 * g + 32 * cc;
+                    const float4* b1 = reinterpret_cast<const float4*>(s_vec + SRK_MV_B1 + 128 * c + 64 * g + 32 * cc);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(gelu_fast(__uint_as_float(v[i]) + b1[i]));
-                    store_row_chunks(hi + (2 * c + g) * ATOM_A, row, cc * 4, v, nullptr, 1.0f);
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 b = b1[i];
+                        v[4 * i + 0] = __float_as_uint(gelu_fast(__uint_as_float(v[4 * i + 0]) + b.x));
+                        v[4 * i + 1] = __float_as_uint(gelu_fast(__uint_as_float(v[4 * i + 1]) + b.y));
+                        v[4 * i + 2] = __float_as_uint(gelu_fast(__uint_as_float(v[4 * i + 2]) + b.z));
+                        v[4 * i + 3] = __float_as_uint(gelu_fast(__uint_as_float(v[4 * i + 3]) + b.w));
+                    }
+                    store_row_chunks<false, false>(hi + (2 * c + g) * ATOM_A, row, cc * 4, v, nullptr, 1.0f);
                 }
                 tc_fence_before();
                 fence_proxy_async_smem();
                 mbar_arrive(&bars[MB_HR0 + c]);
+                SRK_TL(dbg, it, 2 + 2 * c);
             }
-            // ---- the x image is free (all fc1 GEMMs of this tile are complete): LayerNorm the next tile while fc2 runs
+            // ---- the x image is free (all fc1 GEMMs of this tile are complete): normalise the next tile while fc2 runs
             if (tile + static_cast<int>(gridDim.x) < p.n_tiles) ln_tile(tile + gridDim.x);
+            SRK_TL(dbg, it, 7);
             // ---- fc2 accumulators + b2 + shortcut -> y
-            store_rows_coalesced(tmem + TC_F2, lanebase, stage_buf, 6 + g, s_vec + SRK_MV_B2, p.x, p.ld_in, p.y, p.ld_out,
-                                 p.add_residual, row, wg, g, lane, tok_of_row, [&]() {
+            store_rows_coalesced(tmem + TC_F2, lanebase, stage_buf, s_vec + SRK_MV_B2, p.x, p.ld_in, p.y, p.ld_out,
+                                 p.add_residual, q, g, lane, tok_of_row, [&]() {
                                      mbar_wait(&bars[MB_F2], ph_f2); ph_f2 ^= 1;
                                      tc_fence_after();
+                                     SRK_TL(dbg, it, 8);
                                  });
             tc_fence_before();
+            SRK_TL(dbg, it, 9);
         }
     }
     tc_fence_before();

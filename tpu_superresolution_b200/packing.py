@@ -7,7 +7,10 @@ the exact order the kernel's producer warp streams them (csrc/swin_kernels.cu).
 
 Folded at pack time: q scale (head_dim**-0.5, network_swinir.py:86,124) and log2(e) for the
 exp2-domain softmax into Wq/bq; log2(e) into the relative-position-bias table; head_dim 30 -> 32 and
-C 180 -> 192 zero padding; W_proj columns re-indexed to the padded head layout.
+C 180 -> 192 zero padding; W_proj columns re-indexed to the padded head layout; LayerNorm's gamma into the
+columns of the following weight and beta into its bias (the kernels only compute (x - mean) * rstd); the k bias
+is dropped (it adds the same q.b_k to every logit of a row, which softmax cancels); the v bias moves into the
+proj bias (softmax rows sum to one, so P (V + 1 b_v^T) = P V + b_v^T).
 """
 from __future__ import annotations
 
@@ -71,12 +74,17 @@ def pack_attention(qkv_w, qkv_b, proj_w, proj_b, rpb_table, ln_w=None, ln_b=None
         raise RuntimeError(f"unsupported attention geometry qkv {tuple(qkv_w.shape)} proj {tuple(proj_w.shape)} "
                            f"rpb {tuple(rpb_table.shape)}: kernels serve dim 180 / 6 heads / window 8 only")
     scale = (L.HEAD_DIM ** -0.5) if scale is None else float(scale)
-    qkv_w = qkv_w.detach().float()
-    qkv_b = torch.zeros(3 * C, device=dev) if qkv_b is None else qkv_b.detach().float()
-    wq = _pad_cols(_pad_heads(qkv_w[:C] * (scale * LOG2E)), L.DIM_PAD)          # (192, 192)
-    wk = _pad_cols(_pad_heads(qkv_w[C:2 * C]), L.DIM_PAD)
-    wv = _pad_cols(_pad_heads(qkv_w[2 * C:]), L.DIM_PAD)
-    bq, bk, bv = _pad_heads(qkv_b[:C] * (scale * LOG2E)), _pad_heads(qkv_b[C:2 * C]), _pad_heads(qkv_b[2 * C:])
+    qkv_w = qkv_w.detach().double()
+    qkv_b = torch.zeros(3 * C, device=dev, dtype=torch.float64) if qkv_b is None else qkv_b.detach().double()
+    gamma = torch.ones(C, device=dev, dtype=torch.float64) if ln_w is None else ln_w.detach().double()
+    beta = torch.zeros(C, device=dev, dtype=torch.float64) if ln_b is None else ln_b.detach().double()
+    qkv_b = qkv_b + qkv_w @ beta                     # LN beta -> bias
+    qkv_w = qkv_w * gamma[None, :]                   # LN gamma -> weight columns
+    wq = _pad_cols(_pad_heads((qkv_w[:C] * (scale * LOG2E)).float()), L.DIM_PAD)          # (192, 192)
+    wk = _pad_cols(_pad_heads(qkv_w[C:2 * C].float()), L.DIM_PAD)
+    wv = _pad_cols(_pad_heads(qkv_w[2 * C:].float()), L.DIM_PAD)
+    bq = _pad_heads((qkv_b[:C] * (scale * LOG2E)).float())
+    proj_b_eff = (proj_b.detach().double() + proj_w.detach().double() @ qkv_b[2 * C:]).float()   # v bias -> proj bias
 
     slabs = []
     wv256 = wv.new_zeros(256, L.DIM_PAD)
@@ -95,14 +103,8 @@ def pack_attention(qkv_w, qkv_b, proj_w, proj_b, rpb_table, ln_w=None, ln_b=None
     assert wstream.numel() == L.ATTN_WSTREAM_BYTES
 
     vec = torch.zeros(L.ATTN_VEC_FLOATS, device=dev, dtype=torch.float32)
-    vec[L.AV_LN_W:L.AV_LN_W + C] = 1.0 if ln_w is None else ln_w.detach().float()
-    if ln_b is not None:
-        vec[L.AV_LN_B:L.AV_LN_B + C] = ln_b.detach().float()
-    vec[L.AV_BIAS_V:L.AV_BIAS_V + 192] = bv
-    for p in range(3):
-        vec[L.AV_BIAS_QK + 128 * p:L.AV_BIAS_QK + 128 * p + 64] = bq[64 * p:64 * p + 64]
-        vec[L.AV_BIAS_QK + 128 * p + 64:L.AV_BIAS_QK + 128 * p + 128] = bk[64 * p:64 * p + 64]
-    vec[L.AV_BIAS_PROJ:L.AV_BIAS_PROJ + C] = proj_b.detach().float()
+    vec[L.AV_BIAS_Q:L.AV_BIAS_Q + 192] = bq
+    vec[L.AV_BIAS_PROJ:L.AV_BIAS_PROJ + C] = proj_b_eff
     rpb = vec[L.AV_RPB:L.AV_RPB + L.HEADS * L.AV_RPB_STRIDE].view(L.HEADS, L.AV_RPB_STRIDE)
     rpb[:, :225] = rpb_table.detach().float().t() * LOG2E
     return wstream, vec
@@ -116,8 +118,14 @@ def pack_mlp(fc1_w, fc1_b, fc2_w, fc2_b, ln_w=None, ln_b=None) -> Tuple[torch.Te
     if tuple(fc1_w.shape) != (Hd, C) or tuple(fc2_w.shape) != (C, Hd):
         raise RuntimeError(f"unsupported MLP geometry fc1 {tuple(fc1_w.shape)} fc2 {tuple(fc2_w.shape)}: "
                            "kernels serve dim 180 / mlp_ratio 2 only")
+    f1 = fc1_w.detach().double()
+    b1 = torch.zeros(Hd, device=dev, dtype=torch.float64) if fc1_b is None else fc1_b.detach().double()
+    if ln_b is not None:
+        b1 = b1 + f1 @ ln_b.detach().double()        # LN beta -> bias
+    if ln_w is not None:
+        f1 = f1 * ln_w.detach().double()[None, :]    # LN gamma -> weight columns
     w1 = fc1_w.new_zeros(L.HIDDEN_PAD, L.DIM_PAD, dtype=torch.float32)
-    w1[:Hd, :C] = fc1_w.detach().float()
+    w1[:Hd, :C] = f1.float()
     w2 = fc2_w.new_zeros(L.DIM_PAD, L.HIDDEN_PAD, dtype=torch.float32)
     w2[:C, :Hd] = fc2_w.detach().float()
     slabs = []
@@ -127,11 +135,7 @@ def pack_mlp(fc1_w, fc1_b, fc2_w, fc2_b, ln_w=None, ln_b=None) -> Tuple[torch.Te
     wstream = torch.cat([s.reshape(-1) for s in slabs]).contiguous().view(torch.uint8)
     assert wstream.numel() == L.MLP_WSTREAM_BYTES
     vec = torch.zeros(L.MLP_VEC_FLOATS, device=dev, dtype=torch.float32)
-    vec[L.MV_LN_W:L.MV_LN_W + C] = 1.0 if ln_w is None else ln_w.detach().float()
-    if ln_b is not None:
-        vec[L.MV_LN_B:L.MV_LN_B + C] = ln_b.detach().float()
-    if fc1_b is not None:
-        vec[L.MV_B1:L.MV_B1 + Hd] = fc1_b.detach().float()
+    vec[L.MV_B1:L.MV_B1 + Hd] = b1.float()
     if fc2_b is not None:
         vec[L.MV_B2:L.MV_B2 + C] = fc2_b.detach().float()
     return wstream, vec
