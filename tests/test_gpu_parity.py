@@ -177,3 +177,22 @@ def test_unsupported_geometry_is_an_error():
         blk(torch.zeros(1, 12 * 12, 180, device="cuda"), (12, 12))
     with pytest.raises(RuntimeError):
         blk(torch.zeros(1, 256, 180, device="cuda", dtype=torch.float16), (16, 16))
+
+
+def test_tiled_inference_matches_per_tile_oracle_and_shards_bit_identically():
+    """BASELINE.json configs[4] at a reduced size: overlapping 64-px tiles, E / W stitch, N logical ranks on one GPU."""
+    from tpu_superresolution_b200 import tiling
+    m, cfg, sd = _model("swinir_x4_d2", "init", 1234)
+    lr = synth.make_lr_batch(1, 136, 120, seed=9)
+    res = tiling.TiledSuperResolver(m, scale=4, tile=64, overlap=8, batch=16)
+    full = res(lr.cuda())
+    assert full.shape == (1, 3, 544, 480)
+    E, Wt = torch.zeros(3, 544, 480), torch.zeros(544, 480)
+    for t in tiling.plan_tiles(136, 120, 64, 8):
+        y = O.swinir_forward(lr[:, :, t.y0:t.y0 + 64, t.x0:t.x0 + 64], sd, cfg)[0]
+        E[:, 4 * t.y0:4 * t.y0 + 256, 4 * t.x0:4 * t.x0 + 256] += y
+        Wt[4 * t.y0:4 * t.y0 + 256, 4 * t.x0:4 * t.x0 + 256] += 1
+    assert (full[0].cpu() - E / Wt).abs().max().item() <= 2e-3
+    for world in (2, 4):
+        bands = [res.band(lr.cuda(), r, world)[0] for r in range(world)]
+        assert torch.equal(torch.cat(bands, dim=1), full[0])

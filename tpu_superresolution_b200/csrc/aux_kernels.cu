@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) stitch_accumulate_kernel(const float* __r
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per; i += gridDim.x * blockDim.x) {
         const int ty = i / tile_w, tx = i - ty * tile_w;
         const int oy = y0 + ty, ox = x0 + tx;
-        if (oy >= out_h || ox >= out_w) continue;
+        if (oy < 0 || ox < 0 || oy >= out_h || ox >= out_w) continue;   // rows of a seam tile outside this rank's band
         const int64_t o = static_cast<int64_t>(oy) * out_w + ox;
         for (int c = 0; c < channels; ++c) E[static_cast<int64_t>(c) * out_h * out_w + o] += src[c * per + i];
         Wt[o] += 1.0f;
