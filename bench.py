@@ -209,6 +209,13 @@ def run_ours(args):
             _barrier(world)
             return sum(a.elapsed_time(b) for a, b in evs) / 1e3        # seconds of device time in the K steps
 
+    with torch.no_grad():                       # a benchmark of a wrong result is worthless: check the output first
+        y_chk = step_resident(0)
+        torch.cuda.synchronize()
+        if not bool(torch.isfinite(y_chk).all()) or not (0.0 < float(y_chk.mean()) < 1.0):
+            raise SystemExit("bench.py: model output is not finite / out of range; refusing to time it")
+        del y_chk
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()

@@ -113,6 +113,28 @@ def test_block_kat_vs_golden(tag, b_idx, shift, res, x_size):
     assert torch.equal(y2, y)
 
 
+@pytest.mark.parametrize("shift", [0, 4])
+def test_block_at_bench_scale_many_tiles_per_cta(shift):
+    """B=16 x 64x64 = 512 attention tiles / 512 MLP tiles on 148 persistent CTAs: exercises the cross-tile pipeline
+    (next-tile normalisation and GEMMs overlapping the store phase).  Repeated to shake out timing-dependent races."""
+    sd = _stress_sd()
+    b_idx = 1 if shift else 0
+    blk = srk.SwinTransformerBlock(180, (64, 64), 6, window_size=8, shift_size=shift, mlp_ratio=2.0).eval()
+    st = _block_sd(sd, f"layers.0.residual_group.blocks.{b_idx}.")
+    if shift:
+        st["attn_mask"] = blk.attn_mask.clone()
+    blk.load_state_dict(st, strict=True)
+    blk.cuda()
+    xt = synth.make_tokens(16, 64, 64, 180, seed=21)
+    ref = O.swin_block(xt[[0, 7, 15]], (64, 64), sd, f"layers.0.residual_group.blocks.{b_idx}.", 6, 8, shift)
+    xc = xt.cuda()
+    y0 = blk(xc, (64, 64))
+    assert torch.isfinite(y0).all()
+    assert _rel(y0[[0, 7, 15]], ref) < 1.5e-2
+    for _ in range(20):
+        assert torch.equal(blk(xc, (64, 64)), y0), "non-deterministic result: race between tiles"
+
+
 def test_rstb_kat_vs_golden():
     g = np.load(os.path.join(GOLDEN, "kat_rstb.npz"))
     sd = _stress_sd()

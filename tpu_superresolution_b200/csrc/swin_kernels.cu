@@ -566,6 +566,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_attn_kernel(const AttnParams
                                      SRK_TL(dbg, it, 26);
                                  });
             tc_fence_before();
+            // all transposers (V^T region) are drained before any warp writes the next tile's V^T image over them
+            named_bar_sync(1, NROWTHREADS);
             SRK_TL(dbg, it, 27);
         }
     }
@@ -741,6 +743,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_mlp_kernel(const MlpParams p
                                      SRK_TL(dbg, it, 8);
                                  });
             tc_fence_before();
+            // all transposers (H region) are drained before any warp writes the next tile's H image over them
+            named_bar_sync(1, NROWTHREADS);
             SRK_TL(dbg, it, 9);
         }
     }
