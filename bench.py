@@ -83,6 +83,7 @@ def _dist_setup(n_gpus: int):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = os.environ.get("SRK_NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     return world, rank, local
@@ -253,8 +254,12 @@ def run_ours(args):
         with open(tpath) as f:
             traffic = json.load(f).get("swin_attn_kernel_dram_bytes_per_launch")
 
-    cpu_val, cores, cpu_s = cpu_oracle_rate(tiles=TILES_PER_STEP if (os.cpu_count() or 1) >= 16 else 4)
     cpu_tiles = TILES_PER_STEP if (os.cpu_count() or 1) >= 16 else 4
+    cpu_baseline = None                         # reported at N = 1 only (driver contract)
+    if world == 1:
+        cpu_val, cores, cpu_s = cpu_oracle_rate(tiles=cpu_tiles)
+        cpu_baseline = {"value": cpu_val, "unit": "Mpix/s", "cores": cores, "kind": "port",
+                        "sample": f"{cpu_tiles} of the {TILES_PER_STEP} tiles of one step, fp32 oracle port (torch CPU ops), {cpu_s:.1f} s"}
 
     ms_step = t_res / args.steps * 1e3
     value = world * mpix_step * args.steps / t_res
@@ -280,8 +285,7 @@ def run_ours(args):
                                                            "achieved": FLOP_PER_TOKEN_MLP * tokens / (mlp_ms * 1e-3) / 1e12,
                                                            "frac": FLOP_PER_TOKEN_MLP * tokens / (mlp_ms * 1e-3) / 1e12 / peak_tf}},
                      "libsrk_ms_per_step": sum(v[0] * v[1] for v in kstats.values()) / 3.0},
-        "cpu_baseline": {"value": cpu_val, "unit": "Mpix/s", "cores": cores, "kind": "port",
-                         "sample": f"{cpu_tiles} of the {TILES_PER_STEP} tiles of one step, fp32 oracle port (torch CPU ops), {cpu_s:.1f} s"},
+        "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(out))
     if world > 1:
