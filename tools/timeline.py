@@ -22,10 +22,13 @@ lib = L.load()
 buf = torch.zeros(512, dtype=torch.int64, device="cuda")
 aw, av = blk.attn._packed(blk.norm1)
 mw, mv = blk.mlp._packed(blk.norm2)
-names1 = {0: "tile start", 1: "LN done", 2: "VTF seen", 3: "VT epi done", 4: "QKep0,1 done", 23: "OF seen", 24: "O epi done", 25: "PJF seen", 26: "store done",
-          32: "MMA tile start", 33: "MMA XA seen", 34: "MMA VT issued", 41: "MMA PV5 issued", 42: "MMA OR seen", 43: "MMA proj issued"}
+names1 = {0: "tile start", 2: "VTF seen", 3: "VT epi done", 23: "OF seen", 24: "O epi done", 25: "LN(next) done", 26: "PJF seen",
+          27: "store done", 32: "MMA tile start", 33: "MMA XA seen", 34: "MMA VT issued", 41: "MMA PV5 issued", 42: "MMA OR seen",
+          43: "MMA proj issued"}
+for hh in range(3):
+    names1[4 + 3 * hh] = f"g0 QKep(h{2*hh}) done"; names1[5 + 3 * hh] = f"g0 SF(h{2*hh}) seen"; names1[6 + 3 * hh] = f"g0 softmax(h{2*hh}) done"
 for h in range(6):
-    names1[5 + 3 * h] = f"SF{h} seen"; names1[6 + 3 * h] = f"softmax{h} done"; names1[7 + 3 * h] = f"QKep{h+2} done"; names1[35 + h] = f"MMA QKR{h} seen"
+    names1[35 + h] = f"MMA QKR{h} seen"
 names2 = {0: "tile start", 1: "F1c0 seen", 2: "gelu0 done", 3: "F1c1 seen", 4: "gelu1 done", 5: "F1c2 seen", 6: "gelu2 done", 7: "LN next done", 8: "F2 seen", 9: "store done"}
 for which, names in (("attn", names1), ("mlp", names2)):
     buf.zero_()

@@ -69,15 +69,18 @@ def pack_attention(qkv_w, qkv_b, proj_w, proj_b, rpb_table, ln_w=None, ln_b=None
     ln_w/ln_b (180) or None for the identity (WindowAttention used stand-alone).
     """
     dev = qkv_w.device
+    # pack on the host (dozens of tiny index ops; one H2D copy of the result instead of hundreds of launches)
+    qkv_w, qkv_b, proj_w, proj_b, rpb_table, ln_w, ln_b = [None if t is None else t.detach().cpu() for t in
+                                                           (qkv_w, qkv_b, proj_w, proj_b, rpb_table, ln_w, ln_b)]
     C = L.DIM
     if tuple(qkv_w.shape) != (3 * C, C) or tuple(proj_w.shape) != (C, C) or tuple(rpb_table.shape) != (225, L.HEADS):
         raise RuntimeError(f"unsupported attention geometry qkv {tuple(qkv_w.shape)} proj {tuple(proj_w.shape)} "
                            f"rpb {tuple(rpb_table.shape)}: kernels serve dim 180 / 6 heads / window 8 only")
     scale = (L.HEAD_DIM ** -0.5) if scale is None else float(scale)
     qkv_w = qkv_w.detach().double()
-    qkv_b = torch.zeros(3 * C, device=dev, dtype=torch.float64) if qkv_b is None else qkv_b.detach().double()
-    gamma = torch.ones(C, device=dev, dtype=torch.float64) if ln_w is None else ln_w.detach().double()
-    beta = torch.zeros(C, device=dev, dtype=torch.float64) if ln_b is None else ln_b.detach().double()
+    qkv_b = torch.zeros(3 * C, dtype=torch.float64) if qkv_b is None else qkv_b.detach().double()
+    gamma = torch.ones(C, dtype=torch.float64) if ln_w is None else ln_w.detach().double()
+    beta = torch.zeros(C, dtype=torch.float64) if ln_b is None else ln_b.detach().double()
     qkv_b = qkv_b + qkv_w @ beta                     # LN beta -> bias
     qkv_w = qkv_w * gamma[None, :]                   # LN gamma -> weight columns
     wq = _pad_cols(_pad_heads((qkv_w[:C] * (scale * LOG2E)).float()), L.DIM_PAD)          # (192, 192)
@@ -102,24 +105,26 @@ def pack_attention(qkv_w, qkv_b, proj_w, proj_b, rpb_table, ln_w=None, ln_b=None
     wstream = torch.cat([s.reshape(-1) for s in slabs]).contiguous().view(torch.uint8)
     assert wstream.numel() == L.ATTN_WSTREAM_BYTES
 
-    vec = torch.zeros(L.ATTN_VEC_FLOATS, device=dev, dtype=torch.float32)
+    vec = torch.zeros(L.ATTN_VEC_FLOATS, dtype=torch.float32)
     vec[L.AV_BIAS_Q:L.AV_BIAS_Q + 192] = bq
     vec[L.AV_BIAS_PROJ:L.AV_BIAS_PROJ + C] = proj_b_eff
     rpb = vec[L.AV_RPB:L.AV_RPB + L.HEADS * L.AV_RPB_STRIDE].view(L.HEADS, L.AV_RPB_STRIDE)
     rpb[:, :225] = rpb_table.detach().float().t() * LOG2E
-    return wstream, vec
+    return wstream.to(dev), vec.to(dev)
 
 
 @torch.no_grad()
 def pack_mlp(fc1_w, fc1_b, fc2_w, fc2_b, ln_w=None, ln_b=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """fc1 (360,180), fc2 (180,360) -> (wstream uint8[MLP_WSTREAM_BYTES], vec float32[MLP_VEC_FLOATS])."""
     dev = fc1_w.device
+    fc1_w, fc1_b, fc2_w, fc2_b, ln_w, ln_b = [None if t is None else t.detach().cpu() for t in
+                                              (fc1_w, fc1_b, fc2_w, fc2_b, ln_w, ln_b)]
     C, Hd = L.DIM, L.HIDDEN
     if tuple(fc1_w.shape) != (Hd, C) or tuple(fc2_w.shape) != (C, Hd):
         raise RuntimeError(f"unsupported MLP geometry fc1 {tuple(fc1_w.shape)} fc2 {tuple(fc2_w.shape)}: "
                            "kernels serve dim 180 / mlp_ratio 2 only")
     f1 = fc1_w.detach().double()
-    b1 = torch.zeros(Hd, device=dev, dtype=torch.float64) if fc1_b is None else fc1_b.detach().double()
+    b1 = torch.zeros(Hd, dtype=torch.float64) if fc1_b is None else fc1_b.detach().double()
     if ln_b is not None:
         b1 = b1 + f1 @ ln_b.detach().double()        # LN beta -> bias
     if ln_w is not None:
@@ -134,8 +139,8 @@ def pack_mlp(fc1_w, fc1_b, fc2_w, fc2_b, ln_w=None, ln_b=None) -> Tuple[torch.Te
     slabs += _slabs(w2)
     wstream = torch.cat([s.reshape(-1) for s in slabs]).contiguous().view(torch.uint8)
     assert wstream.numel() == L.MLP_WSTREAM_BYTES
-    vec = torch.zeros(L.MLP_VEC_FLOATS, device=dev, dtype=torch.float32)
+    vec = torch.zeros(L.MLP_VEC_FLOATS, dtype=torch.float32)
     vec[L.MV_B1:L.MV_B1 + Hd] = b1.float()
     if fc2_b is not None:
         vec[L.MV_B2:L.MV_B2 + C] = fc2_b.detach().float()
-    return wstream, vec
+    return wstream.to(dev), vec.to(dev)
