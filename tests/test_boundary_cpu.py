@@ -113,9 +113,9 @@ def test_pack_mlp_reconstructs_reference_math(with_ln):
     pre = blk + "mlp."
     ln = (sd[blk + "norm2.weight"], sd[blk + "norm2.bias"]) if with_ln else (None, None)
     w, vec = packing.pack_mlp(sd[pre + "fc1.weight"], sd[pre + "fc1.bias"], sd[pre + "fc2.weight"], sd[pre + "fc2.bias"], *ln)
-    slabs = _unpack_slabs(w, [128] * 9 + [192] * 6)
-    w1 = torch.cat([torch.cat(slabs[3 * c:3 * c + 3], 1) for c in range(3)], 0)         # (384, 192)
-    w2 = torch.cat(slabs[9:15], 1)                                                       # (192, 384)
+    slabs = _unpack_slabs(w, [128] * 6 + [192] * 2 + [128] * 3 + [192] * 4)
+    w1 = torch.cat([torch.cat(slabs[0:3], 1), torch.cat(slabs[3:6], 1), torch.cat(slabs[8:11], 1)], 0)   # (384, 192)
+    w2 = torch.cat(slabs[6:8] + slabs[11:15], 1)                                         # (192, 384)
     x = synth.make_tokens(1, 8, 8, 180, seed=7)[0]
     xhat = (x - x.mean(-1, keepdim=True)) / torch.sqrt(x.var(-1, unbiased=False, keepdim=True) + 1e-5) if with_ln else x
     xb = torch.zeros(64, 192)

@@ -18,20 +18,21 @@ B = int(os.environ.get("KB_BATCH", "16"))
 NX = int(os.environ.get("KB_NX", "3"))
 xs = [synth.make_tokens(B, 64, 64, 180, seed=i).cuda() for i in range(NX)]
 y = torch.empty_like(xs[0])
+INPLACE = os.environ.get('KB_INPLACE', '1') == '1'
 aw, av = blk.attn._packed(blk.norm1)
 mw, mv = blk.mlp._packed(blk.norm2)
 lib = L.load()
 
 def run(kind, n=30):
     for i in range(5):
-        (L.swin_attn(xs[i % NX], y, aw, av, mode=L.MODE_IMAGE, batch=B, height=64, width=64, ld_in=180, ld_out=180, shift=4, mask_mode=L.MASK_SHIFT)
-         if kind == "attn" else L.swin_mlp(xs[i % NX], y, mw, mv, num_tokens=B * 4096, ld_in=180, ld_out=180))
+        (L.swin_attn(xs[i % NX], xs[i % NX] if INPLACE else y, aw, av, mode=L.MODE_IMAGE, batch=B, height=64, width=64, ld_in=180, ld_out=180, shift=4, mask_mode=L.MASK_SHIFT)
+         if kind == "attn" else L.swin_mlp(xs[i % NX], xs[i % NX] if INPLACE else y, mw, mv, num_tokens=B * 4096, ld_in=180, ld_out=180))
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(n):
-        (L.swin_attn(xs[i % NX], y, aw, av, mode=L.MODE_IMAGE, batch=B, height=64, width=64, ld_in=180, ld_out=180, shift=4, mask_mode=L.MASK_SHIFT)
-         if kind == "attn" else L.swin_mlp(xs[i % NX], y, mw, mv, num_tokens=B * 4096, ld_in=180, ld_out=180))
+        (L.swin_attn(xs[i % NX], xs[i % NX] if INPLACE else y, aw, av, mode=L.MODE_IMAGE, batch=B, height=64, width=64, ld_in=180, ld_out=180, shift=4, mask_mode=L.MASK_SHIFT)
+         if kind == "attn" else L.swin_mlp(xs[i % NX], xs[i % NX] if INPLACE else y, mw, mv, num_tokens=B * 4096, ld_in=180, ld_out=180))
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n * 1e3

@@ -78,6 +78,13 @@ int srk_swin_attn_fwd(const SrkSwinAttnDesc* d, const float* x, float* y, const 
     if (d->mask_mode == SRK_MASK_SHIFT && d->shift == 0 && d->mode == SRK_MODE_IMAGE) p.mask_mode = SRK_MASK_NONE;
     if (d->mask_mode == SRK_MASK_SHIFT && d->mode == SRK_MODE_WINDOWS) p.shift = SRK_WINDOW / 2;   // regions of the shifted grid
     p.n_tiles = (p.total_windows + 1) / 2;
+    if (d->add_residual && x != y) {
+        // the kernel adds into y (bulk reduce-add): start from y = x
+        if (d->ld_in != d->ld_out) return fail("srk_swin_attn_fwd: out-of-place residual needs ld_in == ld_out");
+        const size_t bytes = static_cast<size_t>(p.total_windows) * 64 * d->ld_in * sizeof(float);
+        cudaError_t e = cudaMemcpyAsync(y, x, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream));
+        if (e != cudaSuccess) return fail("srk_swin_attn_fwd: %s", cudaGetErrorString(e));
+    }
     p.dbg = srk::g_timeline;
     p.stagger = p.n_tiles >= 2 * 148 ? srk::g_stagger_attn : 0;
     return check(srk::launch_swin_attn(p, static_cast<cudaStream_t>(stream)), "srk_swin_attn_fwd");
@@ -94,6 +101,12 @@ int srk_swin_mlp_fwd(const SrkMlpDesc* d, const float* x, float* y, const void* 
     p.x = x; p.y = y; p.wstream = static_cast<const uint8_t*>(wstream); p.vec = vec;
     p.num_tokens = d->num_tokens; p.n_tiles = static_cast<int>((d->num_tokens + 127) / 128);
     p.ld_in = d->ld_in; p.ld_out = d->ld_out; p.apply_ln = d->apply_ln; p.add_residual = d->add_residual;
+    if (d->add_residual && x != y) {
+        if (d->ld_in != d->ld_out) return fail("srk_swin_mlp_fwd: out-of-place residual needs ld_in == ld_out");
+        cudaError_t e = cudaMemcpyAsync(y, x, static_cast<size_t>(d->num_tokens) * d->ld_in * sizeof(float), cudaMemcpyDeviceToDevice,
+                                        static_cast<cudaStream_t>(stream));
+        if (e != cudaSuccess) return fail("srk_swin_mlp_fwd: %s", cudaGetErrorString(e));
+    }
     p.dbg = srk::g_timeline;
     p.stagger = p.n_tiles >= 2 * 148 ? srk::g_stagger_mlp : 0;
     return check(srk::launch_swin_mlp(p, static_cast<cudaStream_t>(stream)), "srk_swin_mlp_fwd");

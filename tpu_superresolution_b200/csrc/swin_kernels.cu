@@ -31,8 +31,6 @@ constexpr uint32_t ATOM_A = 16384;      // 128 rows x 128 B: one k-atom of a 128
 constexpr uint32_t VT_ATOM = 24576;     // 192 rows x 128 B: one k-atom (64 keys) of the V^T image
 constexpr uint32_t RING_STAGE = 24576;  // largest weight slab (192 rows x 64 k)
 constexpr int RING_N = 3;
-constexpr int STAGE_LD = 36;            // fp32 words per row of the store transposer (conflict-free float4)
-constexpr uint32_t STAGE_WARP_BYTES = 32 * STAGE_LD * 4;   // warp-private 32 x 32 fp32 transposer
 
 constexpr uint32_t IDESC_128x128 = umma_idesc_bf16(128, 128);
 constexpr uint32_t IDESC_128x192 = umma_idesc_bf16(128, 192);
@@ -149,58 +147,72 @@ __device__ __forceinline__ void store_row_chunks(uint32_t img_atom, uint32_t row
     }
 }
 
-// Final epilogue shared by K1/K2.  Each warp owns the 32 accumulator rows of its TMEM lane quadrant and the columns
-// [96 g, 96 g + 96) of its group: TMEM -> (+bias) -> warp-private shared-memory transposer (32 x 32 fp32, only
-// __syncwarp) -> coalesced (+ shortcut) global store, 4 rows x 128 B per warp instruction.  The shortcut loads of
-// whole 96-column slice are issued before `wait_acc()` so their latency hides behind the last GEMM.
-template <typename TokFn, typename WaitFn>
-__device__ __forceinline__ void store_rows_coalesced(uint32_t tmem_acc, uint32_t lanebase, float* stage, const float* s_bias,
-                                                     const float* __restrict__ x, int ld_in, float* __restrict__ y, int ld_out,
-                                                     int add_residual, int q, int g, int lane, TokFn tok_of_row, WaitFn wait_acc) {
-    int64_t toks[8];
-#pragma unroll
-    for (int it = 0; it < 8; ++it) toks[it] = tok_of_row(q * 32 + it * 4 + (lane >> 3));
-    const int c4 = lane & 7;
-    float4 sc[3][8];
-#pragma unroll
-    for (int ci = 0; ci < 3; ++ci) {
-        const int ch = 32 * (3 * g + ci) + 4 * c4;
-#pragma unroll
-        for (int it = 0; it < 8; ++it)
-            sc[ci][it] = (add_residual && ch < SRK_DIM && toks[it] >= 0)
-                             ? __ldg(reinterpret_cast<const float4*>(x + toks[it] * ld_in + ch))
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
+// Final epilogue shared by K1/K2: accumulator (+bias) -> fp32 rows staged in shared memory in the exact global row
+// layout (720 B per token row) -> the TMA engine writes them out with one bulk copy per contiguous run of tokens.
+// With add_residual the copy is `cp.reduce.async.bulk ... add.f32`: the residual stream is updated in place
+// (y += delta), so the shortcut is never loaded into the SM.  Thread = accumulator row; the two groups fill columns
+// [96 g, 96 g + 96) of the same rows.  `half` / `nhalf` let a caller with < 92 KB of staging do the 32 rows of each
+// lane quadrant in two passes of 16.
+constexpr uint32_t ROW_BYTES = SRK_DIM * 4;     // 720
+template <typename TokFn>
+__device__ __forceinline__ void stage_rows_and_bulk_store(uint32_t tmem_acc, uint32_t lanebase, uint8_t* stage_base, const float* s_bias,
+                                                          float* __restrict__ y, int ld_out, int add_residual, int q, int g, int lane,
+                                                          int nhalf, bool dedicated, TokFn tok_of_row) {
+    const int rows_per_pass = 32 / nhalf;
+    if (dedicated) {
+        // the staging rows are private to this phase: only the previous tile's copies may still be reading them
+        if (g == 0) bulk_wait_read0();
+        named_bar_sync(2 + q, 64);
     }
-    wait_acc();
+    for (int hlf = 0; hlf < nhalf; ++hlf) {
+        uint8_t* stage_q = stage_base + q * (rows_per_pass * ROW_BYTES);
+        const bool mine = nhalf == 1 || (lane >> 4) == hlf;
+        float* dst = reinterpret_cast<float*>(stage_q + (lane & (rows_per_pass - 1)) * ROW_BYTES);
 #pragma unroll
-    for (int ci = 0; ci < 3; ++ci) {
-        const int c = 3 * g + ci;
-        uint32_t v[32];
-        tmem_ld32(tmem_acc + lanebase + 32 * c, v);
-        tmem_ld_wait();
+        for (int ci = 0; ci < 3; ++ci) {
+            const int c = 3 * g + ci;
+            uint32_t v[32];
+            tmem_ld32(tmem_acc + lanebase + 32 * c, v);
+            tmem_ld_wait();
+            if (mine) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float4 b = reinterpret_cast<const float4*>(s_bias + 32 * c)[k];
-            float4 o;
-            o.x = __uint_as_float(v[4 * k + 0]) + b.x;
-            o.y = __uint_as_float(v[4 * k + 1]) + b.y;
-            o.z = __uint_as_float(v[4 * k + 2]) + b.z;
-            o.w = __uint_as_float(v[4 * k + 3]) + b.w;
-            *reinterpret_cast<float4*>(stage + lane * STAGE_LD + 4 * k) = o;
-        }
-        __syncwarp();
-        const int ch = 32 * c + 4 * c4;
-        if (ch < SRK_DIM) {
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                if (toks[it] >= 0) {
-                    float4 o = *reinterpret_cast<const float4*>(stage + (it * 4 + (lane >> 3)) * STAGE_LD + 4 * c4);
-                    o.x += sc[ci][it].x; o.y += sc[ci][it].y; o.z += sc[ci][it].z; o.w += sc[ci][it].w;
-                    *reinterpret_cast<float4*>(y + toks[it] * ld_out + ch) = o;
+                for (int k = 0; k < 8; ++k) {
+                    if (32 * c + 4 * k < SRK_DIM) {
+                        const float4 b = reinterpret_cast<const float4*>(s_bias + 32 * c)[k];
+                        float4 o;
+                        o.x = __uint_as_float(v[4 * k + 0]) + b.x;
+                        o.y = __uint_as_float(v[4 * k + 1]) + b.y;
+                        o.z = __uint_as_float(v[4 * k + 2]) + b.z;
+                        o.w = __uint_as_float(v[4 * k + 3]) + b.w;
+                        *reinterpret_cast<float4*>(dst + 32 * c + 4 * k) = o;
+                    }
                 }
             }
         }
-        __syncwarp();
+        fence_proxy_async_smem();                   // generic-proxy smem writes -> visible to the bulk copy engine
+        named_bar_sync(2 + q, 64);                  // both groups of this lane quadrant have written their columns
+        if (g == 0) {
+            // one bulk copy per maximal run of tokens that are contiguous in memory
+            const int rowbase = q * 32 + hlf * rows_per_pass;
+            const int64_t tok = lane < rows_per_pass ? tok_of_row(rowbase + lane) : static_cast<int64_t>(-1);
+            const int64_t prev = __shfl_up_sync(0xffffffffu, tok, 1);
+            const bool valid = tok >= 0;
+            const bool start = valid && (lane == 0 || ld_out != SRK_DIM || prev < 0 || tok != prev + 1);
+            const uint32_t m_start = __ballot_sync(0xffffffffu, start);
+            const uint32_t m_stop = m_start | ~__ballot_sync(0xffffffffu, valid);      // next start or first invalid row ends a run
+            if (start) {
+                const uint32_t after = lane == 31 ? 0u : (m_stop >> (lane + 1));
+                const int len = after ? __ffs(after) : (32 - lane);
+                float* gdst = y + tok * ld_out;
+                const uint32_t src = smem_u32(stage_q + lane * ROW_BYTES);
+                if (add_residual) bulk_s2g_add_f32(gdst, src, len * ROW_BYTES);
+                else              bulk_s2g(gdst, src, len * ROW_BYTES);
+                bulk_commit();
+            }
+            if (hlf + 1 < nhalf) bulk_wait_read0();  // staging is reused by the next pass
+            __syncwarp();
+        }
+        if (hlf + 1 < nhalf) named_bar_sync(2 + q, 64);
     }
 }
 
@@ -216,7 +228,7 @@ constexpr uint32_t A_BAR = A_VEC + ((SRK_ATTN_VEC_FLOATS * 4 + 127) / 128) * 128
 constexpr uint32_t A_END = A_BAR + 256;
 constexpr uint32_t K1_SMEM = A_END + 1024;            // + alignment slack
 static_assert(K1_SMEM <= 232448, "K1 shared memory exceeds 227 KB");
-static_assert(8 * STAGE_WARP_BYTES <= 2 * VT_ATOM && 3 * ATOM_A <= 2 * VT_ATOM, "O image / transposers must fit in the V^T image");
+static_assert(64 * 720 <= 2 * VT_ATOM && 3 * ATOM_A <= 2 * VT_ATOM, "O image / store staging must fit in the V^T image");
 
 // TMEM columns (fp32, 128 lanes)
 constexpr uint32_t TC_O = 0;                          // O accumulator, 6 heads x 32; later the proj accumulator (192)
@@ -369,7 +381,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_attn_kernel(const AttnParams
         const int row = q * 32 + lane;              // accumulator row == token row of the tile
         const uint32_t lanebase = static_cast<uint32_t>(q * 32) << 16;
         const uint32_t xa = sbase + A_XA, vt = sbase + A_VT, qki = sbase + A_QKI + g * ATOM_A;
-        float* stage_buf = reinterpret_cast<float*>(sm + A_VT + cw8 * STAGE_WARP_BYTES);
         const int half = row >> 6, t = row & 63;
         const int rpb_base = (t >> 3) * 15 + (t & 7) + 112;
         uint32_t ph_vtf = 0, ph_qkf = 0, ph_sf = 0, ph_of = 0, ph_pjf = 0;
@@ -552,21 +563,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_attn_kernel(const AttnParams
 
             // ---- every GEMM that reads the x image is complete: normalise the next tile while proj runs, so that the
             //      next tile's V^T / q|k GEMMs overlap this tile's store phase
-            int64_t toks_cur[8];
-#pragma unroll
-            for (int i8 = 0; i8 < 8; ++i8) toks_cur[i8] = tok_of_row(q * 32 + i8 * 4 + (lane >> 3));
+            // destination tokens of rows q*32 + lane and q*32 + 16 + lane of THIS tile (ln_tile overwrites the geometry)
+            const int64_t tok_lo = tok_of_row(q * 32 + (lane & 15)), tok_hi = tok_of_row(q * 32 + 16 + (lane & 15));
             if (tile + static_cast<int>(gridDim.x) < p.n_tiles) ln_tile(tile + gridDim.x);
             SRK_TL(dbg, it, 25);
 
-            // ---- phase 5: proj accumulators + bias + shortcut -> y (window reverse + un-shift in the store)
-            store_rows_coalesced(tmem + TC_PROJ, lanebase, stage_buf, s_vec + SRK_AV_BIAS_PROJ, p.x, p.ld_in, p.y, p.ld_out,
-                                 p.add_residual, q, g, lane, [&](int r) { return toks_cur[((r - q * 32) >> 2)]; }, [&]() {
-                                     mbar_wait(&bars[B_PJF], ph_pjf); ph_pjf ^= 1;
-                                     tc_fence_after();
-                                     SRK_TL(dbg, it, 26);
-                                 });
+            // ---- phase 5: proj accumulators + bias -> staged rows -> bulk (reduce-add) store; window reverse + un-shift
+            //      are the destination addresses of the copies.  Staging = the V^T region (two passes of 16 rows).
+            mbar_wait(&bars[B_PJF], ph_pjf); ph_pjf ^= 1;
+            tc_fence_after();
+            SRK_TL(dbg, it, 26);
+            stage_rows_and_bulk_store(tmem + TC_PROJ, lanebase, sm + A_VT, s_vec + SRK_AV_BIAS_PROJ, p.y, p.ld_out, p.add_residual,
+                                      q, g, lane, 2, false, [&](int r) { return ((r - q * 32) & 16) ? tok_hi : tok_lo; });
             tc_fence_before();
-            // all transposers (V^T region) are drained before any warp writes the next tile's V^T image over them
+            // every bulk copy has finished reading the staging rows before any warp writes the next tile's V^T image there
+            if (g == 0) bulk_wait_read0();
             named_bar_sync(1, NROWTHREADS);
             SRK_TL(dbg, it, 27);
         }
@@ -580,14 +591,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_attn_kernel(const AttnParams
 // K2: MLP half
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t M_XA = 0;                           // normalised x image [128 x 192]
-constexpr uint32_t M_H = M_XA + 3 * ATOM_A;            // gelu(fc1) image [128 x 384] = 6 k-atoms; later the transposers
-constexpr uint32_t M_RING = M_H + 6 * ATOM_A;
+constexpr uint32_t M_STAGE = M_XA + 3 * ATOM_A;        // output rows staged for the bulk store (private: copies drain asynchronously)
+constexpr uint32_t M_RING = M_STAGE + 6 * ATOM_A;
 constexpr uint32_t M_VEC = M_RING + RING_N * RING_STAGE;
 constexpr uint32_t M_BAR = M_VEC + ((SRK_MLP_VEC_FLOATS * 4 + 127) / 128) * 128;
 constexpr uint32_t M_END = M_BAR + 256;
 constexpr uint32_t K2_SMEM = M_END + 1024;
 static_assert(K2_SMEM <= 232448, "K2 shared memory exceeds 227 KB");
-constexpr uint32_t TC_F1A = 0, TC_F1B = 128;   // fc1 accumulators of one 128-unit hidden chunk, double buffered
+static_assert(128 * 720 <= 6 * ATOM_A, "store staging size");
+// TMEM: fc1 accumulators of one 128-unit hidden chunk, double buffered.  gelu(fc1) is written back over them as bf16 pairs
+// (group g: fp32 columns [64 g, 64 g + 64) -> packed columns [64 g, 64 g + 32)) and is the A operand of fc2 straight from TMEM.
+constexpr uint32_t TC_F1A = 0, TC_F1B = 128;
 constexpr uint32_t TC_F2 = 256;                // fc2 accumulator, 192 cols
 enum { MB_FULL = 0, MB_EMPTY = 3, MB_XA = 6, MB_F1A = 7, MB_F1B = 8, MB_HR0 = 9, MB_HR1 = 10, MB_HR2 = 11, MB_F2 = 12, MB_COUNT = 13 };
 
@@ -630,8 +644,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_mlp_kernel(const MlpParams p
             uint32_t stage = 0, phase = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                 uint32_t off = 0;
-                for (int s = 0; s < 15; ++s) {      // 9 x 16 KB (fc1, three 128-unit chunks), 6 x 24 KB (fc2)
-                    const uint32_t bytes = s < 9 ? 16384u : 24576u;
+                for (int s = 0; s < 15; ++s) {      // MMA order: fc1 c0, c1 (6 x 16 KB) | fc2 k-atoms 0,1 (2 x 24 KB) | fc1 c2 (3 x 16 KB) | fc2 k-atoms 2..5
+                    const uint32_t bytes = (s < 6 || (s >= 8 && s < 11)) ? 16384u : 24576u;
                     mbar_wait(&bars[MB_EMPTY + stage], phase ^ 1);
                     mbar_arrive_expect_tx(&bars[MB_FULL + stage], bytes);
                     bulk_g2s(sm + M_RING + stage * RING_STAGE, p.wstream + off, bytes, &bars[MB_FULL + stage]);
@@ -645,35 +659,52 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_mlp_kernel(const MlpParams p
         if (lane == 0) {
             uint32_t stage = 0, phase = 0, ph_xa = 0, ph_hr[3] = {0, 0, 0};
             uint32_t nchunk = 0;                              // fc1 chunk counter -> TMEM buffer parity
-            const uint32_t xa = sbase + M_XA, hi = sbase + M_H, ring = sbase + M_RING;
-            auto slab_mma = [&](uint32_t d_tmem, uint32_t a_img, uint32_t idesc, bool first) {
-                mbar_wait(&bars[MB_FULL + stage], phase);
-                tc_fence_after();
-                const uint32_t b = ring + stage * RING_STAGE;
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                    umma_ss(d_tmem, umma_desc_sw128(a_img + ks * 32), umma_desc_sw128(b + ks * 32), idesc, !(first && ks == 0));
-                umma_commit(&bars[MB_EMPTY + stage]);
-                if (++stage == RING_N) { stage = 0; phase ^= 1; }
-            };
-            auto fc1_chunk = [&]() {
+            const uint32_t xa = sbase + M_XA, ring = sbase + M_RING;
+            auto fc1_chunk = [&]() {                            // 128 hidden units: A = x image, B = W1 slab (128 rows)
                 const uint32_t buf = nchunk & 1;
-                for (int ka = 0; ka < 3; ++ka) slab_mma(tmem + (buf ? TC_F1B : TC_F1A), xa + ka * ATOM_A, IDESC_128x128, ka == 0);
+                for (int ka = 0; ka < 3; ++ka) {
+                    mbar_wait(&bars[MB_FULL + stage], phase);
+                    tc_fence_after();
+                    const uint32_t a = xa + ka * ATOM_A, b = ring + stage * RING_STAGE;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma_ss(tmem + (buf ? TC_F1B : TC_F1A), umma_desc_sw128(a + ks * 32), umma_desc_sw128(b + ks * 32), IDESC_128x128,
+                                (ka | ks) != 0);
+                    umma_commit(&bars[MB_EMPTY + stage]);
+                    if (++stage == RING_N) { stage = 0; phase ^= 1; }
+                }
                 umma_commit(&bars[buf ? MB_F1B : MB_F1A]);
                 ++nchunk;
+            };
+            auto fc2_chunk = [&](uint32_t buf, bool first) {    // K = 128 hidden units of one chunk: A = H (TMEM), B = two W2 slabs
+                for (int half = 0; half < 2; ++half) {
+                    mbar_wait(&bars[MB_FULL + stage], phase);
+                    tc_fence_after();
+                    const uint32_t b = ring + stage * RING_STAGE;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma_ts(tmem + TC_F2, tmem + (buf ? TC_F1B : TC_F1A) + 64 * half + 8 * ks, umma_desc_sw128(b + ks * 32), IDESC_128x192,
+                                !(first && half == 0 && ks == 0));
+                    umma_commit(&bars[MB_EMPTY + stage]);
+                    if (++stage == RING_N) { stage = 0; phase ^= 1; }
+                }
             };
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                 mbar_wait(&bars[MB_XA], ph_xa); ph_xa ^= 1;
                 tc_fence_after();
-                fc1_chunk();
-                fc1_chunk();
-                for (int c = 0; c < 3; ++c) {
-                    mbar_wait(&bars[MB_HR0 + c], ph_hr[c]); ph_hr[c] ^= 1;     // H atoms 2c, 2c+1 written; fc1 buffer of chunk c drained
-                    tc_fence_after();
-                    if (c == 0) fc1_chunk();                                   // third hidden chunk reuses chunk 0's buffer
-                    slab_mma(tmem + TC_F2, hi + (2 * c) * ATOM_A, IDESC_128x192, c == 0);
-                    slab_mma(tmem + TC_F2, hi + (2 * c + 1) * ATOM_A, IDESC_128x192, false);
-                }
+                const uint32_t b0 = nchunk & 1;
+                fc1_chunk();                                                   // chunk 0 -> buffer b0
+                fc1_chunk();                                                   // chunk 1 -> buffer b0 ^ 1
+                mbar_wait(&bars[MB_HR0], ph_hr[0]); ph_hr[0] ^= 1;             // H of chunk 0 written over its accumulators
+                tc_fence_after();
+                fc2_chunk(b0, true);
+                fc1_chunk();                                                   // chunk 2 -> buffer b0 (after fc2 consumed H of chunk 0)
+                mbar_wait(&bars[MB_HR1], ph_hr[1]); ph_hr[1] ^= 1;
+                tc_fence_after();
+                fc2_chunk(b0 ^ 1, false);
+                mbar_wait(&bars[MB_HR2], ph_hr[2]); ph_hr[2] ^= 1;
+                tc_fence_after();
+                fc2_chunk(b0, false);
                 umma_commit(&bars[MB_F2]);
             }
         }
@@ -681,8 +712,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_mlp_kernel(const MlpParams p
     } else {
         const int cw8 = warp - 2, g = cw8 >> 2, q = warp & 3, row = q * 32 + lane;
         const uint32_t lanebase = static_cast<uint32_t>(q * 32) << 16;
-        const uint32_t xa = sbase + M_XA, hi = sbase + M_H;
-        float* stage_buf = reinterpret_cast<float*>(sm + M_H + cw8 * STAGE_WARP_BYTES);
+        const uint32_t xa = sbase + M_XA;
         uint32_t ph_f1[2] = {0, 0}, ph_f2 = 0, nchunk = 0;
         auto ln_tile = [&](int tile) {
             auto tok_of_row = [&](int r) -> int64_t {
@@ -711,40 +741,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_mlp_kernel(const MlpParams p
                 mbar_wait(&bars[buf ? MB_F1B : MB_F1A], ph_f1[buf]); ph_f1[buf] ^= 1;
                 tc_fence_after();
                 SRK_TL(dbg, it, 1 + 2 * c);
-#pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem + lanebase + (buf ? TC_F1B : TC_F1A) + 64 * g + 32 * cc, v);
+                {
+                    const uint32_t col = (buf ? TC_F1B : TC_F1A) + 64 * g;
+                    uint32_t v0[32], v1[32];
+                    tmem_ld32(tmem + lanebase + col, v0);
+                    tmem_ld32(tmem + lanebase + col + 32, v1);
                     tmem_ld_wait();
-                    const float4* b1 = reinterpret_cast<const float4*>(s_vec + SRK_MV_B1 + 128 * c + 64 * g + 32 * cc);
+                    const float4* b1 = reinterpret_cast<const float4*>(s_vec + SRK_MV_B1 + 128 * c + 64 * g);
+                    uint32_t hw[32];                               // 64 hidden units of this row as bf16 pairs
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float4 b = b1[i];
-                        v[4 * i + 0] = __float_as_uint(gelu_fast(__uint_as_float(v[4 * i + 0]) + b.x));
-                        v[4 * i + 1] = __float_as_uint(gelu_fast(__uint_as_float(v[4 * i + 1]) + b.y));
-                        v[4 * i + 2] = __float_as_uint(gelu_fast(__uint_as_float(v[4 * i + 2]) + b.z));
-                        v[4 * i + 3] = __float_as_uint(gelu_fast(__uint_as_float(v[4 * i + 3]) + b.w));
+                        hw[2 * i] = pack_bf16x2(gelu_fast(__uint_as_float(v0[4 * i + 0]) + b.x), gelu_fast(__uint_as_float(v0[4 * i + 1]) + b.y));
+                        hw[2 * i + 1] = pack_bf16x2(gelu_fast(__uint_as_float(v0[4 * i + 2]) + b.z), gelu_fast(__uint_as_float(v0[4 * i + 3]) + b.w));
                     }
-                    store_row_chunks<false, false>(hi + (2 * c + g) * ATOM_A, row, cc * 4, v, nullptr, 1.0f);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 b = b1[8 + i];
+                        hw[16 + 2 * i] = pack_bf16x2(gelu_fast(__uint_as_float(v1[4 * i + 0]) + b.x), gelu_fast(__uint_as_float(v1[4 * i + 1]) + b.y));
+                        hw[16 + 2 * i + 1] = pack_bf16x2(gelu_fast(__uint_as_float(v1[4 * i + 2]) + b.z), gelu_fast(__uint_as_float(v1[4 * i + 3]) + b.w));
+                    }
+                    tmem_st32(tmem + lanebase + col, hw);          // H aliases the first half of this thread's own accumulator columns
+                    tmem_st_wait();
                 }
                 tc_fence_before();
-                fence_proxy_async_smem();
                 mbar_arrive(&bars[MB_HR0 + c]);
                 SRK_TL(dbg, it, 2 + 2 * c);
             }
             // ---- the x image is free (all fc1 GEMMs of this tile are complete): normalise the next tile while fc2 runs
             if (tile + static_cast<int>(gridDim.x) < p.n_tiles) ln_tile(tile + gridDim.x);
             SRK_TL(dbg, it, 7);
-            // ---- fc2 accumulators + b2 + shortcut -> y
-            store_rows_coalesced(tmem + TC_F2, lanebase, stage_buf, s_vec + SRK_MV_B2, p.x, p.ld_in, p.y, p.ld_out,
-                                 p.add_residual, q, g, lane, tok_of_row, [&]() {
-                                     mbar_wait(&bars[MB_F2], ph_f2); ph_f2 ^= 1;
-                                     tc_fence_after();
-                                     SRK_TL(dbg, it, 8);
-                                 });
+            // ---- fc2 accumulators + b2 -> staged rows (private staging) -> bulk (reduce-add) store, drained asynchronously
+            mbar_wait(&bars[MB_F2], ph_f2); ph_f2 ^= 1;
+            tc_fence_after();
+            SRK_TL(dbg, it, 8);
+            stage_rows_and_bulk_store(tmem + TC_F2, lanebase, sm + M_STAGE, s_vec + SRK_MV_B2, p.y, p.ld_out, p.add_residual, q, g, lane, 1,
+                                      true, tok_of_row);
             tc_fence_before();
-            // all transposers (H region) are drained before any warp writes the next tile's H image over them
-            named_bar_sync(1, NROWTHREADS);
             SRK_TL(dbg, it, 9);
         }
     }

@@ -133,10 +133,9 @@ def pack_mlp(fc1_w, fc1_b, fc2_w, fc2_b, ln_w=None, ln_b=None) -> Tuple[torch.Te
     w1[:Hd, :C] = f1.float()
     w2 = fc2_w.new_zeros(L.DIM_PAD, L.HIDDEN_PAD, dtype=torch.float32)
     w2[:C, :Hd] = fc2_w.detach().float()
-    slabs = []
-    for c in range(3):                                   # fc1 in three 128-unit hidden chunks
-        slabs += _slabs(w1[128 * c:128 * (c + 1)])
-    slabs += _slabs(w2)
+    f1 = [_slabs(w1[128 * c:128 * (c + 1)]) for c in range(3)]     # fc1 in three 128-unit hidden chunks (3 k-atoms each)
+    f2 = _slabs(w2)                                                  # fc2: 6 k-atoms of 64 hidden units
+    slabs = f1[0] + f1[1] + f2[0:2] + f1[2] + f2[2:6]               # the order the MMA warp consumes them
     wstream = torch.cat([s.reshape(-1) for s in slabs]).contiguous().view(torch.uint8)
     assert wstream.numel() == L.MLP_WSTREAM_BYTES
     vec = torch.zeros(L.MLP_VEC_FLOATS, dtype=torch.float32)
