@@ -25,8 +25,9 @@
 
 namespace srk {
 
-constexpr int NTHREADS = 320;
+constexpr int NTHREADS = 320;          // K2: producer + MMA + 8 row warps
 constexpr int NROWTHREADS = 256;
+constexpr int K1_THREADS = 448;        // K1: + 4 utility warps (q|k epilogues, next-tile normalisation)
 constexpr uint32_t ATOM_A = 16384;      // 128 rows x 128 B: one k-atom of a 128-row operand image
 constexpr uint32_t VT_ATOM = 24576;     // 192 rows x 128 B: one k-atom (64 keys) of the V^T image
 constexpr uint32_t RING_STAGE = 24576;  // largest weight slab (192 rows x 64 k)
@@ -154,65 +155,53 @@ __device__ __forceinline__ void store_row_chunks(uint32_t img_atom, uint32_t row
 // [96 g, 96 g + 96) of the same rows.  `half` / `nhalf` let a caller with < 92 KB of staging do the 32 rows of each
 // lane quadrant in two passes of 16.
 constexpr uint32_t ROW_BYTES = SRK_DIM * 4;     // 720
+// Staging geometry: rows 0 .. main_rows-1 of every lane quadrant live at stage_main + (q * main_rows + r) * 720, the
+// remaining rows at stage_tail + (q * (32 - main_rows) + r - main_rows) * 720 (K1 has no single 92 KB hole).
 template <typename TokFn>
-__device__ __forceinline__ void stage_rows_and_bulk_store(uint32_t tmem_acc, uint32_t lanebase, uint8_t* stage_base, const float* s_bias,
-                                                          float* __restrict__ y, int ld_out, int add_residual, int q, int g, int lane,
-                                                          int nhalf, bool dedicated, TokFn tok_of_row) {
-    const int rows_per_pass = 32 / nhalf;
-    if (dedicated) {
-        // the staging rows are private to this phase: only the previous tile's copies may still be reading them
-        if (g == 0) bulk_wait_read0();
-        named_bar_sync(2 + q, 64);
+__device__ __forceinline__ void stage_rows_and_bulk_store(uint32_t tmem_acc, uint32_t lanebase, uint8_t* stage_main, uint8_t* stage_tail,
+                                                          int main_rows, const float* s_bias, float* __restrict__ y, int ld_out,
+                                                          int add_residual, int q, int g, int lane, TokFn tok_of_row) {
+    uint8_t* const my_row = lane < main_rows ? stage_main + (q * main_rows + lane) * ROW_BYTES
+                                             : stage_tail + (q * (32 - main_rows) + lane - main_rows) * ROW_BYTES;
+    float* dst = reinterpret_cast<float*>(my_row);
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) {
+        const int c = 3 * g + ci;
+        uint32_t v[32];
+        tmem_ld32(tmem_acc + lanebase + 32 * c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (32 * c + 4 * k < SRK_DIM) {
+                const float4 b = reinterpret_cast<const float4*>(s_bias + 32 * c)[k];
+                float4 o;
+                o.x = __uint_as_float(v[4 * k + 0]) + b.x;
+                o.y = __uint_as_float(v[4 * k + 1]) + b.y;
+                o.z = __uint_as_float(v[4 * k + 2]) + b.z;
+                o.w = __uint_as_float(v[4 * k + 3]) + b.w;
+                *reinterpret_cast<float4*>(dst + 32 * c + 4 * k) = o;
+            }
+        }
     }
-    for (int hlf = 0; hlf < nhalf; ++hlf) {
-        uint8_t* stage_q = stage_base + q * (rows_per_pass * ROW_BYTES);
-        const bool mine = nhalf == 1 || (lane >> 4) == hlf;
-        float* dst = reinterpret_cast<float*>(stage_q + (lane & (rows_per_pass - 1)) * ROW_BYTES);
-#pragma unroll
-        for (int ci = 0; ci < 3; ++ci) {
-            const int c = 3 * g + ci;
-            uint32_t v[32];
-            tmem_ld32(tmem_acc + lanebase + 32 * c, v);
-            tmem_ld_wait();
-            if (mine) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    if (32 * c + 4 * k < SRK_DIM) {
-                        const float4 b = reinterpret_cast<const float4*>(s_bias + 32 * c)[k];
-                        float4 o;
-                        o.x = __uint_as_float(v[4 * k + 0]) + b.x;
-                        o.y = __uint_as_float(v[4 * k + 1]) + b.y;
-                        o.z = __uint_as_float(v[4 * k + 2]) + b.z;
-                        o.w = __uint_as_float(v[4 * k + 3]) + b.w;
-                        *reinterpret_cast<float4*>(dst + 32 * c + 4 * k) = o;
-                    }
-                }
-            }
+    fence_proxy_async_smem();                   // generic-proxy smem writes -> visible to the bulk copy engine
+    named_bar_sync(2 + q, 64);                  // both groups of this lane quadrant have written their columns
+    if (g == 0) {
+        // one bulk copy per maximal run of tokens that are contiguous in memory (and in the staging buffer)
+        const int64_t tok = tok_of_row(q * 32 + lane);
+        const int64_t prev = __shfl_up_sync(0xffffffffu, tok, 1);
+        const bool valid = tok >= 0;
+        const bool start = valid && (lane == 0 || lane == main_rows || ld_out != SRK_DIM || prev < 0 || tok != prev + 1);
+        const uint32_t m_start = __ballot_sync(0xffffffffu, start);
+        const uint32_t m_stop = m_start | ~__ballot_sync(0xffffffffu, valid);      // next start or first invalid row ends a run
+        if (start) {
+            const uint32_t after = lane == 31 ? 0u : (m_stop >> (lane + 1));
+            const int len = after ? __ffs(after) : (32 - lane);
+            float* gdst = y + tok * ld_out;
+            if (add_residual) bulk_s2g_add_f32(gdst, smem_u32(my_row), len * ROW_BYTES);
+            else              bulk_s2g(gdst, smem_u32(my_row), len * ROW_BYTES);
+            bulk_commit();
         }
-        fence_proxy_async_smem();                   // generic-proxy smem writes -> visible to the bulk copy engine
-        named_bar_sync(2 + q, 64);                  // both groups of this lane quadrant have written their columns
-        if (g == 0) {
-            // one bulk copy per maximal run of tokens that are contiguous in memory
-            const int rowbase = q * 32 + hlf * rows_per_pass;
-            const int64_t tok = lane < rows_per_pass ? tok_of_row(rowbase + lane) : static_cast<int64_t>(-1);
-            const int64_t prev = __shfl_up_sync(0xffffffffu, tok, 1);
-            const bool valid = tok >= 0;
-            const bool start = valid && (lane == 0 || ld_out != SRK_DIM || prev < 0 || tok != prev + 1);
-            const uint32_t m_start = __ballot_sync(0xffffffffu, start);
-            const uint32_t m_stop = m_start | ~__ballot_sync(0xffffffffu, valid);      // next start or first invalid row ends a run
-            if (start) {
-                const uint32_t after = lane == 31 ? 0u : (m_stop >> (lane + 1));
-                const int len = after ? __ffs(after) : (32 - lane);
-                float* gdst = y + tok * ld_out;
-                const uint32_t src = smem_u32(stage_q + lane * ROW_BYTES);
-                if (add_residual) bulk_s2g_add_f32(gdst, src, len * ROW_BYTES);
-                else              bulk_s2g(gdst, src, len * ROW_BYTES);
-                bulk_commit();
-            }
-            if (hlf + 1 < nhalf) bulk_wait_read0();  // staging is reused by the next pass
-            __syncwarp();
-        }
-        if (hlf + 1 < nhalf) named_bar_sync(2 + q, 64);
+        __syncwarp();
     }
 }
 
@@ -224,11 +213,12 @@ constexpr uint32_t A_VT = A_XA + 3 * ATOM_A;          // V^T image [192 x 128 ke
 constexpr uint32_t A_QKI = A_VT + 2 * VT_ATOM;        // 2 x [q_h | k_h] images [128 x (32+32)] (one per softmax group)
 constexpr uint32_t A_RING = A_QKI + 2 * ATOM_A;       // weight ring
 constexpr uint32_t A_VEC = A_RING + RING_N * RING_STAGE;
-constexpr uint32_t A_BAR = A_VEC + ((SRK_ATTN_VEC_FLOATS * 4 + 127) / 128) * 128;
+constexpr uint32_t A_TAIL = A_VEC + ((SRK_ATTN_VEC_FLOATS * 4 + 127) / 128) * 128;   // staging rows 28..31 of each quadrant
+constexpr uint32_t A_BAR = A_TAIL + 16 * 720;
 constexpr uint32_t A_END = A_BAR + 256;
 constexpr uint32_t K1_SMEM = A_END + 1024;            // + alignment slack
 static_assert(K1_SMEM <= 232448, "K1 shared memory exceeds 227 KB");
-static_assert(64 * 720 <= 2 * VT_ATOM && 3 * ATOM_A <= 2 * VT_ATOM, "O image / store staging must fit in the V^T image");
+static_assert(112 * 720 <= 2 * VT_ATOM + 2 * ATOM_A && 3 * ATOM_A <= 2 * VT_ATOM, "O image / store staging must fit");
 
 // TMEM columns (fp32, 128 lanes)
 constexpr uint32_t TC_O = 0;                          // O accumulator, 6 heads x 32; later the proj accumulator (192)
@@ -238,8 +228,8 @@ constexpr uint32_t TC_VT0 = 192, TC_VT1 = 320;        // V^T accumulators (befor
 constexpr uint32_t TC_PROJ = 0;
 
 enum {  // K1 barrier slots
-    B_FULL = 0, B_EMPTY = 3, B_XA = 6, B_VTF = 7, B_VTD = 8, B_QKF0 = 9, B_QKF1 = 10, B_QKR0 = 11, B_QKR1 = 12, B_SF0 = 13,
-    B_SF1 = 14, B_PR0 = 15, B_PR1 = 16, B_OF = 17, B_OR = 18, B_PJF = 19, B_COUNT = 20
+    B_FULL = 0, B_EMPTY = 3, B_XA = 6, B_VTF = 7, B_VTD = 8, B_QKF = 9, B_QKR = 10, B_SF0 = 11, B_SF1 = 12, B_PR0 = 13, B_PR1 = 14,
+    B_OF = 15, B_OR = 16, B_PJF = 17, B_DRAIN = 18, B_COUNT = 19
 };
 
 struct TileGeom {
@@ -247,8 +237,23 @@ struct TileGeom {
     int y0[2], x0[2];
     bool valid[2];
 };
+__device__ __forceinline__ void set_tile_geom(const AttnParams& p, int tile, TileGeom& geo) {
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+        const int gw = tile * 2 + hf;
+        geo.valid[hf] = gw < p.total_windows;
+        if (p.mode == SRK_MODE_WINDOWS) {
+            geo.base[hf] = static_cast<int64_t>(gw) * 64; geo.y0[hf] = 0; geo.x0[hf] = 0;
+        } else {
+            const int b = gw / p.nw_img, w = gw - b * p.nw_img;
+            const int wy = w / p.nwx, wx = w - wy * p.nwx;
+            geo.base[hf] = static_cast<int64_t>(b) * p.H * p.W;
+            geo.y0[hf] = wy * 8 + p.shift; geo.x0[hf] = wx * 8 + p.shift;
+        }
+    }
+}
 
-__global__ void __launch_bounds__(NTHREADS, 1) swin_attn_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t sbase = (raw + 1023u) & ~1023u;
@@ -262,11 +267,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_attn_kernel(const AttnParams
     for (int i = threadIdx.x; i < SRK_ATTN_VEC_FLOATS; i += blockDim.x) s_vec[i] = p.vec[i];
     if (threadIdx.x == 0) {
         for (int i = 0; i < RING_N; ++i) { mbar_init(&bars[B_FULL + i], 1); mbar_init(&bars[B_EMPTY + i], 1); }
-        mbar_init(&bars[B_XA], NROWTHREADS); mbar_init(&bars[B_VTF], 1);    mbar_init(&bars[B_VTD], NROWTHREADS);
-        mbar_init(&bars[B_QKF0], 1);         mbar_init(&bars[B_QKF1], 1);   mbar_init(&bars[B_QKR0], 128);
-        mbar_init(&bars[B_QKR1], 128);       mbar_init(&bars[B_SF0], 1);    mbar_init(&bars[B_SF1], 1);
+        mbar_init(&bars[B_XA], 128);         mbar_init(&bars[B_VTF], 1);    mbar_init(&bars[B_VTD], NROWTHREADS);
+        mbar_init(&bars[B_QKF], 1);          mbar_init(&bars[B_QKR], 128);  mbar_init(&bars[B_SF0], 1);    mbar_init(&bars[B_SF1], 1);
         mbar_init(&bars[B_PR0], 128);        mbar_init(&bars[B_PR1], 128);  mbar_init(&bars[B_OF], 1);
-        mbar_init(&bars[B_OR], NROWTHREADS); mbar_init(&bars[B_PJF], 1);
+        mbar_init(&bars[B_OR], NROWTHREADS); mbar_init(&bars[B_PJF], 1);    mbar_init(&bars[B_DRAIN], 128);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -281,8 +285,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_attn_kernel(const AttnParams
             uint32_t stage = 0, phase = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                 uint32_t off = 0;
-                for (int s = 0; s < 27; ++s) {      // 6 x 16 KB (V^T), 18 x 8 KB (q|k per head), 3 x 24 KB (proj)
-                    const uint32_t bytes = s < 6 ? 16384u : (s < 24 ? 8192u : 24576u);
+                for (int s = 0; s < 15; ++s) {      // 6 x 16 KB (V^T k-atoms), 6 x 24 KB (q|k of one head: 3 k-atoms x 64 rows), 3 x 24 KB (proj)
+                    const uint32_t bytes = s < 6 ? 16384u : 24576u;
                     mbar_wait(&bars[B_EMPTY + stage], phase ^ 1);
                     mbar_arrive_expect_tx(&bars[B_FULL + stage], bytes);
                     bulk_g2s(sm + A_RING + stage * RING_STAGE, p.wstream + off, bytes, &bars[B_FULL + stage]);
@@ -296,7 +300,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_attn_kernel(const AttnParams
         // ===================================================== MMA issuer
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            uint32_t ph_xa = 0, ph_vtd = 0, ph_qkr[2] = {0, 0}, ph_pr[2] = {0, 0}, ph_or = 0;
+            uint32_t ph_xa = 0, ph_vtd = 0, ph_qkr = 0, ph_pr[2] = {0, 0}, ph_or = 0;
             const uint32_t xa = sbase + A_XA, vt = sbase + A_VT, qki = sbase + A_QKI, ring = sbase + A_RING;
             // one GEMM over K = 192: 3 ring slabs x 4 k-steps
             auto gemm_k192 = [&](uint32_t d_tmem, uint32_t img, bool img_is_a, uint32_t idesc) {
@@ -311,6 +315,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_attn_kernel(const AttnParams
                     umma_commit(&bars[B_EMPTY + stage]);
                     if (++stage == RING_N) { stage = 0; phase ^= 1; }
                 }
+            };
+            auto gemm_qk = [&]() {             // [q_h | k_h] = xhat * W^T, N = 64; the three k-atoms of W arrive as one ring stage
+                mbar_wait(&bars[B_FULL + stage], phase);
+                tc_fence_after();
+                const uint32_t w = ring + stage * RING_STAGE;
+#pragma unroll
+                for (int ka = 0; ka < 3; ++ka)
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma_ss(tmem + TC_QK, umma_desc_sw128(xa + ka * ATOM_A + ks * 32), umma_desc_sw128(w + ka * 8192 + ks * 32),
+                                IDESC_128x64, (ka | ks) != 0);
+                umma_commit(&bars[B_EMPTY + stage]);
+                if (++stage == RING_N) { stage = 0; phase ^= 1; }
             };
             auto issue_pv = [&](int h) {     // O_h = P v_h : A = P (TMEM, aliases S), B = V^T rows of head h (32 x 128 keys)
                 const uint32_t pcol = (h & 1) ? TC_S1 : TC_S0;
@@ -331,10 +348,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_attn_kernel(const AttnParams
                 umma_commit(&bars[B_VTF]);
                 SRK_TL(p.dbg, it, 34);
                 // ---- [q_0 | k_0]
-                gemm_k192(tmem + TC_QK, xa, true, IDESC_128x64);
-                umma_commit(&bars[B_QKF0]);
+                gemm_qk();
+                umma_commit(&bars[B_QKF]);
                 for (int h = 0; h < 6; ++h) {
-                    mbar_wait(&bars[B_QKR0 + (h & 1)], ph_qkr[h & 1]); ph_qkr[h & 1] ^= 1;   // image h written, QK accumulator drained
+                    mbar_wait(&bars[B_QKR], ph_qkr); ph_qkr ^= 1;          // image h written (utility warps), QK accumulator drained
                     tc_fence_after();
                     SRK_TL(p.dbg, it, 35 + h);
                     if (h == 0) {                                          // V^T accumulators drained (S columns free), V^T image ready
@@ -348,9 +365,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_attn_kernel(const AttnParams
                         umma_ss(tmem + ((h & 1) ? TC_S1 : TC_S0), umma_desc_sw128(img + ks * 32), umma_desc_sw128(img + 64 + ks * 32),
                                 IDESC_128x128, ks != 0);
                     umma_commit(&bars[B_SF0 + (h & 1)]);
+                    SRK_TL(p.dbg, it, 44 + h);
                     if (h < 5) {                                           // next head's q|k GEMM overlaps softmax(h)
-                        gemm_k192(tmem + TC_QK, xa, true, IDESC_128x64);
-                        umma_commit(&bars[B_QKF0 + ((h + 1) & 1)]);
+                        gemm_qk();
+                        umma_commit(&bars[B_QKF]);
                     }
                     if (h >= 1) {
                         mbar_wait(&bars[B_PR0 + ((h - 1) & 1)], ph_pr[(h - 1) & 1]); ph_pr[(h - 1) & 1] ^= 1;
@@ -373,39 +391,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_attn_kernel(const AttnParams
             }
         }
         __syncwarp();
-    } else {
-        // ===================================================== 256 row threads
-        const int cw8 = warp - 2;                   // 0..7: 16-row slice this warp loads in the LN phase
-        const int g = cw8 >> 2;                     // group: softmax of heads h = g (mod 2); column half elsewhere
-        const int q = warp & 3;                     // TMEM lane quadrant this warp may access
-        const int row = q * 32 + lane;              // accumulator row == token row of the tile
+    } else if (warp >= 10) {
+        // ===================================================== 128 utility threads: q|k epilogues and the next tile's x image
+        const int cwu = warp - 10;                  // 0..3: 32-row slice of the LN phase
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
         const uint32_t lanebase = static_cast<uint32_t>(q * 32) << 16;
-        const uint32_t xa = sbase + A_XA, vt = sbase + A_VT, qki = sbase + A_QKI + g * ATOM_A;
-        const int half = row >> 6, t = row & 63;
-        const int rpb_base = (t >> 3) * 15 + (t & 7) + 112;
-        uint32_t ph_vtf = 0, ph_qkf = 0, ph_sf = 0, ph_of = 0, ph_pjf = 0;
-        uint64_t* const bar_qkf = &bars[B_QKF0 + g];
-        uint64_t* const bar_qkr = &bars[B_QKR0 + g];
-        uint64_t* const bar_sf = &bars[B_SF0 + g];
-        uint64_t* const bar_pr = &bars[B_PR0 + g];
-        const uint32_t scol = g ? TC_S1 : TC_S0;
-
+        const uint32_t xa = sbase + A_XA, qki = sbase + A_QKI;
+        uint32_t ph_qkf = 0;
         TileGeom geo;
-        auto set_geom = [&](int tile) {
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-                const int gw = tile * 2 + hf;
-                geo.valid[hf] = gw < p.total_windows;
-                if (p.mode == SRK_MODE_WINDOWS) {
-                    geo.base[hf] = static_cast<int64_t>(gw) * 64; geo.y0[hf] = 0; geo.x0[hf] = 0;
-                } else {
-                    const int b = gw / p.nw_img, w = gw - b * p.nw_img;
-                    const int wy = w / p.nwx, wx = w - wy * p.nwx;
-                    geo.base[hf] = static_cast<int64_t>(b) * p.H * p.W;
-                    geo.y0[hf] = wy * 8 + p.shift; geo.x0[hf] = wx * 8 + p.shift;
-                }
-            }
-        };
         auto tok_of_row = [&](int r) -> int64_t {
             const int hf = r >> 6, tt = r & 63;
             if (!geo.valid[hf]) return static_cast<int64_t>(-1);
@@ -416,20 +410,81 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_attn_kernel(const AttnParams
             if (xx >= p.W) xx -= p.W;
             return geo.base[hf] + static_cast<int64_t>(yy) * p.W + xx;
         };
-        auto ln_tile = [&](int tile) {               // gather + normalise -> x image
-            set_geom(tile);
-            ln_rows_to_image(p.x, p.ld_in, p.apply_ln, xa, cw8, lane, tok_of_row);
+        auto ln_tile = [&](int tile) {               // gather + normalise -> x image (32 rows per warp)
+            set_tile_geom(p, tile, geo);
+            ln_rows_to_image(p.x, p.ld_in, p.apply_ln, xa, 2 * cwu, lane, tok_of_row);
+            ln_rows_to_image(p.x, p.ld_in, p.apply_ln, xa, 2 * cwu + 1, lane, tok_of_row);
             fence_proxy_async_smem();
             mbar_arrive(&bars[B_XA]);
         };
-        stagger_start(p.stagger);
         if (static_cast<int>(blockIdx.x) < p.n_tiles) ln_tile(blockIdx.x);
+        uint32_t ph_drain = 0;
+        bool first_tile = true;
+        int uit = 0;
+        unsigned long long* udbg = threadIdx.x == 320 ? p.dbg : nullptr;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            if (!first_tile) {      // the previous tile's output rows (staged over the V^T / q|k images) have left shared memory
+                mbar_wait(&bars[B_DRAIN], ph_drain); ph_drain ^= 1;
+            }
+            first_tile = false;
+#pragma unroll 1
+            for (int h = 0; h < 6; ++h) {
+                // ---- q,k accumulators of head h -> [q_h | k_h] image (h & 1).  The k bias is dropped: it shifts every
+                //      logit of a row by the same amount, which the softmax cancels.
+                mbar_wait(&bars[B_QKF], ph_qkf); ph_qkf ^= 1;
+                tc_fence_after();
+                SRK_TL(udbg, uit, 50 + h);
+                const uint32_t img = qki + (h & 1) * ATOM_A;
+                uint32_t v[32];
+                tmem_ld32(tmem + lanebase + TC_QK, v);
+                tmem_ld_wait();
+                store_row_chunks<true, false>(img, row, 0, v, s_vec + SRK_AV_BIAS_Q + 32 * h, 1.0f);
+                tmem_ld32(tmem + lanebase + TC_QK + 32, v);
+                tmem_ld_wait();
+                store_row_chunks<false, false>(img, row, 4, v, nullptr, 1.0f);
+                tc_fence_before();
+                fence_proxy_async_smem();
+                mbar_arrive(&bars[B_QKR]);
+                SRK_TL(udbg, uit, 56 + h);
+            }
+            // ---- the q|k GEMM of head 5 is complete, so nothing reads the x image any more: build the next tile's
+            if (tile + static_cast<int>(gridDim.x) < p.n_tiles) ln_tile(tile + gridDim.x);
+            SRK_TL(udbg, uit, 62);
+            ++uit;
+        }
+    } else {
+        // ===================================================== 256 row threads (two softmax groups)
+        const int cw8 = warp - 2;
+        const int g = cw8 >> 2;                     // group: softmax of heads h = g (mod 2); column half elsewhere
+        const int q = warp & 3;                     // TMEM lane quadrant this warp may access
+        const int row = q * 32 + lane;              // accumulator row == token row of the tile
+        const uint32_t lanebase = static_cast<uint32_t>(q * 32) << 16;
+        const uint32_t vt = sbase + A_VT;
+        const int half = row >> 6, t = row & 63;
+        const int rpb_base = (t >> 3) * 15 + (t & 7) + 112;
+        uint32_t ph_vtf = 0, ph_sf = 0, ph_of = 0, ph_pjf = 0;
+        uint64_t* const bar_sf = &bars[B_SF0 + g];
+        uint64_t* const bar_pr = &bars[B_PR0 + g];
+        const uint32_t scol = g ? TC_S1 : TC_S0;
+
+        TileGeom geo;
+        auto tok_of_row = [&](int r) -> int64_t {
+            const int hf = r >> 6, tt = r & 63;
+            if (!geo.valid[hf]) return static_cast<int64_t>(-1);
+            if (p.mode == SRK_MODE_WINDOWS) return geo.base[hf] + tt;
+            int yy = geo.y0[hf] + (tt >> 3);
+            if (yy >= p.H) yy -= p.H;
+            int xx = geo.x0[hf] + (tt & 7);
+            if (xx >= p.W) xx -= p.W;
+            return geo.base[hf] + static_cast<int64_t>(yy) * p.W + xx;
+        };
+        stagger_start(p.stagger);
 
         int it = 0;
         unsigned long long* dbg = threadIdx.x == 64 ? p.dbg : nullptr;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
             SRK_TL(dbg, it, 0);
-            set_geom(tile);
+            set_tile_geom(p, tile, geo);
             // mask bits of this row (closed form of calculate_mask, network_swinir.py:216-237)
             const int gw_row = tile * 2 + half;
             uint32_t mh = 0xffu, mw = 0xffu;
@@ -477,24 +532,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_attn_kernel(const AttnParams
 #pragma unroll
             for (int hh = 0; hh < 3; ++hh) {
                 const int h = 2 * hh + g;
-                // ---- q,k accumulators of head h -> [q_h | k_h] image of this group.  The k bias is dropped: it shifts
-                //      every logit of a row by the same amount, which the softmax cancels.
-                mbar_wait(bar_qkf, ph_qkf); ph_qkf ^= 1;
-                tc_fence_after();
-                {
-                    uint32_t v[32];
-                    tmem_ld32(tmem + lanebase + TC_QK, v);
-                    tmem_ld_wait();
-                    store_row_chunks<true, false>(qki, row, 0, v, s_vec + SRK_AV_BIAS_Q + 32 * h, 1.0f);
-                    tmem_ld32(tmem + lanebase + TC_QK + 32, v);
-                    tmem_ld_wait();
-                    store_row_chunks<false, false>(qki, row, 4, v, nullptr, 1.0f);
-                }
-                tc_fence_before();
-                fence_proxy_async_smem();
-                mbar_arrive(bar_qkr);
-                SRK_TL(dbg, it, 4 + 3 * hh);
-
                 // ---- softmax of this row over the 64 keys of its own window (exp2 domain; log2 e folded into Wq, rpb)
                 mbar_wait(bar_sf, ph_sf); ph_sf ^= 1;
                 tc_fence_after();
@@ -561,24 +598,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_attn_kernel(const AttnParams
             mbar_arrive(&bars[B_OR]);
             SRK_TL(dbg, it, 24);
 
-            // ---- every GEMM that reads the x image is complete: normalise the next tile while proj runs, so that the
-            //      next tile's V^T / q|k GEMMs overlap this tile's store phase
-            // destination tokens of rows q*32 + lane and q*32 + 16 + lane of THIS tile (ln_tile overwrites the geometry)
-            const int64_t tok_lo = tok_of_row(q * 32 + (lane & 15)), tok_hi = tok_of_row(q * 32 + 16 + (lane & 15));
-            if (tile + static_cast<int>(gridDim.x) < p.n_tiles) ln_tile(tile + gridDim.x);
-            SRK_TL(dbg, it, 25);
-
             // ---- phase 5: proj accumulators + bias -> staged rows -> bulk (reduce-add) store; window reverse + un-shift
-            //      are the destination addresses of the copies.  Staging = the V^T region (two passes of 16 rows).
+            //      are the destination addresses of the copies.  Staging = V^T + q|k image regions + a small tail.
             mbar_wait(&bars[B_PJF], ph_pjf); ph_pjf ^= 1;
             tc_fence_after();
             SRK_TL(dbg, it, 26);
-            stage_rows_and_bulk_store(tmem + TC_PROJ, lanebase, sm + A_VT, s_vec + SRK_AV_BIAS_PROJ, p.y, p.ld_out, p.add_residual,
-                                      q, g, lane, 2, false, [&](int r) { return ((r - q * 32) & 16) ? tok_hi : tok_lo; });
+            stage_rows_and_bulk_store(tmem + TC_PROJ, lanebase, sm + A_VT, sm + A_TAIL, 28, s_vec + SRK_AV_BIAS_PROJ, p.y, p.ld_out,
+                                      p.add_residual, q, g, lane, tok_of_row);
             tc_fence_before();
-            // every bulk copy has finished reading the staging rows before any warp writes the next tile's V^T image there
-            if (g == 0) bulk_wait_read0();
-            named_bar_sync(1, NROWTHREADS);
+            // the copies drain while the next tile's V^T / q|k GEMMs run; nobody may write the V^T or q|k images before that
+            if (g == 0) {
+                bulk_wait_read0();
+                mbar_arrive(&bars[B_DRAIN]);        // -> utility warps (q|k images)
+            }
+            named_bar_sync(1, NROWTHREADS);         // -> both groups (V^T image)
             SRK_TL(dbg, it, 27);
         }
     }
@@ -775,8 +808,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_mlp_kernel(const MlpParams p
             mbar_wait(&bars[MB_F2], ph_f2); ph_f2 ^= 1;
             tc_fence_after();
             SRK_TL(dbg, it, 8);
-            stage_rows_and_bulk_store(tmem + TC_F2, lanebase, sm + M_STAGE, s_vec + SRK_MV_B2, p.y, p.ld_out, p.add_residual, q, g, lane, 1,
-                                      true, tok_of_row);
+            if (g == 0) bulk_wait_read0();          // the previous tile's copies no longer read the private staging rows
+            named_bar_sync(2 + q, 64);
+            stage_rows_and_bulk_store(tmem + TC_F2, lanebase, sm + M_STAGE, sm + M_STAGE, 32, s_vec + SRK_MV_B2, p.y, p.ld_out,
+                                      p.add_residual, q, g, lane, tok_of_row);
             tc_fence_before();
             SRK_TL(dbg, it, 9);
         }
@@ -808,7 +843,7 @@ cudaError_t launch_swin_attn(const AttnParams& p, cudaStream_t stream) {
         configured = true;
     }
     const int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
-    swin_attn_kernel<<<grid, NTHREADS, K1_SMEM, stream>>>(p);
+    swin_attn_kernel<<<grid, K1_THREADS, K1_SMEM, stream>>>(p);
     return cudaGetLastError();
 }
 
