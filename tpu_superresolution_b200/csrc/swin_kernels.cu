@@ -37,6 +37,8 @@ constexpr uint32_t IDESC_128x128 = umma_idesc_bf16(128, 128);
 constexpr uint32_t IDESC_128x192 = umma_idesc_bf16(128, 192);
 constexpr uint32_t IDESC_128x64 = umma_idesc_bf16(128, 64);
 constexpr uint32_t IDESC_128x32 = umma_idesc_bf16(128, 32);
+constexpr uint32_t IDESC_64x64 = umma_idesc_bf16(64, 64);
+constexpr uint32_t IDESC_64x32 = umma_idesc_bf16(64, 32);
 constexpr float LOG2E = 1.4426950408889634f;
 
 // Optional per-CTA timeline (debug): CTA 0 writes clock64() at event `id` of its `it`-th tile.
@@ -220,16 +222,20 @@ constexpr uint32_t K1_SMEM = A_END + 1024;            // + alignment slack
 static_assert(K1_SMEM <= 232448, "K1 shared memory exceeds 227 KB");
 static_assert(112 * 720 <= 2 * VT_ATOM + 2 * ATOM_A && 3 * ATOM_A <= 2 * VT_ATOM, "O image / store staging must fit");
 
-// TMEM columns (fp32, 128 lanes)
+// TMEM columns (fp32, 128 lanes).  S and P v run as two M = 64 UMMAs per head, one per window: an M = 64 accumulator
+// occupies lanes {0-15, 32-47, 64-79, 96-111} and the second window's interleaves at lane offset 16, so both windows of
+// the tile share the same 64 columns (no block-diagonal waste, no zero fill).  Softmax/O row of lane L:
+// window (L % 32) / 16, token 16 * (L / 32) + L % 16.
 constexpr uint32_t TC_O = 0;                          // O accumulator, 6 heads x 32; later the proj accumulator (192)
-constexpr uint32_t TC_S0 = 192, TC_S1 = 320;          // S = q k^T (128 x 128, block diagonal used); P (bf16) aliases cols 0..63
-constexpr uint32_t TC_QK = 448;                       // [q_h | k_h] accumulator of one head (64 cols)
-constexpr uint32_t TC_VT0 = 192, TC_VT1 = 320;        // V^T accumulators (before the first S of the tile)
+constexpr uint32_t TC_S0 = 192, TC_S1 = 256;          // S = q k^T (64 keys); P (bf16 pairs) aliases cols 0..31
+constexpr uint32_t TC_QK1 = 384, TC_QK0 = 448;        // [q_h | k_h] accumulators (64 cols), double buffered by head parity
+constexpr uint32_t TC_VT0 = 192, TC_VT1 = 320;        // V^T accumulators (before the first S / odd q|k GEMM of the tile)
 constexpr uint32_t TC_PROJ = 0;
+constexpr uint32_t LANE16 = 16u << 16;                // TMEM lane offset of the second window's M = 64 tile
 
 enum {  // K1 barrier slots
-    B_FULL = 0, B_EMPTY = 3, B_XA = 6, B_VTF = 7, B_VTD = 8, B_QKF = 9, B_QKR = 10, B_SF0 = 11, B_SF1 = 12, B_PR0 = 13, B_PR1 = 14,
-    B_OF = 15, B_OR = 16, B_PJF = 17, B_DRAIN = 18, B_COUNT = 19
+    B_FULL = 0, B_EMPTY = 3, B_XA = 6, B_VTF = 7, B_VTD = 8, B_QKF0 = 9, B_QKF1 = 10, B_QKR0 = 11, B_QKR1 = 12, B_SF0 = 13, B_SF1 = 14,
+    B_PR0 = 15, B_PR1 = 16, B_OF = 17, B_OR = 18, B_PJF = 19, B_DRAIN = 20, B_COUNT = 21
 };
 
 struct TileGeom {
@@ -268,7 +274,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
     if (threadIdx.x == 0) {
         for (int i = 0; i < RING_N; ++i) { mbar_init(&bars[B_FULL + i], 1); mbar_init(&bars[B_EMPTY + i], 1); }
         mbar_init(&bars[B_XA], 128);         mbar_init(&bars[B_VTF], 1);    mbar_init(&bars[B_VTD], NROWTHREADS);
-        mbar_init(&bars[B_QKF], 1);          mbar_init(&bars[B_QKR], 128);  mbar_init(&bars[B_SF0], 1);    mbar_init(&bars[B_SF1], 1);
+        mbar_init(&bars[B_QKF0], 1);         mbar_init(&bars[B_QKF1], 1);   mbar_init(&bars[B_QKR0], 128); mbar_init(&bars[B_QKR1], 128);
+        mbar_init(&bars[B_SF0], 1);          mbar_init(&bars[B_SF1], 1);
         mbar_init(&bars[B_PR0], 128);        mbar_init(&bars[B_PR1], 128);  mbar_init(&bars[B_OF], 1);
         mbar_init(&bars[B_OR], NROWTHREADS); mbar_init(&bars[B_PJF], 1);    mbar_init(&bars[B_DRAIN], 128);
         fence_barrier_init();
@@ -300,7 +307,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
         // ===================================================== MMA issuer
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            uint32_t ph_xa = 0, ph_vtd = 0, ph_qkr = 0, ph_pr[2] = {0, 0}, ph_or = 0;
+            uint32_t ph_xa = 0, ph_vtd = 0, ph_qkr[2] = {0, 0}, ph_pr[2] = {0, 0}, ph_or = 0;
             const uint32_t xa = sbase + A_XA, vt = sbase + A_VT, qki = sbase + A_QKI, ring = sbase + A_RING;
             // one GEMM over K = 192: 3 ring slabs x 4 k-steps
             auto gemm_k192 = [&](uint32_t d_tmem, uint32_t img, bool img_is_a, uint32_t idesc) {
@@ -316,25 +323,40 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
                     if (++stage == RING_N) { stage = 0; phase ^= 1; }
                 }
             };
-            auto gemm_qk = [&]() {             // [q_h | k_h] = xhat * W^T, N = 64; the three k-atoms of W arrive as one ring stage
+            auto gemm_qk = [&](int h) {        // [q_h | k_h] = xhat * W^T, N = 64; the three k-atoms of W arrive as one ring stage
                 mbar_wait(&bars[B_FULL + stage], phase);
                 tc_fence_after();
                 const uint32_t w = ring + stage * RING_STAGE;
+                const uint32_t acc = tmem + ((h & 1) ? TC_QK1 : TC_QK0);
 #pragma unroll
                 for (int ka = 0; ka < 3; ++ka)
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)
-                        umma_ss(tmem + TC_QK, umma_desc_sw128(xa + ka * ATOM_A + ks * 32), umma_desc_sw128(w + ka * 8192 + ks * 32),
+                        umma_ss(acc, umma_desc_sw128(xa + ka * ATOM_A + ks * 32), umma_desc_sw128(w + ka * 8192 + ks * 32),
                                 IDESC_128x64, (ka | ks) != 0);
                 umma_commit(&bars[B_EMPTY + stage]);
                 if (++stage == RING_N) { stage = 0; phase ^= 1; }
+                umma_commit(&bars[B_QKF0 + (h & 1)]);
             };
-            auto issue_pv = [&](int h) {     // O_h = P v_h : A = P (TMEM, aliases S), B = V^T rows of head h (32 x 128 keys)
-                const uint32_t pcol = (h & 1) ? TC_S1 : TC_S0;
+            auto issue_s = [&](int h) {        // S_w = q_h k_h^T per window w: two M = 64, N = 64 UMMAs sharing 64 columns
+                const uint32_t img = qki + (h & 1) * ATOM_A;
+                const uint32_t scol = tmem + ((h & 1) ? TC_S1 : TC_S0);
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk)
-                    umma_ts(tmem + TC_O + 32 * h, tmem + pcol + 8 * kk,
-                            umma_desc_sw128(vt + (kk >> 2) * VT_ATOM + h * 4096 + (kk & 3) * 32), IDESC_128x32, kk != 0);
+                for (int w = 0; w < 2; ++w)
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks)
+                        umma_ss(scol + w * LANE16, umma_desc_sw128(img + w * 8192 + ks * 32), umma_desc_sw128(img + w * 8192 + 64 + ks * 32),
+                                IDESC_64x64, ks != 0);
+                umma_commit(&bars[B_SF0 + (h & 1)]);
+            };
+            auto issue_pv = [&](int h) {       // O_h = P v_h per window: A = P (TMEM, aliases S), B = V^T rows of head h, keys of window w
+                const uint32_t pcol = tmem + ((h & 1) ? TC_S1 : TC_S0);
+#pragma unroll
+                for (int w = 0; w < 2; ++w)
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_ts(tmem + TC_O + 32 * h + w * LANE16, pcol + w * LANE16 + 8 * kk,
+                                umma_desc_sw128(vt + w * VT_ATOM + h * 4096 + kk * 32), IDESC_64x32, kk != 0);
             };
             int it = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
@@ -347,29 +369,18 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
                 gemm_k192(tmem + TC_VT1, xa, false, IDESC_128x128);
                 umma_commit(&bars[B_VTF]);
                 SRK_TL(p.dbg, it, 34);
-                // ---- [q_0 | k_0]
-                gemm_qk();
-                umma_commit(&bars[B_QKF]);
+                // ---- [q_0 | k_0] (its accumulator does not overlap the V^T accumulators), then, once those are drained, [q_1 | k_1]
+                gemm_qk(0);
+                mbar_wait(&bars[B_VTD], ph_vtd); ph_vtd ^= 1;
+                tc_fence_after();
+                gemm_qk(1);
                 for (int h = 0; h < 6; ++h) {
-                    mbar_wait(&bars[B_QKR], ph_qkr); ph_qkr ^= 1;          // image h written (utility warps), QK accumulator drained
+                    mbar_wait(&bars[B_QKR0 + (h & 1)], ph_qkr[h & 1]); ph_qkr[h & 1] ^= 1;   // image h written, accumulator h & 1 drained
                     tc_fence_after();
                     SRK_TL(p.dbg, it, 35 + h);
-                    if (h == 0) {                                          // V^T accumulators drained (S columns free), V^T image ready
-                        mbar_wait(&bars[B_VTD], ph_vtd); ph_vtd ^= 1;
-                        tc_fence_after();
-                    }
-                    // ---- S = q_h k_h^T over the whole 128-token tile (two windows, block diagonal used)
-                    const uint32_t img = qki + (h & 1) * ATOM_A;
-#pragma unroll
-                    for (int ks = 0; ks < 2; ++ks)
-                        umma_ss(tmem + ((h & 1) ? TC_S1 : TC_S0), umma_desc_sw128(img + ks * 32), umma_desc_sw128(img + 64 + ks * 32),
-                                IDESC_128x128, ks != 0);
-                    umma_commit(&bars[B_SF0 + (h & 1)]);
+                    issue_s(h);
                     SRK_TL(p.dbg, it, 44 + h);
-                    if (h < 5) {                                           // next head's q|k GEMM overlaps softmax(h)
-                        gemm_qk();
-                        umma_commit(&bars[B_QKF]);
-                    }
+                    if (h + 2 < 6) gemm_qk(h + 2);                         // runs two heads ahead of the softmax
                     if (h >= 1) {
                         mbar_wait(&bars[B_PR0 + ((h - 1) & 1)], ph_pr[(h - 1) & 1]); ph_pr[(h - 1) & 1] ^= 1;
                         tc_fence_after();
@@ -398,7 +409,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
         const int row = q * 32 + lane;
         const uint32_t lanebase = static_cast<uint32_t>(q * 32) << 16;
         const uint32_t xa = sbase + A_XA, qki = sbase + A_QKI;
-        uint32_t ph_qkf = 0;
+        uint32_t ph_qkf[2] = {0, 0};
         TileGeom geo;
         auto tok_of_row = [&](int r) -> int64_t {
             const int hf = r >> 6, tt = r & 63;
@@ -431,20 +442,21 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
             for (int h = 0; h < 6; ++h) {
                 // ---- q,k accumulators of head h -> [q_h | k_h] image (h & 1).  The k bias is dropped: it shifts every
                 //      logit of a row by the same amount, which the softmax cancels.
-                mbar_wait(&bars[B_QKF], ph_qkf); ph_qkf ^= 1;
+                mbar_wait(&bars[B_QKF0 + (h & 1)], ph_qkf[h & 1]); ph_qkf[h & 1] ^= 1;
                 tc_fence_after();
                 SRK_TL(udbg, uit, 50 + h);
                 const uint32_t img = qki + (h & 1) * ATOM_A;
+                const uint32_t acc = tmem + lanebase + ((h & 1) ? TC_QK1 : TC_QK0);
                 uint32_t v[32];
-                tmem_ld32(tmem + lanebase + TC_QK, v);
+                tmem_ld32(acc, v);
                 tmem_ld_wait();
                 store_row_chunks<true, false>(img, row, 0, v, s_vec + SRK_AV_BIAS_Q + 32 * h, 1.0f);
-                tmem_ld32(tmem + lanebase + TC_QK + 32, v);
+                tmem_ld32(acc + 32, v);
                 tmem_ld_wait();
                 store_row_chunks<false, false>(img, row, 4, v, nullptr, 1.0f);
                 tc_fence_before();
                 fence_proxy_async_smem();
-                mbar_arrive(&bars[B_QKR]);
+                mbar_arrive(&bars[B_QKR0 + (h & 1)]);
                 SRK_TL(udbg, uit, 56 + h);
             }
             // ---- the q|k GEMM of head 5 is complete, so nothing reads the x image any more: build the next tile's
@@ -460,7 +472,9 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
         const int row = q * 32 + lane;              // accumulator row == token row of the tile
         const uint32_t lanebase = static_cast<uint32_t>(q * 32) << 16;
         const uint32_t vt = sbase + A_VT;
-        const int half = row >> 6, t = row & 63;
+        // softmax / O row of this lane (M = 64 accumulator layout): window `half`, token t of that window
+        const int half = lane >> 4, t = 16 * q + (lane & 15);
+        const int srow = 64 * half + t;             // the same row in tile order (row of the q|k / O images)
         const int rpb_base = (t >> 3) * 15 + (t & 7) + 112;
         uint32_t ph_vtf = 0, ph_sf = 0, ph_of = 0, ph_pjf = 0;
         uint64_t* const bar_sf = &bars[B_SF0 + g];
@@ -537,8 +551,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
                 tc_fence_after();
                 SRK_TL(dbg, it, 5 + 3 * hh);
                 uint32_t v0[32], v1[32];
-                tmem_ld32(tmem + lanebase + scol + 64 * half, v0);
-                tmem_ld32(tmem + lanebase + scol + 64 * half + 32, v1);
+                tmem_ld32(tmem + lanebase + scol, v0);
+                tmem_ld32(tmem + lanebase + scol + 32, v1);
                 tmem_ld_wait();
                 const float* rpb = s_vec + SRK_AV_RPB + h * SRK_AV_RPB_STRIDE + rpb_base;
                 float s[64];
@@ -570,11 +584,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
                     pw[jx >> 1] = pack_bf16x2(e0, e1);
                 }
                 inv_sum[hh] = __frcp_rn(sum0 + sum1);
-                uint32_t zeros[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) zeros[i] = 0u;
-                tmem_st32(tmem + lanebase + scol + 32 * half, pw);            // P aliases the S columns
-                tmem_st32(tmem + lanebase + scol + 32 * (1 - half), zeros);   // the other window's keys
+                tmem_st32(tmem + lanebase + scol, pw);                        // P aliases the first half of the S columns
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(bar_pr);
@@ -591,7 +601,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
                 uint32_t v[32];
                 tmem_ld32(tmem + lanebase + TC_O + 32 * h, v);
                 tmem_ld_wait();
-                store_row_chunks<false, true>(vt + (h >> 1) * ATOM_A, row, (h & 1) * 4, v, nullptr, inv_sum[hh]);
+                store_row_chunks<false, true>(vt + (h >> 1) * ATOM_A, srow, (h & 1) * 4, v, nullptr, inv_sum[hh]);
             }
             tc_fence_before();
             fence_proxy_async_smem();
