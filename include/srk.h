@@ -86,6 +86,63 @@ typedef struct SrkMlpDesc {
 int srk_swin_mlp_fwd(const SrkMlpDesc* desc, const float* x, float* y, const void* wstream /* SRK_MLP_WSTREAM_BYTES */,
                      const float* vec /* SRK_MLP_VEC_FLOATS */, void* stream);
 
+/* Token-wise linear layer on tcgen05 for the HAT / DAT paths:  out[tok, :] = act(A[tok, :] W^T + b), N in chunks of 192
+ * columns.  Replaces the nn.Linear call sites hat_arch.py:179, :195, :401, :436 and dat_arch.py:371, :435, :483, :526, :79-88.
+ *   A  SRK_LIN_A_ROWS  : fp32 token rows [tok][ld_in] (180 valid), optional LayerNorm (affine folded into W, b at pack time)
+ *      SRK_LIN_A_PLANES: bf16 planes [k_atoms][num_tokens][64] (128 B per token row, 16-byte chunks permuted by chunk ^ (tok & 7))
+ *   out SRK_LIN_OUT_PLANES: bf16 planes [3 * n_chunks][num_tokens][64]; plane p is permuted with (tok + 4) & 7 when bit p of
+ *                          plane_phase_mask is set (operand-row phase of the consumer's window images)
+ *       SRK_LIN_OUT_ROWS  : fp32 rows [tok][ld_out] (n_chunks = 1, 180 valid columns), added into `out` when add_residual. */
+enum { SRK_LIN_A_ROWS = 0, SRK_LIN_A_PLANES = 1 };
+enum { SRK_LIN_OUT_PLANES = 0, SRK_LIN_OUT_ROWS = 1 };
+enum { SRK_LIN_ACT_NONE = 0, SRK_LIN_ACT_GELU = 1 };
+#define SRK_LIN_SLAB_BYTES 24576   /* one weight slab: 192 output rows x 64 k, bf16, 128-byte swizzle */
+#define SRK_LIN_MAX_CHUNKS 8
+
+typedef struct SrkLinearDesc {
+    int64_t num_tokens;
+    int32_t a_mode;        /* SRK_LIN_A_* */
+    int32_t k_atoms;       /* K / 64: 3 or 6 */
+    int32_t ld_in;         /* floats per token row (A_ROWS) */
+    int32_t apply_ln;      /* A_ROWS: 1 = LayerNorm first */
+    int32_t n_chunks;      /* N / 192 */
+    int32_t act;           /* SRK_LIN_ACT_* */
+    int32_t out_mode;      /* SRK_LIN_OUT_* */
+    int32_t ld_out;        /* floats per output row (OUT_ROWS) */
+    int32_t add_residual;  /* OUT_ROWS: 1 = out += result */
+    uint32_t plane_phase_mask;
+} SrkLinearDesc;
+
+int srk_linear_fwd(const SrkLinearDesc* desc, const void* a, const void* wstream /* n_chunks * k_atoms * SRK_LIN_SLAB_BYTES */,
+                   const float* bias /* n_chunks * 192 */, void* out, void* stream);
+
+/* Window attention on q/k/v planes: softmax(q k^T + bias[+ mask]) v for every 256-query window and head.
+ *   SRK_WA_HAT_WMSA  hat_arch.py:166-197 inside HAB (:281-301): 16x16 windows, cyclic shift (0 or 8), closed-form shift mask
+ *                    (:921-940) or an explicit (nW, 256, 256) mask, relative position bias (961-entry table)
+ *   SRK_WA_HAT_OCAB  hat_arch.py:403-432: 16x16 queries against the zero-padded 24x24 overlapping key window (nn.Unfold :378)
+ *   SRK_WA_DAT_8x32 / SRK_WA_DAT_32x8  dat_arch.py:193-244: rectangular windows, dynamic position bias, shift (4,16) / (16,4)
+ * q/k/v: plane p = heads 2p, 2p+1 (32 padded dims each), [p][batch*height*width][64] bf16, swizzled as written by
+ * srk_linear_fwd.  bias_table: [2 * ceil(n_heads / 2)][srk_window_attention_table_floats(kind)] floats, already * log2(e),
+ * entry (dy * SY + dx) for query-key offset (dy, dx) (see packing.py).  q must already carry scale * log2(e).
+ * out_mode 0: bf16 planes [ceil(n_heads/2)][tokens][64] swizzled with tok & 7 (A operand of the proj srk_linear_fwd);
+ * out_mode 1: fp32 rows, out[tok * out_ld + out_col0 + head * 30 + d]. */
+enum { SRK_WA_HAT_WMSA = 0, SRK_WA_HAT_OCAB = 1, SRK_WA_DAT_8x32 = 2, SRK_WA_DAT_32x8 = 3 };
+
+typedef struct SrkWinAttnDesc {
+    int32_t kind;
+    int32_t batch, height, width;
+    int32_t shift_y, shift_x;   /* cyclic shift of the window grid (torch.roll(-shift)) */
+    int32_t mask_shift;         /* 1: closed-form shifted-window mask */
+    int32_t n_heads;            /* heads in the planes (6; 3 per DAT branch) */
+    int32_t emask_nw;           /* explicit mask: number of windows in the mask tensor (0 = none) */
+    int32_t out_mode, out_ld, out_col0;
+} SrkWinAttnDesc;
+
+int srk_window_attention_fwd(const SrkWinAttnDesc* desc, const void* q_planes, const void* k_planes, const void* v_planes,
+                             const float* bias_table, const float* emask, const void* zero_page /* >= 4096 zero bytes */,
+                             void* out, void* stream);
+int srk_window_attention_table_floats(int32_t kind);
+
 /* Row LayerNorm over the 180 channels of token rows (patch_embed.norm / final norm,
  * network_swinir.py:526-527, :800). */
 int srk_layernorm_fwd(const float* x, float* y, const float* w, const float* b, int64_t num_tokens, int32_t ld_in,

@@ -112,6 +112,87 @@ int srk_swin_mlp_fwd(const SrkMlpDesc* d, const float* x, float* y, const void* 
     return check(srk::launch_swin_mlp(p, static_cast<cudaStream_t>(stream)), "srk_swin_mlp_fwd");
 }
 
+int srk_linear_fwd(const SrkLinearDesc* d, const void* a, const void* wstream, const float* bias, void* out, void* stream) {
+    if (!d || !a || !wstream || !bias || !out) return fail("srk_linear_fwd: null argument");
+    if (!aligned16(a) || !aligned16(wstream) || !aligned16(bias) || !aligned16(out)) return fail("srk_linear_fwd: pointers must be 16-byte aligned");
+    if (d->num_tokens <= 0 || d->num_tokens > (1ll << 31)) return fail("srk_linear_fwd: bad num_tokens");
+    if (d->k_atoms != 3 && d->k_atoms != 6) return fail("srk_linear_fwd: k_atoms must be 3 or 6 (got %d)", d->k_atoms);
+    if (d->n_chunks < 1 || d->n_chunks > SRK_LIN_MAX_CHUNKS) return fail("srk_linear_fwd: n_chunks must be 1..%d", SRK_LIN_MAX_CHUNKS);
+    srk::LinearParams p{};
+    p.a_mode = d->a_mode; p.k_atoms = d->k_atoms; p.num_tokens = d->num_tokens;
+    p.n_tiles = static_cast<int>((d->num_tokens + 127) / 128);
+    p.wstream = static_cast<const uint8_t*>(wstream); p.bias = bias; p.n_chunks = d->n_chunks; p.act = d->act;
+    p.out_mode = d->out_mode; p.plane_phase_mask = d->plane_phase_mask;
+    if (d->a_mode == SRK_LIN_A_ROWS) {
+        if (d->k_atoms != 3) return fail("srk_linear_fwd: fp32 row input needs k_atoms = 3 (K = 180)");
+        if (d->ld_in < SRK_DIM || (d->ld_in & 3)) return fail("srk_linear_fwd: bad ld_in %d", d->ld_in);
+        p.x = static_cast<const float*>(a); p.ld_in = d->ld_in; p.apply_ln = d->apply_ln;
+    } else if (d->a_mode == SRK_LIN_A_PLANES) {
+        p.a_planes = static_cast<const uint8_t*>(a); p.a_plane_stride = d->num_tokens * 128;
+    } else {
+        return fail("srk_linear_fwd: unknown a_mode %d", d->a_mode);
+    }
+    if (d->out_mode == SRK_LIN_OUT_PLANES) {
+        p.out_planes = static_cast<uint8_t*>(out); p.out_plane_stride = d->num_tokens * 128;
+    } else if (d->out_mode == SRK_LIN_OUT_ROWS) {
+        if (d->n_chunks != 1) return fail("srk_linear_fwd: fp32 row output needs n_chunks = 1");
+        if (d->act != SRK_LIN_ACT_NONE) return fail("srk_linear_fwd: fp32 row output has no activation");
+        if (d->ld_out < SRK_DIM || (d->ld_out & 3)) return fail("srk_linear_fwd: bad ld_out %d", d->ld_out);
+        p.y = static_cast<float*>(out); p.ld_out = d->ld_out; p.add_residual = d->add_residual;
+    } else {
+        return fail("srk_linear_fwd: unknown out_mode %d", d->out_mode);
+    }
+    return check(srk::launch_token_linear(p, static_cast<cudaStream_t>(stream)), "srk_linear_fwd");
+}
+
+int srk_window_attention_table_floats(int32_t kind) { return srk::winattn_table_floats(kind); }
+
+int srk_window_attention_fwd(const SrkWinAttnDesc* d, const void* q_planes, const void* k_planes, const void* v_planes,
+                             const float* bias_table, const float* emask, const void* zero_page, void* out, void* stream) {
+    if (!d || !q_planes || !k_planes || !v_planes || !bias_table || !zero_page || !out) return fail("srk_window_attention_fwd: null argument");
+    if (!aligned16(q_planes) || !aligned16(k_planes) || !aligned16(v_planes) || !aligned16(bias_table) || !aligned16(zero_page) || !aligned16(out))
+        return fail("srk_window_attention_fwd: pointers must be 16-byte aligned");
+    int qh, qw, sy, c0, koff = 0, wrap = 1;
+    switch (d->kind) {
+        case SRK_WA_HAT_WMSA: qh = 16; qw = 16; sy = 48; c0 = 15 * sy + 15; break;
+        case SRK_WA_HAT_OCAB: qh = 16; qw = 16; sy = 48; c0 = 23 * sy + 23; koff = -4; wrap = 0; break;
+        case SRK_WA_DAT_8x32: qh = 8; qw = 32; sy = 64; c0 = 7 * sy + 31; break;
+        case SRK_WA_DAT_32x8: qh = 32; qw = 8; sy = 24; c0 = 31 * sy + 7; break;
+        default: return fail("srk_window_attention_fwd: unknown kind %d", d->kind);
+    }
+    if (d->batch <= 0 || d->height <= 0 || d->width <= 0 || d->height % qh || d->width % qw || d->width % 8)
+        return fail("srk_window_attention_fwd: height/width (%d x %d) must be positive multiples of the %d x %d window", d->height, d->width, qh, qw);
+    if (d->n_heads < 1 || d->n_heads > SRK_HEADS) return fail("srk_window_attention_fwd: n_heads must be 1..%d", SRK_HEADS);
+    if (d->shift_y < 0 || d->shift_y >= qh || d->shift_x < 0 || d->shift_x >= qw) return fail("srk_window_attention_fwd: shift out of range");
+    if (!wrap && (d->shift_y || d->shift_x || d->mask_shift || emask)) return fail("srk_window_attention_fwd: OCAB takes no shift / mask");
+    if (d->mask_shift && (d->shift_y == 0 || d->shift_x == 0)) return fail("srk_window_attention_fwd: mask_shift needs a non-zero shift");
+    // operand-row phase: (x + phase) & 7 must equal the image row & 7 of every window row -> shift_x must be a multiple of 4
+    if (d->shift_x & 3) return fail("srk_window_attention_fwd: shift_x must be a multiple of 4");
+    if (emask && (d->emask_nw <= 0 || !aligned16(emask))) return fail("srk_window_attention_fwd: explicit mask needs emask_nw > 0");
+    const int64_t tokens = static_cast<int64_t>(d->batch) * d->height * d->width;
+    if (tokens > (1ll << 31)) return fail("srk_window_attention_fwd: too many tokens");
+    srk::WinAttnParams p{};
+    p.q_planes = static_cast<const uint8_t*>(q_planes); p.k_planes = static_cast<const uint8_t*>(k_planes);
+    p.v_planes = static_cast<const uint8_t*>(v_planes); p.plane_stride = tokens * 128;
+    p.tab = bias_table; p.c0 = c0; p.zero_page = static_cast<const uint8_t*>(zero_page);
+    p.B = d->batch; p.H = d->height; p.W = d->width; p.koff = koff; p.shift_y = d->shift_y; p.shift_x = d->shift_x;
+    p.wrap = wrap; p.mask_shift = d->mask_shift; p.emask = emask; p.emask_nw = emask ? d->emask_nw : 1;
+    p.n_heads = d->n_heads; p.nwy = d->height / qh; p.nwx = d->width / qw;
+    const int64_t items = static_cast<int64_t>(d->batch) * p.nwy * p.nwx * ((d->n_heads + 1) / 2);
+    if (items > (1ll << 30)) return fail("srk_window_attention_fwd: too many windows");
+    p.n_items = static_cast<int>(items);
+    p.out_mode = d->out_mode;
+    if (d->out_mode == 0) {
+        p.o_planes = static_cast<uint8_t*>(out); p.o_plane_stride = tokens * 128;
+    } else if (d->out_mode == 1) {
+        if (d->out_ld < SRK_HEAD_DIM * d->n_heads + d->out_col0 || (d->out_ld & 1) || (d->out_col0 & 1)) return fail("srk_window_attention_fwd: bad out_ld / out_col0");
+        p.o_rows = static_cast<float*>(out); p.o_ld = d->out_ld; p.o_col0 = d->out_col0;
+    } else {
+        return fail("srk_window_attention_fwd: unknown out_mode %d", d->out_mode);
+    }
+    return check(srk::launch_winattn(d->kind, p, static_cast<cudaStream_t>(stream)), "srk_window_attention_fwd");
+}
+
 int srk_layernorm_fwd(const float* x, float* y, const float* w, const float* b, int64_t num_tokens, int32_t ld_in,
                       int32_t ld_out, void* stream) {
     if (!x || !y || !w || !b) return fail("srk_layernorm_fwd: null argument");

@@ -34,10 +34,53 @@ struct MlpParams {
     int stagger;
 };
 
+// token_linear_kernel (linear_kernel.cu)
+struct LinearParams {
+    const float* x;              // SRK_LIN_A_ROWS: fp32 token rows
+    int ld_in, apply_ln;
+    const uint8_t* a_planes;     // SRK_LIN_A_PLANES: bf16 planes [k-atom][tok][128 B]
+    int64_t a_plane_stride;
+    int a_mode, k_atoms;         // k_atoms = K / 64: 3 (K = 192) or 6 (K = 384)
+    int64_t num_tokens;
+    int n_tiles;
+    const uint8_t* wstream;      // n_chunks x k_atoms slabs of 192 rows x 128 B
+    const float* bias;           // n_chunks x 192
+    int n_chunks, act;
+    int out_mode;
+    uint8_t* out_planes;         // SRK_LIN_OUT_PLANES: 3 planes per chunk
+    int64_t out_plane_stride;
+    uint32_t plane_phase_mask;   // bit p set: plane p is swizzled with (tok + 4) & 7 instead of tok & 7
+    float* y;                    // SRK_LIN_OUT_ROWS
+    int ld_out, add_residual;
+};
+
+// winattn_kernel (winattn_kernel.cu)
+struct WinAttnParams {
+    const uint8_t *q_planes, *k_planes, *v_planes;   // plane 0 (head pair 0) of each operand
+    int64_t plane_stride;        // bytes between planes
+    const float* tab;            // [2 * pairs][TABF] strided bias table, * log2(e)
+    int c0;                      // table index of (query i, key j) = c0 + SY * (yi - yj) + (xi - xj)
+    const uint8_t* zero_page;    // >= 4 KB of zeros (OCAB padding)
+    int B, H, W;
+    int koff;                    // key-window offset relative to the query window (OCAB: -4)
+    int shift_y, shift_x, wrap, mask_shift;
+    const float* emask;          // explicit (nW, 256, NK) mask or nullptr
+    int emask_nw;
+    int n_heads, nwy, nwx, n_items;
+    int out_mode;                // 0: bf16 planes (k-atoms of the proj GEMM's A operand), 1: fp32 rows
+    uint8_t* o_planes;
+    int64_t o_plane_stride;
+    float* o_rows;
+    int o_ld, o_col0;
+};
+
 extern unsigned long long* g_timeline;
 extern int g_stagger_attn, g_stagger_mlp;
 cudaError_t launch_swin_attn(const AttnParams& p, cudaStream_t stream);
 cudaError_t launch_swin_mlp(const MlpParams& p, cudaStream_t stream);
+cudaError_t launch_token_linear(const LinearParams& p, cudaStream_t stream);
+cudaError_t launch_winattn(int kind, const WinAttnParams& p, cudaStream_t stream);
+int winattn_table_floats(int kind);
 cudaError_t launch_layernorm(const float* x, float* y, const float* w, const float* b, int64_t num_tokens, int ld_in,
                              int ld_out, cudaStream_t stream);
 cudaError_t launch_pixelshuffle_nhwc(const float* x, float* y, int batch, int height, int width, int out_channels, int r,

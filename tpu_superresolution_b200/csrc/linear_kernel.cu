@@ -1,0 +1,239 @@
+// Token-wise linear layers on tcgen05 for the HAT / DAT paths (sm_100a): y[tok, :] = act(A[tok, :] W^T + b).
+//
+//   A operand   SRK_LIN_A_ROWS  : fp32 token rows [tok][ld] (the residual stream) with optional LayerNorm -- the
+//                                 (x - mean) * rstd image is built by the row threads, the affine is folded into W, b;
+//               SRK_LIN_A_PLANES: bf16 planes [k-atom][tok][128 B] (chunk ^ (tok & 7) swizzle) written by a previous
+//                                 kernel: one 16 KB bulk TMA copy per k-atom drops 128 tokens into the operand image.
+//   output      SRK_LIN_OUT_PLANES: bf16 planes of 64 columns each (q / k / v head pairs, hidden units), swizzle phase
+//                                 per plane (so a later kernel can bulk-copy window rows as UMMA operand rows);
+//               SRK_LIN_OUT_ROWS  : fp32 rows [tok][ld_out] (180 valid columns), plain or added into y with
+//                                 cp.reduce.async.bulk (residual update in place).
+// Replaces nn.Linear call sites hat_arch.py:179 (qkv), :195 (proj), :401, :436 (OCAB qkv / proj) and dat_arch.py:371,
+// :435, :483, :526, :79-88 (qkv / proj / fc1 / fc2).
+//
+// One persistent CTA per SM over 128-token tiles, N processed in chunks of 192 columns with double-buffered TMEM
+// accumulators (the epilogue of chunk c overlaps the MMAs of chunk c + 1).  320 threads: warp 0 producer (weight
+// slabs through a 3-stage ring, A planes), warp 1 MMA issuer, warps 2..9 = 256 row threads (thread <-> TMEM lane <->
+// token row; the two groups split the columns of every chunk).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+#include "rowops.cuh"
+#include "umma.cuh"
+
+namespace srk {
+
+namespace {
+constexpr int LIN_THREADS = 320;
+constexpr int LIN_RING_N = 3;
+constexpr uint32_t LIN_SLAB = 24576;             // 192 rows x 64 k
+constexpr uint32_t LIN_NC = 192;                 // columns per chunk
+constexpr uint32_t LIN_IDESC = umma_idesc_bf16(128, 192);
+constexpr uint32_t L_A = 0;                      // A image: k_atoms k-atoms of 16 KB (48 KB or 96 KB); the rest follows at run time:
+// ring (72 KB) | bias vector (6 KB) | barriers | [k_atoms = 3 and OUT_ROWS: 90 KB of fp32 row staging].  With k_atoms = 6 the
+// staging rows alias the A image, which is dead once the single chunk's GEMM has completed.
+constexpr uint32_t LIN_VEC_BYTES = 1536 * 4;
+__host__ __device__ constexpr uint32_t lin_off_ring(int k_atoms) { return k_atoms * ATOM_A; }
+__host__ __device__ constexpr uint32_t lin_off_vec(int k_atoms) { return lin_off_ring(k_atoms) + LIN_RING_N * LIN_SLAB; }
+__host__ __device__ constexpr uint32_t lin_off_bar(int k_atoms) { return lin_off_vec(k_atoms) + LIN_VEC_BYTES; }
+__host__ __device__ constexpr uint32_t lin_off_stage(int k_atoms) { return lin_off_bar(k_atoms) + 256; }
+__host__ __device__ constexpr uint32_t lin_smem(int k_atoms, bool separate_stage) {
+    return lin_off_stage(k_atoms) + (separate_stage ? 128 * 720 : 0) + 1024;
+}
+static_assert(lin_smem(3, true) <= 232448 && lin_smem(6, false) <= 232448, "token_linear shared memory");
+enum { LB_FULL = 0, LB_EMPTY = 3, LB_AFULL = 6, LB_AEMPTY = 7, LB_ACCF = 8, LB_ACCE = 10, LB_DRAIN = 12, LB_COUNT = 13 };
+
+__device__ __forceinline__ void st_global_v4b(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+}  // namespace
+
+__global__ void __launch_bounds__(LIN_THREADS, 1) token_linear_kernel(const LinearParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t sbase = (raw + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (sbase - raw);
+    const uint32_t L_RING = lin_off_ring(p.k_atoms);
+    float* s_vec = reinterpret_cast<float*>(sm + lin_off_vec(p.k_atoms));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + lin_off_bar(p.k_atoms));
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + LB_COUNT + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool a_rows = p.a_mode == SRK_LIN_A_ROWS;
+    const bool out_rows = p.out_mode == SRK_LIN_OUT_ROWS;
+    const bool stage_alias = out_rows && p.k_atoms == 6;           // staging rows live in the A image (dead after the GEMM)
+    uint8_t* const stage = stage_alias ? sm + L_A : sm + lin_off_stage(p.k_atoms);
+
+    for (int i = threadIdx.x; i < p.n_chunks * (int)LIN_NC; i += blockDim.x) s_vec[i] = p.bias[i];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < LIN_RING_N; ++i) { mbar_init(&bars[LB_FULL + i], 1); mbar_init(&bars[LB_EMPTY + i], 1); }
+        mbar_init(&bars[LB_AFULL], a_rows ? 256 : 1);
+        mbar_init(&bars[LB_AEMPTY], 1);
+        mbar_init(&bars[LB_ACCF], 1);     mbar_init(&bars[LB_ACCF + 1], 1);
+        mbar_init(&bars[LB_ACCE], 256);   mbar_init(&bars[LB_ACCE + 1], 256);
+        mbar_init(&bars[LB_DRAIN], 128);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================================== producer
+        if (lane == 0) {
+            uint32_t stage_i = 0, phase = 0, ph_ae = 1, ph_dr = 1;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                if (!a_rows) {
+                    mbar_wait(&bars[LB_AEMPTY], ph_ae); ph_ae ^= 1;           // previous tile's MMAs have read the A image
+                    if (stage_alias) { mbar_wait(&bars[LB_DRAIN], ph_dr); ph_dr ^= 1; }   // ... and its output rows have left it
+                    const int64_t tok0 = static_cast<int64_t>(tile) * 128;
+                    const int64_t left = p.num_tokens - tok0;
+                    const uint32_t rows = left < 128 ? static_cast<uint32_t>(left) : 128u;
+                    mbar_arrive_expect_tx(&bars[LB_AFULL], rows * 128u * p.k_atoms);
+                    for (int ka = 0; ka < p.k_atoms; ++ka)
+                        bulk_g2s(sm + L_A + ka * ATOM_A, p.a_planes + ka * p.a_plane_stride + tok0 * 128, rows * 128u, &bars[LB_AFULL]);
+                }
+                const uint8_t* w = p.wstream;
+                for (int s = 0; s < p.n_chunks * p.k_atoms; ++s) {
+                    mbar_wait(&bars[LB_EMPTY + stage_i], phase ^ 1);
+                    mbar_arrive_expect_tx(&bars[LB_FULL + stage_i], LIN_SLAB);
+                    bulk_g2s(sm + L_RING + stage_i * LIN_SLAB, w, LIN_SLAB, &bars[LB_FULL + stage_i]);
+                    w += LIN_SLAB;
+                    if (++stage_i == LIN_RING_N) { stage_i = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        if (lane == 0) {
+            uint32_t stage_i = 0, phase = 0, ph_af = 0, ph_acce[2] = {1, 1}, nacc = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                mbar_wait(&bars[LB_AFULL], ph_af); ph_af ^= 1;
+                tc_fence_after();
+                for (int c = 0; c < p.n_chunks; ++c) {
+                    const uint32_t buf = nacc & 1;
+                    ++nacc;
+                    mbar_wait(&bars[LB_ACCE + buf], ph_acce[buf]); ph_acce[buf] ^= 1;      // epilogue has drained this accumulator
+                    tc_fence_after();
+                    for (int ka = 0; ka < p.k_atoms; ++ka) {
+                        mbar_wait(&bars[LB_FULL + stage_i], phase);
+                        tc_fence_after();
+                        const uint32_t a = sbase + L_A + ka * ATOM_A, b = sbase + L_RING + stage_i * LIN_SLAB;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            umma_ss(tmem + 256 * buf, umma_desc_sw128(a + ks * 32), umma_desc_sw128(b + ks * 32), LIN_IDESC, (ka | ks) != 0);
+                        umma_commit(&bars[LB_EMPTY + stage_i]);
+                        if (++stage_i == LIN_RING_N) { stage_i = 0; phase ^= 1; }
+                    }
+                    umma_commit(&bars[LB_ACCF + buf]);
+                }
+                umma_commit(&bars[LB_AEMPTY]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================================================== 256 row threads
+        const int cw8 = warp - 2, g = cw8 >> 2, q = warp & 3, row = q * 32 + lane;
+        const uint32_t lanebase = static_cast<uint32_t>(q * 32) << 16;
+        uint32_t ph_accf[2] = {0, 0}, nacc = 0;
+        auto ln_tile = [&](int tile) {
+            auto tok_of_row = [&](int r) -> int64_t {
+                const int64_t tk = static_cast<int64_t>(tile) * 128 + r;
+                return tk < p.num_tokens ? tk : static_cast<int64_t>(-1);
+            };
+            ln_rows_to_image(p.x, p.ld_in, p.apply_ln, sbase + L_A, cw8, lane, tok_of_row);
+            fence_proxy_async_smem();
+            mbar_arrive(&bars[LB_AFULL]);
+        };
+        if (a_rows && static_cast<int>(blockIdx.x) < p.n_tiles) ln_tile(blockIdx.x);
+        bool first_tile = true;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const int64_t tok = static_cast<int64_t>(tile) * 128 + row;
+            const bool live = tok < p.num_tokens;
+            auto tok_of_row = [&](int r) -> int64_t {
+                const int64_t tk = static_cast<int64_t>(tile) * 128 + r;
+                return tk < p.num_tokens ? tk : static_cast<int64_t>(-1);
+            };
+            for (int c = 0; c < p.n_chunks; ++c) {
+                const uint32_t buf = nacc & 1;
+                ++nacc;
+                mbar_wait(&bars[LB_ACCF + buf], ph_accf[buf]); ph_accf[buf] ^= 1;
+                tc_fence_after();
+                // all GEMMs of this tile are complete after its last chunk: the A image is free for the next tile
+                if (a_rows && c == p.n_chunks - 1 && tile + static_cast<int>(gridDim.x) < p.n_tiles) ln_tile(tile + gridDim.x);
+                const uint32_t acc = tmem + lanebase + 256 * buf;
+                if (!out_rows) {
+#pragma unroll 1
+                    for (int pi = 0; pi < 3; ++pi) {
+                        const int piece = 3 * g + pi;                       // 32 columns of the chunk
+                        uint32_t v[32];
+                        tmem_ld32(acc + 32 * piece, v);
+                        tmem_ld_wait();
+                        const float4* bb = reinterpret_cast<const float4*>(s_vec + c * LIN_NC + 32 * piece);
+                        uint32_t pw[16];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const float4 b4 = bb[k];
+                            float f0 = __uint_as_float(v[4 * k]) + b4.x, f1 = __uint_as_float(v[4 * k + 1]) + b4.y;
+                            float f2 = __uint_as_float(v[4 * k + 2]) + b4.z, f3 = __uint_as_float(v[4 * k + 3]) + b4.w;
+                            if (p.act == SRK_LIN_ACT_GELU) { f0 = gelu_fast(f0); f1 = gelu_fast(f1); f2 = gelu_fast(f2); f3 = gelu_fast(f3); }
+                            pw[2 * k] = pack_bf16x2(f0, f1);
+                            pw[2 * k + 1] = pack_bf16x2(f2, f3);
+                        }
+                        if (live) {
+                            const int plane = c * 3 + (piece >> 1);
+                            const uint32_t key = static_cast<uint32_t>(tok + (((p.plane_phase_mask >> plane) & 1u) << 2)) & 7u;
+                            uint8_t* dst = p.out_planes + plane * p.out_plane_stride + tok * 128;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                st_global_v4b(dst + (((4 * (piece & 1) + k) ^ key) << 4), pw[4 * k], pw[4 * k + 1], pw[4 * k + 2], pw[4 * k + 3]);
+                        }
+                    }
+                } else {
+                    if (!first_tile && !stage_alias) {      // the previous tile's copies no longer read the staging rows
+                        if (g == 0) bulk_wait_read0();
+                        named_bar_sync(2 + q, 64);
+                    }
+                    stage_rows_and_bulk_store(acc, 0u, stage, stage, 32, s_vec, p.y, p.ld_out, p.add_residual, q, g, lane, tok_of_row);
+                    if (stage_alias && g == 0) {
+                        bulk_wait_read0();
+                        mbar_arrive(&bars[LB_DRAIN]);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&bars[LB_ACCE + buf]);
+            }
+            first_tile = false;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+cudaError_t launch_token_linear(const LinearParams& p, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(token_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_smem(3, true));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    const bool need_stage = p.out_mode == SRK_LIN_OUT_ROWS && p.k_atoms == 3;
+    const uint32_t smem = lin_smem(p.k_atoms, need_stage);
+    const int grid = p.n_tiles < sms ? p.n_tiles : sms;
+    token_linear_kernel<<<grid, LIN_THREADS, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace srk

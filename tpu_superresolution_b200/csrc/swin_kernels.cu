@@ -22,13 +22,13 @@
 
 #include "kernels.h"
 #include "umma.cuh"
+#include "rowops.cuh"
 
 namespace srk {
 
 constexpr int NTHREADS = 320;          // K2: producer + MMA + 8 row warps
 constexpr int NROWTHREADS = 256;
 constexpr int K1_THREADS = 448;        // K1: + 4 utility warps (q|k epilogues, next-tile normalisation)
-constexpr uint32_t ATOM_A = 16384;      // 128 rows x 128 B: one k-atom of a 128-row operand image
 constexpr uint32_t VT_ATOM = 24576;     // 192 rows x 128 B: one k-atom (64 keys) of the V^T image
 constexpr uint32_t RING_STAGE = 24576;  // largest weight slab (192 rows x 64 k)
 constexpr int RING_N = 3;
@@ -54,156 +54,6 @@ __device__ __forceinline__ void stagger_start(int cycles) {
     if (wait > 0) {
         const long long t0 = clock64();
         while (clock64() - t0 < wait) {}
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// shared helpers for the 256 row threads
-// ------------------------------------------------------------------------------------------------
-// (x - mean) * rstd of 16 token rows per warp -> bf16 SW128 image at `xa` (3 k-atoms).  LayerNorm's affine
-// (gamma, beta) is folded into the following GEMM's weights / bias at pack time (packing.py).
-// Half-warp per token: 16 lanes x 3 float4 cover the 180 channels (45 float4) fully coalesced.  All 24 loads
-// of a lane are issued before the first use (one exposed memory latency per tile).
-template <typename TokFn>
-__device__ __forceinline__ void ln_rows_to_image(const float* __restrict__ x, int ld, int apply_ln, uint32_t xa, int cw8,
-                                                 int lane, TokFn tok_of_row) {
-    const int l16 = lane & 15;
-    const bool live2 = l16 < 13;            // float4 index l16 + 32 < 45
-    float4 v[8][3];
-#pragma unroll
-    for (int pass = 0; pass < 8; ++pass) {
-        const int r = cw8 * 16 + pass * 2 + (lane >> 4);
-        const int64_t tok = tok_of_row(r);
-        const float4* src = reinterpret_cast<const float4*>(x + (tok >= 0 ? tok : 0) * ld) + l16;
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        v[pass][0] = tok >= 0 ? __ldg(src) : z;
-        v[pass][1] = tok >= 0 ? __ldg(src + 16) : z;
-        v[pass][2] = (tok >= 0 && live2) ? __ldg(src + 32) : z;
-    }
-    // statistics of all 8 passes first, then the 4 butterfly rounds over all passes at once: the 16 shuffles of a
-    // round are independent, so their latency overlaps instead of serialising 8 x 4 dependent steps
-    float s[8], q[8];
-#pragma unroll
-    for (int pass = 0; pass < 8; ++pass) {
-        float4(&w)[3] = v[pass];
-        s[pass] = 0.f; q[pass] = 0.f;
-#pragma unroll
-        for (int jj = 0; jj < 3; ++jj) {
-            s[pass] += (w[jj].x + w[jj].y) + (w[jj].z + w[jj].w);
-            q[pass] = fmaf(w[jj].x, w[jj].x, q[pass]); q[pass] = fmaf(w[jj].y, w[jj].y, q[pass]);
-            q[pass] = fmaf(w[jj].z, w[jj].z, q[pass]); q[pass] = fmaf(w[jj].w, w[jj].w, q[pass]);
-        }
-    }
-    if (apply_ln) {
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {
-#pragma unroll
-            for (int pass = 0; pass < 8; ++pass) {
-                s[pass] += __shfl_xor_sync(0xffffffffu, s[pass], o);
-                q[pass] += __shfl_xor_sync(0xffffffffu, q[pass], o);
-            }
-        }
-    }
-    const uint32_t r0 = cw8 * 16 + (lane >> 4);
-#pragma unroll
-    for (int pass = 0; pass < 8; ++pass) {
-        float4(&w)[3] = v[pass];
-        if (apply_ln) {
-            const float mean = s[pass] * (1.0f / SRK_DIM);
-            const float var = fmaxf(fmaf(-mean, mean, q[pass] * (1.0f / SRK_DIM)), 0.f);
-            const float rstd = rsqrtf(var + 1e-5f);
-            const float nm = -mean * rstd;
-#pragma unroll
-            for (int jj = 0; jj < 3; ++jj) {
-                w[jj].x = fmaf(w[jj].x, rstd, nm); w[jj].y = fmaf(w[jj].y, rstd, nm);
-                w[jj].z = fmaf(w[jj].z, rstd, nm); w[jj].w = fmaf(w[jj].w, rstd, nm);
-            }
-            if (!live2) w[2] = make_float4(0.f, 0.f, 0.f, 0.f);      // padded channels 180..191 stay exactly zero
-        }
-        const uint32_t r = r0 + 2 * pass;
-        const uint32_t off = xa + sw128_off(r, l16 >> 1) + (l16 & 1) * 8;
-#pragma unroll
-        for (int jj = 0; jj < 3; ++jj)      // channel 4f = 64*jj + 4*l16 -> atom jj, chunk l16>>1, byte (l16&1)*8
-            st_shared_v2(off + jj * ATOM_A, pack_bf16x2(w[jj].x, w[jj].y), pack_bf16x2(w[jj].z, w[jj].w));
-    }
-}
-
-// 32 fp32 accumulators (+ per-column bias from smem | * scale) -> 4 x 16-byte bf16 chunks of one image row.
-template <bool HAS_BIAS, bool HAS_SCALE>
-__device__ __forceinline__ void store_row_chunks(uint32_t img_atom, uint32_t row, uint32_t c16base, const uint32_t (&v)[32],
-                                                 const float* bias, float scale) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        float f[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * k + e]);
-        if (HAS_BIAS) {
-            const float4 b0 = reinterpret_cast<const float4*>(bias)[2 * k], b1 = reinterpret_cast<const float4*>(bias)[2 * k + 1];
-            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-        }
-        if (HAS_SCALE) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] *= scale;
-        }
-        st_shared_v4(img_atom + sw128_off(row, c16base + k), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                     pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-    }
-}
-
-// Final epilogue shared by K1/K2: accumulator (+bias) -> fp32 rows staged in shared memory in the exact global row
-// layout (720 B per token row) -> the TMA engine writes them out with one bulk copy per contiguous run of tokens.
-// With add_residual the copy is `cp.reduce.async.bulk ... add.f32`: the residual stream is updated in place
-// (y += delta), so the shortcut is never loaded into the SM.  Thread = accumulator row; the two groups fill columns
-// [96 g, 96 g + 96) of the same rows.  `half` / `nhalf` let a caller with < 92 KB of staging do the 32 rows of each
-// lane quadrant in two passes of 16.
-constexpr uint32_t ROW_BYTES = SRK_DIM * 4;     // 720
-// Staging geometry: rows 0 .. main_rows-1 of every lane quadrant live at stage_main + (q * main_rows + r) * 720, the
-// remaining rows at stage_tail + (q * (32 - main_rows) + r - main_rows) * 720 (K1 has no single 92 KB hole).
-template <typename TokFn>
-__device__ __forceinline__ void stage_rows_and_bulk_store(uint32_t tmem_acc, uint32_t lanebase, uint8_t* stage_main, uint8_t* stage_tail,
-                                                          int main_rows, const float* s_bias, float* __restrict__ y, int ld_out,
-                                                          int add_residual, int q, int g, int lane, TokFn tok_of_row) {
-    uint8_t* const my_row = lane < main_rows ? stage_main + (q * main_rows + lane) * ROW_BYTES
-                                             : stage_tail + (q * (32 - main_rows) + lane - main_rows) * ROW_BYTES;
-    float* dst = reinterpret_cast<float*>(my_row);
-#pragma unroll
-    for (int ci = 0; ci < 3; ++ci) {
-        const int c = 3 * g + ci;
-        uint32_t v[32];
-        tmem_ld32(tmem_acc + lanebase + 32 * c, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (32 * c + 4 * k < SRK_DIM) {
-                const float4 b = reinterpret_cast<const float4*>(s_bias + 32 * c)[k];
-                float4 o;
-                o.x = __uint_as_float(v[4 * k + 0]) + b.x;
-                o.y = __uint_as_float(v[4 * k + 1]) + b.y;
-                o.z = __uint_as_float(v[4 * k + 2]) + b.z;
-                o.w = __uint_as_float(v[4 * k + 3]) + b.w;
-                *reinterpret_cast<float4*>(dst + 32 * c + 4 * k) = o;
-            }
-        }
-    }
-    fence_proxy_async_smem();                   // generic-proxy smem writes -> visible to the bulk copy engine
-    named_bar_sync(2 + q, 64);                  // both groups of this lane quadrant have written their columns
-    if (g == 0) {
-        // one bulk copy per maximal run of tokens that are contiguous in memory (and in the staging buffer)
-        const int64_t tok = tok_of_row(q * 32 + lane);
-        const int64_t prev = __shfl_up_sync(0xffffffffu, tok, 1);
-        const bool valid = tok >= 0;
-        const bool start = valid && (lane == 0 || lane == main_rows || ld_out != SRK_DIM || prev < 0 || tok != prev + 1);
-        const uint32_t m_start = __ballot_sync(0xffffffffu, start);
-        const uint32_t m_stop = m_start | ~__ballot_sync(0xffffffffu, valid);      // next start or first invalid row ends a run
-        if (start) {
-            const uint32_t after = lane == 31 ? 0u : (m_stop >> (lane + 1));
-            const int len = after ? __ffs(after) : (32 - lane);
-            float* gdst = y + tok * ld_out;
-            if (add_residual) bulk_s2g_add_f32(gdst, smem_u32(my_row), len * ROW_BYTES);
-            else              bulk_s2g(gdst, smem_u32(my_row), len * ROW_BYTES);
-            bulk_commit();
-        }
-        __syncwarp();
     }
 }
 
@@ -647,16 +497,6 @@ static_assert(128 * 720 <= 6 * ATOM_A, "store staging size");
 constexpr uint32_t TC_F1A = 0, TC_F1B = 128;
 constexpr uint32_t TC_F2 = 256;                // fc2 accumulator, 192 cols
 enum { MB_FULL = 0, MB_EMPTY = 3, MB_XA = 6, MB_F1A = 7, MB_F1B = 8, MB_HR0 = 9, MB_HR1 = 10, MB_HR2 = 11, MB_F2 = 12, MB_COUNT = 13 };
-
-// gelu(x) = x Phi(x).  Phi(x) = 0.5 (1 + erf(x / sqrt 2)) is evaluated as 0.5 (1 + tanh(x (c1 + c3 u + c5 u^2))),
-// u = min(x^2, 64): minimax fit, |error| <= 2.6e-5 on the GELU output for all x, plus the MUFU.TANH error (2^-11 rel.)
-// -- both far below the bf16 rounding (2^-9 rel.) applied to the result right after.  One MUFU per element.
-__device__ __forceinline__ float gelu_fast(float x) {
-    const float u2 = fminf(x * x, 64.0f);
-    const float qv = x * fmaf(u2, fmaf(u2, -3.51517176e-04f, 3.70056486e-02f), 7.97507881e-01f);
-    const float hx = 0.5f * x;
-    return fmaf(hx, tanh_approx(qv), hx);
-}
 
 __global__ void __launch_bounds__(NTHREADS, 1) swin_mlp_kernel(const MlpParams p) {
     extern __shared__ uint8_t smem_raw[];
