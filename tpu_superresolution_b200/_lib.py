@@ -32,6 +32,23 @@ class MlpDesc(Structure):
                 ("add_residual", c_int32)]
 
 
+class LinearDesc(Structure):
+    _fields_ = [("num_tokens", c_int64)] + [(n, c_int32) for n in ("a_mode", "k_atoms", "ld_in", "apply_ln", "n_chunks", "act",
+                                                                    "out_mode", "ld_out", "add_residual")] + \
+               [("plane_phase_mask", ctypes.c_uint32)]
+
+
+class WinAttnDesc(Structure):
+    _fields_ = [(n, c_int32) for n in ("kind", "batch", "height", "width", "shift_y", "shift_x", "mask_shift", "n_heads",
+                                       "emask_nw", "out_mode", "out_ld", "out_col0")]
+
+
+LIN_A_ROWS, LIN_A_PLANES = 0, 1
+LIN_OUT_PLANES, LIN_OUT_ROWS = 0, 1
+LIN_ACT_NONE, LIN_ACT_GELU = 0, 1
+LIN_SLAB_BYTES = 24576
+WA_HAT_WMSA, WA_HAT_OCAB, WA_DAT_8x32, WA_DAT_32x8 = 0, 1, 2, 3
+
 _lib = None
 # bench.py sets this to a dict to get CUDA-event timings of every launch: {"swin_attn": [(ev0, ev1), ...], ...}
 PROFILE = None
@@ -72,12 +89,17 @@ def load():
     lib.srk_stitch_accumulate.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                           c_int32, c_int32, c_void_p]
     lib.srk_stitch_normalize.argtypes = [c_void_p, c_void_p, c_int32, c_int64, c_void_p]
+    lib.srk_linear_fwd.argtypes = [POINTER(LinearDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.srk_window_attention_fwd.argtypes = [POINTER(WinAttnDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                             c_void_p, c_void_p]
+    lib.srk_window_attention_table_floats.argtypes = [c_int32]
     lib.srk_debug_set_timeline.argtypes = [c_void_p]
     lib.srk_debug_set_timeline.restype = None
     lib.srk_debug_set_stagger.argtypes = [c_int32, c_int32]
     lib.srk_debug_set_stagger.restype = None
     for f in ("srk_swin_attn_fwd", "srk_swin_mlp_fwd", "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd",
-              "srk_stitch_accumulate", "srk_stitch_normalize"):
+              "srk_stitch_accumulate", "srk_stitch_normalize", "srk_linear_fwd", "srk_window_attention_fwd",
+              "srk_window_attention_table_floats"):
         getattr(lib, f).restype = c_int32
     if lib.srk_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libsrk.so ABI {lib.srk_abi_version()} != expected {ABI_VERSION}; rebuild")
@@ -86,7 +108,8 @@ def load():
 
 
 EXPORTS = ("srk_abi_version", "srk_last_error_string", "srk_launch_count", "srk_swin_attn_fwd", "srk_swin_mlp_fwd",
-           "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd", "srk_stitch_accumulate", "srk_stitch_normalize", "srk_debug_set_timeline", "srk_debug_set_stagger")
+           "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd", "srk_stitch_accumulate", "srk_stitch_normalize", "srk_debug_set_timeline", "srk_debug_set_stagger",
+           "srk_linear_fwd", "srk_window_attention_fwd", "srk_window_attention_table_floats")
 
 
 def _check(rc: int, lib) -> None:
@@ -156,3 +179,43 @@ def stitch_normalize(E, Wt, *, channels, pixels) -> None:
     lib = load()
     _require_cuda_f32(E, Wt)
     _check(lib.srk_stitch_normalize(E.data_ptr(), Wt.data_ptr(), channels, pixels, _stream()), lib)
+
+
+_ZERO_PAGES = {}
+
+
+def zero_page(device) -> torch.Tensor:
+    """4 KB of device zeros: source of the bulk copies that fill OCAB's out-of-image key rows."""
+    key = str(device)
+    if key not in _ZERO_PAGES:
+        _ZERO_PAGES[key] = torch.zeros(4096, dtype=torch.uint8, device=device)
+    return _ZERO_PAGES[key]
+
+
+def linear(a, wstream, bias, out, *, num_tokens, a_mode, k_atoms=3, ld_in=0, apply_ln=False, n_chunks, act=LIN_ACT_NONE,
+           out_mode, ld_out=0, add_residual=False, plane_phase_mask=0) -> None:
+    """srk_linear_fwd: a = fp32 rows (A_ROWS) or uint8/bf16 plane buffer (A_PLANES); out = plane buffer or fp32 rows."""
+    lib = load()
+    for t in (a, wstream, bias, out):
+        if not t.is_cuda:
+            raise RuntimeError("tpu_superresolution_b200 kernels need CUDA tensors (no CPU fallback)")
+    if wstream.numel() * wstream.element_size() != n_chunks * k_atoms * LIN_SLAB_BYTES or bias.numel() != n_chunks * 192:
+        raise RuntimeError("linear: weight stream / bias size does not match n_chunks, k_atoms")
+    d = LinearDesc(num_tokens, a_mode, k_atoms, ld_in, int(apply_ln), n_chunks, act, out_mode, ld_out, int(add_residual),
+                   plane_phase_mask)
+    with _timed("linear"):
+        _check(lib.srk_linear_fwd(ctypes.byref(d), a.data_ptr(), wstream.data_ptr(), bias.data_ptr(), out.data_ptr(), _stream()), lib)
+
+
+def window_attention(q_planes, k_planes, v_planes, table, out, *, kind, batch, height, width, shift=(0, 0), mask_shift=False,
+                     n_heads=6, emask=None, out_mode=0, out_ld=0, out_col0=0) -> None:
+    """srk_window_attention_fwd on plane buffers written by linear()."""
+    lib = load()
+    if table.numel() != 2 * ((n_heads + 1) // 2) * lib.srk_window_attention_table_floats(kind):
+        raise RuntimeError("window_attention: bias table size does not match kind / n_heads")
+    d = WinAttnDesc(kind, batch, height, width, shift[0], shift[1], int(mask_shift), n_heads,
+                    0 if emask is None else emask.shape[0], out_mode, out_ld, out_col0)
+    with _timed("window_attention"):
+        _check(lib.srk_window_attention_fwd(ctypes.byref(d), q_planes.data_ptr(), k_planes.data_ptr(), v_planes.data_ptr(),
+                                            table.data_ptr(), 0 if emask is None else emask.data_ptr(),
+                                            zero_page(out.device).data_ptr(), out.data_ptr(), _stream()), lib)

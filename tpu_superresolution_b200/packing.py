@@ -143,3 +143,96 @@ def pack_mlp(fc1_w, fc1_b, fc2_w, fc2_b, ln_w=None, ln_b=None) -> Tuple[torch.Te
     if fc2_b is not None:
         vec[L.MV_B2:L.MV_B2 + C] = fc2_b.detach().float()
     return wstream.to(dev), vec.to(dev)
+
+
+# ------------------------------------------------------------------------------------------------
+# HAT / DAT path: token-linear weight streams (csrc/linear_kernel.cu) and strided bias tables (csrc/winattn_kernel.cu)
+# ------------------------------------------------------------------------------------------------
+def pack_linear_stream(w_pad: torch.Tensor) -> torch.Tensor:
+    """(n_chunks * 192, k_atoms * 64) padded weight -> uint8 stream of n_chunks x k_atoms swizzled slabs (192 x 64 bf16)."""
+    N, K = w_pad.shape
+    assert N % 192 == 0 and K % 64 == 0
+    slabs = []
+    for c in range(N // 192):
+        slabs += _slabs(w_pad[192 * c:192 * (c + 1)])
+    return torch.cat([s.reshape(-1) for s in slabs]).contiguous().view(torch.uint8)
+
+
+@torch.no_grad()
+def pack_qkv_planes(qkv_w, qkv_b, ln_w=None, ln_b=None, scale=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """qkv Linear (540, 180) -> (wstream, bias[576]) producing 9 planes: q heads (0,1) (2,3) (4,5), then k, then v, each
+    head padded 30 -> 32.  LayerNorm's affine is folded in; q carries head_dim**-0.5 * log2(e) (hat_arch.py:182, exp2 softmax).
+    Unlike the SwinIR kernel the k and v biases stay: OCAB zero-pads the PROJECTED k, v (hat_arch.py:409), so they are not
+    row constants there."""
+    dev = qkv_w.device
+    qkv_w, qkv_b, ln_w, ln_b = [None if t is None else t.detach().cpu().double() for t in (qkv_w, qkv_b, ln_w, ln_b)]
+    C = L.DIM
+    if tuple(qkv_w.shape) != (3 * C, C):
+        raise RuntimeError(f"unsupported qkv geometry {tuple(qkv_w.shape)}: kernels serve dim 180 / 6 heads only")
+    scale = (L.HEAD_DIM ** -0.5) if scale is None else float(scale)
+    b = torch.zeros(3 * C, dtype=torch.float64) if qkv_b is None else qkv_b.clone()
+    w = qkv_w.clone()
+    if ln_b is not None:
+        b = b + w @ ln_b
+    if ln_w is not None:
+        w = w * ln_w[None, :]
+    w[:C] *= scale * LOG2E
+    b[:C] *= scale * LOG2E
+    w_pad = torch.cat([_pad_cols(_pad_heads(w[i * C:(i + 1) * C].float()), L.DIM_PAD) for i in range(3)], 0)   # (576, 192)
+    b_pad = torch.cat([_pad_heads(b[i * C:(i + 1) * C].float()) for i in range(3)], 0)
+    return pack_linear_stream(w_pad).to(dev), b_pad.contiguous().to(dev)
+
+
+@torch.no_grad()
+def pack_proj_planes(proj_w, proj_b) -> Tuple[torch.Tensor, torch.Tensor]:
+    """proj Linear (180, 180) consuming the attention output planes (K index = head * 32 + d) -> (wstream, bias[192])."""
+    dev = proj_w.device
+    C = L.DIM
+    if tuple(proj_w.shape) != (C, C):
+        raise RuntimeError(f"unsupported proj geometry {tuple(proj_w.shape)}")
+    wp = proj_w.detach().cpu().float().view(C, L.HEADS, L.HEAD_DIM)
+    w_pad = wp.new_zeros(L.DIM_PAD, L.HEADS, L.HEAD_PAD)
+    w_pad[:C, :, :L.HEAD_DIM] = wp
+    b = torch.zeros(L.DIM_PAD)
+    if proj_b is not None:
+        b[:C] = proj_b.detach().cpu().float()
+    return pack_linear_stream(w_pad.reshape(L.DIM_PAD, L.DIM_PAD)).to(dev), b.to(dev)
+
+
+@torch.no_grad()
+def pack_bias_table_wmsa(table: torch.Tensor, ws: int = 16, sy: int = 48) -> torch.Tensor:
+    """(961, nH) relative-position table (hat_arch.py:153-154) -> [nH][31 * sy] floats * log2(e); entry dy * sy + dx holds the
+    bias of query-key offset (dy, dx) = (yi - yj + ws - 1, xi - xj + ws - 1).  The padded row stride sy keeps the row threads'
+    shared-memory reads bank-conflict free (16 query columns per warp -> stride = 16 mod 32)."""
+    n = 2 * ws - 1
+    t = table.detach().cpu().float().t().reshape(-1, n, n) * LOG2E
+    out = torch.zeros(t.shape[0], n, sy)
+    out[:, :, :n] = t
+    return out.reshape(t.shape[0], n * sy).contiguous().to(table.device)
+
+
+@torch.no_grad()
+def pack_bias_table_ocab(table: torch.Tensor, ws: int = 16, wse: int = 24, sy: int = 48) -> torch.Tensor:
+    """(1521, nH) OCAB table -> [nH][39 * sy] * log2(e) with entry dy * sy + dx for (dy, dx) = (yi - yj + wse - 1, xi - xj + wse - 1).
+
+    hat_arch.py:911-918 indexes the table with ((yj - yi) + ws - wse + 1) * (ws + wse - 1) + ((xj - xi) + ws - wse + 1), which is
+    negative for most pairs and wraps (python indexing) -- SURVEY.md A.3; the wrap is applied here, once."""
+    n = ws + wse - 1
+    d = torch.arange(n)
+    e = ws - d                      # (yj - yi) + ws - wse + 1 with yj - yi = wse - 1 - dy
+    idx = (e[:, None] * n + e[None, :]) % (n * n)
+    t = table.detach().cpu().float()[idx.reshape(-1)].reshape(n, n, -1).permute(2, 0, 1) * LOG2E
+    out = torch.zeros(t.shape[0], n, sy)
+    out[:, :, :n] = t
+    return out.reshape(t.shape[0], n * sy).contiguous().to(table.device)
+
+
+def unswizzle_planes(planes: torch.Tensor, phase: int = 0) -> torch.Tensor:
+    """(P, T, 64) bf16 plane buffer -> logical channel order (inverse of chunk ^ ((tok + phase) & 7)); debugging / tests."""
+    P, T, _ = planes.shape
+    ch = planes.reshape(P, T, 8, 8)
+    tok = torch.arange(T, device=planes.device)
+    key = (tok + phase) & 7
+    c = torch.arange(8, device=planes.device)
+    src = c[None, :] ^ key[:, None]                      # logical chunk c lives at position c ^ key
+    return torch.gather(ch, 2, src[None, :, :, None].expand(P, T, 8, 8)).reshape(P, T, 64)
