@@ -124,6 +124,9 @@ int srk_linear_fwd(const SrkLinearDesc* desc, const void* a, const void* wstream
  * q/k/v: plane p = heads 2p, 2p+1 (32 padded dims each), [p][batch*height*width][64] bf16, swizzled as written by
  * srk_linear_fwd.  bias_table: [2 * ceil(n_heads / 2)][srk_window_attention_table_floats(kind)] floats, already * log2(e),
  * entry (dy * SY + dx) for query-key offset (dy, dx) (see packing.py).  q must already carry scale * log2(e).
+ * The softmax row sum is taken from the P v GEMM: padded dim 30 of every v head must be 1 (packing.py sets that bias).
+ * pad_pages: 4096 zero bytes (k rows of OCAB's zero padding) followed by 32 v padding rows of 128 B (zeros except bf16 1.0
+ * at dim 30 of both heads, chunk-swizzled with row & 7) -- packing.make_pad_pages().
  * out_mode 0: bf16 planes [ceil(n_heads/2)][tokens][64] swizzled with tok & 7 (A operand of the proj srk_linear_fwd);
  * out_mode 1: fp32 rows, out[tok * out_ld + out_col0 + head * 30 + d]. */
 enum { SRK_WA_HAT_WMSA = 0, SRK_WA_HAT_OCAB = 1, SRK_WA_DAT_8x32 = 2, SRK_WA_DAT_32x8 = 3 };
@@ -139,7 +142,7 @@ typedef struct SrkWinAttnDesc {
 } SrkWinAttnDesc;
 
 int srk_window_attention_fwd(const SrkWinAttnDesc* desc, const void* q_planes, const void* k_planes, const void* v_planes,
-                             const float* bias_table, const float* emask, const void* zero_page /* >= 4096 zero bytes */,
+                             const float* bias_table, const float* emask, const void* pad_pages /* 8192 bytes, see below */,
                              void* out, void* stream);
 int srk_window_attention_table_floats(int32_t kind);
 
@@ -168,6 +171,8 @@ int64_t srk_launch_count(void);
 void srk_debug_set_timeline(void* device_buf);
 /* tuning: start skew (cycles per CTA index mod 4) of the attention / MLP kernels, see stagger_start() */
 void srk_debug_set_stagger(int attn_cycles, int mlp_cycles);
+/* tuning: cycles the second query-half group of srk_window_attention_fwd starts behind the first (default 4000) */
+void srk_debug_set_winattn_stagger(int cycles);
 
 #ifdef __cplusplus
 }

@@ -123,12 +123,13 @@ def cab(x_img: Tensor, p: Dict[str, Tensor], pre: str) -> Tensor:
 
 
 def hab(x: Tensor, x_size: Tuple[int, int], p: Dict[str, Tensor], pre: str, num_heads: int, ws: int, shift: int,
-        conv_scale: float) -> Tensor:
-    """HAB.forward, hat_arch.py:267-310."""
+        conv_scale: float, input_resolution: Optional[Tuple[int, int]] = None) -> Tensor:
+    """HAB.forward, hat_arch.py:267-310.  The window/shift clamp of :247-250 looks at the CONSTRUCTOR's input_resolution
+    (img_size), not at x_size: a 16x16 input to a model built for 64x64 still runs shifted 16x16 windows."""
     H, W = x_size
     B, L, C = x.shape
-    if min(H, W) <= ws:                                                          # :247-250
-        shift, ws = 0, min(H, W)
+    if input_resolution is not None and min(input_resolution) <= ws:             # :247-250
+        shift, ws = 0, min(input_resolution)
     xn = layer_norm(x, p[pre + "norm1.weight"], p[pre + "norm1.bias"])
     conv_x = image_to_tokens(cab(tokens_to_image(xn, x_size), p, pre + "conv_block."))   # on the UN-shifted LN1 output
     pix = window_token_pixels(H, W, ws, shift)

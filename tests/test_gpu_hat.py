@@ -54,8 +54,10 @@ def test_linear_qkv_planes(sd, ntok):
         L.linear(x.cuda(), qw, qb, planes, num_tokens=ntok, a_mode=L.LIN_A_ROWS, ld_in=180, apply_ln=True, n_chunks=3,
                  out_mode=L.LIN_OUT_PLANES, plane_phase_mask=mask)
         got = torch.cat([packing.unswizzle_planes(planes[p:p + 1], 4 if (mask >> p) & 1 else 0)[0] for p in range(9)], 1).float()
-        pad = got.view(ntok, 3, 6, 32)[..., 30:]
-        assert float(pad.abs().max()) == 0.0                       # padded head dims stay exactly zero
+        pad = got.view(ntok, 3, 6, 32)[..., 30:].clone()
+        assert bool((pad[:, 2, :, 0] == 1.0).all())                # ones column of v (softmax row sum via the P v GEMM)
+        pad[:, 2, :, 0] = 0.0
+        assert float(pad.abs().max()) == 0.0                       # the other padded head dims stay exactly zero
         assert _rel(got.view(ntok, 3, 6, 32)[..., :30].reshape(ntok, 540), ref) < 1.5e-2
 
 

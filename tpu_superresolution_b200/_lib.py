@@ -97,6 +97,8 @@ def load():
     lib.srk_debug_set_timeline.restype = None
     lib.srk_debug_set_stagger.argtypes = [c_int32, c_int32]
     lib.srk_debug_set_stagger.restype = None
+    lib.srk_debug_set_winattn_stagger.argtypes = [c_int32]
+    lib.srk_debug_set_winattn_stagger.restype = None
     for f in ("srk_swin_attn_fwd", "srk_swin_mlp_fwd", "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd",
               "srk_stitch_accumulate", "srk_stitch_normalize", "srk_linear_fwd", "srk_window_attention_fwd",
               "srk_window_attention_table_floats"):
@@ -109,7 +111,7 @@ def load():
 
 EXPORTS = ("srk_abi_version", "srk_last_error_string", "srk_launch_count", "srk_swin_attn_fwd", "srk_swin_mlp_fwd",
            "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd", "srk_stitch_accumulate", "srk_stitch_normalize", "srk_debug_set_timeline", "srk_debug_set_stagger",
-           "srk_linear_fwd", "srk_window_attention_fwd", "srk_window_attention_table_floats")
+           "srk_linear_fwd", "srk_window_attention_fwd", "srk_window_attention_table_floats", "srk_debug_set_winattn_stagger")
 
 
 def _check(rc: int, lib) -> None:
@@ -185,10 +187,11 @@ _ZERO_PAGES = {}
 
 
 def zero_page(device) -> torch.Tensor:
-    """4 KB of device zeros: source of the bulk copies that fill OCAB's out-of-image key rows."""
+    """8 KB padding pages (packing.make_pad_pages): source of the bulk copies that fill OCAB's out-of-image key / value rows."""
     key = str(device)
     if key not in _ZERO_PAGES:
-        _ZERO_PAGES[key] = torch.zeros(4096, dtype=torch.uint8, device=device)
+        from . import packing
+        _ZERO_PAGES[key] = packing.make_pad_pages(device)
     return _ZERO_PAGES[key]
 
 

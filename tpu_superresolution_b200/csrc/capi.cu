@@ -33,6 +33,7 @@ extern "C" {
 int srk_abi_version(void) { return SRK_ABI_VERSION; }
 const char* srk_last_error_string(void) { return g_err; }
 void srk_debug_set_stagger(int attn_cycles, int mlp_cycles) { srk::g_stagger_attn = attn_cycles; srk::g_stagger_mlp = mlp_cycles; }
+void srk_debug_set_winattn_stagger(int cycles) { srk::g_stagger_winattn = cycles; }
 void srk_debug_set_timeline(void* buf) { srk::g_timeline = static_cast<unsigned long long*>(buf); }
 int64_t srk_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
@@ -148,7 +149,8 @@ int srk_linear_fwd(const SrkLinearDesc* d, const void* a, const void* wstream, c
 int srk_window_attention_table_floats(int32_t kind) { return srk::winattn_table_floats(kind); }
 
 int srk_window_attention_fwd(const SrkWinAttnDesc* d, const void* q_planes, const void* k_planes, const void* v_planes,
-                             const float* bias_table, const float* emask, const void* zero_page, void* out, void* stream) {
+                             const float* bias_table, const float* emask, const void* pad_pages, void* out, void* stream) {
+    const void* zero_page = pad_pages;
     if (!d || !q_planes || !k_planes || !v_planes || !bias_table || !zero_page || !out) return fail("srk_window_attention_fwd: null argument");
     if (!aligned16(q_planes) || !aligned16(k_planes) || !aligned16(v_planes) || !aligned16(bias_table) || !aligned16(zero_page) || !aligned16(out))
         return fail("srk_window_attention_fwd: pointers must be 16-byte aligned");
@@ -190,6 +192,8 @@ int srk_window_attention_fwd(const SrkWinAttnDesc* d, const void* q_planes, cons
     } else {
         return fail("srk_window_attention_fwd: unknown out_mode %d", d->out_mode);
     }
+    p.dbg = srk::g_timeline;
+    p.stagger = srk::g_stagger_winattn;
     return check(srk::launch_winattn(d->kind, p, static_cast<cudaStream_t>(stream)), "srk_window_attention_fwd");
 }
 

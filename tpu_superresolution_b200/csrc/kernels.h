@@ -60,7 +60,7 @@ struct WinAttnParams {
     int64_t plane_stride;        // bytes between planes
     const float* tab;            // [2 * pairs][TABF] strided bias table, * log2(e)
     int c0;                      // table index of (query i, key j) = c0 + SY * (yi - yj) + (xi - xj)
-    const uint8_t* zero_page;    // >= 4 KB of zeros (OCAB padding)
+    const uint8_t* zero_page;    // 8 KB: 4 KB of zeros (padded k rows) + 4 KB v padding pattern (ones column, swizzled per row & 7)
     int B, H, W;
     int koff;                    // key-window offset relative to the query window (OCAB: -4)
     int shift_y, shift_x, wrap, mask_shift;
@@ -72,10 +72,12 @@ struct WinAttnParams {
     int64_t o_plane_stride;
     float* o_rows;
     int o_ld, o_col0;
+    unsigned long long* dbg;     // optional timeline buffer (srk_debug_set_timeline)
+    int stagger;                 // cycles group 1 starts behind group 0
 };
 
 extern unsigned long long* g_timeline;
-extern int g_stagger_attn, g_stagger_mlp;
+extern int g_stagger_attn, g_stagger_mlp, g_stagger_winattn;
 cudaError_t launch_swin_attn(const AttnParams& p, cudaStream_t stream);
 cudaError_t launch_swin_mlp(const MlpParams& p, cudaStream_t stream);
 cudaError_t launch_token_linear(const LinearParams& p, cudaStream_t stream);

@@ -44,7 +44,7 @@ constexpr float LOG2E = 1.4426950408889634f;
 // Optional per-CTA timeline (debug): CTA 0 writes clock64() at event `id` of its `it`-th tile.
 #define SRK_TL(dbgptr, it, id) do { if ((dbgptr) != nullptr && blockIdx.x == 0 && (it) < 8) (dbgptr)[(it) * 64 + (id)] = clock64(); } while (0)
 unsigned long long* g_timeline = nullptr;
-int g_stagger_attn = 0, g_stagger_mlp = 0;
+int g_stagger_attn = 0, g_stagger_mlp = 0, g_stagger_winattn = 4000;
 
 // All CTAs of a launch run the same phase sequence; started together they hit their memory phases (tile load, tile
 // store) at the same time and leave HBM / L2 idle in between.  Skewing the start of CTA i by (i mod 4) * `cycles`

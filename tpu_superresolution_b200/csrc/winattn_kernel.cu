@@ -10,7 +10,7 @@
 // eight 16-byte chunks of a token row permuted by chunk ^ ((token + phase) & 7).  Because a window row is a run of
 // consecutive tokens, ONE 1-D bulk TMA copy per window row drops it into shared memory as rows of a 128-byte-swizzled
 // UMMA operand image -- roll, window partition and the OCAB unfold are only the source addresses of those copies
-// (out-of-image OCAB keys are copied from a zero page).  Q and K are K-major operands (head hh at byte 64 hh of the
+// (out-of-image OCAB keys are copied from a padding page).  Q and K are K-major operands (head hh at byte 64 hh of the
 // row); V is consumed directly as an MN-major B operand (keys = K dimension), so no transpose exists anywhere.
 //
 // One persistent CTA per SM; work item = (window, head pair).  320 threads:
@@ -19,8 +19,8 @@
 //   warp 1      : tcgen05.mma issuer.  Per head and query half g: S_g = Q_g K^T (M 128 x N keys, fp32 in TMEM),
 //                 later O_g (+)= P_g V with P read from TMEM (bf16 pairs written over S by the row threads);
 //   warps 2..9  : two groups of 128 row threads, group g = queries [128 g, 128 g + 128); thread <-> TMEM lane <-> query.
-//                 Sweep 1: logits + position bias (+ mask) -> running max, written back; sweep 2: exp2, row sum,
-//                 P as bf16 pairs in place.  With several key chunks the O accumulator is rescaled in TMEM (online
+//                 Sweep 1: logits + position bias (+ mask) -> running max, written back; sweep 2: exp2, P as bf16
+//                 pairs in place (the row sum comes out of the P v GEMM: padded dim 30 of every V head is 1).  With several key chunks the O accumulator is rescaled in TMEM (online
 //                 softmax).  Finally O / rowsum -> bf16 plane rows (the proj GEMM's A operand) or fp32 rows.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -30,6 +30,8 @@
 #include "umma.cuh"
 
 namespace srk {
+
+#define WA_TL(dbgptr, slot, id) do { if ((dbgptr) != nullptr && (slot) < 8) (dbgptr)[(slot) * 64 + (id)] = clock64(); } while (0)
 
 namespace {
 constexpr float WA_LOG2E = 1.4426950408889634f;
@@ -45,6 +47,69 @@ __device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, ui
     asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 }  // namespace
+
+
+// ---- sweep 1 of the softmax: logits (exp2 domain, already scaled) + position bias (+ mask) -> running max; the biased
+//      logits are written back in place.  The TMEM load of piece pc + 1 is in flight while piece pc is processed.
+//      MASKED (shifted-window mask) is a separate instantiation so un-masked windows pay nothing for it.
+template <int KH, int KW, int SY, int NCH, bool MASKED>
+__device__ __forceinline__ float softmax_sweep1(uint32_t tacc, const float* rp, int c, const uint32_t (&rowmask)[KH],
+                                                const float* emrow, float mx) {
+    constexpr int NP = NCH / 32;
+    uint32_t va[32], vb[32];
+    tmem_ld32(tacc, va);
+#pragma unroll
+    for (int pc = 0; pc < NP; ++pc) {
+        uint32_t(&v)[32] = (pc & 1) ? vb : va;
+        tmem_ld_wait();
+        if (pc + 1 < NP) tmem_ld32(tacc + 32 * (pc + 1), (pc & 1) ? va : vb);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            const int col = c * NCH + 32 * pc + e, yj = col / KW, xj = col - yj * KW;
+            float sv = __uint_as_float(v[e]) + rp[-(SY * yj + xj)];
+            if (MASKED) {
+                if (!((rowmask[yj] >> xj) & 1u)) sv -= 100.0f * WA_LOG2E;
+            }
+            v[e] = __float_as_uint(sv);
+        }
+        if (emrow) {
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+                const float4 mk = __ldg(reinterpret_cast<const float4*>(emrow + c * NCH + 32 * pc + e));
+                v[e] = __float_as_uint(fmaf(mk.x, WA_LOG2E, __uint_as_float(v[e])));
+                v[e + 1] = __float_as_uint(fmaf(mk.y, WA_LOG2E, __uint_as_float(v[e + 1])));
+                v[e + 2] = __float_as_uint(fmaf(mk.z, WA_LOG2E, __uint_as_float(v[e + 2])));
+                v[e + 3] = __float_as_uint(fmaf(mk.w, WA_LOG2E, __uint_as_float(v[e + 3])));
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
+        tmem_st32(tacc + 32 * pc, v);
+    }
+    tmem_st_wait();
+    return mx;
+}
+
+// ---- sweep 2: p = exp2(s - max) as bf16 pairs written over the S columns already consumed.  The row sum is not
+//      accumulated here: padded dim 30 of every V head is 1, so the P v GEMM delivers sum_j p_ij in column 30 of O.
+template <int NCH>
+__device__ __forceinline__ void softmax_sweep2(uint32_t tacc, float mx) {
+    constexpr int NP = NCH / 32;
+    uint32_t va[32], vb[32];
+    tmem_ld32(tacc, va);
+#pragma unroll
+    for (int pc = 0; pc < NP; ++pc) {
+        uint32_t(&v)[32] = (pc & 1) ? vb : va;
+        tmem_ld_wait();
+        if (pc + 1 < NP) tmem_ld32(tacc + 32 * (pc + 1), (pc & 1) ? va : vb);
+        uint32_t pw[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2)
+            pw[e >> 1] = pack_bf16x2(ex2_approx(__uint_as_float(v[e]) - mx), ex2_approx(__uint_as_float(v[e + 1]) - mx));
+        tmem_st16(tacc + 16 * pc, pw);
+    }
+    tmem_st_wait();
+}
 
 template <int QH, int QW, int KH, int KW, int SY, int NCH>
 struct WinAttnCfg {
@@ -139,9 +204,12 @@ __global__ void __launch_bounds__(320, 1) winattn_kernel(const WinAttnParams p) 
                     int hi = xa + KW > p.W ? xa + KW - p.W : 0;            // zero columns on the right
                     if (y < 0 || y >= p.H) { lo = KW; hi = 0; }
                     const int mid = KW - lo - hi;
+                    // padded keys: k = 0; v = 0 except the ones column (dim 30 of each head) that carries the softmax row sum --
+                    // the pattern page is pre-swizzled per row & 7, so the copy starts at the destination row's phase
+                    const uint8_t* vpad = p.zero_page + 4096;
                     if (lo > 0) {
                         bulk_g2s(set + C::K_OFF + d0, p.zero_page, lo * 128, full);
-                        bulk_g2s(set + C::V_OFF + d0, p.zero_page, lo * 128, full);
+                        bulk_g2s(set + C::V_OFF + d0, vpad, lo * 128, full);
                     }
                     if (mid > 0) {
                         const int64_t t = (img0 + static_cast<int64_t>(y) * p.W + xa + lo) * 128;
@@ -150,7 +218,7 @@ __global__ void __launch_bounds__(320, 1) winattn_kernel(const WinAttnParams p) 
                     }
                     if (hi > 0) {
                         bulk_g2s(set + C::K_OFF + d0 + (lo + mid) * 128, p.zero_page, hi * 128, full);
-                        bulk_g2s(set + C::V_OFF + d0 + (lo + mid) * 128, p.zero_page, hi * 128, full);
+                        bulk_g2s(set + C::V_OFF + d0 + (lo + mid) * 128, vpad + ((lo + mid) & 7) * 128, hi * 128, full);
                     }
                 }
             }
@@ -163,43 +231,70 @@ __global__ void __launch_bounds__(320, 1) winattn_kernel(const WinAttnParams p) 
         if (lane == 0) {
             constexpr uint32_t IDESC_S = umma_idesc_bf16(128, NCH);
             constexpr uint32_t IDESC_PV = umma_idesc_bf16_bmn(128, 32);
-            uint32_t s = 0, ph = 0, ph_free[2] = {1, 1}, ph_pr[2] = {0, 0};
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                const int pair = item % npairs;
-                const int nh = (p.n_heads - 2 * pair) < 2 ? (p.n_heads - 2 * pair) : 2;
-                mbar_wait(&bars[W_FULL + s], ph);
-                tc_fence_after();
-                const uint32_t set = sbase + s * C::SET_BYTES;
-                for (int hh = 0; hh < nh; ++hh) {
-#pragma unroll 1
-                    for (int c = 0; c < NCHUNKS; ++c) {
+            // Event-driven: each query-half group g walks its own sequence of (item, head, key chunk) steps -- S = Q K^T when its
+            // TMEM region is free, P v when its P is written -- and the issuer serves whichever group is ready.  The groups are
+            // started half a step apart (see the row threads) so one is in the LDS-bound sweep 1 while the other is in the
+            // MUFU-bound sweep 2; a fixed service order would pull them back into lockstep.
+            int item_g[2] = {static_cast<int>(blockIdx.x), static_cast<int>(blockIdx.x)};
+            int k_g[2] = {0, 0}, hh_g[2] = {0, 0}, c_g[2] = {0, 0}, st_g[2] = {0, 0};
+            int k_full = -1, done[2] = {0, 0};
+            uint32_t ph_free[2] = {1, 1}, ph_pr[2] = {0, 0};
+            const long long t_start = clock64();
+            while (item_g[0] < p.n_items || item_g[1] < p.n_items) {
 #pragma unroll
-                        for (int g = 0; g < 2; ++g) {
-                            if (c == 0) {       // the group has drained the previous O accumulator (it aliases S when NCH = 256)
-                                mbar_wait(&bars[W_FREE + g], ph_free[g]); ph_free[g] ^= 1;
-                                tc_fence_after();
-                            }
-#pragma unroll
-                            for (int ks = 0; ks < 2; ++ks)
-                                umma_ss(tmem + 256 * g, umma_desc_sw128(set + C::Q_OFF + g * 16384 + 64 * hh + 32 * ks),
-                                        umma_desc_sw128(set + C::K_OFF + c * NCH * 128 + 64 * hh + 32 * ks), IDESC_S, ks);
-                            umma_commit(&bars[W_SF + g]);
+                for (int g = 0; g < 2; ++g) {
+                    if (item_g[g] >= p.n_items) continue;
+                    const int k = k_g[g];
+                    const uint32_t s = k % NSETS;
+                    if (k > k_full) {                       // first touch of this item's set: its images must have landed
+                        if (!mbar_test_wait(&bars[W_FULL + s], (k / NSETS) & 1)) continue;
+                        k_full = k;
+                        tc_fence_after();
+                    }
+                    const uint32_t set = sbase + s * C::SET_BYTES;
+                    const int pair = item_g[g] % npairs;
+                    const int nh = (p.n_heads - 2 * pair) < 2 ? (p.n_heads - 2 * pair) : 2;
+                    const int hh = hh_g[g], c = c_g[g];
+                    if (st_g[g] == 0) {
+                        if (c == 0) {       // the group has drained the previous O accumulator (it aliases S when NCH = 256)
+                            if (!mbar_test_wait(&bars[W_FREE + g], ph_free[g])) continue;
+                            ph_free[g] ^= 1;
+                            tc_fence_after();
                         }
 #pragma unroll
-                        for (int g = 0; g < 2; ++g) {
-                            mbar_wait(&bars[W_PR + g], ph_pr[g]); ph_pr[g] ^= 1;
-                            tc_fence_after();
+                        for (int ks = 0; ks < 2; ++ks)
+                            umma_ss(tmem + 256 * g, umma_desc_sw128(set + C::Q_OFF + g * 16384 + 64 * hh + 32 * ks),
+                                    umma_desc_sw128(set + C::K_OFF + c * NCH * 128 + 64 * hh + 32 * ks), IDESC_S, ks);
+                        umma_commit(&bars[W_SF + g]);
+                        st_g[g] = 1;
+                    } else {
+                        if (!mbar_test_wait(&bars[W_PR + g], ph_pr[g])) continue;
+                        ph_pr[g] ^= 1;
+                        tc_fence_after();
 #pragma unroll
-                            for (int kk = 0; kk < NCH / 16; ++kk)
-                                umma_ts(tmem + 256 * g + TC_OACC, tmem + 256 * g + 8 * kk,
-                                        umma_desc_sw128_mn(set + C::V_OFF + (c * NCH + 16 * kk) * 128 + 64 * hh), IDESC_PV,
-                                        (c | kk) != 0);
-                            umma_commit(&bars[W_OF + g]);
+                        for (int kk = 0; kk < NCH / 16; ++kk)
+                            umma_ts(tmem + 256 * g + TC_OACC, tmem + 256 * g + 8 * kk,
+                                    umma_desc_sw128_mn(set + C::V_OFF + (c * NCH + 16 * kk) * 128 + 64 * hh), IDESC_PV, (c | kk) != 0);
+                        umma_commit(&bars[W_OF + g]);
+                        st_g[g] = 0;
+                        if (++c_g[g] == NCHUNKS) {
+                            c_g[g] = 0;
+                            if (++hh_g[g] == nh) {          // this group is done with the item; the second one to finish releases the set
+                                hh_g[g] = 0;
+                                if (++done[k & 1] == 2) {
+                                    done[k & 1] = 0;
+                                    umma_commit(&bars[W_EMPTY + s]);
+                                }
+                                ++k_g[g];
+                                item_g[g] += gridDim.x;
+                            }
                         }
                     }
                 }
-                umma_commit(&bars[W_EMPTY + s]);
-                if (++s == NSETS) { s = 0; ph ^= 1; }
+                if (clock64() - t_start > SRK_WAIT_TIMEOUT_CYCLES) {
+                    printf("srk: winattn MMA issuer timeout (block %d)\n", (int)blockIdx.x);
+                    __trap();
+                }
             }
         }
         __syncwarp();
@@ -211,6 +306,9 @@ __global__ void __launch_bounds__(320, 1) winattn_kernel(const WinAttnParams p) 
         const int yi = qi / QW, xi = qi - yi * QW;
         const uint32_t tacc = tmem + (static_cast<uint32_t>(q * 32) << 16) + 256 * g;
         uint32_t s = 0, ph = 0, ph_sf = 0, ph_of = 0;
+        bool first_item = true;
+        unsigned long long* dbg = (blockIdx.x == 0 && (threadIdx.x == 64 || threadIdx.x == 192)) ? p.dbg : nullptr;   // first lane of each group
+        int slot = g;                                       // timeline slots: 2 * (head step) + group
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             const int pair = item % npairs, wg = item / npairs;
             const int b = wg / nw_img, w = wg - b * nw_img;
@@ -222,65 +320,56 @@ __global__ void __launch_bounds__(320, 1) winattn_kernel(const WinAttnParams p) 
             if (x >= p.W) x -= p.W;
             const int64_t tok = (static_cast<int64_t>(b) * p.H + y) * p.W + x;
             // closed form of the shifted-window mask (hat_arch.py:921-940, dat_arch.py:318-361): keys in another region get -100
-            uint32_t mh = 0xffffffffu, mw = 0xffffffffu;
+            uint32_t rowmask[KH];                           // bit xj of rowmask[yj]: key (yj, xj) is in this query's region
             bool masked = false;
             if (p.mask_shift) {
                 auto regy = [&](int pos) { return (pos >= p.H - QH ? 1 : 0) + (pos >= p.H - p.shift_y ? 1 : 0); };
                 auto regx = [&](int pos) { return (pos >= p.W - QW ? 1 : 0) + (pos >= p.W - p.shift_x ? 1 : 0); };
                 const int ry = regy(wy * QH + yi), rx = regx(wx * QW + xi);
-                mh = 0; mw = 0;
-                for (int a = 0; a < KH; ++a) mh |= (regy(wy * QH + a) == ry ? 1u : 0u) << a;
+                uint32_t mw = 0;
                 for (int a = 0; a < KW; ++a) mw |= (regx(wx * QW + a) == rx ? 1u : 0u) << a;
-                const uint32_t fh = KH == 32 ? 0xffffffffu : ((1u << KH) - 1u), fw = KW == 32 ? 0xffffffffu : ((1u << KW) - 1u);
-                masked = (mh != fh) || (mw != fw);
+                const uint32_t fw = KW == 32 ? 0xffffffffu : ((1u << KW) - 1u);
+                masked = mw != fw;
+#pragma unroll
+                for (int a = 0; a < KH; ++a) {
+                    const bool same = regy(wy * QH + a) == ry;
+                    rowmask[a] = same ? mw : 0u;
+                    masked = masked || !same;
+                }
+                masked = __any_sync(0xffffffffu, masked);   // warp-uniform choice of the sweep variant
+            } else {
+#pragma unroll
+                for (int a = 0; a < KH; ++a) rowmask[a] = 0xffffffffu;
             }
             const float* emrow = nullptr;
             if (p.emask) emrow = p.emask + (static_cast<int64_t>(wg % p.emask_nw) * C::NQ + qi) * NK;
 
             mbar_wait(&bars[W_FULL + s], ph);               // the pair's bias tables have landed
+            if (g == 1 && (first_item || NSETS == 1) && p.stagger > 0) {
+                // start half a step behind group 0 (with one set both groups restart together at every item)
+                const long long t0 = clock64();
+                while (clock64() - t0 < p.stagger) {}
+            }
+            first_item = false;
             const float* tab_s = reinterpret_cast<const float*>(sm + s * C::SET_BYTES + C::T_OFF);
             const int base_i = p.c0 + SY * yi + xi;
 #pragma unroll 1
             for (int hh = 0; hh < nh; ++hh) {
                 const float* rp = tab_s + hh * TABF + base_i;
-                float m_run = -1.0e30f, l0 = 0.f, l1 = 0.f;
+                float m_run = -1.0e30f;
+                WA_TL(dbg, slot, 0);
 #pragma unroll
                 for (int c = 0; c < NCHUNKS; ++c) {
                     mbar_wait(&bars[W_SF + g], ph_sf); ph_sf ^= 1;
                     tc_fence_after();
-                    // ---- sweep 1: logits (already scaled, exp2 domain) + bias (+ mask) -> max; written back in place
-                    float mx = m_run;
-#pragma unroll
-                    for (int pc = 0; pc < NCH / 32; ++pc) {
-                        uint32_t v[32];
-                        tmem_ld32(tacc + 32 * pc, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) {
-                            const int col = c * NCH + 32 * pc + e, yj = col / KW, xj = col - yj * KW;
-                            float sv = __uint_as_float(v[e]) + rp[-(SY * yj + xj)];
-                            if (masked) sv = (((mh >> yj) & (mw >> xj)) & 1u) ? sv : sv - 100.0f * WA_LOG2E;
-                            v[e] = __float_as_uint(sv);
-                        }
-                        if (emrow) {
-#pragma unroll
-                            for (int e = 0; e < 32; e += 4) {
-                                const float4 mk = __ldg(reinterpret_cast<const float4*>(emrow + c * NCH + 32 * pc + e));
-                                v[e] = __float_as_uint(fmaf(mk.x, WA_LOG2E, __uint_as_float(v[e])));
-                                v[e + 1] = __float_as_uint(fmaf(mk.y, WA_LOG2E, __uint_as_float(v[e + 1])));
-                                v[e + 2] = __float_as_uint(fmaf(mk.z, WA_LOG2E, __uint_as_float(v[e + 2])));
-                                v[e + 3] = __float_as_uint(fmaf(mk.w, WA_LOG2E, __uint_as_float(v[e + 3])));
-                            }
-                        }
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
-                        tmem_st32(tacc + 32 * pc, v);
-                    }
-                    tmem_st_wait();
+                    WA_TL(dbg, slot, 1 + 4 * c);
+                    const float mx = masked ? softmax_sweep1<KH, KW, SY, NCH, true>(tacc, rp, c, rowmask, emrow, m_run)
+                                            : softmax_sweep1<KH, KW, SY, NCH, false>(tacc, rp, c, rowmask, emrow, m_run);
+                    WA_TL(dbg, slot, 2 + 4 * c);
                     if (c > 0) {
-                        // ---- online softmax: rescale the running sum and the O accumulator (previous P v has completed)
+                        // ---- online softmax: rescale the O accumulator (its column 30 is the running row sum); the previous
+                        //      P v has completed
                         const float corr = ex2_approx(m_run - mx);
-                        l0 *= corr; l1 *= corr;
                         mbar_wait(&bars[W_OF + g], ph_of); ph_of ^= 1;
                         tc_fence_after();
                         uint32_t o[32];
@@ -291,33 +380,22 @@ __global__ void __launch_bounds__(320, 1) winattn_kernel(const WinAttnParams p) 
                         tmem_st32(tacc + TC_OACC, o);
                     }
                     m_run = mx;
-                    // ---- sweep 2: p = exp2(s - max) as bf16 pairs, written over the S columns already consumed
-#pragma unroll
-                    for (int pc = 0; pc < NCH / 32; ++pc) {
-                        uint32_t v[32], pw[16];
-                        tmem_ld32(tacc + 32 * pc, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int e = 0; e < 32; e += 2) {
-                            const float e0 = ex2_approx(__uint_as_float(v[e]) - mx), e1 = ex2_approx(__uint_as_float(v[e + 1]) - mx);
-                            l0 += e0; l1 += e1;
-                            pw[e >> 1] = pack_bf16x2(e0, e1);
-                        }
-                        tmem_st16(tacc + 16 * pc, pw);
-                    }
-                    tmem_st_wait();
+                    softmax_sweep2<NCH>(tacc, mx);
                     tc_fence_before();
                     mbar_arrive(&bars[W_PR + g]);
+                    WA_TL(dbg, slot, 3 + 4 * c);
                 }
                 // ---- O / rowsum -> output
                 mbar_wait(&bars[W_OF + g], ph_of); ph_of ^= 1;
                 tc_fence_after();
+                WA_TL(dbg, slot, 20);
                 uint32_t o[32];
                 tmem_ld32(tacc + TC_OACC, o);
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(&bars[W_FREE + g]);             // S / O columns of this group may be overwritten
-                const float inv = __frcp_rn(l0 + l1);
+                const float inv = __frcp_rn(__uint_as_float(o[SRK_HEAD_DIM]));   // column 30 = sum_j p_ij (ones column of V)
+                o[SRK_HEAD_DIM] = 0u;                                            // padded dims leave as zeros
                 if (p.out_mode == 0) {
                     uint8_t* dst = p.o_planes + pair * p.o_plane_stride + tok * 128;
                     const uint32_t key = static_cast<uint32_t>(tok) & 7u;
@@ -335,6 +413,8 @@ __global__ void __launch_bounds__(320, 1) winattn_kernel(const WinAttnParams p) 
                     for (int d = 0; d < SRK_HEAD_DIM; d += 2)
                         *reinterpret_cast<float2*>(dst + d) = make_float2(__uint_as_float(o[d]) * inv, __uint_as_float(o[d + 1]) * inv);
                 }
+                WA_TL(dbg, slot, 21);
+                slot += 2;
             }
             mbar_arrive(&bars[W_EMPTY + s]);                // tables of this set no longer read
             if (++s == NSETS) { s = 0; ph ^= 1; }

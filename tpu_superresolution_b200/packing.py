@@ -180,6 +180,9 @@ def pack_qkv_planes(qkv_w, qkv_b, ln_w=None, ln_b=None, scale=None) -> Tuple[tor
     b[:C] *= scale * LOG2E
     w_pad = torch.cat([_pad_cols(_pad_heads(w[i * C:(i + 1) * C].float()), L.DIM_PAD) for i in range(3)], 0)   # (576, 192)
     b_pad = torch.cat([_pad_heads(b[i * C:(i + 1) * C].float()) for i in range(3)], 0)
+    # ones column: padded dim 30 of every v head is the constant 1, so the attention kernel's P v GEMM also returns the
+    # softmax row sum (column 30 of O) and the row threads never add up p
+    b_pad.view(3, L.HEADS, L.HEAD_PAD)[2, :, L.HEAD_DIM] = 1.0
     return pack_linear_stream(w_pad).to(dev), b_pad.contiguous().to(dev)
 
 
@@ -236,3 +239,13 @@ def unswizzle_planes(planes: torch.Tensor, phase: int = 0) -> torch.Tensor:
     c = torch.arange(8, device=planes.device)
     src = c[None, :] ^ key[:, None]                      # logical chunk c lives at position c ^ key
     return torch.gather(ch, 2, src[None, :, :, None].expand(P, T, 8, 8)).reshape(P, T, 64)
+
+
+def make_pad_pages(device) -> torch.Tensor:
+    """8 KB for srk_window_attention_fwd: 4 KB of zeros (k rows of OCAB's zero padding, hat_arch.py:378) then 32 v padding rows:
+    zeros except bf16 1.0 at padded dim 30 of both heads (the ones column), 16-byte chunks permuted by chunk ^ (row & 7)."""
+    rows = torch.zeros(1, 32, 64, dtype=torch.bfloat16)
+    rows[0, :, L.HEAD_DIM] = 1.0
+    rows[0, :, L.HEAD_PAD + L.HEAD_DIM] = 1.0
+    v = unswizzle_planes(rows, 0)[0].contiguous().view(torch.uint8).reshape(-1)      # involution: this applies the swizzle
+    return torch.cat([torch.zeros(4096, dtype=torch.uint8), v]).to(device)
