@@ -3,8 +3,9 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-One "step" = one pass of the hot path over one batch of synthetic input: BASELINE.json configs[1],
-SwinIR classical x4 on a batch of 16 LR tiles of 64x64 per GPU (16 x 3 x 256 x 256 = 1.049 output Mpix).
+One "step" = one pass of the hot path over one batch of synthetic input: by default BASELINE.json configs[1],
+SwinIR classical x4 on a batch of 16 LR tiles of 64x64 per GPU (16 x 3 x 256 x 256 = 1.049 output Mpix);
+`--workload hat_x4` times configs[2] (HAT x4, batch 8) the same way.
 With N > 1 (torchrun, one rank per GPU) every rank runs its own batch -- tiles are independent, there is
 no collective on the data path -- so scaling is "weak" and `value` is the sum over ranks divided by the
 slowest rank's time.  JSON keys follow the driver contract; see DESIGN.md "Measurement".
@@ -24,15 +25,40 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-TILES_PER_STEP = 16
 TILE = 64
 SCALE = 4
-MODEL = "swinir_x4"
-# algorithmic FLOPs, 2/MAC, un-padded dims
-FLOP_PER_TOKEN_ATTN = 305_280          # qkv + qk^T + pv + proj per token (one swin_attn_kernel launch covers B*4096 tokens)
-FLOP_PER_TOKEN_MLP = 259_200           # fc1 + fc2
-GFLOP_PER_TILE_MODEL = 107.113         # whole SwinIR x4 forward, one 64x64 tile
-WORKLOAD = "SwinIR classical x4 (embed 180, 6 RSTB x 6, window 8, 6 heads, mlp_ratio 2), batch 16 of 64x64 LR tiles per GPU"
+# algorithmic FLOPs, 2/MAC, un-padded dims.  "kernels": libsrk launch name -> FLOP per token per launch.
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on (default)
+    "swinir_x4": dict(
+        metric="SwinIR x4 output Mpix/s", family="swinir", cfg="swinir_x4", tiles=16, gflop_per_tile=107.113,
+        workload="SwinIR classical x4 (embed 180, 6 RSTB x 6, window 8, 6 heads, mlp_ratio 2), batch 16 of 64x64 LR tiles per GPU",
+        dominant="swin_attn", kernel_name="swin_attn_kernel",
+        kernels={"swin_attn": 305_280,      # qkv + qk^T + pv + proj (one swin_attn_kernel launch covers all tokens of the batch)
+                 "swin_mlp": 259_200}),     # fc1 + fc2
+    # BASELINE.json configs[2]: HAT x4, window 16, OCAB overlap 0.5, CAB, batch 8
+    "hat_x4": dict(
+        metric="HAT x4 output Mpix/s", family="hat", cfg="hat_x4", tiles=8, gflop_per_tile=207.761,
+        workload="HAT x4 (embed 180, 6 RHAG x (6 HAB + OCAB), window 16, overlap 0.5, CAB 3/30, mlp_ratio 2), batch 8 of 64x64 LR tiles per GPU",
+        dominant="window_attention", kernel_name="winattn_kernel",
+        kernels={"window_attention": (36 * 184_320 + 6 * 414_720) / 42,    # qk^T + pv: 256 keys (36 W-MSA) / 576 keys (6 OCAB) per launch
+                 "linear": (42 * 194_400 + 42 * 64_800) / 84,              # qkv and proj launches
+                 "swin_mlp": 259_200}),
+}
+W = WORKLOADS["swinir_x4"]      # replaced in main()
+
+
+def _build(family, cfg_name):
+    """-> (cfg, state_dict, model class, CPU oracle forward) for a workload (synthetic weights, numpy RNG)."""
+    from oracle import synth
+    import tpu_superresolution_b200 as srk
+    if family == "swinir":
+        from oracle import swinir_oracle as O
+        cfg = synth.CONFIGS[cfg_name]
+        return cfg, synth.make_swinir_state_dict(cfg, seed=1234, kind="init"), srk.SwinIR, O.swinir_forward
+    from oracle import hat_oracle as HO
+    cfg = synth.HAT_CONFIGS[cfg_name]
+    return cfg, synth.make_hat_state_dict(cfg, seed=1234, kind="init"), srk.HAT, HO.hat_forward
 
 
 def _peaks():
@@ -108,19 +134,17 @@ def _barrier(world: int):
 def cpu_oracle_rate(tiles: int, reps: int = 1, warm: bool = True):
     """Reference algorithm on the host cores (oracle port, fp32): output Mpix/s on `tiles` tiles of the workload."""
     from oracle import synth
-    from oracle import swinir_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = synth.CONFIGS[MODEL]
-    sd = synth.make_swinir_state_dict(cfg, seed=1234, kind="init")
+    cfg, sd, _, oracle_fwd = _build(W["family"], W["cfg"])
     lr = synth.make_lr_batch(tiles, TILE, TILE, seed=2)
     with torch.no_grad():
         if warm:
-            O.swinir_forward(lr[:1], sd, cfg)
+            oracle_fwd(lr[:1], sd, cfg)
         best = float("inf")
         for _ in range(reps):
             t0 = time.perf_counter()
-            O.swinir_forward(lr, sd, cfg)
+            oracle_fwd(lr, sd, cfg)
             best = min(best, time.perf_counter() - t0)
     return tiles * (TILE * SCALE) ** 2 / best / 1e6, cores, best
 
@@ -132,28 +156,26 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import synth
-    from oracle import swinir_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sample_tiles = 2
-    cfg = synth.CONFIGS[MODEL]
-    sd = synth.make_swinir_state_dict(cfg, seed=1234, kind="init")
+    cfg, sd, _, oracle_fwd = _build(W["family"], W["cfg"])
     lr = synth.make_lr_batch(sample_tiles, TILE, TILE, seed=2)
     with torch.no_grad():
         for _ in range(args.warmup):
-            O.swinir_forward(lr, sd, cfg)
+            oracle_fwd(lr, sd, cfg)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            O.swinir_forward(lr, sd, cfg)
+            oracle_fwd(lr, sd, cfg)
         dt = time.perf_counter() - t0
     mpix = sample_tiles * (TILE * SCALE) ** 2 / 1e6
     value = mpix * args.steps / dt
-    sample = f"{sample_tiles} of the {TILES_PER_STEP} tiles of one step per timed step, fp32, torch CPU ops, {cores} threads"
+    sample = f"{sample_tiles} of the {W['tiles']} tiles of one step per timed step, fp32, torch CPU ops, {cores} threads"
     print(json.dumps({
-        "impl": "reference", "metric": "SwinIR x4 output Mpix/s", "value": value, "unit": "Mpix/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": W["metric"], "value": value, "unit": "Mpix/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
+        "config": {"workload": W["workload"], "sample": sample},
         "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -173,10 +195,15 @@ def run_ours(args):
     torch.backends.cudnn.allow_tf32 = True
     torch.backends.cudnn.benchmark = True
 
-    cfg = synth.CONFIGS[MODEL]
-    model = srk.SwinIR(**cfg.as_kwargs()).eval()
-    model.load_state_dict(synth.make_swinir_state_dict(cfg, seed=1234, kind="init"), strict=True)
+    TILES_PER_STEP = W["tiles"]
+    cfg, sd, model_cls, _ = _build(W["family"], W["cfg"])
+    model = model_cls(**cfg.as_kwargs()).eval()
+    model.load_state_dict(sd, strict=True)
     model.to(dev)
+    # one cudaGraphLaunch per step instead of ~1000 kernel launches: at this batch size the eager forward is bound by the
+    # host's launch rate (tpu_superresolution_b200/graphs.py); --eager times the plain module instead
+    from tpu_superresolution_b200.graphs import GraphedModel
+    runner = model if args.eager else GraphedModel(model)
     n_in = 4                                        # rotate distinct input batches
     host_in = [synth.make_lr_batch(TILES_PER_STEP, TILE, TILE, seed=100 + rank * n_in + i).pin_memory() for i in range(n_in)]
     dev_in = [h.to(dev) for h in host_in]
@@ -186,11 +213,13 @@ def run_ours(args):
     stream = torch.cuda.current_stream()
 
     def step_resident(i):
-        return model(dev_in[i % n_in])
+        return runner(dev_in[i % n_in])
 
     def step_e2e(i):
-        x = host_in[i % n_in].to(dev, non_blocking=True)
-        y = model(x)
+        if args.eager:
+            y = runner(host_in[i % n_in].to(dev, non_blocking=True))
+        else:
+            y = runner(host_in[i % n_in])          # H2D straight into the graph's static input buffer
         host_out.copy_(y, non_blocking=True)
         return y
 
@@ -217,12 +246,16 @@ def run_ours(args):
             raise SystemExit("bench.py: model output is not finite / out of range; refusing to time it")
         del y_chk
 
+    with torch.no_grad():                       # libsrk launches of ONE forward (a graph replays exactly these)
+        l0 = L.launch_count()
+        model(dev_in[0])
+        torch.cuda.synchronize()
+        launches_per_step = L.launch_count() - l0
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    launches0 = L.launch_count()
     t_res = _max_over_ranks(timed(step_resident, args.steps, args.warmup), world)
-    launches = (L.launch_count() - launches0) * args.steps // (args.steps + args.warmup)
+    launches = launches_per_step * args.steps
     t_e2e = _max_over_ranks(timed(step_e2e, args.steps, max(1, args.warmup // 2)), world)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -232,7 +265,7 @@ def run_ours(args):
     with torch.no_grad():
         for i in range(3):
             flush.zero_()
-            step_resident(i)
+            model(dev_in[i % n_in])             # eager: events cannot be recorded around kernels inside a graph
     torch.cuda.synchronize()
     L.PROFILE = None
     kstats = {k: (sum(a.elapsed_time(b) for a, b in v) / len(v), len(v)) for k, v in prof.items()}
@@ -245,14 +278,19 @@ def run_ours(args):
 
     peak_tf, peak_gbs, peak_src = _peaks()
     tokens = TILES_PER_STEP * TILE * TILE
-    attn_ms, attn_n = kstats.get("swin_attn", (float("nan"), 0))
-    mlp_ms, mlp_n = kstats.get("swin_mlp", (float("nan"), 0))
-    attn_tf = FLOP_PER_TOKEN_ATTN * tokens / (attn_ms * 1e-3) / 1e12
+
+    def kstat(name):
+        ms, n = kstats.get(name, (float("nan"), 0))
+        tf = W["kernels"][name] * tokens / (ms * 1e-3) / 1e12
+        return {"avg_launch_ms": ms, "launches_timed": n, "achieved": tf, "frac": tf / peak_tf,
+                "algorithmic_flop_per_launch": W["kernels"][name] * tokens}
+
+    dom = kstat(W["dominant"])
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.isfile(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get("swin_attn_kernel_dram_bytes_per_launch")
+            traffic = json.load(f).get(W["kernel_name"] + "_dram_bytes_per_launch")
 
     cpu_tiles = TILES_PER_STEP if (os.cpu_count() or 1) >= 16 else 4
     cpu_baseline = None                         # reported at N = 1 only (driver contract)
@@ -263,13 +301,14 @@ def run_ours(args):
 
     ms_step = t_res / args.steps * 1e3
     value = world * mpix_step * args.steps / t_res
-    model_tf = world * GFLOP_PER_TILE_MODEL * TILES_PER_STEP * args.steps / t_res / 1e3
+    model_tf = world * W["gflop_per_tile"] * TILES_PER_STEP * args.steps / t_res / 1e3
     out = {
-        "metric": "SwinIR x4 output Mpix/s", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+        "metric": W["metric"], "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "tiles_per_step_per_gpu": TILES_PER_STEP, "parallelism": f"tile-sharded x{world}, no collective",
+        "config": {"workload": W["workload"], "tiles_per_step_per_gpu": TILES_PER_STEP, "parallelism": f"tile-sharded x{world}, no collective",
                    "precision": "bf16 MMA operands, fp32 accumulate, fp32 residual stream; convs cuDNN TF32",
+                   "launch": "eager" if args.eager else "one CUDA graph replay per step",
                    "l2": "flushed between steps (256 MiB memset outside the timed events)",
                    "whole_model_tflops": model_tf, "whole_model_frac_of_peak": model_tf / world / peak_tf},
         "e2e": {"value": world * mpix_step * args.steps / t_e2e, "unit": "Mpix/s",
@@ -277,13 +316,11 @@ def run_ours(args):
                 "ms_per_step": t_e2e / args.steps * 1e3},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "swin_attn_kernel", "bound": "tensor", "achieved": attn_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": attn_tf / peak_tf, "traffic": traffic, "peak_source": peak_src,
-                     "avg_launch_ms": attn_ms, "launches_timed": attn_n,
-                     "algorithmic_flop_per_launch": FLOP_PER_TOKEN_ATTN * tokens,
-                     "other_kernels": {"swin_mlp_kernel": {"avg_launch_ms": mlp_ms, "launches_timed": mlp_n,
-                                                           "achieved": FLOP_PER_TOKEN_MLP * tokens / (mlp_ms * 1e-3) / 1e12,
-                                                           "frac": FLOP_PER_TOKEN_MLP * tokens / (mlp_ms * 1e-3) / 1e12 / peak_tf}},
+        "roofline": {"kernel": W["kernel_name"], "bound": "tensor", "achieved": dom["achieved"], "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src,
+                     "avg_launch_ms": dom["avg_launch_ms"], "launches_timed": dom["launches_timed"],
+                     "algorithmic_flop_per_launch": dom["algorithmic_flop_per_launch"],
+                     "other_kernels": {k: kstat(k) for k in W["kernels"] if k != W["dominant"]},
                      "libsrk_ms_per_step": sum(v[0] * v[1] for v in kstats.values()) / 3.0},
         "cpu_baseline": cpu_baseline,
     }
@@ -299,7 +336,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="swinir_x4", choices=sorted(WORKLOADS))
+    ap.add_argument("--eager", action="store_true", help="time the plain module instead of the CUDA-graph replay")
     args = ap.parse_args()
+    global W
+    W = WORKLOADS[args.workload]
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

@@ -1,0 +1,61 @@
+"""CUDA-graph replay of a whole SR forward (SwinIR / HAT / DAT drop-in models).
+
+A forward is several hundred kernel launches (36 fused blocks x 2-8 kernels + cuDNN convolutions + the tail) of 10-100 us
+each, so at batch 8-16 the host's launch rate, not the GPU, bounds the step.  ``GraphedModel`` captures one forward per
+input shape into a ``torch.cuda.CUDAGraph`` -- libsrk's entry points only enqueue on the current stream and never
+allocate or synchronise, so they capture like any other kernel -- and replays it with one ``cudaGraphLaunch``.
+
+    g = GraphedModel(model)          # model: srk.SwinIR / srk.HAT, eval mode, on the GPU
+    y = g(x)                         # first call per shape: warm-up + capture; later calls: copy-in, replay.
+                                     # x may be a (pinned) host tensor: it is copied straight into the graph's input buffer
+
+The returned tensor is the graph's static output buffer: it is overwritten by the next call with the same shape
+(``clone()`` it to keep it).  Weights are baked in by address: after changing parameters call ``reset()``.
+"""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import torch
+import torch.nn as nn
+
+
+class GraphedModel(nn.Module):
+    def __init__(self, model: nn.Module, warmup: int = 2):
+        super().__init__()
+        self.model = model
+        self.warmup = warmup
+        self._graphs: Dict[Tuple, Tuple[torch.cuda.CUDAGraph, torch.Tensor, torch.Tensor]] = {}
+
+    def reset(self) -> None:
+        self._graphs.clear()
+
+    @torch.no_grad()
+    def _capture(self, x: torch.Tensor):
+        static_in = x.clone()
+        side = torch.cuda.Stream(device=x.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                       # warm-up off the capture: packs weights, lets cuDNN pick algorithms
+            for _ in range(self.warmup):
+                self.model(static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(x.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_out = self.model(static_in)
+        return graph, static_in, static_out
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        dev = next(self.model.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("GraphedModel: the model must live on a CUDA device (no CPU fallback)")
+        key = (tuple(x.shape), x.dtype)
+        entry = self._graphs.get(key)
+        if entry is None:
+            entry = self._capture(x.to(dev))
+            self._graphs[key] = entry
+        graph, static_in, static_out = entry
+        static_in.copy_(x, non_blocking=True)
+        graph.replay()
+        return static_out
