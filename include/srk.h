@@ -92,7 +92,8 @@ int srk_swin_mlp_fwd(const SrkMlpDesc* desc, const float* x, float* y, const voi
  *      SRK_LIN_A_PLANES: bf16 planes [k_atoms][num_tokens][64] (128 B per token row, 16-byte chunks permuted by chunk ^ (tok & 7))
  *   out SRK_LIN_OUT_PLANES: bf16 planes [3 * n_chunks][num_tokens][64]; plane p is permuted with (tok + 4) & 7 when bit p of
  *                          plane_phase_mask is set (operand-row phase of the consumer's window images)
- *       SRK_LIN_OUT_ROWS  : fp32 rows [tok][ld_out] (n_chunks = 1, 180 valid columns), added into `out` when add_residual. */
+ *       SRK_LIN_OUT_ROWS  : fp32 rows [tok][ld_out]; chunk c writes columns [180 c, 180 c + 180) (so a 720-wide hidden layer is
+ *                          4 chunks); added into `out` when add_residual. */
 enum { SRK_LIN_A_ROWS = 0, SRK_LIN_A_PLANES = 1 };
 enum { SRK_LIN_OUT_PLANES = 0, SRK_LIN_OUT_ROWS = 1 };
 enum { SRK_LIN_ACT_NONE = 0, SRK_LIN_ACT_GELU = 1 };

@@ -213,6 +213,136 @@ CONFIGS = {
 }
 
 
+def dat_manifest(cfg) -> List[Tuple[str, Tuple[int, ...], str]]:
+    """(key, shape, kind) in the reference DAT's state_dict order (dat_arch.py:262-316, 452-479, 57-90, 531-555, 738-812)."""
+    from .dat_oracle import is_shifted
+    C, nf = cfg.embed_dim, cfg.num_feat
+    hid = int(C * cfg.expansion_factor)
+    s0, s1 = cfg.split_size
+    N = s0 * s1
+    nwin = (cfg.img_size // s0) * (cfg.img_size // s1)
+    out: List[Tuple[str, Tuple[int, ...], str]] = []
+
+    def conv(name, co, ci, k=3, wk="conv_w"):
+        out.append((f"{name}.weight", (co, ci, k, k), wk))
+        out.append((f"{name}.bias", (co,), "conv_b"))
+
+    def ln(name, n=None):
+        out.append((f"{name}.weight", (n or C,), "ln_w"))
+        out.append((f"{name}.bias", (n or C,), "ln_b"))
+
+    def lin(name, co, ci, wk="lin_w"):
+        out.append((f"{name}.weight", (co, ci), wk))
+        out.append((f"{name}.bias", (co,), "lin_b"))
+
+    def bn(name, n):
+        ln(name, n)
+        out.append((f"{name}.running_mean", (n,), "bn_mean"))
+        out.append((f"{name}.running_var", (n,), "bn_var"))
+        out.append((f"{name}.num_batches_tracked", (), "bn_count"))
+
+    def aim(pre):
+        conv(pre + "dwconv.0", C, 1, 3, "dw_w")
+        bn(pre + "dwconv.1", C)
+        conv(pre + "channel_interaction.1", C // 8, C, 1)
+        bn(pre + "channel_interaction.2", C // 8)
+        conv(pre + "channel_interaction.4", C, C // 8, 1)
+        conv(pre + "spatial_interaction.0", C // 16, C, 1)
+        bn(pre + "spatial_interaction.1", C // 16)
+        conv(pre + "spatial_interaction.3", 1, C // 16, 1)
+
+    conv("conv_first", C, cfg.in_chans)
+    ln("before_RG.1")
+    for g, (depth, nh) in enumerate(zip(cfg.depth, cfg.num_heads)):
+        for b in range(depth):
+            pre = f"layers.{g}.blocks.{b}."
+            ln(pre + "norm1")
+            a = pre + "attn."
+            if b % 2 == 0:
+                if is_shifted(g, b):
+                    out.append((a + "attn_mask_0", (nwin, N, N), "dat_mask0"))
+                    out.append((a + "attn_mask_1", (nwin, N, N), "dat_mask1"))
+                lin(a + "qkv", 3 * C, C, "qkv_w")
+                lin(a + "proj", C, C)
+                pd = (C // 2) // 4 // 4                       # DynamicPosBias(dim // 4) -> pos_dim = dim // 16 (dat_arch.py:170, :105)
+                for i in range(2):
+                    s = a + f"attns.{i}."
+                    out.append((s + "rpe_biases", ((2 * s0 - 1) * (2 * s1 - 1), 2), f"rpe{i}"))
+                    out.append((s + "relative_position_index", (N, N), f"rpi{i}"))
+                    lin(s + "pos.pos_proj", pd, 2, "pos_w")
+                    for j, o in ((1, pd), (2, pd), (3, nh // 2)):
+                        ln(s + f"pos.pos{j}.0", pd)
+                        lin(s + f"pos.pos{j}.2", o, pd, "pos_w")
+            else:
+                out.append((a + "temperature", (nh, 1, 1), "temperature"))
+                lin(a + "qkv", 3 * C, C, "qkv_w")
+                lin(a + "proj", C, C)
+            aim(a)
+            f = pre + "ffn."
+            lin(f + "fc1", hid, C)
+            ln(f + "sg.norm", hid // 2)
+            conv(f + "sg.conv", hid // 2, 1, 3, "dw_w")
+            lin(f + "fc2", C, hid // 2)
+            ln(pre + "norm2")
+        conv(f"layers.{g}.conv", C, C)
+    ln("norm")
+    conv("conv_after_body", C, C)
+    conv("conv_before_upsample.0", nf, C)
+    for i in range(int(math.log2(cfg.upscale))):
+        conv(f"upsample.{2 * i}", 4 * nf, nf)
+    conv("conv_last", cfg.in_chans, nf)
+    return out
+
+
+def make_dat_state_dict(cfg, seed: int = 1234, kind: str = "init") -> Dict[str, torch.Tensor]:
+    """Synthetic DAT state_dict with the reference's keys/shapes.  "stress" also gives the BatchNorms non-trivial running
+    statistics and the dynamic-position-bias MLP weights of order one, so the bias table is far from constant."""
+    from .dat_oracle import rect_relative_position_index, rect_shift_mask
+    assert kind in ("init", "stress")
+    rng = np.random.default_rng(seed)
+    s0, s1 = cfg.split_size
+    R = cfg.img_size
+    sd: Dict[str, torch.Tensor] = {}
+    for key, shape, k in dat_manifest(cfg):
+        if k in ("rpe0", "rpe1"):
+            hs, ws = (s0, s1) if k == "rpe0" else (s1, s0)
+            dy, dx = torch.arange(1 - hs, hs), torch.arange(1 - ws, ws)
+            sd[key] = torch.stack(torch.meshgrid(dy, dx, indexing="ij")).flatten(1).transpose(0, 1).contiguous().float()
+        elif k in ("rpi0", "rpi1"):
+            sd[key] = rect_relative_position_index(*((s0, s1) if k == "rpi0" else (s1, s0)))
+        elif k == "dat_mask0":
+            sd[key] = rect_shift_mask(R, R, s0, s1, s0 // 2, s1 // 2)
+        elif k == "dat_mask1":
+            sd[key] = rect_shift_mask(R, R, s1, s0, s1 // 2, s0 // 2)
+        elif k == "bn_count":
+            sd[key] = torch.tensor(0, dtype=torch.int64)
+        else:
+            if k == "bn_mean":
+                a = np.zeros(shape) if kind == "init" else rng.normal(0, 0.2, size=shape)
+            elif k == "bn_var":
+                a = np.ones(shape) if kind == "init" else rng.uniform(0.5, 1.5, size=shape)
+            elif k == "temperature":
+                a = np.ones(shape) if kind == "init" else rng.uniform(0.5, 3.0, size=shape)
+            elif k == "dw_w":
+                a = rng.uniform(-1.0 / 3.0, 1.0 / 3.0, size=shape)
+            elif k == "pos_w":
+                a = np.clip(rng.normal(0, 0.02, size=shape), -0.04, 0.04) if kind == "init" else rng.normal(0, 0.7, size=shape)
+            else:
+                a = _draw(rng, k, shape, kind, cfg.embed_dim)
+            sd[key] = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    return sd
+
+
+def _dat_configs():
+    from .dat_oracle import DATConfig
+    return {
+        # BASELINE.json configs[3]: DAT x2, split 8x32, expansion 4 (SURVEY.md 8d cfg4)
+        "dat_x2": DATConfig(upscale=2),
+        # reduced depth, full widths: RG 0 holds an un-shifted and a shifted spatial block (b = 0, 2), RG 1 a shifted one at b = 0
+        "dat_x2_d3": DATConfig(upscale=2, depth=[3, 2], num_heads=[6, 6]),
+    }
+
+
 def _hat_configs():
     from .hat_oracle import HATConfig
     return {
@@ -225,3 +355,4 @@ def _hat_configs():
 
 
 HAT_CONFIGS = _hat_configs()
+DAT_CONFIGS = _dat_configs()

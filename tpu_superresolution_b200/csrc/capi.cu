@@ -136,9 +136,8 @@ int srk_linear_fwd(const SrkLinearDesc* d, const void* a, const void* wstream, c
     if (d->out_mode == SRK_LIN_OUT_PLANES) {
         p.out_planes = static_cast<uint8_t*>(out); p.out_plane_stride = d->num_tokens * 128;
     } else if (d->out_mode == SRK_LIN_OUT_ROWS) {
-        if (d->n_chunks != 1) return fail("srk_linear_fwd: fp32 row output needs n_chunks = 1");
-        if (d->act != SRK_LIN_ACT_NONE) return fail("srk_linear_fwd: fp32 row output has no activation");
-        if (d->ld_out < SRK_DIM || (d->ld_out & 3)) return fail("srk_linear_fwd: bad ld_out %d", d->ld_out);
+        if (d->k_atoms == 6 && d->n_chunks != 1) return fail("srk_linear_fwd: fp32 row output with k_atoms = 6 needs n_chunks = 1");
+        if (d->ld_out < SRK_DIM * d->n_chunks || (d->ld_out & 3)) return fail("srk_linear_fwd: bad ld_out %d", d->ld_out);
         p.y = static_cast<float*>(out); p.ld_out = d->ld_out; p.add_residual = d->add_residual;
     } else {
         return fail("srk_linear_fwd: unknown out_mode %d", d->out_mode);

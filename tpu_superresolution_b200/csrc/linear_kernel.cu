@@ -6,8 +6,8 @@
 //                                 kernel: one 16 KB bulk TMA copy per k-atom drops 128 tokens into the operand image.
 //   output      SRK_LIN_OUT_PLANES: bf16 planes of 64 columns each (q / k / v head pairs, hidden units), swizzle phase
 //                                 per plane (so a later kernel can bulk-copy window rows as UMMA operand rows);
-//               SRK_LIN_OUT_ROWS  : fp32 rows [tok][ld_out] (180 valid columns), plain or added into y with
-//                                 cp.reduce.async.bulk (residual update in place).
+//               SRK_LIN_OUT_ROWS  : fp32 rows [tok][ld_out], chunk c = columns [180 c, 180 c + 180), plain or added into y
+//                                 with cp.reduce.async.bulk (residual update in place).
 // Replaces nn.Linear call sites hat_arch.py:179 (qkv), :195 (proj), :401, :436 (OCAB qkv / proj) and dat_arch.py:371,
 // :435, :483, :526, :79-88 (qkv / proj / fc1 / fc2).
 //
@@ -194,11 +194,13 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) token_linear_kernel(const Line
                         }
                     }
                 } else {
-                    if (!first_tile && !stage_alias) {      // the previous tile's copies no longer read the staging rows
+                    if (!(first_tile && c == 0) && !stage_alias) {      // the previous chunk's copies no longer read the staging rows
                         if (g == 0) bulk_wait_read0();
                         named_bar_sync(2 + q, 64);
                     }
-                    stage_rows_and_bulk_store(acc, 0u, stage, stage, 32, s_vec, p.y, p.ld_out, p.add_residual, q, g, lane, tok_of_row);
+                    // chunk c = output columns [180 c, 180 c + 180) of the ld_out-wide rows
+                    stage_rows_and_bulk_store(acc, 0u, stage, stage, 32, s_vec + c * LIN_NC, p.y + c * SRK_DIM, p.ld_out, p.add_residual, q, g,
+                                              lane, tok_of_row, p.act == SRK_LIN_ACT_GELU);
                     if (stage_alias && g == 0) {
                         bulk_wait_read0();
                         mbar_arrive(&bars[LB_DRAIN]);

@@ -105,6 +105,17 @@ __device__ __forceinline__ void store_row_chunks(uint32_t img_atom, uint32_t row
     }
 }
 
+// gelu(x) = x Phi(x).  Phi(x) = 0.5 (1 + erf(x / sqrt 2)) is evaluated as 0.5 (1 + tanh(x (c1 + c3 u + c5 u^2))),
+// u = min(x^2, 64): minimax fit, |error| <= 2.6e-5 on the GELU output for all x, plus the MUFU.TANH error (2^-11 rel.)
+// -- both far below the bf16 rounding (2^-9 rel.) applied to the result right after.  One MUFU per element.
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float u2 = fminf(x * x, 64.0f);
+    const float qv = x * fmaf(u2, fmaf(u2, -3.51517176e-04f, 3.70056486e-02f), 7.97507881e-01f);
+    const float hx = 0.5f * x;
+    return fmaf(hx, tanh_approx(qv), hx);
+}
+
+
 // Final epilogue shared by K1/K2: accumulator (+bias) -> fp32 rows staged in shared memory in the exact global row
 // layout (720 B per token row) -> the TMA engine writes them out with one bulk copy per contiguous run of tokens.
 // With add_residual the copy is `cp.reduce.async.bulk ... add.f32`: the residual stream is updated in place
@@ -117,7 +128,7 @@ constexpr uint32_t ROW_BYTES = SRK_DIM * 4;     // 720
 template <typename TokFn>
 __device__ __forceinline__ void stage_rows_and_bulk_store(uint32_t tmem_acc, uint32_t lanebase, uint8_t* stage_main, uint8_t* stage_tail,
                                                           int main_rows, const float* s_bias, float* __restrict__ y, int ld_out,
-                                                          int add_residual, int q, int g, int lane, TokFn tok_of_row) {
+                                                          int add_residual, int q, int g, int lane, TokFn tok_of_row, int act_gelu = 0) {
     uint8_t* const my_row = lane < main_rows ? stage_main + (q * main_rows + lane) * ROW_BYTES
                                              : stage_tail + (q * (32 - main_rows) + lane - main_rows) * ROW_BYTES;
     float* dst = reinterpret_cast<float*>(my_row);
@@ -136,6 +147,7 @@ __device__ __forceinline__ void stage_rows_and_bulk_store(uint32_t tmem_acc, uin
                 o.y = __uint_as_float(v[4 * k + 1]) + b.y;
                 o.z = __uint_as_float(v[4 * k + 2]) + b.z;
                 o.w = __uint_as_float(v[4 * k + 3]) + b.w;
+                if (act_gelu) { o.x = gelu_fast(o.x); o.y = gelu_fast(o.y); o.z = gelu_fast(o.z); o.w = gelu_fast(o.w); }
                 *reinterpret_cast<float4*>(dst + 32 * c + 4 * k) = o;
             }
         }
@@ -162,15 +174,5 @@ __device__ __forceinline__ void stage_rows_and_bulk_store(uint32_t tmem_acc, uin
     }
 }
 
-
-// gelu(x) = x Phi(x).  Phi(x) = 0.5 (1 + erf(x / sqrt 2)) is evaluated as 0.5 (1 + tanh(x (c1 + c3 u + c5 u^2))),
-// u = min(x^2, 64): minimax fit, |error| <= 2.6e-5 on the GELU output for all x, plus the MUFU.TANH error (2^-11 rel.)
-// -- both far below the bf16 rounding (2^-9 rel.) applied to the result right after.  One MUFU per element.
-__device__ __forceinline__ float gelu_fast(float x) {
-    const float u2 = fminf(x * x, 64.0f);
-    const float qv = x * fmaf(u2, fmaf(u2, -3.51517176e-04f, 3.70056486e-02f), 7.97507881e-01f);
-    const float hx = 0.5f * x;
-    return fmaf(hx, tanh_approx(qv), hx);
-}
 
 }  // namespace srk
