@@ -1,10 +1,15 @@
 """B200-native (sm_100a) fused window-attention super-resolution: drop-in modules for the reference's
-SwinIR / HAT blocks (ViacheslavTimofeev/tpu_superresolution, modules/network_swinir.py, modules/hat_arch.py) backed by libsrk.so."""
+SwinIR / HAT / DAT blocks (ViacheslavTimofeev/tpu_superresolution, modules/network_swinir.py, hat_arch.py, dat_arch.py) backed by libsrk.so."""
 from .swinir import (Mlp, WindowAttention, SwinTransformerBlock, BasicLayer, RSTB, PatchEmbed, PatchUnEmbed,
                      PixelShuffle, Upsample, UpsampleOneStep, SwinIR, calculate_mask)
 from . import hat
 from .hat import HAT, HAB, OCAB, RHAG, CAB, ChannelAttention, AttenBlocks
+from . import dat
+from .dat import DAT, DATB, ResidualGroup, Adaptive_Spatial_Attention, Adaptive_Channel_Attention, SGFN, SpatialGate, DynamicPosBias
+from .graphs import GraphedModel
 
 __all__ = ["Mlp", "WindowAttention", "SwinTransformerBlock", "BasicLayer", "RSTB", "PatchEmbed", "PatchUnEmbed",
            "PixelShuffle", "Upsample", "UpsampleOneStep", "SwinIR", "calculate_mask",
-           "hat", "HAT", "HAB", "OCAB", "RHAG", "CAB", "ChannelAttention", "AttenBlocks"]
+           "hat", "HAT", "HAB", "OCAB", "RHAG", "CAB", "ChannelAttention", "AttenBlocks",
+           "dat", "DAT", "DATB", "ResidualGroup", "Adaptive_Spatial_Attention", "Adaptive_Channel_Attention", "SGFN", "SpatialGate",
+           "DynamicPosBias", "GraphedModel"]

@@ -1,0 +1,484 @@
+"""Drop-in DAT modules (reference: ``modules/dat_arch.py``) backed by the sm_100a kernels in libsrk.so.
+
+Same constructor arguments, forward signatures and state_dict keys as the reference, including the
+``attns.{0,1}`` sub-modules with their ``rpe_biases`` / ``relative_position_index`` buffers and DynamicPosBias MLPs, the
+eval-mode BatchNorms of the adaptive interaction module and ``attn_mask_{0,1}`` on the shifted blocks.
+
+What runs where (per DATB, dat_arch.py:556-565)
+  * LN1 + qkv Linear                     -> srk_linear_fwd  (tcgen05; q/k/v head planes for the window kernel, fp32 rows for v)
+  * rectangular split-window attention on the two channel halves (8x32 and 32x8 windows, shift (4,16)/(16,4), dynamic
+    position bias, per-axis shift masks) -> srk_window_attention_fwd (tcgen05, kinds DAT_8x32 / DAT_32x8); img2windows,
+    torch.roll and windows2img are the kernel's load / store addressing
+  * proj, LN2 + fc1 + GELU, fc2 (+ residual) -> srk_linear_fwd
+  * the small HBM-bound glue -- depthwise 3x3 convolutions (+BN+GELU), the two squeeze gates of the adaptive interaction
+    module, the 30x30 channel-attention matrices of the DCTB blocks, the spatial gate's LayerNorm -- runs as torch CUDA ops
+    this round (library calls; fusing them is listed in DESIGN.md "next").
+The dynamic position bias is input independent: its 4-layer MLP is evaluated once per weight version at pack time.
+Inference only; no CPU / eager fallback for the kernels.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib as L
+from . import packing
+from .swinir import Upsample, UpsampleOneStep, _PackedCache, _inference_only
+
+
+def is_shifted(rg_idx: int, b_idx: int) -> bool:
+    """dat_arch.py:290: spatial blocks that run on the shifted window grid."""
+    return (rg_idx % 2 == 0 and b_idx > 0 and (b_idx - 2) % 4 == 0) or (rg_idx % 2 != 0 and b_idx % 4 == 0)
+
+
+def _rect_rpi(hs: int, ws: int) -> torch.Tensor:
+    t = torch.arange(hs * ws)
+    y, x = t // ws, t % ws
+    return (y[:, None] - y[None, :] + hs - 1) * (2 * ws - 1) + (x[:, None] - x[None, :] + ws - 1)
+
+
+def _rect_mask(H: int, W: int, hs: int, ws: int, sy: int, sx: int) -> torch.Tensor:
+    """dat_arch.py:318-361 for one branch, closed form (only populates the state_dict buffer; the kernel never reads it)."""
+    def region(p, Ln, win, shift):
+        return (p >= Ln - win).long() + (p >= Ln - shift).long()
+    ids = 3 * region(torch.arange(H), H, hs, sy)[:, None] + region(torch.arange(W), W, ws, sx)[None, :]
+    ids = ids.view(H // hs, hs, W // ws, ws).permute(0, 2, 1, 3).reshape(-1, hs * ws)
+    diff = ids[:, None, :] != ids[:, :, None]
+    return torch.zeros(diff.shape).masked_fill(diff, -100.0)
+
+
+class SpatialGate(nn.Module):
+    """dat_arch.py:38-54."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.norm = nn.LayerNorm(dim)
+        self.conv = nn.Conv2d(dim, dim, kernel_size=3, stride=1, padding=1, groups=dim)
+
+    def forward(self, x, H, W):
+        x1, x2 = x.chunk(2, dim=-1)
+        B, N, C = x.shape
+        x2 = F.layer_norm(x2, (C // 2,), self.norm.weight, self.norm.bias, self.norm.eps)
+        x2 = self.conv(x2.view(B, H, W, C // 2).permute(0, 3, 1, 2)).permute(0, 2, 3, 1).reshape(B, N, C // 2)
+        return x1 * x2
+
+
+class SGFN(nn.Module):
+    """dat_arch.py:57-90 spatial-gate feed-forward.  forward(x: (B, H*W, 180), H, W)."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        if act_layer is not nn.GELU:
+            raise RuntimeError("SGFN: only nn.GELU is implemented")
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = act_layer()
+        self.sg = SpatialGate(hidden_features // 2)
+        self.fc2 = nn.Linear(hidden_features // 2, out_features)
+        self.drop = nn.Dropout(drop)
+        self._cache = _PackedCache()
+
+    def _packed(self, norm: Optional[nn.LayerNorm]):
+        hid, C = self.fc1.weight.shape
+        if C != L.DIM or hid % (2 * L.DIM) or self.fc2.weight.shape != (L.DIM, hid // 2):
+            raise RuntimeError(f"SGFN: unsupported geometry fc1 {tuple(self.fc1.weight.shape)} fc2 {tuple(self.fc2.weight.shape)}")
+        ps = [self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias] + ([norm.weight, norm.bias] if norm is not None else [])
+
+        def build():
+            f1 = packing.pack_rows_linear(self.fc1.weight, self.fc1.bias, None if norm is None else norm.weight,
+                                          None if norm is None else norm.bias)
+            halves = []
+            for i in range(hid // 2 // L.DIM):      # fc2's K = hidden / 2 in slices of 180: y += x[:, 180 i : 180 i + 180] W[:, slice]^T
+                halves.append(packing.pack_rows_linear(self.fc2.weight[:, L.DIM * i:L.DIM * (i + 1)], self.fc2.bias if i == 0 else None))
+            return f1, halves
+        return self._cache.get(ps, build)
+
+    def run(self, x, out, H, W, norm: Optional[nn.LayerNorm], add_residual: bool):
+        """out (+)= fc2(gate(gelu(fc1(LN(x)))))."""
+        _inference_only(self)
+        B, N, C = x.shape
+        hid = self.fc1.weight.shape[0]
+        (f1w, f1b), halves = self._packed(norm)
+        h = torch.empty((B, N, hid), device=x.device, dtype=torch.float32)
+        L.linear(x, f1w, f1b, h, num_tokens=B * N, a_mode=L.LIN_A_ROWS, ld_in=C, apply_ln=norm is not None, n_chunks=hid // L.DIM,
+                 act=L.LIN_ACT_GELU, out_mode=L.LIN_OUT_ROWS, ld_out=hid)
+        g = self.sg(h, H, W).contiguous()                                       # (B, N, hid / 2)
+        for i, (w2, b2) in enumerate(halves):
+            L.linear(g[..., L.DIM * i:], w2, b2, out, num_tokens=B * N, a_mode=L.LIN_A_ROWS, ld_in=hid // 2, apply_ln=False,
+                     n_chunks=1, out_mode=L.LIN_OUT_ROWS, ld_out=C, add_residual=add_residual or i > 0)
+        return out
+
+    def forward(self, x, H, W):
+        x = x.contiguous()
+        return self.run(x, torch.empty_like(x), H, W, None, False)
+
+
+class DynamicPosBias(nn.Module):
+    """dat_arch.py:93-130."""
+
+    def __init__(self, dim, num_heads, residual):
+        super().__init__()
+        self.residual, self.num_heads = residual, num_heads
+        self.pos_dim = dim // 4
+        self.pos_proj = nn.Linear(2, self.pos_dim)
+        self.pos1 = nn.Sequential(nn.LayerNorm(self.pos_dim), nn.ReLU(inplace=True), nn.Linear(self.pos_dim, self.pos_dim))
+        self.pos2 = nn.Sequential(nn.LayerNorm(self.pos_dim), nn.ReLU(inplace=True), nn.Linear(self.pos_dim, self.pos_dim))
+        self.pos3 = nn.Sequential(nn.LayerNorm(self.pos_dim), nn.ReLU(inplace=True), nn.Linear(self.pos_dim, self.num_heads))
+
+    def forward(self, biases):
+        if self.residual:
+            pos = self.pos_proj(biases)
+            pos = pos + self.pos1(pos)
+            pos = pos + self.pos2(pos)
+            return self.pos3(pos)
+        return self.pos3(self.pos2(self.pos1(self.pos_proj(biases))))
+
+
+class Spatial_Attention(nn.Module):
+    """dat_arch.py:133-244: one rectangular-window branch.  Holds the branch's buffers and position-bias MLP; the attention
+    itself is launched by Adaptive_Spatial_Attention on the shared q/k/v planes."""
+
+    def __init__(self, dim, idx, split_size=[8, 8], dim_out=None, num_heads=6, attn_drop=0., proj_drop=0., qk_scale=None,
+                 position_bias=True):
+        super().__init__()
+        self.dim, self.dim_out, self.split_size, self.num_heads, self.idx = dim, dim_out or dim, split_size, num_heads, idx
+        self.position_bias = position_bias
+        head_dim = dim // num_heads
+        self.scale = qk_scale or head_dim ** -0.5
+        if idx == 0:
+            self.H_sp, self.W_sp = split_size[0], split_size[1]
+        elif idx == 1:
+            self.W_sp, self.H_sp = split_size[0], split_size[1]
+        else:
+            raise ValueError(f"ERROR MODE {idx}")
+        if not position_bias:
+            raise RuntimeError("Spatial_Attention: position_bias=False is never used by DAT and is not implemented")
+        self.pos = DynamicPosBias(self.dim // 4, self.num_heads, residual=False)
+        dy, dx = torch.arange(1 - self.H_sp, self.H_sp), torch.arange(1 - self.W_sp, self.W_sp)
+        self.register_buffer('rpe_biases', torch.stack(torch.meshgrid(dy, dx, indexing="ij")).flatten(1).transpose(0, 1).contiguous().float())
+        self.register_buffer('relative_position_index', _rect_rpi(self.H_sp, self.W_sp))
+        self.attn_drop = nn.Dropout(attn_drop)
+
+    def bias_table(self) -> torch.Tensor:
+        """(offsets, heads) dynamic position bias (dat_arch.py:219-220), input independent."""
+        with torch.no_grad():
+            return self.pos(self.rpe_biases)
+
+
+class _AIM(nn.Module):
+    """The convolution branch and the two interaction gates shared by both attention flavours (dat_arch.py:300-316)."""
+
+    def _build_aim(self, dim):
+        self.dwconv = nn.Sequential(nn.Conv2d(dim, dim, kernel_size=3, stride=1, padding=1, groups=dim), nn.BatchNorm2d(dim), nn.GELU())
+        self.channel_interaction = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Conv2d(dim, dim // 8, kernel_size=1),
+                                                 nn.BatchNorm2d(dim // 8), nn.GELU(), nn.Conv2d(dim // 8, dim, kernel_size=1))
+        self.spatial_interaction = nn.Sequential(nn.Conv2d(dim, dim // 16, kernel_size=1), nn.BatchNorm2d(dim // 16), nn.GELU(),
+                                                 nn.Conv2d(dim // 16, 1, kernel_size=1))
+
+    @staticmethod
+    def _img(t, B, H, W):
+        return t.view(B, H, W, -1).permute(0, 3, 1, 2)          # channels-last NCHW view of token rows
+
+
+class Adaptive_Spatial_Attention(_AIM):
+    """dat_arch.py:247-438.  forward(x: (B, H*W, 180) already normalised, H, W)."""
+
+    def __init__(self, dim, num_heads, reso=64, split_size=[8, 8], shift_size=[1, 2], qkv_bias=False, qk_scale=None, drop=0.,
+                 attn_drop=0., rg_idx=0, b_idx=0):
+        super().__init__()
+        self.dim, self.num_heads, self.split_size, self.shift_size = dim, num_heads, split_size, shift_size
+        self.b_idx, self.rg_idx, self.patches_resolution = b_idx, rg_idx, reso
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        assert 0 <= self.shift_size[0] < self.split_size[0], "shift_size must in 0-split_size0"
+        assert 0 <= self.shift_size[1] < self.split_size[1], "shift_size must in 0-split_size1"
+        self.branch_num = 2
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(drop)
+        self.attns = nn.ModuleList([Spatial_Attention(dim // 2, idx=i, split_size=split_size, num_heads=num_heads // 2,
+                                                      dim_out=dim // 2, qk_scale=qk_scale, attn_drop=attn_drop, proj_drop=drop,
+                                                      position_bias=True) for i in range(self.branch_num)])
+        self.shifted = is_shifted(rg_idx, b_idx)
+        if self.shifted:
+            m0, m1 = self.calculate_mask(reso, reso)
+            self.register_buffer("attn_mask_0", m0)
+            self.register_buffer("attn_mask_1", m1)
+        else:
+            self.register_buffer("attn_mask_0", None)
+            self.register_buffer("attn_mask_1", None)
+        self._build_aim(dim)
+        self.scale = qk_scale or (dim // num_heads) ** -0.5
+        self._cache = _PackedCache()
+
+    def calculate_mask(self, H, W):
+        s, sh = self.split_size, self.shift_size
+        return _rect_mask(H, W, s[0], s[1], sh[0], sh[1]), _rect_mask(H, W, s[1], s[0], sh[1], sh[0])
+
+    def _packed(self, norm: Optional[nn.LayerNorm]):
+        if self.dim != L.DIM or self.num_heads != L.HEADS or list(self.split_size) != [8, 32] or list(self.shift_size) != [4, 16]:
+            raise RuntimeError(f"Adaptive_Spatial_Attention(dim={self.dim}, heads={self.num_heads}, split={self.split_size}, "
+                               f"shift={self.shift_size}): kernels serve dim 180 / 6 heads / split [8, 32] / shift [4, 16] only")
+        ps = [self.qkv.weight, self.qkv.bias, self.proj.weight, self.proj.bias] + [p for a in self.attns for p in a.pos.parameters()] + \
+             ([norm.weight, norm.bias] if norm is not None else [])
+
+        def build():
+            lw, lb = (None, None) if norm is None else (norm.weight, norm.bias)
+            C = self.dim
+            qkv = packing.pack_dat_qkv_planes(self.qkv.weight, self.qkv.bias, lw, lb, self.scale)
+            vrow = packing.pack_rows_linear(self.qkv.weight[2 * C:], None if self.qkv.bias is None else self.qkv.bias[2 * C:], lw, lb)
+            proj = packing.pack_rows_linear(self.proj.weight, self.proj.bias)
+            t0 = packing.pack_bias_table_rect(self.attns[0].bias_table(), 8, 32, 64)
+            t1 = packing.pack_bias_table_rect(self.attns[1].bias_table(), 32, 8, 24)
+            return qkv, vrow, proj, t0, t1
+        return self._cache.get(ps, build)
+
+    def run(self, x, out, H, W, norm: Optional[nn.LayerNorm], add_residual: bool):
+        """out (+)= Adaptive_Spatial_Attention(LN(x)) with the LayerNorm folded into the qkv GEMM when `norm` is given."""
+        _inference_only(self)
+        B, Ltok, C = x.shape
+        if Ltok != H * W:
+            raise RuntimeError("flatten img_tokens has wrong size")
+        if H % 32 or W % 32:
+            raise RuntimeError(f"Adaptive_Spatial_Attention: H, W ({H}, {W}) must be multiples of 32 (the padded case of "
+                               "dat_arch.py:376-385 is not implemented)")
+        if self.training:
+            raise RuntimeError("Adaptive_Spatial_Attention: eval mode required (BatchNorm running statistics)")
+        tokens = B * Ltok
+        (qw, qb), (vw, vb), (pw, pb), t0, t1 = self._packed(norm)
+        ln = norm is not None
+        planes = torch.empty((12, tokens, 64), dtype=torch.bfloat16, device=x.device)
+        # 32x8 windows shifted by 4 columns start 4 pixels off a multiple of 8: their planes use the (tok + 4) & 7 row phase
+        phase = sum(1 << p for p in (2, 3, 6, 7, 10, 11)) if self.shifted else 0
+        L.linear(x, qw, qb, planes, num_tokens=tokens, a_mode=L.LIN_A_ROWS, ld_in=C, apply_ln=ln, n_chunks=4,
+                 out_mode=L.LIN_OUT_PLANES, plane_phase_mask=phase)
+        v_rows = torch.empty((B, Ltok, C), dtype=torch.float32, device=x.device)
+        L.linear(x, vw, vb, v_rows, num_tokens=tokens, a_mode=L.LIN_A_ROWS, ld_in=C, apply_ln=ln, n_chunks=1,
+                 out_mode=L.LIN_OUT_ROWS, ld_out=C)
+        att = torch.empty((B, Ltok, C), dtype=torch.float32, device=x.device)
+        s0, s1 = self.shift_size
+        for i, (kind, tab, shift) in enumerate(((L.WA_DAT_8x32, t0, (s0, s1)), (L.WA_DAT_32x8, t1, (s1, s0)))):
+            L.window_attention(planes[2 * i:2 * i + 2], planes[4 + 2 * i:6 + 2 * i], planes[8 + 2 * i:10 + 2 * i], tab, att, kind=kind,
+                               batch=B, height=H, width=W, shift=shift if self.shifted else (0, 0), mask_shift=self.shifted,
+                               n_heads=3, out_mode=1, out_ld=C, out_col0=(C // 2) * i)
+        # adaptive interaction module (dat_arch.py:418-431): torch glue on channels-last views
+        conv_x = self.dwconv(self._img(v_rows, B, H, W))
+        channel_map = self.channel_interaction(conv_x).reshape(B, 1, C)
+        spatial_map = self.spatial_interaction(self._img(att, B, H, W))                       # (B, 1, H, W)
+        mix = att * torch.sigmoid(channel_map) + (torch.sigmoid(spatial_map) * conv_x).permute(0, 2, 3, 1).reshape(B, Ltok, C)
+        L.linear(mix.contiguous(), pw, pb, out, num_tokens=tokens, a_mode=L.LIN_A_ROWS, ld_in=C, apply_ln=False, n_chunks=1,
+                 out_mode=L.LIN_OUT_ROWS, ld_out=C, add_residual=add_residual)
+        return out
+
+    def forward(self, x, H, W):
+        x = x.contiguous()
+        return self.run(x, torch.empty_like(x), H, W, None, False)
+
+
+class Adaptive_Channel_Attention(_AIM):
+    """dat_arch.py:441-528.  forward(x: (B, H*W, 180) already normalised, H, W)."""
+
+    def __init__(self, dim, num_heads=8, qkv_bias=False, qk_scale=None, attn_drop=0., proj_drop=0.):
+        super().__init__()
+        self.num_heads = num_heads
+        self.temperature = nn.Parameter(torch.ones(num_heads, 1, 1))
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop)
+        self._build_aim(dim)
+        self._cache = _PackedCache()
+
+    def _packed(self, norm: Optional[nn.LayerNorm]):
+        if self.qkv.weight.shape != (3 * L.DIM, L.DIM):
+            raise RuntimeError(f"Adaptive_Channel_Attention: unsupported qkv geometry {tuple(self.qkv.weight.shape)}")
+        ps = [self.qkv.weight, self.qkv.bias, self.proj.weight, self.proj.bias] + ([norm.weight, norm.bias] if norm is not None else [])
+
+        def build():
+            lw, lb = (None, None) if norm is None else (norm.weight, norm.bias)
+            return packing.pack_rows_linear(self.qkv.weight, self.qkv.bias, lw, lb), packing.pack_rows_linear(self.proj.weight, self.proj.bias)
+        return self._cache.get(ps, build)
+
+    def run(self, x, out, H, W, norm: Optional[nn.LayerNorm], add_residual: bool):
+        _inference_only(self)
+        B, N, C = x.shape
+        if self.training:
+            raise RuntimeError("Adaptive_Channel_Attention: eval mode required (BatchNorm running statistics)")
+        nh, d = self.num_heads, C // self.num_heads
+        (qw, qb), (pw, pb) = self._packed(norm)
+        qkv = torch.empty((B, N, 3 * C), dtype=torch.float32, device=x.device)
+        L.linear(x, qw, qb, qkv, num_tokens=B * N, a_mode=L.LIN_A_ROWS, ld_in=C, apply_ln=norm is not None, n_chunks=3,
+                 out_mode=L.LIN_OUT_ROWS, ld_out=3 * C)
+        q, k, v = (qkv[..., i * C:(i + 1) * C].reshape(B, N, nh, d).permute(0, 2, 3, 1) for i in range(3))       # (B, nh, d, N)
+        attn = (F.normalize(q, dim=-1) @ F.normalize(k, dim=-1).transpose(-2, -1)) * self.temperature             # (B, nh, d, d)
+        att = (attn.softmax(dim=-1) @ v).permute(0, 3, 1, 2).reshape(B, N, C)
+        conv_x = self.dwconv(self._img(qkv[..., 2 * C:], B, H, W))
+        channel_map = self.channel_interaction(self._img(att, B, H, W))                       # (B, C, 1, 1)
+        spatial_map = self.spatial_interaction(conv_x).permute(0, 2, 3, 1).reshape(B, N, 1)
+        mix = att * torch.sigmoid(spatial_map) + (conv_x * torch.sigmoid(channel_map)).permute(0, 2, 3, 1).reshape(B, N, C)
+        L.linear(mix.contiguous(), pw, pb, out, num_tokens=B * N, a_mode=L.LIN_A_ROWS, ld_in=C, apply_ln=False, n_chunks=1,
+                 out_mode=L.LIN_OUT_ROWS, ld_out=C, add_residual=add_residual)
+        return out
+
+    def forward(self, x, H, W):
+        x = x.contiguous()
+        return self.run(x, torch.empty_like(x), H, W, None, False)
+
+
+class DATB(nn.Module):
+    """dat_arch.py:531-565.  forward(x: (B, H*W, 180), x_size)."""
+
+    def __init__(self, dim, num_heads, reso=64, split_size=[2, 4], shift_size=[1, 2], expansion_factor=4., qkv_bias=False,
+                 qk_scale=None, drop=0., attn_drop=0., drop_path=0., act_layer=nn.GELU, norm_layer=nn.LayerNorm, rg_idx=0, b_idx=0):
+        super().__init__()
+        if norm_layer is not nn.LayerNorm:
+            raise RuntimeError("DATB: only nn.LayerNorm is implemented")
+        self.norm1 = norm_layer(dim)
+        if b_idx % 2 == 0:
+            self.attn = Adaptive_Spatial_Attention(dim, num_heads=num_heads, reso=reso, split_size=split_size, shift_size=shift_size,
+                                                   qkv_bias=qkv_bias, qk_scale=qk_scale, drop=drop, attn_drop=attn_drop,
+                                                   rg_idx=rg_idx, b_idx=b_idx)
+        else:
+            self.attn = Adaptive_Channel_Attention(dim, num_heads=num_heads, qkv_bias=qkv_bias, qk_scale=qk_scale,
+                                                   attn_drop=attn_drop, proj_drop=drop)
+        self.drop_path = nn.Identity()
+        self.ffn = SGFN(in_features=dim, hidden_features=int(dim * expansion_factor), out_features=dim, act_layer=act_layer)
+        self.norm2 = norm_layer(dim)
+
+    def forward_into(self, x, x_size, out):
+        """out = DATB(x); ``out`` may be ``x`` (in place)."""
+        H, W = x_size
+        if out.data_ptr() != x.data_ptr():
+            out.copy_(x)
+        self.attn.run(x, out, H, W, self.norm1, True)            # x + attn(norm1(x)); x itself is only read before `out` changes
+        self.ffn.run(out, out, H, W, self.norm2, True)           # + ffn(norm2(.))
+        return out
+
+    def forward(self, x, x_size):
+        x = x.contiguous()
+        return self.forward_into(x, x_size, torch.empty_like(x))
+
+
+class ResidualGroup(nn.Module):
+    """dat_arch.py:568-652."""
+
+    def __init__(self, dim, reso, num_heads, split_size=[2, 4], expansion_factor=4., qkv_bias=False, qk_scale=None, drop=0.,
+                 attn_drop=0., drop_paths=None, act_layer=nn.GELU, norm_layer=nn.LayerNorm, depth=2, use_chk=False,
+                 resi_connection='1conv', rg_idx=0):
+        super().__init__()
+        self.use_chk, self.reso = use_chk, reso
+        self.blocks = nn.ModuleList([
+            DATB(dim=dim, num_heads=num_heads, reso=reso, split_size=split_size, shift_size=[split_size[0] // 2, split_size[1] // 2],
+                 expansion_factor=expansion_factor, qkv_bias=qkv_bias, qk_scale=qk_scale, drop=drop, attn_drop=attn_drop,
+                 drop_path=0., act_layer=act_layer, norm_layer=norm_layer, rg_idx=rg_idx, b_idx=i) for i in range(depth)])
+        if resi_connection == '1conv':
+            self.conv = nn.Conv2d(dim, dim, 3, 1, 1)
+        elif resi_connection == '3conv':
+            self.conv = nn.Sequential(nn.Conv2d(dim, dim // 4, 3, 1, 1), nn.LeakyReLU(negative_slope=0.2, inplace=True),
+                                      nn.Conv2d(dim // 4, dim // 4, 1, 1, 0), nn.LeakyReLU(negative_slope=0.2, inplace=True),
+                                      nn.Conv2d(dim // 4, dim, 3, 1, 1))
+        else:
+            raise ValueError(resi_connection)
+
+    def forward(self, x, x_size):
+        H, W = x_size
+        x = x.contiguous()
+        B, Ltok, C = x.shape
+        out = torch.empty_like(x)
+        src = x
+        for blk in self.blocks:          # first block out of place (x is the group's residual), the rest in place
+            blk.forward_into(src, x_size, out)
+            src = out
+        y = self.conv(out.view(B, H, W, C).permute(0, 3, 1, 2))
+        return x + y.permute(0, 2, 3, 1).reshape(B, Ltok, C)
+
+
+class DAT(nn.Module):
+    """dat_arch.py:697-858.  forward(x: (B, 3, H, W)) -> (B, 3, H*s, W*s); H, W multiples of 32."""
+
+    def __init__(self, img_size=64, in_chans=3, embed_dim=180, split_size=[2, 4], depth=[2, 2, 2, 2], num_heads=[2, 2, 2, 2],
+                 expansion_factor=4., qkv_bias=True, qk_scale=None, drop_rate=0., attn_drop_rate=0., drop_path_rate=0.1,
+                 act_layer=nn.GELU, norm_layer=nn.LayerNorm, use_chk=False, upscale=2, img_range=1., resi_connection='1conv',
+                 upsampler='pixelshuffle', **kwargs):
+        super().__init__()
+        num_in_ch = num_out_ch = in_chans
+        num_feat = 64
+        self.img_range = img_range
+        self.mean = torch.Tensor((0.4488, 0.4371, 0.4040)).view(1, 3, 1, 1) if in_chans == 3 else torch.zeros(1, 1, 1, 1)
+        self.upscale, self.upsampler = upscale, upsampler
+        self.conv_first = nn.Conv2d(num_in_ch, embed_dim, 3, 1, 1)
+        self.num_layers, self.use_chk = len(depth), use_chk
+        self.num_features = self.embed_dim = embed_dim
+        # index 0 of the reference's Sequential is einops' Rearrange('b c h w -> b (h w) c'): a view here (channels-last stream)
+        self.before_RG = nn.Sequential(nn.Identity(), nn.LayerNorm(embed_dim))
+        self.layers = nn.ModuleList([
+            ResidualGroup(dim=embed_dim, num_heads=num_heads[i], reso=img_size, split_size=split_size,
+                          expansion_factor=expansion_factor, qkv_bias=qkv_bias, qk_scale=qk_scale, drop=drop_rate,
+                          attn_drop=attn_drop_rate, drop_paths=None, act_layer=act_layer, norm_layer=norm_layer, depth=depth[i],
+                          use_chk=use_chk, resi_connection=resi_connection, rg_idx=i) for i in range(self.num_layers)])
+        self.norm = norm_layer(embed_dim)
+        if resi_connection == '1conv':
+            self.conv_after_body = nn.Conv2d(embed_dim, embed_dim, 3, 1, 1)
+        elif resi_connection == '3conv':
+            self.conv_after_body = nn.Sequential(
+                nn.Conv2d(embed_dim, embed_dim // 4, 3, 1, 1), nn.LeakyReLU(negative_slope=0.2, inplace=True),
+                nn.Conv2d(embed_dim // 4, embed_dim // 4, 1, 1, 0), nn.LeakyReLU(negative_slope=0.2, inplace=True),
+                nn.Conv2d(embed_dim // 4, embed_dim, 3, 1, 1))
+        if self.upsampler == 'pixelshuffle':
+            self.conv_before_upsample = nn.Sequential(nn.Conv2d(embed_dim, num_feat, 3, 1, 1), nn.LeakyReLU(inplace=True))
+            self.upsample = Upsample(upscale, num_feat)
+            self.conv_last = nn.Conv2d(num_feat, num_out_ch, 3, 1, 1)
+        elif self.upsampler == 'pixelshuffledirect':
+            self.upsample = UpsampleOneStep(upscale, embed_dim, num_out_ch, (img_size, img_size))
+        self.apply(self._init_weights)
+        self._channels_last_done = None
+
+    def _init_weights(self, m):
+        if isinstance(m, nn.Linear):
+            nn.init.trunc_normal_(m.weight, std=.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, (nn.LayerNorm, nn.BatchNorm2d, nn.GroupNorm, nn.InstanceNorm2d)):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    def _prepare(self, device):
+        if self._channels_last_done != str(device):
+            for m in self.modules():
+                if isinstance(m, nn.Conv2d):
+                    m.weight.data = m.weight.data.contiguous(memory_format=torch.channels_last)
+            self._channels_last_done = str(device)
+
+    def forward_features(self, x):
+        B, C, H, W = x.shape
+        x_size = [H, W]
+        t = x.permute(0, 2, 3, 1).reshape(B, H * W, C).contiguous()
+        y = torch.empty_like(t)
+        ln = self.before_RG[1]
+        L.layernorm(t, y, ln.weight, ln.bias, num_tokens=B * H * W, ld_in=C, ld_out=C)
+        for layer in self.layers:
+            y = layer(y, x_size)
+        y = y.contiguous()
+        L.layernorm(y, y, self.norm.weight, self.norm.bias, num_tokens=B * H * W, ld_in=C, ld_out=C)
+        return y.view(B, H, W, C).permute(0, 3, 1, 2)
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("DAT: CUDA input required (no CPU fallback)")
+        if self.training:
+            raise RuntimeError("DAT: eval mode required")
+        _inference_only(self.conv_first)
+        self._prepare(x.device)
+        self.mean = self.mean.type_as(x)
+        x = ((x - self.mean) * self.img_range).contiguous(memory_format=torch.channels_last)
+        x = self.conv_first(x)
+        x = self.conv_after_body(self.forward_features(x)) + x
+        if self.upsampler == 'pixelshuffle':
+            x = self.conv_before_upsample(x)
+            x = self.conv_last(self.upsample(x))
+        else:
+            x = self.upsample(x)
+        return x / self.img_range + self.mean

@@ -249,3 +249,73 @@ def make_pad_pages(device) -> torch.Tensor:
     rows[0, :, L.HEAD_PAD + L.HEAD_DIM] = 1.0
     v = unswizzle_planes(rows, 0)[0].contiguous().view(torch.uint8).reshape(-1)      # involution: this applies the swizzle
     return torch.cat([torch.zeros(4096, dtype=torch.uint8), v]).to(device)
+
+
+# ------------------------------------------------------------------------------------------------
+# DAT path
+# ------------------------------------------------------------------------------------------------
+def _fold_ln(w: torch.Tensor, b, ln_w, ln_b):
+    """(W, b) of a Linear applied to LayerNorm(x) -> (W', b') applied to (x - mean) * rstd."""
+    w = w.detach().cpu().double()
+    b = torch.zeros(w.shape[0], dtype=torch.float64) if b is None else b.detach().cpu().double()
+    if ln_b is not None:
+        b = b + w @ ln_b.detach().cpu().double()
+    if ln_w is not None:
+        w = w * ln_w.detach().cpu().double()[None, :]
+    return w, b
+
+
+@torch.no_grad()
+def pack_rows_linear(w, b, ln_w=None, ln_b=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Linear (N, 180) with N a multiple of 180 -> (wstream, bias) for srk_linear_fwd with fp32 row output: chunk c = output
+    columns [180 c, 180 c + 180), each padded to 192 weight rows."""
+    dev = w.device
+    N, K = w.shape
+    if K != L.DIM or N % L.DIM:
+        raise RuntimeError(f"unsupported linear geometry {tuple(w.shape)}: K must be 180 and N a multiple of 180")
+    wf, bf = _fold_ln(w, b, ln_w, ln_b)
+    nch = N // L.DIM
+    w_pad = torch.zeros(nch, 192, L.DIM_PAD)
+    w_pad[:, :L.DIM, :K] = wf.float().view(nch, L.DIM, K)
+    b_pad = torch.zeros(nch, 192)
+    b_pad[:, :L.DIM] = bf.float().view(nch, L.DIM)
+    return pack_linear_stream(w_pad.reshape(nch * 192, L.DIM_PAD)).to(dev), b_pad.reshape(-1).contiguous().to(dev)
+
+
+@torch.no_grad()
+def pack_dat_qkv_planes(qkv_w, qkv_b, ln_w=None, ln_b=None, scale=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """DAT spatial block qkv (540, 180) -> (wstream, bias[768]) producing 12 planes: for each of q, k, v the head pairs
+    (h0, h1) (h2, -) of the first channel half (8x32 windows) and (h3, h4) (h5, -) of the second (32x8 windows),
+    dat_arch.py:286-291, :409-415.  q carries head_dim**-0.5 * log2(e); dim 30 of every real v head is the ones column."""
+    dev = qkv_w.device
+    C = L.DIM
+    if tuple(qkv_w.shape) != (3 * C, C):
+        raise RuntimeError(f"unsupported qkv geometry {tuple(qkv_w.shape)}")
+    scale = (L.HEAD_DIM ** -0.5) if scale is None else float(scale)
+    w, b = _fold_ln(qkv_w, qkv_b, ln_w, ln_b)
+    w[:C] *= scale * LOG2E
+    b[:C] *= scale * LOG2E
+    slots = [0, 1, 2, None, 3, 4, 5, None]                         # head in each 32-row slot of a 256-row part
+    w_pad = torch.zeros(3, 8, L.HEAD_PAD, L.DIM_PAD)
+    b_pad = torch.zeros(3, 8, L.HEAD_PAD)
+    for part in range(3):
+        for s, h in enumerate(slots):
+            if h is None:
+                continue
+            rows = slice(part * C + h * L.HEAD_DIM, part * C + (h + 1) * L.HEAD_DIM)
+            w_pad[part, s, :L.HEAD_DIM, :C] = w[rows].float()
+            b_pad[part, s, :L.HEAD_DIM] = b[rows].float()
+            if part == 2:
+                b_pad[part, s, L.HEAD_DIM] = 1.0
+    return pack_linear_stream(w_pad.reshape(768, L.DIM_PAD)).to(dev), b_pad.reshape(-1).contiguous().to(dev)
+
+
+@torch.no_grad()
+def pack_bias_table_rect(pos: torch.Tensor, hs: int, ws: int, sy: int) -> torch.Tensor:
+    """Dynamic position bias (offsets (2hs-1)(2ws-1), heads 3) (dat_arch.py:219-225) -> [4][(2hs-1) * sy] floats * log2(e),
+    entry dy * sy + dx for (dy, dx) = (yi - yj + hs - 1, xi - xj + ws - 1); head slot 3 is padding."""
+    nh = pos.shape[1]
+    t = pos.detach().cpu().float().t().reshape(nh, 2 * hs - 1, 2 * ws - 1) * LOG2E
+    out = torch.zeros(4, 2 * hs - 1, sy)
+    out[:nh, :, :2 * ws - 1] = t
+    return out.reshape(4, -1).contiguous().to(pos.device)
