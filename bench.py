@@ -5,7 +5,7 @@
 
 One "step" = one pass of the hot path over one batch of synthetic input: by default BASELINE.json configs[1],
 SwinIR classical x4 on a batch of 16 LR tiles of 64x64 per GPU (16 x 3 x 256 x 256 = 1.049 output Mpix);
-`--workload hat_x4` times configs[2] (HAT x4, batch 8) the same way.
+`--workload hat_x4` / `dat_x2` time configs[2] (HAT x4, batch 8) and configs[3] (DAT x2, batch 16) the same way.
 With N > 1 (torchrun, one rank per GPU) every rank runs its own batch -- tiles are independent, there is
 no collective on the data path -- so scaling is "weak" and `value` is the sum over ranks divided by the
 slowest rank's time.  JSON keys follow the driver contract; see DESIGN.md "Measurement".
@@ -26,24 +26,31 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 TILE = 64
-SCALE = 4
 # algorithmic FLOPs, 2/MAC, un-padded dims.  "kernels": libsrk launch name -> FLOP per token per launch.
 WORKLOADS = {
     # BASELINE.json configs[1]: the configuration the metric is quoted on (default)
     "swinir_x4": dict(
-        metric="SwinIR x4 output Mpix/s", family="swinir", cfg="swinir_x4", tiles=16, gflop_per_tile=107.113,
+        metric="SwinIR x4 output Mpix/s", family="swinir", cfg="swinir_x4", tiles=16, scale=4, gflop_per_tile=107.113,
         workload="SwinIR classical x4 (embed 180, 6 RSTB x 6, window 8, 6 heads, mlp_ratio 2), batch 16 of 64x64 LR tiles per GPU",
         dominant="swin_attn", kernel_name="swin_attn_kernel",
         kernels={"swin_attn": 305_280,      # qkv + qk^T + pv + proj (one swin_attn_kernel launch covers all tokens of the batch)
                  "swin_mlp": 259_200}),     # fc1 + fc2
     # BASELINE.json configs[2]: HAT x4, window 16, OCAB overlap 0.5, CAB, batch 8
     "hat_x4": dict(
-        metric="HAT x4 output Mpix/s", family="hat", cfg="hat_x4", tiles=8, gflop_per_tile=207.761,
+        metric="HAT x4 output Mpix/s", family="hat", cfg="hat_x4", tiles=8, scale=4, gflop_per_tile=207.761,
         workload="HAT x4 (embed 180, 6 RHAG x (6 HAB + OCAB), window 16, overlap 0.5, CAB 3/30, mlp_ratio 2), batch 8 of 64x64 LR tiles per GPU",
         dominant="window_attention", kernel_name="winattn_kernel",
         kernels={"window_attention": (36 * 184_320 + 6 * 414_720) / 42,    # qk^T + pv: 256 keys (36 W-MSA) / 576 keys (6 OCAB) per launch
                  "linear": (42 * 194_400 + 42 * 64_800) / 84,              # qkv and proj launches
                  "swin_mlp": 259_200}),
+    # BASELINE.json configs[3]: DAT x2, split 8x32, expansion 4, batch 16
+    "dat_x2": dict(
+        metric="DAT x2 output Mpix/s", family="dat", cfg="dat_x2", tiles=16, scale=2, gflop_per_tile=131.635,
+        workload="DAT x2 (embed 180, 6 RG x 6 DATB, split 8x32, 6 heads, expansion 4), batch 16 of 64x64 LR tiles per GPU",
+        dominant="window_attention", kernel_name="winattn_kernel",
+        kernels={"window_attention": 92_160,       # qk^T + pv of the 3 heads of one channel half (two launches per spatial block)
+                 # per DATB: spatial qkv planes 194400 + v rows 64800 (or channel qkv 194400) + proj 64800 + fc1 259200 + fc2 2 x 64800
+                 "linear": (18 * (194_400 + 64_800) + 18 * 194_400 + 36 * (64_800 + 259_200 + 129_600)) / (18 * 2 + 18 + 36 * 4)}),
 }
 W = WORKLOADS["swinir_x4"]      # replaced in main()
 
@@ -56,9 +63,13 @@ def _build(family, cfg_name):
         from oracle import swinir_oracle as O
         cfg = synth.CONFIGS[cfg_name]
         return cfg, synth.make_swinir_state_dict(cfg, seed=1234, kind="init"), srk.SwinIR, O.swinir_forward
-    from oracle import hat_oracle as HO
-    cfg = synth.HAT_CONFIGS[cfg_name]
-    return cfg, synth.make_hat_state_dict(cfg, seed=1234, kind="init"), srk.HAT, HO.hat_forward
+    if family == "hat":
+        from oracle import hat_oracle as HO
+        cfg = synth.HAT_CONFIGS[cfg_name]
+        return cfg, synth.make_hat_state_dict(cfg, seed=1234, kind="init"), srk.HAT, HO.hat_forward
+    from oracle import dat_oracle as DO
+    cfg = synth.DAT_CONFIGS[cfg_name]
+    return cfg, synth.make_dat_state_dict(cfg, seed=1234, kind="init"), srk.DAT, DO.dat_forward
 
 
 def _peaks():
@@ -146,7 +157,7 @@ def cpu_oracle_rate(tiles: int, reps: int = 1, warm: bool = True):
             t0 = time.perf_counter()
             oracle_fwd(lr, sd, cfg)
             best = min(best, time.perf_counter() - t0)
-    return tiles * (TILE * SCALE) ** 2 / best / 1e6, cores, best
+    return tiles * (TILE * W['scale']) ** 2 / best / 1e6, cores, best
 
 
 def run_reference(args):
@@ -168,7 +179,7 @@ def run_reference(args):
         for _ in range(args.steps):
             oracle_fwd(lr, sd, cfg)
         dt = time.perf_counter() - t0
-    mpix = sample_tiles * (TILE * SCALE) ** 2 / 1e6
+    mpix = sample_tiles * (TILE * W['scale']) ** 2 / 1e6
     value = mpix * args.steps / dt
     sample = f"{sample_tiles} of the {W['tiles']} tiles of one step per timed step, fp32, torch CPU ops, {cores} threads"
     print(json.dumps({
@@ -207,9 +218,9 @@ def run_ours(args):
     n_in = 4                                        # rotate distinct input batches
     host_in = [synth.make_lr_batch(TILES_PER_STEP, TILE, TILE, seed=100 + rank * n_in + i).pin_memory() for i in range(n_in)]
     dev_in = [h.to(dev) for h in host_in]
-    host_out = torch.empty(TILES_PER_STEP, 3, TILE * SCALE, TILE * SCALE).pin_memory()
+    host_out = torch.empty(TILES_PER_STEP, 3, TILE * W['scale'], TILE * W['scale']).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
-    mpix_step = TILES_PER_STEP * (TILE * SCALE) ** 2 / 1e6
+    mpix_step = TILES_PER_STEP * (TILE * W['scale']) ** 2 / 1e6
     stream = torch.cuda.current_stream()
 
     def step_resident(i):
