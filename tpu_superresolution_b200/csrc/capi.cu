@@ -142,6 +142,7 @@ int srk_linear_fwd(const SrkLinearDesc* d, const void* a, const void* wstream, c
     } else {
         return fail("srk_linear_fwd: unknown out_mode %d", d->out_mode);
     }
+    p.dbg = srk::g_timeline;
     return check(srk::launch_token_linear(p, static_cast<cudaStream_t>(stream)), "srk_linear_fwd");
 }
 

@@ -52,6 +52,7 @@ struct LinearParams {
     uint32_t plane_phase_mask;   // bit p set: plane p is swizzled with (tok + 4) & 7 instead of tok & 7
     float* y;                    // SRK_LIN_OUT_ROWS
     int ld_out, add_residual;
+    unsigned long long* dbg;     // optional timeline buffer (srk_debug_set_timeline)
 };
 
 // winattn_kernel (winattn_kernel.cu)

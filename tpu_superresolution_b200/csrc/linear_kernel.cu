@@ -12,9 +12,10 @@
 // :435, :483, :526, :79-88 (qkv / proj / fc1 / fc2).
 //
 // One persistent CTA per SM over 128-token tiles, N processed in chunks of 192 columns with double-buffered TMEM
-// accumulators (the epilogue of chunk c overlaps the MMAs of chunk c + 1).  320 threads: warp 0 producer (weight
+// accumulators (the epilogue of chunk c overlaps the MMAs of chunk c + 1).  448 threads: warp 0 producer (weight
 // slabs through a 3-stage ring, A planes), warp 1 MMA issuer, warps 2..9 = 256 row threads (thread <-> TMEM lane <->
-// token row; the two groups split the columns of every chunk).
+// token row; the two groups split the columns of every chunk), warps 10..13 = LayerNorm warps that load and normalise the
+// NEXT tile's rows into registers while this tile's GEMMs still read the operand image, then dump them into it.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -26,7 +27,7 @@
 namespace srk {
 
 namespace {
-constexpr int LIN_THREADS = 320;
+constexpr int LIN_THREADS = 448;          // producer, MMA issuer, 8 row warps, 4 LayerNorm warps
 constexpr int LIN_RING_N = 3;
 constexpr uint32_t LIN_SLAB = 24576;             // 192 rows x 64 k
 constexpr uint32_t LIN_NC = 192;                 // columns per chunk
@@ -39,10 +40,15 @@ __host__ __device__ constexpr uint32_t lin_off_ring(int k_atoms) { return k_atom
 __host__ __device__ constexpr uint32_t lin_off_vec(int k_atoms) { return lin_off_ring(k_atoms) + LIN_RING_N * LIN_SLAB; }
 __host__ __device__ constexpr uint32_t lin_off_bar(int k_atoms) { return lin_off_vec(k_atoms) + LIN_VEC_BYTES; }
 __host__ __device__ constexpr uint32_t lin_off_stage(int k_atoms) { return lin_off_bar(k_atoms) + 256; }
-__host__ __device__ constexpr uint32_t lin_smem(int k_atoms, bool separate_stage) {
-    return lin_off_stage(k_atoms) + (separate_stage ? 128 * 720 : 0) + 1024;
+// OUT_PLANES: the three 64-column planes of a chunk are staged as [plane][128 rows][128 B] -- exactly the global layout of 128
+// consecutive tokens -- and leave with one 16 KB bulk copy per plane; double buffered when the A image is 48 KB.
+constexpr uint32_t LIN_PSTAGE = 3 * ATOM_A;
+__host__ __device__ constexpr int lin_n_pstage(int k_atoms) { return k_atoms == 3 ? 2 : 1; }
+__host__ __device__ constexpr uint32_t lin_smem(int k_atoms, bool separate_stage, bool planes_out = false) {
+    return lin_off_stage(k_atoms) + (separate_stage ? 128 * 720 : 0) + (planes_out ? lin_n_pstage(k_atoms) * LIN_PSTAGE : 0) + 1024;
 }
-static_assert(lin_smem(3, true) <= 232448 && lin_smem(6, false) <= 232448, "token_linear shared memory");
+static_assert(lin_smem(3, true) <= 232448 && lin_smem(6, false) <= 232448 && lin_smem(3, false, true) <= 232448 &&
+              lin_smem(6, false, true) <= 232448, "token_linear shared memory");
 enum { LB_FULL = 0, LB_EMPTY = 3, LB_AFULL = 6, LB_AEMPTY = 7, LB_ACCF = 8, LB_ACCE = 10, LB_DRAIN = 12, LB_COUNT = 13 };
 
 __device__ __forceinline__ void st_global_v4b(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -68,7 +74,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) token_linear_kernel(const Line
     for (int i = threadIdx.x; i < p.n_chunks * (int)LIN_NC; i += blockDim.x) s_vec[i] = p.bias[i];
     if (threadIdx.x == 0) {
         for (int i = 0; i < LIN_RING_N; ++i) { mbar_init(&bars[LB_FULL + i], 1); mbar_init(&bars[LB_EMPTY + i], 1); }
-        mbar_init(&bars[LB_AFULL], a_rows ? 256 : 1);
+        mbar_init(&bars[LB_AFULL], a_rows ? 128 : 1);
         mbar_init(&bars[LB_AEMPTY], 1);
         mbar_init(&bars[LB_ACCF], 1);     mbar_init(&bars[LB_ACCF + 1], 1);
         mbar_init(&bars[LB_ACCE], 256);   mbar_init(&bars[LB_ACCE + 1], 256);
@@ -135,23 +141,54 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) token_linear_kernel(const Line
             }
         }
         __syncwarp();
+    } else if (warp >= 10) {
+        // ===================================================== 4 LayerNorm warps (fp32 row input): run one tile ahead of the GEMMs
+        if (a_rows) {
+            const int lw = warp - 10;                 // rows [32 lw, 32 lw + 32) of the tile
+            uint32_t ph_ae = 0;
+            // the first tile is normalised by the 8 row warps (twice the loads in flight at kernel start); these warps start on the second
+            for (int tile = blockIdx.x + gridDim.x; tile < p.n_tiles; tile += gridDim.x) {
+                auto tok_of_row = [&](int r) -> int64_t {
+                    const int64_t tk = static_cast<int64_t>(tile) * 128 + r;
+                    return tk < p.num_tokens ? tk : static_cast<int64_t>(-1);
+                };
+                uint2 h0[4][3], h1[4][3], h2[4][3], h3[4][3];     // 32 rows x 192 channels / 32 lanes, bf16: 96 registers
+                ln_rows_hold<4>(p.x, p.ld_in, p.apply_ln, 32 * lw, lane, tok_of_row, h0);
+                ln_rows_hold<4>(p.x, p.ld_in, p.apply_ln, 32 * lw + 8, lane, tok_of_row, h1);
+                ln_rows_hold<4>(p.x, p.ld_in, p.apply_ln, 32 * lw + 16, lane, tok_of_row, h2);
+                ln_rows_hold<4>(p.x, p.ld_in, p.apply_ln, 32 * lw + 24, lane, tok_of_row, h3);
+                mbar_wait(&bars[LB_AEMPTY], ph_ae); ph_ae ^= 1;             // the previous tile's MMAs have read the A image
+                ln_rows_dump<4>(sbase + L_A, 32 * lw, lane, h0);
+                ln_rows_dump<4>(sbase + L_A, 32 * lw + 8, lane, h1);
+                ln_rows_dump<4>(sbase + L_A, 32 * lw + 16, lane, h2);
+                ln_rows_dump<4>(sbase + L_A, 32 * lw + 24, lane, h3);
+                fence_proxy_async_smem();
+                mbar_arrive(&bars[LB_AFULL]);
+            }
+        }
     } else {
         // ===================================================== 256 row threads
         const int cw8 = warp - 2, g = cw8 >> 2, q = warp & 3, row = q * 32 + lane;
         const uint32_t lanebase = static_cast<uint32_t>(q * 32) << 16;
-        uint32_t ph_accf[2] = {0, 0}, nacc = 0;
-        auto ln_tile = [&](int tile) {
+        uint32_t ph_accf[2] = {0, 0}, nacc = 0, nplane = 0;
+        if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) p.dbg[62] = clock64();
+        if (a_rows && static_cast<int>(blockIdx.x) < p.n_tiles) {      // first tile: all 8 row warps normalise it (see the LayerNorm warps)
+            const int tile = blockIdx.x;
             auto tok_of_row = [&](int r) -> int64_t {
                 const int64_t tk = static_cast<int64_t>(tile) * 128 + r;
                 return tk < p.num_tokens ? tk : static_cast<int64_t>(-1);
             };
             ln_rows_to_image(p.x, p.ld_in, p.apply_ln, sbase + L_A, cw8, lane, tok_of_row);
             fence_proxy_async_smem();
-            mbar_arrive(&bars[LB_AFULL]);
-        };
-        if (a_rows && static_cast<int>(blockIdx.x) < p.n_tiles) ln_tile(blockIdx.x);
+            named_bar_sync(1, 256);
+            if (g == 0) mbar_arrive(&bars[LB_AFULL]);
+        }
         bool first_tile = true;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        unsigned long long* dbg = (blockIdx.x == 0 && threadIdx.x == 64) ? p.dbg : nullptr;
+        int it = 0;
+        if (dbg) dbg[63] = clock64();
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            if (dbg && it < 8) dbg[it * 64 + 0] = clock64();
             const int64_t tok = static_cast<int64_t>(tile) * 128 + row;
             const bool live = tok < p.num_tokens;
             auto tok_of_row = [&](int r) -> int64_t {
@@ -163,10 +200,18 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) token_linear_kernel(const Line
                 ++nacc;
                 mbar_wait(&bars[LB_ACCF + buf], ph_accf[buf]); ph_accf[buf] ^= 1;
                 tc_fence_after();
-                // all GEMMs of this tile are complete after its last chunk: the A image is free for the next tile
-                if (a_rows && c == p.n_chunks - 1 && tile + static_cast<int>(gridDim.x) < p.n_tiles) ln_tile(tile + gridDim.x);
+                if (dbg && it < 8) dbg[it * 64 + 1 + 3 * c] = clock64();
+                if (dbg && it < 8) dbg[it * 64 + 2 + 3 * c] = clock64();
                 const uint32_t acc = tmem + lanebase + 256 * buf;
                 if (!out_rows) {
+                    // ---- accumulator + bias (+ GELU) -> bf16 -> staged plane rows -> one bulk copy per plane
+                    const int n_ps = lin_n_pstage(p.k_atoms);
+                    uint8_t* pst = sm + ((lin_off_stage(p.k_atoms) + 1023u) & ~1023u) + (nplane % n_ps) * LIN_PSTAGE;
+                    ++nplane;
+                    if (threadIdx.x == 64) {                  // the issuing thread: the copies that last read this buffer are done
+                        if (n_ps == 2) bulk_wait_read1(); else bulk_wait_read0();
+                    }
+                    named_bar_sync(1, 256);
 #pragma unroll 1
                     for (int pi = 0; pi < 3; ++pi) {
                         const int piece = 3 * g + pi;                       // 32 columns of the chunk
@@ -184,14 +229,23 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) token_linear_kernel(const Line
                             pw[2 * k] = pack_bf16x2(f0, f1);
                             pw[2 * k + 1] = pack_bf16x2(f2, f3);
                         }
-                        if (live) {
-                            const int plane = c * 3 + (piece >> 1);
-                            const uint32_t key = static_cast<uint32_t>(tok + (((p.plane_phase_mask >> plane) & 1u) << 2)) & 7u;
-                            uint8_t* dst = p.out_planes + plane * p.out_plane_stride + tok * 128;
+                        const int plane = c * 3 + (piece >> 1);
+                        const uint32_t key = static_cast<uint32_t>(tok + (((p.plane_phase_mask >> plane) & 1u) << 2)) & 7u;
+                        const uint32_t dst = smem_u32(pst) + (piece >> 1) * ATOM_A + row * 128;
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                st_global_v4b(dst + (((4 * (piece & 1) + k) ^ key) << 4), pw[4 * k], pw[4 * k + 1], pw[4 * k + 2], pw[4 * k + 3]);
-                        }
+                        for (int k = 0; k < 4; ++k)
+                            st_shared_v4(dst + (((4 * (piece & 1) + k) ^ key) << 4), pw[4 * k], pw[4 * k + 1], pw[4 * k + 2], pw[4 * k + 3]);
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(1, 256);
+                    if (threadIdx.x == 64) {
+                        const int64_t tok0 = static_cast<int64_t>(tile) * 128;
+                        const int64_t left = p.num_tokens - tok0;
+                        const uint32_t bytes = (left < 128 ? static_cast<uint32_t>(left) : 128u) * 128u;
+#pragma unroll
+                        for (int pl = 0; pl < 3; ++pl)
+                            bulk_s2g(p.out_planes + (c * 3 + pl) * p.out_plane_stride + tok0 * 128, smem_u32(pst) + pl * ATOM_A, bytes);
+                        bulk_commit();
                     }
                 } else {
                     if (!(first_tile && c == 0) && !stage_alias) {      // the previous chunk's copies no longer read the staging rows
@@ -208,9 +262,11 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) token_linear_kernel(const Line
                 }
                 tc_fence_before();
                 mbar_arrive(&bars[LB_ACCE + buf]);
+                if (dbg && it < 8) dbg[it * 64 + 3 + 3 * c] = clock64();
             }
             first_tile = false;
         }
+        bulk_wait_read0();          // shared memory must outlive the bulk copies that read it
     }
     tc_fence_before();
     __syncthreads();
@@ -220,7 +276,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) token_linear_kernel(const Line
 cudaError_t launch_token_linear(const LinearParams& p, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(token_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_smem(3, true));
+        cudaError_t e = cudaFuncSetAttribute(token_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) return e;
         configured = true;
     }
@@ -232,7 +288,7 @@ cudaError_t launch_token_linear(const LinearParams& p, cudaStream_t stream) {
         if (sms <= 0) sms = 148;
     }
     const bool need_stage = p.out_mode == SRK_LIN_OUT_ROWS && p.k_atoms == 3;
-    const uint32_t smem = lin_smem(p.k_atoms, need_stage);
+    const uint32_t smem = lin_smem(p.k_atoms, need_stage, p.out_mode == SRK_LIN_OUT_PLANES) + 1024;
     const int grid = p.n_tiles < sms ? p.n_tiles : sms;
     token_linear_kernel<<<grid, LIN_THREADS, smem, stream>>>(p);
     return cudaGetLastError();

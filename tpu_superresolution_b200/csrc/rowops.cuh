@@ -83,6 +83,79 @@ __device__ __forceinline__ void ln_rows_to_image(const float* __restrict__ x, in
     }
 }
 
+
+// Split form of ln_rows_to_image for dedicated LayerNorm warps that run AHEAD of the GEMMs: ln_rows_hold() loads and
+// normalises NPASS x 2 token rows (half-warp per row) and keeps them as packed bf16 in registers (6 per row pair) while
+// the operand image is still being read by the previous tile's MMAs; ln_rows_dump() writes them into the image once it is
+// free -- the global-memory latency of the next tile is then off the critical path, only the dump (a few hundred cycles) is on it.
+template <int NPASS, typename TokFn>
+__device__ __forceinline__ void ln_rows_hold(const float* __restrict__ x, int ld, int apply_ln, int row0, int lane, TokFn tok_of_row,
+                                             uint2 (&held)[NPASS][3]) {
+    const int l16 = lane & 15;
+    const bool live2 = l16 < 13;
+    float4 v[NPASS][3];
+#pragma unroll
+    for (int pass = 0; pass < NPASS; ++pass) {
+        const int64_t tok = tok_of_row(row0 + pass * 2 + (lane >> 4));
+        const float4* src = reinterpret_cast<const float4*>(x + (tok >= 0 ? tok : 0) * ld) + l16;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        v[pass][0] = tok >= 0 ? __ldg(src) : z;
+        v[pass][1] = tok >= 0 ? __ldg(src + 16) : z;
+        v[pass][2] = (tok >= 0 && live2) ? __ldg(src + 32) : z;
+    }
+    float s[NPASS], q[NPASS];
+#pragma unroll
+    for (int pass = 0; pass < NPASS; ++pass) {
+        float4(&w)[3] = v[pass];
+        s[pass] = 0.f; q[pass] = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 3; ++jj) {
+            s[pass] += (w[jj].x + w[jj].y) + (w[jj].z + w[jj].w);
+            q[pass] = fmaf(w[jj].x, w[jj].x, q[pass]); q[pass] = fmaf(w[jj].y, w[jj].y, q[pass]);
+            q[pass] = fmaf(w[jj].z, w[jj].z, q[pass]); q[pass] = fmaf(w[jj].w, w[jj].w, q[pass]);
+        }
+    }
+    if (apply_ln) {
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+#pragma unroll
+            for (int pass = 0; pass < NPASS; ++pass) {
+                s[pass] += __shfl_xor_sync(0xffffffffu, s[pass], o);
+                q[pass] += __shfl_xor_sync(0xffffffffu, q[pass], o);
+            }
+        }
+    }
+#pragma unroll
+    for (int pass = 0; pass < NPASS; ++pass) {
+        float4(&w)[3] = v[pass];
+        if (apply_ln) {
+            const float mean = s[pass] * (1.0f / SRK_DIM);
+            const float var = fmaxf(fmaf(-mean, mean, q[pass] * (1.0f / SRK_DIM)), 0.f);
+            const float rstd = rsqrtf(var + 1e-5f);
+            const float nm = -mean * rstd;
+#pragma unroll
+            for (int jj = 0; jj < 3; ++jj) {
+                w[jj].x = fmaf(w[jj].x, rstd, nm); w[jj].y = fmaf(w[jj].y, rstd, nm);
+                w[jj].z = fmaf(w[jj].z, rstd, nm); w[jj].w = fmaf(w[jj].w, rstd, nm);
+            }
+            if (!live2) w[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int jj = 0; jj < 3; ++jj) held[pass][jj] = make_uint2(pack_bf16x2(w[jj].x, w[jj].y), pack_bf16x2(w[jj].z, w[jj].w));
+    }
+}
+template <int NPASS>
+__device__ __forceinline__ void ln_rows_dump(uint32_t xa, int row0, int lane, const uint2 (&held)[NPASS][3]) {
+    const int l16 = lane & 15;
+#pragma unroll
+    for (int pass = 0; pass < NPASS; ++pass) {
+        const uint32_t r = row0 + 2 * pass + (lane >> 4);
+        const uint32_t off = xa + sw128_off(r, l16 >> 1) + (l16 & 1) * 8;
+#pragma unroll
+        for (int jj = 0; jj < 3; ++jj) st_shared_v2(off + jj * ATOM_A, held[pass][jj].x, held[pass][jj].y);
+    }
+}
+
 // 32 fp32 accumulators (+ per-column bias from smem | * scale) -> 4 x 16-byte bf16 chunks of one image row.
 template <bool HAS_BIAS, bool HAS_SCALE>
 __device__ __forceinline__ void store_row_chunks(uint32_t img_atom, uint32_t row, uint32_t c16base, const uint32_t (&v)[32],

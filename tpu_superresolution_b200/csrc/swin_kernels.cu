@@ -26,7 +26,7 @@
 
 namespace srk {
 
-constexpr int NTHREADS = 320;          // K2: producer + MMA + 8 row warps
+constexpr int NTHREADS = 448;          // K2: producer + MMA + 8 row warps + 4 LayerNorm warps
 constexpr int NROWTHREADS = 256;
 constexpr int K1_THREADS = 448;        // K1: + 4 utility warps (q|k epilogues, next-tile normalisation)
 constexpr uint32_t VT_ATOM = 24576;     // 192 rows x 128 B: one k-atom (64 keys) of the V^T image
@@ -496,7 +496,7 @@ static_assert(128 * 720 <= 6 * ATOM_A, "store staging size");
 // (group g: fp32 columns [64 g, 64 g + 64) -> packed columns [64 g, 64 g + 32)) and is the A operand of fc2 straight from TMEM.
 constexpr uint32_t TC_F1A = 0, TC_F1B = 128;
 constexpr uint32_t TC_F2 = 256;                // fc2 accumulator, 192 cols
-enum { MB_FULL = 0, MB_EMPTY = 3, MB_XA = 6, MB_F1A = 7, MB_F1B = 8, MB_HR0 = 9, MB_HR1 = 10, MB_HR2 = 11, MB_F2 = 12, MB_COUNT = 13 };
+enum { MB_FULL = 0, MB_EMPTY = 3, MB_XA = 6, MB_F1A = 7, MB_F1B = 8, MB_HR0 = 9, MB_HR1 = 10, MB_HR2 = 11, MB_F2 = 12, MB_XAFREE = 13, MB_COUNT = 14 };
 
 __global__ void __launch_bounds__(NTHREADS, 1) swin_mlp_kernel(const MlpParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -511,7 +511,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_mlp_kernel(const MlpParams p
     for (int i = threadIdx.x; i < SRK_MLP_VEC_FLOATS; i += blockDim.x) s_vec[i] = p.vec[i];
     if (threadIdx.x == 0) {
         for (int i = 0; i < RING_N; ++i) { mbar_init(&bars[MB_FULL + i], 1); mbar_init(&bars[MB_EMPTY + i], 1); }
-        mbar_init(&bars[MB_XA], NROWTHREADS);  mbar_init(&bars[MB_F1A], 1);           mbar_init(&bars[MB_F1B], 1);
+        mbar_init(&bars[MB_XA], 128);          mbar_init(&bars[MB_F1A], 1);           mbar_init(&bars[MB_F1B], 1);
+        mbar_init(&bars[MB_XAFREE], 1);
         mbar_init(&bars[MB_HR0], NROWTHREADS); mbar_init(&bars[MB_HR1], NROWTHREADS); mbar_init(&bars[MB_HR2], NROWTHREADS);
         mbar_init(&bars[MB_F2], 1);
         fence_barrier_init();
@@ -582,6 +583,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_mlp_kernel(const MlpParams p
                 tc_fence_after();
                 fc2_chunk(b0, true);
                 fc1_chunk();                                                   // chunk 2 -> buffer b0 (after fc2 consumed H of chunk 0)
+                umma_commit(&bars[MB_XAFREE]);                                 // all fc1 GEMMs issued: the x image is free once they complete
                 mbar_wait(&bars[MB_HR1], ph_hr[1]); ph_hr[1] ^= 1;
                 tc_fence_after();
                 fc2_chunk(b0 ^ 1, false);
@@ -592,22 +594,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_mlp_kernel(const MlpParams p
             }
         }
         __syncwarp();
-    } else {
-        const int cw8 = warp - 2, g = cw8 >> 2, q = warp & 3, row = q * 32 + lane;
-        const uint32_t lanebase = static_cast<uint32_t>(q * 32) << 16;
+    } else if (warp >= 10) {
+        // ===================================================== 4 LayerNorm warps: one tile ahead of the GEMMs.  The next tile's rows are
+        // loaded and normalised into registers while fc1 still reads the x image, then dumped into it (rowops.cuh)
+        const int lw = warp - 10;
         const uint32_t xa = sbase + M_XA;
-        uint32_t ph_f1[2] = {0, 0}, ph_f2 = 0, nchunk = 0;
-        auto ln_tile = [&](int tile) {
+        uint32_t ph_free = 0;
+        // the first tile is normalised by the 8 row warps (twice the loads in flight at kernel start); these warps start on the second
+        for (int tile = blockIdx.x + gridDim.x; tile < p.n_tiles; tile += gridDim.x) {
             auto tok_of_row = [&](int r) -> int64_t {
                 const int64_t tk = static_cast<int64_t>(tile) * 128 + r;
                 return tk < p.num_tokens ? tk : static_cast<int64_t>(-1);
             };
-            ln_rows_to_image(p.x, p.ld_in, p.apply_ln, xa, cw8, lane, tok_of_row);
+            uint2 h0[4][3], h1[4][3], h2[4][3], h3[4][3];
+            ln_rows_hold<4>(p.x, p.ld_in, p.apply_ln, 32 * lw, lane, tok_of_row, h0);
+            ln_rows_hold<4>(p.x, p.ld_in, p.apply_ln, 32 * lw + 8, lane, tok_of_row, h1);
+            ln_rows_hold<4>(p.x, p.ld_in, p.apply_ln, 32 * lw + 16, lane, tok_of_row, h2);
+            ln_rows_hold<4>(p.x, p.ld_in, p.apply_ln, 32 * lw + 24, lane, tok_of_row, h3);
+            mbar_wait(&bars[MB_XAFREE], ph_free); ph_free ^= 1;        // the previous tile's fc1 GEMMs have read the x image
+            ln_rows_dump<4>(xa, 32 * lw, lane, h0);
+            ln_rows_dump<4>(xa, 32 * lw + 8, lane, h1);
+            ln_rows_dump<4>(xa, 32 * lw + 16, lane, h2);
+            ln_rows_dump<4>(xa, 32 * lw + 24, lane, h3);
             fence_proxy_async_smem();
             mbar_arrive(&bars[MB_XA]);
-        };
+        }
+    } else {
+        const int cw8 = warp - 2, g = cw8 >> 2, q = warp & 3, row = q * 32 + lane;
+        const uint32_t lanebase = static_cast<uint32_t>(q * 32) << 16;
+        uint32_t ph_f1[2] = {0, 0}, ph_f2 = 0, nchunk = 0;
         stagger_start(p.stagger);
-        if (static_cast<int>(blockIdx.x) < p.n_tiles) ln_tile(blockIdx.x);
+        if (static_cast<int>(blockIdx.x) < p.n_tiles) {         // first tile: all 8 row warps normalise it (see the LayerNorm warps)
+            const int tile = blockIdx.x;
+            auto tok_of_row = [&](int r) -> int64_t {
+                const int64_t tk = static_cast<int64_t>(tile) * 128 + r;
+                return tk < p.num_tokens ? tk : static_cast<int64_t>(-1);
+            };
+            ln_rows_to_image(p.x, p.ld_in, p.apply_ln, sbase + M_XA, cw8, lane, tok_of_row);
+            fence_proxy_async_smem();
+            named_bar_sync(1, NROWTHREADS);
+            if (g == 0) mbar_arrive(&bars[MB_XA]);
+        }
         int it = 0;
         unsigned long long* dbg = threadIdx.x == 64 ? p.dbg : nullptr;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
@@ -651,8 +678,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_mlp_kernel(const MlpParams p
                 mbar_arrive(&bars[MB_HR0 + c]);
                 SRK_TL(dbg, it, 2 + 2 * c);
             }
-            // ---- the x image is free (all fc1 GEMMs of this tile are complete): normalise the next tile while fc2 runs
-            if (tile + static_cast<int>(gridDim.x) < p.n_tiles) ln_tile(tile + gridDim.x);
             SRK_TL(dbg, it, 7);
             // ---- fc2 accumulators + b2 -> staged rows (private staging) -> bulk (reduce-add) store, drained asynchronously
             mbar_wait(&bars[MB_F2], ph_f2); ph_f2 ^= 1;
@@ -665,6 +690,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_mlp_kernel(const MlpParams p
             tc_fence_before();
             SRK_TL(dbg, it, 9);
         }
+        bulk_wait_read0();          // shared memory must outlive the bulk copies that read it
     }
     tc_fence_before();
     __syncthreads();
