@@ -152,6 +152,12 @@ int srk_window_attention_table_floats(int32_t kind);
 int srk_layernorm_fwd(const float* x, float* y, const float* w, const float* b, int64_t num_tokens, int32_t ld_in,
                       int32_t ld_out, void* stream);
 
+/* HAT CAB tail: out[b, t, c] += scale * y[b, t, c] * sigmoid(W2 relu(W1 mean_t(y[b, :, c]) + b1) + b2)[c] on channels-last
+ * (batch, tokens_per_image, 180) fp32 tensors -- ChannelAttention (hat_arch.py:41-59) fused with `+ conv_x * conv_scale`
+ * (hat_arch.py:307).  w1 (hidden, 180), w2 (180, hidden), hidden <= 32; sums_ws: batch * 180 floats of scratch. */
+int srk_cab_gate_add(const float* y, float* out, float* sums_ws, const float* w1, const float* b1, const float* w2, const float* b2,
+                     int32_t hidden, float scale, int32_t batch, int32_t tokens_per_image, void* stream);
+
 /* PixelShuffle(r) on channels-last activations, optional fused LeakyReLU:
  * out[b, h*r+i, w*r+j, c] = in[b, h, w, c*r*r + i*r + j].  Replaces nn.PixelShuffle in Upsample
  * (network_swinir.py:580-588). */

@@ -93,6 +93,7 @@ def load():
     lib.srk_window_attention_fwd.argtypes = [POINTER(WinAttnDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_void_p]
     lib.srk_window_attention_table_floats.argtypes = [c_int32]
+    lib.srk_cab_gate_add.argtypes = [c_void_p] * 7 + [c_int32, ctypes.c_float, c_int32, c_int32, c_void_p]
     lib.srk_debug_set_timeline.argtypes = [c_void_p]
     lib.srk_debug_set_timeline.restype = None
     lib.srk_debug_set_stagger.argtypes = [c_int32, c_int32]
@@ -101,7 +102,7 @@ def load():
     lib.srk_debug_set_winattn_stagger.restype = None
     for f in ("srk_swin_attn_fwd", "srk_swin_mlp_fwd", "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd",
               "srk_stitch_accumulate", "srk_stitch_normalize", "srk_linear_fwd", "srk_window_attention_fwd",
-              "srk_window_attention_table_floats"):
+              "srk_window_attention_table_floats", "srk_cab_gate_add"):
         getattr(lib, f).restype = c_int32
     if lib.srk_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libsrk.so ABI {lib.srk_abi_version()} != expected {ABI_VERSION}; rebuild")
@@ -111,7 +112,8 @@ def load():
 
 EXPORTS = ("srk_abi_version", "srk_last_error_string", "srk_launch_count", "srk_swin_attn_fwd", "srk_swin_mlp_fwd",
            "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd", "srk_stitch_accumulate", "srk_stitch_normalize", "srk_debug_set_timeline", "srk_debug_set_stagger",
-           "srk_linear_fwd", "srk_window_attention_fwd", "srk_window_attention_table_floats", "srk_debug_set_winattn_stagger")
+           "srk_linear_fwd", "srk_window_attention_fwd", "srk_window_attention_table_floats", "srk_debug_set_winattn_stagger",
+           "srk_cab_gate_add")
 
 
 def _check(rc: int, lib) -> None:
@@ -222,3 +224,13 @@ def window_attention(q_planes, k_planes, v_planes, table, out, *, kind, batch, h
         _check(lib.srk_window_attention_fwd(ctypes.byref(d), q_planes.data_ptr(), k_planes.data_ptr(), v_planes.data_ptr(),
                                             table.data_ptr(), 0 if emask is None else emask.data_ptr(),
                                             zero_page(out.device).data_ptr(), out.data_ptr(), _stream()), lib)
+
+
+def cab_gate_add(y, out, w1, b1, w2, b2, *, scale, batch, tokens_per_image) -> None:
+    """srk_cab_gate_add: out += scale * y * squeeze_excite_gate(y) on channels-last (batch, tokens, 180) fp32 tensors."""
+    lib = load()
+    _require_cuda_f32(y, out, w1, b1, w2, b2)
+    ws = torch.empty(batch * DIM, dtype=torch.float32, device=y.device)
+    with _timed("cab_gate_add"):
+        _check(lib.srk_cab_gate_add(y.data_ptr(), out.data_ptr(), ws.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+                                    b2.data_ptr(), w1.shape[0], float(scale), batch, tokens_per_image, _stream()), lib)

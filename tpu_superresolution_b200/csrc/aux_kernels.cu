@@ -169,4 +169,76 @@ cudaError_t launch_stitch_normalize(float* E, const float* Wt, int channels, int
     return cudaGetLastError();
 }
 
+// ---- HAT CAB tail (hat_arch.py:41-59 ChannelAttention + :307 `+ conv_x * conv_scale`):
+//      out[b, t, c] += scale * y[b, t, c] * sigmoid(W2 relu(W1 mean_t(y[b, :, c]) + b1) + b2)[c]
+// y is the CAB's second convolution output in channels-last memory (B, H*W, 180).  Two streaming passes over y (L2 resident):
+// (1) per-(image, channel) sums; (2) the 180 -> hidden -> 180 squeeze-excite gate (recomputed by every block: 2 x 180 x hidden
+// MACs) fused with the scaled residual add.  Replaces five torch launches (mean, two 1x1 convs, ReLU / sigmoid, addcmul).
+constexpr int CAB_TOK_PER_BLOCK = 64;
+__global__ void __launch_bounds__(192) cab_pool_kernel(const float* __restrict__ y, float* __restrict__ sums, int tokens_per_image) {
+    const int b = blockIdx.y, c = threadIdx.x;
+    const int t0 = blockIdx.x * CAB_TOK_PER_BLOCK;
+    const int t1 = min(t0 + CAB_TOK_PER_BLOCK, tokens_per_image);
+    if (c >= SRK_DIM) return;
+    const float* src = y + (static_cast<int64_t>(b) * tokens_per_image + t0) * SRK_DIM + c;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int t = t0;
+    for (; t + 4 <= t1; t += 4, src += 4 * SRK_DIM) {
+        s0 += __ldg(src); s1 += __ldg(src + SRK_DIM); s2 += __ldg(src + 2 * SRK_DIM); s3 += __ldg(src + 3 * SRK_DIM);
+    }
+    for (; t < t1; ++t, src += SRK_DIM) s0 += __ldg(src);
+    atomicAdd(sums + b * SRK_DIM + c, (s0 + s1) + (s2 + s3));
+}
+
+__global__ void __launch_bounds__(256) cab_gate_add_kernel(const float* __restrict__ y, float* __restrict__ out,
+                                                           const float* __restrict__ sums, const float* __restrict__ w1,
+                                                           const float* __restrict__ b1, const float* __restrict__ w2,
+                                                           const float* __restrict__ b2, int hidden, float scale,
+                                                           int tokens_per_image) {
+    __shared__ float s_mean[SRK_DIM], s_hid[32];
+    __shared__ __align__(16) float s_gate[SRK_DIM];
+    const int b = blockIdx.y;
+    for (int c = threadIdx.x; c < SRK_DIM; c += blockDim.x) s_mean[c] = sums[b * SRK_DIM + c] / static_cast<float>(tokens_per_image);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int j = warp; j < hidden; j += 8) {                 // hidden unit j: one warp, lanes stride over the 180 inputs
+        float a = 0.f;
+        for (int c = lane; c < SRK_DIM; c += 32) a = fmaf(w1[j * SRK_DIM + c], s_mean[c], a);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) s_hid[j] = fmaxf(a + b1[j], 0.f);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < SRK_DIM; c += blockDim.x) {
+        float a = b2[c];
+        for (int j = 0; j < hidden; ++j) a = fmaf(w2[c * hidden + j], s_hid[j], a);
+        s_gate[c] = scale / (1.0f + __expf(-a));
+    }
+    __syncthreads();
+    // 64 tokens x 45 float4 per block
+    const int t0 = blockIdx.x * CAB_TOK_PER_BLOCK;
+    const int nt = min(CAB_TOK_PER_BLOCK, tokens_per_image - t0);
+    const int64_t base = (static_cast<int64_t>(b) * tokens_per_image + t0) * (SRK_DIM / 4);
+    const float4* ys = reinterpret_cast<const float4*>(y) + base;
+    float4* os = reinterpret_cast<float4*>(out) + base;
+    const float4* gs = reinterpret_cast<const float4*>(s_gate);
+    for (int i = threadIdx.x; i < nt * (SRK_DIM / 4); i += blockDim.x) {
+        const float4 g = gs[i % (SRK_DIM / 4)], v = __ldg(ys + i);
+        float4 o = os[i];
+        o.x = fmaf(v.x, g.x, o.x); o.y = fmaf(v.y, g.y, o.y); o.z = fmaf(v.z, g.z, o.z); o.w = fmaf(v.w, g.w, o.w);
+        os[i] = o;
+    }
+}
+
+cudaError_t launch_cab_gate_add(const float* y, float* out, float* sums, const float* w1, const float* b1, const float* w2,
+                                const float* b2, int hidden, float scale, int batch, int tokens_per_image, cudaStream_t stream) {
+    if (batch <= 0 || tokens_per_image <= 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(sums, 0, static_cast<size_t>(batch) * SRK_DIM * sizeof(float), stream);
+    if (e != cudaSuccess) return e;
+    dim3 grid((tokens_per_image + CAB_TOK_PER_BLOCK - 1) / CAB_TOK_PER_BLOCK, batch);
+    cab_pool_kernel<<<grid, 192, 0, stream>>>(y, sums, tokens_per_image);
+    cab_gate_add_kernel<<<grid, 256, 0, stream>>>(y, out, sums, w1, b1, w2, b2, hidden, scale, tokens_per_image);
+    return cudaGetLastError();
+}
+
 }  // namespace srk

@@ -90,6 +90,8 @@ cudaError_t launch_pixelshuffle_nhwc(const float* x, float* y, int batch, int he
                                      cudaStream_t stream);
 cudaError_t launch_stitch_accumulate(const float* tiles, float* E, float* Wt, const int32_t* tile_yx, int num_tiles,
                                      int channels, int tile_h, int tile_w, int out_h, int out_w, cudaStream_t stream);
+cudaError_t launch_cab_gate_add(const float* y, float* out, float* sums, const float* w1, const float* b1, const float* w2,
+                                const float* b2, int hidden, float scale, int batch, int tokens_per_image, cudaStream_t stream);
 cudaError_t launch_stitch_normalize(float* E, const float* Wt, int channels, int64_t pixels, cudaStream_t stream);
 
 }  // namespace srk

@@ -498,7 +498,10 @@ constexpr uint32_t TC_F1A = 0, TC_F1B = 128;
 constexpr uint32_t TC_F2 = 256;                // fc2 accumulator, 192 cols
 enum { MB_FULL = 0, MB_EMPTY = 3, MB_XA = 6, MB_F1A = 7, MB_F1B = 8, MB_HR0 = 9, MB_HR1 = 10, MB_HR2 = 11, MB_F2 = 12, MB_XAFREE = 13, MB_COUNT = 14 };
 
-__global__ void __launch_bounds__(NTHREADS, 1) swin_mlp_kernel(const MlpParams p) {
+// LNW = true: 448 threads, 4 dedicated LayerNorm warps run one tile ahead (pays off from ~3 tiles per CTA); LNW = false: 320
+// threads, the 8 row warps normalise the next tile while fc2 runs (more registers for the row path, better for 1-2 tiles per CTA).
+template <bool LNW>
+__global__ void __launch_bounds__(LNW ? NTHREADS : 320, 1) swin_mlp_kernel(const MlpParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t sbase = (raw + 1023u) & ~1023u;
@@ -594,7 +597,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_mlp_kernel(const MlpParams p
             }
         }
         __syncwarp();
-    } else if (warp >= 10) {
+    } else if (LNW && warp >= 10) {
         // ===================================================== 4 LayerNorm warps: one tile ahead of the GEMMs.  The next tile's rows are
         // loaded and normalised into registers while fc1 still reads the x image, then dumped into it (rowops.cuh)
         const int lw = warp - 10;
@@ -679,6 +682,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) swin_mlp_kernel(const MlpParams p
                 SRK_TL(dbg, it, 2 + 2 * c);
             }
             SRK_TL(dbg, it, 7);
+            if (!LNW && tile + static_cast<int>(gridDim.x) < p.n_tiles) {
+                // ---- the x image is free (all fc1 GEMMs of this tile are complete): normalise the next tile while fc2 runs
+                const int nt = tile + gridDim.x;
+                auto tok_next = [&](int r) -> int64_t {
+                    const int64_t tk = static_cast<int64_t>(nt) * 128 + r;
+                    return tk < p.num_tokens ? tk : static_cast<int64_t>(-1);
+                };
+                ln_rows_to_image(p.x, p.ld_in, p.apply_ln, sbase + M_XA, cw8, lane, tok_next);
+                fence_proxy_async_smem();
+                named_bar_sync(1, NROWTHREADS);
+                if (g == 0) mbar_arrive(&bars[MB_XA]);
+            }
             // ---- fc2 accumulators + b2 -> staged rows (private staging) -> bulk (reduce-add) store, drained asynchronously
             mbar_wait(&bars[MB_F2], ph_f2); ph_f2 ^= 1;
             tc_fence_after();
@@ -726,12 +741,14 @@ cudaError_t launch_swin_attn(const AttnParams& p, cudaStream_t stream) {
 cudaError_t launch_swin_mlp(const MlpParams& p, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(swin_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(swin_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(swin_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     const int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
-    swin_mlp_kernel<<<grid, NTHREADS, K2_SMEM, stream>>>(p);
+    if (p.n_tiles > 2 * grid) swin_mlp_kernel<true><<<grid, NTHREADS, K2_SMEM, stream>>>(p);
+    else                      swin_mlp_kernel<false><<<grid, 320, K2_SMEM, stream>>>(p);
     return cudaGetLastError();
 }
 

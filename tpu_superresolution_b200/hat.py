@@ -9,7 +9,8 @@ What runs where (per HAB, hat_arch.py:267-310)
   * LN1 + qkv Linear                      -> srk_linear_fwd          (tcgen05, q/k/v head-pair planes in bf16)
   * roll + partition + softmax(qk^T+rpb+mask)v + reverse + un-roll -> srk_window_attention_fwd (tcgen05, kind HAT_WMSA)
   * proj Linear + shortcut                -> srk_linear_fwd          (bulk reduce-add into the residual stream)
-  * CAB conv branch on LN1(x)             -> srk_layernorm_fwd + cuDNN 3x3 convs (library) + squeeze-excite gate in torch
+  * CAB conv branch on LN1(x)             -> srk_layernorm_fwd + cuDNN 3x3 convs (library) + srk_cab_gate_add (squeeze-excite
+                                             gate fused with the `+ conv_x * conv_scale` residual update)
   * LN2 + Mlp + shortcut                  -> srk_swin_mlp_fwd
 OCAB (hat_arch.py:393-439): the same three kernels with kind HAT_OCAB -- the nn.Unfold(24, stride 16, pad 4) of k, v is the
 source addressing of the key-window copies.
@@ -88,10 +89,9 @@ class CAB(nn.Module):
     def forward(self, x):
         return self.cab(x)
 
-    def body_and_gate(self, x):
-        """-> (conv output y (B,C,H,W), sigmoid gate (B,C,1,1)); forward(x) == y * gate."""
-        y = self.cab[2](self.cab[1](self.cab[0](x)))
-        return y, self.cab[3].gate(y)
+    def body(self, x):
+        """conv3x3 -> GELU -> conv3x3 (cuDNN); the channel attention that follows is fused into srk_cab_gate_add by HAB."""
+        return self.cab[2](self.cab[1](self.cab[0](x)))
 
 
 class WindowAttention(nn.Module):
@@ -213,7 +213,7 @@ class HAB(nn.Module):
         # conv branch on the un-shifted LN1 output (:276-278)
         xn = torch.empty_like(x)
         L.layernorm(x, xn, self.norm1.weight, self.norm1.bias, num_tokens=tokens, ld_in=C, ld_out=C)
-        y, gate = self.conv_block.body_and_gate(xn.view(B, H, W, C).permute(0, 3, 1, 2))     # channels-last views
+        y = self.conv_block.body(xn.view(B, H, W, C).permute(0, 3, 1, 2))                    # channels-last views
         # attention branch (reads x before `out` is touched)
         src = x
         mw, mv = self.mlp._packed(self.norm2)
@@ -228,8 +228,10 @@ class HAB(nn.Module):
             out.copy_(x)
         L.linear(o, pw, pb, out, num_tokens=tokens, a_mode=L.LIN_A_PLANES, n_chunks=1, out_mode=L.LIN_OUT_ROWS, ld_out=C,
                  add_residual=True)                                                           # out = shortcut + attn
-        y_tok = y.permute(0, 2, 3, 1).reshape(B, Ltok, C)                                     # a view when y is channels-last
-        out.addcmul_(y_tok, gate.reshape(B, 1, C), value=self.conv_scale)                     # + conv_x * conv_scale (:307)
+        y_tok = y.permute(0, 2, 3, 1).reshape(B, Ltok, C).contiguous()                        # a view when y is channels-last
+        ca = self.conv_block.cab[3].attention                                                 # squeeze-excite gate + `+ conv_x * conv_scale` (:307)
+        L.cab_gate_add(y_tok, out, ca[1].weight.reshape(ca[1].weight.shape[0], C), ca[1].bias, ca[3].weight.reshape(C, -1), ca[3].bias,
+                       scale=self.conv_scale, batch=B, tokens_per_image=Ltok)
         L.swin_mlp(out, out, mw, mv, num_tokens=tokens, ld_in=C, ld_out=C, apply_ln=True, add_residual=True)
         return out
 
