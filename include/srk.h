@@ -178,7 +178,7 @@ int64_t srk_launch_count(void);
 void srk_debug_set_timeline(void* device_buf);
 /* tuning: start skew (cycles per CTA index mod 4) of the attention / MLP kernels, see stagger_start() */
 void srk_debug_set_stagger(int attn_cycles, int mlp_cycles);
-/* tuning: cycles the second query-half group of srk_window_attention_fwd starts behind the first (default 4000) */
+/* tuning: cycles the second query-half group of srk_window_attention_fwd starts behind the first (default 1500) */
 void srk_debug_set_winattn_stagger(int cycles);
 
 #ifdef __cplusplus
