@@ -288,13 +288,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
                 mbar_wait(&bars[B_DRAIN], ph_drain); ph_drain ^= 1;
             }
             first_tile = false;
-            // The next tile's rows are gathered and normalised into registers in four batches of 8 rows per warp, one after each of
-            // the first four q|k epilogues (rowops.cuh: ln_rows_hold), and dumped into the x image once the last q|k GEMM has read
-            // it -- the global-memory latency of the next tile is paid while the softmaxes of this one run.
-            const bool has_next = tile + static_cast<int>(gridDim.x) < p.n_tiles;
-            uint2 held[4][4][3];
-            if (has_next) set_tile_geom(p, tile + gridDim.x, geo);
-#pragma unroll
+#pragma unroll 1
             for (int h = 0; h < 6; ++h) {
                 // ---- q,k accumulators of head h -> [q_h | k_h] image (h & 1).  The k bias is dropped: it shifts every
                 //      logit of a row by the same amount, which the softmax cancels.
@@ -303,28 +297,20 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
                 SRK_TL(udbg, uit, 50 + h);
                 const uint32_t img = qki + (h & 1) * ATOM_A;
                 const uint32_t acc = tmem + lanebase + ((h & 1) ? TC_QK1 : TC_QK0);
-                {
-                    uint32_t v[32];
-                    tmem_ld32(acc, v);
-                    tmem_ld_wait();
-                    store_row_chunks<true, false>(img, row, 0, v, s_vec + SRK_AV_BIAS_Q + 32 * h, 1.0f);
-                    tmem_ld32(acc + 32, v);
-                    tmem_ld_wait();
-                    store_row_chunks<false, false>(img, row, 4, v, nullptr, 1.0f);
-                }
+                uint32_t v[32];
+                tmem_ld32(acc, v);
+                tmem_ld_wait();
+                store_row_chunks<true, false>(img, row, 0, v, s_vec + SRK_AV_BIAS_Q + 32 * h, 1.0f);
+                tmem_ld32(acc + 32, v);
+                tmem_ld_wait();
+                store_row_chunks<false, false>(img, row, 4, v, nullptr, 1.0f);
                 tc_fence_before();
                 fence_proxy_async_smem();
                 mbar_arrive(&bars[B_QKR0 + (h & 1)]);
                 SRK_TL(udbg, uit, 56 + h);
-                if (h < 4 && has_next) ln_rows_hold<4>(p.x, p.ld_in, p.apply_ln, 32 * cwu + 8 * h, lane, tok_of_row, held[h]);
             }
-            // ---- the q|k GEMM of head 5 is complete, so nothing reads the x image any more: dump the next tile's rows into it
-            if (has_next) {
-#pragma unroll
-                for (int h = 0; h < 4; ++h) ln_rows_dump<4>(xa, 32 * cwu + 8 * h, lane, held[h]);
-                fence_proxy_async_smem();
-                mbar_arrive(&bars[B_XA]);
-            }
+            // ---- the q|k GEMM of head 5 is complete, so nothing reads the x image any more: build the next tile's
+            if (tile + static_cast<int>(gridDim.x) < p.n_tiles) ln_tile(tile + gridDim.x);
             SRK_TL(udbg, uit, 62);
             ++uit;
         }
