@@ -158,6 +158,28 @@ int srk_layernorm_fwd(const float* x, float* y, const float* w, const float* b, 
 int srk_cab_gate_add(const float* y, float* out, float* sums_ws, const float* w1, const float* b1, const float* w2, const float* b2,
                      int32_t hidden, float scale, int32_t batch, int32_t tokens_per_image, void* stream);
 
+/* ---- DAT glue on fp32 channels-last token rows (dat_arch.py) ------------------------------------------------------------
+ * Depthwise 3x3 convolution (zero padding) over (batch, height, width) token rows: channel slice [c_in, c_in + channels) of rows
+ * of ld_in floats, weights w9c[9][channels] (tap major), out = act((conv) * scale + shift) [* gate slice].  With ln_stats the
+ * input rows are LayerNorm-ed first ((x - mean) * rstd * ln_gamma + ln_beta, stats from srk_row_stats_fwd; zero padding applies
+ * to the normalised tensor).  Replaces dwconv + BatchNorm + GELU (dat_arch.py:300-304, :418, :508) and SpatialGate (:38-54). */
+int srk_dwconv3x3_rows_fwd(const float* in, int32_t ld_in, int32_t c_in, const float* w9c, const float* scale, const float* shift,
+                           const float* ln_stats, const float* ln_gamma, const float* ln_beta, const float* gate, int32_t ld_gate,
+                           int32_t c_gate, float* out, int32_t ld_out, int32_t channels, int32_t batch, int32_t height, int32_t width,
+                           int32_t act_gelu, void* stream);
+/* stats[tok] = (mean, rstd) over the channel slice (nn.LayerNorm statistics, biased variance). */
+int srk_row_stats_fwd(const float* in, int32_t ld_in, int32_t c_in, int32_t channels, int64_t tokens, float eps, float* stats, void* stream);
+/* Adaptive interaction module (dat_arch.py:420-433 mode 0, :510-523 mode 1) on (tokens, 180) rows: s = w2 . gelu(W1 src + b1) + b2
+ * with src = att (mode 0) / conv (mode 1), W1 (hidden <= 16, 180) with its BatchNorm folded; cmap (batch, 180) = channel map
+ * before the sigmoid.  mode 0: mix = att * sigmoid(cmap) + sigmoid(s) * conv;  mode 1: mix = att * sigmoid(s) + conv * sigmoid(cmap). */
+int srk_dat_mix_fwd(const float* att, const float* conv, const float* cmap, const float* w1, const float* b1, const float* w2, float b2,
+                    int32_t hidden, int32_t mode, float* mix, int64_t tokens, int32_t tokens_per_image, void* stream);
+/* Channel attention (dat_arch.py:497-505) on qkv rows (batch * tokens_per_image, 540) = q | k | v:
+ * gram[b][h] = 900 products sum_n q[n, d1] k[n, d2], then 30 sums of q^2, then 30 sums of k^2 (960 floats per image and head);
+ * apply: out[tok, h*30 + d1] = sum_d2 attn[b, h, d1, d2] v[tok, h*30 + d2], attn (batch, 6, 30, 30). */
+int srk_dat_channel_gram_fwd(const float* qkv, float* gram, int32_t batch, int32_t tokens_per_image, void* stream);
+int srk_dat_channel_apply_fwd(const float* qkv, const float* attn, float* out, int32_t batch, int32_t tokens_per_image, void* stream);
+
 /* PixelShuffle(r) on channels-last activations, optional fused LeakyReLU:
  * out[b, h*r+i, w*r+j, c] = in[b, h, w, c*r*r + i*r + j].  Replaces nn.PixelShuffle in Upsample
  * (network_swinir.py:580-588). */

@@ -93,6 +93,13 @@ def load():
     lib.srk_window_attention_fwd.argtypes = [POINTER(WinAttnDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_void_p]
     lib.srk_window_attention_table_floats.argtypes = [c_int32]
+    f32 = ctypes.c_float
+    lib.srk_dwconv3x3_rows_fwd.argtypes = [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
+    lib.srk_row_stats_fwd.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int64, f32, c_void_p, c_void_p]
+    lib.srk_dat_mix_fwd.argtypes = [c_void_p] * 6 + [f32, c_int32, c_int32, c_void_p, c_int64, c_int32, c_void_p]
+    lib.srk_dat_channel_gram_fwd.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_void_p]
+    lib.srk_dat_channel_apply_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]
     lib.srk_cab_gate_add.argtypes = [c_void_p] * 7 + [c_int32, ctypes.c_float, c_int32, c_int32, c_void_p]
     lib.srk_debug_set_timeline.argtypes = [c_void_p]
     lib.srk_debug_set_timeline.restype = None
@@ -102,7 +109,8 @@ def load():
     lib.srk_debug_set_winattn_stagger.restype = None
     for f in ("srk_swin_attn_fwd", "srk_swin_mlp_fwd", "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd",
               "srk_stitch_accumulate", "srk_stitch_normalize", "srk_linear_fwd", "srk_window_attention_fwd",
-              "srk_window_attention_table_floats", "srk_cab_gate_add"):
+              "srk_window_attention_table_floats", "srk_cab_gate_add", "srk_dwconv3x3_rows_fwd", "srk_row_stats_fwd", "srk_dat_mix_fwd",
+              "srk_dat_channel_gram_fwd", "srk_dat_channel_apply_fwd"):
         getattr(lib, f).restype = c_int32
     if lib.srk_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libsrk.so ABI {lib.srk_abi_version()} != expected {ABI_VERSION}; rebuild")
@@ -113,7 +121,8 @@ def load():
 EXPORTS = ("srk_abi_version", "srk_last_error_string", "srk_launch_count", "srk_swin_attn_fwd", "srk_swin_mlp_fwd",
            "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd", "srk_stitch_accumulate", "srk_stitch_normalize", "srk_debug_set_timeline", "srk_debug_set_stagger",
            "srk_linear_fwd", "srk_window_attention_fwd", "srk_window_attention_table_floats", "srk_debug_set_winattn_stagger",
-           "srk_cab_gate_add")
+           "srk_cab_gate_add", "srk_dwconv3x3_rows_fwd", "srk_row_stats_fwd", "srk_dat_mix_fwd", "srk_dat_channel_gram_fwd",
+           "srk_dat_channel_apply_fwd")
 
 
 def _check(rc: int, lib) -> None:
@@ -234,3 +243,47 @@ def cab_gate_add(y, out, w1, b1, w2, b2, *, scale, batch, tokens_per_image) -> N
     with _timed("cab_gate_add"):
         _check(lib.srk_cab_gate_add(y.data_ptr(), out.data_ptr(), ws.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
                                     b2.data_ptr(), w1.shape[0], float(scale), batch, tokens_per_image, _stream()), lib)
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def dwconv3x3_rows(inp, w9c, scale, shift, out, *, ld_in, c_in, ld_out, channels, batch, height, width, act_gelu=False, ln_stats=None,
+                   ln_gamma=None, ln_beta=None, gate=None, ld_gate=0, c_gate=0) -> None:
+    """srk_dwconv3x3_rows_fwd on fp32 token rows (see include/srk.h)."""
+    lib = load()
+    _require_cuda_f32(inp, w9c, scale, shift, out, ln_stats, ln_gamma, ln_beta, gate)
+    with _timed("dwconv3x3_rows"):
+        _check(lib.srk_dwconv3x3_rows_fwd(inp.data_ptr(), ld_in, c_in, w9c.data_ptr(), scale.data_ptr(), shift.data_ptr(), _ptr(ln_stats),
+                                          _ptr(ln_gamma), _ptr(ln_beta), _ptr(gate), ld_gate, c_gate, out.data_ptr(), ld_out, channels, batch,
+                                          height, width, int(act_gelu), _stream()), lib)
+
+
+def row_stats(inp, stats, *, ld_in, c_in, channels, tokens, eps) -> None:
+    lib = load()
+    _require_cuda_f32(inp, stats)
+    with _timed("row_stats"):
+        _check(lib.srk_row_stats_fwd(inp.data_ptr(), ld_in, c_in, channels, tokens, float(eps), stats.data_ptr(), _stream()), lib)
+
+
+def dat_mix(att, conv, cmap, w1, b1, w2, b2, mix, *, mode, tokens, tokens_per_image) -> None:
+    lib = load()
+    _require_cuda_f32(att, conv, cmap, w1, b1, w2, mix)
+    with _timed("dat_mix"):
+        _check(lib.srk_dat_mix_fwd(att.data_ptr(), conv.data_ptr(), cmap.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), float(b2),
+                                   w1.shape[0], mode, mix.data_ptr(), tokens, tokens_per_image, _stream()), lib)
+
+
+def dat_channel_gram(qkv, gram, *, batch, tokens_per_image) -> None:
+    lib = load()
+    _require_cuda_f32(qkv, gram)
+    with _timed("dat_channel_gram"):
+        _check(lib.srk_dat_channel_gram_fwd(qkv.data_ptr(), gram.data_ptr(), batch, tokens_per_image, _stream()), lib)
+
+
+def dat_channel_apply(qkv, attn, out, *, batch, tokens_per_image) -> None:
+    lib = load()
+    _require_cuda_f32(qkv, attn, out)
+    with _timed("dat_channel_apply"):
+        _check(lib.srk_dat_channel_apply_fwd(qkv.data_ptr(), attn.data_ptr(), out.data_ptr(), batch, tokens_per_image, _stream()), lib)

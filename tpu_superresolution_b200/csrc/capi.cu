@@ -218,6 +218,53 @@ int srk_cab_gate_add(const float* y, float* out, float* sums_ws, const float* w1
     return check(e, "srk_cab_gate_add");
 }
 
+int srk_dwconv3x3_rows_fwd(const float* in, int32_t ld_in, int32_t c_in, const float* w9c, const float* scale, const float* shift,
+                           const float* ln_stats, const float* ln_gamma, const float* ln_beta, const float* gate, int32_t ld_gate,
+                           int32_t c_gate, float* out, int32_t ld_out, int32_t channels, int32_t batch, int32_t height, int32_t width,
+                           int32_t act_gelu, void* stream) {
+    if (!in || !w9c || !scale || !shift || !out) return fail("srk_dwconv3x3_rows_fwd: null argument");
+    if (ln_stats && (!ln_gamma || !ln_beta)) return fail("srk_dwconv3x3_rows_fwd: LayerNorm input needs gamma and beta");
+    if (channels <= 0 || (channels & 3) || (ld_in & 3) || (c_in & 3) || (ld_out & 3) || c_in + channels > ld_in || channels > ld_out)
+        return fail("srk_dwconv3x3_rows_fwd: channels / ld / offsets must be multiples of 4 and consistent");
+    if (gate && ((ld_gate & 3) || (c_gate & 3) || c_gate + channels > ld_gate)) return fail("srk_dwconv3x3_rows_fwd: bad gate slice");
+    if (!aligned16(in) || !aligned16(w9c) || !aligned16(scale) || !aligned16(shift) || !aligned16(out) || (gate && !aligned16(gate)) ||
+        (ln_stats && (!aligned16(ln_gamma) || !aligned16(ln_beta))))
+        return fail("srk_dwconv3x3_rows_fwd: pointers must be 16-byte aligned");
+    if (batch < 0 || height <= 0 || width <= 0) return fail("srk_dwconv3x3_rows_fwd: bad shape");
+    return check(srk::launch_dwconv3x3_rows(in, ld_in, c_in, w9c, scale, shift, ln_stats, ln_gamma, ln_beta, gate, ld_gate, c_gate, out,
+                                            ld_out, channels, batch, height, width, act_gelu, static_cast<cudaStream_t>(stream)),
+                 "srk_dwconv3x3_rows_fwd");
+}
+
+int srk_row_stats_fwd(const float* in, int32_t ld_in, int32_t c_in, int32_t channels, int64_t tokens, float eps, float* stats, void* stream) {
+    if (!in || !stats) return fail("srk_row_stats_fwd: null argument");
+    if (channels <= 0 || (channels & 3) || (ld_in & 3) || (c_in & 3) || c_in + channels > ld_in || !aligned16(in))
+        return fail("srk_row_stats_fwd: channels / ld / offset must be multiples of 4, 16-byte aligned rows");
+    if (tokens < 0) return fail("srk_row_stats_fwd: bad tokens");
+    return check(srk::launch_row_stats(in, ld_in, c_in, channels, tokens, eps, stats, static_cast<cudaStream_t>(stream)), "srk_row_stats_fwd");
+}
+
+int srk_dat_mix_fwd(const float* att, const float* conv, const float* cmap, const float* w1, const float* b1, const float* w2, float b2,
+                    int32_t hidden, int32_t mode, float* mix, int64_t tokens, int32_t tokens_per_image, void* stream) {
+    if (!att || !conv || !cmap || !w1 || !b1 || !w2 || !mix) return fail("srk_dat_mix_fwd: null argument");
+    if (!aligned16(att) || !aligned16(conv) || !aligned16(cmap) || !aligned16(mix)) return fail("srk_dat_mix_fwd: pointers must be 16-byte aligned");
+    if (hidden < 1 || hidden > 16 || (mode != 0 && mode != 1) || tokens < 0 || tokens_per_image <= 0) return fail("srk_dat_mix_fwd: bad arguments");
+    return check(srk::launch_dat_mix(att, conv, cmap, w1, b1, w2, b2, hidden, mode, mix, tokens, tokens_per_image,
+                                     static_cast<cudaStream_t>(stream)), "srk_dat_mix_fwd");
+}
+
+int srk_dat_channel_gram_fwd(const float* qkv, float* gram, int32_t batch, int32_t tokens_per_image, void* stream) {
+    if (!qkv || !gram) return fail("srk_dat_channel_gram_fwd: null argument");
+    if (batch < 0 || batch > 65535 || tokens_per_image <= 0) return fail("srk_dat_channel_gram_fwd: bad shape");
+    return check(srk::launch_channel_gram(qkv, gram, batch, tokens_per_image, static_cast<cudaStream_t>(stream)), "srk_dat_channel_gram_fwd");
+}
+
+int srk_dat_channel_apply_fwd(const float* qkv, const float* attn, float* out, int32_t batch, int32_t tokens_per_image, void* stream) {
+    if (!qkv || !attn || !out) return fail("srk_dat_channel_apply_fwd: null argument");
+    if (batch < 0 || batch > 65535 || tokens_per_image <= 0) return fail("srk_dat_channel_apply_fwd: bad shape");
+    return check(srk::launch_channel_apply(qkv, attn, out, batch, tokens_per_image, static_cast<cudaStream_t>(stream)), "srk_dat_channel_apply_fwd");
+}
+
 int srk_pixelshuffle_nhwc_fwd(const float* x, float* y, int32_t batch, int32_t height, int32_t width, int32_t out_channels,
                               int32_t r, void* stream) {
     if (!x || !y) return fail("srk_pixelshuffle_nhwc_fwd: null argument");

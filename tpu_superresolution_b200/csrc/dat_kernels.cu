@@ -1,0 +1,273 @@
+// HBM / L2-bound kernels of the DAT blocks (dat_arch.py), all on fp32 channels-last token rows [token][ld]:
+//
+//   dwconv3x3_rows_kernel   depthwise 3x3 (zero padding) + per-channel affine (eval BatchNorm folded) + GELU, optionally on
+//                           LayerNorm-ed input rows and multiplied by a gate operand:
+//                             * dwconv + BN + GELU of v     (dat_arch.py:300-304, :418, :508)
+//                             * SpatialGate: x1 * dwconv(LayerNorm(x2))   (dat_arch.py:38-54)
+//   row_stats_kernel        per-token mean / rstd over a channel slice (the SpatialGate LayerNorm statistics)
+//   dat_mix_kernel          adaptive interaction module (dat_arch.py:420-433, :510-523): per-token squeeze MLP 180 -> 11 -> 1
+//                           (BatchNorm folded, exact GELU), sigmoid gates, attention / convolution branch mix
+//   channel_gram_kernel     per (image, head): q^T k over the tokens, squared norms of q, k (dat_arch.py:497-500)
+//   channel_apply_kernel    out[tok, h*30+d1] = sum_d2 A[b, h, d1, d2] v[tok, h*30+d2]      (dat_arch.py:505)
+// 128-bit accesses where the layout allows, grid-stride or one block per token chunk, no tensor cores: these are
+// streaming kernels whose bound is bytes moved.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "kernels.h"
+
+namespace srk {
+
+namespace {
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+}  // namespace
+
+// ---- depthwise 3x3 on token rows.  in: rows of `ld_in` floats, channel slice [c_in, c_in + C); weights w[9][C] (tap major),
+//      out = act((sum_taps w * xin) * scale + shift) [* gate], xin = LayerNorm(in) when stats != nullptr (gamma, beta given).
+__global__ void __launch_bounds__(256) dwconv3x3_rows_kernel(const float* __restrict__ in, int ld_in, int c_in, const float* __restrict__ w,
+                                                             const float* __restrict__ scale, const float* __restrict__ shift,
+                                                             const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, const float* __restrict__ gate, int ld_gate,
+                                                             int c_gate, float* __restrict__ out, int ld_out, int C, int batch, int H,
+                                                             int W, int act_gelu) {
+    const int C4 = C >> 2;
+    const int64_t total = static_cast<int64_t>(batch) * H * W * C4;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int c4 = static_cast<int>(i % C4);
+        const int64_t tok = i / C4;
+        const int x = static_cast<int>(tok % W);
+        const int y = static_cast<int>((tok / W) % H);
+        float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (stats) { g4 = __ldg(reinterpret_cast<const float4*>(gamma) + c4); b4 = __ldg(reinterpret_cast<const float4*>(beta) + c4); }
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int yy = y + dy, xx = x + dx;
+                if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;           // zero padding (of the normalised tensor)
+                const int64_t nt = tok + dy * W + dx;
+                float4 v = __ldg(reinterpret_cast<const float4*>(in + nt * ld_in + c_in) + c4);
+                if (stats) {
+                    const float mu = __ldg(stats + 2 * nt), rs = __ldg(stats + 2 * nt + 1);
+                    v.x = (v.x - mu) * rs * g4.x + b4.x; v.y = (v.y - mu) * rs * g4.y + b4.y;
+                    v.z = (v.z - mu) * rs * g4.z + b4.z; v.w = (v.w - mu) * rs * g4.w + b4.w;
+                }
+                const float4 ww = __ldg(reinterpret_cast<const float4*>(w + ((dy + 1) * 3 + dx + 1) * C) + c4);
+                acc.x = fmaf(ww.x, v.x, acc.x); acc.y = fmaf(ww.y, v.y, acc.y); acc.z = fmaf(ww.z, v.z, acc.z); acc.w = fmaf(ww.w, v.w, acc.w);
+            }
+        }
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + c4), sh = __ldg(reinterpret_cast<const float4*>(shift) + c4);
+        float4 o = make_float4(fmaf(acc.x, sc.x, sh.x), fmaf(acc.y, sc.y, sh.y), fmaf(acc.z, sc.z, sh.z), fmaf(acc.w, sc.w, sh.w));
+        if (act_gelu) { o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w); }
+        if (gate) {
+            const float4 gt = __ldg(reinterpret_cast<const float4*>(gate + tok * ld_gate + c_gate) + c4);
+            o.x *= gt.x; o.y *= gt.y; o.z *= gt.z; o.w *= gt.w;
+        }
+        reinterpret_cast<float4*>(out + tok * ld_out)[c4] = o;
+    }
+}
+
+// ---- LayerNorm statistics of a channel slice: stats[tok] = (mean, rstd); one warp per token
+__global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict__ in, int ld_in, int c_in, int C, int64_t tokens,
+                                                        float eps, float* __restrict__ stats) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    const int C4 = C >> 2;
+    for (int64_t tok = warp; tok < tokens; tok += nwarps) {
+        const float4* src = reinterpret_cast<const float4*>(in + tok * ld_in + c_in);
+        float s = 0.f, q = 0.f;
+        for (int c = lane; c < C4; c += 32) {
+            const float4 v = __ldg(src + c);
+            s += (v.x + v.y) + (v.z + v.w);
+            q = fmaf(v.x, v.x, q); q = fmaf(v.y, v.y, q); q = fmaf(v.z, v.z, q); q = fmaf(v.w, v.w, q);
+        }
+        s = warp_sum(s); q = warp_sum(q);
+        if (lane == 0) {
+            const float mean = s / C;
+            const float var = fmaxf(q / C - mean * mean, 0.f);
+            stats[2 * tok] = mean;
+            stats[2 * tok + 1] = rsqrtf(var + eps);
+        }
+    }
+}
+
+// ---- adaptive interaction module.  s(tok) = w2 . gelu(W1 src(tok) + b1) + b2 with src = att (mode 0) or conv (mode 1);
+//      mode 0 (spatial block, dat_arch.py:420-433): mix = att * sigmoid(cmap[b]) + sigmoid(s) * conv
+//      mode 1 (channel block, dat_arch.py:510-523): mix = att * sigmoid(s) + conv * sigmoid(cmap[b])
+//      One warp per token; W1 (hidden x 180, BatchNorm folded) lives in shared memory.
+constexpr int MIX_MAX_HIDDEN = 16;
+__global__ void __launch_bounds__(256) dat_mix_kernel(const float* __restrict__ att, const float* __restrict__ conv, const float* __restrict__ cmap,
+                                                      const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+                                                      float b2, int hidden, int mode, float* __restrict__ mix, int64_t tokens,
+                                                      int tokens_per_image) {
+    __shared__ __align__(16) float s_w1[MIX_MAX_HIDDEN * SRK_DIM];
+    __shared__ float s_b1[MIX_MAX_HIDDEN], s_w2[MIX_MAX_HIDDEN];
+    for (int i = threadIdx.x; i < hidden * SRK_DIM; i += blockDim.x) s_w1[i] = w1[i];
+    if (threadIdx.x < hidden) { s_b1[threadIdx.x] = b1[threadIdx.x]; s_w2[threadIdx.x] = w2[threadIdx.x]; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    constexpr int C4 = SRK_DIM / 4;                       // 45 float4 per row: lane handles float4 `lane` and `lane + 32`
+    const bool has2 = lane + 32 < C4;
+    for (int64_t tok = warp; tok < tokens; tok += nwarps) {
+        const float4* a4 = reinterpret_cast<const float4*>(att + tok * SRK_DIM);
+        const float4* c4 = reinterpret_cast<const float4*>(conv + tok * SRK_DIM);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 a0 = __ldg(a4 + lane), a1 = has2 ? __ldg(a4 + lane + 32) : z;
+        const float4 v0 = __ldg(c4 + lane), v1 = has2 ? __ldg(c4 + lane + 32) : z;
+        const float4 s0 = mode == 0 ? a0 : v0, s1 = mode == 0 ? a1 : v1;
+        float sacc = b2;
+        for (int j = 0; j < hidden; ++j) {
+            const float4* wj = reinterpret_cast<const float4*>(s_w1 + j * SRK_DIM);
+            const float4 wa = wj[lane];
+            float d = (wa.x * s0.x + wa.y * s0.y) + (wa.z * s0.z + wa.w * s0.w);
+            if (has2) {
+                const float4 wb = wj[lane + 32];
+                d += (wb.x * s1.x + wb.y * s1.y) + (wb.z * s1.z + wb.w * s1.w);
+            }
+            d = warp_sum(d);
+            sacc = fmaf(s_w2[j], gelu_erf(d + s_b1[j]), sacc);
+        }
+        const float sg = sigmoidf_(sacc);
+        const float4* m4 = reinterpret_cast<const float4*>(cmap + (tok / tokens_per_image) * SRK_DIM);
+        float4* o4 = reinterpret_cast<float4*>(mix + tok * SRK_DIM);
+        {
+            const float4 cm = __ldg(m4 + lane);
+            const float4 cg = make_float4(sigmoidf_(cm.x), sigmoidf_(cm.y), sigmoidf_(cm.z), sigmoidf_(cm.w));
+            float4 o;
+            if (mode == 0) o = make_float4(fmaf(a0.x, cg.x, sg * v0.x), fmaf(a0.y, cg.y, sg * v0.y), fmaf(a0.z, cg.z, sg * v0.z), fmaf(a0.w, cg.w, sg * v0.w));
+            else           o = make_float4(fmaf(v0.x, cg.x, sg * a0.x), fmaf(v0.y, cg.y, sg * a0.y), fmaf(v0.z, cg.z, sg * a0.z), fmaf(v0.w, cg.w, sg * a0.w));
+            o4[lane] = o;
+        }
+        if (has2) {
+            const float4 cm = __ldg(m4 + lane + 32);
+            const float4 cg = make_float4(sigmoidf_(cm.x), sigmoidf_(cm.y), sigmoidf_(cm.z), sigmoidf_(cm.w));
+            float4 o;
+            if (mode == 0) o = make_float4(fmaf(a1.x, cg.x, sg * v1.x), fmaf(a1.y, cg.y, sg * v1.y), fmaf(a1.z, cg.z, sg * v1.z), fmaf(a1.w, cg.w, sg * v1.w));
+            else           o = make_float4(fmaf(v1.x, cg.x, sg * a1.x), fmaf(v1.y, cg.y, sg * a1.y), fmaf(v1.z, cg.z, sg * a1.z), fmaf(v1.w, cg.w, sg * a1.w));
+            o4[lane + 32] = o;
+        }
+    }
+}
+
+// ---- channel attention statistics.  qkv rows [tok][540] = q | k | v.  One block per (token chunk, head, image): 64 tokens of
+//      q_h, k_h (30 dims) staged in shared memory; thread (d1, d2) accumulates q[:, d1] . k[:, d2]; the first 60 threads also the
+//      squared norms.  gram[b][h] = 30x30 products, then 30 |q_d|^2, then 30 |k_d|^2 (atomic adds; zeroed by the launcher).
+constexpr int GRAM_TOK = 64;
+constexpr int GRAM_STRIDE = SRK_HEAD_DIM * SRK_HEAD_DIM + 2 * SRK_HEAD_DIM;      // 960 floats per (image, head)
+__global__ void __launch_bounds__(960) channel_gram_kernel(const float* __restrict__ qkv, float* __restrict__ gram, int tokens_per_image) {
+    __shared__ float s_q[GRAM_TOK][SRK_HEAD_DIM + 1], s_k[GRAM_TOK][SRK_HEAD_DIM + 1];
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int t0 = blockIdx.x * GRAM_TOK;
+    const int nt = min(GRAM_TOK, tokens_per_image - t0);
+    const float* base = qkv + (static_cast<int64_t>(b) * tokens_per_image + t0) * (3 * SRK_DIM) + h * SRK_HEAD_DIM;
+    for (int i = threadIdx.x; i < nt * 2 * SRK_HEAD_DIM; i += blockDim.x) {
+        const int t = i / (2 * SRK_HEAD_DIM), r = i % (2 * SRK_HEAD_DIM);
+        const float v = __ldg(base + static_cast<int64_t>(t) * (3 * SRK_DIM) + (r < SRK_HEAD_DIM ? r : SRK_DIM + r - SRK_HEAD_DIM));
+        if (r < SRK_HEAD_DIM) s_q[t][r] = v; else s_k[t][r - SRK_HEAD_DIM] = v;
+    }
+    __syncthreads();
+    float* dst = gram + (static_cast<int64_t>(b) * SRK_HEADS + h) * GRAM_STRIDE;
+    const int i = threadIdx.x;
+    if (i < SRK_HEAD_DIM * SRK_HEAD_DIM) {
+        const int d1 = i / SRK_HEAD_DIM, d2 = i % SRK_HEAD_DIM;
+        float a = 0.f;
+        for (int t = 0; t < nt; ++t) a = fmaf(s_q[t][d1], s_k[t][d2], a);
+        atomicAdd(dst + i, a);
+    } else if (i < GRAM_STRIDE) {
+        const int d = (i - SRK_HEAD_DIM * SRK_HEAD_DIM) % SRK_HEAD_DIM;
+        const bool isq = i < SRK_HEAD_DIM * SRK_HEAD_DIM + SRK_HEAD_DIM;
+        float a = 0.f;
+        for (int t = 0; t < nt; ++t) { const float v = isq ? s_q[t][d] : s_k[t][d]; a = fmaf(v, v, a); }
+        atomicAdd(dst + i, a);
+    }
+}
+
+// ---- out[tok, h*30 + d1] = sum_d2 attn[b, h, d1, d2] * v[tok, h*30 + d2]; one block per (image, 64-token chunk), the image's six
+//      30x30 matrices in shared memory, one warp per token, lane -> output channels lane, lane + 32, ...
+constexpr int APPLY_TOK = 64;
+__global__ void __launch_bounds__(256) channel_apply_kernel(const float* __restrict__ qkv, const float* __restrict__ attn, float* __restrict__ out,
+                                                            int tokens_per_image) {
+    __shared__ float s_a[SRK_HEADS * SRK_HEAD_DIM * SRK_HEAD_DIM];
+    __shared__ float s_v[8][SRK_DIM];
+    const int b = blockIdx.y;
+    for (int i = threadIdx.x; i < SRK_HEADS * SRK_HEAD_DIM * SRK_HEAD_DIM; i += blockDim.x)
+        s_a[i] = attn[static_cast<int64_t>(b) * SRK_HEADS * SRK_HEAD_DIM * SRK_HEAD_DIM + i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t0 = blockIdx.x * APPLY_TOK;
+    const int nt = min(APPLY_TOK, tokens_per_image - t0);
+    for (int t = warp; t < nt; t += 8) {
+        const int64_t tok = static_cast<int64_t>(b) * tokens_per_image + t0 + t;
+        const float* v = qkv + tok * (3 * SRK_DIM) + 2 * SRK_DIM;
+        for (int c = lane; c < SRK_DIM; c += 32) s_v[warp][c] = __ldg(v + c);
+        __syncwarp();
+        for (int c = lane; c < SRK_DIM; c += 32) {
+            const int h = c / SRK_HEAD_DIM, d1 = c - h * SRK_HEAD_DIM;
+            const float* arow = s_a + (h * SRK_HEAD_DIM + d1) * SRK_HEAD_DIM;
+            const float* vh = s_v[warp] + h * SRK_HEAD_DIM;
+            float a = 0.f;
+#pragma unroll
+            for (int d2 = 0; d2 < SRK_HEAD_DIM; ++d2) a = fmaf(arow[d2], vh[d2], a);
+            out[tok * SRK_DIM + c] = a;
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+static int grid_for(int64_t threads_needed) {
+    const int64_t blocks = (threads_needed + 255) / 256;
+    return static_cast<int>(blocks < 148 * 16 ? (blocks > 0 ? blocks : 1) : 148 * 16);
+}
+
+cudaError_t launch_dwconv3x3_rows(const float* in, int ld_in, int c_in, const float* w, const float* scale, const float* shift,
+                                  const float* stats, const float* gamma, const float* beta, const float* gate, int ld_gate, int c_gate,
+                                  float* out, int ld_out, int C, int batch, int H, int W, int act_gelu, cudaStream_t stream) {
+    const int64_t total = static_cast<int64_t>(batch) * H * W * (C / 4);
+    if (total <= 0) return cudaSuccess;
+    dwconv3x3_rows_kernel<<<grid_for(total), 256, 0, stream>>>(in, ld_in, c_in, w, scale, shift, stats, gamma, beta, gate, ld_gate, c_gate,
+                                                               out, ld_out, C, batch, H, W, act_gelu);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_row_stats(const float* in, int ld_in, int c_in, int C, int64_t tokens, float eps, float* stats, cudaStream_t stream) {
+    if (tokens <= 0) return cudaSuccess;
+    row_stats_kernel<<<grid_for(tokens * 32), 256, 0, stream>>>(in, ld_in, c_in, C, tokens, eps, stats);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dat_mix(const float* att, const float* conv, const float* cmap, const float* w1, const float* b1, const float* w2,
+                           float b2, int hidden, int mode, float* mix, int64_t tokens, int tokens_per_image, cudaStream_t stream) {
+    if (tokens <= 0) return cudaSuccess;
+    dat_mix_kernel<<<grid_for(tokens * 32), 256, 0, stream>>>(att, conv, cmap, w1, b1, w2, b2, hidden, mode, mix, tokens, tokens_per_image);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_channel_gram(const float* qkv, float* gram, int batch, int tokens_per_image, cudaStream_t stream) {
+    if (batch <= 0 || tokens_per_image <= 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(gram, 0, static_cast<size_t>(batch) * SRK_HEADS * GRAM_STRIDE * sizeof(float), stream);
+    if (e != cudaSuccess) return e;
+    dim3 grid((tokens_per_image + GRAM_TOK - 1) / GRAM_TOK, SRK_HEADS, batch);
+    channel_gram_kernel<<<grid, 960, 0, stream>>>(qkv, gram, tokens_per_image);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_channel_apply(const float* qkv, const float* attn, float* out, int batch, int tokens_per_image, cudaStream_t stream) {
+    if (batch <= 0 || tokens_per_image <= 0) return cudaSuccess;
+    dim3 grid((tokens_per_image + APPLY_TOK - 1) / APPLY_TOK, batch);
+    channel_apply_kernel<<<grid, 256, 0, stream>>>(qkv, attn, out, tokens_per_image);
+    return cudaGetLastError();
+}
+
+}  // namespace srk

@@ -10,9 +10,11 @@ What runs where (per DATB, dat_arch.py:556-565)
     position bias, per-axis shift masks) -> srk_window_attention_fwd (tcgen05, kinds DAT_8x32 / DAT_32x8); img2windows,
     torch.roll and windows2img are the kernel's load / store addressing
   * proj, LN2 + fc1 + GELU, fc2 (+ residual) -> srk_linear_fwd
-  * the small HBM-bound glue -- depthwise 3x3 convolutions (+BN+GELU), the two squeeze gates of the adaptive interaction
-    module, the 30x30 channel-attention matrices of the DCTB blocks, the spatial gate's LayerNorm -- runs as torch CUDA ops
-    this round (library calls; fusing them is listed in DESIGN.md "next").
+  * depthwise 3x3 convolutions (+BN+GELU), the spatial gate (LayerNorm + depthwise conv + multiply), the adaptive interaction
+    module's per-token squeeze MLP / gates / branch mix, the channel attention's q^T k statistics and attn @ v
+                                         -> srk_dwconv3x3_rows_fwd, srk_row_stats_fwd, srk_dat_mix_fwd, srk_dat_channel_gram_fwd /
+                                            srk_dat_channel_apply_fwd (csrc/dat_kernels.cu, HBM-bound streaming kernels)
+  * what stays in torch: the per-image (B, 180) channel map MLP and the 6 x 30 x 30 channel softmax -- a few thousand values.
 The dynamic position bias is input independent: its 4-layer MLP is evaluated once per weight version at pack time.
 Inference only; no CPU / eager fallback for the kernels.
 """
@@ -59,12 +61,31 @@ class SpatialGate(nn.Module):
         self.norm = nn.LayerNorm(dim)
         self.conv = nn.Conv2d(dim, dim, kernel_size=3, stride=1, padding=1, groups=dim)
 
-    def forward(self, x, H, W):
-        x1, x2 = x.chunk(2, dim=-1)
+    def _packed(self):
+        ps = [self.conv.weight, self.conv.bias]
+
+        def build():
+            Ch = self.conv.weight.shape[0]
+            w9c = self.conv.weight.detach().reshape(Ch, 9).t().contiguous()                 # [tap][channel]
+            return w9c, torch.ones(Ch, device=w9c.device), self.conv.bias.detach().clone()
+        if not hasattr(self, "_cache"):
+            self._cache = _PackedCache()
+        return self._cache.get(ps, build)
+
+    def gate_rows(self, x, H, W):
+        """x (B, N, 2*Ch) fp32 CUDA rows -> x1 * dwconv3x3(LayerNorm(x2)) (B, N, Ch): srk_row_stats_fwd + srk_dwconv3x3_rows_fwd."""
         B, N, C = x.shape
-        x2 = F.layer_norm(x2, (C // 2,), self.norm.weight, self.norm.bias, self.norm.eps)
-        x2 = self.conv(x2.view(B, H, W, C // 2).permute(0, 3, 1, 2)).permute(0, 2, 3, 1).reshape(B, N, C // 2)
-        return x1 * x2
+        Ch = C // 2
+        w9c, one, bias = self._packed()
+        stats = torch.empty((B * N, 2), dtype=torch.float32, device=x.device)
+        L.row_stats(x, stats, ld_in=C, c_in=Ch, channels=Ch, tokens=B * N, eps=self.norm.eps)
+        out = torch.empty((B, N, Ch), dtype=torch.float32, device=x.device)
+        L.dwconv3x3_rows(x, w9c, one, bias, out, ld_in=C, c_in=Ch, ld_out=Ch, channels=Ch, batch=B, height=H, width=W, ln_stats=stats,
+                         ln_gamma=self.norm.weight, ln_beta=self.norm.bias, gate=x, ld_gate=C, c_gate=0)
+        return out
+
+    def forward(self, x, H, W):
+        return self.gate_rows(x.contiguous(), H, W)
 
 
 class SGFN(nn.Module):
@@ -107,7 +128,7 @@ class SGFN(nn.Module):
         h = torch.empty((B, N, hid), device=x.device, dtype=torch.float32)
         L.linear(x, f1w, f1b, h, num_tokens=B * N, a_mode=L.LIN_A_ROWS, ld_in=C, apply_ln=norm is not None, n_chunks=hid // L.DIM,
                  act=L.LIN_ACT_GELU, out_mode=L.LIN_OUT_ROWS, ld_out=hid)
-        g = self.sg(h, H, W).contiguous()                                       # (B, N, hid / 2)
+        g = self.sg.gate_rows(h, H, W)                                          # (B, N, hid / 2): x1 * dwconv(LayerNorm(x2))
         for i, (w2, b2) in enumerate(halves):
             L.linear(g[..., L.DIM * i:], w2, b2, out, num_tokens=B * N, a_mode=L.LIN_A_ROWS, ld_in=hid // 2, apply_ln=False,
                      n_chunks=1, out_mode=L.LIN_OUT_ROWS, ld_out=C, add_residual=add_residual or i > 0)
@@ -183,6 +204,48 @@ class _AIM(nn.Module):
     @staticmethod
     def _img(t, B, H, W):
         return t.view(B, H, W, -1).permute(0, 3, 1, 2)          # channels-last NCHW view of token rows
+
+    def _aim_packed(self):
+        """Folded parameters of the convolution branch and the spatial gate: depthwise weights [tap][channel] with the eval
+        BatchNorm as scale / shift (dat_arch.py:300-304); spatial_interaction's first 1x1 conv with its BatchNorm folded (:311-316)."""
+        dw, bn = self.dwconv[0], self.dwconv[1]
+        c0, bn0, c3 = self.spatial_interaction[0], self.spatial_interaction[1], self.spatial_interaction[3]
+        ps = [dw.weight, dw.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, c0.weight, c0.bias, bn0.weight, bn0.bias,
+              bn0.running_mean, bn0.running_var, c3.weight, c3.bias]
+
+        def build():
+            C = dw.weight.shape[0]
+            s = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
+            w9c = dw.weight.detach().reshape(C, 9).t().contiguous()
+            shift = (dw.bias.detach() - bn.running_mean) * s + bn.bias.detach()
+            s0 = bn0.weight.detach() / torch.sqrt(bn0.running_var + bn0.eps)
+            w1 = (c0.weight.detach().reshape(c0.weight.shape[0], C) * s0[:, None]).contiguous()
+            b1 = ((c0.bias.detach() - bn0.running_mean) * s0 + bn0.bias.detach()).contiguous()
+            w2 = c3.weight.detach().reshape(-1).contiguous()
+            return w9c, s.contiguous(), shift.contiguous(), w1, b1, w2, float(c3.bias.detach().item())
+        if not hasattr(self, "_aim_cache"):
+            self._aim_cache = _PackedCache()
+        return self._aim_cache.get(ps, build)
+
+    def _conv_branch(self, rows, ld_in, c_in, B, H, W):
+        """dwconv3x3 + BatchNorm + GELU of the v slice of `rows` -> (B, H*W, C) fp32 (srk_dwconv3x3_rows_fwd)."""
+        w9c, scale, shift = self._aim_packed()[:3]
+        C = w9c.shape[1]
+        out = torch.empty((B, H * W, C), dtype=torch.float32, device=rows.device)
+        L.dwconv3x3_rows(rows, w9c, scale, shift, out, ld_in=ld_in, c_in=c_in, ld_out=C, channels=C, batch=B, height=H, width=W, act_gelu=True)
+        return out
+
+    def _channel_map(self, rows):
+        """channel_interaction (dat_arch.py:305-310) on (B, N, C) rows -> (B, C) map before the sigmoid; a few hundred MACs per image."""
+        B, N, C = rows.shape
+        return self.channel_interaction[1:](rows.mean(dim=1).view(B, C, 1, 1)).reshape(B, C).contiguous()
+
+    def _mix(self, att, conv_x, cmap, mode):
+        w1, b1, w2, b2 = self._aim_packed()[3:]
+        B, N, C = att.shape
+        mix = torch.empty_like(att)
+        L.dat_mix(att, conv_x, cmap, w1, b1, w2, b2, mix, mode=mode, tokens=B * N, tokens_per_image=N)
+        return mix
 
 
 class Adaptive_Spatial_Attention(_AIM):
@@ -264,12 +327,10 @@ class Adaptive_Spatial_Attention(_AIM):
             L.window_attention(planes[2 * i:2 * i + 2], planes[4 + 2 * i:6 + 2 * i], planes[8 + 2 * i:10 + 2 * i], tab, att, kind=kind,
                                batch=B, height=H, width=W, shift=shift if self.shifted else (0, 0), mask_shift=self.shifted,
                                n_heads=3, out_mode=1, out_ld=C, out_col0=(C // 2) * i)
-        # adaptive interaction module (dat_arch.py:418-431): torch glue on channels-last views
-        conv_x = self.dwconv(self._img(v_rows, B, H, W))
-        channel_map = self.channel_interaction(conv_x).reshape(B, 1, C)
-        spatial_map = self.spatial_interaction(self._img(att, B, H, W))                       # (B, 1, H, W)
-        mix = att * torch.sigmoid(channel_map) + (torch.sigmoid(spatial_map) * conv_x).permute(0, 2, 3, 1).reshape(B, Ltok, C)
-        L.linear(mix.contiguous(), pw, pb, out, num_tokens=tokens, a_mode=L.LIN_A_ROWS, ld_in=C, apply_ln=False, n_chunks=1,
+        # convolution branch + adaptive interaction module (dat_arch.py:418-431)
+        conv_x = self._conv_branch(v_rows, C, 0, B, H, W)
+        mix = self._mix(att, conv_x, self._channel_map(conv_x), 0)
+        L.linear(mix, pw, pb, out, num_tokens=tokens, a_mode=L.LIN_A_ROWS, ld_in=C, apply_ln=False, n_chunks=1,
                  out_mode=L.LIN_OUT_ROWS, ld_out=C, add_residual=add_residual)
         return out
 
@@ -312,14 +373,20 @@ class Adaptive_Channel_Attention(_AIM):
         qkv = torch.empty((B, N, 3 * C), dtype=torch.float32, device=x.device)
         L.linear(x, qw, qb, qkv, num_tokens=B * N, a_mode=L.LIN_A_ROWS, ld_in=C, apply_ln=norm is not None, n_chunks=3,
                  out_mode=L.LIN_OUT_ROWS, ld_out=3 * C)
-        q, k, v = (qkv[..., i * C:(i + 1) * C].reshape(B, N, nh, d).permute(0, 2, 3, 1) for i in range(3))       # (B, nh, d, N)
-        attn = (F.normalize(q, dim=-1) @ F.normalize(k, dim=-1).transpose(-2, -1)) * self.temperature             # (B, nh, d, d)
-        att = (attn.softmax(dim=-1) @ v).permute(0, 3, 1, 2).reshape(B, N, C)
-        conv_x = self.dwconv(self._img(qkv[..., 2 * C:], B, H, W))
-        channel_map = self.channel_interaction(self._img(att, B, H, W))                       # (B, C, 1, 1)
-        spatial_map = self.spatial_interaction(conv_x).permute(0, 2, 3, 1).reshape(B, N, 1)
-        mix = att * torch.sigmoid(spatial_map) + (conv_x * torch.sigmoid(channel_map)).permute(0, 2, 3, 1).reshape(B, N, C)
-        L.linear(mix.contiguous(), pw, pb, out, num_tokens=B * N, a_mode=L.LIN_A_ROWS, ld_in=C, apply_ln=False, n_chunks=1,
+        if nh != L.HEADS or d != L.HEAD_DIM:
+            raise RuntimeError("Adaptive_Channel_Attention: kernels serve 6 heads of 30 channels only")
+        # q^T k over the tokens and the squared norms (srk_dat_channel_gram_fwd); the 6 x 30 x 30 softmax per image is a few thousand
+        # values (torch); then attn @ v per token (srk_dat_channel_apply_fwd)
+        gram = torch.empty((B, nh, d * d + 2 * d), dtype=torch.float32, device=x.device)
+        L.dat_channel_gram(qkv, gram, batch=B, tokens_per_image=N)
+        nq = gram[..., d * d:d * d + d].sqrt().clamp_min(1e-12)                                # F.normalize over the tokens (:497-498)
+        nk = gram[..., d * d + d:].sqrt().clamp_min(1e-12)
+        attn = (gram[..., :d * d].view(B, nh, d, d) / (nq[..., :, None] * nk[..., None, :]) * self.temperature).softmax(dim=-1).contiguous()
+        att = torch.empty((B, N, C), dtype=torch.float32, device=x.device)
+        L.dat_channel_apply(qkv, attn, att, batch=B, tokens_per_image=N)
+        conv_x = self._conv_branch(qkv, 3 * C, 2 * C, B, H, W)
+        mix = self._mix(att, conv_x, self._channel_map(att), 1)
+        L.linear(mix, pw, pb, out, num_tokens=B * N, a_mode=L.LIN_A_ROWS, ld_in=C, apply_ln=False, n_chunks=1,
                  out_mode=L.LIN_OUT_ROWS, ld_out=C, add_residual=add_residual)
         return out
 
