@@ -154,7 +154,9 @@ int srk_layernorm_fwd(const float* x, float* y, const float* w, const float* b, 
 
 /* HAT CAB tail: out[b, t, c] += scale * y[b, t, c] * sigmoid(W2 relu(W1 mean_t(y[b, :, c]) + b1) + b2)[c] on channels-last
  * (batch, tokens_per_image, 180) fp32 tensors -- ChannelAttention (hat_arch.py:41-59) fused with `+ conv_x * conv_scale`
- * (hat_arch.py:307).  w1 (hidden, 180), w2 (180, hidden), hidden <= 32; sums_ws: batch * 180 floats of scratch. */
+ * (hat_arch.py:307).  w1 (hidden, 180), w2 (180, hidden), hidden <= 32; sums_ws: srk_cab_ws_floats() floats of scratch (per-chunk
+ * partial sums, reduced in a fixed order: results are run-to-run identical). */
+int srk_cab_ws_floats(int32_t batch, int32_t tokens_per_image);
 int srk_cab_gate_add(const float* y, float* out, float* sums_ws, const float* w1, const float* b1, const float* w2, const float* b2,
                      int32_t hidden, float scale, int32_t batch, int32_t tokens_per_image, void* stream);
 
@@ -177,7 +179,9 @@ int srk_dat_mix_fwd(const float* att, const float* conv, const float* cmap, cons
 /* Channel attention (dat_arch.py:497-505) on qkv rows (batch * tokens_per_image, 540) = q | k | v:
  * gram[b][h] = 900 products sum_n q[n, d1] k[n, d2], then 30 sums of q^2, then 30 sums of k^2 (960 floats per image and head);
  * apply: out[tok, h*30 + d1] = sum_d2 attn[b, h, d1, d2] v[tok, h*30 + d2], attn (batch, 6, 30, 30). */
-int srk_dat_channel_gram_fwd(const float* qkv, float* gram, int32_t batch, int32_t tokens_per_image, void* stream);
+int srk_dat_channel_gram_fwd(const float* qkv, float* gram, float* ws /* srk_dat_channel_gram_ws_floats() */, int32_t batch,
+                             int32_t tokens_per_image, void* stream);
+int srk_dat_channel_gram_ws_floats(int32_t batch, int32_t tokens_per_image);
 int srk_dat_channel_apply_fwd(const float* qkv, const float* attn, float* out, int32_t batch, int32_t tokens_per_image, void* stream);
 
 /* PixelShuffle(r) on channels-last activations, optional fused LeakyReLU:

@@ -83,3 +83,10 @@ def test_unsupported_geometry_is_an_error(model):
     xt = synth.make_tokens(1, 48, 64, 180, seed=1).cuda()
     with pytest.raises(RuntimeError):
         model.layers[0].blocks[0].attn(xt, 48, 64)            # H not a multiple of 32: the padded path is not implemented
+
+
+def test_determinism(model):
+    """Two runs are bit-identical (the channel-attention statistics are reduced in a fixed order, no float atomics)."""
+    lr = synth.make_lr_batch(2, 64, 64, seed=9).cuda()
+    y1, y2 = model(lr), model(lr)
+    assert torch.isfinite(y1).all() and torch.equal(y1, y2)

@@ -98,7 +98,9 @@ def load():
                                            c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
     lib.srk_row_stats_fwd.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int64, f32, c_void_p, c_void_p]
     lib.srk_dat_mix_fwd.argtypes = [c_void_p] * 6 + [f32, c_int32, c_int32, c_void_p, c_int64, c_int32, c_void_p]
-    lib.srk_dat_channel_gram_fwd.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_void_p]
+    lib.srk_dat_channel_gram_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]
+    lib.srk_dat_channel_gram_ws_floats.argtypes = [c_int32, c_int32]
+    lib.srk_cab_ws_floats.argtypes = [c_int32, c_int32]
     lib.srk_dat_channel_apply_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]
     lib.srk_cab_gate_add.argtypes = [c_void_p] * 7 + [c_int32, ctypes.c_float, c_int32, c_int32, c_void_p]
     lib.srk_debug_set_timeline.argtypes = [c_void_p]
@@ -110,7 +112,7 @@ def load():
     for f in ("srk_swin_attn_fwd", "srk_swin_mlp_fwd", "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd",
               "srk_stitch_accumulate", "srk_stitch_normalize", "srk_linear_fwd", "srk_window_attention_fwd",
               "srk_window_attention_table_floats", "srk_cab_gate_add", "srk_dwconv3x3_rows_fwd", "srk_row_stats_fwd", "srk_dat_mix_fwd",
-              "srk_dat_channel_gram_fwd", "srk_dat_channel_apply_fwd"):
+              "srk_dat_channel_gram_fwd", "srk_dat_channel_apply_fwd", "srk_dat_channel_gram_ws_floats", "srk_cab_ws_floats"):
         getattr(lib, f).restype = c_int32
     if lib.srk_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libsrk.so ABI {lib.srk_abi_version()} != expected {ABI_VERSION}; rebuild")
@@ -122,7 +124,7 @@ EXPORTS = ("srk_abi_version", "srk_last_error_string", "srk_launch_count", "srk_
            "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd", "srk_stitch_accumulate", "srk_stitch_normalize", "srk_debug_set_timeline", "srk_debug_set_stagger",
            "srk_linear_fwd", "srk_window_attention_fwd", "srk_window_attention_table_floats", "srk_debug_set_winattn_stagger",
            "srk_cab_gate_add", "srk_dwconv3x3_rows_fwd", "srk_row_stats_fwd", "srk_dat_mix_fwd", "srk_dat_channel_gram_fwd",
-           "srk_dat_channel_apply_fwd")
+           "srk_dat_channel_apply_fwd", "srk_dat_channel_gram_ws_floats", "srk_cab_ws_floats")
 
 
 def _check(rc: int, lib) -> None:
@@ -239,7 +241,7 @@ def cab_gate_add(y, out, w1, b1, w2, b2, *, scale, batch, tokens_per_image) -> N
     """srk_cab_gate_add: out += scale * y * squeeze_excite_gate(y) on channels-last (batch, tokens, 180) fp32 tensors."""
     lib = load()
     _require_cuda_f32(y, out, w1, b1, w2, b2)
-    ws = torch.empty(batch * DIM, dtype=torch.float32, device=y.device)
+    ws = torch.empty(lib.srk_cab_ws_floats(batch, tokens_per_image), dtype=torch.float32, device=y.device)
     with _timed("cab_gate_add"):
         _check(lib.srk_cab_gate_add(y.data_ptr(), out.data_ptr(), ws.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
                                     b2.data_ptr(), w1.shape[0], float(scale), batch, tokens_per_image, _stream()), lib)
@@ -278,8 +280,9 @@ def dat_mix(att, conv, cmap, w1, b1, w2, b2, mix, *, mode, tokens, tokens_per_im
 def dat_channel_gram(qkv, gram, *, batch, tokens_per_image) -> None:
     lib = load()
     _require_cuda_f32(qkv, gram)
+    ws = torch.empty(lib.srk_dat_channel_gram_ws_floats(batch, tokens_per_image), dtype=torch.float32, device=qkv.device)
     with _timed("dat_channel_gram"):
-        _check(lib.srk_dat_channel_gram_fwd(qkv.data_ptr(), gram.data_ptr(), batch, tokens_per_image, _stream()), lib)
+        _check(lib.srk_dat_channel_gram_fwd(qkv.data_ptr(), gram.data_ptr(), ws.data_ptr(), batch, tokens_per_image, _stream()), lib)
 
 
 def dat_channel_apply(qkv, attn, out, *, batch, tokens_per_image) -> None:

@@ -187,7 +187,8 @@ __global__ void __launch_bounds__(192) cab_pool_kernel(const float* __restrict__
         s0 += __ldg(src); s1 += __ldg(src + SRK_DIM); s2 += __ldg(src + 2 * SRK_DIM); s3 += __ldg(src + 3 * SRK_DIM);
     }
     for (; t < t1; ++t, src += SRK_DIM) s0 += __ldg(src);
-    atomicAdd(sums + b * SRK_DIM + c, (s0 + s1) + (s2 + s3));
+    // one partial per (image, token chunk): summed in a fixed order by cab_gate_add_kernel, so the result is run-to-run identical
+    sums[(static_cast<int64_t>(b) * gridDim.x + blockIdx.x) * SRK_DIM + c] = (s0 + s1) + (s2 + s3);
 }
 
 __global__ void __launch_bounds__(256) cab_gate_add_kernel(const float* __restrict__ y, float* __restrict__ out,
@@ -198,7 +199,11 @@ __global__ void __launch_bounds__(256) cab_gate_add_kernel(const float* __restri
     __shared__ float s_mean[SRK_DIM], s_hid[32];
     __shared__ __align__(16) float s_gate[SRK_DIM];
     const int b = blockIdx.y;
-    for (int c = threadIdx.x; c < SRK_DIM; c += blockDim.x) s_mean[c] = sums[b * SRK_DIM + c] / static_cast<float>(tokens_per_image);
+    for (int c = threadIdx.x; c < SRK_DIM; c += blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < static_cast<int>(gridDim.x); ++k) s += __ldg(sums + (static_cast<int64_t>(b) * gridDim.x + k) * SRK_DIM + c);
+        s_mean[c] = s / static_cast<float>(tokens_per_image);
+    }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int j = warp; j < hidden; j += 8) {                 // hidden unit j: one warp, lanes stride over the 180 inputs
@@ -230,11 +235,13 @@ __global__ void __launch_bounds__(256) cab_gate_add_kernel(const float* __restri
     }
 }
 
+int cab_ws_floats(int batch, int tokens_per_image) {
+    return batch * ((tokens_per_image + CAB_TOK_PER_BLOCK - 1) / CAB_TOK_PER_BLOCK) * SRK_DIM;
+}
+
 cudaError_t launch_cab_gate_add(const float* y, float* out, float* sums, const float* w1, const float* b1, const float* w2,
                                 const float* b2, int hidden, float scale, int batch, int tokens_per_image, cudaStream_t stream) {
     if (batch <= 0 || tokens_per_image <= 0) return cudaSuccess;
-    cudaError_t e = cudaMemsetAsync(sums, 0, static_cast<size_t>(batch) * SRK_DIM * sizeof(float), stream);
-    if (e != cudaSuccess) return e;
     dim3 grid((tokens_per_image + CAB_TOK_PER_BLOCK - 1) / CAB_TOK_PER_BLOCK, batch);
     cab_pool_kernel<<<grid, 192, 0, stream>>>(y, sums, tokens_per_image);
     cab_gate_add_kernel<<<grid, 256, 0, stream>>>(y, out, sums, w1, b1, w2, b2, hidden, scale, tokens_per_image);

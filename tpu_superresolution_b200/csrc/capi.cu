@@ -253,10 +253,14 @@ int srk_dat_mix_fwd(const float* att, const float* conv, const float* cmap, cons
                                      static_cast<cudaStream_t>(stream)), "srk_dat_mix_fwd");
 }
 
-int srk_dat_channel_gram_fwd(const float* qkv, float* gram, int32_t batch, int32_t tokens_per_image, void* stream) {
-    if (!qkv || !gram) return fail("srk_dat_channel_gram_fwd: null argument");
+int srk_dat_channel_gram_ws_floats(int32_t batch, int32_t tokens_per_image) { return srk::channel_gram_ws_floats(batch, tokens_per_image); }
+int srk_cab_ws_floats(int32_t batch, int32_t tokens_per_image) { return srk::cab_ws_floats(batch, tokens_per_image); }
+
+int srk_dat_channel_gram_fwd(const float* qkv, float* gram, float* ws, int32_t batch, int32_t tokens_per_image, void* stream) {
+    if (!qkv || !gram || !ws) return fail("srk_dat_channel_gram_fwd: null argument");
+    if (!aligned16(qkv)) return fail("srk_dat_channel_gram_fwd: qkv must be 16-byte aligned");
     if (batch < 0 || batch > 65535 || tokens_per_image <= 0) return fail("srk_dat_channel_gram_fwd: bad shape");
-    return check(srk::launch_channel_gram(qkv, gram, batch, tokens_per_image, static_cast<cudaStream_t>(stream)), "srk_dat_channel_gram_fwd");
+    return check(srk::launch_channel_gram(qkv, gram, ws, batch, tokens_per_image, static_cast<cudaStream_t>(stream)), "srk_dat_channel_gram_fwd");
 }
 
 int srk_dat_channel_apply_fwd(const float* qkv, const float* attn, float* out, int32_t batch, int32_t tokens_per_image, void* stream) {

@@ -35,28 +35,31 @@ __global__ void __launch_bounds__(256) dwconv3x3_rows_kernel(const float* __rest
                                                              const float* __restrict__ scale, const float* __restrict__ shift,
                                                              const float* __restrict__ stats, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, const float* __restrict__ gate, int ld_gate,
-                                                             int c_gate, float* __restrict__ out, int ld_out, int C, int batch, int H,
-                                                             int W, int act_gelu) {
+                                                             int c_gate, float* __restrict__ out, int ld_out, int C, int H, int W,
+                                                             int act_gelu) {
+    // one block per image row (blockIdx.x = b * H + y): no 64-bit divisions in the element loop
     const int C4 = C >> 2;
-    const int64_t total = static_cast<int64_t>(batch) * H * W * C4;
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int c4 = static_cast<int>(i % C4);
-        const int64_t tok = i / C4;
-        const int x = static_cast<int>(tok % W);
-        const int y = static_cast<int>((tok / W) % H);
+    const int y = blockIdx.x % H;
+    const int64_t row0 = static_cast<int64_t>(blockIdx.x) * W;         // first token of this image row
+    const bool up = y > 0, down = y + 1 < H;
+    for (int i = threadIdx.x; i < W * C4; i += blockDim.x) {
+        const int x = i / C4, c4 = i - x * C4;
+        const int64_t tok = row0 + x;
         float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (stats) { g4 = __ldg(reinterpret_cast<const float4*>(gamma) + c4); b4 = __ldg(reinterpret_cast<const float4*>(beta) + c4); }
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int dy = -1; dy <= 1; ++dy) {
+            if ((dy < 0 && !up) || (dy > 0 && !down)) continue;               // zero padding (of the normalised tensor)
 #pragma unroll
             for (int dx = -1; dx <= 1; ++dx) {
-                const int yy = y + dy, xx = x + dx;
-                if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;           // zero padding (of the normalised tensor)
+                const int xx = x + dx;
+                if (xx < 0 || xx >= W) continue;
                 const int64_t nt = tok + dy * W + dx;
                 float4 v = __ldg(reinterpret_cast<const float4*>(in + nt * ld_in + c_in) + c4);
                 if (stats) {
-                    const float mu = __ldg(stats + 2 * nt), rs = __ldg(stats + 2 * nt + 1);
+                    const float2 st = __ldg(reinterpret_cast<const float2*>(stats) + nt);
+                    const float mu = st.x, rs = st.y;
                     v.x = (v.x - mu) * rs * g4.x + b4.x; v.y = (v.y - mu) * rs * g4.y + b4.y;
                     v.z = (v.z - mu) * rs * g4.z + b4.z; v.w = (v.w - mu) * rs * g4.w + b4.w;
                 }
@@ -161,67 +164,109 @@ __global__ void __launch_bounds__(256) dat_mix_kernel(const float* __restrict__ 
 }
 
 // ---- channel attention statistics.  qkv rows [tok][540] = q | k | v.  One block per (token chunk, head, image): 64 tokens of
-//      q_h, k_h (30 dims) staged in shared memory; thread (d1, d2) accumulates q[:, d1] . k[:, d2]; the first 60 threads also the
-//      squared norms.  gram[b][h] = 30x30 products, then 30 |q_d|^2, then 30 |k_d|^2 (atomic adds; zeroed by the launcher).
-constexpr int GRAM_TOK = 64;
+//      q, k staged in shared memory; gram[b][h] = 30x30 products, then 30 |q_d|^2, then 30 |k_d|^2 (per-block partials + ordered reduce).
+constexpr int GRAM_TOK = 32;
 constexpr int GRAM_STRIDE = SRK_HEAD_DIM * SRK_HEAD_DIM + 2 * SRK_HEAD_DIM;      // 960 floats per (image, head)
-__global__ void __launch_bounds__(960) channel_gram_kernel(const float* __restrict__ qkv, float* __restrict__ gram, int tokens_per_image) {
-    __shared__ float s_q[GRAM_TOK][SRK_HEAD_DIM + 1], s_k[GRAM_TOK][SRK_HEAD_DIM + 1];
-    const int h = blockIdx.y, b = blockIdx.z;
-    const int t0 = blockIdx.x * GRAM_TOK;
-    const int nt = min(GRAM_TOK, tokens_per_image - t0);
-    const float* base = qkv + (static_cast<int64_t>(b) * tokens_per_image + t0) * (3 * SRK_DIM) + h * SRK_HEAD_DIM;
-    for (int i = threadIdx.x; i < nt * 2 * SRK_HEAD_DIM; i += blockDim.x) {
-        const int t = i / (2 * SRK_HEAD_DIM), r = i % (2 * SRK_HEAD_DIM);
-        const float v = __ldg(base + static_cast<int64_t>(t) * (3 * SRK_DIM) + (r < SRK_HEAD_DIM ? r : SRK_DIM + r - SRK_HEAD_DIM));
-        if (r < SRK_HEAD_DIM) s_q[t][r] = v; else s_k[t][r - SRK_HEAD_DIM] = v;
-    }
-    __syncthreads();
-    float* dst = gram + (static_cast<int64_t>(b) * SRK_HEADS + h) * GRAM_STRIDE;
+// thread (head, 5x5 tile of the 30x30 products): 10 shared-memory reads per 25 FMAs; 6 heads x 36 tiles = 216 threads
+constexpr int GRAM_CHUNKS = 8;             // token chunks per block: partial sums stay in registers across them
+__global__ void __launch_bounds__(224) channel_gram_kernel(const float* __restrict__ qkv, float* __restrict__ part, int tokens_per_image) {
+    __shared__ float s_qk[GRAM_TOK][2 * SRK_DIM + 4];            // q | k rows of the token chunk
+    const int b = blockIdx.y;
     const int i = threadIdx.x;
-    if (i < SRK_HEAD_DIM * SRK_HEAD_DIM) {
-        const int d1 = i / SRK_HEAD_DIM, d2 = i % SRK_HEAD_DIM;
-        float a = 0.f;
-        for (int t = 0; t < nt; ++t) a = fmaf(s_q[t][d1], s_k[t][d2], a);
-        atomicAdd(dst + i, a);
-    } else if (i < GRAM_STRIDE) {
-        const int d = (i - SRK_HEAD_DIM * SRK_HEAD_DIM) % SRK_HEAD_DIM;
-        const bool isq = i < SRK_HEAD_DIM * SRK_HEAD_DIM + SRK_HEAD_DIM;
-        float a = 0.f;
-        for (int t = 0; t < nt; ++t) { const float v = isq ? s_q[t][d] : s_k[t][d]; a = fmaf(v, v, a); }
-        atomicAdd(dst + i, a);
+    const bool worker = i < SRK_HEADS * 36;
+    const int h = i / 36, tile = i - h * 36, r0 = (tile / 6) * 5, c0 = (tile % 6) * 5;
+    const int qo = h * SRK_HEAD_DIM + r0, ko = SRK_DIM + h * SRK_HEAD_DIM + c0;
+    float acc[5][5], nq[5], nk[5];
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+        nq[a] = 0.f; nk[a] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) acc[a][c] = 0.f;
+    }
+    for (int ch = 0; ch < GRAM_CHUNKS; ++ch) {
+        const int t0 = (blockIdx.x * GRAM_CHUNKS + ch) * GRAM_TOK;
+        const int nt = min(GRAM_TOK, tokens_per_image - t0);
+        if (nt <= 0) break;
+        const float* base = qkv + (static_cast<int64_t>(b) * tokens_per_image + t0) * (3 * SRK_DIM);
+        __syncthreads();
+        for (int e = threadIdx.x; e < nt * (2 * SRK_DIM / 4); e += blockDim.x) {
+            const int tk = e / (2 * SRK_DIM / 4), r = e - tk * (2 * SRK_DIM / 4);
+            const float4 v = __ldg(reinterpret_cast<const float4*>(base + static_cast<int64_t>(tk) * (3 * SRK_DIM)) + r);
+            *reinterpret_cast<float4*>(&s_qk[tk][4 * r]) = v;
+        }
+        __syncthreads();
+        if (worker) {
+            for (int tk = 0; tk < nt; ++tk) {
+                float qv[5], kv[5];
+#pragma unroll
+                for (int a = 0; a < 5; ++a) { qv[a] = s_qk[tk][qo + a]; kv[a] = s_qk[tk][ko + a]; }
+#pragma unroll
+                for (int a = 0; a < 5; ++a) {
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) acc[a][c] = fmaf(qv[a], kv[c], acc[a][c]);
+                    nq[a] = fmaf(qv[a], qv[a], nq[a]);
+                    nk[a] = fmaf(kv[a], kv[a], nk[a]);
+                }
+            }
+        }
+    }
+    if (!worker) return;
+    // one partial per (image, block): reduced in a fixed order by channel_gram_reduce_kernel (run-to-run identical results)
+    float* dst = part + ((static_cast<int64_t>(b) * gridDim.x + blockIdx.x) * SRK_HEADS + h) * GRAM_STRIDE;
+#pragma unroll
+    for (int a = 0; a < 5; ++a)
+#pragma unroll
+        for (int c = 0; c < 5; ++c) dst[(r0 + a) * SRK_HEAD_DIM + c0 + c] = acc[a][c];
+    if (tile % 6 == 0) {            // first tile of a tile row owns the q norms of its 5 rows
+#pragma unroll
+        for (int a = 0; a < 5; ++a) dst[SRK_HEAD_DIM * SRK_HEAD_DIM + r0 + a] = nq[a];
+    }
+    if (tile / 6 == 0) {            // first tile of a tile column owns the k norms of its 5 columns
+#pragma unroll
+        for (int a = 0; a < 5; ++a) dst[SRK_HEAD_DIM * SRK_HEAD_DIM + SRK_HEAD_DIM + c0 + a] = nk[a];
     }
 }
 
-// ---- out[tok, h*30 + d1] = sum_d2 attn[b, h, d1, d2] * v[tok, h*30 + d2]; one block per (image, 64-token chunk), the image's six
-//      30x30 matrices in shared memory, one warp per token, lane -> output channels lane, lane + 32, ...
-constexpr int APPLY_TOK = 64;
-__global__ void __launch_bounds__(256) channel_apply_kernel(const float* __restrict__ qkv, const float* __restrict__ attn, float* __restrict__ out,
+__global__ void __launch_bounds__(256) channel_gram_reduce_kernel(const float* __restrict__ part, float* __restrict__ gram, int nblk, int per_image) {
+    const int b = blockIdx.y;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < per_image; e += gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < nblk; ++k) s += __ldg(part + (static_cast<int64_t>(b) * nblk + k) * per_image + e);
+        gram[static_cast<int64_t>(b) * per_image + e] = s;
+    }
+}
+
+// ---- out[tok, h*30 + d1] = sum_d2 attn[b, h, d1, d2] * v[tok, h*30 + d2]; one block per (image, 32-token chunk), the image's six
+//      30x30 matrices in shared memory
+constexpr int APPLY_TOK = 32;
+// warp = 32 tokens x one head: every lane keeps its token's 30 v values in registers and the head's 30x30 matrix is read from
+// shared memory as warp-wide broadcasts (one wavefront per read); 6 warps per block = the 6 heads of the same 32 tokens
+__global__ void __launch_bounds__(192) channel_apply_kernel(const float* __restrict__ qkv, const float* __restrict__ attn, float* __restrict__ out,
                                                             int tokens_per_image) {
     __shared__ float s_a[SRK_HEADS * SRK_HEAD_DIM * SRK_HEAD_DIM];
-    __shared__ float s_v[8][SRK_DIM];
     const int b = blockIdx.y;
     for (int i = threadIdx.x; i < SRK_HEADS * SRK_HEAD_DIM * SRK_HEAD_DIM; i += blockDim.x)
         s_a[i] = attn[static_cast<int64_t>(b) * SRK_HEADS * SRK_HEAD_DIM * SRK_HEAD_DIM + i];
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t0 = blockIdx.x * APPLY_TOK;
-    const int nt = min(APPLY_TOK, tokens_per_image - t0);
-    for (int t = warp; t < nt; t += 8) {
-        const int64_t tok = static_cast<int64_t>(b) * tokens_per_image + t0 + t;
-        const float* v = qkv + tok * (3 * SRK_DIM) + 2 * SRK_DIM;
-        for (int c = lane; c < SRK_DIM; c += 32) s_v[warp][c] = __ldg(v + c);
-        __syncwarp();
-        for (int c = lane; c < SRK_DIM; c += 32) {
-            const int h = c / SRK_HEAD_DIM, d1 = c - h * SRK_HEAD_DIM;
-            const float* arow = s_a + (h * SRK_HEAD_DIM + d1) * SRK_HEAD_DIM;
-            const float* vh = s_v[warp] + h * SRK_HEAD_DIM;
-            float a = 0.f;
+    const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * APPLY_TOK + lane;
+    if (t >= tokens_per_image) return;
+    const int64_t tok = static_cast<int64_t>(b) * tokens_per_image + t;
+    const float2* v2 = reinterpret_cast<const float2*>(qkv + tok * (3 * SRK_DIM) + 2 * SRK_DIM + h * SRK_HEAD_DIM);
+    float v[SRK_HEAD_DIM];
 #pragma unroll
-            for (int d2 = 0; d2 < SRK_HEAD_DIM; ++d2) a = fmaf(arow[d2], vh[d2], a);
-            out[tok * SRK_DIM + c] = a;
+    for (int d = 0; d < SRK_HEAD_DIM / 2; ++d) { const float2 x = __ldg(v2 + d); v[2 * d] = x.x; v[2 * d + 1] = x.y; }
+    const float* ah = s_a + h * SRK_HEAD_DIM * SRK_HEAD_DIM;
+    float2* o2 = reinterpret_cast<float2*>(out + tok * SRK_DIM + h * SRK_HEAD_DIM);
+#pragma unroll 2
+    for (int d1 = 0; d1 < SRK_HEAD_DIM; d1 += 2) {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int d2 = 0; d2 < SRK_HEAD_DIM; ++d2) {
+            a0 = fmaf(ah[d1 * SRK_HEAD_DIM + d2], v[d2], a0);
+            a1 = fmaf(ah[(d1 + 1) * SRK_HEAD_DIM + d2], v[d2], a1);
         }
-        __syncwarp();
+        o2[d1 >> 1] = make_float2(a0, a1);
     }
 }
 
@@ -234,10 +279,9 @@ static int grid_for(int64_t threads_needed) {
 cudaError_t launch_dwconv3x3_rows(const float* in, int ld_in, int c_in, const float* w, const float* scale, const float* shift,
                                   const float* stats, const float* gamma, const float* beta, const float* gate, int ld_gate, int c_gate,
                                   float* out, int ld_out, int C, int batch, int H, int W, int act_gelu, cudaStream_t stream) {
-    const int64_t total = static_cast<int64_t>(batch) * H * W * (C / 4);
-    if (total <= 0) return cudaSuccess;
-    dwconv3x3_rows_kernel<<<grid_for(total), 256, 0, stream>>>(in, ld_in, c_in, w, scale, shift, stats, gamma, beta, gate, ld_gate, c_gate,
-                                                               out, ld_out, C, batch, H, W, act_gelu);
+    if (batch <= 0) return cudaSuccess;
+    dwconv3x3_rows_kernel<<<batch * H, 256, 0, stream>>>(in, ld_in, c_in, w, scale, shift, stats, gamma, beta, gate, ld_gate, c_gate, out,
+                                                         ld_out, C, H, W, act_gelu);
     return cudaGetLastError();
 }
 
@@ -254,19 +298,21 @@ cudaError_t launch_dat_mix(const float* att, const float* conv, const float* cma
     return cudaGetLastError();
 }
 
-cudaError_t launch_channel_gram(const float* qkv, float* gram, int batch, int tokens_per_image, cudaStream_t stream) {
+static int gram_blocks(int tokens_per_image) { return (tokens_per_image + GRAM_TOK * GRAM_CHUNKS - 1) / (GRAM_TOK * GRAM_CHUNKS); }
+int channel_gram_ws_floats(int batch, int tokens_per_image) { return batch * gram_blocks(tokens_per_image) * SRK_HEADS * GRAM_STRIDE; }
+
+cudaError_t launch_channel_gram(const float* qkv, float* gram, float* ws, int batch, int tokens_per_image, cudaStream_t stream) {
     if (batch <= 0 || tokens_per_image <= 0) return cudaSuccess;
-    cudaError_t e = cudaMemsetAsync(gram, 0, static_cast<size_t>(batch) * SRK_HEADS * GRAM_STRIDE * sizeof(float), stream);
-    if (e != cudaSuccess) return e;
-    dim3 grid((tokens_per_image + GRAM_TOK - 1) / GRAM_TOK, SRK_HEADS, batch);
-    channel_gram_kernel<<<grid, 960, 0, stream>>>(qkv, gram, tokens_per_image);
+    const int nblk = gram_blocks(tokens_per_image);
+    channel_gram_kernel<<<dim3(nblk, batch), 224, 0, stream>>>(qkv, ws, tokens_per_image);
+    channel_gram_reduce_kernel<<<dim3(6, batch), 256, 0, stream>>>(ws, gram, nblk, SRK_HEADS * GRAM_STRIDE);
     return cudaGetLastError();
 }
 
 cudaError_t launch_channel_apply(const float* qkv, const float* attn, float* out, int batch, int tokens_per_image, cudaStream_t stream) {
     if (batch <= 0 || tokens_per_image <= 0) return cudaSuccess;
     dim3 grid((tokens_per_image + APPLY_TOK - 1) / APPLY_TOK, batch);
-    channel_apply_kernel<<<grid, 256, 0, stream>>>(qkv, attn, out, tokens_per_image);
+    channel_apply_kernel<<<grid, 192, 0, stream>>>(qkv, attn, out, tokens_per_image);
     return cudaGetLastError();
 }
 

@@ -90,6 +90,8 @@ cudaError_t launch_pixelshuffle_nhwc(const float* x, float* y, int batch, int he
                                      cudaStream_t stream);
 cudaError_t launch_stitch_accumulate(const float* tiles, float* E, float* Wt, const int32_t* tile_yx, int num_tiles,
                                      int channels, int tile_h, int tile_w, int out_h, int out_w, cudaStream_t stream);
+int cab_ws_floats(int batch, int tokens_per_image);
+int channel_gram_ws_floats(int batch, int tokens_per_image);
 cudaError_t launch_cab_gate_add(const float* y, float* out, float* sums, const float* w1, const float* b1, const float* w2,
                                 const float* b2, int hidden, float scale, int batch, int tokens_per_image, cudaStream_t stream);
 cudaError_t launch_dwconv3x3_rows(const float* in, int ld_in, int c_in, const float* w, const float* scale, const float* shift,
@@ -98,7 +100,7 @@ cudaError_t launch_dwconv3x3_rows(const float* in, int ld_in, int c_in, const fl
 cudaError_t launch_row_stats(const float* in, int ld_in, int c_in, int C, int64_t tokens, float eps, float* stats, cudaStream_t stream);
 cudaError_t launch_dat_mix(const float* att, const float* conv, const float* cmap, const float* w1, const float* b1, const float* w2,
                            float b2, int hidden, int mode, float* mix, int64_t tokens, int tokens_per_image, cudaStream_t stream);
-cudaError_t launch_channel_gram(const float* qkv, float* gram, int batch, int tokens_per_image, cudaStream_t stream);
+cudaError_t launch_channel_gram(const float* qkv, float* gram, float* ws, int batch, int tokens_per_image, cudaStream_t stream);
 cudaError_t launch_channel_apply(const float* qkv, const float* attn, float* out, int batch, int tokens_per_image, cudaStream_t stream);
 cudaError_t launch_stitch_normalize(float* E, const float* Wt, int channels, int64_t pixels, cudaStream_t stream);
 
