@@ -120,9 +120,25 @@ def _dist_setup(n_gpus: int):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("SRK_NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line
+        # keep stdout to the one JSON line: whatever NCCL_DEBUG level is in force, its log (incl. the version banner) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if "SRK_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["SRK_NCCL_DEBUG"]
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on stdout when the communicator is created: create it (first collective) with fd 1
+        # pointed at stderr so that stdout carries nothing but the JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            warm = torch.zeros(1, device="cuda")
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     return world, rank, local
 
 
