@@ -206,6 +206,8 @@ void srk_debug_set_timeline(void* device_buf);
 void srk_debug_set_stagger(int attn_cycles, int mlp_cycles);
 /* tuning: cycles the second query-half group of srk_window_attention_fwd starts behind the first (default 1500) */
 void srk_debug_set_winattn_stagger(int cycles);
+/* tuning: 0 disables programmatic dependent launch of the fused Swin kernels (default 1) */
+void srk_debug_set_pdl(int enabled);
 
 #ifdef __cplusplus
 }

@@ -109,6 +109,8 @@ def load():
     lib.srk_debug_set_stagger.restype = None
     lib.srk_debug_set_winattn_stagger.argtypes = [c_int32]
     lib.srk_debug_set_winattn_stagger.restype = None
+    lib.srk_debug_set_pdl.argtypes = [c_int32]
+    lib.srk_debug_set_pdl.restype = None
     for f in ("srk_swin_attn_fwd", "srk_swin_mlp_fwd", "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd",
               "srk_stitch_accumulate", "srk_stitch_normalize", "srk_linear_fwd", "srk_window_attention_fwd",
               "srk_window_attention_table_floats", "srk_cab_gate_add", "srk_dwconv3x3_rows_fwd", "srk_row_stats_fwd", "srk_dat_mix_fwd",
@@ -122,7 +124,7 @@ def load():
 
 EXPORTS = ("srk_abi_version", "srk_last_error_string", "srk_launch_count", "srk_swin_attn_fwd", "srk_swin_mlp_fwd",
            "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd", "srk_stitch_accumulate", "srk_stitch_normalize", "srk_debug_set_timeline", "srk_debug_set_stagger",
-           "srk_linear_fwd", "srk_window_attention_fwd", "srk_window_attention_table_floats", "srk_debug_set_winattn_stagger",
+           "srk_linear_fwd", "srk_window_attention_fwd", "srk_window_attention_table_floats", "srk_debug_set_winattn_stagger", "srk_debug_set_pdl",
            "srk_cab_gate_add", "srk_dwconv3x3_rows_fwd", "srk_row_stats_fwd", "srk_dat_mix_fwd", "srk_dat_channel_gram_fwd",
            "srk_dat_channel_apply_fwd", "srk_dat_channel_gram_ws_floats", "srk_cab_ws_floats")
 

@@ -34,6 +34,7 @@ int srk_abi_version(void) { return SRK_ABI_VERSION; }
 const char* srk_last_error_string(void) { return g_err; }
 void srk_debug_set_stagger(int attn_cycles, int mlp_cycles) { srk::g_stagger_attn = attn_cycles; srk::g_stagger_mlp = mlp_cycles; }
 void srk_debug_set_winattn_stagger(int cycles) { srk::g_stagger_winattn = cycles; }
+void srk_debug_set_pdl(int enabled) { srk::g_pdl = enabled; }
 void srk_debug_set_timeline(void* buf) { srk::g_timeline = static_cast<unsigned long long*>(buf); }
 int64_t srk_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 

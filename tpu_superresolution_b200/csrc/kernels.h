@@ -78,7 +78,7 @@ struct WinAttnParams {
 };
 
 extern unsigned long long* g_timeline;
-extern int g_stagger_attn, g_stagger_mlp, g_stagger_winattn;
+extern int g_stagger_attn, g_stagger_mlp, g_stagger_winattn, g_pdl;
 cudaError_t launch_swin_attn(const AttnParams& p, cudaStream_t stream);
 cudaError_t launch_swin_mlp(const MlpParams& p, cudaStream_t stream);
 cudaError_t launch_token_linear(const LinearParams& p, cudaStream_t stream);

@@ -45,6 +45,7 @@ constexpr float LOG2E = 1.4426950408889634f;
 #define SRK_TL(dbgptr, it, id) do { if ((dbgptr) != nullptr && blockIdx.x == 0 && (it) < 8) (dbgptr)[(it) * 64 + (id)] = clock64(); } while (0)
 unsigned long long* g_timeline = nullptr;
 int g_stagger_attn = 0, g_stagger_mlp = 0, g_stagger_winattn = 1500;
+int g_pdl = 1;
 
 // All CTAs of a launch run the same phase sequence; started together they hit their memory phases (tile load, tile
 // store) at the same time and leave HBM / L2 idle in between.  Skewing the start of CTA i by (i mod 4) * `cycles`
@@ -120,7 +121,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    for (int i = threadIdx.x; i < SRK_ATTN_VEC_FLOATS; i += blockDim.x) s_vec[i] = p.vec[i];
+    pdl_launch_dependents();
+    for (int i = threadIdx.x; i < SRK_ATTN_VEC_FLOATS; i += blockDim.x) s_vec[i] = p.vec[i];      // constants: before the PDL wait
     if (threadIdx.x == 0) {
         for (int i = 0; i < RING_N; ++i) { mbar_init(&bars[B_FULL + i], 1); mbar_init(&bars[B_EMPTY + i], 1); }
         mbar_init(&bars[B_XA], 128);         mbar_init(&bars[B_VTF], 1);    mbar_init(&bars[B_VTD], NROWTHREADS);
@@ -135,6 +137,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    if (warp != 0) pdl_wait();      // the weight producer starts streaming (constant) slabs while the previous kernel finishes
 
     if (warp == 0) {
         // ===================================================== weight producer
@@ -278,7 +281,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
             fence_proxy_async_smem();
             mbar_arrive(&bars[B_XA]);
         };
-        if (static_cast<int>(blockIdx.x) < p.n_tiles) ln_tile(blockIdx.x);
+        // (the first tile is normalised by the 8 row warps, idle at kernel start: twice the loads in flight while HBM is cold)
         uint32_t ph_drain = 0;
         bool first_tile = true;
         int uit = 0;
@@ -343,6 +346,13 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
             return geo.base[hf] + static_cast<int64_t>(yy) * p.W + xx;
         };
         stagger_start(p.stagger);
+        if (static_cast<int>(blockIdx.x) < p.n_tiles) {      // first tile's x image (later ones: the utility warps, one tile ahead)
+            set_tile_geom(p, blockIdx.x, geo);
+            ln_rows_to_image(p.x, p.ld_in, p.apply_ln, sbase + A_XA, cw8, lane, tok_of_row);
+            fence_proxy_async_smem();
+            named_bar_sync(1, NROWTHREADS);
+            if (g == 0) mbar_arrive(&bars[B_XA]);
+        }
 
         int it = 0;
         unsigned long long* dbg = threadIdx.x == 64 ? p.dbg : nullptr;
@@ -511,7 +521,8 @@ __global__ void __launch_bounds__(LNW ? NTHREADS : 320, 1) swin_mlp_kernel(const
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + MB_COUNT + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    for (int i = threadIdx.x; i < SRK_MLP_VEC_FLOATS; i += blockDim.x) s_vec[i] = p.vec[i];
+    pdl_launch_dependents();
+    for (int i = threadIdx.x; i < SRK_MLP_VEC_FLOATS; i += blockDim.x) s_vec[i] = p.vec[i];       // constants: before the PDL wait
     if (threadIdx.x == 0) {
         for (int i = 0; i < RING_N; ++i) { mbar_init(&bars[MB_FULL + i], 1); mbar_init(&bars[MB_EMPTY + i], 1); }
         mbar_init(&bars[MB_XA], 128);          mbar_init(&bars[MB_F1A], 1);           mbar_init(&bars[MB_F1B], 1);
@@ -525,6 +536,7 @@ __global__ void __launch_bounds__(LNW ? NTHREADS : 320, 1) swin_mlp_kernel(const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    if (warp != 0) pdl_wait();      // the weight producer starts streaming (constant) slabs while the previous kernel finishes
 
     if (warp == 0) {
         if (lane == 0) {
@@ -726,6 +738,23 @@ static int num_sms() {
     return g_num_sms;
 }
 
+// Launch with programmatic stream serialisation: the kernel may be scheduled while its predecessor in the stream is still running;
+// it orders itself with griddepcontrol.wait (umma.cuh: pdl_wait).
+template <typename P>
+static cudaError_t launch_pdl(void (*kern)(const P), int grid, int threads, size_t smem, cudaStream_t stream, const P& p) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
 cudaError_t launch_swin_attn(const AttnParams& p, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
@@ -734,8 +763,7 @@ cudaError_t launch_swin_attn(const AttnParams& p, cudaStream_t stream) {
         configured = true;
     }
     const int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
-    swin_attn_kernel<<<grid, K1_THREADS, K1_SMEM, stream>>>(p);
-    return cudaGetLastError();
+    return launch_pdl(swin_attn_kernel, grid, K1_THREADS, K1_SMEM, stream, p);
 }
 
 cudaError_t launch_swin_mlp(const MlpParams& p, cudaStream_t stream) {
@@ -747,9 +775,8 @@ cudaError_t launch_swin_mlp(const MlpParams& p, cudaStream_t stream) {
         configured = true;
     }
     const int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
-    if (p.n_tiles > 2 * grid) swin_mlp_kernel<true><<<grid, NTHREADS, K2_SMEM, stream>>>(p);
-    else                      swin_mlp_kernel<false><<<grid, 320, K2_SMEM, stream>>>(p);
-    return cudaGetLastError();
+    if (p.n_tiles > 2 * grid) return launch_pdl(swin_mlp_kernel<true>, grid, NTHREADS, K2_SMEM, stream, p);
+    return launch_pdl(swin_mlp_kernel<false>, grid, 320, K2_SMEM, stream, p);
 }
 
 }  // namespace srk

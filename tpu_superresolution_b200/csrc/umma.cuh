@@ -209,6 +209,13 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// launch_dependents: the next kernel in the stream may start being scheduled (its CTAs become resident as SMs free up and run
+// their prologue: barrier init, TMEM allocation, constant weights streaming into the ring).  wait: blocks until the previous kernel
+// has completed and its global writes are visible -- executed by every thread before it touches activations.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------ small helpers
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);   // .x = lo (low 16 bits), .y = hi
