@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
     for (int i = threadIdx.x; i < SRK_ATTN_VEC_FLOATS; i += blockDim.x) s_vec[i] = p.vec[i];      // constants: before the PDL wait
     if (threadIdx.x == 0) {
         for (int i = 0; i < RING_N; ++i) { mbar_init(&bars[B_FULL + i], 1); mbar_init(&bars[B_EMPTY + i], 1); }
-        mbar_init(&bars[B_XA], 128 + NROWTHREADS);         mbar_init(&bars[B_VTF], 1);    mbar_init(&bars[B_VTD], NROWTHREADS);
+        mbar_init(&bars[B_XA], 128);         mbar_init(&bars[B_VTF], 1);    mbar_init(&bars[B_VTD], NROWTHREADS);
         mbar_init(&bars[B_QKF0], 1);         mbar_init(&bars[B_QKF1], 1);   mbar_init(&bars[B_QKR0], 128); mbar_init(&bars[B_QKR1], 128);
         mbar_init(&bars[B_SF0], 1);          mbar_init(&bars[B_SF1], 1);
         mbar_init(&bars[B_PR0], 128);        mbar_init(&bars[B_PR1], 128);  mbar_init(&bars[B_OF], 1);
@@ -274,19 +274,14 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
             if (xx >= p.W) xx -= p.W;
             return geo.base[hf] + static_cast<int64_t>(yy) * p.W + xx;
         };
-        auto ln_tile = [&](int tile) {               // gather + normalise rows [0, 64) of the next tile -> x image (16 rows per warp);
-            set_tile_geom(p, tile, geo);             // rows [64, 128) are done by the row warps once they have stored this tile
-#pragma unroll 1
-            for (int k = 0; k < 2; ++k) {
-                uint2 hb[4][3];
-                ln_rows_hold<4>(p.x, p.ld_in, p.apply_ln, 16 * cwu + 8 * k, lane, tok_of_row, hb);
-                ln_rows_dump<4>(xa, 16 * cwu + 8 * k, lane, hb);
-            }
+        auto ln_tile = [&](int tile) {               // gather + normalise -> x image (32 rows per warp)
+            set_tile_geom(p, tile, geo);
+            ln_rows_to_image(p.x, p.ld_in, p.apply_ln, xa, 2 * cwu, lane, tok_of_row);
+            ln_rows_to_image(p.x, p.ld_in, p.apply_ln, xa, 2 * cwu + 1, lane, tok_of_row);
             fence_proxy_async_smem();
             mbar_arrive(&bars[B_XA]);
         };
         // (the first tile is normalised by the 8 row warps, idle at kernel start: twice the loads in flight while HBM is cold)
-        if (static_cast<int>(blockIdx.x) < p.n_tiles) mbar_arrive(&bars[B_XA]);
         uint32_t ph_drain = 0;
         bool first_tile = true;
         int uit = 0;
@@ -355,7 +350,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
             set_tile_geom(p, blockIdx.x, geo);
             ln_rows_to_image(p.x, p.ld_in, p.apply_ln, sbase + A_XA, cw8, lane, tok_of_row);
             fence_proxy_async_smem();
-            mbar_arrive(&bars[B_XA]);
+            named_bar_sync(1, NROWTHREADS);
+            if (g == 0) mbar_arrive(&bars[B_XA]);
         }
 
         int it = 0;
@@ -487,15 +483,6 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
             }
             named_bar_sync(1, NROWTHREADS);         // -> both groups (V^T image)
             SRK_TL(dbg, it, 27);
-            if (tile + static_cast<int>(gridDim.x) < p.n_tiles) {
-                // rows [64, 128) of the next tile's x image (8 per warp): these warps would otherwise idle until its V^T GEMM is done
-                set_tile_geom(p, tile + gridDim.x, geo);
-                uint2 hb[4][3];
-                ln_rows_hold<4>(p.x, p.ld_in, p.apply_ln, 64 + 8 * cw8, lane, tok_of_row, hb);
-                ln_rows_dump<4>(sbase + A_XA, 64 + 8 * cw8, lane, hb);
-                fence_proxy_async_smem();
-                mbar_arrive(&bars[B_XA]);
-            }
         }
     }
     tc_fence_before();
