@@ -19,21 +19,22 @@ constexpr uint32_t ATOM_A = 16384;      // 128 rows x 128 B: one k-atom of a 128
 // (gamma, beta) is folded into the following GEMM's weights / bias at pack time (packing.py).
 // Half-warp per token: 16 lanes x 3 float4 cover the 180 channels (45 float4) fully coalesced.  All 24 loads
 // of a lane are issued before the first use (one exposed memory latency per tile).
-template <typename TokFn>
-__device__ __forceinline__ void ln_rows_to_image(const float* __restrict__ x, int ld, int apply_ln, uint32_t xa, int cw8,
-                                                 int lane, TokFn tok_of_row) {
+// Core form: `row_ptr(pass)` returns the global address of the token row this lane's half-warp handles in `pass`
+// (image row cw8 * 16 + 2 * pass + (lane >> 4)), or nullptr for a padding row.  A single warp runs dependent scalar
+// code at one instruction per ~6 cycles, so callers keep the per-pass address arithmetic to an add or two.
+template <typename PtrFn>
+__device__ __forceinline__ void ln_rows_to_image_p(int apply_ln, uint32_t xa, int cw8, int lane, PtrFn row_ptr) {
     const int l16 = lane & 15;
     const bool live2 = l16 < 13;            // float4 index l16 + 32 < 45
     float4 v[8][3];
 #pragma unroll
     for (int pass = 0; pass < 8; ++pass) {
-        const int r = cw8 * 16 + pass * 2 + (lane >> 4);
-        const int64_t tok = tok_of_row(r);
-        const float4* src = reinterpret_cast<const float4*>(x + (tok >= 0 ? tok : 0) * ld) + l16;
+        const float* rp = row_ptr(pass);
+        const float4* src = reinterpret_cast<const float4*>(rp) + l16;
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        v[pass][0] = tok >= 0 ? __ldg(src) : z;
-        v[pass][1] = tok >= 0 ? __ldg(src + 16) : z;
-        v[pass][2] = (tok >= 0 && live2) ? __ldg(src + 32) : z;
+        v[pass][0] = rp ? __ldg(src) : z;
+        v[pass][1] = rp ? __ldg(src + 16) : z;
+        v[pass][2] = (rp && live2) ? __ldg(src + 32) : z;
     }
     // statistics of all 8 passes first, then the 4 butterfly rounds over all passes at once: the 16 shuffles of a
     // round are independent, so their latency overlaps instead of serialising 8 x 4 dependent steps
@@ -82,26 +83,33 @@ __device__ __forceinline__ void ln_rows_to_image(const float* __restrict__ x, in
             st_shared_v2(off + jj * ATOM_A, pack_bf16x2(w[jj].x, w[jj].y), pack_bf16x2(w[jj].z, w[jj].w));
     }
 }
+template <typename TokFn>
+__device__ __forceinline__ void ln_rows_to_image(const float* __restrict__ x, int ld, int apply_ln, uint32_t xa, int cw8,
+                                                 int lane, TokFn tok_of_row) {
+    ln_rows_to_image_p(apply_ln, xa, cw8, lane, [&](int pass) -> const float* {
+        const int64_t tok = tok_of_row(cw8 * 16 + pass * 2 + (lane >> 4));
+        return tok >= 0 ? x + tok * ld : nullptr;
+    });
+}
 
 
 // Split form of ln_rows_to_image for dedicated LayerNorm warps that run AHEAD of the GEMMs: ln_rows_hold() loads and
 // normalises NPASS x 2 token rows (half-warp per row) and keeps them as packed bf16 in registers (6 per row pair) while
 // the operand image is still being read by the previous tile's MMAs; ln_rows_dump() writes them into the image once it is
 // free -- the global-memory latency of the next tile is then off the critical path, only the dump (a few hundred cycles) is on it.
-template <int NPASS, typename TokFn>
-__device__ __forceinline__ void ln_rows_hold(const float* __restrict__ x, int ld, int apply_ln, int row0, int lane, TokFn tok_of_row,
-                                             uint2 (&held)[NPASS][3]) {
+template <int NPASS, typename PtrFn>
+__device__ __forceinline__ void ln_rows_hold_p(int apply_ln, int lane, PtrFn row_ptr, uint2 (&held)[NPASS][3]) {
     const int l16 = lane & 15;
     const bool live2 = l16 < 13;
     float4 v[NPASS][3];
 #pragma unroll
     for (int pass = 0; pass < NPASS; ++pass) {
-        const int64_t tok = tok_of_row(row0 + pass * 2 + (lane >> 4));
-        const float4* src = reinterpret_cast<const float4*>(x + (tok >= 0 ? tok : 0) * ld) + l16;
+        const float* rp = row_ptr(pass);
+        const float4* src = reinterpret_cast<const float4*>(rp) + l16;
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        v[pass][0] = tok >= 0 ? __ldg(src) : z;
-        v[pass][1] = tok >= 0 ? __ldg(src + 16) : z;
-        v[pass][2] = (tok >= 0 && live2) ? __ldg(src + 32) : z;
+        v[pass][0] = rp ? __ldg(src) : z;
+        v[pass][1] = rp ? __ldg(src + 16) : z;
+        v[pass][2] = (rp && live2) ? __ldg(src + 32) : z;
     }
     float s[NPASS], q[NPASS];
 #pragma unroll
@@ -143,6 +151,14 @@ __device__ __forceinline__ void ln_rows_hold(const float* __restrict__ x, int ld
 #pragma unroll
         for (int jj = 0; jj < 3; ++jj) held[pass][jj] = make_uint2(pack_bf16x2(w[jj].x, w[jj].y), pack_bf16x2(w[jj].z, w[jj].w));
     }
+}
+template <int NPASS, typename TokFn>
+__device__ __forceinline__ void ln_rows_hold(const float* __restrict__ x, int ld, int apply_ln, int row0, int lane, TokFn tok_of_row,
+                                             uint2 (&held)[NPASS][3]) {
+    ln_rows_hold_p<NPASS>(apply_ln, lane, [&](int pass) -> const float* {
+        const int64_t tok = tok_of_row(row0 + pass * 2 + (lane >> 4));
+        return tok >= 0 ? x + tok * ld : nullptr;
+    }, held);
 }
 template <int NPASS>
 __device__ __forceinline__ void ln_rows_dump(uint32_t xa, int row0, int lane, const uint2 (&held)[NPASS][3]) {

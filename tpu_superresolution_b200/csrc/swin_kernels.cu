@@ -28,7 +28,7 @@ namespace srk {
 
 constexpr int NTHREADS = 448;          // K2: producer + MMA + 8 row warps + 4 LayerNorm warps
 constexpr int NROWTHREADS = 256;
-constexpr int K1_THREADS = 448;        // K1: + 4 utility warps (q|k epilogues, next-tile normalisation)
+constexpr int K1_THREADS = 512;        // K1: + 4 utility warps (q|k epilogues, next-tile rows 0-63) + 2 LayerNorm warps (rows 64-127)
 constexpr uint32_t VT_ATOM = 24576;     // 192 rows x 128 B: one k-atom (64 keys) of the V^T image
 constexpr uint32_t RING_STAGE = 24576;  // largest weight slab (192 rows x 64 k)
 constexpr int RING_N = 3;
@@ -42,7 +42,11 @@ constexpr uint32_t IDESC_64x32 = umma_idesc_bf16(64, 32);
 constexpr float LOG2E = 1.4426950408889634f;
 
 // Optional per-CTA timeline (debug): CTA 0 writes clock64() at event `id` of its `it`-th tile.
+#ifdef SRK_NO_TIMELINE
+#define SRK_TL(dbgptr, it, id) do { } while (0)
+#else
 #define SRK_TL(dbgptr, it, id) do { if ((dbgptr) != nullptr && blockIdx.x == 0 && (it) < 8) (dbgptr)[(it) * 64 + (id)] = clock64(); } while (0)
+#endif
 unsigned long long* g_timeline = nullptr;
 int g_stagger_attn = 0, g_stagger_mlp = 0, g_stagger_winattn = 1500;
 int g_pdl = 1;
@@ -86,7 +90,7 @@ constexpr uint32_t LANE16 = 16u << 16;                // TMEM lane offset of the
 
 enum {  // K1 barrier slots
     B_FULL = 0, B_EMPTY = 3, B_XA = 6, B_VTF = 7, B_VTD = 8, B_QKF0 = 9, B_QKF1 = 10, B_QKR0 = 11, B_QKR1 = 12, B_SF0 = 13, B_SF1 = 14,
-    B_PR0 = 15, B_PR1 = 16, B_OF = 17, B_OR = 18, B_PJF = 19, B_DRAIN = 20, B_COUNT = 21
+    B_PR0 = 15, B_PR1 = 16, B_OF = 17, B_OR = 18, B_PJF = 19, B_DRAIN = 20, B_XAFREE = 21, B_COUNT = 22
 };
 
 struct TileGeom {
@@ -110,6 +114,109 @@ __device__ __forceinline__ void set_tile_geom(const AttnParams& p, int tile, Til
     }
 }
 
+// token index of tile row r (-1: padding window).  Selects instead of geo.x[hf]: a runtime index would put geo in local memory.
+__device__ __forceinline__ int64_t tile_tok(const AttnParams& p, const TileGeom& geo, int r) {
+    const bool hi = r >= 64;
+    const int tt = r & 63;
+    if (!(hi ? geo.valid[1] : geo.valid[0])) return static_cast<int64_t>(-1);
+    const int64_t base = hi ? geo.base[1] : geo.base[0];
+    if (p.mode == SRK_MODE_WINDOWS) return base + tt;
+    int yy = (hi ? geo.y0[1] : geo.y0[0]) + (tt >> 3);
+    if (yy >= p.H) yy -= p.H;
+    int xx = (hi ? geo.x0[1] : geo.x0[0]) + (tt & 7);
+    if (xx >= p.W) xx -= p.W;
+    return base + static_cast<int64_t>(yy) * p.W + xx;
+}
+
+// Row addresses of a 16-row batch (tile rows row0 .. row0 + 15, row0 a multiple of 16: two window rows of 8 tokens) for
+// ln_rows_to_image_p: this lane's row in pass p is token (ty0 + (p >> 2), 2 (p & 3) + (lane >> 4)) of the window, so
+// two row bases and four column offsets cover all eight passes -- one add per pass instead of the full index arithmetic.
+struct RowSrc16 {
+    const float* yrow[2];
+    int xo[4];
+    __device__ __forceinline__ const float* ptr(int pass) const { return yrow[pass >> 2] ? yrow[pass >> 2] + xo[pass & 3] : nullptr; }
+};
+__device__ __forceinline__ RowSrc16 make_row_src16(const AttnParams& p, const TileGeom& geo, int row0, int lane) {
+    RowSrc16 rs;
+    const bool hi = row0 >= 64;
+    const int tt0 = row0 & 63, sub = lane >> 4;
+    const int64_t base = hi ? geo.base[1] : geo.base[0];
+    if (!(hi ? geo.valid[1] : geo.valid[0])) {
+        rs.yrow[0] = rs.yrow[1] = nullptr;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rs.xo[k] = 0;
+    } else if (p.mode == SRK_MODE_WINDOWS) {
+        rs.yrow[0] = p.x + (base + tt0 + sub) * p.ld_in;
+        rs.yrow[1] = rs.yrow[0] + 8 * p.ld_in;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rs.xo[k] = 2 * k * p.ld_in;
+    } else {
+        int ya = (hi ? geo.y0[1] : geo.y0[0]) + (tt0 >> 3);
+        if (ya >= p.H) ya -= p.H;
+        int yb = ya + 1;
+        if (yb >= p.H) yb -= p.H;
+        rs.yrow[0] = p.x + (base + static_cast<int64_t>(ya) * p.W) * p.ld_in;
+        rs.yrow[1] = p.x + (base + static_cast<int64_t>(yb) * p.W) * p.ld_in;
+        const int x0 = (hi ? geo.x0[1] : geo.x0[0]) + sub;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int xx = x0 + 2 * k;
+            if (xx >= p.W) xx -= p.W;
+            rs.xo[k] = xx * p.ld_in;
+        }
+    }
+    return rs;
+}
+
+// One out-of-line copy of the 16-row LayerNorm -> image routine for the three roles that use it.
+static __device__ __noinline__ void k1_ln16_to_image(const float* y0, const float* y1, int xo0, int xo1, int xo2, int xo3, int apply_ln,
+                                                     uint32_t xa, int cw8, int lane) {
+    RowSrc16 rs;
+    rs.yrow[0] = y0; rs.yrow[1] = y1; rs.xo[0] = xo0; rs.xo[1] = xo1; rs.xo[2] = xo2; rs.xo[3] = xo3;
+    ln_rows_to_image_p(apply_ln, xa, cw8, lane, [&](int pass) { return rs.ptr(pass); });
+}
+__device__ __forceinline__ void k1_ln16(const AttnParams& p, const TileGeom& geo, uint32_t xa, int cw8, int lane) {
+    const RowSrc16 rs = make_row_src16(p, geo, 16 * cw8, lane);
+    k1_ln16_to_image(rs.yrow[0], rs.yrow[1], rs.xo[0], rs.xo[1], rs.xo[2], rs.xo[3], p.apply_ln, xa, cw8, lane);
+}
+
+// MMA-issue building blocks of K1, out of line: the kernel is ~200 KB of SASS, its first tile runs from a cold
+// instruction cache (2.5x slower than the steady state), and these bodies were inlined at 3 call sites each.
+// All are called by the whole MMA warp with uniform arguments (see umma_ss_w).  `cur` = ring stage | phase << 8.
+static __device__ __noinline__ uint32_t k1_gemm_k192(uint64_t* bars, uint32_t ring, uint32_t cur, uint32_t d_tmem, uint32_t img,
+                                                     uint32_t img_is_a, uint32_t idesc) {      // K = 192: 3 ring slabs x 4 k-steps
+    uint32_t stage = cur & 0xffu, phase = cur >> 8;
+#pragma unroll 1
+    for (int ka = 0; ka < 3; ++ka) {
+        mbar_wait(&bars[B_FULL + stage], phase);
+        tc_fence_after();
+        const uint32_t w = ring + stage * RING_STAGE, im = img + ka * ATOM_A;
+        const uint32_t a = img_is_a ? im : w, b = img_is_a ? w : im;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+            umma_ss_w(d_tmem, umma_desc_sw128(a + ks * 32), umma_desc_sw128(b + ks * 32), idesc, (ka | ks) != 0);
+        umma_commit_w(&bars[B_EMPTY + stage]);
+        if (++stage == RING_N) { stage = 0; phase ^= 1; }
+    }
+    return stage | (phase << 8);
+}
+// [q_h | k_h] = xhat * W^T, N = 64; the three k-atoms of W arrive as one ring stage
+static __device__ __noinline__ uint32_t k1_gemm_qk(uint64_t* bars, uint32_t ring, uint32_t cur, uint32_t acc, uint32_t xa, uint64_t* done_bar) {
+    uint32_t stage = cur & 0xffu, phase = cur >> 8;
+    mbar_wait(&bars[B_FULL + stage], phase);
+    tc_fence_after();
+    const uint32_t w = ring + stage * RING_STAGE;
+#pragma unroll
+    for (int ka = 0; ka < 3; ++ka)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+            umma_ss_w(acc, umma_desc_sw128(xa + ka * ATOM_A + ks * 32), umma_desc_sw128(w + ka * 8192 + ks * 32), IDESC_128x64, (ka | ks) != 0);
+    umma_commit_w(&bars[B_EMPTY + stage]);
+    if (++stage == RING_N) { stage = 0; phase ^= 1; }
+    umma_commit_w(done_bar);
+    return stage | (phase << 8);
+}
+
 __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -125,7 +232,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
     for (int i = threadIdx.x; i < SRK_ATTN_VEC_FLOATS; i += blockDim.x) s_vec[i] = p.vec[i];      // constants: before the PDL wait
     if (threadIdx.x == 0) {
         for (int i = 0; i < RING_N; ++i) { mbar_init(&bars[B_FULL + i], 1); mbar_init(&bars[B_EMPTY + i], 1); }
-        mbar_init(&bars[B_XA], 128);         mbar_init(&bars[B_VTF], 1);    mbar_init(&bars[B_VTD], NROWTHREADS);
+        mbar_init(&bars[B_XA], 192); mbar_init(&bars[B_XAFREE], 1);        mbar_init(&bars[B_VTF], 1);    mbar_init(&bars[B_VTD], NROWTHREADS);
         mbar_init(&bars[B_QKF0], 1);         mbar_init(&bars[B_QKF1], 1);   mbar_init(&bars[B_QKR0], 128); mbar_init(&bars[B_QKR1], 128);
         mbar_init(&bars[B_SF0], 1);          mbar_init(&bars[B_SF1], 1);
         mbar_init(&bars[B_PR0], 128);        mbar_init(&bars[B_PR1], 128);  mbar_init(&bars[B_OF], 1);
@@ -157,39 +264,17 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ===================================================== MMA issuer
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
+        // ===================================================== MMA issuer (warp-uniform: see umma_ss_w)
+        {
+            unsigned long long* mdbg = lane == 0 ? p.dbg : nullptr;
             uint32_t ph_xa = 0, ph_vtd = 0, ph_qkr[2] = {0, 0}, ph_pr[2] = {0, 0}, ph_or = 0;
             const uint32_t xa = sbase + A_XA, vt = sbase + A_VT, qki = sbase + A_QKI, ring = sbase + A_RING;
-            // one GEMM over K = 192: 3 ring slabs x 4 k-steps
+            uint32_t cur = 0;                   // weight ring cursor (stage | phase << 8)
             auto gemm_k192 = [&](uint32_t d_tmem, uint32_t img, bool img_is_a, uint32_t idesc) {
-                for (int ka = 0; ka < 3; ++ka) {
-                    mbar_wait(&bars[B_FULL + stage], phase);
-                    tc_fence_after();
-                    const uint32_t w = ring + stage * RING_STAGE, im = img + ka * ATOM_A;
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        umma_ss(d_tmem, umma_desc_sw128((img_is_a ? im : w) + ks * 32), umma_desc_sw128((img_is_a ? w : im) + ks * 32),
-                                idesc, (ka | ks) != 0);
-                    umma_commit(&bars[B_EMPTY + stage]);
-                    if (++stage == RING_N) { stage = 0; phase ^= 1; }
-                }
+                cur = k1_gemm_k192(bars, ring, cur, d_tmem, img, img_is_a ? 1u : 0u, idesc);
             };
-            auto gemm_qk = [&](int h) {        // [q_h | k_h] = xhat * W^T, N = 64; the three k-atoms of W arrive as one ring stage
-                mbar_wait(&bars[B_FULL + stage], phase);
-                tc_fence_after();
-                const uint32_t w = ring + stage * RING_STAGE;
-                const uint32_t acc = tmem + ((h & 1) ? TC_QK1 : TC_QK0);
-#pragma unroll
-                for (int ka = 0; ka < 3; ++ka)
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        umma_ss(acc, umma_desc_sw128(xa + ka * ATOM_A + ks * 32), umma_desc_sw128(w + ka * 8192 + ks * 32),
-                                IDESC_128x64, (ka | ks) != 0);
-                umma_commit(&bars[B_EMPTY + stage]);
-                if (++stage == RING_N) { stage = 0; phase ^= 1; }
-                umma_commit(&bars[B_QKF0 + (h & 1)]);
+            auto gemm_qk = [&](int h) {
+                cur = k1_gemm_qk(bars, ring, cur, tmem + ((h & 1) ? TC_QK1 : TC_QK0), xa, &bars[B_QKF0 + (h & 1)]);
             };
             auto issue_s = [&](int h) {        // S_w = q_h k_h^T per window w: two M = 64, N = 64 UMMAs sharing 64 columns
                 const uint32_t img = qki + (h & 1) * ATOM_A;
@@ -198,9 +283,9 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
                 for (int w = 0; w < 2; ++w)
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks)
-                        umma_ss(scol + w * LANE16, umma_desc_sw128(img + w * 8192 + ks * 32), umma_desc_sw128(img + w * 8192 + 64 + ks * 32),
+                        umma_ss_w(scol + w * LANE16, umma_desc_sw128(img + w * 8192 + ks * 32), umma_desc_sw128(img + w * 8192 + 64 + ks * 32),
                                 IDESC_64x64, ks != 0);
-                umma_commit(&bars[B_SF0 + (h & 1)]);
+                umma_commit_w(&bars[B_SF0 + (h & 1)]);
             };
             auto issue_pv = [&](int h) {       // O_h = P v_h per window: A = P (TMEM, aliases S), B = V^T rows of head h, keys of window w
                 const uint32_t pcol = tmem + ((h & 1) ? TC_S1 : TC_S0);
@@ -208,32 +293,34 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
                 for (int w = 0; w < 2; ++w)
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)
-                        umma_ts(tmem + TC_O + 32 * h + w * LANE16, pcol + w * LANE16 + 8 * kk,
+                        umma_ts_w(tmem + TC_O + 32 * h + w * LANE16, pcol + w * LANE16 + 8 * kk,
                                 umma_desc_sw128(vt + w * VT_ATOM + h * 4096 + kk * 32), IDESC_64x32, kk != 0);
             };
             int it = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-                SRK_TL(p.dbg, it, 32);
+                SRK_TL(mdbg, it, 32);
                 mbar_wait(&bars[B_XA], ph_xa); ph_xa ^= 1;
                 tc_fence_after();
-                SRK_TL(p.dbg, it, 33);
+                SRK_TL(mdbg, it, 33);
                 // ---- V^T = Wv * xhat^T : A = Wv slab (128 v-dims), B = x image (128 tokens)
                 gemm_k192(tmem + TC_VT0, xa, false, IDESC_128x128);
                 gemm_k192(tmem + TC_VT1, xa, false, IDESC_128x128);
-                umma_commit(&bars[B_VTF]);
-                SRK_TL(p.dbg, it, 34);
+                umma_commit_w(&bars[B_VTF]);
+                SRK_TL(mdbg, it, 34);
                 // ---- [q_0 | k_0] (its accumulator does not overlap the V^T accumulators), then, once those are drained, [q_1 | k_1]
                 gemm_qk(0);
-                mbar_wait(&bars[B_VTD], ph_vtd); ph_vtd ^= 1;
+                mbar_wait(&bars[B_VTD], ph_vtd); ph_vtd ^= 1;              // S0 / S1 / [q_1 | k_1] accumulators alias the V^T ones
                 tc_fence_after();
-                gemm_qk(1);
+#pragma unroll 1
                 for (int h = 0; h < 6; ++h) {
                     mbar_wait(&bars[B_QKR0 + (h & 1)], ph_qkr[h & 1]); ph_qkr[h & 1] ^= 1;   // image h written, accumulator h & 1 drained
                     tc_fence_after();
-                    SRK_TL(p.dbg, it, 35 + h);
+                    SRK_TL(mdbg, it, 35 + h);
                     issue_s(h);
-                    SRK_TL(p.dbg, it, 44 + h);
+                    SRK_TL(mdbg, it, 44 + h);
+                    if (h == 0) gemm_qk(1);                                // (after S0: the softmax warps are already waiting for it)
                     if (h + 2 < 6) gemm_qk(h + 2);                         // runs two heads ahead of the softmax
+                    if (h == 3) umma_commit_w(&bars[B_XAFREE]);            // last GEMM reading the x image: free once it completes
                     if (h >= 1) {
                         mbar_wait(&bars[B_PR0 + ((h - 1) & 1)], ph_pr[(h - 1) & 1]); ph_pr[(h - 1) & 1] ^= 1;
                         tc_fence_after();
@@ -243,18 +330,40 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
                 mbar_wait(&bars[B_PR1], ph_pr[1]); ph_pr[1] ^= 1;
                 tc_fence_after();
                 issue_pv(5);
-                umma_commit(&bars[B_OF]);
-                SRK_TL(p.dbg, it, 41);
+                umma_commit_w(&bars[B_OF]);
+                SRK_TL(mdbg, it, 41);
                 mbar_wait(&bars[B_OR], ph_or); ph_or ^= 1;
                 tc_fence_after();
-                SRK_TL(p.dbg, it, 42);
+                SRK_TL(mdbg, it, 42);
                 // ---- proj: A = O image (in the V^T region), B = Wproj slab (192 rows)
                 gemm_k192(tmem + TC_PROJ, vt, true, IDESC_128x192);
-                umma_commit(&bars[B_PJF]);
-                SRK_TL(p.dbg, it, 43);
+                umma_commit_w(&bars[B_PJF]);
+                SRK_TL(mdbg, it, 43);
             }
         }
         __syncwarp();
+    } else if (warp >= 14) {
+        // ===================================================== 2 LayerNorm warps: rows [64, 128) of the next tile's x image.
+        // 16 rows per warp are loaded and normalised into registers while the heads of the current tile run, dumped as
+        // soon as the last q|k GEMM has read the image, and followed by the other 16.
+        const int lw = warp - 14;
+        const uint32_t xa = sbase + A_XA;
+        uint32_t ph_free = 0;
+        TileGeom geo;
+        if (static_cast<int>(blockIdx.x) < p.n_tiles) mbar_arrive(&bars[B_XA]);      // first tile: the row warps do all of it
+        for (int tile = blockIdx.x; tile + static_cast<int>(gridDim.x) < p.n_tiles; tile += gridDim.x) {
+            set_tile_geom(p, tile + gridDim.x, geo);
+            uint2 hb[8][3];
+            {
+                const RowSrc16 rs = make_row_src16(p, geo, 64 + 32 * lw, lane);
+                ln_rows_hold_p<8>(p.apply_ln, lane, [&](int pass) { return rs.ptr(pass); }, hb);
+            }
+            mbar_wait(&bars[B_XAFREE], ph_free); ph_free ^= 1;
+            ln_rows_dump<8>(xa, 64 + 32 * lw, lane, hb);
+            k1_ln16(p, geo, xa, 4 + 2 * lw + 1, lane);
+            fence_proxy_async_smem();
+            mbar_arrive(&bars[B_XA]);
+        }
     } else if (warp >= 10) {
         // ===================================================== 128 utility threads: q|k epilogues and the next tile's x image
         const int cwu = warp - 10;                  // 0..3: 32-row slice of the LN phase
@@ -264,28 +373,18 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
         const uint32_t xa = sbase + A_XA, qki = sbase + A_QKI;
         uint32_t ph_qkf[2] = {0, 0};
         TileGeom geo;
-        auto tok_of_row = [&](int r) -> int64_t {
-            const int hf = r >> 6, tt = r & 63;
-            if (!geo.valid[hf]) return static_cast<int64_t>(-1);
-            if (p.mode == SRK_MODE_WINDOWS) return geo.base[hf] + tt;
-            int yy = geo.y0[hf] + (tt >> 3);
-            if (yy >= p.H) yy -= p.H;
-            int xx = geo.x0[hf] + (tt & 7);
-            if (xx >= p.W) xx -= p.W;
-            return geo.base[hf] + static_cast<int64_t>(yy) * p.W + xx;
-        };
-        auto ln_tile = [&](int tile) {               // gather + normalise -> x image (32 rows per warp)
+        auto tok_of_row = [&](int r) -> int64_t { return tile_tok(p, geo, r); };
+        int uit = 0;
+        unsigned long long* udbg = threadIdx.x == 320 ? p.dbg : nullptr;
+        auto ln_tile = [&](int tile) {               // gather + normalise rows [0, 64) of the next tile -> x image (16 rows per warp)
             set_tile_geom(p, tile, geo);
-            ln_rows_to_image(p.x, p.ld_in, p.apply_ln, xa, 2 * cwu, lane, tok_of_row);
-            ln_rows_to_image(p.x, p.ld_in, p.apply_ln, xa, 2 * cwu + 1, lane, tok_of_row);
+            k1_ln16(p, geo, xa, cwu, lane);
             fence_proxy_async_smem();
             mbar_arrive(&bars[B_XA]);
         };
         // (the first tile is normalised by the 8 row warps, idle at kernel start: twice the loads in flight while HBM is cold)
         uint32_t ph_drain = 0;
         bool first_tile = true;
-        int uit = 0;
-        unsigned long long* udbg = threadIdx.x == 320 ? p.dbg : nullptr;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             if (!first_tile) {      // the previous tile's output rows (staged over the V^T / q|k images) have left shared memory
                 mbar_wait(&bars[B_DRAIN], ph_drain); ph_drain ^= 1;
@@ -335,49 +434,51 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
         const uint32_t scol = g ? TC_S1 : TC_S0;
 
         TileGeom geo;
-        auto tok_of_row = [&](int r) -> int64_t {
-            const int hf = r >> 6, tt = r & 63;
-            if (!geo.valid[hf]) return static_cast<int64_t>(-1);
-            if (p.mode == SRK_MODE_WINDOWS) return geo.base[hf] + tt;
-            int yy = geo.y0[hf] + (tt >> 3);
-            if (yy >= p.H) yy -= p.H;
-            int xx = geo.x0[hf] + (tt & 7);
-            if (xx >= p.W) xx -= p.W;
-            return geo.base[hf] + static_cast<int64_t>(yy) * p.W + xx;
-        };
+        auto tok_of_row = [&](int r) -> int64_t { return tile_tok(p, geo, r); };
         stagger_start(p.stagger);
         if (static_cast<int>(blockIdx.x) < p.n_tiles) {      // first tile's x image (later ones: the utility warps, one tile ahead)
             set_tile_geom(p, blockIdx.x, geo);
-            ln_rows_to_image(p.x, p.ld_in, p.apply_ln, sbase + A_XA, cw8, lane, tok_of_row);
+            k1_ln16(p, geo, sbase + A_XA, cw8, lane);
             fence_proxy_async_smem();
             named_bar_sync(1, NROWTHREADS);
             if (g == 0) mbar_arrive(&bars[B_XA]);
         }
 
-        int it = 0;
-        unsigned long long* dbg = threadIdx.x == 64 ? p.dbg : nullptr;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-            SRK_TL(dbg, it, 0);
-            set_tile_geom(p, tile, geo);
-            // mask bits of this row (closed form of calculate_mask, network_swinir.py:216-237)
+        // Per-tile row state: window geometry and the mask bits of this row (closed form of calculate_mask,
+        // network_swinir.py:216-237).  ~300 dependent scalar instructions: computed for the NEXT tile while the proj GEMM
+        // runs (the row warps would only wait), not between the store and the next tile's first epilogue.
+        struct RowState { TileGeom geo; uint32_t mh, mw; const float* emask; };
+        auto prep = [&](int tile, RowState& st) {
+            set_tile_geom(p, tile, st.geo);
             const int gw_row = tile * 2 + half;
-            uint32_t mh = 0xffu, mw = 0xffu;
+            st.mh = 0xffu; st.mw = 0xffu;
             if (p.mask_mode == SRK_MASK_SHIFT) {
                 const int w = gw_row % p.nw_img;
                 const int wy = w / p.nwx, wx = w - wy * p.nwx;
                 auto reg = [&](int pos, int L) { return (pos >= L - 8 ? 1 : 0) + (pos >= L - p.shift ? 1 : 0); };
                 const int rh = reg(wy * 8 + (t >> 3), p.H), rw = reg(wx * 8 + (t & 7), p.W);
-                mh = 0; mw = 0;
+                st.mh = 0; st.mw = 0;
 #pragma unroll
                 for (int a = 0; a < 8; ++a) {
-                    mh |= (reg(wy * 8 + a, p.H) == rh ? 1u : 0u) << a;
-                    mw |= (reg(wx * 8 + a, p.W) == rw ? 1u : 0u) << a;
+                    st.mh |= (reg(wy * 8 + a, p.H) == rh ? 1u : 0u) << a;
+                    st.mw |= (reg(wx * 8 + a, p.W) == rw ? 1u : 0u) << a;
                 }
             }
-            const bool masked = (mh & mw) != 0xffu;
-            const float* emask = nullptr;
+            st.emask = nullptr;
             if (p.mask_mode == SRK_MASK_EXPLICIT && gw_row < p.total_windows)
-                emask = p.mask + (static_cast<int64_t>(gw_row % p.mask_nw) * 64 + t) * 64;
+                st.emask = p.mask + (static_cast<int64_t>(gw_row % p.mask_nw) * 64 + t) * 64;
+        };
+        RowState nxt;
+        if (static_cast<int>(blockIdx.x) < p.n_tiles) prep(blockIdx.x, nxt);
+
+        int it = 0;
+        unsigned long long* dbg = threadIdx.x == 64 ? p.dbg : nullptr;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            SRK_TL(dbg, it, 0);
+            geo = nxt.geo;
+            const uint32_t mh = nxt.mh, mw = nxt.mw;
+            const float* emask = nxt.emask;
+            const bool masked = (mh & mw) != 0xffu;
 
             // ---- phase 1: V^T accumulators -> V^T image (thread = v-dim row, group g = tokens 64 g .. 64 g + 63).
             //      The v bias is folded into the proj bias at pack time (softmax rows sum to one).
@@ -402,8 +503,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
             mbar_arrive(&bars[B_VTD]);
             SRK_TL(dbg, it, 3);
 
-            float inv_sum[3];
-#pragma unroll
+            float inv_sum0 = 0.f, inv_sum1 = 0.f, inv_sum2 = 0.f;      // (scalars: the loops over hh are not unrolled -- code size)
+#pragma unroll 1
             for (int hh = 0; hh < 3; ++hh) {
                 const int h = 2 * hh + g;
                 // ---- softmax of this row over the 64 keys of its own window (exp2 domain; log2 e folded into Wq, rpb)
@@ -443,7 +544,10 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
                     sum0 += e0; sum1 += e1;
                     pw[jx >> 1] = pack_bf16x2(e0, e1);
                 }
-                inv_sum[hh] = __frcp_rn(sum0 + sum1);
+                {
+                    const float is = __frcp_rn(sum0 + sum1);
+                    if (hh == 0) inv_sum0 = is; else if (hh == 1) inv_sum1 = is; else inv_sum2 = is;
+                }
                 tmem_st32(tmem + lanebase + scol, pw);                        // P aliases the first half of the S columns
                 tmem_st_wait();
                 tc_fence_before();
@@ -455,18 +559,19 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
             mbar_wait(&bars[B_OF], ph_of); ph_of ^= 1;
             tc_fence_after();
             SRK_TL(dbg, it, 23);
-#pragma unroll
+#pragma unroll 1
             for (int hh = 0; hh < 3; ++hh) {
                 const int h = 2 * hh + g;
                 uint32_t v[32];
                 tmem_ld32(tmem + lanebase + TC_O + 32 * h, v);
                 tmem_ld_wait();
-                store_row_chunks<false, true>(vt + (h >> 1) * ATOM_A, srow, (h & 1) * 4, v, nullptr, inv_sum[hh]);
+                store_row_chunks<false, true>(vt + (h >> 1) * ATOM_A, srow, (h & 1) * 4, v, nullptr, hh == 0 ? inv_sum0 : (hh == 1 ? inv_sum1 : inv_sum2));
             }
             tc_fence_before();
             fence_proxy_async_smem();
             mbar_arrive(&bars[B_OR]);
             SRK_TL(dbg, it, 24);
+            if (tile + static_cast<int>(gridDim.x) < p.n_tiles) prep(tile + gridDim.x, nxt);
 
             // ---- phase 5: proj accumulators + bias -> staged rows -> bulk (reduce-add) store; window reverse + un-shift
             //      are the destination addresses of the copies.  Staging = V^T + q|k image regions + a small tail.
@@ -476,9 +581,11 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
             stage_rows_and_bulk_store(tmem + TC_PROJ, lanebase, sm + A_VT, sm + A_TAIL, 28, s_vec + SRK_AV_BIAS_PROJ, p.y, p.ld_out,
                                       p.add_residual, q, g, lane, tok_of_row);
             tc_fence_before();
+            SRK_TL(dbg, it, 28);
             // the copies drain while the next tile's V^T / q|k GEMMs run; nobody may write the V^T or q|k images before that
             if (g == 0) {
                 bulk_wait_read0();
+                SRK_TL(dbg, it, 29);
                 mbar_arrive(&bars[B_DRAIN]);        // -> utility warps (q|k images)
             }
             named_bar_sync(1, NROWTHREADS);         // -> both groups (V^T image)

@@ -64,15 +64,16 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
 #ifndef SRK_WAIT_TIMEOUT_CYCLES
 #define SRK_WAIT_TIMEOUT_CYCLES (4000000000ll)   // ~2 s at 1.9 GHz: a deadlock traps instead of hanging the GPU
 #endif
+// (out of line: an inlined printf call site costs ~25 instructions and a stack frame at each of the ~20 waits of a kernel)
+static __device__ __noinline__ void mbar_timeout_trap(uint32_t bar, uint32_t parity) {
+    printf("srk: mbarrier wait timeout (block %d thread %d bar@%u parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+    __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > SRK_WAIT_TIMEOUT_CYCLES) {
-            printf("srk: mbarrier wait timeout (block %d thread %d bar@%u parity %u)\n", (int)blockIdx.x,
-                   (int)threadIdx.x, smem_u32(bar), parity);
-            __trap();
-        }
+        if (clock64() - t0 > SRK_WAIT_TIMEOUT_CYCLES) mbar_timeout_trap(smem_u32(bar), parity);
     }
 }
 
@@ -156,6 +157,42 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
         "}" ::"r"(d_tmem),
         "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Warp-uniform forms: the WHOLE warp executes the call with identical operands and one elected lane issues the
+// instruction.  Inside an `if (lane == 0)` region the compiler must assume divergent operands and wraps every
+// tcgen05.mma (its descriptors live in uniform registers) in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop
+// -- ~15 dependent instructions, ~90 cycles per MMA, which made the issuing thread the bottleneck of the fused
+// kernels.  Issued from convergent code the descriptors are computed on the uniform datapath directly.
+__device__ __forceinline__ void umma_ss_w(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_ts_w(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_w(uint64_t* bar) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}" ::"r"(smem_u32(bar))
         : "memory");
 }
 // mbarrier arrives once every previously issued tcgen05.mma of this thread has completed.
