@@ -114,8 +114,8 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) token_linear_kernel(const Line
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ===================================================== MMA issuer
-        if (lane == 0) {
+        // ===================================================== MMA issuer (the whole warp, uniform: see umma_ss_w)
+        {
             uint32_t stage_i = 0, phase = 0, ph_af = 0, ph_acce[2] = {1, 1}, nacc = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                 mbar_wait(&bars[LB_AFULL], ph_af); ph_af ^= 1;
@@ -131,13 +131,13 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) token_linear_kernel(const Line
                         const uint32_t a = sbase + L_A + ka * ATOM_A, b = sbase + L_RING + stage_i * LIN_SLAB;
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks)
-                            umma_ss(tmem + 256 * buf, umma_desc_sw128(a + ks * 32), umma_desc_sw128(b + ks * 32), LIN_IDESC, (ka | ks) != 0);
-                        umma_commit(&bars[LB_EMPTY + stage_i]);
+                            umma_ss_w(tmem + 256 * buf, umma_desc_sw128(a + ks * 32), umma_desc_sw128(b + ks * 32), LIN_IDESC, (ka | ks) != 0);
+                        umma_commit_w(&bars[LB_EMPTY + stage_i]);
                         if (++stage_i == LIN_RING_N) { stage_i = 0; phase ^= 1; }
                     }
-                    umma_commit(&bars[LB_ACCF + buf]);
+                    umma_commit_w(&bars[LB_ACCF + buf]);
                 }
-                umma_commit(&bars[LB_AEMPTY]);
+                umma_commit_w(&bars[LB_AEMPTY]);
             }
         }
         __syncwarp();

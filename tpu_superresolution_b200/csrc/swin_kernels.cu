@@ -21,6 +21,7 @@
 #include <stdint.h>
 
 #include "kernels.h"
+#define SRK_OOL_TIMEOUT 1      // see umma.cuh: mbar_wait
 #include "umma.cuh"
 #include "rowops.cuh"
 
@@ -47,6 +48,7 @@ constexpr float LOG2E = 1.4426950408889634f;
 #else
 #define SRK_TL(dbgptr, it, id) do { if ((dbgptr) != nullptr && blockIdx.x == 0 && (it) < 8) (dbgptr)[(it) * 64 + (id)] = clock64(); } while (0)
 #endif
+#define SRK_TL0(dbgptr, id) do { if (threadIdx.x == 64) SRK_TL(dbgptr, 0, id); } while (0)
 unsigned long long* g_timeline = nullptr;
 int g_stagger_attn = 0, g_stagger_mlp = 0, g_stagger_winattn = 1500;
 int g_pdl = 1;
@@ -228,6 +230,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+    SRK_TL0(p.dbg, 13);
     pdl_launch_dependents();
     for (int i = threadIdx.x; i < SRK_ATTN_VEC_FLOATS; i += blockDim.x) s_vec[i] = p.vec[i];      // constants: before the PDL wait
     if (threadIdx.x == 0) {
@@ -244,7 +247,9 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    SRK_TL0(p.dbg, 14);
     if (warp != 0) pdl_wait();      // the weight producer starts streaming (constant) slabs while the previous kernel finishes
+    SRK_TL0(p.dbg, 15);
 
     if (warp == 0) {
         // ===================================================== weight producer
@@ -592,8 +597,10 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
             SRK_TL(dbg, it, 27);
         }
     }
+    SRK_TL0(p.dbg, 16);
     tc_fence_before();
     __syncthreads();
+    SRK_TL0(p.dbg, 17);
     if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
@@ -617,6 +624,39 @@ enum { MB_FULL = 0, MB_EMPTY = 3, MB_XA = 6, MB_F1A = 7, MB_F1B = 8, MB_HR0 = 9,
 
 // LNW = true: 448 threads, 4 dedicated LayerNorm warps run one tile ahead (pays off from ~3 tiles per CTA); LNW = false: 320
 // threads, the 8 row warps normalise the next tile while fc2 runs (more registers for the row path, better for 1-2 tiles per CTA).
+// Out-of-line MMA-issue blocks of K2 (whole MMA warp, uniform arguments; `cur` = ring stage | phase << 8): see K1.
+static __device__ __noinline__ uint32_t k2_fc1_chunk(uint64_t* bars, uint32_t ring, uint32_t cur, uint32_t acc, uint32_t xa, uint64_t* done_bar) {
+    uint32_t stage = cur & 0xffu, phase = cur >> 8;
+#pragma unroll 1
+    for (int ka = 0; ka < 3; ++ka) {
+        mbar_wait(&bars[MB_FULL + stage], phase);
+        tc_fence_after();
+        const uint32_t a = xa + ka * ATOM_A, b = ring + stage * RING_STAGE;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+            umma_ss_w(acc, umma_desc_sw128(a + ks * 32), umma_desc_sw128(b + ks * 32), IDESC_128x128, (ka | ks) != 0);
+        umma_commit_w(&bars[MB_EMPTY + stage]);
+        if (++stage == RING_N) { stage = 0; phase ^= 1; }
+    }
+    umma_commit_w(done_bar);
+    return stage | (phase << 8);
+}
+static __device__ __noinline__ uint32_t k2_fc2_chunk(uint64_t* bars, uint32_t ring, uint32_t cur, uint32_t acc, uint32_t h_tmem, uint32_t first) {
+    uint32_t stage = cur & 0xffu, phase = cur >> 8;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        mbar_wait(&bars[MB_FULL + stage], phase);
+        tc_fence_after();
+        const uint32_t b = ring + stage * RING_STAGE;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+            umma_ts_w(acc, h_tmem + 64 * half + 8 * ks, umma_desc_sw128(b + ks * 32), IDESC_128x192, !(first && half == 0 && ks == 0));
+        umma_commit_w(&bars[MB_EMPTY + stage]);
+        if (++stage == RING_N) { stage = 0; phase ^= 1; }
+    }
+    return stage | (phase << 8);
+}
+
 template <bool LNW>
 __global__ void __launch_bounds__(LNW ? NTHREADS : 320, 1) swin_mlp_kernel(const MlpParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -628,6 +668,7 @@ __global__ void __launch_bounds__(LNW ? NTHREADS : 320, 1) swin_mlp_kernel(const
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + MB_COUNT + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+    SRK_TL0(p.dbg, 13);
     pdl_launch_dependents();
     for (int i = threadIdx.x; i < SRK_MLP_VEC_FLOATS; i += blockDim.x) s_vec[i] = p.vec[i];       // constants: before the PDL wait
     if (threadIdx.x == 0) {
@@ -643,7 +684,9 @@ __global__ void __launch_bounds__(LNW ? NTHREADS : 320, 1) swin_mlp_kernel(const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    SRK_TL0(p.dbg, 14);
     if (warp != 0) pdl_wait();      // the weight producer starts streaming (constant) slabs while the previous kernel finishes
+    SRK_TL0(p.dbg, 15);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -662,38 +705,18 @@ __global__ void __launch_bounds__(LNW ? NTHREADS : 320, 1) swin_mlp_kernel(const
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0, ph_xa = 0, ph_hr[3] = {0, 0, 0};
+        // ===================================================== MMA issuer (warp-uniform: see umma_ss_w)
+        {
+            uint32_t cur = 0, ph_xa = 0, ph_hr[3] = {0, 0, 0};     // cur: weight ring cursor (stage | phase << 8)
             uint32_t nchunk = 0;                              // fc1 chunk counter -> TMEM buffer parity
             const uint32_t xa = sbase + M_XA, ring = sbase + M_RING;
             auto fc1_chunk = [&]() {                            // 128 hidden units: A = x image, B = W1 slab (128 rows)
                 const uint32_t buf = nchunk & 1;
-                for (int ka = 0; ka < 3; ++ka) {
-                    mbar_wait(&bars[MB_FULL + stage], phase);
-                    tc_fence_after();
-                    const uint32_t a = xa + ka * ATOM_A, b = ring + stage * RING_STAGE;
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        umma_ss(tmem + (buf ? TC_F1B : TC_F1A), umma_desc_sw128(a + ks * 32), umma_desc_sw128(b + ks * 32), IDESC_128x128,
-                                (ka | ks) != 0);
-                    umma_commit(&bars[MB_EMPTY + stage]);
-                    if (++stage == RING_N) { stage = 0; phase ^= 1; }
-                }
-                umma_commit(&bars[buf ? MB_F1B : MB_F1A]);
+                cur = k2_fc1_chunk(bars, ring, cur, tmem + (buf ? TC_F1B : TC_F1A), xa, &bars[buf ? MB_F1B : MB_F1A]);
                 ++nchunk;
             };
             auto fc2_chunk = [&](uint32_t buf, bool first) {    // K = 128 hidden units of one chunk: A = H (TMEM), B = two W2 slabs
-                for (int half = 0; half < 2; ++half) {
-                    mbar_wait(&bars[MB_FULL + stage], phase);
-                    tc_fence_after();
-                    const uint32_t b = ring + stage * RING_STAGE;
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        umma_ts(tmem + TC_F2, tmem + (buf ? TC_F1B : TC_F1A) + 64 * half + 8 * ks, umma_desc_sw128(b + ks * 32), IDESC_128x192,
-                                !(first && half == 0 && ks == 0));
-                    umma_commit(&bars[MB_EMPTY + stage]);
-                    if (++stage == RING_N) { stage = 0; phase ^= 1; }
-                }
+                cur = k2_fc2_chunk(bars, ring, cur, tmem + TC_F2, tmem + (buf ? TC_F1B : TC_F1A), first ? 1u : 0u);
             };
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                 mbar_wait(&bars[MB_XA], ph_xa); ph_xa ^= 1;
@@ -705,14 +728,14 @@ __global__ void __launch_bounds__(LNW ? NTHREADS : 320, 1) swin_mlp_kernel(const
                 tc_fence_after();
                 fc2_chunk(b0, true);
                 fc1_chunk();                                                   // chunk 2 -> buffer b0 (after fc2 consumed H of chunk 0)
-                umma_commit(&bars[MB_XAFREE]);                                 // all fc1 GEMMs issued: the x image is free once they complete
+                umma_commit_w(&bars[MB_XAFREE]);                               // all fc1 GEMMs issued: the x image is free once they complete
                 mbar_wait(&bars[MB_HR1], ph_hr[1]); ph_hr[1] ^= 1;
                 tc_fence_after();
                 fc2_chunk(b0 ^ 1, false);
                 mbar_wait(&bars[MB_HR2], ph_hr[2]); ph_hr[2] ^= 1;
                 tc_fence_after();
                 fc2_chunk(b0, false);
-                umma_commit(&bars[MB_F2]);
+                umma_commit_w(&bars[MB_F2]);
             }
         }
         __syncwarp();
@@ -826,8 +849,10 @@ __global__ void __launch_bounds__(LNW ? NTHREADS : 320, 1) swin_mlp_kernel(const
         }
         bulk_wait_read0();          // shared memory must outlive the bulk copies that read it
     }
+    SRK_TL0(p.dbg, 16);
     tc_fence_before();
     __syncthreads();
+    SRK_TL0(p.dbg, 17);
     if (warp == 1) tmem_dealloc(tmem, 512);
 }
 

@@ -61,10 +61,16 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// warp-uniform probe: every lane gets the same answer (a phase that any lane saw complete is complete)
+__device__ __forceinline__ bool mbar_test_wait_w(uint64_t* bar, uint32_t parity) {
+    return __any_sync(0xffffffffu, mbar_test_wait(bar, parity)) != 0;
+}
 #ifndef SRK_WAIT_TIMEOUT_CYCLES
 #define SRK_WAIT_TIMEOUT_CYCLES (4000000000ll)   // ~2 s at 1.9 GHz: a deadlock traps instead of hanging the GPU
 #endif
-// (out of line: an inlined printf call site costs ~25 instructions and a stack frame at each of the ~20 waits of a kernel)
+// With SRK_OOL_TIMEOUT (defined by a translation unit before this header) the timeout report is an out-of-line call: an inlined
+// printf site costs ~25 instructions at each of the ~20 waits of a kernel, which matters for the 130+ KB fused Swin kernels (cold
+// instruction cache on the first tile).  The window-attention kernel is faster with the inline form (the call costs it stack spills).
 static __device__ __noinline__ void mbar_timeout_trap(uint32_t bar, uint32_t parity) {
     printf("srk: mbarrier wait timeout (block %d thread %d bar@%u parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
     __trap();
@@ -73,7 +79,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
+#ifndef SRK_OOL_TIMEOUT
+        if (clock64() - t0 > SRK_WAIT_TIMEOUT_CYCLES) {
+            printf("srk: mbarrier wait timeout (block %d thread %d bar@%u parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar), parity);
+            __trap();
+        }
+#else
         if (clock64() - t0 > SRK_WAIT_TIMEOUT_CYCLES) mbar_timeout_trap(smem_u32(bar), parity);
+#endif
     }
 }
 

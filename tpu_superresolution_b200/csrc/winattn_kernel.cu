@@ -227,8 +227,8 @@ __global__ void __launch_bounds__(320, 1) winattn_kernel(const WinAttnParams p) 
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ===================================================== MMA issuer
-        if (lane == 0) {
+        // ===================================================== MMA issuer (the whole warp, uniform: see umma_ss_w)
+        {
             constexpr uint32_t IDESC_S = umma_idesc_bf16(128, NCH);
             constexpr uint32_t IDESC_PV = umma_idesc_bf16_bmn(128, 32);
             // Event-driven: each query-half group g walks its own sequence of (item, head, key chunk) steps -- S = Q K^T when its
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(320, 1) winattn_kernel(const WinAttnParams p) 
                     const int k = k_g[g];
                     const uint32_t s = k % NSETS;
                     if (k > k_full) {                       // first touch of this item's set: its images must have landed
-                        if (!mbar_test_wait(&bars[W_FULL + s], (k / NSETS) & 1)) continue;
+                        if (!mbar_test_wait_w(&bars[W_FULL + s], (k / NSETS) & 1)) continue;
                         k_full = k;
                         tc_fence_after();
                     }
@@ -257,25 +257,25 @@ __global__ void __launch_bounds__(320, 1) winattn_kernel(const WinAttnParams p) 
                     const int hh = hh_g[g], c = c_g[g];
                     if (st_g[g] == 0) {
                         if (c == 0) {       // the group has drained the previous O accumulator (it aliases S when NCH = 256)
-                            if (!mbar_test_wait(&bars[W_FREE + g], ph_free[g])) continue;
+                            if (!mbar_test_wait_w(&bars[W_FREE + g], ph_free[g])) continue;
                             ph_free[g] ^= 1;
                             tc_fence_after();
                         }
 #pragma unroll
                         for (int ks = 0; ks < 2; ++ks)
-                            umma_ss(tmem + 256 * g, umma_desc_sw128(set + C::Q_OFF + g * 16384 + 64 * hh + 32 * ks),
+                            umma_ss_w(tmem + 256 * g, umma_desc_sw128(set + C::Q_OFF + g * 16384 + 64 * hh + 32 * ks),
                                     umma_desc_sw128(set + C::K_OFF + c * NCH * 128 + 64 * hh + 32 * ks), IDESC_S, ks);
-                        umma_commit(&bars[W_SF + g]);
+                        umma_commit_w(&bars[W_SF + g]);
                         st_g[g] = 1;
                     } else {
-                        if (!mbar_test_wait(&bars[W_PR + g], ph_pr[g])) continue;
+                        if (!mbar_test_wait_w(&bars[W_PR + g], ph_pr[g])) continue;
                         ph_pr[g] ^= 1;
                         tc_fence_after();
 #pragma unroll
                         for (int kk = 0; kk < NCH / 16; ++kk)
-                            umma_ts(tmem + 256 * g + TC_OACC, tmem + 256 * g + 8 * kk,
+                            umma_ts_w(tmem + 256 * g + TC_OACC, tmem + 256 * g + 8 * kk,
                                     umma_desc_sw128_mn(set + C::V_OFF + (c * NCH + 16 * kk) * 128 + 64 * hh), IDESC_PV, (c | kk) != 0);
-                        umma_commit(&bars[W_OF + g]);
+                        umma_commit_w(&bars[W_OF + g]);
                         st_g[g] = 0;
                         if (++c_g[g] == NCHUNKS) {
                             c_g[g] = 0;
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(320, 1) winattn_kernel(const WinAttnParams p) 
                                 hh_g[g] = 0;
                                 if (++done[k & 1] == 2) {
                                     done[k & 1] = 0;
-                                    umma_commit(&bars[W_EMPTY + s]);
+                                    umma_commit_w(&bars[W_EMPTY + s]);
                                 }
                                 ++k_g[g];
                                 item_g[g] += gridDim.x;
