@@ -189,6 +189,19 @@ int srk_dat_channel_apply_fwd(const float* qkv, const float* attn, float* out, i
  * (network_swinir.py:580-588). */
 int srk_pixelshuffle_nhwc_fwd(const float* x, float* y, int32_t batch, int32_t height, int32_t width,
                               int32_t out_channels, int32_t r, void* stream);
+/* The same with the preceding convolution's bias added on the way (bias[in_channel], may be NULL): the Upsample
+ * stage is [conv, PixelShuffle] (network_swinir.py:580-588) and the conv is run without bias. */
+int srk_pixelshuffle_nhwc_bias_fwd(const float* x, const float* bias, float* y, int32_t batch, int32_t height, int32_t width,
+                                   int32_t out_channels, int32_t r, void* stream);
+
+/* y[p, c] = act(x[p, c] + bias[c]) + residual[p, c] on channels-last activations (p < pixels, c < channels).
+ * The tail of every conv of the reference networks: conv bias, then LeakyReLU (conv_before_upsample,
+ * network_swinir.py:722-723) or the residual add (RSTB: `self.patch_embed(self.conv(...)) + x`, :501; the long skip,
+ * :829).  bias / residual may be NULL; y may alias x or residual. */
+#define SRK_ACT_NONE 0
+#define SRK_ACT_LEAKY_RELU 1
+int srk_bias_act_add_nhwc(const float* x, const float* bias, const float* residual, float* y, int64_t pixels, int32_t channels,
+                          int32_t act, float slope, void* stream);
 
 /* Weighted tile accumulation for the overlapping-tile stitcher (BASELINE.json configs[4]):
  * E[:, y0:y0+th, x0:x0+tw] += tile, Wt[y0:.., x0:..] += 1  (tiles of one launch must not overlap). */

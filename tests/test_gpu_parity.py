@@ -61,6 +61,39 @@ def test_pixelshuffle_kernel_bit_exact(r, shape):
     assert np.array_equal(srk.PixelShuffle(2)(ps_in).cpu().numpy(), g["ps"])
 
 
+@pytest.mark.parametrize("r,shape", [(2, (2, 16, 5, 7)), (2, (1, 256, 9, 4)), (3, (1, 27, 4, 5))])
+def test_pixelshuffle_with_conv_bias_bit_exact(r, shape):
+    # Upsample runs its conv bias-free and the shuffle adds the bias on the way: same fp32 add, moved
+    x = torch.randn(shape, device="cuda").contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(shape[1], device="cuda")
+    y = srk.PixelShuffle(r)(x, bias=bias)
+    ref = O.pixel_shuffle((x + bias.view(1, -1, 1, 1)).cpu(), r)
+    assert torch.equal(y.cpu(), ref)
+
+
+@pytest.mark.parametrize("pixels,C", [(1, 4), (37, 180), (16 * 64 * 64, 180), (513, 3), (1000, 64)])
+@pytest.mark.parametrize("act", [0, 1])
+@pytest.mark.parametrize("use_bias,use_res", [(True, True), (True, False), (False, True)])
+def test_bias_act_add_kernel_bit_exact(pixels, C, act, use_bias, use_res):
+    from tpu_superresolution_b200 import _lib as L
+    g = torch.Generator(device="cpu").manual_seed(pixels * 7 + C)
+    x = torch.randn(pixels, C, generator=g).cuda()
+    bias = torch.randn(C, generator=g).cuda() if use_bias else None
+    res = torch.randn(pixels, C, generator=g).cuda() if use_res else None
+    ref = x.clone()
+    if bias is not None:
+        ref = ref + bias
+    if act == 1:
+        ref = torch.where(ref > 0, ref, ref * 0.2)
+    if res is not None:
+        ref = ref + res
+    y = torch.empty_like(x)
+    L.bias_act_add_nhwc(x, y, pixels=pixels, channels=C, bias=bias, residual=res, act=act, slope=0.2)
+    assert torch.equal(y, ref)
+    L.bias_act_add_nhwc(x, x, pixels=pixels, channels=C, bias=bias, residual=res, act=act, slope=0.2)      # in place
+    assert torch.equal(x, ref)
+
+
 @pytest.mark.parametrize("ntok", [64, 128, 1000, 128 * 149 + 5])
 def test_mlp_kernel(ntok):
     sd = _stress_sd()

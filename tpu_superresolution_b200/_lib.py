@@ -86,6 +86,8 @@ def load():
     lib.srk_swin_mlp_fwd.argtypes = [POINTER(MlpDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.srk_layernorm_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]
     lib.srk_pixelshuffle_nhwc_fwd.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
+    lib.srk_pixelshuffle_nhwc_bias_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
+    lib.srk_bias_act_add_nhwc.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, ctypes.c_float, c_void_p]
     lib.srk_stitch_accumulate.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                           c_int32, c_int32, c_void_p]
     lib.srk_stitch_normalize.argtypes = [c_void_p, c_void_p, c_int32, c_int64, c_void_p]
@@ -111,7 +113,7 @@ def load():
     lib.srk_debug_set_winattn_stagger.restype = None
     lib.srk_debug_set_pdl.argtypes = [c_int32]
     lib.srk_debug_set_pdl.restype = None
-    for f in ("srk_swin_attn_fwd", "srk_swin_mlp_fwd", "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd",
+    for f in ("srk_swin_attn_fwd", "srk_swin_mlp_fwd", "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd", "srk_pixelshuffle_nhwc_bias_fwd", "srk_bias_act_add_nhwc",
               "srk_stitch_accumulate", "srk_stitch_normalize", "srk_linear_fwd", "srk_window_attention_fwd",
               "srk_window_attention_table_floats", "srk_cab_gate_add", "srk_dwconv3x3_rows_fwd", "srk_row_stats_fwd", "srk_dat_mix_fwd",
               "srk_dat_channel_gram_fwd", "srk_dat_channel_apply_fwd", "srk_dat_channel_gram_ws_floats", "srk_cab_ws_floats"):
@@ -123,7 +125,7 @@ def load():
 
 
 EXPORTS = ("srk_abi_version", "srk_last_error_string", "srk_launch_count", "srk_swin_attn_fwd", "srk_swin_mlp_fwd",
-           "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd", "srk_stitch_accumulate", "srk_stitch_normalize", "srk_debug_set_timeline", "srk_debug_set_stagger",
+           "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd", "srk_pixelshuffle_nhwc_bias_fwd", "srk_bias_act_add_nhwc", "srk_stitch_accumulate", "srk_stitch_normalize", "srk_debug_set_timeline", "srk_debug_set_stagger",
            "srk_linear_fwd", "srk_window_attention_fwd", "srk_window_attention_table_floats", "srk_debug_set_winattn_stagger", "srk_debug_set_pdl",
            "srk_cab_gate_add", "srk_dwconv3x3_rows_fwd", "srk_row_stats_fwd", "srk_dat_mix_fwd", "srk_dat_channel_gram_fwd",
            "srk_dat_channel_apply_fwd", "srk_dat_channel_gram_ws_floats", "srk_cab_ws_floats")
@@ -178,11 +180,30 @@ def layernorm(x, y, w, b, *, num_tokens, ld_in, ld_out) -> None:
         _check(lib.srk_layernorm_fwd(x.data_ptr(), y.data_ptr(), w.data_ptr(), b.data_ptr(), num_tokens, ld_in, ld_out, _stream()), lib)
 
 
-def pixelshuffle_nhwc(x, y, *, batch, height, width, out_channels, r) -> None:
+def pixelshuffle_nhwc(x, y, *, batch, height, width, out_channels, r, bias=None) -> None:
     lib = load()
     _require_cuda_f32(x, y)
+    if bias is not None:
+        _require_cuda_f32(bias)
     with _timed("pixelshuffle"):
-        _check(lib.srk_pixelshuffle_nhwc_fwd(x.data_ptr(), y.data_ptr(), batch, height, width, out_channels, r, _stream()), lib)
+        _check(lib.srk_pixelshuffle_nhwc_bias_fwd(x.data_ptr(), bias.data_ptr() if bias is not None else None, y.data_ptr(), batch,
+                                                  height, width, out_channels, r, _stream()), lib)
+
+
+ACT_NONE, ACT_LEAKY_RELU = 0, 1
+
+
+def bias_act_add_nhwc(x, y, *, pixels, channels, bias=None, residual=None, act=ACT_NONE, slope=0.0) -> None:
+    """y[p, c] = act(x[p, c] + bias[c]) + residual[p, c] (include/srk.h: srk_bias_act_add_nhwc); y may alias x / residual."""
+    lib = load()
+    _require_cuda_f32(x, y)
+    for t in (bias, residual):
+        if t is not None:
+            _require_cuda_f32(t)
+    with _timed("bias_act_add"):
+        _check(lib.srk_bias_act_add_nhwc(x.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                         residual.data_ptr() if residual is not None else None, y.data_ptr(), pixels, channels, act,
+                                         float(slope), _stream()), lib)
 
 
 def stitch_accumulate(tiles, E, Wt, tile_yx, *, channels, tile_h, tile_w, out_h, out_w) -> None:

@@ -70,8 +70,8 @@ cudaError_t launch_layernorm(const float* x, float* y, const float* w, const flo
 // ---- PixelShuffle(2) on NHWC: out[b, 2h+i, 2w+j, c] = in[b, h, w, 4c + 2i + j]   (network_swinir.py:585)
 // One float4 load = the 4 sub-pixels of channel c; a group of `oc` lanes reads 16*oc contiguous bytes and writes
 // four oc*4-byte contiguous runs.  Generic r via the scalar path.
-__global__ void __launch_bounds__(256) pixelshuffle2_nhwc_kernel(const float4* __restrict__ x, float* __restrict__ y,
-                                                                 int64_t in_pixels, int height, int width, int oc) {
+__global__ void __launch_bounds__(256) pixelshuffle2_nhwc_kernel(const float4* __restrict__ x, const float4* __restrict__ bias,
+                                                                 float* __restrict__ y, int64_t in_pixels, int height, int width, int oc) {
     const int64_t total = in_pixels * oc;
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -79,7 +79,8 @@ __global__ void __launch_bounds__(256) pixelshuffle2_nhwc_kernel(const float4* _
         const int c = static_cast<int>(i - pix * oc);
         const int w = static_cast<int>(pix % width);
         const int64_t bh = pix / width;                      // b * height + h
-        const float4 v = __ldg(x + i);
+        float4 v = __ldg(x + i);
+        if (bias) { const float4 b = __ldg(bias + c); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }   // conv bias of channels 4c..4c+3
         float* o = y + ((bh * 2) * (2 * static_cast<int64_t>(width)) + 2 * w) * oc + c;
         o[0] = v.x;
         o[oc] = v.y;
@@ -88,9 +89,9 @@ __global__ void __launch_bounds__(256) pixelshuffle2_nhwc_kernel(const float4* _
     }
 }
 
-__global__ void __launch_bounds__(256) pixelshuffle_nhwc_generic_kernel(const float* __restrict__ x, float* __restrict__ y,
-                                                                        int64_t out_elems, int height, int width, int oc,
-                                                                        int r) {
+__global__ void __launch_bounds__(256) pixelshuffle_nhwc_generic_kernel(const float* __restrict__ x, const float* __restrict__ bias,
+                                                                        float* __restrict__ y, int64_t out_elems, int height, int width,
+                                                                        int oc, int r) {
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < out_elems;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int c = static_cast<int>(i % oc);
@@ -100,26 +101,69 @@ __global__ void __launch_bounds__(256) pixelshuffle_nhwc_generic_kernel(const fl
         const int oh = static_cast<int>(t % (static_cast<int64_t>(height) * r));
         const int64_t b = t / (static_cast<int64_t>(height) * r);
         const int h = oh / r, ii = oh % r, w = ow / r, jj = ow % r;
-        y[i] = __ldg(x + ((b * height + h) * width + w) * (static_cast<int64_t>(oc) * r * r) + c * r * r + ii * r + jj);
+        const int ic = c * r * r + ii * r + jj;
+        y[i] = __ldg(x + ((b * height + h) * width + w) * (static_cast<int64_t>(oc) * r * r) + ic) + (bias ? __ldg(bias + ic) : 0.f);
     }
 }
 
-cudaError_t launch_pixelshuffle_nhwc(const float* x, float* y, int batch, int height, int width, int out_channels, int r,
-                                     cudaStream_t stream) {
+cudaError_t launch_pixelshuffle_nhwc(const float* x, const float* bias, float* y, int batch, int height, int width, int out_channels,
+                                     int r, cudaStream_t stream) {
     const int64_t in_pixels = static_cast<int64_t>(batch) * height * width;
     if (in_pixels == 0) return cudaSuccess;
     if (r == 2) {
         const int64_t total = in_pixels * out_channels;
         const int64_t blocks = (total + 255) / 256;
         const int grid = static_cast<int>(blocks < 148 * 32 ? blocks : 148 * 32);
-        pixelshuffle2_nhwc_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(x), y, in_pixels, height, width,
-                                                            out_channels);
+        pixelshuffle2_nhwc_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(bias), y,
+                                                            in_pixels, height, width, out_channels);
     } else {
         const int64_t total = in_pixels * out_channels * r * r;
         const int64_t blocks = (total + 255) / 256;
         const int grid = static_cast<int>(blocks < 148 * 32 ? blocks : 148 * 32);
-        pixelshuffle_nhwc_generic_kernel<<<grid, 256, 0, stream>>>(x, y, total, height, width, out_channels, r);
+        pixelshuffle_nhwc_generic_kernel<<<grid, 256, 0, stream>>>(x, bias, y, total, height, width, out_channels, r);
     }
+    return cudaGetLastError();
+}
+
+// ---- y = act(x + bias[c]) + residual on channels-last activations ([pixels, C] rows): the per-channel bias of a
+// library convolution, an optional LeakyReLU and the block's residual add in one pass (torch runs these as a
+// non-vectorised broadcast add plus one more elementwise kernel per operation).  y may alias x or residual.
+template <bool VEC>
+__global__ void __launch_bounds__(256) bias_act_add_kernel(const float* x, const float* __restrict__ bias, const float* residual,
+                                                           float* y, int64_t total, int channels, int act, float slope) {
+    const int64_t n = VEC ? total / 4 : total;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        if (VEC) {
+            const int c = static_cast<int>((i * 4) % channels);
+            float4 v = reinterpret_cast<const float4*>(x)[i];
+            if (bias) { const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c)); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
+            if (act == 1) {
+                v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
+                v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
+            }
+            if (residual) { const float4 r = reinterpret_cast<const float4*>(residual)[i]; v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
+            reinterpret_cast<float4*>(y)[i] = v;
+        } else {
+            float v = x[i];
+            if (bias) v += __ldg(bias + static_cast<int>(i % channels));
+            if (act == 1) v = v > 0.f ? v : v * slope;
+            if (residual) v += residual[i];
+            y[i] = v;
+        }
+    }
+}
+
+cudaError_t launch_bias_act_add(const float* x, const float* bias, const float* residual, float* y, int64_t pixels, int channels,
+                                int act, float slope, cudaStream_t stream) {
+    const int64_t total = pixels * channels;
+    if (total <= 0) return cudaSuccess;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    const bool vec = (channels % 4 == 0) && al16(x) && al16(y) && (!bias || al16(bias)) && (!residual || al16(residual));
+    const int64_t n = vec ? total / 4 : total;
+    const int64_t blocks = (n + 255) / 256;
+    const int grid = static_cast<int>(blocks < 148 * 32 ? blocks : 148 * 32);
+    if (vec) bias_act_add_kernel<true><<<grid, 256, 0, stream>>>(x, bias, residual, y, total, channels, act, slope);
+    else     bias_act_add_kernel<false><<<grid, 256, 0, stream>>>(x, bias, residual, y, total, channels, act, slope);
     return cudaGetLastError();
 }
 

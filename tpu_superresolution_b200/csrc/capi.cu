@@ -270,13 +270,26 @@ int srk_dat_channel_apply_fwd(const float* qkv, const float* attn, float* out, i
     return check(srk::launch_channel_apply(qkv, attn, out, batch, tokens_per_image, static_cast<cudaStream_t>(stream)), "srk_dat_channel_apply_fwd");
 }
 
-int srk_pixelshuffle_nhwc_fwd(const float* x, float* y, int32_t batch, int32_t height, int32_t width, int32_t out_channels,
-                              int32_t r, void* stream) {
+int srk_pixelshuffle_nhwc_bias_fwd(const float* x, const float* bias, float* y, int32_t batch, int32_t height, int32_t width,
+                                   int32_t out_channels, int32_t r, void* stream) {
     if (!x || !y) return fail("srk_pixelshuffle_nhwc_fwd: null argument");
     if (batch < 0 || height < 0 || width < 0 || out_channels <= 0 || r <= 0) return fail("srk_pixelshuffle_nhwc_fwd: bad shape");
-    if (r == 2 && !aligned16(x)) return fail("srk_pixelshuffle_nhwc_fwd: x must be 16-byte aligned");
-    return check(srk::launch_pixelshuffle_nhwc(x, y, batch, height, width, out_channels, r, static_cast<cudaStream_t>(stream)),
+    if (r == 2 && (!aligned16(x) || (bias && !aligned16(bias)))) return fail("srk_pixelshuffle_nhwc_fwd: x / bias must be 16-byte aligned");
+    return check(srk::launch_pixelshuffle_nhwc(x, bias, y, batch, height, width, out_channels, r, static_cast<cudaStream_t>(stream)),
                  "srk_pixelshuffle_nhwc_fwd");
+}
+int srk_pixelshuffle_nhwc_fwd(const float* x, float* y, int32_t batch, int32_t height, int32_t width, int32_t out_channels,
+                              int32_t r, void* stream) {
+    return srk_pixelshuffle_nhwc_bias_fwd(x, nullptr, y, batch, height, width, out_channels, r, stream);
+}
+
+int srk_bias_act_add_nhwc(const float* x, const float* bias, const float* residual, float* y, int64_t pixels, int32_t channels,
+                          int32_t act, float slope, void* stream) {
+    if (!x || !y) return fail("srk_bias_act_add_nhwc: null argument");
+    if (pixels < 0 || channels <= 0) return fail("srk_bias_act_add_nhwc: bad shape");
+    if (act != SRK_ACT_NONE && act != SRK_ACT_LEAKY_RELU) return fail("srk_bias_act_add_nhwc: unknown activation");
+    return check(srk::launch_bias_act_add(x, bias, residual, y, pixels, channels, act, slope, static_cast<cudaStream_t>(stream)),
+                 "srk_bias_act_add_nhwc");
 }
 
 int srk_stitch_accumulate(const float* tiles, float* E, float* Wt, const int32_t* tile_yx, int32_t num_tiles, int32_t channels,

@@ -86,8 +86,10 @@ cudaError_t launch_winattn(int kind, const WinAttnParams& p, cudaStream_t stream
 int winattn_table_floats(int kind);
 cudaError_t launch_layernorm(const float* x, float* y, const float* w, const float* b, int64_t num_tokens, int ld_in,
                              int ld_out, cudaStream_t stream);
-cudaError_t launch_pixelshuffle_nhwc(const float* x, float* y, int batch, int height, int width, int out_channels, int r,
-                                     cudaStream_t stream);
+cudaError_t launch_pixelshuffle_nhwc(const float* x, const float* bias, float* y, int batch, int height, int width, int out_channels,
+                                     int r, cudaStream_t stream);
+cudaError_t launch_bias_act_add(const float* x, const float* bias, const float* residual, float* y, int64_t pixels, int channels,
+                                int act, float slope, cudaStream_t stream);
 cudaError_t launch_stitch_accumulate(const float* tiles, float* E, float* Wt, const int32_t* tile_yx, int num_tiles,
                                      int channels, int tile_h, int tile_w, int out_h, int out_w, cudaStream_t stream);
 int cab_ws_floats(int batch, int tokens_per_image);

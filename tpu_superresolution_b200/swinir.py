@@ -282,6 +282,26 @@ class PatchUnEmbed(nn.Module):
         return x.reshape(B, x_size[0], x_size[1], C).permute(0, 3, 1, 2)
 
 
+def _conv_tail(conv, x, *, residual=None, act=L.ACT_NONE, slope=0.0):
+    """conv(x) as the library convolution WITHOUT bias, then bias (+ LeakyReLU) (+ residual) in one pass
+    (srk_bias_act_add_nhwc).  `residual`: [B, H*W, C] tokens or a channels-last [B,C,H,W] map.  Returns [B,C,H,W]
+    (channels-last memory)."""
+    z = F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+    zt = z.permute(0, 2, 3, 1)                      # [B,H,W,C] view of the channels-last result
+    if not zt.is_contiguous():
+        zt = zt.contiguous()
+        z = zt.permute(0, 3, 1, 2)
+    B, H, W, C = zt.shape
+    res = None
+    if residual is not None:
+        res = residual if residual.dim() == 3 else residual.permute(0, 2, 3, 1)
+        if not res.is_contiguous():
+            res = res.contiguous()
+    if conv.bias is not None or res is not None or act != L.ACT_NONE:
+        L.bias_act_add_nhwc(zt, zt, pixels=B * H * W, channels=C, bias=conv.bias, residual=res, act=act, slope=slope)
+    return z
+
+
 class RSTB(nn.Module):
     """network_swinir.py:419-492: blocks -> 3x3 conv -> + input."""
 
@@ -308,6 +328,8 @@ class RSTB(nn.Module):
 
     def forward(self, x, x_size):
         y = self.patch_unembed(self.residual_group(x, x_size), x_size)
+        if isinstance(self.conv, nn.Conv2d):        # '1conv': bias + residual fused behind the conv
+            return self.patch_embed(_conv_tail(self.conv, y, residual=x))
         return self.patch_embed(self.conv(y)) + x
 
 
@@ -318,7 +340,8 @@ class PixelShuffle(nn.Module):
         super().__init__()
         self.upscale_factor = upscale_factor
 
-    def forward(self, x):
+    def forward(self, x, bias=None):
+        """`bias`: per-input-channel bias of the preceding (bias-free) convolution, added on the way."""
         r = self.upscale_factor
         B, C, H, W = x.shape
         oc = C // (r * r)
@@ -326,7 +349,7 @@ class PixelShuffle(nn.Module):
         if not xin.is_contiguous():
             xin = xin.contiguous()
         y = torch.empty((B, H * r, W * r, oc), device=x.device, dtype=x.dtype)
-        L.pixelshuffle_nhwc(xin, y, batch=B, height=H, width=W, out_channels=oc, r=r)
+        L.pixelshuffle_nhwc(xin, y, batch=B, height=H, width=W, out_channels=oc, r=r, bias=bias)
         return y.permute(0, 3, 1, 2)          # logical NCHW, channels-last memory
 
     def extra_repr(self) -> str:
@@ -346,6 +369,19 @@ class Upsample(nn.Sequential):
         else:
             raise ValueError(f'scale {scale} is not supported. Supported scales: 2^n and 3.')
         super().__init__(*m)
+
+    def forward(self, x):
+        mods = list(self)
+        i = 0
+        while i < len(mods):
+            if isinstance(mods[i], nn.Conv2d) and i + 1 < len(mods) and isinstance(mods[i + 1], PixelShuffle):
+                c = mods[i]                 # the conv runs bias-free; the shuffle adds the bias while it moves the data
+                x = mods[i + 1](F.conv2d(x, c.weight, None, c.stride, c.padding, c.dilation, c.groups), bias=c.bias)
+                i += 2
+            else:
+                x = mods[i](x)
+                i += 1
+        return x
 
 
 class UpsampleOneStep(nn.Sequential):
@@ -459,9 +495,13 @@ class SwinIR(nn.Module):
         self.mean = self.mean.type_as(x)
         x = ((x - self.mean) * self.img_range).contiguous(memory_format=torch.channels_last)
         if self.upsampler == 'pixelshuffle':
-            x = self.conv_first(x)
-            x = self.conv_after_body(self.forward_features(x)) + x
-            x = self.conv_before_upsample(x)
+            x = _conv_tail(self.conv_first, x)
+            if isinstance(self.conv_after_body, nn.Conv2d):
+                x = _conv_tail(self.conv_after_body, self.forward_features(x), residual=x)
+            else:
+                x = self.conv_after_body(self.forward_features(x)) + x
+            cbu = self.conv_before_upsample      # Sequential(conv, LeakyReLU)
+            x = _conv_tail(cbu[0], x, act=L.ACT_LEAKY_RELU, slope=cbu[1].negative_slope)
             x = self.conv_last(self.upsample(x))
         elif self.upsampler == 'pixelshuffledirect':
             x = self.conv_first(x)
