@@ -129,9 +129,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) token_linear_kernel(const Line
                         mbar_wait(&bars[LB_FULL + stage_i], phase);
                         tc_fence_after();
                         const uint32_t a = sbase + L_A + ka * ATOM_A, b = sbase + L_RING + stage_i * LIN_SLAB;
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            umma_ss_w(tmem + 256 * buf, umma_desc_sw128(a + ks * 32), umma_desc_sw128(b + ks * 32), LIN_IDESC, (ka | ks) != 0);
+                        umma_ss_w4(tmem + 256 * buf, umma_desc_sw128(a), umma_desc_sw128(b), LIN_IDESC, ka != 0);
                         umma_commit_w(&bars[LB_EMPTY + stage_i]);
                         if (++stage_i == LIN_RING_N) { stage_i = 0; phase ^= 1; }
                     }

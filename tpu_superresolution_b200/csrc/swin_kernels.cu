@@ -194,9 +194,7 @@ static __device__ __noinline__ uint32_t k1_gemm_k192(uint64_t* bars, uint32_t ri
         tc_fence_after();
         const uint32_t w = ring + stage * RING_STAGE, im = img + ka * ATOM_A;
         const uint32_t a = img_is_a ? im : w, b = img_is_a ? w : im;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-            umma_ss_w(d_tmem, umma_desc_sw128(a + ks * 32), umma_desc_sw128(b + ks * 32), idesc, (ka | ks) != 0);
+        umma_ss_w4(d_tmem, umma_desc_sw128(a), umma_desc_sw128(b), idesc, ka != 0);
         umma_commit_w(&bars[B_EMPTY + stage]);
         if (++stage == RING_N) { stage = 0; phase ^= 1; }
     }
@@ -204,15 +202,17 @@ static __device__ __noinline__ uint32_t k1_gemm_k192(uint64_t* bars, uint32_t ri
 }
 // [q_h | k_h] = xhat * W^T, N = 64; the three k-atoms of W arrive as one ring stage
 static __device__ __noinline__ uint32_t k1_gemm_qk(uint64_t* bars, uint32_t ring, uint32_t cur, uint32_t acc, uint32_t xa, uint64_t* done_bar) {
+    // (arguments arrive in vector registers; a lane-0 broadcast tells the compiler they are warp-uniform, so the
+    //  descriptor arithmetic below runs on the uniform datapath instead of being moved there per MMA)
+    ring = __shfl_sync(0xffffffffu, ring, 0); cur = __shfl_sync(0xffffffffu, cur, 0);
+    acc = __shfl_sync(0xffffffffu, acc, 0);   xa = __shfl_sync(0xffffffffu, xa, 0);
     uint32_t stage = cur & 0xffu, phase = cur >> 8;
     mbar_wait(&bars[B_FULL + stage], phase);
     tc_fence_after();
     const uint32_t w = ring + stage * RING_STAGE;
 #pragma unroll
     for (int ka = 0; ka < 3; ++ka)
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-            umma_ss_w(acc, umma_desc_sw128(xa + ka * ATOM_A + ks * 32), umma_desc_sw128(w + ka * 8192 + ks * 32), IDESC_128x64, (ka | ks) != 0);
+        umma_ss_w4(acc, umma_desc_sw128(xa + ka * ATOM_A), umma_desc_sw128(w + ka * 8192), IDESC_128x64, ka != 0);
     umma_commit_w(&bars[B_EMPTY + stage]);
     if (++stage == RING_N) { stage = 0; phase ^= 1; }
     umma_commit_w(done_bar);
@@ -296,10 +296,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
                 const uint32_t pcol = tmem + ((h & 1) ? TC_S1 : TC_S0);
 #pragma unroll
                 for (int w = 0; w < 2; ++w)
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        umma_ts_w(tmem + TC_O + 32 * h + w * LANE16, pcol + w * LANE16 + 8 * kk,
-                                umma_desc_sw128(vt + w * VT_ATOM + h * 4096 + kk * 32), IDESC_64x32, kk != 0);
+                    umma_ts_w4(tmem + TC_O + 32 * h + w * LANE16, pcol + w * LANE16, umma_desc_sw128(vt + w * VT_ATOM + h * 4096), IDESC_64x32, 0);
             };
             int it = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
@@ -632,9 +629,7 @@ static __device__ __noinline__ uint32_t k2_fc1_chunk(uint64_t* bars, uint32_t ri
         mbar_wait(&bars[MB_FULL + stage], phase);
         tc_fence_after();
         const uint32_t a = xa + ka * ATOM_A, b = ring + stage * RING_STAGE;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-            umma_ss_w(acc, umma_desc_sw128(a + ks * 32), umma_desc_sw128(b + ks * 32), IDESC_128x128, (ka | ks) != 0);
+        umma_ss_w4(acc, umma_desc_sw128(a), umma_desc_sw128(b), IDESC_128x128, ka != 0);
         umma_commit_w(&bars[MB_EMPTY + stage]);
         if (++stage == RING_N) { stage = 0; phase ^= 1; }
     }
@@ -648,9 +643,7 @@ static __device__ __noinline__ uint32_t k2_fc2_chunk(uint64_t* bars, uint32_t ri
         mbar_wait(&bars[MB_FULL + stage], phase);
         tc_fence_after();
         const uint32_t b = ring + stage * RING_STAGE;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-            umma_ts_w(acc, h_tmem + 64 * half + 8 * ks, umma_desc_sw128(b + ks * 32), IDESC_128x192, !(first && half == 0 && ks == 0));
+        umma_ts_w4(acc, h_tmem + 64 * half, umma_desc_sw128(b), IDESC_128x192, !(first && half == 0));
         umma_commit_w(&bars[MB_EMPTY + stage]);
         if (++stage == RING_N) { stage = 0; phase ^= 1; }
     }

@@ -188,6 +188,48 @@ __device__ __forceinline__ void umma_ss_w(uint32_t d_tmem, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Four consecutive k-steps (K = 64: one SW128 k-atom) of an SS MMA with one election: descriptors advance by
+// 32 bytes (>> 4 = 2) per step.  `accumulate_first` applies to step 0; steps 1..3 always accumulate.
+__device__ __forceinline__ void umma_ss_w4(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate_first) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, e;\n\t"
+        ".reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "add.u64 a1, %1, 2;\n\t add.u64 b1, %2, 2;\n\t"
+        "add.u64 a2, %1, 4;\n\t add.u64 b2, %2, 4;\n\t"
+        "add.u64 a3, %1, 6;\n\t add.u64 b3, %2, 6;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, 1;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, 1;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, 1;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate_first)
+        : "memory");
+}
+// The TS form: A = packed bf16 in TMEM, 8 columns (16 k-values) per step; B advances by BSTEP descriptor units
+// (16 bytes each) per step: 2 for a K-major SW128 operand, 128 for the MN-major V operand (16 key rows of 128 B).
+template <int BSTEP = 2>
+__device__ __forceinline__ void umma_ts_w4(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate_first) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, e;\n\t"
+        ".reg .b32 a1, a2, a3;\n\t"
+        ".reg .b64 b1, b2, b3;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "add.u32 a1, %1, 8;\n\t add.u64 b1, %2, %5;\n\t"
+        "add.u32 a2, %1, 16;\n\t add.u64 b2, %2, %6;\n\t"
+        "add.u32 a3, %1, 24;\n\t add.u64 b3, %2, %7;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], b1, %3, 1;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], b2, %3, 1;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], b3, %3, 1;\n\t"
+        "}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate_first), "n"(BSTEP), "n"(2 * BSTEP), "n"(3 * BSTEP)
+        : "memory");
+}
 __device__ __forceinline__ void umma_ts_w(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"

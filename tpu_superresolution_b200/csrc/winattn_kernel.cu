@@ -272,9 +272,9 @@ __global__ void __launch_bounds__(320, 1) winattn_kernel(const WinAttnParams p) 
                         ph_pr[g] ^= 1;
                         tc_fence_after();
 #pragma unroll
-                        for (int kk = 0; kk < NCH / 16; ++kk)
-                            umma_ts_w(tmem + 256 * g + TC_OACC, tmem + 256 * g + 8 * kk,
-                                    umma_desc_sw128_mn(set + C::V_OFF + (c * NCH + 16 * kk) * 128 + 64 * hh), IDESC_PV, (c | kk) != 0);
+                        for (int k4 = 0; k4 < NCH / 64; ++k4)       // 4 k-steps (64 keys) per call
+                            umma_ts_w4<128>(tmem + 256 * g + TC_OACC, tmem + 256 * g + 32 * k4,
+                                            umma_desc_sw128_mn(set + C::V_OFF + (c * NCH + 64 * k4) * 128 + 64 * hh), IDESC_PV, (c | k4) != 0);
                         umma_commit_w(&bars[W_OF + g]);
                         st_g[g] = 0;
                         if (++c_g[g] == NCHUNKS) {
