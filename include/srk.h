@@ -38,7 +38,7 @@ extern "C" {
 #define SRK_HIDDEN_PAD 384
 
 /* byte sizes of the packed weight streams (see packing.py for the slab order) */
-#define SRK_ATTN_WSTREAM_BYTES (6 * 16384 + 18 * 8192 + 3 * 24576)
+#define SRK_ATTN_WSTREAM_BYTES (3 * 24576 + 9 * 16384 + 3 * 24576)
 #define SRK_MLP_WSTREAM_BYTES (9 * 16384 + 6 * 24576)
 /* float offsets inside the packed per-block vectors.  LayerNorm's affine, the k bias and the v bias do not appear:
  * packing.py folds gamma/beta into the following GEMM, drops the k bias (softmax-invariant) and moves the v bias

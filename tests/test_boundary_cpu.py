@@ -79,15 +79,16 @@ def test_pack_attention_reconstructs_reference_math(with_ln):
     w, vec = packing.pack_attention(sd[pre + "qkv.weight"], sd[pre + "qkv.bias"], sd[pre + "proj.weight"], sd[pre + "proj.bias"],
                                     sd[pre + "relative_position_bias_table"], *ln)
     assert w.numel() == L.ATTN_WSTREAM_BYTES and vec.numel() == L.ATTN_VEC_FLOATS
-    slabs = _unpack_slabs(w, [128] * 6 + [64] * 18 + [192] * 3)
-    wv = torch.cat([torch.cat(slabs[0:3], 1), torch.cat(slabs[3:6], 1)], 0)           # (256, 192)
-    wqk = [torch.cat(slabs[6 + 3 * h:9 + 3 * h], 1) for h in range(6)]                  # 6 x (64, 192): [q_h | k_h]
-    wp = torch.cat(slabs[24:27], 1)                                                      # (192, 192)
+    slabs = _unpack_slabs(w, [192] * 3 + [128] * 9 + [192] * 3)
+    wv = torch.cat(slabs[0:3], 1)                                                        # (192, 192) padded v-dims
+    pairs = [torch.cat(slabs[3 + 3 * p:6 + 3 * p], 1) for p in range(3)]                 # 3 x (128, 192): [q_h | k_h | q_h+1 | k_h+1]
+    wqk = [pairs[h >> 1][64 * (h & 1):64 * (h & 1) + 64] for h in range(6)]              # 6 x (64, 192): [q_h | k_h]
+    wp = torch.cat(slabs[12:15], 1)                                                      # (192, 192)
     xw = synth.make_tokens(4, 8, 8, 180, seed=5)
     xhat = (xw - xw.mean(-1, keepdim=True)) / torch.sqrt(xw.var(-1, unbiased=False, keepdim=True) + 1e-5) if with_ln else xw
     xb = torch.zeros(4, 64, 192)
     xb[..., :180] = xhat.bfloat16().float()
-    v = xb @ wv.T                                                                        # (4, 64, 256) padded head layout, no bias
+    v = xb @ wv.T                                                                        # (4, 64, 192) padded head layout, no bias
     o = torch.zeros(4, 64, 192)
     rpb = vec[L.AV_RPB:].view(6, L.AV_RPB_STRIDE)
     idx = O.relative_position_index(8)

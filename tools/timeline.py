@@ -29,7 +29,7 @@ for hh in range(3):
     names1[4 + 3 * hh] = f"g0 QKep(h{2*hh}) done"; names1[5 + 3 * hh] = f"g0 SF(h{2*hh}) seen"; names1[6 + 3 * hh] = f"g0 softmax(h{2*hh}) done"
 for h in range(6):
     names1[35 + h] = f"MMA QKR{h} seen"; names1[44 + h] = f"MMA S{h} issued"; names1[50 + h] = f"U QKF{h} seen"; names1[56 + h] = f"U QKep{h} done"
-names1[62] = "U LN(next) done"; names1[28] = "rows staged, copies issued"; names1[29] = "copies read smem"
+names1[62] = "U LN(next) done"; names1[1] = "MMA weights of qk(4) landed"; names1[30] = "MMA gemm_qk(4) issued"; names1[31] = "MMA PR(1) seen"; names1[63] = "MMA PV(1) issued"; names1[28] = "rows staged, copies issued"; names1[29] = "copies read smem"
 names2 = {0: "tile start", 1: "F1c0 seen", 2: "gelu0 done", 3: "F1c1 seen", 4: "gelu1 done", 5: "F1c2 seen", 6: "gelu2 done", 7: "LN next done", 8: "F2 seen", 9: "store done"}
 for nm in (names1, names2):
     nm.update({13: "kernel entry", 14: "prologue done (TMEM, barriers)", 15: "PDL wait done", 16: "role loop done", 17: "all warps done"})

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libsrk.so")
 # mirrors of the #defines in include/srk.h
 ABI_VERSION = 1
 DIM, DIM_PAD, HEADS, HEAD_DIM, HEAD_PAD, WINDOW, HIDDEN, HIDDEN_PAD = 180, 192, 6, 30, 32, 8, 360, 384
-ATTN_WSTREAM_BYTES = 6 * 16384 + 18 * 8192 + 3 * 24576
+ATTN_WSTREAM_BYTES = 3 * 24576 + 9 * 16384 + 3 * 24576
 MLP_WSTREAM_BYTES = 9 * 16384 + 6 * 24576
 AV_BIAS_Q, AV_BIAS_PROJ, AV_RPB, AV_RPB_STRIDE = 384, 1024, 1216, 232
 ATTN_VEC_FLOATS = 1216 + 6 * 232

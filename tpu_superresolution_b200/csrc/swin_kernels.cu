@@ -39,7 +39,7 @@ constexpr uint32_t IDESC_128x192 = umma_idesc_bf16(128, 192);
 constexpr uint32_t IDESC_128x64 = umma_idesc_bf16(128, 64);
 constexpr uint32_t IDESC_128x32 = umma_idesc_bf16(128, 32);
 constexpr uint32_t IDESC_64x64 = umma_idesc_bf16(64, 64);
-constexpr uint32_t IDESC_64x32 = umma_idesc_bf16(64, 32);
+constexpr uint32_t IDESC_64x32_BMN = umma_idesc_bf16(64, 32) | (1u << 16);     // B (= V) MN-major: [key][dim] rows
 constexpr float LOG2E = 1.4426950408889634f;
 
 // Optional per-CTA timeline (debug): CTA 0 writes clock64() at event `id` of its `it`-th tile.
@@ -68,7 +68,7 @@ __device__ __forceinline__ void stagger_start(int cycles) {
 // K1: attention half
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t A_XA = 0;                          // normalised x image [128 x 192]
-constexpr uint32_t A_VT = A_XA + 3 * ATOM_A;          // V^T image [192 x 128 keys]; then the O image; then the transposers
+constexpr uint32_t A_VT = A_XA + 3 * ATOM_A;          // V image [128 tokens x 192 dims]; then the O image; then the store staging
 constexpr uint32_t A_QKI = A_VT + 2 * VT_ATOM;        // 2 x [q_h | k_h] images [128 x (32+32)] (one per softmax group)
 constexpr uint32_t A_RING = A_QKI + 2 * ATOM_A;       // weight ring
 constexpr uint32_t A_VEC = A_RING + RING_N * RING_STAGE;
@@ -85,8 +85,8 @@ static_assert(112 * 720 <= 2 * VT_ATOM + 2 * ATOM_A && 3 * ATOM_A <= 2 * VT_ATOM
 // window (L % 32) / 16, token 16 * (L / 32) + L % 16.
 constexpr uint32_t TC_O = 0;                          // O accumulator, 6 heads x 32; later the proj accumulator (192)
 constexpr uint32_t TC_S0 = 192, TC_S1 = 256;          // S = q k^T (64 keys); P (bf16 pairs) aliases cols 0..31
-constexpr uint32_t TC_QK1 = 384, TC_QK0 = 448;        // [q_h | k_h] accumulators (64 cols), double buffered by head parity
-constexpr uint32_t TC_VT0 = 192, TC_VT1 = 320;        // V^T accumulators (before the first S / odd q|k GEMM of the tile)
+constexpr uint32_t TC_QK0 = 384, TC_QK1 = 448;        // [q_h | k_h] accumulators (64 cols), double buffered by head parity
+constexpr uint32_t TC_V = 192;                        // V accumulator [128 tokens x 192 dims] (before the first S of the tile)
 constexpr uint32_t TC_PROJ = 0;
 constexpr uint32_t LANE16 = 16u << 16;                // TMEM lane offset of the second window's M = 64 tile
 
@@ -200,25 +200,6 @@ static __device__ __noinline__ uint32_t k1_gemm_k192(uint64_t* bars, uint32_t ri
     }
     return stage | (phase << 8);
 }
-// [q_h | k_h] = xhat * W^T, N = 64; the three k-atoms of W arrive as one ring stage
-static __device__ __noinline__ uint32_t k1_gemm_qk(uint64_t* bars, uint32_t ring, uint32_t cur, uint32_t acc, uint32_t xa, uint64_t* done_bar) {
-    // (arguments arrive in vector registers; a lane-0 broadcast tells the compiler they are warp-uniform, so the
-    //  descriptor arithmetic below runs on the uniform datapath instead of being moved there per MMA)
-    ring = __shfl_sync(0xffffffffu, ring, 0); cur = __shfl_sync(0xffffffffu, cur, 0);
-    acc = __shfl_sync(0xffffffffu, acc, 0);   xa = __shfl_sync(0xffffffffu, xa, 0);
-    uint32_t stage = cur & 0xffu, phase = cur >> 8;
-    mbar_wait(&bars[B_FULL + stage], phase);
-    tc_fence_after();
-    const uint32_t w = ring + stage * RING_STAGE;
-#pragma unroll
-    for (int ka = 0; ka < 3; ++ka)
-        umma_ss_w4(acc, umma_desc_sw128(xa + ka * ATOM_A), umma_desc_sw128(w + ka * 8192), IDESC_128x64, ka != 0);
-    umma_commit_w(&bars[B_EMPTY + stage]);
-    if (++stage == RING_N) { stage = 0; phase ^= 1; }
-    umma_commit_w(done_bar);
-    return stage | (phase << 8);
-}
-
 __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -257,8 +238,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
             uint32_t stage = 0, phase = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                 uint32_t off = 0;
-                for (int s = 0; s < 15; ++s) {      // 6 x 16 KB (V^T k-atoms), 6 x 24 KB (q|k of one head: 3 k-atoms x 64 rows), 3 x 24 KB (proj)
-                    const uint32_t bytes = s < 6 ? 16384u : 24576u;
+                for (int s = 0; s < 15; ++s) {      // 3 x 24 KB (Wv k-atoms), 9 x 16 KB (3 head pairs x 3 k-atoms of [q|k|q|k]), 3 x 24 KB (proj)
+                    const uint32_t bytes = (s < 3 || s >= 12) ? 24576u : 16384u;
                     mbar_wait(&bars[B_EMPTY + stage], phase ^ 1);
                     mbar_arrive_expect_tx(&bars[B_FULL + stage], bytes);
                     bulk_g2s(sm + A_RING + stage * RING_STAGE, p.wstream + off, bytes, &bars[B_FULL + stage]);
@@ -278,8 +259,10 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
             auto gemm_k192 = [&](uint32_t d_tmem, uint32_t img, bool img_is_a, uint32_t idesc) {
                 cur = k1_gemm_k192(bars, ring, cur, d_tmem, img, img_is_a ? 1u : 0u, idesc);
             };
-            auto gemm_qk = [&](int h) {
-                cur = k1_gemm_qk(bars, ring, cur, tmem + ((h & 1) ? TC_QK1 : TC_QK0), xa, &bars[B_QKF0 + (h & 1)]);
+            auto gemm_qk_pair = [&]() {         // [q_h | k_h | q_h+1 | k_h+1] = xhat * W^T for a pair of heads: one N = 128 GEMM
+                gemm_k192(tmem + TC_QK0, xa, true, IDESC_128x128);
+                umma_commit_w(&bars[B_QKF0]);
+                umma_commit_w(&bars[B_QKF1]);
             };
             auto issue_s = [&](int h) {        // S_w = q_h k_h^T per window w: two M = 64, N = 64 UMMAs sharing 64 columns
                 const uint32_t img = qki + (h & 1) * ATOM_A;
@@ -292,11 +275,12 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
                                 IDESC_64x64, ks != 0);
                 umma_commit_w(&bars[B_SF0 + (h & 1)]);
             };
-            auto issue_pv = [&](int h) {       // O_h = P v_h per window: A = P (TMEM, aliases S), B = V^T rows of head h, keys of window w
+            auto issue_pv = [&](int h) {       // O_h = P v_h per window: A = P (TMEM, aliases S), B = V rows (keys) of window w, dims of head h (MN-major)
                 const uint32_t pcol = tmem + ((h & 1) ? TC_S1 : TC_S0);
 #pragma unroll
                 for (int w = 0; w < 2; ++w)
-                    umma_ts_w4(tmem + TC_O + 32 * h + w * LANE16, pcol + w * LANE16, umma_desc_sw128(vt + w * VT_ATOM + h * 4096), IDESC_64x32, 0);
+                    umma_ts_w4<128>(tmem + TC_O + 32 * h + w * LANE16, pcol + w * LANE16,
+                                    umma_desc_sw128(vt + (h >> 1) * ATOM_A + w * 8192 + (h & 1) * 64), IDESC_64x32_BMN, 0);
             };
             int it = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
@@ -304,24 +288,22 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
                 mbar_wait(&bars[B_XA], ph_xa); ph_xa ^= 1;
                 tc_fence_after();
                 SRK_TL(mdbg, it, 33);
-                // ---- V^T = Wv * xhat^T : A = Wv slab (128 v-dims), B = x image (128 tokens)
-                gemm_k192(tmem + TC_VT0, xa, false, IDESC_128x128);
-                gemm_k192(tmem + TC_VT1, xa, false, IDESC_128x128);
+                // ---- V = xhat * Wv^T [128 tokens x 192 dims]: A = x image, B = Wv slab (192 rows)
+                gemm_k192(tmem + TC_V, xa, true, IDESC_128x192);
                 umma_commit_w(&bars[B_VTF]);
                 SRK_TL(mdbg, it, 34);
-                // ---- [q_0 | k_0] (its accumulator does not overlap the V^T accumulators), then, once those are drained, [q_1 | k_1]
-                gemm_qk(0);
-                mbar_wait(&bars[B_VTD], ph_vtd); ph_vtd ^= 1;              // S0 / S1 / [q_1 | k_1] accumulators alias the V^T ones
+                // ---- heads 0, 1 (their accumulator does not overlap V's); S needs V drained (S0 / S1 alias it)
+                gemm_qk_pair();
+                mbar_wait(&bars[B_VTD], ph_vtd); ph_vtd ^= 1;
                 tc_fence_after();
 #pragma unroll 1
                 for (int h = 0; h < 6; ++h) {
-                    mbar_wait(&bars[B_QKR0 + (h & 1)], ph_qkr[h & 1]); ph_qkr[h & 1] ^= 1;   // image h written, accumulator h & 1 drained
+                    mbar_wait(&bars[B_QKR0 + (h & 1)], ph_qkr[h & 1]); ph_qkr[h & 1] ^= 1;   // image h written, accumulator half h & 1 drained
                     tc_fence_after();
                     SRK_TL(mdbg, it, 35 + h);
                     issue_s(h);
                     SRK_TL(mdbg, it, 44 + h);
-                    if (h == 0) gemm_qk(1);                                // (after S0: the softmax warps are already waiting for it)
-                    if (h + 2 < 6) gemm_qk(h + 2);                         // runs two heads ahead of the softmax
+                    if ((h & 1) && h < 5) gemm_qk_pair();                  // both halves drained: the next pair of heads
                     if (h == 3) umma_commit_w(&bars[B_XAFREE]);            // last GEMM reading the x image: free once it completes
                     if (h >= 1) {
                         mbar_wait(&bars[B_PR0 + ((h - 1) & 1)], ph_pr[(h - 1) & 1]); ph_pr[(h - 1) & 1] ^= 1;
@@ -482,23 +464,18 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
             const float* emask = nxt.emask;
             const bool masked = (mh & mw) != 0xffu;
 
-            // ---- phase 1: V^T accumulators -> V^T image (thread = v-dim row, group g = tokens 64 g .. 64 g + 63).
+            // ---- phase 1: V accumulators -> V image [token][dim] (3 k-atoms of 64 dims; thread = token row, group g = dims 96 g ..).
             //      The v bias is folded into the proj bias at pack time (softmax rows sum to one).
             mbar_wait(&bars[B_VTF], ph_vtf); ph_vtf ^= 1;
             tc_fence_after();
             SRK_TL(dbg, it, 2);
 #pragma unroll
-            for (int m = 0; m < 2; ++m) {
-                if (m == 0 || q < 2) {      // v-dims 192..255 are padding
-                    const int vrow = m * 128 + row;
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        uint32_t v[32];
-                        tmem_ld32(tmem + lanebase + (m ? TC_VT1 : TC_VT0) + 64 * g + 32 * c, v);
-                        tmem_ld_wait();
-                        store_row_chunks<false, false>(vt + g * VT_ATOM, vrow, c * 4, v, nullptr, 1.0f);
-                    }
-                }
+            for (int c = 0; c < 3; ++c) {
+                const int d0 = 96 * g + 32 * c;
+                uint32_t v[32];
+                tmem_ld32(tmem + lanebase + TC_V + d0, v);
+                tmem_ld_wait();
+                store_row_chunks<false, false>(vt + (d0 >> 6) * ATOM_A, row, (d0 & 63) >> 3, v, nullptr, 1.0f);
             }
             tc_fence_before();
             fence_proxy_async_smem();

@@ -89,13 +89,10 @@ def pack_attention(qkv_w, qkv_b, proj_w, proj_b, rpb_table, ln_w=None, ln_b=None
     bq = _pad_heads((qkv_b[:C] * (scale * LOG2E)).float())
     proj_b_eff = (proj_b.detach().double() + proj_w.detach().double() @ qkv_b[2 * C:]).float()   # v bias -> proj bias
 
-    slabs = []
-    wv256 = wv.new_zeros(256, L.DIM_PAD)
-    wv256[:192] = wv
-    for m in range(2):                                   # V^T pass: A operand = 128 v-dims per half
-        slabs += _slabs(wv256[128 * m:128 * (m + 1)])
-    for h in range(L.HEADS):                             # head h: [q_h | k_h] rows (B operand, N = 64)
-        rows = torch.cat([wq[32 * h:32 * h + 32], wk[32 * h:32 * h + 32]], 0)
+    slabs = _slabs(wv)                                   # V = xhat Wv^T: B operand, N = 192 padded v-dims (3 k-atoms x 24 KB)
+    for h in range(0, L.HEADS, 2):                       # heads h, h+1: [q_h | k_h | q_h+1 | k_h+1] rows (B operand, N = 128)
+        rows = torch.cat([wq[32 * h:32 * h + 32], wk[32 * h:32 * h + 32],
+                          wq[32 * h + 32:32 * h + 64], wk[32 * h + 32:32 * h + 64]], 0)
         slabs += _slabs(rows)
     # proj: K index is the padded head layout of O
     wp = proj_w.detach().float().view(C, L.HEADS, L.HEAD_DIM)
