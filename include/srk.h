@@ -157,7 +157,7 @@ int srk_layernorm_fwd(const float* x, float* y, const float* w, const float* b, 
  * (hat_arch.py:307).  w1 (hidden, 180), w2 (180, hidden), hidden <= 32; sums_ws: srk_cab_ws_floats() floats of scratch (per-chunk
  * partial sums, reduced in a fixed order: results are run-to-run identical). */
 int srk_cab_ws_floats(int32_t batch, int32_t tokens_per_image);
-int srk_cab_gate_add(const float* y, float* out, float* sums_ws, const float* w1, const float* b1, const float* w2, const float* b2,
+int srk_cab_gate_add(const float* y, const float* y_bias /* bias of the conv that produced y, or NULL: y + y_bias is used */, float* out, float* sums_ws, const float* w1, const float* b1, const float* w2, const float* b2,
                      int32_t hidden, float scale, int32_t batch, int32_t tokens_per_image, void* stream);
 
 /* ---- DAT glue on fp32 channels-last token rows (dat_arch.py) ------------------------------------------------------------
@@ -200,6 +200,7 @@ int srk_pixelshuffle_nhwc_bias_fwd(const float* x, const float* bias, float* y, 
  * :829).  bias / residual may be NULL; y may alias x or residual. */
 #define SRK_ACT_NONE 0
 #define SRK_ACT_LEAKY_RELU 1
+#define SRK_ACT_GELU 2        /* exact (erf) GELU: nn.GELU() between the CAB convs, hat_arch.py:68 */
 int srk_bias_act_add_nhwc(const float* x, const float* bias, const float* residual, float* y, int64_t pixels, int32_t channels,
                           int32_t act, float slope, void* stream);
 

@@ -104,7 +104,7 @@ def load():
     lib.srk_dat_channel_gram_ws_floats.argtypes = [c_int32, c_int32]
     lib.srk_cab_ws_floats.argtypes = [c_int32, c_int32]
     lib.srk_dat_channel_apply_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]
-    lib.srk_cab_gate_add.argtypes = [c_void_p] * 7 + [c_int32, ctypes.c_float, c_int32, c_int32, c_void_p]
+    lib.srk_cab_gate_add.argtypes = [c_void_p] * 8 + [c_int32, ctypes.c_float, c_int32, c_int32, c_void_p]
     lib.srk_debug_set_timeline.argtypes = [c_void_p]
     lib.srk_debug_set_timeline.restype = None
     lib.srk_debug_set_stagger.argtypes = [c_int32, c_int32]
@@ -190,7 +190,7 @@ def pixelshuffle_nhwc(x, y, *, batch, height, width, out_channels, r, bias=None)
                                                   height, width, out_channels, r, _stream()), lib)
 
 
-ACT_NONE, ACT_LEAKY_RELU = 0, 1
+ACT_NONE, ACT_LEAKY_RELU, ACT_GELU = 0, 1, 2
 
 
 def bias_act_add_nhwc(x, y, *, pixels, channels, bias=None, residual=None, act=ACT_NONE, slope=0.0) -> None:
@@ -260,14 +260,15 @@ def window_attention(q_planes, k_planes, v_planes, table, out, *, kind, batch, h
                                             zero_page(out.device).data_ptr(), out.data_ptr(), _stream()), lib)
 
 
-def cab_gate_add(y, out, w1, b1, w2, b2, *, scale, batch, tokens_per_image) -> None:
-    """srk_cab_gate_add: out += scale * y * squeeze_excite_gate(y) on channels-last (batch, tokens, 180) fp32 tensors."""
+def cab_gate_add(y, out, w1, b1, w2, b2, *, scale, batch, tokens_per_image, y_bias=None) -> None:
+    """srk_cab_gate_add: out += scale * (y + y_bias) * squeeze_excite_gate(y + y_bias) on channels-last (batch, tokens, 180) fp32."""
     lib = load()
-    _require_cuda_f32(y, out, w1, b1, w2, b2)
+    _require_cuda_f32(y, out, w1, b1, w2, b2, y_bias)
     ws = torch.empty(lib.srk_cab_ws_floats(batch, tokens_per_image), dtype=torch.float32, device=y.device)
     with _timed("cab_gate_add"):
-        _check(lib.srk_cab_gate_add(y.data_ptr(), out.data_ptr(), ws.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
-                                    b2.data_ptr(), w1.shape[0], float(scale), batch, tokens_per_image, _stream()), lib)
+        _check(lib.srk_cab_gate_add(y.data_ptr(), y_bias.data_ptr() if y_bias is not None else None, out.data_ptr(), ws.data_ptr(),
+                                    w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), w1.shape[0], float(scale), batch,
+                                    tokens_per_image, _stream()), lib)
 
 
 def _ptr(t):

@@ -128,6 +128,7 @@ cudaError_t launch_pixelshuffle_nhwc(const float* x, const float* bias, float* y
 // ---- y = act(x + bias[c]) + residual on channels-last activations ([pixels, C] rows): the per-channel bias of a
 // library convolution, an optional LeakyReLU and the block's residual add in one pass (torch runs these as a
 // non-vectorised broadcast add plus one more elementwise kernel per operation).  y may alias x or residual.
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }   // nn.GELU() (exact)
 template <bool VEC>
 __global__ void __launch_bounds__(256) bias_act_add_kernel(const float* x, const float* __restrict__ bias, const float* residual,
                                                            float* y, int64_t total, int channels, int act, float slope) {
@@ -140,6 +141,8 @@ __global__ void __launch_bounds__(256) bias_act_add_kernel(const float* x, const
             if (act == 1) {
                 v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
                 v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
+            } else if (act == 2) {
+                v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
             }
             if (residual) { const float4 r = reinterpret_cast<const float4*>(residual)[i]; v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
             reinterpret_cast<float4*>(y)[i] = v;
@@ -147,6 +150,7 @@ __global__ void __launch_bounds__(256) bias_act_add_kernel(const float* x, const
             float v = x[i];
             if (bias) v += __ldg(bias + static_cast<int>(i % channels));
             if (act == 1) v = v > 0.f ? v : v * slope;
+            else if (act == 2) v = gelu_erf(v);
             if (residual) v += residual[i];
             y[i] = v;
         }
@@ -235,18 +239,21 @@ __global__ void __launch_bounds__(192) cab_pool_kernel(const float* __restrict__
     sums[(static_cast<int64_t>(b) * gridDim.x + blockIdx.x) * SRK_DIM + c] = (s0 + s1) + (s2 + s3);
 }
 
-__global__ void __launch_bounds__(256) cab_gate_add_kernel(const float* __restrict__ y, float* __restrict__ out,
+__global__ void __launch_bounds__(256) cab_gate_add_kernel(const float* __restrict__ y, const float* __restrict__ y_bias,
+                                                           float* __restrict__ out,
                                                            const float* __restrict__ sums, const float* __restrict__ w1,
                                                            const float* __restrict__ b1, const float* __restrict__ w2,
                                                            const float* __restrict__ b2, int hidden, float scale,
                                                            int tokens_per_image) {
     __shared__ float s_mean[SRK_DIM], s_hid[32];
-    __shared__ __align__(16) float s_gate[SRK_DIM];
+    __shared__ __align__(16) float s_gate[SRK_DIM], s_yb[SRK_DIM];      // s_yb: the bias of the conv that produced y (or 0)
     const int b = blockIdx.y;
     for (int c = threadIdx.x; c < SRK_DIM; c += blockDim.x) {
         float s = 0.f;
         for (int k = 0; k < static_cast<int>(gridDim.x); ++k) s += __ldg(sums + (static_cast<int64_t>(b) * gridDim.x + k) * SRK_DIM + c);
-        s_mean[c] = s / static_cast<float>(tokens_per_image);
+        const float yb = y_bias ? __ldg(y_bias + c) : 0.f;
+        s_yb[c] = yb;
+        s_mean[c] = s / static_cast<float>(tokens_per_image) + yb;      // mean(y + bias) = mean(y) + bias
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -271,10 +278,11 @@ __global__ void __launch_bounds__(256) cab_gate_add_kernel(const float* __restri
     const float4* ys = reinterpret_cast<const float4*>(y) + base;
     float4* os = reinterpret_cast<float4*>(out) + base;
     const float4* gs = reinterpret_cast<const float4*>(s_gate);
+    const float4* bs = reinterpret_cast<const float4*>(s_yb);
     for (int i = threadIdx.x; i < nt * (SRK_DIM / 4); i += blockDim.x) {
-        const float4 g = gs[i % (SRK_DIM / 4)], v = __ldg(ys + i);
+        const float4 g = gs[i % (SRK_DIM / 4)], yb = bs[i % (SRK_DIM / 4)], v = __ldg(ys + i);
         float4 o = os[i];
-        o.x = fmaf(v.x, g.x, o.x); o.y = fmaf(v.y, g.y, o.y); o.z = fmaf(v.z, g.z, o.z); o.w = fmaf(v.w, g.w, o.w);
+        o.x = fmaf(v.x + yb.x, g.x, o.x); o.y = fmaf(v.y + yb.y, g.y, o.y); o.z = fmaf(v.z + yb.z, g.z, o.z); o.w = fmaf(v.w + yb.w, g.w, o.w);
         os[i] = o;
     }
 }
@@ -283,12 +291,12 @@ int cab_ws_floats(int batch, int tokens_per_image) {
     return batch * ((tokens_per_image + CAB_TOK_PER_BLOCK - 1) / CAB_TOK_PER_BLOCK) * SRK_DIM;
 }
 
-cudaError_t launch_cab_gate_add(const float* y, float* out, float* sums, const float* w1, const float* b1, const float* w2,
+cudaError_t launch_cab_gate_add(const float* y, const float* y_bias, float* out, float* sums, const float* w1, const float* b1, const float* w2,
                                 const float* b2, int hidden, float scale, int batch, int tokens_per_image, cudaStream_t stream) {
     if (batch <= 0 || tokens_per_image <= 0) return cudaSuccess;
     dim3 grid((tokens_per_image + CAB_TOK_PER_BLOCK - 1) / CAB_TOK_PER_BLOCK, batch);
     cab_pool_kernel<<<grid, 192, 0, stream>>>(y, sums, tokens_per_image);
-    cab_gate_add_kernel<<<grid, 256, 0, stream>>>(y, out, sums, w1, b1, w2, b2, hidden, scale, tokens_per_image);
+    cab_gate_add_kernel<<<grid, 256, 0, stream>>>(y, y_bias, out, sums, w1, b1, w2, b2, hidden, scale, tokens_per_image);
     return cudaGetLastError();
 }
 

@@ -207,13 +207,13 @@ int srk_layernorm_fwd(const float* x, float* y, const float* w, const float* b, 
     return check(srk::launch_layernorm(x, y, w, b, num_tokens, ld_in, ld_out, static_cast<cudaStream_t>(stream)), "srk_layernorm_fwd");
 }
 
-int srk_cab_gate_add(const float* y, float* out, float* sums_ws, const float* w1, const float* b1, const float* w2, const float* b2,
+int srk_cab_gate_add(const float* y, const float* y_bias, float* out, float* sums_ws, const float* w1, const float* b1, const float* w2, const float* b2,
                      int32_t hidden, float scale, int32_t batch, int32_t tokens_per_image, void* stream) {
     if (!y || !out || !sums_ws || !w1 || !b1 || !w2 || !b2) return fail("srk_cab_gate_add: null argument");
     if (!aligned16(y) || !aligned16(out)) return fail("srk_cab_gate_add: y / out must be 16-byte aligned");
     if (hidden < 1 || hidden > 32) return fail("srk_cab_gate_add: hidden must be 1..32 (got %d)", hidden);
     if (batch < 0 || batch > 65535 || tokens_per_image < 0) return fail("srk_cab_gate_add: bad shape");
-    cudaError_t e = srk::launch_cab_gate_add(y, out, sums_ws, w1, b1, w2, b2, hidden, scale, batch, tokens_per_image,
+    cudaError_t e = srk::launch_cab_gate_add(y, y_bias, out, sums_ws, w1, b1, w2, b2, hidden, scale, batch, tokens_per_image,
                                              static_cast<cudaStream_t>(stream));
     if (e == cudaSuccess) g_launches.fetch_add(1, std::memory_order_relaxed);      // two kernels: check() below counts the second
     return check(e, "srk_cab_gate_add");
@@ -287,7 +287,7 @@ int srk_bias_act_add_nhwc(const float* x, const float* bias, const float* residu
                           int32_t act, float slope, void* stream) {
     if (!x || !y) return fail("srk_bias_act_add_nhwc: null argument");
     if (pixels < 0 || channels <= 0) return fail("srk_bias_act_add_nhwc: bad shape");
-    if (act != SRK_ACT_NONE && act != SRK_ACT_LEAKY_RELU) return fail("srk_bias_act_add_nhwc: unknown activation");
+    if (act != SRK_ACT_NONE && act != SRK_ACT_LEAKY_RELU && act != SRK_ACT_GELU) return fail("srk_bias_act_add_nhwc: unknown activation");
     return check(srk::launch_bias_act_add(x, bias, residual, y, pixels, channels, act, slope, static_cast<cudaStream_t>(stream)),
                  "srk_bias_act_add_nhwc");
 }

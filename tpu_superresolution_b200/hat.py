@@ -27,7 +27,7 @@ import torch.nn.functional as F
 
 from . import _lib as L
 from . import packing
-from .swinir import (Mlp, PatchEmbed, PatchUnEmbed, Upsample, _PackedCache, _inference_only, _to_2tuple,
+from .swinir import (Mlp, PatchEmbed, PatchUnEmbed, Upsample, _PackedCache, _conv_tail, _inference_only, _to_2tuple,
                      calculate_mask as _calculate_mask)
 
 WS = 16          # window size served by the kernels
@@ -92,6 +92,16 @@ class CAB(nn.Module):
     def body(self, x):
         """conv3x3 -> GELU -> conv3x3 (cuDNN); the channel attention that follows is fused into srk_cab_gate_add by HAB."""
         return self.cab[2](self.cab[1](self.cab[0](x)))
+
+    def body_nobias(self, x):
+        """The same with the library convs run bias-free: conv -> (+bias, GELU in one pass) -> conv; returns (y, bias of the last
+        conv), which srk_cab_gate_add folds into its pool and gate."""
+        approx = getattr(self.cab[1], "approximate", "none")
+        if approx != "none":
+            return self.body(x), None
+        h = _conv_tail(self.cab[0], x, act=L.ACT_GELU)
+        c2 = self.cab[2]
+        return F.conv2d(h, c2.weight, None, c2.stride, c2.padding, c2.dilation, c2.groups), c2.bias
 
 
 class WindowAttention(nn.Module):
@@ -213,7 +223,7 @@ class HAB(nn.Module):
         # conv branch on the un-shifted LN1 output (:276-278)
         xn = torch.empty_like(x)
         L.layernorm(x, xn, self.norm1.weight, self.norm1.bias, num_tokens=tokens, ld_in=C, ld_out=C)
-        y = self.conv_block.body(xn.view(B, H, W, C).permute(0, 3, 1, 2))                    # channels-last views
+        y, y_bias = self.conv_block.body_nobias(xn.view(B, H, W, C).permute(0, 3, 1, 2))     # channels-last views
         # attention branch (reads x before `out` is touched)
         src = x
         mw, mv = self.mlp._packed(self.norm2)
@@ -231,7 +241,7 @@ class HAB(nn.Module):
         y_tok = y.permute(0, 2, 3, 1).reshape(B, Ltok, C).contiguous()                        # a view when y is channels-last
         ca = self.conv_block.cab[3].attention                                                 # squeeze-excite gate + `+ conv_x * conv_scale` (:307)
         L.cab_gate_add(y_tok, out, ca[1].weight.reshape(ca[1].weight.shape[0], C), ca[1].bias, ca[3].weight.reshape(C, -1), ca[3].bias,
-                       scale=self.conv_scale, batch=B, tokens_per_image=Ltok)
+                       scale=self.conv_scale, batch=B, tokens_per_image=Ltok, y_bias=y_bias)
         L.swin_mlp(out, out, mw, mv, num_tokens=tokens, ld_in=C, ld_out=C, apply_ln=True, add_residual=True)
         return out
 
@@ -371,6 +381,8 @@ class RHAG(nn.Module):
 
     def forward(self, x, x_size, params):
         y = self.patch_unembed(self.residual_group(x, x_size, params), x_size)
+        if isinstance(self.conv, nn.Conv2d):
+            return self.patch_embed(_conv_tail(self.conv, y, residual=x))
         return self.patch_embed(self.conv(y)) + x
 
 
@@ -480,9 +492,13 @@ class HAT(nn.Module):
         x = self.check_image_size(x)
         self.mean = self.mean.type_as(x)
         x = ((x - self.mean) * self.img_range).contiguous(memory_format=torch.channels_last)
-        x = self.conv_first(x)
-        x = self.conv_after_body(self.forward_features(x)) + x
-        x = self.conv_before_upsample(x)
+        x = _conv_tail(self.conv_first, x)
+        if isinstance(self.conv_after_body, nn.Conv2d):      # bias + long skip in one pass behind the (bias-free) conv
+            x = _conv_tail(self.conv_after_body, self.forward_features(x), residual=x)
+        else:
+            x = self.conv_after_body(self.forward_features(x)) + x
+        cbu = self.conv_before_upsample                       # Sequential(conv, LeakyReLU)
+        x = _conv_tail(cbu[0], x, act=L.ACT_LEAKY_RELU, slope=cbu[1].negative_slope)
         x = self.conv_last(self.upsample(x))
         x = x / self.img_range + self.mean
         return x[:, :, :H * self.upscale, :W * self.upscale]
