@@ -31,43 +31,72 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // ---- depthwise 3x3 on token rows.  in: rows of `ld_in` floats, channel slice [c_in, c_in + C); weights w[9][C] (tap major),
 //      out = act((sum_taps w * xin) * scale + shift) [* gate], xin = LayerNorm(in) when stats != nullptr (gamma, beta given).
-__global__ void __launch_bounds__(256) dwconv3x3_rows_kernel(const float* __restrict__ in, int ld_in, int c_in, const float* __restrict__ w,
-                                                             const float* __restrict__ scale, const float* __restrict__ shift,
-                                                             const float* __restrict__ stats, const float* __restrict__ gamma,
-                                                             const float* __restrict__ beta, const float* __restrict__ gate, int ld_gate,
-                                                             int c_gate, float* __restrict__ out, int ld_out, int C, int H, int W,
-                                                             int act_gelu) {
-    // one block per image row (blockIdx.x = b * H + y): no 64-bit divisions in the element loop
+//      Block = (image row, slab of DW_SLAB float4 channel groups), 16 x DW_SLAB threads: thread = (channel group c, column
+//      phase xl), so everything per-channel (tap weights, LayerNorm affine, BN scale / shift) sits in registers and the loops
+//      have no divisions -- the first version of this kernel spent ~450 instructions per output float4, mostly on index
+//      arithmetic.  The three input rows of the slab (plus a zero halo column on each side) are staged in shared memory once,
+//      LayerNorm applied on the way in: each input element is read three times (once per output row) instead of nine.
+constexpr int DW_SLAB = 15;            // float4 channel groups per block: 60 channels, 240 contiguous bytes per token
+constexpr int DW_XL = 16;              // column phases per block
+__global__ void __launch_bounds__(DW_SLAB * DW_XL) dwconv3x3_rows_kernel(const float* __restrict__ in, int ld_in, int c_in,
+                                                                         const float* __restrict__ w, const float* __restrict__ scale,
+                                                                         const float* __restrict__ shift, const float* __restrict__ stats,
+                                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                         const float* __restrict__ gate, int ld_gate, int c_gate,
+                                                                         float* __restrict__ out, int ld_out, int C, int H, int W, int act_gelu) {
+    extern __shared__ float4 dw_smem[];                      // [3][W + 2][DW_SLAB] input tile
     const int C4 = C >> 2;
+    const int c = threadIdx.x % DW_SLAB, xl = threadIdx.x / DW_SLAB;
+    const int c4 = blockIdx.y * DW_SLAB + c;                 // this thread's float4 channel group
+    const bool live = c4 < C4;
     const int y = blockIdx.x % H;
     const int64_t row0 = static_cast<int64_t>(blockIdx.x) * W;         // first token of this image row
-    const bool up = y > 0, down = y + 1 < H;
-    for (int i = threadIdx.x; i < W * C4; i += blockDim.x) {
-        const int x = i / C4, c4 = i - x * C4;
-        const int64_t tok = row0 + x;
-        float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (stats) { g4 = __ldg(reinterpret_cast<const float4*>(gamma) + c4); b4 = __ldg(reinterpret_cast<const float4*>(beta) + c4); }
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int WP = W + 2;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = zero4;
+    if (stats && live) { g4 = __ldg(reinterpret_cast<const float4*>(gamma) + c4); b4 = __ldg(reinterpret_cast<const float4*>(beta) + c4); }
 #pragma unroll
-        for (int dy = -1; dy <= 1; ++dy) {
-            if ((dy < 0 && !up) || (dy > 0 && !down)) continue;               // zero padding (of the normalised tensor)
-#pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) {
-                const int xx = x + dx;
-                if (xx < 0 || xx >= W) continue;
-                const int64_t nt = tok + dy * W + dx;
-                float4 v = __ldg(reinterpret_cast<const float4*>(in + nt * ld_in + c_in) + c4);
+    for (int r = 0; r < 3; ++r) {
+        const int yy = y + r - 1;
+        const bool rowok = live && yy >= 0 && yy < H;
+        const int64_t rtok = row0 + (r - 1) * W;            // token of column 0 of this input row
+        float4* trow = dw_smem + r * WP * DW_SLAB + c;
+#pragma unroll 4
+        for (int col = xl; col < WP; col += DW_XL) {        // tile column col holds input column col - 1
+            const int xx = col - 1;
+            float4 v = zero4;                                // zero padding (of the normalised tensor)
+            if (rowok && xx >= 0 && xx < W) {
+                v = __ldg(reinterpret_cast<const float4*>(in + (rtok + xx) * ld_in + c_in) + c4);
                 if (stats) {
-                    const float2 st = __ldg(reinterpret_cast<const float2*>(stats) + nt);
+                    const float2 st = __ldg(reinterpret_cast<const float2*>(stats) + rtok + xx);
                     const float mu = st.x, rs = st.y;
                     v.x = (v.x - mu) * rs * g4.x + b4.x; v.y = (v.y - mu) * rs * g4.y + b4.y;
                     v.z = (v.z - mu) * rs * g4.z + b4.z; v.w = (v.w - mu) * rs * g4.w + b4.w;
                 }
-                const float4 ww = __ldg(reinterpret_cast<const float4*>(w + ((dy + 1) * 3 + dx + 1) * C) + c4);
+            }
+            trow[col * DW_SLAB] = v;
+        }
+    }
+    float4 wk[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) wk[k] = live ? __ldg(reinterpret_cast<const float4*>(w + k * C) + c4) : zero4;
+    const float4 sc = live ? __ldg(reinterpret_cast<const float4*>(scale) + c4) : zero4;
+    const float4 sh = live ? __ldg(reinterpret_cast<const float4*>(shift) + c4) : zero4;
+    __syncthreads();
+    if (!live) return;
+#pragma unroll 2
+    for (int x = xl; x < W; x += DW_XL) {
+        float4 acc = zero4;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {                 // taps in (dy, dx) row-major order, as the 9-load version summed them
+                const float4 v = dw_smem[(r * WP + x + dx) * DW_SLAB + c];
+                const float4 ww = wk[r * 3 + dx];
                 acc.x = fmaf(ww.x, v.x, acc.x); acc.y = fmaf(ww.y, v.y, acc.y); acc.z = fmaf(ww.z, v.z, acc.z); acc.w = fmaf(ww.w, v.w, acc.w);
             }
         }
-        const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + c4), sh = __ldg(reinterpret_cast<const float4*>(shift) + c4);
+        const int64_t tok = row0 + x;
         float4 o = make_float4(fmaf(acc.x, sc.x, sh.x), fmaf(acc.y, sc.y, sh.y), fmaf(acc.z, sc.z, sh.z), fmaf(acc.w, sc.w, sh.w));
         if (act_gelu) { o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w); }
         if (gate) {
@@ -280,8 +309,17 @@ cudaError_t launch_dwconv3x3_rows(const float* in, int ld_in, int c_in, const fl
                                   const float* stats, const float* gamma, const float* beta, const float* gate, int ld_gate, int c_gate,
                                   float* out, int ld_out, int C, int batch, int H, int W, int act_gelu, cudaStream_t stream) {
     if (batch <= 0) return cudaSuccess;
-    dwconv3x3_rows_kernel<<<batch * H, 256, 0, stream>>>(in, ld_in, c_in, w, scale, shift, stats, gamma, beta, gate, ld_gate, c_gate, out,
-                                                         ld_out, C, H, W, act_gelu);
+    const int C4 = C >> 2;
+    const size_t smem = static_cast<size_t>(3) * (W + 2) * DW_SLAB * sizeof(float4);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(dwconv3x3_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    dwconv3x3_rows_kernel<<<dim3(batch * H, (C4 + DW_SLAB - 1) / DW_SLAB), DW_SLAB * DW_XL, smem, stream>>>(in, ld_in, c_in, w, scale, shift, stats, gamma,
+                                                                                                  beta, gate, ld_gate, c_gate, out, ld_out, C, H,
+                                                                                                  W, act_gelu);
     return cudaGetLastError();
 }
 
