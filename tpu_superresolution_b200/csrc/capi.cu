@@ -227,7 +227,6 @@ int srk_dwconv3x3_rows_fwd(const float* in, int32_t ld_in, int32_t c_in, const f
     if (ln_stats && (!ln_gamma || !ln_beta)) return fail("srk_dwconv3x3_rows_fwd: LayerNorm input needs gamma and beta");
     if (channels <= 0 || (channels & 3) || (ld_in & 3) || (c_in & 3) || (ld_out & 3) || c_in + channels > ld_in || channels > ld_out)
         return fail("srk_dwconv3x3_rows_fwd: channels / ld / offsets must be multiples of 4 and consistent");
-    if (width > 900) return fail("srk_dwconv3x3_rows_fwd: image rows of at most 900 tokens (three rows of a 60-channel slab are staged in shared memory)");
     if (gate && ((ld_gate & 3) || (c_gate & 3) || c_gate + channels > ld_gate)) return fail("srk_dwconv3x3_rows_fwd: bad gate slice");
     if (!aligned16(in) || !aligned16(w9c) || !aligned16(scale) || !aligned16(shift) || !aligned16(out) || (gate && !aligned16(gate)) ||
         (ln_stats && (!aligned16(ln_gamma) || !aligned16(ln_beta))))

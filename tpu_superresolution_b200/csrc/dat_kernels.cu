@@ -31,79 +31,134 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // ---- depthwise 3x3 on token rows.  in: rows of `ld_in` floats, channel slice [c_in, c_in + C); weights w[9][C] (tap major),
 //      out = act((sum_taps w * xin) * scale + shift) [* gate], xin = LayerNorm(in) when stats != nullptr (gamma, beta given).
-//      Block = (image row, slab of DW_SLAB float4 channel groups), 16 x DW_SLAB threads: thread = (channel group c, column
-//      phase xl), so everything per-channel (tap weights, LayerNorm affine, BN scale / shift) sits in registers and the loops
-//      have no divisions -- the first version of this kernel spent ~450 instructions per output float4, mostly on index
-//      arithmetic.  The three input rows of the slab (plus a zero halo column on each side) are staged in shared memory once,
-//      LayerNorm applied on the way in: each input element is read three times (once per output row) instead of nine.
+//      Block = (image, band of DW_ROWS output rows, slab of DW_SLAB float4 channel groups), 16 x DW_SLAB threads: thread =
+//      (channel group c, column phase xl), so everything per-channel (tap weights, LayerNorm affine, BN scale / shift) sits in
+//      registers and the loops have no divisions.  The block walks down its band with a ring of four input rows in shared
+//      memory (zero halo column on each side, LayerNorm applied on the way in): while output row y is computed from rows
+//      y-1 .. y+1, the global loads of row y+2 are already in flight in registers.  Each input element is read
+//      (DW_ROWS + 2) / DW_ROWS times instead of nine.
 constexpr int DW_SLAB = 15;            // float4 channel groups per block: 60 channels, 240 contiguous bytes per token
 constexpr int DW_XL = 16;              // column phases per block
-__global__ void __launch_bounds__(DW_SLAB * DW_XL) dwconv3x3_rows_kernel(const float* __restrict__ in, int ld_in, int c_in,
+constexpr int DW_ROWS = 8;             // output rows per block
+constexpr int DW_XC = 64;              // output columns per block (blockIdx.z = column chunk)
+constexpr int DW_MAXCOL = 5;           // tile columns per thread: ceil((DW_XC + 2) / DW_XL)
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+    // erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, below fp32 rounding of the GELU output): a dozen instructions
+    // instead of the ~70 of erff(), which dominated this kernel's instruction count
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+    const float e = 1.0f - poly * __expf(-z * z);
+    return 0.5f * x * (1.0f + copysignf(e, x));
+}
+template <bool HAS_LN, bool HAS_GATE>
+__global__ void __launch_bounds__(DW_SLAB * DW_XL, 2) dwconv3x3_rows_kernel(const float* __restrict__ in, int ld_in, int c_in,
                                                                          const float* __restrict__ w, const float* __restrict__ scale,
                                                                          const float* __restrict__ shift, const float* __restrict__ stats,
                                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                          const float* __restrict__ gate, int ld_gate, int c_gate,
                                                                          float* __restrict__ out, int ld_out, int C, int H, int W, int act_gelu) {
-    extern __shared__ float4 dw_smem[];                      // [3][W + 2][DW_SLAB] input tile
+    extern __shared__ float4 dw_smem[];                      // [4][WC + 2][DW_SLAB]: ring of input rows
     const int C4 = C >> 2;
     const int c = threadIdx.x % DW_SLAB, xl = threadIdx.x / DW_SLAB;
     const int c4 = blockIdx.y * DW_SLAB + c;                 // this thread's float4 channel group
     const bool live = c4 < C4;
-    const int y = blockIdx.x % H;
-    const int64_t row0 = static_cast<int64_t>(blockIdx.x) * W;         // first token of this image row
-    const int WP = W + 2;
+    const int bands = (H + DW_ROWS - 1) / DW_ROWS;
+    const int img = blockIdx.x / bands, band = blockIdx.x - img * bands;
+    const int y0 = band * DW_ROWS, y1 = min(y0 + DW_ROWS, H);
+    const int64_t img0 = static_cast<int64_t>(img) * H * W;  // first token of this image
+    const int cx0 = blockIdx.z * DW_XC;                      // first output column of this block
+    const int WC = min(DW_XC, W - cx0);                      // output columns of this block
+    const int WP = WC + 2;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = zero4;
-    if (stats && live) { g4 = __ldg(reinterpret_cast<const float4*>(gamma) + c4); b4 = __ldg(reinterpret_cast<const float4*>(beta) + c4); }
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        const int yy = y + r - 1;
-        const bool rowok = live && yy >= 0 && yy < H;
-        const int64_t rtok = row0 + (r - 1) * W;            // token of column 0 of this input row
-        float4* trow = dw_smem + r * WP * DW_SLAB + c;
-#pragma unroll 4
-        for (int col = xl; col < WP; col += DW_XL) {        // tile column col holds input column col - 1
-            const int xx = col - 1;
-            float4 v = zero4;                                // zero padding (of the normalised tensor)
-            if (rowok && xx >= 0 && xx < W) {
-                v = __ldg(reinterpret_cast<const float4*>(in + (rtok + xx) * ld_in + c_in) + c4);
-                if (stats) {
-                    const float2 st = __ldg(reinterpret_cast<const float2*>(stats) + rtok + xx);
-                    const float mu = st.x, rs = st.y;
-                    v.x = (v.x - mu) * rs * g4.x + b4.x; v.y = (v.y - mu) * rs * g4.y + b4.y;
-                    v.z = (v.z - mu) * rs * g4.z + b4.z; v.w = (v.w - mu) * rs * g4.w + b4.w;
-                }
-            }
-            trow[col * DW_SLAB] = v;
-        }
-    }
+    if (HAS_LN && live) { g4 = __ldg(reinterpret_cast<const float4*>(gamma) + c4); b4 = __ldg(reinterpret_cast<const float4*>(beta) + c4); }
     float4 wk[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) wk[k] = live ? __ldg(reinterpret_cast<const float4*>(w + k * C) + c4) : zero4;
     const float4 sc = live ? __ldg(reinterpret_cast<const float4*>(scale) + c4) : zero4;
     const float4 sh = live ? __ldg(reinterpret_cast<const float4*>(shift) + c4) : zero4;
-    __syncthreads();
-    if (!live) return;
-#pragma unroll 2
-    for (int x = xl; x < W; x += DW_XL) {
-        float4 acc = zero4;
+
+    float4 rv[DW_MAXCOL];                                    // one input row's columns of this thread, in flight
+    float2 rs[DW_MAXCOL];
+    auto row_issue = [&](int yy) {                           // start the loads of input row yy (zeros outside the image)
+        const bool rowok = live && yy >= 0 && yy < H;
+        const int64_t rtok = img0 + static_cast<int64_t>(yy) * W;
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {                 // taps in (dy, dx) row-major order, as the 9-load version summed them
-                const float4 v = dw_smem[(r * WP + x + dx) * DW_SLAB + c];
-                const float4 ww = wk[r * 3 + dx];
-                acc.x = fmaf(ww.x, v.x, acc.x); acc.y = fmaf(ww.y, v.y, acc.y); acc.z = fmaf(ww.z, v.z, acc.z); acc.w = fmaf(ww.w, v.w, acc.w);
+        for (int k = 0; k < DW_MAXCOL; ++k) {
+            const int col = xl + k * DW_XL, xx = cx0 + col - 1;      // tile column col holds input column xx
+            rv[k] = zero4; rs[k] = make_float2(0.f, 0.f);
+            if (rowok && col < WP && xx >= 0 && xx < W) {
+                rv[k] = __ldg(reinterpret_cast<const float4*>(in + (rtok + xx) * ld_in + c_in) + c4);
+                if (HAS_LN) rs[k] = __ldg(reinterpret_cast<const float2*>(stats) + rtok + xx);
             }
         }
-        const int64_t tok = row0 + x;
-        float4 o = make_float4(fmaf(acc.x, sc.x, sh.x), fmaf(acc.y, sc.y, sh.y), fmaf(acc.z, sc.z, sh.z), fmaf(acc.w, sc.w, sh.w));
-        if (act_gelu) { o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w); }
-        if (gate) {
-            const float4 gt = __ldg(reinterpret_cast<const float4*>(gate + tok * ld_gate + c_gate) + c4);
-            o.x *= gt.x; o.y *= gt.y; o.z *= gt.z; o.w *= gt.w;
+    };
+    auto row_commit = [&](int yy) {                          // normalise and store the row into ring slot yy & 3
+        const bool rowok = live && yy >= 0 && yy < H;
+        float4* trow = dw_smem + ((yy + 4) & 3) * WP * DW_SLAB + c;
+#pragma unroll
+        for (int k = 0; k < DW_MAXCOL; ++k) {
+            const int col = xl + k * DW_XL, xx = cx0 + col - 1;
+            if (col < WP) {
+                float4 v = rv[k];
+                if (HAS_LN && rowok && xx >= 0 && xx < W) {   // (zero padding applies to the normalised tensor)
+                    const float mu = rs[k].x, r_ = rs[k].y;
+                    v.x = (v.x - mu) * r_ * g4.x + b4.x; v.y = (v.y - mu) * r_ * g4.y + b4.y;
+                    v.z = (v.z - mu) * r_ * g4.z + b4.z; v.w = (v.w - mu) * r_ * g4.w + b4.w;
+                }
+                trow[col * DW_SLAB] = v;
+            }
         }
-        reinterpret_cast<float4*>(out + tok * ld_out)[c4] = o;
+    };
+    row_issue(y0 - 1); row_commit(y0 - 1);
+    row_issue(y0);     row_commit(y0);
+    row_issue(y0 + 1); row_commit(y0 + 1);
+    __syncthreads();
+    for (int y = y0; y < y1; ++y) {
+        const bool more = y + 1 < y1;
+        if (more) row_issue(y + 2);                          // in flight while row y is computed
+        float4 gv[DW_XC / DW_XL];                            // this row's gate operands: loaded up front, not one exposed latency per output
+        if (HAS_GATE && live) {
+#pragma unroll
+            for (int k = 0; k < DW_XC / DW_XL; ++k) {
+                const int x = xl + k * DW_XL;
+                gv[k] = x < WC ? __ldg(reinterpret_cast<const float4*>(gate + (img0 + static_cast<int64_t>(y) * W + cx0 + x) * ld_gate + c_gate) + c4)
+                               : zero4;
+            }
+        }
+        if (live) {
+            const float4* r0 = dw_smem + ((y + 3) & 3) * WP * DW_SLAB + c;      // rows y - 1, y, y + 1
+            const float4* r1 = dw_smem + (y & 3) * WP * DW_SLAB + c;
+            const float4* r2 = dw_smem + ((y + 1) & 3) * WP * DW_SLAB + c;
+            const int64_t rtok = img0 + static_cast<int64_t>(y) * W + cx0;
+#pragma unroll
+            for (int k = 0; k < DW_XC / DW_XL; ++k) {
+                const int x = xl + k * DW_XL;
+                if (x >= WC) break;
+                float4 acc = zero4;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const float4* rr = r == 0 ? r0 : (r == 1 ? r1 : r2);
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {         // taps in (dy, dx) row-major order, as the 9-load version summed them
+                        const float4 v = rr[(x + dx) * DW_SLAB];
+                        const float4 ww = wk[r * 3 + dx];
+                        acc.x = fmaf(ww.x, v.x, acc.x); acc.y = fmaf(ww.y, v.y, acc.y); acc.z = fmaf(ww.z, v.z, acc.z); acc.w = fmaf(ww.w, v.w, acc.w);
+                    }
+                }
+                const int64_t tok = rtok + x;
+                float4 o = make_float4(fmaf(acc.x, sc.x, sh.x), fmaf(acc.y, sc.y, sh.y), fmaf(acc.z, sc.z, sh.z), fmaf(acc.w, sc.w, sh.w));
+                if (act_gelu) { o.x = gelu_erf_fast(o.x); o.y = gelu_erf_fast(o.y); o.z = gelu_erf_fast(o.z); o.w = gelu_erf_fast(o.w); }
+                if (HAS_GATE) { o.x *= gv[k].x; o.y *= gv[k].y; o.z *= gv[k].z; o.w *= gv[k].w; }
+                reinterpret_cast<float4*>(out + tok * ld_out)[c4] = o;
+            }
+        }
+        if (more) {
+            // slot (y + 2) & 3 held row y - 2: nobody reads it in this iteration, so no barrier is needed before the write
+            row_commit(y + 2);
+            __syncthreads();
+        }
     }
 }
 
@@ -310,16 +365,19 @@ cudaError_t launch_dwconv3x3_rows(const float* in, int ld_in, int c_in, const fl
                                   float* out, int ld_out, int C, int batch, int H, int W, int act_gelu, cudaStream_t stream) {
     if (batch <= 0) return cudaSuccess;
     const int C4 = C >> 2;
-    const size_t smem = static_cast<size_t>(3) * (W + 2) * DW_SLAB * sizeof(float4);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(dwconv3x3_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    const size_t smem = static_cast<size_t>(4) * (DW_XC + 2) * DW_SLAB * sizeof(float4);
+    const dim3 grid(batch * ((H + DW_ROWS - 1) / DW_ROWS), (C4 + DW_SLAB - 1) / DW_SLAB, (W + DW_XC - 1) / DW_XC);
+    auto go = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
-        configured = smem;
-    }
-    dwconv3x3_rows_kernel<<<dim3(batch * H, (C4 + DW_SLAB - 1) / DW_SLAB), DW_SLAB * DW_XL, smem, stream>>>(in, ld_in, c_in, w, scale, shift, stats, gamma,
-                                                                                                  beta, gate, ld_gate, c_gate, out, ld_out, C, H,
-                                                                                                  W, act_gelu);
+        kern<<<grid, DW_SLAB * DW_XL, smem, stream>>>(in, ld_in, c_in, w, scale, shift, stats, gamma, beta, gate, ld_gate, c_gate, out, ld_out, C, H,
+                                                    W, act_gelu);
+        return cudaSuccess;
+    };
+    cudaError_t e;
+    if (stats) e = gate ? go(dwconv3x3_rows_kernel<true, true>) : go(dwconv3x3_rows_kernel<true, false>);
+    else       e = gate ? go(dwconv3x3_rows_kernel<false, true>) : go(dwconv3x3_rows_kernel<false, false>);
+    if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
 
