@@ -34,3 +34,10 @@ a = timed(lambda: L.dwconv3x3_rows(qkv, w9, sc, sh, out, ld_in=540, c_in=360, ld
 b = timed(lambda: L.dwconv3x3_rows(h, w9, sc, sh, out, ld_in=360, c_in=180, ld_out=C, channels=C, batch=B, height=H, width=W,
                                    ln_stats=stats, ln_gamma=g, ln_beta=bt, gate=h, ld_gate=360, c_gate=0))
 print(f"dwconv v-branch (GELU): {a:.1f} us   spatial-gate (LN, gate): {b:.1f} us")
+
+att = torch.randn(T, C, device="cuda"); conv = torch.randn(T, C, device="cuda"); mix = torch.empty(T, C, device="cuda")
+cmap = torch.randn(B, C, device="cuda")
+w1 = torch.randn(11, C, device="cuda") * 0.1; b1 = torch.randn(11, device="cuda"); w2 = torch.randn(11, device="cuda")
+for mode in (0, 1):
+    t = timed(lambda: L.dat_mix(att, conv, cmap, w1, b1, w2, 0.1, mix, mode=mode, tokens=T, tokens_per_image=H * W))
+    print(f"dat_mix mode {mode}: {t:.1f} us")

@@ -191,59 +191,115 @@ __global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict_
 //      mode 0 (spatial block, dat_arch.py:420-433): mix = att * sigmoid(cmap[b]) + sigmoid(s) * conv
 //      mode 1 (channel block, dat_arch.py:510-523): mix = att * sigmoid(s) + conv * sigmoid(cmap[b])
 //      One warp per token; W1 (hidden x 180, BatchNorm folded) lives in shared memory.
+//      Lane = token for the squeeze MLP: a warp stages 32 source rows in shared memory (coalesced), each lane then runs the
+//      180 -> hidden matvec of ITS token with the weights broadcast from shared memory -- no cross-lane reductions and one GELU
+//      per (token, unit).  The first version (warp = token, 11 warp reductions and 11 redundant GELUs per token) spent ~600
+//      instructions per token and was issue bound at 82 us; the output pass is coalesced again (lane = float4 of a row).
 constexpr int MIX_MAX_HIDDEN = 16;
-__global__ void __launch_bounds__(256) dat_mix_kernel(const float* __restrict__ att, const float* __restrict__ conv, const float* __restrict__ cmap,
-                                                      const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
-                                                      float b2, int hidden, int mode, float* __restrict__ mix, int64_t tokens,
-                                                      int tokens_per_image) {
-    __shared__ __align__(16) float s_w1[MIX_MAX_HIDDEN * SRK_DIM];
-    __shared__ float s_b1[MIX_MAX_HIDDEN], s_w2[MIX_MAX_HIDDEN];
-    for (int i = threadIdx.x; i < hidden * SRK_DIM; i += blockDim.x) s_w1[i] = w1[i];
-    if (threadIdx.x < hidden) { s_b1[threadIdx.x] = b1[threadIdx.x]; s_w2[threadIdx.x] = w2[threadIdx.x]; }
+constexpr int MIX_WARPS = 4;                       // warps per block, 32 tokens each
+constexpr int MIX_STRIDE = 188;                    // floats per staged row: 16-byte aligned, conflict-free for lane-per-row LDS.128
+__global__ void __launch_bounds__(32 * MIX_WARPS) dat_mix_kernel(const float* __restrict__ att, const float* __restrict__ conv,
+                                                                 const float* __restrict__ cmap, const float* __restrict__ w1,
+                                                                 const float* __restrict__ b1, const float* __restrict__ w2, float b2, int hidden,
+                                                                 int mode, float* __restrict__ mix, int64_t tokens, int tokens_per_image) {
+    extern __shared__ __align__(16) float mix_smem[];
+    float* s_w1t = mix_smem;                                               // [180][16]: W1 transposed, hidden padded to 16 (zeros)
+    float* s_b1 = s_w1t + SRK_DIM * MIX_MAX_HIDDEN;                        // [16]
+    float* s_w2 = s_b1 + MIX_MAX_HIDDEN;                                   // [16]
+    float* s_rows = s_w2 + MIX_MAX_HIDDEN;                                 // [MIX_WARPS][32][MIX_STRIDE]
+    for (int i = threadIdx.x; i < SRK_DIM * MIX_MAX_HIDDEN; i += blockDim.x) {
+        const int c = i / MIX_MAX_HIDDEN, j = i - c * MIX_MAX_HIDDEN;
+        s_w1t[i] = j < hidden ? w1[j * SRK_DIM + c] : 0.f;
+    }
+    if (threadIdx.x < MIX_MAX_HIDDEN) {
+        s_b1[threadIdx.x] = threadIdx.x < hidden ? b1[threadIdx.x] : 0.f;
+        s_w2[threadIdx.x] = threadIdx.x < hidden ? w2[threadIdx.x] : 0.f;      // padded units contribute w2 = 0
+    }
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-    constexpr int C4 = SRK_DIM / 4;                       // 45 float4 per row: lane handles float4 `lane` and `lane + 32`
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float* rows = s_rows + wib * 32 * MIX_STRIDE;
+    constexpr int C4 = SRK_DIM / 4;                       // 45 float4 per row
     const bool has2 = lane + 32 < C4;
-    for (int64_t tok = warp; tok < tokens; tok += nwarps) {
-        const float4* a4 = reinterpret_cast<const float4*>(att + tok * SRK_DIM);
-        const float4* c4 = reinterpret_cast<const float4*>(conv + tok * SRK_DIM);
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 a0 = __ldg(a4 + lane), a1 = has2 ? __ldg(a4 + lane + 32) : z;
-        const float4 v0 = __ldg(c4 + lane), v1 = has2 ? __ldg(c4 + lane + 32) : z;
-        const float4 s0 = mode == 0 ? a0 : v0, s1 = mode == 0 ? a1 : v1;
-        float sacc = b2;
-        for (int j = 0; j < hidden; ++j) {
-            const float4* wj = reinterpret_cast<const float4*>(s_w1 + j * SRK_DIM);
-            const float4 wa = wj[lane];
-            float d = (wa.x * s0.x + wa.y * s0.y) + (wa.z * s0.z + wa.w * s0.w);
-            if (has2) {
-                const float4 wb = wj[lane + 32];
-                d += (wb.x * s1.x + wb.y * s1.y) + (wb.z * s1.z + wb.w * s1.w);
+    const float* src = mode == 0 ? att : conv;            // the operand the squeeze MLP looks at
+    const int64_t ngroups = (tokens + 31) >> 5;
+    for (int64_t grp = static_cast<int64_t>(blockIdx.x) * MIX_WARPS + wib; grp < ngroups; grp += static_cast<int64_t>(gridDim.x) * MIX_WARPS) {
+        const int64_t tok0 = grp << 5;
+        const int nt = static_cast<int>(min(static_cast<int64_t>(32), tokens - tok0));
+        // ---- stage the 32 source rows (coalesced: lane = float4 of the row)
+#pragma unroll 8
+        for (int t = 0; t < nt; ++t) {
+            const float4* r4 = reinterpret_cast<const float4*>(src + (tok0 + t) * SRK_DIM);
+            float4* d4 = reinterpret_cast<float4*>(rows + t * MIX_STRIDE);
+            d4[lane] = __ldg(r4 + lane);
+            if (has2) d4[lane + 32] = __ldg(r4 + lane + 32);
+        }
+        __syncwarp();
+        // ---- lane = token: hidden pre-activations
+        float acc[MIX_MAX_HIDDEN];
+#pragma unroll
+        for (int j = 0; j < MIX_MAX_HIDDEN; ++j) acc[j] = 0.f;
+        if (lane < nt) {
+            const float4* x4 = reinterpret_cast<const float4*>(rows + lane * MIX_STRIDE);
+#pragma unroll 3
+            for (int c4 = 0; c4 < C4; ++c4) {
+                const float4 xv = x4[c4];
+                const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float4* wv = reinterpret_cast<const float4*>(s_w1t + (4 * c4 + e) * MIX_MAX_HIDDEN);      // broadcast
+#pragma unroll
+                    for (int q = 0; q < MIX_MAX_HIDDEN / 4; ++q) {
+                        const float4 ww = wv[q];
+                        acc[4 * q] = fmaf(ww.x, xs[e], acc[4 * q]); acc[4 * q + 1] = fmaf(ww.y, xs[e], acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(ww.z, xs[e], acc[4 * q + 2]); acc[4 * q + 3] = fmaf(ww.w, xs[e], acc[4 * q + 3]);
+                    }
+                }
             }
-            d = warp_sum(d);
-            sacc = fmaf(s_w2[j], gelu_erf(d + s_b1[j]), sacc);
         }
-        const float sg = sigmoidf_(sacc);
-        const float4* m4 = reinterpret_cast<const float4*>(cmap + (tok / tokens_per_image) * SRK_DIM);
-        float4* o4 = reinterpret_cast<float4*>(mix + tok * SRK_DIM);
-        {
-            const float4 cm = __ldg(m4 + lane);
-            const float4 cg = make_float4(sigmoidf_(cm.x), sigmoidf_(cm.y), sigmoidf_(cm.z), sigmoidf_(cm.w));
-            float4 o;
-            if (mode == 0) o = make_float4(fmaf(a0.x, cg.x, sg * v0.x), fmaf(a0.y, cg.y, sg * v0.y), fmaf(a0.z, cg.z, sg * v0.z), fmaf(a0.w, cg.w, sg * v0.w));
-            else           o = make_float4(fmaf(v0.x, cg.x, sg * a0.x), fmaf(v0.y, cg.y, sg * a0.y), fmaf(v0.z, cg.z, sg * a0.z), fmaf(v0.w, cg.w, sg * a0.w));
-            o4[lane] = o;
+        float sacc = b2;
+#pragma unroll
+        for (int j = 0; j < MIX_MAX_HIDDEN; ++j) sacc = fmaf(s_w2[j], gelu_erf_fast(acc[j] + s_b1[j]), sacc);
+        const float sg_mine = sigmoidf_(sacc);            // gate of token tok0 + lane
+        // ---- output pass (coalesced): lane = float4 `lane` / `lane + 32` of every row of the group
+        const float4* m4 = reinterpret_cast<const float4*>(cmap + (tok0 / tokens_per_image) * SRK_DIM);
+        const int64_t img_end = (tok0 / tokens_per_image + 1) * tokens_per_image;     // a group may straddle two images
+        float4 cg0, cg1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto load_cg = [&](const float4* m) {
+            const float4 cm = __ldg(m + lane);
+            cg0 = make_float4(sigmoidf_(cm.x), sigmoidf_(cm.y), sigmoidf_(cm.z), sigmoidf_(cm.w));
+            if (has2) {
+                const float4 cn = __ldg(m + lane + 32);
+                cg1 = make_float4(sigmoidf_(cn.x), sigmoidf_(cn.y), sigmoidf_(cn.z), sigmoidf_(cn.w));
+            }
+        };
+        load_cg(m4);
+        const float* oth = mode == 0 ? conv : att;        // the operand that is not staged
+        // mode 0: mix = att * cg + sg * conv (staged = att); mode 1: mix = att * sg + conv * cg (staged = conv)
+        auto emit = [&](int t) {
+            const int64_t tok = tok0 + t;
+            const float sg = __shfl_sync(0xffffffffu, sg_mine, t);
+            const float4* s4 = reinterpret_cast<const float4*>(rows + t * MIX_STRIDE);
+            const float4* o4 = reinterpret_cast<const float4*>(oth + tok * SRK_DIM);
+            float4* y4 = reinterpret_cast<float4*>(mix + tok * SRK_DIM);
+            {
+                const float4 a = s4[lane], b = __ldg(o4 + lane);
+                y4[lane] = make_float4(fmaf(a.x, cg0.x, sg * b.x), fmaf(a.y, cg0.y, sg * b.y), fmaf(a.z, cg0.z, sg * b.z), fmaf(a.w, cg0.w, sg * b.w));
+            }
+            if (has2) {
+                const float4 a = s4[lane + 32], b = __ldg(o4 + lane + 32);
+                y4[lane + 32] = make_float4(fmaf(a.x, cg1.x, sg * b.x), fmaf(a.y, cg1.y, sg * b.y), fmaf(a.z, cg1.z, sg * b.z), fmaf(a.w, cg1.w, sg * b.w));
+            }
+        };
+        if (nt == 32 && tok0 + 32 <= img_end) {           // the common case, unrolled: 8 rows of the other operand in flight per lane
+#pragma unroll 8
+            for (int t = 0; t < 32; ++t) emit(t);
+        } else {
+            for (int t = 0; t < nt; ++t) {
+                if (tok0 + t == img_end) load_cg(m4 + C4); // (warp-uniform) next image's channel map
+                emit(t);
+            }
         }
-        if (has2) {
-            const float4 cm = __ldg(m4 + lane + 32);
-            const float4 cg = make_float4(sigmoidf_(cm.x), sigmoidf_(cm.y), sigmoidf_(cm.z), sigmoidf_(cm.w));
-            float4 o;
-            if (mode == 0) o = make_float4(fmaf(a1.x, cg.x, sg * v1.x), fmaf(a1.y, cg.y, sg * v1.y), fmaf(a1.z, cg.z, sg * v1.z), fmaf(a1.w, cg.w, sg * v1.w));
-            else           o = make_float4(fmaf(v1.x, cg.x, sg * a1.x), fmaf(v1.y, cg.y, sg * a1.y), fmaf(v1.z, cg.z, sg * a1.z), fmaf(v1.w, cg.w, sg * a1.w));
-            o4[lane + 32] = o;
-        }
+        __syncwarp();
     }
 }
 
@@ -390,7 +446,17 @@ cudaError_t launch_row_stats(const float* in, int ld_in, int c_in, int C, int64_
 cudaError_t launch_dat_mix(const float* att, const float* conv, const float* cmap, const float* w1, const float* b1, const float* w2,
                            float b2, int hidden, int mode, float* mix, int64_t tokens, int tokens_per_image, cudaStream_t stream) {
     if (tokens <= 0) return cudaSuccess;
-    dat_mix_kernel<<<grid_for(tokens * 32), 256, 0, stream>>>(att, conv, cmap, w1, b1, w2, b2, hidden, mode, mix, tokens, tokens_per_image);
+    const size_t smem = (static_cast<size_t>(SRK_DIM) * MIX_MAX_HIDDEN + 2 * MIX_MAX_HIDDEN + MIX_WARPS * 32 * MIX_STRIDE) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(dat_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int64_t groups = (tokens + 31) / 32;
+    const int64_t blocks = (groups + MIX_WARPS - 1) / MIX_WARPS;
+    const int grid = static_cast<int>(blocks < 148 * 2 ? blocks : 148 * 2);       // 2 CTAs of 108 KB per SM, persistent over token groups
+    dat_mix_kernel<<<grid, 32 * MIX_WARPS, smem, stream>>>(att, conv, cmap, w1, b1, w2, b2, hidden, mode, mix, tokens, tokens_per_image);
     return cudaGetLastError();
 }
 
