@@ -86,6 +86,28 @@ typedef struct SrkMlpDesc {
 int srk_swin_mlp_fwd(const SrkMlpDesc* desc, const float* x, float* y, const void* wstream /* SRK_MLP_WSTREAM_BYTES */,
                      const float* vec /* SRK_MLP_VEC_FLOATS */, void* stream);
 
+/* Optional fine-grained ordering of the two halves of consecutive Swin blocks that work in place on one residual stream
+ * (a BasicLayer, network_swinir.py:349-416, SRK_MODE_IMAGE).  The kernels are launched with programmatic dependent launch;
+ * with a progress array a kernel does not wait for the whole previous grid but, tile by tile, for the image the tile belongs
+ * to -- the next kernel's first (cold) tiles then run on the SMs that the previous kernel's uneven last round leaves idle.
+ *   progress: int32[2 * batch], zeroed by the caller (stream-ordered) before the first block of the group;
+ *             [0, batch): windows finished by srk_swin_attn_fwd_sync launches, [batch, 2 batch): 128-token tiles finished by
+ *             srk_swin_mlp_fwd_sync launches, per image (both accumulate over the blocks of the group).
+ *   wait_target: value the OTHER half's counter of a tile's image must have reached before the tile is read: block k
+ *             (0-based) of the group passes k * tokens_per_image / 128 to the attention half and (k + 1) * windows_per_image
+ *             to the MLP half; 0 = order after all preceding work in the stream (first launch of a group, or no counters).
+ * sync == NULL (or the plain entry points above): whole-grid ordering. */
+typedef struct SrkBlockSync {
+    int32_t* progress;
+    int32_t batch;
+    int32_t tokens_per_image;
+    int32_t wait_target;
+} SrkBlockSync;
+int srk_swin_attn_fwd_sync(const SrkSwinAttnDesc* desc, const float* x, float* y, const void* wstream, const float* vec,
+                           const float* mask /* or NULL */, const SrkBlockSync* sync /* or NULL */, void* stream);
+int srk_swin_mlp_fwd_sync(const SrkMlpDesc* desc, const float* x, float* y, const void* wstream, const float* vec,
+                          const SrkBlockSync* sync /* or NULL */, void* stream);
+
 /* Token-wise linear layer on tcgen05 for the HAT / DAT paths:  out[tok, :] = act(A[tok, :] W^T + b), N in chunks of 192
  * columns.  Replaces the nn.Linear call sites hat_arch.py:179, :195, :401, :436 and dat_arch.py:371, :435, :483, :526, :79-88.
  *   A  SRK_LIN_A_ROWS  : fp32 token rows [tok][ld_in] (180 valid), optional LayerNorm (affine folded into W, b at pack time)

@@ -254,3 +254,32 @@ def test_tiled_inference_matches_per_tile_oracle_and_shards_bit_identically():
     for world in (2, 4):
         bands = [res.band(lr.cuda(), r, world)[0] for r in range(world)]
         assert torch.equal(torch.cat(bands, dim=1), full[0])
+
+
+def test_block_sync_progress_counters_bit_identical():
+    """Image progress counters (SrkBlockSync): the kernels of a BasicLayer order themselves per image instead of per grid.
+    The result must be bit-identical to whole-grid ordering, run after run, eager and under CUDA-graph replay."""
+    from tpu_superresolution_b200 import swinir
+    cfg = synth.CONFIGS["swinir_x4_d2"] if "swinir_x4_d2" in synth.CONFIGS else synth.CONFIGS["swinir_x2_d2"]
+    m = srk.SwinIR(**cfg.as_kwargs()).eval()
+    m.load_state_dict(synth.make_swinir_state_dict(cfg, seed=77, kind="stress"), strict=True)
+    m.cuda()
+    x = synth.make_lr_batch(16, 64, 64, seed=3).cuda()
+    old = swinir.USE_BLOCK_SYNC
+    try:
+        with torch.no_grad():
+            swinir.USE_BLOCK_SYNC = False
+            ref = m(x).clone()
+            swinir.USE_BLOCK_SYNC = True
+            for _ in range(10):
+                assert torch.equal(m(x), ref)
+            g = srk.GraphedModel(m)
+            for _ in range(10):
+                assert torch.equal(g(x), ref)
+            # a size whose images are not whole 128-token tiles falls back to whole-grid ordering
+            x2 = synth.make_lr_batch(2, 24, 40, seed=4).cuda()
+            y2 = m(x2).clone()
+            swinir.USE_BLOCK_SYNC = False
+            assert torch.equal(m(x2), y2)
+    finally:
+        swinir.USE_BLOCK_SYNC = old

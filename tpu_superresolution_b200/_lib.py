@@ -27,6 +27,11 @@ class SwinAttnDesc(Structure):
                                        "apply_ln", "add_residual", "mask_mode", "mask_nw")]
 
 
+class BlockSync(Structure):
+    """include/srk.h: SrkBlockSync (image progress counters between the halves of consecutive Swin blocks)."""
+    _fields_ = [("progress", c_void_p), ("batch", c_int32), ("tokens_per_image", c_int32), ("wait_target", c_int32)]
+
+
 class MlpDesc(Structure):
     _fields_ = [("num_tokens", c_int64), ("ld_in", c_int32), ("ld_out", c_int32), ("apply_ln", c_int32),
                 ("add_residual", c_int32)]
@@ -84,6 +89,8 @@ def load():
     lib.srk_launch_count.restype = c_int64
     lib.srk_swin_attn_fwd.argtypes = [POINTER(SwinAttnDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.srk_swin_mlp_fwd.argtypes = [POINTER(MlpDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.srk_swin_attn_fwd_sync.argtypes = [POINTER(SwinAttnDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(BlockSync), c_void_p]
+    lib.srk_swin_mlp_fwd_sync.argtypes = [POINTER(MlpDesc), c_void_p, c_void_p, c_void_p, c_void_p, POINTER(BlockSync), c_void_p]
     lib.srk_layernorm_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]
     lib.srk_pixelshuffle_nhwc_fwd.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
     lib.srk_pixelshuffle_nhwc_bias_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
@@ -113,7 +120,7 @@ def load():
     lib.srk_debug_set_winattn_stagger.restype = None
     lib.srk_debug_set_pdl.argtypes = [c_int32]
     lib.srk_debug_set_pdl.restype = None
-    for f in ("srk_swin_attn_fwd", "srk_swin_mlp_fwd", "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd", "srk_pixelshuffle_nhwc_bias_fwd", "srk_bias_act_add_nhwc",
+    for f in ("srk_swin_attn_fwd", "srk_swin_mlp_fwd", "srk_swin_attn_fwd_sync", "srk_swin_mlp_fwd_sync", "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd", "srk_pixelshuffle_nhwc_bias_fwd", "srk_bias_act_add_nhwc",
               "srk_stitch_accumulate", "srk_stitch_normalize", "srk_linear_fwd", "srk_window_attention_fwd",
               "srk_window_attention_table_floats", "srk_cab_gate_add", "srk_dwconv3x3_rows_fwd", "srk_row_stats_fwd", "srk_dat_mix_fwd",
               "srk_dat_channel_gram_fwd", "srk_dat_channel_apply_fwd", "srk_dat_channel_gram_ws_floats", "srk_cab_ws_floats"):
@@ -125,6 +132,7 @@ def load():
 
 
 EXPORTS = ("srk_abi_version", "srk_last_error_string", "srk_launch_count", "srk_swin_attn_fwd", "srk_swin_mlp_fwd",
+           "srk_swin_attn_fwd_sync", "srk_swin_mlp_fwd_sync",
            "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd", "srk_pixelshuffle_nhwc_bias_fwd", "srk_bias_act_add_nhwc", "srk_stitch_accumulate", "srk_stitch_normalize", "srk_debug_set_timeline", "srk_debug_set_stagger",
            "srk_linear_fwd", "srk_window_attention_fwd", "srk_window_attention_table_floats", "srk_debug_set_winattn_stagger", "srk_debug_set_pdl",
            "srk_cab_gate_add", "srk_dwconv3x3_rows_fwd", "srk_row_stats_fwd", "srk_dat_mix_fwd", "srk_dat_channel_gram_fwd",
@@ -154,23 +162,36 @@ def launch_count() -> int:
     return int(load().srk_launch_count())
 
 
+def _block_sync(progress, batch, tokens_per_image, wait_target):
+    if progress is None:
+        return None
+    if not (progress.is_cuda and progress.dtype == torch.int32 and progress.is_contiguous() and progress.numel() >= 2 * batch):
+        raise RuntimeError("progress must be a contiguous CUDA int32 tensor of at least 2 * batch elements")
+    return BlockSync(progress.data_ptr(), batch, tokens_per_image, wait_target)
+
+
 def swin_attn(x, y, wstream, vec, *, mode, batch=0, height=0, width=0, num_windows=0, ld_in, ld_out, shift=0,
-              apply_ln=True, add_residual=True, mask_mode=MASK_NONE, mask=None) -> None:
+              apply_ln=True, add_residual=True, mask_mode=MASK_NONE, mask=None, progress=None, wait_target=0) -> None:
+    """progress / wait_target: image progress counters (include/srk.h: SrkBlockSync); None = whole-grid ordering."""
     lib = load()
     _require_cuda_f32(x, y, vec, mask)
     d = SwinAttnDesc(mode, batch, height, width, num_windows, ld_in, ld_out, shift, int(apply_ln), int(add_residual),
                      mask_mode, 0 if mask is None else mask.shape[0])
+    sync = _block_sync(progress, batch, height * width, wait_target)
     with _timed("swin_attn"):
-        _check(lib.srk_swin_attn_fwd(ctypes.byref(d), x.data_ptr(), y.data_ptr(), wstream.data_ptr(), vec.data_ptr(),
-                                     0 if mask is None else mask.data_ptr(), _stream()), lib)
+        _check(lib.srk_swin_attn_fwd_sync(ctypes.byref(d), x.data_ptr(), y.data_ptr(), wstream.data_ptr(), vec.data_ptr(),
+                                          0 if mask is None else mask.data_ptr(), None if sync is None else ctypes.byref(sync), _stream()), lib)
 
 
-def swin_mlp(x, y, wstream, vec, *, num_tokens, ld_in, ld_out, apply_ln=True, add_residual=True) -> None:
+def swin_mlp(x, y, wstream, vec, *, num_tokens, ld_in, ld_out, apply_ln=True, add_residual=True, progress=None, batch=0,
+             tokens_per_image=0, wait_target=0) -> None:
     lib = load()
     _require_cuda_f32(x, y, vec)
     d = MlpDesc(num_tokens, ld_in, ld_out, int(apply_ln), int(add_residual))
+    sync = _block_sync(progress, batch, tokens_per_image, wait_target)
     with _timed("swin_mlp"):
-        _check(lib.srk_swin_mlp_fwd(ctypes.byref(d), x.data_ptr(), y.data_ptr(), wstream.data_ptr(), vec.data_ptr(), _stream()), lib)
+        _check(lib.srk_swin_mlp_fwd_sync(ctypes.byref(d), x.data_ptr(), y.data_ptr(), wstream.data_ptr(), vec.data_ptr(),
+                                         None if sync is None else ctypes.byref(sync), _stream()), lib)
 
 
 def layernorm(x, y, w, b, *, num_tokens, ld_in, ld_out) -> None:

@@ -40,6 +40,11 @@ int64_t srk_launch_count(void) { return g_launches.load(std::memory_order_relaxe
 
 int srk_swin_attn_fwd(const SrkSwinAttnDesc* d, const float* x, float* y, const void* wstream, const float* vec,
                       const float* mask, void* stream) {
+    return srk_swin_attn_fwd_sync(d, x, y, wstream, vec, mask, nullptr, stream);
+}
+
+int srk_swin_attn_fwd_sync(const SrkSwinAttnDesc* d, const float* x, float* y, const void* wstream, const float* vec,
+                           const float* mask, const SrkBlockSync* sync, void* stream) {
     if (!d || !x || !y || !wstream || !vec) return fail("srk_swin_attn_fwd: null argument");
     if (d->ld_in < SRK_DIM || d->ld_out < SRK_DIM || (d->ld_in & 3) || (d->ld_out & 3))
         return fail("srk_swin_attn_fwd: ld_in/ld_out must be >= %d and multiples of 4 (got %d, %d)", SRK_DIM, d->ld_in, d->ld_out);
@@ -87,12 +92,25 @@ int srk_swin_attn_fwd(const SrkSwinAttnDesc* d, const float* x, float* y, const 
         cudaError_t e = cudaMemcpyAsync(y, x, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream));
         if (e != cudaSuccess) return fail("srk_swin_attn_fwd: %s", cudaGetErrorString(e));
     }
+    if (sync && sync->progress) {
+        if (d->mode != SRK_MODE_IMAGE || (p.nw_img & 1) || sync->batch != d->batch || sync->wait_target < 0)
+            return fail("srk_swin_attn_fwd_sync: progress counters need SRK_MODE_IMAGE, an even number of windows per image and batch == desc->batch");
+        if (sync->wait_target > 0 && x != y) return fail("srk_swin_attn_fwd_sync: wait_target > 0 needs the in-place form (x == y)");
+        p.prog_sig = sync->progress;
+        p.prog_wait = sync->progress + sync->batch;
+        p.wait_target = sync->wait_target;
+    }
     p.dbg = srk::g_timeline;
     p.stagger = p.n_tiles >= 2 * 148 ? srk::g_stagger_attn : 0;
     return check(srk::launch_swin_attn(p, static_cast<cudaStream_t>(stream)), "srk_swin_attn_fwd");
 }
 
 int srk_swin_mlp_fwd(const SrkMlpDesc* d, const float* x, float* y, const void* wstream, const float* vec, void* stream) {
+    return srk_swin_mlp_fwd_sync(d, x, y, wstream, vec, nullptr, stream);
+}
+
+int srk_swin_mlp_fwd_sync(const SrkMlpDesc* d, const float* x, float* y, const void* wstream, const float* vec, const SrkBlockSync* sync,
+                          void* stream) {
     if (!d || !x || !y || !wstream || !vec) return fail("srk_swin_mlp_fwd: null argument");
     if (d->ld_in < SRK_DIM || d->ld_out < SRK_DIM || (d->ld_in & 3) || (d->ld_out & 3))
         return fail("srk_swin_mlp_fwd: ld_in/ld_out must be >= %d and multiples of 4 (got %d, %d)", SRK_DIM, d->ld_in, d->ld_out);
@@ -108,6 +126,18 @@ int srk_swin_mlp_fwd(const SrkMlpDesc* d, const float* x, float* y, const void* 
         cudaError_t e = cudaMemcpyAsync(y, x, static_cast<size_t>(d->num_tokens) * d->ld_in * sizeof(float), cudaMemcpyDeviceToDevice,
                                         static_cast<cudaStream_t>(stream));
         if (e != cudaSuccess) return fail("srk_swin_mlp_fwd: %s", cudaGetErrorString(e));
+    }
+    if (sync && sync->progress) {
+        if (sync->tokens_per_image <= 0 || (sync->tokens_per_image % 128) || sync->wait_target < 0 ||
+            static_cast<int64_t>(sync->batch) * sync->tokens_per_image != d->num_tokens)
+            return fail("srk_swin_mlp_fwd_sync: progress counters need tokens_per_image %% 128 == 0 and batch * tokens_per_image == num_tokens");
+        if (sync->wait_target > 0 && x != y) return fail("srk_swin_mlp_fwd_sync: wait_target > 0 needs the in-place form (x == y)");
+        p.prog_sig = sync->progress + sync->batch;
+        p.prog_wait = sync->progress;
+        p.wait_target = sync->wait_target;
+        p.tokens_per_image = sync->tokens_per_image;
+    } else {
+        p.tokens_per_image = 128;
     }
     p.dbg = srk::g_timeline;
     p.stagger = p.n_tiles >= 2 * 148 ? srk::g_stagger_mlp : 0;

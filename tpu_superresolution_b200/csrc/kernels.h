@@ -19,6 +19,11 @@ struct AttnParams {
     int apply_ln, add_residual, mask_mode, mask_nw;
     unsigned long long* dbg;   // optional timeline buffer (srk_debug_set_timeline), else nullptr
     int stagger;               // start skew in cycles per (CTA index mod 4)
+    // image progress counters (umma.cuh), all optional: after a tile's writes have completed prog_sig[image] += 2 (windows);
+    // with wait_target > 0 the kernel waits per tile for prog_wait[image] >= wait_target instead of for the whole previous grid
+    int* prog_sig;
+    const int* prog_wait;
+    int wait_target;
 };
 
 struct MlpParams {
@@ -32,6 +37,10 @@ struct MlpParams {
     int apply_ln, add_residual;
     unsigned long long* dbg;
     int stagger;
+    int* prog_sig;             // += 1 per finished tile of the image (see AttnParams)
+    const int* prog_wait;
+    int wait_target;
+    int tokens_per_image;      // tile -> image (a multiple of 128 when the counters are used)
 };
 
 // token_linear_kernel (linear_kernel.cu)

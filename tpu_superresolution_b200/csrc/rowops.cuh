@@ -32,9 +32,9 @@ __device__ __forceinline__ void ln_rows_to_image_p(int apply_ln, uint32_t xa, in
         const float* rp = row_ptr(pass);
         const float4* src = reinterpret_cast<const float4*>(rp) + l16;
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        v[pass][0] = rp ? __ldg(src) : z;
-        v[pass][1] = rp ? __ldg(src + 16) : z;
-        v[pass][2] = (rp && live2) ? __ldg(src + 32) : z;
+        v[pass][0] = rp ? ld_cg_f4(src) : z;              // through L2 (see umma.cuh: image progress counters)
+        v[pass][1] = rp ? ld_cg_f4(src + 16) : z;
+        v[pass][2] = (rp && live2) ? ld_cg_f4(src + 32) : z;
     }
     // statistics of all 8 passes first, then the 4 butterfly rounds over all passes at once: the 16 shuffles of a
     // round are independent, so their latency overlaps instead of serialising 8 x 4 dependent steps
@@ -107,9 +107,9 @@ __device__ __forceinline__ void ln_rows_hold_p(int apply_ln, int lane, PtrFn row
         const float* rp = row_ptr(pass);
         const float4* src = reinterpret_cast<const float4*>(rp) + l16;
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        v[pass][0] = rp ? __ldg(src) : z;
-        v[pass][1] = rp ? __ldg(src + 16) : z;
-        v[pass][2] = (rp && live2) ? __ldg(src + 32) : z;
+        v[pass][0] = rp ? ld_cg_f4(src) : z;              // through L2 (see umma.cuh: image progress counters)
+        v[pass][1] = rp ? ld_cg_f4(src + 16) : z;
+        v[pass][2] = (rp && live2) ? ld_cg_f4(src + 32) : z;
     }
     float s[NPASS], q[NPASS];
 #pragma unroll

@@ -95,6 +95,17 @@ enum {  // K1 barrier slots
     B_PR0 = 15, B_PR1 = 16, B_OF = 17, B_OR = 18, B_PJF = 19, B_DRAIN = 20, B_XAFREE = 21, B_COUNT = 22
 };
 
+// Progress-counter report of a finished tile (umma.cuh), called by the 128 threads of softmax group 0 -- the threads that issued the
+// tile's bulk stores.  Out of line: inlined into the row-warp loops it changed their code generation even when never executed.
+static __device__ __noinline__ void signal_progress(int* counter, int add) {
+    bulk_wait0();                       // this thread's copies have completed (global writes performed)
+    named_bar_sync(6, 128);             // ... and those of the other issuing threads
+    if (threadIdx.x == 64) {
+        __threadfence();
+        red_release_gpu_add(counter, add);
+    }
+}
+
 struct TileGeom {
     int64_t base[2];
     int y0[2], x0[2];
@@ -138,7 +149,7 @@ struct RowSrc16 {
     int xo[4];
     __device__ __forceinline__ const float* ptr(int pass) const { return yrow[pass >> 2] ? yrow[pass >> 2] + xo[pass & 3] : nullptr; }
 };
-__device__ __forceinline__ RowSrc16 make_row_src16(const AttnParams& p, const TileGeom& geo, int row0, int lane) {
+__device__ __forceinline__ RowSrc16 make_row_src16(const AttnParams& p, const float* xb, const TileGeom& geo, int row0, int lane) {
     RowSrc16 rs;
     const bool hi = row0 >= 64;
     const int tt0 = row0 & 63, sub = lane >> 4;
@@ -148,7 +159,7 @@ __device__ __forceinline__ RowSrc16 make_row_src16(const AttnParams& p, const Ti
 #pragma unroll
         for (int k = 0; k < 4; ++k) rs.xo[k] = 0;
     } else if (p.mode == SRK_MODE_WINDOWS) {
-        rs.yrow[0] = p.x + (base + tt0 + sub) * p.ld_in;
+        rs.yrow[0] = xb + (base + tt0 + sub) * p.ld_in;
         rs.yrow[1] = rs.yrow[0] + 8 * p.ld_in;
 #pragma unroll
         for (int k = 0; k < 4; ++k) rs.xo[k] = 2 * k * p.ld_in;
@@ -157,8 +168,8 @@ __device__ __forceinline__ RowSrc16 make_row_src16(const AttnParams& p, const Ti
         if (ya >= p.H) ya -= p.H;
         int yb = ya + 1;
         if (yb >= p.H) yb -= p.H;
-        rs.yrow[0] = p.x + (base + static_cast<int64_t>(ya) * p.W) * p.ld_in;
-        rs.yrow[1] = p.x + (base + static_cast<int64_t>(yb) * p.W) * p.ld_in;
+        rs.yrow[0] = xb + (base + static_cast<int64_t>(ya) * p.W) * p.ld_in;
+        rs.yrow[1] = xb + (base + static_cast<int64_t>(yb) * p.W) * p.ld_in;
         const int x0 = (hi ? geo.x0[1] : geo.x0[0]) + sub;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -177,8 +188,8 @@ static __device__ __noinline__ void k1_ln16_to_image(const float* y0, const floa
     rs.yrow[0] = y0; rs.yrow[1] = y1; rs.xo[0] = xo0; rs.xo[1] = xo1; rs.xo[2] = xo2; rs.xo[3] = xo3;
     ln_rows_to_image_p(apply_ln, xa, cw8, lane, [&](int pass) { return rs.ptr(pass); });
 }
-__device__ __forceinline__ void k1_ln16(const AttnParams& p, const TileGeom& geo, uint32_t xa, int cw8, int lane) {
-    const RowSrc16 rs = make_row_src16(p, geo, 16 * cw8, lane);
+__device__ __forceinline__ void k1_ln16(const AttnParams& p, const float* xb, const TileGeom& geo, uint32_t xa, int cw8, int lane) {
+    const RowSrc16 rs = make_row_src16(p, xb, geo, 16 * cw8, lane);
     k1_ln16_to_image(rs.yrow[0], rs.yrow[1], rs.xo[0], rs.xo[1], rs.xo[2], rs.xo[3], p.apply_ln, xa, cw8, lane);
 }
 
@@ -229,8 +240,14 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     SRK_TL0(p.dbg, 14);
-    if (warp != 0) pdl_wait();      // the weight producer starts streaming (constant) slabs while the previous kernel finishes
+    // order after the previous kernel: the whole grid (griddepcontrol.wait), or -- with progress counters -- tile by tile below
+    const bool flag_wait = p.prog_wait != nullptr && p.wait_target > 0;
+    if (warp != 0 && !flag_wait) pdl_wait();      // (the weight producer streams constant slabs either way)
     SRK_TL0(p.dbg, 15);
+    // whole warp: returns the residual stream's base once the image of `tile` has been finished by the previous kernel
+    auto tile_ready = [&](int tile) -> const float* {
+        return p.x + progress_wait(flag_wait ? p.prog_wait + (tile * 2) / p.nw_img : nullptr, p.wait_target);
+    };
 
     if (warp == 0) {
         // ===================================================== weight producer
@@ -336,15 +353,16 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
         TileGeom geo;
         if (static_cast<int>(blockIdx.x) < p.n_tiles) mbar_arrive(&bars[B_XA]);      // first tile: the row warps do all of it
         for (int tile = blockIdx.x; tile + static_cast<int>(gridDim.x) < p.n_tiles; tile += gridDim.x) {
+            const float* xb = tile_ready(tile + gridDim.x);
             set_tile_geom(p, tile + gridDim.x, geo);
             uint2 hb[8][3];
             {
-                const RowSrc16 rs = make_row_src16(p, geo, 64 + 32 * lw, lane);
+                const RowSrc16 rs = make_row_src16(p, xb, geo, 64 + 32 * lw, lane);
                 ln_rows_hold_p<8>(p.apply_ln, lane, [&](int pass) { return rs.ptr(pass); }, hb);
             }
             mbar_wait(&bars[B_XAFREE], ph_free); ph_free ^= 1;
             ln_rows_dump<8>(xa, 64 + 32 * lw, lane, hb);
-            k1_ln16(p, geo, xa, 4 + 2 * lw + 1, lane);
+            k1_ln16(p, xb, geo, xa, 4 + 2 * lw + 1, lane);
             fence_proxy_async_smem();
             mbar_arrive(&bars[B_XA]);
         }
@@ -361,8 +379,9 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
         int uit = 0;
         unsigned long long* udbg = threadIdx.x == 320 ? p.dbg : nullptr;
         auto ln_tile = [&](int tile) {               // gather + normalise rows [0, 64) of the next tile -> x image (16 rows per warp)
+            const float* xb = tile_ready(tile);
             set_tile_geom(p, tile, geo);
-            k1_ln16(p, geo, xa, cwu, lane);
+            k1_ln16(p, xb, geo, xa, cwu, lane);
             fence_proxy_async_smem();
             mbar_arrive(&bars[B_XA]);
         };
@@ -421,8 +440,9 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
         auto tok_of_row = [&](int r) -> int64_t { return tile_tok(p, geo, r); };
         stagger_start(p.stagger);
         if (static_cast<int>(blockIdx.x) < p.n_tiles) {      // first tile's x image (later ones: the utility warps, one tile ahead)
+            const float* xb = tile_ready(blockIdx.x);
             set_tile_geom(p, blockIdx.x, geo);
-            k1_ln16(p, geo, sbase + A_XA, cw8, lane);
+            k1_ln16(p, xb, geo, sbase + A_XA, cw8, lane);
             fence_proxy_async_smem();
             named_bar_sync(1, NROWTHREADS);
             if (g == 0) mbar_arrive(&bars[B_XA]);
@@ -454,6 +474,9 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
         };
         RowState nxt;
         if (static_cast<int>(blockIdx.x) < p.n_tiles) prep(blockIdx.x, nxt);
+        // progress counters: group 0 (the threads that issue the bulk stores) reports a tile once its writes have completed --
+        // not right after the store but after the next tile's first softmax, when the copies are long done and nothing stalls
+        auto signal_tile = [&](int tile) { signal_progress(p.prog_sig + (tile * 2) / p.nw_img, min(2, p.total_windows - 2 * tile)); };
 
         int it = 0;
         unsigned long long* dbg = threadIdx.x == 64 ? p.dbg : nullptr;
@@ -532,6 +555,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
                 tc_fence_before();
                 mbar_arrive(bar_pr);
                 SRK_TL(dbg, it, 6 + 3 * hh);
+                if (p.prog_sig != nullptr && g == 0 && hh == 0 && it > 0) signal_tile(tile - static_cast<int>(gridDim.x));
             }
 
             // ---- phase 4: O accumulators / row sums -> O image (in the V^T region); this group's own heads
@@ -570,6 +594,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
             named_bar_sync(1, NROWTHREADS);         // -> both groups (V^T image)
             SRK_TL(dbg, it, 27);
         }
+        if (p.prog_sig != nullptr && g == 0 && it > 0) signal_tile(static_cast<int>(blockIdx.x) + (it - 1) * static_cast<int>(gridDim.x));
     }
     SRK_TL0(p.dbg, 16);
     tc_fence_before();
@@ -655,8 +680,14 @@ __global__ void __launch_bounds__(LNW ? NTHREADS : 320, 1) swin_mlp_kernel(const
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     SRK_TL0(p.dbg, 14);
-    if (warp != 0) pdl_wait();      // the weight producer starts streaming (constant) slabs while the previous kernel finishes
+    const bool flag_wait = p.prog_wait != nullptr && p.wait_target > 0;      // see swin_attn_kernel
+    if (warp != 0 && !flag_wait) pdl_wait();      // (the weight producer streams constant slabs either way)
     SRK_TL0(p.dbg, 15);
+    auto tile_image = [&](int tile) { return static_cast<int>((static_cast<int64_t>(tile) * 128) / p.tokens_per_image); };
+    // whole warp: returns the residual stream's base once the image of `tile` has been finished by the previous kernel
+    auto tile_ready = [&](int tile) -> const float* {
+        return p.x + progress_wait(flag_wait ? p.prog_wait + tile_image(tile) : nullptr, p.wait_target);
+    };
 
     if (warp == 0) {
         if (lane == 0) {
@@ -717,15 +748,16 @@ __global__ void __launch_bounds__(LNW ? NTHREADS : 320, 1) swin_mlp_kernel(const
         uint32_t ph_free = 0;
         // the first tile is normalised by the 8 row warps (twice the loads in flight at kernel start); these warps start on the second
         for (int tile = blockIdx.x + gridDim.x; tile < p.n_tiles; tile += gridDim.x) {
+            const float* xb = tile_ready(tile);
             auto tok_of_row = [&](int r) -> int64_t {
                 const int64_t tk = static_cast<int64_t>(tile) * 128 + r;
                 return tk < p.num_tokens ? tk : static_cast<int64_t>(-1);
             };
             uint2 h0[4][3], h1[4][3], h2[4][3], h3[4][3];
-            ln_rows_hold<4>(p.x, p.ld_in, p.apply_ln, 32 * lw, lane, tok_of_row, h0);
-            ln_rows_hold<4>(p.x, p.ld_in, p.apply_ln, 32 * lw + 8, lane, tok_of_row, h1);
-            ln_rows_hold<4>(p.x, p.ld_in, p.apply_ln, 32 * lw + 16, lane, tok_of_row, h2);
-            ln_rows_hold<4>(p.x, p.ld_in, p.apply_ln, 32 * lw + 24, lane, tok_of_row, h3);
+            ln_rows_hold<4>(xb, p.ld_in, p.apply_ln, 32 * lw, lane, tok_of_row, h0);
+            ln_rows_hold<4>(xb, p.ld_in, p.apply_ln, 32 * lw + 8, lane, tok_of_row, h1);
+            ln_rows_hold<4>(xb, p.ld_in, p.apply_ln, 32 * lw + 16, lane, tok_of_row, h2);
+            ln_rows_hold<4>(xb, p.ld_in, p.apply_ln, 32 * lw + 24, lane, tok_of_row, h3);
             mbar_wait(&bars[MB_XAFREE], ph_free); ph_free ^= 1;        // the previous tile's fc1 GEMMs have read the x image
             ln_rows_dump<4>(xa, 32 * lw, lane, h0);
             ln_rows_dump<4>(xa, 32 * lw + 8, lane, h1);
@@ -741,15 +773,17 @@ __global__ void __launch_bounds__(LNW ? NTHREADS : 320, 1) swin_mlp_kernel(const
         stagger_start(p.stagger);
         if (static_cast<int>(blockIdx.x) < p.n_tiles) {         // first tile: all 8 row warps normalise it (see the LayerNorm warps)
             const int tile = blockIdx.x;
+            const float* xb = tile_ready(tile);
             auto tok_of_row = [&](int r) -> int64_t {
                 const int64_t tk = static_cast<int64_t>(tile) * 128 + r;
                 return tk < p.num_tokens ? tk : static_cast<int64_t>(-1);
             };
-            ln_rows_to_image(p.x, p.ld_in, p.apply_ln, sbase + M_XA, cw8, lane, tok_of_row);
+            ln_rows_to_image(xb, p.ld_in, p.apply_ln, sbase + M_XA, cw8, lane, tok_of_row);
             fence_proxy_async_smem();
             named_bar_sync(1, NROWTHREADS);
             if (g == 0) mbar_arrive(&bars[MB_XA]);
         }
+        auto signal_tile = [&](int tile) { signal_progress(p.prog_sig + tile_image(tile), 1); };      // group 0, once the tile's stores completed
         int it = 0;
         unsigned long long* dbg = threadIdx.x == 64 ? p.dbg : nullptr;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
@@ -794,14 +828,16 @@ __global__ void __launch_bounds__(LNW ? NTHREADS : 320, 1) swin_mlp_kernel(const
                 SRK_TL(dbg, it, 2 + 2 * c);
             }
             SRK_TL(dbg, it, 7);
+            if (p.prog_sig != nullptr && g == 0 && it > 0) signal_tile(tile - static_cast<int>(gridDim.x));   // previous tile: its copies are long done
             if (!LNW && tile + static_cast<int>(gridDim.x) < p.n_tiles) {
                 // ---- the x image is free (all fc1 GEMMs of this tile are complete): normalise the next tile while fc2 runs
                 const int nt = tile + gridDim.x;
+                const float* xb = tile_ready(nt);
                 auto tok_next = [&](int r) -> int64_t {
                     const int64_t tk = static_cast<int64_t>(nt) * 128 + r;
                     return tk < p.num_tokens ? tk : static_cast<int64_t>(-1);
                 };
-                ln_rows_to_image(p.x, p.ld_in, p.apply_ln, sbase + M_XA, cw8, lane, tok_next);
+                ln_rows_to_image(xb, p.ld_in, p.apply_ln, sbase + M_XA, cw8, lane, tok_next);
                 fence_proxy_async_smem();
                 named_bar_sync(1, NROWTHREADS);
                 if (g == 0) mbar_arrive(&bars[MB_XA]);
@@ -818,6 +854,7 @@ __global__ void __launch_bounds__(LNW ? NTHREADS : 320, 1) swin_mlp_kernel(const
             SRK_TL(dbg, it, 9);
         }
         bulk_wait_read0();          // shared memory must outlive the bulk copies that read it
+        if (p.prog_sig != nullptr && g == 0 && it > 0) signal_tile(static_cast<int>(blockIdx.x) + (it - 1) * static_cast<int>(gridDim.x));
     }
     SRK_TL0(p.dbg, 16);
     tc_fence_before();

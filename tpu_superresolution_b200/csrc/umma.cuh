@@ -116,6 +116,49 @@ __device__ __forceinline__ void bulk_s2g_add_f32(void* gdst, uint32_t smem_src, 
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+// all bulk copies committed by this thread have completed (their global writes are performed), not just read their source
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// ------------------------------------------------------------------ fine-grained ordering between kernels (image progress counters)
+// Consecutive fused Swin kernels run under programmatic dependent launch; instead of waiting for the whole previous grid
+// (griddepcontrol.wait) a kernel may wait, tile by tile, for the image its tile belongs to: the producer kernel adds to a
+// per-image counter once a tile's writes have completed, the consumer polls it with acquire semantics and then reads the
+// tile through L2 (ld.global.cg: the SM's L1 may still hold lines of the residual stream from before the update).
+// (not volatile, no memory clobber: the compiler may batch and hoist these like ordinary loads.  What keeps them behind a
+//  progress wait is a data dependence: progress_wait() returns an opaque zero that the caller adds to the base pointer.)
+__device__ __forceinline__ float4 ld_cg_f4(const float4* p) {
+#ifdef SRK_LN_LDG
+    return __ldg(p);
+#endif
+    float4 v;
+    asm("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// whole warp: returns once *p >= target (p == nullptr: no wait).  The result is always 0, but opaque to the compiler: add it
+// to the base pointer of the loads that must come after the wait.
+__device__ __forceinline__ int progress_wait(const int* p, int target) {
+    if (p != nullptr) {
+        if ((threadIdx.x & 31) == 0 && ld_acquire_gpu(p) < target) {
+            const long long t0 = clock64();
+            while (ld_acquire_gpu(p) < target) {
+                __nanosleep(40);
+                if (clock64() - t0 > SRK_WAIT_TIMEOUT_CYCLES) mbar_timeout_trap(0xfffffffeu, static_cast<uint32_t>(target));
+            }
+        }
+        __syncwarp();
+    }
+    int z;
+    asm volatile("mov.u32 %0, 0;" : "=r"(z)::"memory");
+    return z;
+}
 
 // ------------------------------------------------------------------ TMEM allocation (one full warp)
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot_in_smem, uint32_t ncols) {

@@ -21,6 +21,7 @@ tokens with index math, so no roll / partition / reverse copies exist.
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -186,8 +187,10 @@ class SwinTransformerBlock(nn.Module):
     def calculate_mask(self, x_size):
         return calculate_mask(x_size, self.window_size, self.shift_size)
 
-    def forward_into(self, x: torch.Tensor, x_size: Tuple[int, int], out: torch.Tensor) -> torch.Tensor:
-        """out = block(x); ``out`` may be ``x`` itself (in place)."""
+    def forward_into(self, x: torch.Tensor, x_size: Tuple[int, int], out: torch.Tensor, progress=None, block_index: int = 0) -> torch.Tensor:
+        """out = block(x); ``out`` may be ``x`` itself (in place).  ``progress`` (int32[2 B], zeroed before block 0 of the
+        group) + ``block_index``: image progress counters, so consecutive kernels order themselves per image instead of per
+        grid (include/srk.h: SrkBlockSync)."""
         _inference_only(self)
         H, W = x_size
         B, Ltok, C = x.shape
@@ -199,10 +202,16 @@ class SwinTransformerBlock(nn.Module):
             raise RuntimeError(f"x_size {x_size} must be a multiple of the window size {L.WINDOW}")
         aw, av = self.attn._packed(self.norm1)
         mw, mv = self.mlp._packed(self.norm2)
+        nw_img = (H // L.WINDOW) * (W // L.WINDOW)
+        if progress is not None and (Ltok % 128 or nw_img % 2):
+            progress = None                       # counters need whole 128-token tiles / window pairs per image
+        in_place = x.data_ptr() == out.data_ptr()
         L.swin_attn(x, out, aw, av, mode=L.MODE_IMAGE, batch=B, height=H, width=W, ld_in=C, ld_out=C,
                     shift=self.shift_size, apply_ln=True, add_residual=True,
-                    mask_mode=L.MASK_SHIFT if self.shift_size > 0 else L.MASK_NONE)
-        L.swin_mlp(out, out, mw, mv, num_tokens=B * Ltok, ld_in=C, ld_out=C, apply_ln=True, add_residual=True)
+                    mask_mode=L.MASK_SHIFT if self.shift_size > 0 else L.MASK_NONE, progress=progress,
+                    wait_target=block_index * (Ltok // 128) if (progress is not None and in_place) else 0)
+        L.swin_mlp(out, out, mw, mv, num_tokens=B * Ltok, ld_in=C, ld_out=C, apply_ln=True, add_residual=True, progress=progress,
+                   batch=B, tokens_per_image=Ltok, wait_target=(block_index + 1) * nw_img if progress is not None else 0)
         return out
 
     def forward(self, x, x_size):
@@ -212,6 +221,10 @@ class SwinTransformerBlock(nn.Module):
     def extra_repr(self) -> str:
         return (f"dim={self.dim}, input_resolution={self.input_resolution}, num_heads={self.num_heads}, "
                 f"window_size={self.window_size}, shift_size={self.shift_size}, mlp_ratio={self.mlp_ratio}")
+
+
+# image progress counters between the kernels of a BasicLayer (include/srk.h: SrkBlockSync); SRK_BLOCK_SYNC=0 disables them
+USE_BLOCK_SYNC = os.environ.get("SRK_BLOCK_SYNC", "1") != "0"
 
 
 class BasicLayer(nn.Module):
@@ -236,8 +249,9 @@ class BasicLayer(nn.Module):
         x = x.contiguous()
         out = torch.empty_like(x)
         src = x
-        for blk in self.blocks:          # first block out of place (x is the group's residual), the rest in place
-            blk.forward_into(src, x_size, out)
+        progress = torch.zeros(2 * x.shape[0], dtype=torch.int32, device=x.device) if USE_BLOCK_SYNC else None
+        for i, blk in enumerate(self.blocks):          # first block out of place (x is the group's residual), the rest in place
+            blk.forward_into(src, x_size, out, progress, i)
             src = out
         return out if len(self.blocks) else x
 
