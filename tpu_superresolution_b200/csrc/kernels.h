@@ -88,6 +88,24 @@ struct WinAttnParams {
 
 extern unsigned long long* g_timeline;
 extern int g_stagger_attn, g_stagger_mlp, g_stagger_winattn, g_pdl;
+
+// Launch with programmatic stream serialisation: the kernel may be scheduled while its predecessor in the stream is still running
+// (once every CTA of the predecessor has executed griddepcontrol.launch_dependents, or exited); it orders itself with
+// griddepcontrol.wait (umma.cuh: pdl_wait) before it touches anything the predecessor writes.
+template <typename P>
+inline cudaError_t launch_pdl(void (*kern)(const P), int grid, int threads, size_t smem, cudaStream_t stream, const P& p) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, p);
+}
 cudaError_t launch_swin_attn(const AttnParams& p, cudaStream_t stream);
 cudaError_t launch_swin_mlp(const MlpParams& p, cudaStream_t stream);
 cudaError_t launch_token_linear(const LinearParams& p, cudaStream_t stream);

@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) token_linear_kernel(const Line
     const bool stage_alias = out_rows && p.k_atoms == 6;           // staging rows live in the A image (dead after the GEMM)
     uint8_t* const stage = stage_alias ? sm + L_A : sm + lin_off_stage(p.k_atoms);
 
+    pdl_launch_dependents();            // (see kernels.h: launch_pdl) the prologue below touches only constants
     for (int i = threadIdx.x; i < p.n_chunks * (int)LIN_NC; i += blockDim.x) s_vec[i] = p.bias[i];
     if (threadIdx.x == 0) {
         for (int i = 0; i < LIN_RING_N; ++i) { mbar_init(&bars[LB_FULL + i], 1); mbar_init(&bars[LB_EMPTY + i], 1); }
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) token_linear_kernel(const Line
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_wait();                         // everything the previous kernel wrote is visible from here on
 
     if (warp == 0) {
         // ===================================================== producer
@@ -288,8 +290,7 @@ cudaError_t launch_token_linear(const LinearParams& p, cudaStream_t stream) {
     const bool need_stage = p.out_mode == SRK_LIN_OUT_ROWS && p.k_atoms == 3;
     const uint32_t smem = lin_smem(p.k_atoms, need_stage, p.out_mode == SRK_LIN_OUT_PLANES) + 1024;
     const int grid = p.n_tiles < sms ? p.n_tiles : sms;
-    token_linear_kernel<<<grid, LIN_THREADS, smem, stream>>>(p);
-    return cudaGetLastError();
+    return launch_pdl(token_linear_kernel, grid, LIN_THREADS, smem, stream, p);
 }
 
 }  // namespace srk

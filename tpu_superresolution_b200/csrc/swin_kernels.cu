@@ -877,23 +877,6 @@ static int num_sms() {
     return g_num_sms;
 }
 
-// Launch with programmatic stream serialisation: the kernel may be scheduled while its predecessor in the stream is still running;
-// it orders itself with griddepcontrol.wait (umma.cuh: pdl_wait).
-template <typename P>
-static cudaError_t launch_pdl(void (*kern)(const P), int grid, int threads, size_t smem, cudaStream_t stream, const P& p) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(threads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, p);
-}
-
 cudaError_t launch_swin_attn(const AttnParams& p, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {

@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(320, 1) winattn_kernel(const WinAttnParams p) 
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::BAR_OFF);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + W_COUNT + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_launch_dependents();
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
@@ -152,6 +153,7 @@ __global__ void __launch_bounds__(320, 1) winattn_kernel(const WinAttnParams p) 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_wait();                         // (kernels.h: launch_pdl) the prologue above touched nothing the previous kernel writes
     const int npairs = (p.n_heads + 1) >> 1;
     const int nw_img = p.nwy * p.nwx;
 
@@ -447,8 +449,7 @@ static cudaError_t launch_cfg(const WinAttnParams& p, cudaStream_t stream) {
         configured = true;
     }
     const int grid = p.n_items < wa_num_sms() ? p.n_items : wa_num_sms();
-    kern<<<grid, 320, C::SMEM, stream>>>(p);
-    return cudaGetLastError();
+    return launch_pdl(kern, grid, 320, C::SMEM, stream, p);
 }
 
 int winattn_table_floats(int kind) {
