@@ -20,7 +20,6 @@
 namespace srk {
 
 namespace {
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

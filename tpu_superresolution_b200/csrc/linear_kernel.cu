@@ -51,9 +51,6 @@ static_assert(lin_smem(3, true) <= 232448 && lin_smem(6, false) <= 232448 && lin
               lin_smem(6, false, true) <= 232448, "token_linear shared memory");
 enum { LB_FULL = 0, LB_EMPTY = 3, LB_AFULL = 6, LB_AEMPTY = 7, LB_ACCF = 8, LB_ACCE = 10, LB_DRAIN = 12, LB_COUNT = 13 };
 
-__device__ __forceinline__ void st_global_v4b(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
 }  // namespace
 
 __global__ void __launch_bounds__(LIN_THREADS, 1) token_linear_kernel(const LinearParams p) {
@@ -190,7 +187,6 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) token_linear_kernel(const Line
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
             if (dbg && it < 8) dbg[it * 64 + 0] = clock64();
             const int64_t tok = static_cast<int64_t>(tile) * 128 + row;
-            const bool live = tok < p.num_tokens;
             auto tok_of_row = [&](int r) -> int64_t {
                 const int64_t tk = static_cast<int64_t>(tile) * 128 + r;
                 return tk < p.num_tokens ? tk : static_cast<int64_t>(-1);

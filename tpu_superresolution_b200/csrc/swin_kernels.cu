@@ -36,8 +36,6 @@ constexpr int RING_N = 3;
 
 constexpr uint32_t IDESC_128x128 = umma_idesc_bf16(128, 128);
 constexpr uint32_t IDESC_128x192 = umma_idesc_bf16(128, 192);
-constexpr uint32_t IDESC_128x64 = umma_idesc_bf16(128, 64);
-constexpr uint32_t IDESC_128x32 = umma_idesc_bf16(128, 32);
 constexpr uint32_t IDESC_64x64 = umma_idesc_bf16(64, 64);
 constexpr uint32_t IDESC_64x32_BMN = umma_idesc_bf16(64, 32) | (1u << 16);     // B (= V) MN-major: [key][dim] rows
 constexpr float LOG2E = 1.4426950408889634f;
@@ -375,7 +373,6 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
         const uint32_t xa = sbase + A_XA, qki = sbase + A_QKI;
         uint32_t ph_qkf[2] = {0, 0};
         TileGeom geo;
-        auto tok_of_row = [&](int r) -> int64_t { return tile_tok(p, geo, r); };
         int uit = 0;
         unsigned long long* udbg = threadIdx.x == 320 ? p.dbg : nullptr;
         auto ln_tile = [&](int tile) {               // gather + normalise rows [0, 64) of the next tile -> x image (16 rows per warp)
@@ -767,7 +764,7 @@ __global__ void __launch_bounds__(LNW ? NTHREADS : 320, 1) swin_mlp_kernel(const
             mbar_arrive(&bars[MB_XA]);
         }
     } else {
-        const int cw8 = warp - 2, g = cw8 >> 2, q = warp & 3, row = q * 32 + lane;
+        const int cw8 = warp - 2, g = cw8 >> 2, q = warp & 3;
         const uint32_t lanebase = static_cast<uint32_t>(q * 32) << 16;
         uint32_t ph_f1[2] = {0, 0}, ph_f2 = 0, nchunk = 0;
         stagger_start(p.stagger);
