@@ -29,6 +29,7 @@ ms = sorted(a.elapsed_time(b) for a, b in evs)
 print(f"{name}: eager step median {ms[len(ms)//2]:.3f} ms")
 prof = {}
 L.PROFILE = prof
+L.PROFILE_DETAIL = True
 for _ in range(3):
     m(x)
 torch.cuda.synchronize()

@@ -57,6 +57,7 @@ WA_HAT_WMSA, WA_HAT_OCAB, WA_DAT_8x32, WA_DAT_32x8 = 0, 1, 2, 3
 _lib = None
 # bench.py sets this to a dict to get CUDA-event timings of every launch: {"swin_attn": [(ev0, ev1), ...], ...}
 PROFILE = None
+PROFILE_DETAIL = False          # True: token_linear launches are keyed by shape in PROFILE
 
 
 class _timed:
@@ -263,7 +264,9 @@ def linear(a, wstream, bias, out, *, num_tokens, a_mode, k_atoms=3, ld_in=0, app
         raise RuntimeError("linear: weight stream / bias size does not match n_chunks, k_atoms")
     d = LinearDesc(num_tokens, a_mode, k_atoms, ld_in, int(apply_ln), n_chunks, act, out_mode, ld_out, int(add_residual),
                    plane_phase_mask)
-    with _timed("linear"):
+    label = "linear" if PROFILE is None or not PROFILE_DETAIL else \
+        f"linear {'rows' if a_mode == LIN_A_ROWS else 'planes'}(k{k_atoms}){'+ln' if apply_ln else ''} -> {'planes' if out_mode == LIN_OUT_PLANES else 'rows'} x{n_chunks}{' gelu' if act else ''}{' +res' if add_residual else ''}"
+    with _timed(label):
         _check(lib.srk_linear_fwd(ctypes.byref(d), a.data_ptr(), wstream.data_ptr(), bias.data_ptr(), out.data_ptr(), _stream()), lib)
 
 
