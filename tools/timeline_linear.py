@@ -43,3 +43,30 @@ for name, fn in (("qkv", qkv_run), ("proj", proj_run)):
         if not ev:
             continue
         print(f"  tile {it}: " + "  ".join(f"[{i}] {c - t0}" for c, i in ev))
+
+# DAT: fp32 rows (no LayerNorm) -> 180 fp32 rows added into the residual stream (proj / fc2 of the DAT blocks)
+rw, rb = packing.pack_rows_linear(sd[pre + "attn.proj.weight"].cuda(), sd[pre + "attn.proj.bias"].cuda())
+src = x.clone()
+def rows_run():
+    L.linear(src, rw, rb, y, num_tokens=T, a_mode=L.LIN_A_ROWS, ld_in=180, apply_ln=False, n_chunks=1, out_mode=L.LIN_OUT_ROWS, ld_out=180, add_residual=True)
+for _ in range(3):
+    rows_run()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(20):
+    rows_run()
+e1.record(); torch.cuda.synchronize()
+print(f"rows->rows+res T={T}: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us per launch")
+buf = torch.zeros(512, dtype=torch.int64, device="cuda")
+lib.srk_debug_set_timeline(buf.data_ptr())
+rows_run()
+torch.cuda.synchronize()
+lib.srk_debug_set_timeline(0)
+t = buf.cpu().view(8, 64)
+t0 = int(t[0, 62])
+print(f"  kernel-body start -> first LN done: {int(t[0, 63]) - t0}")
+for it in range(8):
+    ev = [(int(t[it, i]), i) for i in range(0, 13) if int(t[it, i]) != 0]
+    if ev:
+        print(f"  tile {it}: " + "  ".join(f"[{i}] {c - t0}" for c, i in ev))
