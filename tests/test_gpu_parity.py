@@ -283,3 +283,22 @@ def test_block_sync_progress_counters_bit_identical():
             assert torch.equal(m(x2), y2)
     finally:
         swinir.USE_BLOCK_SYNC = old
+
+
+def test_pipelined_runner_matches_direct_forward():
+    """srk.PipelinedRunner (host-to-host loop with the D2H copy on a side stream) returns exactly the model's outputs, in order."""
+    cfg = synth.CONFIGS["swinir_x2_d2"]
+    m = srk.SwinIR(**cfg.as_kwargs()).eval()
+    m.load_state_dict(synth.make_swinir_state_dict(cfg, seed=5, kind="init"), strict=True)
+    m.cuda()
+    xs = [synth.make_lr_batch(2, 32, 32, seed=40 + i).pin_memory() for i in range(5)]
+    with torch.no_grad():
+        refs = [m(x.cuda()).cpu() for x in xs]
+    pr = srk.PipelinedRunner(srk.GraphedModel(m), depth=2)
+    outs = [torch.empty_like(refs[0]).pin_memory() for _ in xs]
+    for x, o in zip(xs, outs):
+        pr.submit(x, o)
+    pr.drain()
+    torch.cuda.synchronize()
+    for o, r in zip(outs, refs):
+        assert torch.equal(o, r)

@@ -6,10 +6,10 @@ from . import hat
 from .hat import HAT, HAB, OCAB, RHAG, CAB, ChannelAttention, AttenBlocks
 from . import dat
 from .dat import DAT, DATB, ResidualGroup, Adaptive_Spatial_Attention, Adaptive_Channel_Attention, SGFN, SpatialGate, DynamicPosBias
-from .graphs import GraphedModel
+from .graphs import GraphedModel, PipelinedRunner
 
 __all__ = ["Mlp", "WindowAttention", "SwinTransformerBlock", "BasicLayer", "RSTB", "PatchEmbed", "PatchUnEmbed",
            "PixelShuffle", "Upsample", "UpsampleOneStep", "SwinIR", "calculate_mask",
            "hat", "HAT", "HAB", "OCAB", "RHAG", "CAB", "ChannelAttention", "AttenBlocks",
            "dat", "DAT", "DATB", "ResidualGroup", "Adaptive_Spatial_Attention", "Adaptive_Channel_Attention", "SGFN", "SpatialGate",
-           "DynamicPosBias", "GraphedModel"]
+           "DynamicPosBias", "GraphedModel", "PipelinedRunner"]

@@ -59,3 +59,49 @@ class GraphedModel(nn.Module):
         static_in.copy_(x, non_blocking=True)
         graph.replay()
         return static_out
+
+
+class PipelinedRunner:
+    """Host-to-host serving loop around a ``GraphedModel``: ``submit(host_in, host_out)`` copies a pinned host batch into the
+    graph's input buffer, replays the forward and copies the result into the pinned ``host_out`` -- the device-to-host copy
+    runs on a side stream, so it overlaps the next batch's forward (the 12.6 MB SR batch of SwinIR x4 B=16 takes ~0.25 ms of
+    PCIe time, 5 % of a step).  Results are complete after ``drain()`` (or once ``submit`` has been called ``depth`` more
+    times).  ``depth`` device-side output buffers decouple the graph's static output from the copies in flight.
+    """
+
+    def __init__(self, graphed: GraphedModel, depth: int = 2):
+        self.graphed = graphed
+        self.depth = depth
+        self._copy_stream = None
+        self._bufs = []          # device staging buffers
+        self._ready = []         # forward finished -> staging buffer holds the result
+        self._done = []          # D2H finished -> staging buffer free
+        self._i = 0
+
+    @torch.no_grad()
+    def submit(self, host_in: torch.Tensor, host_out: torch.Tensor) -> None:
+        y = self.graphed(host_in)                                   # H2D into the static input + replay, current stream
+        cur = torch.cuda.current_stream(y.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=y.device)
+            self._bufs = [torch.empty_like(y) for _ in range(self.depth)]
+            self._ready = [torch.cuda.Event() for _ in range(self.depth)]
+            self._done = [None] * self.depth
+        b = self._i % self.depth
+        self._i += 1
+        if self._done[b] is not None:
+            cur.wait_event(self._done[b])                           # the copy that last read this staging buffer has finished
+        self._bufs[b].copy_(y, non_blocking=True)                   # device-to-device: frees the graph's static output
+        self._ready[b].record(cur)
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._ready[b])
+            host_out.copy_(self._bufs[b], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+            self._done[b] = ev
+
+    def drain(self) -> None:
+        """Make the current stream wait for every copy in flight (then synchronise the stream / an event as usual)."""
+        if self._copy_stream is not None:
+            torch.cuda.current_stream(self._bufs[0].device).wait_stream(self._copy_stream)
+
