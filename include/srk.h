@@ -179,6 +179,10 @@ int srk_layernorm_fwd(const float* x, float* y, const float* w, const float* b, 
  * (hat_arch.py:307).  w1 (hidden, 180), w2 (180, hidden), hidden <= 32; sums_ws: srk_cab_ws_floats() floats of scratch (per-chunk
  * partial sums, reduced in a fixed order: results are run-to-run identical). */
 int srk_cab_ws_floats(int32_t batch, int32_t tokens_per_image);
+/* mean[b, c] = mean over the tokens of x[b, :, c] for channels-last (batch, tokens_per_image, 180) fp32 rows: the
+ * AdaptiveAvgPool2d(1) in front of DAT's channel interaction (dat_arch.py:305-310).  sums_ws: srk_cab_ws_floats() floats
+ * (per-chunk partial sums, reduced in a fixed order). */
+int srk_token_mean_fwd(const float* x, float* mean, float* sums_ws, int32_t batch, int32_t tokens_per_image, void* stream);
 int srk_cab_gate_add(const float* y, const float* y_bias /* bias of the conv that produced y, or NULL: y + y_bias is used */, float* out, float* sums_ws, const float* w1, const float* b1, const float* w2, const float* b2,
                      int32_t hidden, float scale, int32_t batch, int32_t tokens_per_image, void* stream);
 

@@ -111,6 +111,7 @@ def load():
     lib.srk_dat_channel_gram_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]
     lib.srk_dat_channel_gram_ws_floats.argtypes = [c_int32, c_int32]
     lib.srk_cab_ws_floats.argtypes = [c_int32, c_int32]
+    lib.srk_token_mean_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]
     lib.srk_dat_channel_apply_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]
     lib.srk_cab_gate_add.argtypes = [c_void_p] * 8 + [c_int32, ctypes.c_float, c_int32, c_int32, c_void_p]
     lib.srk_debug_set_timeline.argtypes = [c_void_p]
@@ -124,7 +125,7 @@ def load():
     for f in ("srk_swin_attn_fwd", "srk_swin_mlp_fwd", "srk_swin_attn_fwd_sync", "srk_swin_mlp_fwd_sync", "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd", "srk_pixelshuffle_nhwc_bias_fwd", "srk_bias_act_add_nhwc",
               "srk_stitch_accumulate", "srk_stitch_normalize", "srk_linear_fwd", "srk_window_attention_fwd",
               "srk_window_attention_table_floats", "srk_cab_gate_add", "srk_dwconv3x3_rows_fwd", "srk_row_stats_fwd", "srk_dat_mix_fwd",
-              "srk_dat_channel_gram_fwd", "srk_dat_channel_apply_fwd", "srk_dat_channel_gram_ws_floats", "srk_cab_ws_floats"):
+              "srk_dat_channel_gram_fwd", "srk_dat_channel_apply_fwd", "srk_dat_channel_gram_ws_floats", "srk_cab_ws_floats", "srk_token_mean_fwd"):
         getattr(lib, f).restype = c_int32
     if lib.srk_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libsrk.so ABI {lib.srk_abi_version()} != expected {ABI_VERSION}; rebuild")
@@ -137,7 +138,7 @@ EXPORTS = ("srk_abi_version", "srk_last_error_string", "srk_launch_count", "srk_
            "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd", "srk_pixelshuffle_nhwc_bias_fwd", "srk_bias_act_add_nhwc", "srk_stitch_accumulate", "srk_stitch_normalize", "srk_debug_set_timeline", "srk_debug_set_stagger",
            "srk_linear_fwd", "srk_window_attention_fwd", "srk_window_attention_table_floats", "srk_debug_set_winattn_stagger", "srk_debug_set_pdl",
            "srk_cab_gate_add", "srk_dwconv3x3_rows_fwd", "srk_row_stats_fwd", "srk_dat_mix_fwd", "srk_dat_channel_gram_fwd",
-           "srk_dat_channel_apply_fwd", "srk_dat_channel_gram_ws_floats", "srk_cab_ws_floats")
+           "srk_dat_channel_apply_fwd", "srk_dat_channel_gram_ws_floats", "srk_cab_ws_floats", "srk_token_mean_fwd")
 
 
 def _check(rc: int, lib) -> None:
@@ -293,6 +294,17 @@ def cab_gate_add(y, out, w1, b1, w2, b2, *, scale, batch, tokens_per_image, y_bi
         _check(lib.srk_cab_gate_add(y.data_ptr(), y_bias.data_ptr() if y_bias is not None else None, out.data_ptr(), ws.data_ptr(),
                                     w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), w1.shape[0], float(scale), batch,
                                     tokens_per_image, _stream()), lib)
+
+
+def token_mean(x, *, batch, tokens_per_image):
+    """srk_token_mean_fwd: (batch, tokens, 180) fp32 rows -> (batch, 180) mean over the tokens (deterministic)."""
+    lib = load()
+    _require_cuda_f32(x)
+    ws = torch.empty(lib.srk_cab_ws_floats(batch, tokens_per_image), dtype=torch.float32, device=x.device)
+    mean = torch.empty(batch, DIM, dtype=torch.float32, device=x.device)
+    with _timed("token_mean"):
+        _check(lib.srk_token_mean_fwd(x.data_ptr(), mean.data_ptr(), ws.data_ptr(), batch, tokens_per_image, _stream()), lib)
+    return mean
 
 
 def _ptr(t):

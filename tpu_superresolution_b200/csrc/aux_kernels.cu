@@ -287,6 +287,25 @@ __global__ void __launch_bounds__(256) cab_gate_add_kernel(const float* __restri
     }
 }
 
+// ---- mean over the tokens of channels-last (batch, tokens, 180) rows: the per-chunk partial sums of cab_pool_kernel, summed in a
+//      fixed order (run-to-run identical).  DAT's channel-interaction pooling (dat_arch.py:305-310, AdaptiveAvgPool2d(1)).
+__global__ void __launch_bounds__(192) token_mean_reduce_kernel(const float* __restrict__ sums, float* __restrict__ mean, int chunks,
+                                                                int tokens_per_image) {
+    const int b = blockIdx.x, c = threadIdx.x;
+    if (c >= SRK_DIM) return;
+    float s = 0.f;
+    for (int k = 0; k < chunks; ++k) s += __ldg(sums + (static_cast<int64_t>(b) * chunks + k) * SRK_DIM + c);
+    mean[b * SRK_DIM + c] = s / static_cast<float>(tokens_per_image);
+}
+
+cudaError_t launch_token_mean(const float* x, float* mean, float* sums, int batch, int tokens_per_image, cudaStream_t stream) {
+    if (batch <= 0 || tokens_per_image <= 0) return cudaSuccess;
+    const int chunks = (tokens_per_image + CAB_TOK_PER_BLOCK - 1) / CAB_TOK_PER_BLOCK;
+    cab_pool_kernel<<<dim3(chunks, batch), 192, 0, stream>>>(x, sums, tokens_per_image);
+    token_mean_reduce_kernel<<<batch, 192, 0, stream>>>(sums, mean, chunks, tokens_per_image);
+    return cudaGetLastError();
+}
+
 int cab_ws_floats(int batch, int tokens_per_image) {
     return batch * ((tokens_per_image + CAB_TOK_PER_BLOCK - 1) / CAB_TOK_PER_BLOCK) * SRK_DIM;
 }

@@ -284,6 +284,12 @@ int srk_dat_mix_fwd(const float* att, const float* conv, const float* cmap, cons
                                      static_cast<cudaStream_t>(stream)), "srk_dat_mix_fwd");
 }
 
+int srk_token_mean_fwd(const float* x, float* mean, float* sums_ws, int32_t batch, int32_t tokens_per_image, void* stream) {
+    if (!x || !mean || !sums_ws) return fail("srk_token_mean_fwd: null argument");
+    if (batch < 0 || batch > 65535 || tokens_per_image < 0) return fail("srk_token_mean_fwd: bad shape");
+    return check(srk::launch_token_mean(x, mean, sums_ws, batch, tokens_per_image, static_cast<cudaStream_t>(stream)), "srk_token_mean_fwd");
+}
+
 int srk_dat_channel_gram_ws_floats(int32_t batch, int32_t tokens_per_image) { return srk::channel_gram_ws_floats(batch, tokens_per_image); }
 int srk_cab_ws_floats(int32_t batch, int32_t tokens_per_image) { return srk::cab_ws_floats(batch, tokens_per_image); }
 

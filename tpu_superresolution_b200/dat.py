@@ -238,7 +238,8 @@ class _AIM(nn.Module):
     def _channel_map(self, rows):
         """channel_interaction (dat_arch.py:305-310) on (B, N, C) rows -> (B, C) map before the sigmoid; a few hundred MACs per image."""
         B, N, C = rows.shape
-        return self.channel_interaction[1:](rows.mean(dim=1).view(B, C, 1, 1)).reshape(B, C).contiguous()
+        pooled = L.token_mean(rows.contiguous(), batch=B, tokens_per_image=N)        # AdaptiveAvgPool2d(1), deterministic
+        return self.channel_interaction[1:](pooled.view(B, C, 1, 1)).reshape(B, C).contiguous()
 
     def _mix(self, att, conv_x, cmap, mode):
         w1, b1, w2, b2 = self._aim_packed()[3:]
