@@ -29,7 +29,7 @@ import torch.nn.functional as F
 
 from . import _lib as L
 from . import packing
-from .swinir import Upsample, UpsampleOneStep, _PackedCache, _inference_only
+from .swinir import Upsample, UpsampleOneStep, _PackedCache, _conv_tail, _inference_only
 
 
 def is_shifted(rg_idx: int, b_idx: int) -> bool:
@@ -460,7 +460,10 @@ class ResidualGroup(nn.Module):
         for blk in self.blocks:          # first block out of place (x is the group's residual), the rest in place
             blk.forward_into(src, x_size, out)
             src = out
-        y = self.conv(out.view(B, H, W, C).permute(0, 3, 1, 2))
+        img = out.view(B, H, W, C).permute(0, 3, 1, 2)
+        if isinstance(self.conv, nn.Conv2d):      # '1conv': bias + the group's residual in one pass behind the bias-free conv
+            return _conv_tail(self.conv, img, residual=x).permute(0, 2, 3, 1).reshape(B, Ltok, C)
+        y = self.conv(img)
         return x + y.permute(0, 2, 3, 1).reshape(B, Ltok, C)
 
 
@@ -542,10 +545,14 @@ class DAT(nn.Module):
         self._prepare(x.device)
         self.mean = self.mean.type_as(x)
         x = ((x - self.mean) * self.img_range).contiguous(memory_format=torch.channels_last)
-        x = self.conv_first(x)
-        x = self.conv_after_body(self.forward_features(x)) + x
+        x = _conv_tail(self.conv_first, x)
+        if isinstance(self.conv_after_body, nn.Conv2d):
+            x = _conv_tail(self.conv_after_body, self.forward_features(x), residual=x)
+        else:
+            x = self.conv_after_body(self.forward_features(x)) + x
         if self.upsampler == 'pixelshuffle':
-            x = self.conv_before_upsample(x)
+            cbu = self.conv_before_upsample                   # Sequential(conv, LeakyReLU)
+            x = _conv_tail(cbu[0], x, act=L.ACT_LEAKY_RELU, slope=cbu[1].negative_slope)
             x = self.conv_last(self.upsample(x))
         else:
             x = self.upsample(x)
