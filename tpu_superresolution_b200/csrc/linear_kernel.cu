@@ -27,7 +27,7 @@
 namespace srk {
 
 namespace {
-constexpr int LIN_THREADS = 448;          // producer, MMA issuer, 8 row warps, 4 LayerNorm warps
+constexpr int LIN_THREADS = 512;          // producer, MMA issuer, 8 row warps, 6 LayerNorm warps (16 warps: still 128 registers per thread)
 constexpr int LIN_RING_N = 3;
 constexpr uint32_t LIN_SLAB = 24576;             // 192 rows x 64 k
 constexpr uint32_t LIN_NC = 192;                 // columns per chunk
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) token_linear_kernel(const Line
     for (int i = threadIdx.x; i < p.n_chunks * (int)LIN_NC; i += blockDim.x) s_vec[i] = p.bias[i];
     if (threadIdx.x == 0) {
         for (int i = 0; i < LIN_RING_N; ++i) { mbar_init(&bars[LB_FULL + i], 1); mbar_init(&bars[LB_EMPTY + i], 1); }
-        mbar_init(&bars[LB_AFULL], a_rows ? 128 : 1);
+        mbar_init(&bars[LB_AFULL], a_rows ? 192 : 1);        // row input: 6 LayerNorm warps (first tile: 4 row warps + LayerNorm warps 4, 5)
         mbar_init(&bars[LB_AEMPTY], 1);
         mbar_init(&bars[LB_ACCF], 1);     mbar_init(&bars[LB_ACCF + 1], 1);
         mbar_init(&bars[LB_ACCE], 256);   mbar_init(&bars[LB_ACCE + 1], 256);
@@ -139,26 +139,29 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) token_linear_kernel(const Line
         }
         __syncwarp();
     } else if (warp >= 10) {
-        // ===================================================== 4 LayerNorm warps (fp32 row input): run one tile ahead of the GEMMs
+        // ===================================================== 6 LayerNorm warps (fp32 row input): run one tile ahead of the GEMMs
         if (a_rows) {
-            const int lw = warp - 10;                 // rows [32 lw, 32 lw + 32) of the tile
+            const int lw = warp - 10;                 // 0..5
             uint32_t ph_ae = 0;
-            // the first tile is normalised by the 8 row warps (twice the loads in flight at kernel start); these warps start on the second
+            // the first tile is normalised by the 8 row warps (twice the loads in flight at kernel start); these warps start on the second.
+            // Rows per warp: 24 (warps 0-3) or 16 (warps 4, 5) -- with four warps of 32 rows the LayerNorm (6-9 K cycles per tile) was
+            // slower than the GEMM + epilogue of a 180-wide output (5 K).
+            const int nb = lw < 4 ? 3 : 2;
+            const int r0 = lw < 4 ? 24 * lw : 96 + 16 * (lw - 4);
+            if (lw >= 4 && static_cast<int>(blockIdx.x) < p.n_tiles) mbar_arrive(&bars[LB_AFULL]);      // first tile: see the barrier's count
             for (int tile = blockIdx.x + gridDim.x; tile < p.n_tiles; tile += gridDim.x) {
                 auto tok_of_row = [&](int r) -> int64_t {
                     const int64_t tk = static_cast<int64_t>(tile) * 128 + r;
                     return tk < p.num_tokens ? tk : static_cast<int64_t>(-1);
                 };
-                uint2 h0[4][3], h1[4][3], h2[4][3], h3[4][3];     // 32 rows x 192 channels / 32 lanes, bf16: 96 registers
-                ln_rows_hold<4>(p.x, p.ld_in, p.apply_ln, 32 * lw, lane, tok_of_row, h0);
-                ln_rows_hold<4>(p.x, p.ld_in, p.apply_ln, 32 * lw + 8, lane, tok_of_row, h1);
-                ln_rows_hold<4>(p.x, p.ld_in, p.apply_ln, 32 * lw + 16, lane, tok_of_row, h2);
-                ln_rows_hold<4>(p.x, p.ld_in, p.apply_ln, 32 * lw + 24, lane, tok_of_row, h3);
+                uint2 h0[4][3], h1[4][3], h2[4][3];               // up to 24 rows x 192 channels / 32 lanes, bf16: 72 registers
+                ln_rows_hold<4>(p.x, p.ld_in, p.apply_ln, r0, lane, tok_of_row, h0);
+                ln_rows_hold<4>(p.x, p.ld_in, p.apply_ln, r0 + 8, lane, tok_of_row, h1);
+                if (nb == 3) ln_rows_hold<4>(p.x, p.ld_in, p.apply_ln, r0 + 16, lane, tok_of_row, h2);
                 mbar_wait(&bars[LB_AEMPTY], ph_ae); ph_ae ^= 1;             // the previous tile's MMAs have read the A image
-                ln_rows_dump<4>(sbase + L_A, 32 * lw, lane, h0);
-                ln_rows_dump<4>(sbase + L_A, 32 * lw + 8, lane, h1);
-                ln_rows_dump<4>(sbase + L_A, 32 * lw + 16, lane, h2);
-                ln_rows_dump<4>(sbase + L_A, 32 * lw + 24, lane, h3);
+                ln_rows_dump<4>(sbase + L_A, r0, lane, h0);
+                ln_rows_dump<4>(sbase + L_A, r0 + 8, lane, h1);
+                if (nb == 3) ln_rows_dump<4>(sbase + L_A, r0 + 16, lane, h2);
                 fence_proxy_async_smem();
                 mbar_arrive(&bars[LB_AFULL]);
             }
