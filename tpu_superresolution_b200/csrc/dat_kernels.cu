@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(32 * MIX_WARPS) dat_mix_kernel(const float* __
 constexpr int GRAM_TOK = 32;
 constexpr int GRAM_STRIDE = SRK_HEAD_DIM * SRK_HEAD_DIM + 2 * SRK_HEAD_DIM;      // 960 floats per (image, head)
 // thread (head, 5x5 tile of the 30x30 products): 10 shared-memory reads per 25 FMAs; 6 heads x 36 tiles = 216 threads
-constexpr int GRAM_CHUNKS = 8;             // token chunks per block: partial sums stay in registers across them
+constexpr int GRAM_CHUNKS = 4;             // token chunks per block: partial sums stay in registers across them (8: too few blocks, 104 vs 77 us; 2: too many partials)
 __global__ void __launch_bounds__(224) channel_gram_kernel(const float* __restrict__ qkv, float* __restrict__ part, int tokens_per_image) {
     __shared__ float s_qk[GRAM_TOK][2 * SRK_DIM + 4];            // q | k rows of the token chunk
     const int b = blockIdx.y;
