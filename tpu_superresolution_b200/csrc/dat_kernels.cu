@@ -382,28 +382,34 @@ constexpr int APPLY_TOK = 32;
 // shared memory as warp-wide broadcasts (one wavefront per read); 6 warps per block = the 6 heads of the same 32 tokens
 __global__ void __launch_bounds__(192) channel_apply_kernel(const float* __restrict__ qkv, const float* __restrict__ attn, float* __restrict__ out,
                                                             int tokens_per_image) {
-    __shared__ float s_a[SRK_HEADS * SRK_HEAD_DIM * SRK_HEAD_DIM];
+    // matrix rows padded 30 -> 32 floats: a row is read as eight 16-byte broadcasts instead of thirty 4-byte ones (the kernel was
+    // bound by the shared-memory instruction rate: one LDS per FMA)
+    __shared__ __align__(16) float s_a[SRK_HEADS * SRK_HEAD_DIM * 32];
     const int b = blockIdx.y;
-    for (int i = threadIdx.x; i < SRK_HEADS * SRK_HEAD_DIM * SRK_HEAD_DIM; i += blockDim.x)
-        s_a[i] = attn[static_cast<int64_t>(b) * SRK_HEADS * SRK_HEAD_DIM * SRK_HEAD_DIM + i];
+    for (int i = threadIdx.x; i < SRK_HEADS * SRK_HEAD_DIM * 32; i += blockDim.x) {
+        const int r = i >> 5, c = i & 31;                 // r = h * 30 + d1
+        s_a[i] = c < SRK_HEAD_DIM ? attn[static_cast<int64_t>(b) * SRK_HEADS * SRK_HEAD_DIM * SRK_HEAD_DIM + r * SRK_HEAD_DIM + c] : 0.f;
+    }
     __syncthreads();
     const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t = blockIdx.x * APPLY_TOK + lane;
     if (t >= tokens_per_image) return;
     const int64_t tok = static_cast<int64_t>(b) * tokens_per_image + t;
     const float2* v2 = reinterpret_cast<const float2*>(qkv + tok * (3 * SRK_DIM) + 2 * SRK_DIM + h * SRK_HEAD_DIM);
-    float v[SRK_HEAD_DIM];
+    float v[32];
 #pragma unroll
     for (int d = 0; d < SRK_HEAD_DIM / 2; ++d) { const float2 x = __ldg(v2 + d); v[2 * d] = x.x; v[2 * d + 1] = x.y; }
-    const float* ah = s_a + h * SRK_HEAD_DIM * SRK_HEAD_DIM;
+    v[30] = 0.f; v[31] = 0.f;
+    const float4* ah = reinterpret_cast<const float4*>(s_a + h * SRK_HEAD_DIM * 32);
     float2* o2 = reinterpret_cast<float2*>(out + tok * SRK_DIM + h * SRK_HEAD_DIM);
 #pragma unroll 2
     for (int d1 = 0; d1 < SRK_HEAD_DIM; d1 += 2) {
         float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-        for (int d2 = 0; d2 < SRK_HEAD_DIM; ++d2) {
-            a0 = fmaf(ah[d1 * SRK_HEAD_DIM + d2], v[d2], a0);
-            a1 = fmaf(ah[(d1 + 1) * SRK_HEAD_DIM + d2], v[d2], a1);
+        for (int q = 0; q < 8; ++q) {                     // same summation order as before (d2 ascending)
+            const float4 w0 = ah[d1 * 8 + q], w1 = ah[(d1 + 1) * 8 + q];
+            a0 = fmaf(w0.x, v[4 * q], a0); a0 = fmaf(w0.y, v[4 * q + 1], a0); a0 = fmaf(w0.z, v[4 * q + 2], a0); a0 = fmaf(w0.w, v[4 * q + 3], a0);
+            a1 = fmaf(w1.x, v[4 * q], a1); a1 = fmaf(w1.y, v[4 * q + 1], a1); a1 = fmaf(w1.z, v[4 * q + 2], a1); a1 = fmaf(w1.w, v[4 * q + 3], a1);
         }
         o2[d1 >> 1] = make_float2(a0, a1);
     }
