@@ -236,6 +236,25 @@ int srk_stitch_accumulate(const float* tiles, float* E, float* Wt, const int32_t
                           int32_t channels, int32_t tile_h, int32_t tile_w, int32_t out_h, int32_t out_w, void* stream);
 int srk_stitch_normalize(float* E, const float* Wt, int32_t channels, int64_t pixels, void* stream);
 
+/* Tiler, second form (tiling.py; the reference has no tiling -- BASELINE.json configs[4]).
+ * srk_gather_tiles: out (num_tiles, channels, tile_h, tile_w) <- windows of the LR band `slab` (channels, slab_rows, slab_w; channel
+ *   stride slab_cstride floats) at src_yx[k] = (y0, x0): replaces the per-tile slicing + torch.stack of the host loop.
+ * srk_stitch_accumulate_strided: E[c, y0+ty, x0+tx] += tiles[k, c, ty, tx] with explicit element strides of `tiles` (the
+ *   models return channels-last memory) and a channel stride for E (a rank's band may live inside the full output image); the
+ *   tiles of one call must be pairwise disjoint; rows / columns outside [0, out_h) x [0, out_w) are skipped (seam tiles).
+ * srk_stitch_finalize: out = E / (cnt_y[y] * cnt_x[x]) -- the cover count of the E / W rule is separable, so no count plane is
+ *   accumulated -- converted to out_dtype (uint8: round(clamp(v, 0, 1) * 255)); out may alias E for SRK_OUT_F32. */
+#define SRK_OUT_F32 0
+#define SRK_OUT_BF16 1
+#define SRK_OUT_U8 2
+int srk_gather_tiles(const float* slab, int64_t slab_cstride, int32_t slab_rows, int32_t slab_w, const int32_t* src_yx, int32_t num_tiles,
+                     int32_t channels, int32_t tile_h, int32_t tile_w, float* out, void* stream);
+int srk_stitch_accumulate_strided(const float* tiles, int64_t stride_n, int64_t stride_c, int64_t stride_y, int64_t stride_x, float* E,
+                                  int64_t e_channel_stride, const int32_t* dst_yx, int32_t num_tiles, int32_t channels, int32_t tile_h,
+                                  int32_t tile_w, int32_t out_h, int32_t out_w, void* stream);
+int srk_stitch_finalize(const float* E, int64_t e_channel_stride, const float* cnt_y, const float* cnt_x, void* out, int64_t out_channel_stride,
+                        int32_t out_dtype, int32_t channels, int32_t out_h, int32_t out_w, void* stream);
+
 int srk_abi_version(void);
 const char* srk_last_error_string(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */

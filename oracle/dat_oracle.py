@@ -18,30 +18,9 @@ import torch
 import torch.nn.functional as F
 
 from .swinir_oracle import RGB_MEAN, conv3x3, gelu, image_to_tokens, layer_norm, pixel_shuffle, tokens_to_image
+from tpu_superresolution_b200.synth import DATConfig  # noqa: F401  (constructor-argument records live with the synthetic-data generators)
 
 Tensor = torch.Tensor
-
-
-@dataclass
-class DATConfig:
-    """Constructor arguments of the reference DAT (dat_arch.py:717-737); SURVEY.md 8(d) cfg4 values."""
-    upscale: int = 2
-    in_chans: int = 3
-    img_size: int = 64
-    img_range: float = 1.0
-    depth: Sequence[int] = field(default_factory=lambda: [6] * 6)
-    embed_dim: int = 180
-    num_heads: Sequence[int] = field(default_factory=lambda: [6] * 6)
-    expansion_factor: float = 4.0
-    resi_connection: str = "1conv"
-    split_size: Sequence[int] = field(default_factory=lambda: [8, 32])
-    num_feat: int = 64
-
-    def as_kwargs(self) -> dict:
-        return dict(upscale=self.upscale, in_chans=self.in_chans, img_size=self.img_size, img_range=self.img_range,
-                    depth=list(self.depth), embed_dim=self.embed_dim, num_heads=list(self.num_heads),
-                    expansion_factor=self.expansion_factor, resi_connection=self.resi_connection,
-                    split_size=list(self.split_size))
 
 
 def is_shifted(rg_idx: int, b_idx: int) -> bool:

@@ -19,36 +19,9 @@ import torch.nn.functional as F
 
 from .swinir_oracle import (RGB_MEAN, conv3x3, gelu, image_to_tokens, layer_norm, mlp, pixel_shuffle,
                             relative_position_index, shift_attention_mask, tokens_to_image, window_token_pixels)
+from tpu_superresolution_b200.synth import HATConfig  # noqa: F401  (constructor-argument records live with the synthetic-data generators)
 
 Tensor = torch.Tensor
-
-
-@dataclass
-class HATConfig:
-    """Constructor arguments of the reference HAT (hat_arch.py:738-764); SURVEY.md 8(d) cfg3 values."""
-    upscale: int = 4
-    in_chans: int = 3
-    img_size: int = 64
-    window_size: int = 16
-    compress_ratio: int = 3
-    squeeze_factor: int = 30
-    conv_scale: float = 0.01
-    overlap_ratio: float = 0.5
-    img_range: float = 1.0
-    depths: Sequence[int] = field(default_factory=lambda: [6] * 6)
-    embed_dim: int = 180
-    num_heads: Sequence[int] = field(default_factory=lambda: [6] * 6)
-    mlp_ratio: float = 2.0
-    upsampler: str = "pixelshuffle"
-    resi_connection: str = "1conv"
-    num_feat: int = 64
-
-    def as_kwargs(self) -> dict:
-        return dict(upscale=self.upscale, in_chans=self.in_chans, img_size=self.img_size, window_size=self.window_size,
-                    compress_ratio=self.compress_ratio, squeeze_factor=self.squeeze_factor, conv_scale=self.conv_scale,
-                    overlap_ratio=self.overlap_ratio, img_range=self.img_range, depths=list(self.depths),
-                    embed_dim=self.embed_dim, num_heads=list(self.num_heads), mlp_ratio=self.mlp_ratio,
-                    upsampler=self.upsampler, resi_connection=self.resi_connection)
 
 
 # ----------------------------------------------------------------------------------------

@@ -20,32 +20,9 @@ from typing import Dict, Optional, Sequence, Tuple
 
 import torch
 import torch.nn.functional as F
+from tpu_superresolution_b200.synth import SwinIRConfig  # noqa: F401  (constructor-argument records live with the synthetic-data generators)
 
 Tensor = torch.Tensor
-
-
-@dataclass
-class SwinIRConfig:
-    """Constructor arguments of the reference SwinIR (network_swinir.py:646-652)."""
-    upscale: int = 2
-    in_chans: int = 3
-    img_size: int = 64
-    window_size: int = 8
-    img_range: float = 1.0
-    depths: Sequence[int] = field(default_factory=lambda: [6] * 6)
-    embed_dim: int = 180
-    num_heads: Sequence[int] = field(default_factory=lambda: [6] * 6)
-    mlp_ratio: float = 2.0
-    upsampler: str = "pixelshuffle"
-    resi_connection: str = "1conv"
-    num_feat: int = 64
-
-    def as_kwargs(self) -> dict:
-        return dict(upscale=self.upscale, in_chans=self.in_chans, img_size=self.img_size,
-                    window_size=self.window_size, img_range=self.img_range,
-                    depths=list(self.depths), embed_dim=self.embed_dim,
-                    num_heads=list(self.num_heads), mlp_ratio=self.mlp_ratio,
-                    upsampler=self.upsampler, resi_connection=self.resi_connection)
 
 
 RGB_MEAN = (0.4488, 0.4371, 0.4040)  # network_swinir.py:659

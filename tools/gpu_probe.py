@@ -36,7 +36,8 @@ def child(step):
     import torch
     import tpu_superresolution_b200 as srk
     from tpu_superresolution_b200 import _lib as L
-    from oracle import synth, swinir_oracle as O
+    from tpu_superresolution_b200 import synth
+    from oracle import swinir_oracle as O
     torch.set_grad_enabled(False)
     sd = synth.make_swinir_state_dict(synth.CONFIGS["swinir_x2_d2"], seed=99, kind="stress")
     bsd = lambda pre: {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}

@@ -5,7 +5,8 @@ import numpy as np
 import torch
 import tpu_superresolution_b200 as srk
 from tpu_superresolution_b200 import _lib as L, packing, hat as H
-from oracle import synth, hat_oracle as HO, swinir_oracle as O
+from tpu_superresolution_b200 import synth
+from oracle import hat_oracle as HO, swinir_oracle as O
 
 torch.set_grad_enabled(False)
 torch.backends.cudnn.allow_tf32 = True

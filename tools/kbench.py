@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import tpu_superresolution_b200 as srk
 from tpu_superresolution_b200 import _lib as L
-from oracle import synth
+from tpu_superresolution_b200 import synth
 
 torch.set_grad_enabled(False)
 sd = synth.make_swinir_state_dict(synth.CONFIGS["swinir_x2_d2"], seed=99, kind="init")

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from torch.profiler import profile, ProfilerActivity
 import bench
-from oracle import synth
+from tpu_superresolution_b200 import synth
 
 torch.set_grad_enabled(False)
 torch.backends.cudnn.allow_tf32 = True

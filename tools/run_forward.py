@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import tpu_superresolution_b200 as srk
-from oracle import synth
+from tpu_superresolution_b200 import synth
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 cfg = synth.CONFIGS["swinir_x4"]

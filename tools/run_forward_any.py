@@ -7,7 +7,7 @@ import bench
 name = sys.argv[1] if len(sys.argv) > 1 else "hat_x4"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 W = bench.WORKLOADS[name]
-from oracle import synth
+from tpu_superresolution_b200 import synth
 torch.backends.cudnn.allow_tf32 = True
 torch.backends.cudnn.benchmark = True
 cfg, sd, cls, _ = bench._build(W["family"], W["cfg"])

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import tpu_superresolution_b200 as srk
 from tpu_superresolution_b200 import swinir
-from oracle import synth
+from tpu_superresolution_b200 import synth
 
 torch.set_grad_enabled(False)
 cfg = synth.CONFIGS["swinir_x4"]

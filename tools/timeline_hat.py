@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from tpu_superresolution_b200 import _lib as L, packing, hat as H
-from oracle import synth
+from tpu_superresolution_b200 import synth
 
 torch.set_grad_enabled(False)
 kind = L.WA_HAT_OCAB if len(sys.argv) > 1 and sys.argv[1] == "ocab" else L.WA_HAT_WMSA

@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from tpu_superresolution_b200 import _lib as L, packing
-from oracle import synth
+from tpu_superresolution_b200 import synth
 
 torch.set_grad_enabled(False)
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 32768

@@ -60,19 +60,46 @@ PROFILE = None
 PROFILE_DETAIL = False          # True: token_linear launches are keyed by shape in PROFILE
 
 
-class _timed:
-    def __init__(self, name):
+class _launch:
+    """One library call: checks that all tensors live on ONE CUDA device, makes that device current for the duration of the
+    call (the kernels' per-device state -- opt-in shared memory size, SM count -- and the launch itself follow the current
+    device, not the tensors) and hands out that device's current stream.  With PROFILE set it also brackets the call with
+    CUDA events on that stream."""
+
+    def __init__(self, name, *tensors):
         self.name = name
+        dev = None
+        for t in tensors:
+            if t is None:
+                continue
+            if not t.is_cuda:
+                raise RuntimeError("tpu_superresolution_b200 kernels need CUDA tensors (no CPU fallback)")
+            if dev is None:
+                dev = t.device
+            elif t.device != dev:
+                raise RuntimeError(f"{name}: tensors on different devices ({dev} and {t.device})")
+        if dev is None:
+            raise RuntimeError(f"{name}: no CUDA tensor")
+        self.device = dev
+        self._guard = None
 
     def __enter__(self):
+        if torch.cuda.current_device() != self.device.index:
+            self._guard = torch.cuda.device(self.device)
+            self._guard.__enter__()
+        self.stream = torch.cuda.current_stream(self.device)
         if PROFILE is not None:
             self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            self.e0.record(torch.cuda.current_stream())
+            self.e0.record(self.stream)
+        return self.stream.cuda_stream
 
     def __exit__(self, *exc):
         if PROFILE is not None:
-            self.e1.record(torch.cuda.current_stream())
+            self.e1.record(self.stream)
             PROFILE.setdefault(self.name, []).append((self.e0, self.e1))
+        if self._guard is not None:
+            self._guard.__exit__(*exc)
+            self._guard = None
         return False
 
 
@@ -99,6 +126,10 @@ def load():
     lib.srk_stitch_accumulate.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                           c_int32, c_int32, c_void_p]
     lib.srk_stitch_normalize.argtypes = [c_void_p, c_void_p, c_int32, c_int64, c_void_p]
+    lib.srk_gather_tiles.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]
+    lib.srk_stitch_accumulate_strided.argtypes = [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int32, c_int32,
+                                                  c_int32, c_int32, c_int32, c_int32, c_void_p]
+    lib.srk_stitch_finalize.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p]
     lib.srk_linear_fwd.argtypes = [POINTER(LinearDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.srk_window_attention_fwd.argtypes = [POINTER(WinAttnDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_void_p]
@@ -123,7 +154,8 @@ def load():
     lib.srk_debug_set_pdl.argtypes = [c_int32]
     lib.srk_debug_set_pdl.restype = None
     for f in ("srk_swin_attn_fwd", "srk_swin_mlp_fwd", "srk_swin_attn_fwd_sync", "srk_swin_mlp_fwd_sync", "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd", "srk_pixelshuffle_nhwc_bias_fwd", "srk_bias_act_add_nhwc",
-              "srk_stitch_accumulate", "srk_stitch_normalize", "srk_linear_fwd", "srk_window_attention_fwd",
+              "srk_stitch_accumulate", "srk_stitch_normalize", "srk_gather_tiles", "srk_stitch_accumulate_strided", "srk_stitch_finalize",
+              "srk_linear_fwd", "srk_window_attention_fwd",
               "srk_window_attention_table_floats", "srk_cab_gate_add", "srk_dwconv3x3_rows_fwd", "srk_row_stats_fwd", "srk_dat_mix_fwd",
               "srk_dat_channel_gram_fwd", "srk_dat_channel_apply_fwd", "srk_dat_channel_gram_ws_floats", "srk_cab_ws_floats", "srk_token_mean_fwd"):
         getattr(lib, f).restype = c_int32
@@ -135,7 +167,8 @@ def load():
 
 EXPORTS = ("srk_abi_version", "srk_last_error_string", "srk_launch_count", "srk_swin_attn_fwd", "srk_swin_mlp_fwd",
            "srk_swin_attn_fwd_sync", "srk_swin_mlp_fwd_sync",
-           "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd", "srk_pixelshuffle_nhwc_bias_fwd", "srk_bias_act_add_nhwc", "srk_stitch_accumulate", "srk_stitch_normalize", "srk_debug_set_timeline", "srk_debug_set_stagger",
+           "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd", "srk_pixelshuffle_nhwc_bias_fwd", "srk_bias_act_add_nhwc", "srk_stitch_accumulate", "srk_stitch_normalize", "srk_gather_tiles", "srk_stitch_accumulate_strided", "srk_stitch_finalize",
+           "srk_debug_set_timeline", "srk_debug_set_stagger",
            "srk_linear_fwd", "srk_window_attention_fwd", "srk_window_attention_table_floats", "srk_debug_set_winattn_stagger", "srk_debug_set_pdl",
            "srk_cab_gate_add", "srk_dwconv3x3_rows_fwd", "srk_row_stats_fwd", "srk_dat_mix_fwd", "srk_dat_channel_gram_fwd",
            "srk_dat_channel_apply_fwd", "srk_dat_channel_gram_ws_floats", "srk_cab_ws_floats", "srk_token_mean_fwd")
@@ -144,10 +177,6 @@ EXPORTS = ("srk_abi_version", "srk_last_error_string", "srk_launch_count", "srk_
 def _check(rc: int, lib) -> None:
     if rc != 0:
         raise RuntimeError("libsrk: " + lib.srk_last_error_string().decode())
-
-
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
 
 
 def _require_cuda_f32(*tensors) -> None:
@@ -180,9 +209,9 @@ def swin_attn(x, y, wstream, vec, *, mode, batch=0, height=0, width=0, num_windo
     d = SwinAttnDesc(mode, batch, height, width, num_windows, ld_in, ld_out, shift, int(apply_ln), int(add_residual),
                      mask_mode, 0 if mask is None else mask.shape[0])
     sync = _block_sync(progress, batch, height * width, wait_target)
-    with _timed("swin_attn"):
+    with _launch("swin_attn", x, y, wstream, vec, mask, progress) as st:
         _check(lib.srk_swin_attn_fwd_sync(ctypes.byref(d), x.data_ptr(), y.data_ptr(), wstream.data_ptr(), vec.data_ptr(),
-                                          0 if mask is None else mask.data_ptr(), None if sync is None else ctypes.byref(sync), _stream()), lib)
+                                          0 if mask is None else mask.data_ptr(), None if sync is None else ctypes.byref(sync), st), lib)
 
 
 def swin_mlp(x, y, wstream, vec, *, num_tokens, ld_in, ld_out, apply_ln=True, add_residual=True, progress=None, batch=0,
@@ -191,26 +220,24 @@ def swin_mlp(x, y, wstream, vec, *, num_tokens, ld_in, ld_out, apply_ln=True, ad
     _require_cuda_f32(x, y, vec)
     d = MlpDesc(num_tokens, ld_in, ld_out, int(apply_ln), int(add_residual))
     sync = _block_sync(progress, batch, tokens_per_image, wait_target)
-    with _timed("swin_mlp"):
+    with _launch("swin_mlp", x, y, wstream, vec, progress) as st:
         _check(lib.srk_swin_mlp_fwd_sync(ctypes.byref(d), x.data_ptr(), y.data_ptr(), wstream.data_ptr(), vec.data_ptr(),
-                                         None if sync is None else ctypes.byref(sync), _stream()), lib)
+                                         None if sync is None else ctypes.byref(sync), st), lib)
 
 
 def layernorm(x, y, w, b, *, num_tokens, ld_in, ld_out) -> None:
+    """srk_layernorm_fwd; y may be x itself (in place)."""
     lib = load()
     _require_cuda_f32(x, y, w, b)
-    with _timed("layernorm"):
-        _check(lib.srk_layernorm_fwd(x.data_ptr(), y.data_ptr(), w.data_ptr(), b.data_ptr(), num_tokens, ld_in, ld_out, _stream()), lib)
+    with _launch("layernorm", x, y, w, b) as st:
+        _check(lib.srk_layernorm_fwd(x.data_ptr(), y.data_ptr(), w.data_ptr(), b.data_ptr(), num_tokens, ld_in, ld_out, st), lib)
 
 
 def pixelshuffle_nhwc(x, y, *, batch, height, width, out_channels, r, bias=None) -> None:
     lib = load()
-    _require_cuda_f32(x, y)
-    if bias is not None:
-        _require_cuda_f32(bias)
-    with _timed("pixelshuffle"):
-        _check(lib.srk_pixelshuffle_nhwc_bias_fwd(x.data_ptr(), bias.data_ptr() if bias is not None else None, y.data_ptr(), batch,
-                                                  height, width, out_channels, r, _stream()), lib)
+    _require_cuda_f32(x, y, bias)
+    with _launch("pixelshuffle", x, y, bias) as st:
+        _check(lib.srk_pixelshuffle_nhwc_bias_fwd(x.data_ptr(), _ptr(bias), y.data_ptr(), batch, height, width, out_channels, r, st), lib)
 
 
 ACT_NONE, ACT_LEAKY_RELU, ACT_GELU = 0, 1, 2
@@ -219,27 +246,72 @@ ACT_NONE, ACT_LEAKY_RELU, ACT_GELU = 0, 1, 2
 def bias_act_add_nhwc(x, y, *, pixels, channels, bias=None, residual=None, act=ACT_NONE, slope=0.0) -> None:
     """y[p, c] = act(x[p, c] + bias[c]) + residual[p, c] (include/srk.h: srk_bias_act_add_nhwc); y may alias x / residual."""
     lib = load()
-    _require_cuda_f32(x, y)
-    for t in (bias, residual):
-        if t is not None:
-            _require_cuda_f32(t)
-    with _timed("bias_act_add"):
-        _check(lib.srk_bias_act_add_nhwc(x.data_ptr(), bias.data_ptr() if bias is not None else None,
-                                         residual.data_ptr() if residual is not None else None, y.data_ptr(), pixels, channels, act,
-                                         float(slope), _stream()), lib)
+    _require_cuda_f32(x, y, bias, residual)
+    with _launch("bias_act_add", x, y, bias, residual) as st:
+        _check(lib.srk_bias_act_add_nhwc(x.data_ptr(), _ptr(bias), _ptr(residual), y.data_ptr(), pixels, channels, act, float(slope), st), lib)
 
 
 def stitch_accumulate(tiles, E, Wt, tile_yx, *, channels, tile_h, tile_w, out_h, out_w) -> None:
     lib = load()
     _require_cuda_f32(tiles, E, Wt)
-    _check(lib.srk_stitch_accumulate(tiles.data_ptr(), E.data_ptr(), Wt.data_ptr(), tile_yx.data_ptr(), tile_yx.shape[0],
-                                     channels, tile_h, tile_w, out_h, out_w, _stream()), lib)
+    with _launch("stitch_accumulate", tiles, E, Wt, tile_yx) as st:
+        _check(lib.srk_stitch_accumulate(tiles.data_ptr(), E.data_ptr(), Wt.data_ptr(), tile_yx.data_ptr(), tile_yx.shape[0],
+                                         channels, tile_h, tile_w, out_h, out_w, st), lib)
 
 
 def stitch_normalize(E, Wt, *, channels, pixels) -> None:
     lib = load()
     _require_cuda_f32(E, Wt)
-    _check(lib.srk_stitch_normalize(E.data_ptr(), Wt.data_ptr(), channels, pixels, _stream()), lib)
+    with _launch("stitch_normalize", E, Wt) as st:
+        _check(lib.srk_stitch_normalize(E.data_ptr(), Wt.data_ptr(), channels, pixels, st), lib)
+
+
+OUT_F32, OUT_BF16, OUT_U8 = 0, 1, 2
+OUT_DTYPES = {torch.float32: OUT_F32, torch.bfloat16: OUT_BF16, torch.uint8: OUT_U8}
+
+
+def gather_tiles(slab, src_yx, out) -> None:
+    """srk_gather_tiles: out (n, C, th, tw) <- windows of the contiguous LR band `slab` (C, rows, W) at src_yx (n, 2) int32."""
+    lib = load()
+    _require_cuda_f32(slab, out)
+    C, rows, W = slab.shape
+    n, c2, th, tw = out.shape
+    if not (slab.is_contiguous() and out.is_contiguous() and src_yx.dtype == torch.int32 and src_yx.is_contiguous()
+            and c2 == C and src_yx.shape[0] >= n):
+        raise RuntimeError("gather_tiles: contiguous (C, rows, W) slab, (n, C, th, tw) output and an int32 (>= n, 2) table expected")
+    with _launch("gather_tiles", slab, src_yx, out) as st:
+        _check(lib.srk_gather_tiles(slab.data_ptr(), rows * W, rows, W, src_yx.data_ptr(), n, C, th, tw, out.data_ptr(), st), lib)
+
+
+def stitch_accumulate_strided(tiles, E, dst_yx, *, num_tiles=None) -> None:
+    """srk_stitch_accumulate_strided: E[c, y0+ty, x0+tx] += tiles[k, c, ty, tx]; `tiles` (n, C, th, tw) with any strides, `E`
+    (C, out_h, out_w) with contiguous planes (any channel stride), `dst_yx` int32 (>= n, 2).  The tiles must be disjoint."""
+    lib = load()
+    _require_cuda_f32(tiles, E)
+    n, C, th, tw = tiles.shape
+    n = n if num_tiles is None else num_tiles
+    if E.stride(2) != 1 or E.stride(1) != E.shape[2] or dst_yx.dtype != torch.int32 or not dst_yx.is_contiguous() or dst_yx.shape[0] < n:
+        raise RuntimeError("stitch_accumulate_strided: E planes must be contiguous, dst_yx int32 (>= n, 2)")
+    sn, sc, sy, sx = tiles.stride()
+    with _launch("stitch_accumulate", tiles, E, dst_yx) as st:
+        _check(lib.srk_stitch_accumulate_strided(tiles.data_ptr(), sn, sc, sy, sx, E.data_ptr(), E.stride(0), dst_yx.data_ptr(), n, C, th, tw,
+                                                 E.shape[1], E.shape[2], st), lib)
+
+
+def stitch_finalize(E, cnt_y, cnt_x, out) -> None:
+    """srk_stitch_finalize: out = E / (cnt_y[:, None] * cnt_x[None, :]) converted to out.dtype (fp32 / bf16 / uint8)."""
+    lib = load()
+    _require_cuda_f32(E, cnt_y, cnt_x)
+    if out.dtype not in OUT_DTYPES or out.shape != E.shape:
+        raise RuntimeError("stitch_finalize: out must be fp32 / bf16 / uint8 with E's shape")
+    for t in (E, out):
+        if t.stride(2) != 1 or t.stride(1) != t.shape[2]:
+            raise RuntimeError("stitch_finalize: planes must be contiguous")
+    if cnt_y.numel() != E.shape[1] or cnt_x.numel() != E.shape[2]:
+        raise RuntimeError("stitch_finalize: count tables do not match E")
+    with _launch("stitch_finalize", E, cnt_y, cnt_x, out) as st:
+        _check(lib.srk_stitch_finalize(E.data_ptr(), E.stride(0), cnt_y.data_ptr(), cnt_x.data_ptr(), out.data_ptr(), out.stride(0),
+                                       OUT_DTYPES[out.dtype], E.shape[0], E.shape[1], E.shape[2], st), lib)
 
 
 _ZERO_PAGES = {}
@@ -258,17 +330,14 @@ def linear(a, wstream, bias, out, *, num_tokens, a_mode, k_atoms=3, ld_in=0, app
            out_mode, ld_out=0, add_residual=False, plane_phase_mask=0) -> None:
     """srk_linear_fwd: a = fp32 rows (A_ROWS) or uint8/bf16 plane buffer (A_PLANES); out = plane buffer or fp32 rows."""
     lib = load()
-    for t in (a, wstream, bias, out):
-        if not t.is_cuda:
-            raise RuntimeError("tpu_superresolution_b200 kernels need CUDA tensors (no CPU fallback)")
     if wstream.numel() * wstream.element_size() != n_chunks * k_atoms * LIN_SLAB_BYTES or bias.numel() != n_chunks * 192:
         raise RuntimeError("linear: weight stream / bias size does not match n_chunks, k_atoms")
     d = LinearDesc(num_tokens, a_mode, k_atoms, ld_in, int(apply_ln), n_chunks, act, out_mode, ld_out, int(add_residual),
                    plane_phase_mask)
     label = "linear" if PROFILE is None or not PROFILE_DETAIL else \
         f"linear {'rows' if a_mode == LIN_A_ROWS else 'planes'}(k{k_atoms}){'+ln' if apply_ln else ''} -> {'planes' if out_mode == LIN_OUT_PLANES else 'rows'} x{n_chunks}{' gelu' if act else ''}{' +res' if add_residual else ''}"
-    with _timed(label):
-        _check(lib.srk_linear_fwd(ctypes.byref(d), a.data_ptr(), wstream.data_ptr(), bias.data_ptr(), out.data_ptr(), _stream()), lib)
+    with _launch(label, a, wstream, bias, out) as st:
+        _check(lib.srk_linear_fwd(ctypes.byref(d), a.data_ptr(), wstream.data_ptr(), bias.data_ptr(), out.data_ptr(), st), lib)
 
 
 def window_attention(q_planes, k_planes, v_planes, table, out, *, kind, batch, height, width, shift=(0, 0), mask_shift=False,
@@ -279,10 +348,10 @@ def window_attention(q_planes, k_planes, v_planes, table, out, *, kind, batch, h
         raise RuntimeError("window_attention: bias table size does not match kind / n_heads")
     d = WinAttnDesc(kind, batch, height, width, shift[0], shift[1], int(mask_shift), n_heads,
                     0 if emask is None else emask.shape[0], out_mode, out_ld, out_col0)
-    with _timed("window_attention"):
+    zp = zero_page(out.device)
+    with _launch("window_attention", q_planes, k_planes, v_planes, table, emask, out, zp) as st:
         _check(lib.srk_window_attention_fwd(ctypes.byref(d), q_planes.data_ptr(), k_planes.data_ptr(), v_planes.data_ptr(),
-                                            table.data_ptr(), 0 if emask is None else emask.data_ptr(),
-                                            zero_page(out.device).data_ptr(), out.data_ptr(), _stream()), lib)
+                                            table.data_ptr(), _ptr(emask), zp.data_ptr(), out.data_ptr(), st), lib)
 
 
 def cab_gate_add(y, out, w1, b1, w2, b2, *, scale, batch, tokens_per_image, y_bias=None) -> None:
@@ -290,10 +359,9 @@ def cab_gate_add(y, out, w1, b1, w2, b2, *, scale, batch, tokens_per_image, y_bi
     lib = load()
     _require_cuda_f32(y, out, w1, b1, w2, b2, y_bias)
     ws = torch.empty(lib.srk_cab_ws_floats(batch, tokens_per_image), dtype=torch.float32, device=y.device)
-    with _timed("cab_gate_add"):
-        _check(lib.srk_cab_gate_add(y.data_ptr(), y_bias.data_ptr() if y_bias is not None else None, out.data_ptr(), ws.data_ptr(),
-                                    w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), w1.shape[0], float(scale), batch,
-                                    tokens_per_image, _stream()), lib)
+    with _launch("cab_gate_add", y, out, w1, b1, w2, b2, y_bias) as st:
+        _check(lib.srk_cab_gate_add(y.data_ptr(), _ptr(y_bias), out.data_ptr(), ws.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+                                    b2.data_ptr(), w1.shape[0], float(scale), batch, tokens_per_image, st), lib)
 
 
 def token_mean(x, *, batch, tokens_per_image):
@@ -302,8 +370,8 @@ def token_mean(x, *, batch, tokens_per_image):
     _require_cuda_f32(x)
     ws = torch.empty(lib.srk_cab_ws_floats(batch, tokens_per_image), dtype=torch.float32, device=x.device)
     mean = torch.empty(batch, DIM, dtype=torch.float32, device=x.device)
-    with _timed("token_mean"):
-        _check(lib.srk_token_mean_fwd(x.data_ptr(), mean.data_ptr(), ws.data_ptr(), batch, tokens_per_image, _stream()), lib)
+    with _launch("token_mean", x) as st:
+        _check(lib.srk_token_mean_fwd(x.data_ptr(), mean.data_ptr(), ws.data_ptr(), batch, tokens_per_image, st), lib)
     return mean
 
 
@@ -316,37 +384,37 @@ def dwconv3x3_rows(inp, w9c, scale, shift, out, *, ld_in, c_in, ld_out, channels
     """srk_dwconv3x3_rows_fwd on fp32 token rows (see include/srk.h)."""
     lib = load()
     _require_cuda_f32(inp, w9c, scale, shift, out, ln_stats, ln_gamma, ln_beta, gate)
-    with _timed("dwconv3x3_rows"):
+    with _launch("dwconv3x3_rows", inp, w9c, scale, shift, out, ln_stats, ln_gamma, ln_beta, gate) as st:
         _check(lib.srk_dwconv3x3_rows_fwd(inp.data_ptr(), ld_in, c_in, w9c.data_ptr(), scale.data_ptr(), shift.data_ptr(), _ptr(ln_stats),
                                           _ptr(ln_gamma), _ptr(ln_beta), _ptr(gate), ld_gate, c_gate, out.data_ptr(), ld_out, channels, batch,
-                                          height, width, int(act_gelu), _stream()), lib)
+                                          height, width, int(act_gelu), st), lib)
 
 
 def row_stats(inp, stats, *, ld_in, c_in, channels, tokens, eps) -> None:
     lib = load()
     _require_cuda_f32(inp, stats)
-    with _timed("row_stats"):
-        _check(lib.srk_row_stats_fwd(inp.data_ptr(), ld_in, c_in, channels, tokens, float(eps), stats.data_ptr(), _stream()), lib)
+    with _launch("row_stats", inp, stats) as st:
+        _check(lib.srk_row_stats_fwd(inp.data_ptr(), ld_in, c_in, channels, tokens, float(eps), stats.data_ptr(), st), lib)
 
 
 def dat_mix(att, conv, cmap, w1, b1, w2, b2, mix, *, mode, tokens, tokens_per_image) -> None:
     lib = load()
     _require_cuda_f32(att, conv, cmap, w1, b1, w2, mix)
-    with _timed("dat_mix"):
+    with _launch("dat_mix", att, conv, cmap, w1, b1, w2, mix) as st:
         _check(lib.srk_dat_mix_fwd(att.data_ptr(), conv.data_ptr(), cmap.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), float(b2),
-                                   w1.shape[0], mode, mix.data_ptr(), tokens, tokens_per_image, _stream()), lib)
+                                   w1.shape[0], mode, mix.data_ptr(), tokens, tokens_per_image, st), lib)
 
 
 def dat_channel_gram(qkv, gram, *, batch, tokens_per_image) -> None:
     lib = load()
     _require_cuda_f32(qkv, gram)
     ws = torch.empty(lib.srk_dat_channel_gram_ws_floats(batch, tokens_per_image), dtype=torch.float32, device=qkv.device)
-    with _timed("dat_channel_gram"):
-        _check(lib.srk_dat_channel_gram_fwd(qkv.data_ptr(), gram.data_ptr(), ws.data_ptr(), batch, tokens_per_image, _stream()), lib)
+    with _launch("dat_channel_gram", qkv, gram) as st:
+        _check(lib.srk_dat_channel_gram_fwd(qkv.data_ptr(), gram.data_ptr(), ws.data_ptr(), batch, tokens_per_image, st), lib)
 
 
 def dat_channel_apply(qkv, attn, out, *, batch, tokens_per_image) -> None:
     lib = load()
     _require_cuda_f32(qkv, attn, out)
-    with _timed("dat_channel_apply"):
-        _check(lib.srk_dat_channel_apply_fwd(qkv.data_ptr(), attn.data_ptr(), out.data_ptr(), batch, tokens_per_image, _stream()), lib)
+    with _launch("dat_channel_apply", qkv, attn, out) as st:
+        _check(lib.srk_dat_channel_apply_fwd(qkv.data_ptr(), attn.data_ptr(), out.data_ptr(), batch, tokens_per_image, st), lib)

@@ -1,5 +1,6 @@
 // HBM-bound helper kernels: row LayerNorm, channels-last PixelShuffle, tile stitcher.
 // All are pure streaming kernels: 128-bit coalesced loads/stores, grid-stride, no shared memory.
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -173,7 +174,7 @@ cudaError_t launch_bias_act_add(const float* x, const float* bias, const float* 
 
 // ---- overlapping-tile stitcher (BASELINE.json configs[4]): E += tile, Wt += 1 over the tile footprint.
 // tiles: (num_tiles, channels, tile_h, tile_w) NCHW fp32;  E: (channels, out_h, out_w);  Wt: (out_h, out_w).
-// Tiles of one launch must be pairwise disjoint (the tiler launches the 4 parity classes separately).
+// Tiles of one launch must be pairwise disjoint (the tiler launches the 9 parity-or-last classes separately).
 __global__ void __launch_bounds__(256) stitch_accumulate_kernel(const float* __restrict__ tiles, float* __restrict__ E,
                                                                 float* __restrict__ Wt, const int32_t* __restrict__ tile_yx,
                                                                 int channels, int tile_h, int tile_w, int out_h, int out_w) {
@@ -214,6 +215,86 @@ cudaError_t launch_stitch_normalize(float* E, const float* Wt, int channels, int
     const int64_t blocks = (pixels + 255) / 256;
     const int grid = static_cast<int>(blocks < 148 * 32 ? blocks : 148 * 32);
     stitch_normalize_kernel<<<grid, 256, 0, stream>>>(E, Wt, channels, pixels);
+    return cudaGetLastError();
+}
+
+// ---- tiler v2 (tiling.py): tile gather, strided accumulate without the count plane, finalize with count tables.
+// gather: out[n][c][ty][tx] = slab[c][y0 + ty][x0 + tx] for the LR band `slab` (channels, rows, width) of this rank.
+__global__ void __launch_bounds__(256) gather_tiles_kernel(const float* __restrict__ slab, int64_t slab_cstride, int slab_w,
+                                                           const int32_t* __restrict__ src_yx, int channels, int tile_h, int tile_w,
+                                                           float* __restrict__ out) {
+    const int tile = blockIdx.z, c = blockIdx.y;
+    const int y0 = src_yx[2 * tile], x0 = src_yx[2 * tile + 1];
+    const int per = tile_h * tile_w;
+    float* dst = out + (static_cast<int64_t>(tile) * channels + c) * per;
+    const float* src = slab + c * slab_cstride;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per; i += gridDim.x * blockDim.x) {
+        const int ty = i / tile_w, tx = i - ty * tile_w;
+        dst[i] = __ldg(src + static_cast<int64_t>(y0 + ty) * slab_w + x0 + tx);
+    }
+}
+// accumulate: E[c][y0 + ty][x0 + tx] += tiles[n][c][ty][tx] for any element strides of `tiles` (the models return channels-last
+// memory behind an NCHW shape).  Tiles of one launch must be pairwise disjoint (tiling.py launches per class segment); the
+// per-pixel cover count is NOT accumulated -- it is the product of two 1-D tables (stitch_finalize_kernel).
+__global__ void __launch_bounds__(256) stitch_accumulate2_kernel(const float* __restrict__ tiles, int64_t sn, int64_t sc, int64_t sy, int64_t sx,
+                                                                 float* __restrict__ E, int64_t e_cstride, const int32_t* __restrict__ dst_yx,
+                                                                 int channels, int tile_h, int tile_w, int out_h, int out_w) {
+    const int tile = blockIdx.y;
+    const int y0 = dst_yx[2 * tile], x0 = dst_yx[2 * tile + 1];
+    const int per = tile_h * tile_w;
+    const float* src = tiles + tile * sn;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per; i += gridDim.x * blockDim.x) {
+        const int ty = i / tile_w, tx = i - ty * tile_w;
+        const int oy = y0 + ty, ox = x0 + tx;
+        if (oy < 0 || ox < 0 || oy >= out_h || ox >= out_w) continue;   // rows of a seam tile outside this rank's band
+        const int64_t o = static_cast<int64_t>(oy) * out_w + ox;
+        const float* s = src + ty * sy + tx * sx;
+        for (int c = 0; c < channels; ++c) E[c * e_cstride + o] += __ldg(s + c * sc);
+    }
+}
+// finalize: out[c][y][x] = convert(E[c][y][x] / (cnt_y[y] * cnt_x[x])); dtype 0 = fp32 (out may alias E), 1 = bf16, 2 = uint8
+// (round(clamp(v, 0, 1) * 255)).  cnt_* hold small integers as floats, so the divisor is exact: this IS E / W of the upstream rule.
+template <int DTYPE>
+__global__ void __launch_bounds__(256) stitch_finalize_kernel(const float* __restrict__ E, int64_t e_cstride, const float* __restrict__ cnt_y,
+                                                              const float* __restrict__ cnt_x, void* __restrict__ out, int64_t o_cstride,
+                                                              int channels, int out_h, int out_w) {
+    const int64_t pixels = static_cast<int64_t>(out_h) * out_w;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < pixels; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int y = static_cast<int>(i / out_w), x = static_cast<int>(i - static_cast<int64_t>(y) * out_w);
+        const float w = __ldg(cnt_y + y) * __ldg(cnt_x + x);
+        for (int c = 0; c < channels; ++c) {
+            const float v = E[c * e_cstride + i] / w;
+            if (DTYPE == 0) static_cast<float*>(out)[c * o_cstride + i] = v;
+            else if (DTYPE == 1) static_cast<__nv_bfloat16*>(out)[c * o_cstride + i] = __float2bfloat16_rn(v);
+            else static_cast<uint8_t*>(out)[c * o_cstride + i] = static_cast<uint8_t>(__float2int_rn(fminf(fmaxf(v, 0.f), 1.f) * 255.f));
+        }
+    }
+}
+
+cudaError_t launch_gather_tiles(const float* slab, int64_t slab_cstride, int slab_w, const int32_t* src_yx, int num_tiles, int channels,
+                                int tile_h, int tile_w, float* out, cudaStream_t stream) {
+    if (num_tiles <= 0) return cudaSuccess;
+    dim3 grid((tile_h * tile_w + 255) / 256, channels, num_tiles);
+    gather_tiles_kernel<<<grid, 256, 0, stream>>>(slab, slab_cstride, slab_w, src_yx, channels, tile_h, tile_w, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_stitch_accumulate2(const float* tiles, int64_t sn, int64_t sc, int64_t sy, int64_t sx, float* E, int64_t e_cstride,
+                                      const int32_t* dst_yx, int num_tiles, int channels, int tile_h, int tile_w, int out_h, int out_w,
+                                      cudaStream_t stream) {
+    if (num_tiles <= 0) return cudaSuccess;
+    dim3 grid((tile_h * tile_w + 255) / 256, num_tiles);
+    stitch_accumulate2_kernel<<<grid, 256, 0, stream>>>(tiles, sn, sc, sy, sx, E, e_cstride, dst_yx, channels, tile_h, tile_w, out_h, out_w);
+    return cudaGetLastError();
+}
+cudaError_t launch_stitch_finalize(const float* E, int64_t e_cstride, const float* cnt_y, const float* cnt_x, void* out, int64_t o_cstride,
+                                   int dtype, int channels, int out_h, int out_w, cudaStream_t stream) {
+    const int64_t pixels = static_cast<int64_t>(out_h) * out_w;
+    if (pixels <= 0) return cudaSuccess;
+    const int64_t blocks = (pixels + 255) / 256;
+    const int grid = static_cast<int>(blocks < 148 * 32 ? blocks : 148 * 32);
+    if (dtype == 0) stitch_finalize_kernel<0><<<grid, 256, 0, stream>>>(E, e_cstride, cnt_y, cnt_x, out, o_cstride, channels, out_h, out_w);
+    else if (dtype == 1) stitch_finalize_kernel<1><<<grid, 256, 0, stream>>>(E, e_cstride, cnt_y, cnt_x, out, o_cstride, channels, out_h, out_w);
+    else stitch_finalize_kernel<2><<<grid, 256, 0, stream>>>(E, e_cstride, cnt_y, cnt_x, out, o_cstride, channels, out_h, out_w);
     return cudaGetLastError();
 }
 

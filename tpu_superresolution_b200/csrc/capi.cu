@@ -336,6 +336,33 @@ int srk_stitch_accumulate(const float* tiles, float* E, float* Wt, const int32_t
                                                static_cast<cudaStream_t>(stream)), "srk_stitch_accumulate");
 }
 
+int srk_gather_tiles(const float* slab, int64_t slab_cstride, int32_t slab_rows, int32_t slab_w, const int32_t* src_yx, int32_t num_tiles,
+                     int32_t channels, int32_t tile_h, int32_t tile_w, float* out, void* stream) {
+    if (!slab || !src_yx || !out) return fail("srk_gather_tiles: null argument");
+    if (num_tiles < 0 || num_tiles > 65535 || channels <= 0 || channels > 65535 || tile_h <= 0 || tile_w <= 0 || tile_h > slab_rows || tile_w > slab_w)
+        return fail("srk_gather_tiles: bad shape");
+    return check(srk::launch_gather_tiles(slab, slab_cstride, slab_w, src_yx, num_tiles, channels, tile_h, tile_w, out,
+                                          static_cast<cudaStream_t>(stream)), "srk_gather_tiles");
+}
+
+int srk_stitch_accumulate_strided(const float* tiles, int64_t stride_n, int64_t stride_c, int64_t stride_y, int64_t stride_x, float* E,
+                                  int64_t e_channel_stride, const int32_t* dst_yx, int32_t num_tiles, int32_t channels, int32_t tile_h,
+                                  int32_t tile_w, int32_t out_h, int32_t out_w, void* stream) {
+    if (!tiles || !E || !dst_yx) return fail("srk_stitch_accumulate_strided: null argument");
+    if (num_tiles < 0 || num_tiles > 65535 || channels <= 0 || tile_h <= 0 || tile_w <= 0 || out_h <= 0 || out_w <= 0)
+        return fail("srk_stitch_accumulate_strided: bad shape");
+    return check(srk::launch_stitch_accumulate2(tiles, stride_n, stride_c, stride_y, stride_x, E, e_channel_stride, dst_yx, num_tiles, channels,
+                                                tile_h, tile_w, out_h, out_w, static_cast<cudaStream_t>(stream)), "srk_stitch_accumulate_strided");
+}
+
+int srk_stitch_finalize(const float* E, int64_t e_channel_stride, const float* cnt_y, const float* cnt_x, void* out, int64_t out_channel_stride,
+                        int32_t out_dtype, int32_t channels, int32_t out_h, int32_t out_w, void* stream) {
+    if (!E || !cnt_y || !cnt_x || !out) return fail("srk_stitch_finalize: null argument");
+    if (out_dtype < SRK_OUT_F32 || out_dtype > SRK_OUT_U8 || channels <= 0 || out_h <= 0 || out_w <= 0) return fail("srk_stitch_finalize: bad arguments");
+    return check(srk::launch_stitch_finalize(E, e_channel_stride, cnt_y, cnt_x, out, out_channel_stride, out_dtype, channels, out_h, out_w,
+                                             static_cast<cudaStream_t>(stream)), "srk_stitch_finalize");
+}
+
 int srk_stitch_normalize(float* E, const float* Wt, int32_t channels, int64_t pixels, void* stream) {
     if (!E || !Wt) return fail("srk_stitch_normalize: null argument");
     return check(srk::launch_stitch_normalize(E, Wt, channels, pixels, static_cast<cudaStream_t>(stream)), "srk_stitch_normalize");

@@ -452,12 +452,8 @@ cudaError_t launch_dat_mix(const float* att, const float* conv, const float* cma
                            float b2, int hidden, int mode, float* mix, int64_t tokens, int tokens_per_image, cudaStream_t stream) {
     if (tokens <= 0) return cudaSuccess;
     const size_t smem = (static_cast<size_t>(SRK_DIM) * MIX_MAX_HIDDEN + 2 * MIX_MAX_HIDDEN + MIX_WARPS * 32 * MIX_STRIDE) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(dat_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static bool configured[SRK_MAX_DEVICES] = {};
+    if (cudaError_t e = configure_smem_once(configured, dat_mix_kernel, static_cast<int>(smem)); e != cudaSuccess) return e;
     const int64_t groups = (tokens + 31) / 32;
     const int64_t blocks = (groups + MIX_WARPS - 1) / MIX_WARPS;
     const int grid = static_cast<int>(blocks < 148 * 2 ? blocks : 148 * 2);       // 2 CTAs of 108 KB per SM, persistent over token groups

@@ -86,6 +86,37 @@ struct WinAttnParams {
     int stagger;                 // cycles group 1 starts behind group 0
 };
 
+
+// Per-device one-time state.  cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count are properties of the CURRENT device
+// (the Python binding runs every call under the device of its tensors), so "configured once" must be once per device, not per process.
+constexpr int SRK_MAX_DEVICES = 64;
+inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < SRK_MAX_DEVICES) ? dev : 0;
+}
+inline int device_num_sms() {
+    static int sms[SRK_MAX_DEVICES] = {};
+    const int dev = current_device();
+    if (sms[dev] == 0) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        sms[dev] = n > 0 ? n : 148;
+    }
+    return sms[dev];
+}
+// cudaFuncSetAttribute(kern, MaxDynamicSharedMemorySize, bytes) once per (call site, device); `flags` is the call site's static array
+template <typename K>
+inline cudaError_t configure_smem_once(bool (&flags)[SRK_MAX_DEVICES], K kern, int bytes) {
+    const int dev = current_device();
+    if (!flags[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return e;
+        flags[dev] = true;
+    }
+    return cudaSuccess;
+}
+
 extern unsigned long long* g_timeline;
 extern int g_stagger_attn, g_stagger_mlp, g_stagger_winattn, g_pdl;
 
@@ -133,5 +164,12 @@ cudaError_t launch_dat_mix(const float* att, const float* conv, const float* cma
 cudaError_t launch_channel_gram(const float* qkv, float* gram, float* ws, int batch, int tokens_per_image, cudaStream_t stream);
 cudaError_t launch_channel_apply(const float* qkv, const float* attn, float* out, int batch, int tokens_per_image, cudaStream_t stream);
 cudaError_t launch_stitch_normalize(float* E, const float* Wt, int channels, int64_t pixels, cudaStream_t stream);
+cudaError_t launch_gather_tiles(const float* slab, int64_t slab_cstride, int slab_w, const int32_t* src_yx, int num_tiles, int channels,
+                                int tile_h, int tile_w, float* out, cudaStream_t stream);
+cudaError_t launch_stitch_accumulate2(const float* tiles, int64_t sn, int64_t sc, int64_t sy, int64_t sx, float* E, int64_t e_cstride,
+                                      const int32_t* dst_yx, int num_tiles, int channels, int tile_h, int tile_w, int out_h, int out_w,
+                                      cudaStream_t stream);
+cudaError_t launch_stitch_finalize(const float* E, int64_t e_cstride, const float* cnt_y, const float* cnt_x, void* out, int64_t o_cstride,
+                                   int dtype, int channels, int out_h, int out_w, cudaStream_t stream);
 
 }  // namespace srk

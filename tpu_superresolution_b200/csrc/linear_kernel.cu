@@ -273,19 +273,9 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) token_linear_kernel(const Line
 }
 
 cudaError_t launch_token_linear(const LinearParams& p, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(token_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
+    static bool configured[SRK_MAX_DEVICES] = {};
+    if (cudaError_t e = configure_smem_once(configured, token_linear_kernel, 232448); e != cudaSuccess) return e;
+    const int sms = device_num_sms();
     const bool need_stage = p.out_mode == SRK_LIN_OUT_ROWS && p.k_atoms == 3;
     const uint32_t smem = lin_smem(p.k_atoms, need_stage, p.out_mode == SRK_LIN_OUT_PLANES) + 1024;
     const int grid = p.n_tiles < sms ? p.n_tiles : sms;

@@ -863,36 +863,19 @@ __global__ void __launch_bounds__(LNW ? NTHREADS : 320, 1) swin_mlp_kernel(const
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-static int g_num_sms = 0;
-static int num_sms() {
-    if (g_num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
-    }
-    return g_num_sms;
-}
+static int num_sms() { return device_num_sms(); }
 
 cudaError_t launch_swin_attn(const AttnParams& p, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(swin_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static bool configured[SRK_MAX_DEVICES] = {};
+    if (cudaError_t e = configure_smem_once(configured, swin_attn_kernel, K1_SMEM); e != cudaSuccess) return e;
     const int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
     return launch_pdl(swin_attn_kernel, grid, K1_THREADS, K1_SMEM, stream, p);
 }
 
 cudaError_t launch_swin_mlp(const MlpParams& p, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(swin_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(swin_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static bool configured_a[SRK_MAX_DEVICES] = {}, configured_b[SRK_MAX_DEVICES] = {};
+    if (cudaError_t e = configure_smem_once(configured_a, swin_mlp_kernel<true>, K2_SMEM); e != cudaSuccess) return e;
+    if (cudaError_t e = configure_smem_once(configured_b, swin_mlp_kernel<false>, K2_SMEM); e != cudaSuccess) return e;
     const int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
     if (p.n_tiles > 2 * grid) return launch_pdl(swin_mlp_kernel<true>, grid, NTHREADS, K2_SMEM, stream, p);
     return launch_pdl(swin_mlp_kernel<false>, grid, 320, K2_SMEM, stream, p);

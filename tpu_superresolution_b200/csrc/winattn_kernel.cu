@@ -427,27 +427,14 @@ __global__ void __launch_bounds__(320, 1) winattn_kernel(const WinAttnParams p) 
     if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
-static int wa_num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
-}
+static int wa_num_sms() { return device_num_sms(); }
 
 template <int QH, int QW, int KH, int KW, int SY, int NCH>
 static cudaError_t launch_cfg(const WinAttnParams& p, cudaStream_t stream) {
     using C = WinAttnCfg<QH, QW, KH, KW, SY, NCH>;
-    static bool configured = false;
+    static bool configured[SRK_MAX_DEVICES] = {};
     auto kern = winattn_kernel<QH, QW, KH, KW, SY, NCH>;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    if (cudaError_t e = configure_smem_once(configured, kern, C::SMEM); e != cudaSuccess) return e;
     const int grid = p.n_items < wa_num_sms() ? p.n_items : wa_num_sms();
     return launch_pdl(kern, grid, 320, C::SMEM, stream, p);
 }
