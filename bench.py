@@ -1,14 +1,24 @@
 #!/usr/bin/env python
 """Benchmark of the fused window-attention SR path (BASELINE.json: "SwinIR/HAT x4 output Mpix/s").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
 
 One "step" = one pass of the hot path over one batch of synthetic input: by default BASELINE.json configs[1],
 SwinIR classical x4 on a batch of 16 LR tiles of 64x64 per GPU (16 x 3 x 256 x 256 = 1.049 output Mpix);
 `--workload hat_x4` / `dat_x2` time configs[2] (HAT x4, batch 8) and configs[3] (DAT x2, batch 16) the same way.
 With N > 1 (torchrun, one rank per GPU) every rank runs its own batch -- tiles are independent, there is
 no collective on the data path -- so scaling is "weak" and `value` is the sum over ranks divided by the
-slowest rank's time.  JSON keys follow the driver contract; see DESIGN.md "Measurement".
+slowest rank's time.
+
+configs[4] -- tiled x4 SwinIR inference of a synthetic 4096x4096 LR image (5 329 overlapping 64-px tiles) sharded over
+the ranks, timed from LR-resident to the stitched image resident on rank 0, the NCCL gather of the bands included -- is
+measured (a) as the `tiled_4096` object of every default line (a few steps, so SCALE_rNN.json carries its strong
+scaling at N = 1/2/4/8 beside the replica numbers) and (b) as the main metric with `--workload tiled_4096`
+(`scaling: "strong"`, value = unique output Mpix/s).
+
+Reference arms: `--impl reference` = the UNMODIFIED reference modules (staged into oracle/_ref by build(); else the
+oracle port) on the host cores, full step; the default line also carries `reference_gpu` = the same unmodified modules'
+eager CUDA forward (fp32 and bf16 autocast, finetune_swinir.py:194) on the same GPU.  JSON keys follow the driver contract.
 """
 from __future__ import annotations
 
@@ -34,7 +44,8 @@ WORKLOADS = {
         workload="SwinIR classical x4 (embed 180, 6 RSTB x 6, window 8, 6 heads, mlp_ratio 2), batch 16 of 64x64 LR tiles per GPU",
         dominant="swin_attn", kernel_name="swin_attn_kernel",
         kernels={"swin_attn": 305_280,      # qkv + qk^T + pv + proj (one swin_attn_kernel launch covers all tokens of the batch)
-                 "swin_mlp": 259_200}),     # fc1 + fc2
+                 "swin_mlp": 259_200,       # fc1 + fc2
+                 "conv3x3_c180": 583_200}), # 3x3 conv 180 -> 180 as an implicit GEMM
     # BASELINE.json configs[2]: HAT x4, window 16, OCAB overlap 0.5, CAB, batch 8
     "hat_x4": dict(
         metric="HAT x4 output Mpix/s", family="hat", cfg="hat_x4", tiles=8, scale=4, gflop_per_tile=207.761,
@@ -52,24 +63,58 @@ WORKLOADS = {
                  # per DATB: spatial qkv planes 194400 + v rows 64800 (or channel qkv 194400) + proj 64800 + fc1 259200 + fc2 2 x 64800
                  "linear": (18 * (194_400 + 64_800) + 18 * 194_400 + 36 * (64_800 + 259_200 + 129_600)) / (18 * 2 + 18 + 36 * 4)}),
 }
+# BASELINE.json configs[4]: same model as swinir_x4
+TILED = dict(height=4096, width=4096, overlap=8, batch=16, tiles=5329, unique_mpix=268.435456,
+             workload="tiled x4 SwinIR inference of a synthetic 4096x4096 LR image: 5329 overlapping 64-px tiles (overlap 8), HR row bands sharded over the GPUs, "
+                      "seam tiles recomputed, one gather of the stitched bands to GPU 0")
+WORKLOADS["tiled_4096"] = dict(WORKLOADS["swinir_x4"], metric="tiled SwinIR x4 unique output Mpix/s (4096x4096 LR)", workload=TILED["workload"])
 W = WORKLOADS["swinir_x4"]      # replaced in main()
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def shared_config():
+    """The `config` object of BOTH arms (identical, so the driver can pair them)."""
+    return {"workload": W["workload"], "tiles_per_step_per_gpu": W["tiles"], "input": "synthetic fp32 LR tiles in [0,1), numpy RNG",
+            "l2": "GPU arm: flushed between steps (256 MiB memset outside the timed events); CPU arm: not applicable"}
 
 
 def _build(family, cfg_name):
-    """-> (cfg, state_dict, model class, CPU oracle forward) for a workload (synthetic weights, numpy RNG)."""
-    from oracle import synth
+    """-> (cfg, state_dict, drop-in model class) for a workload (synthetic weights, numpy RNG)."""
+    from tpu_superresolution_b200 import synth
     import tpu_superresolution_b200 as srk
     if family == "swinir":
-        from oracle import swinir_oracle as O
         cfg = synth.CONFIGS[cfg_name]
-        return cfg, synth.make_swinir_state_dict(cfg, seed=1234, kind="init"), srk.SwinIR, O.swinir_forward
+        return cfg, synth.make_swinir_state_dict(cfg, seed=1234, kind="init"), srk.SwinIR
+    if family == "hat":
+        cfg = synth.HAT_CONFIGS[cfg_name]
+        return cfg, synth.make_hat_state_dict(cfg, seed=1234, kind="init"), srk.HAT
+    cfg = synth.DAT_CONFIGS[cfg_name]
+    return cfg, synth.make_dat_state_dict(cfg, seed=1234, kind="init"), srk.DAT
+
+
+def reference_forward(family, cfg, sd, device="cpu"):
+    """-> (callable lr -> sr, kind): the UNMODIFIED reference module (oracle/_ref, staged by build()) when present -- kind
+    "reference" -- else the oracle restatement (CPU only) -- kind "port".  The only place bench.py executes oracle/."""
+    have_ref = os.path.isfile(os.path.join(REF_DIR, "modules", "network_swinir.py")) or os.path.isdir("/root/reference/modules")
+    if have_ref:
+        if not os.path.isdir("/root/reference/modules"):
+            os.environ["SRK_REFERENCE_ROOT"] = REF_DIR
+        from oracle.reference_loader import load_reference_module
+        modname, clsname = {"swinir": ("network_swinir", "SwinIR"), "hat": ("hat_arch", "HAT"), "dat": ("dat_arch", "DAT")}[family]
+        model = getattr(load_reference_module(modname), clsname)(**cfg.as_kwargs()).eval()
+        model.load_state_dict(sd, strict=True)
+        model.to(device)
+        return (lambda lr: model(lr)), "reference"
+    if device != "cpu":
+        return None, "unavailable"
+    if family == "swinir":
+        from oracle import swinir_oracle as O
+        return (lambda lr: O.swinir_forward(lr, sd, cfg)), "port"
     if family == "hat":
         from oracle import hat_oracle as HO
-        cfg = synth.HAT_CONFIGS[cfg_name]
-        return cfg, synth.make_hat_state_dict(cfg, seed=1234, kind="init"), srk.HAT, HO.hat_forward
+        return (lambda lr: HO.hat_forward(lr, sd, cfg)), "port"
     from oracle import dat_oracle as DO
-    cfg = synth.DAT_CONFIGS[cfg_name]
-    return cfg, synth.make_dat_state_dict(cfg, seed=1234, kind="init"), srk.DAT, DO.dat_forward
+    return (lambda lr: DO.dat_forward(lr, sd, cfg)), "port"
 
 
 def _peaks():
@@ -158,59 +203,149 @@ def _barrier(world: int):
     torch.cuda.synchronize()
 
 
-def cpu_oracle_rate(tiles: int, reps: int = 1, warm: bool = True):
-    """Reference algorithm on the host cores (oracle port, fp32): output Mpix/s on `tiles` tiles of the workload."""
-    from oracle import synth
+def cpu_reference_rate(tiles: int, reps: int = 1, warm: bool = True):
+    """The reference's CPU forward (unmodified modules if staged, else the oracle port; fp32) on the host cores:
+    output Mpix/s on `tiles` tiles of the workload."""
+    from tpu_superresolution_b200 import synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg, sd, _, oracle_fwd = _build(W["family"], W["cfg"])
+    cfg, sd, _ = _build(W["family"], W["cfg"])
+    fwd, kind = reference_forward(W["family"], cfg, sd)
     lr = synth.make_lr_batch(tiles, TILE, TILE, seed=2)
     with torch.no_grad():
         if warm:
-            oracle_fwd(lr[:1], sd, cfg)
+            fwd(lr[:1])
         best = float("inf")
         for _ in range(reps):
             t0 = time.perf_counter()
-            oracle_fwd(lr, sd, cfg)
+            fwd(lr)
             best = min(best, time.perf_counter() - t0)
-    return tiles * (TILE * W['scale']) ** 2 / best / 1e6, cores, best
+    return tiles * (TILE * W['scale']) ** 2 / best / 1e6, cores, best, kind
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port; the reference is pure Python and cannot be
-    compiled into oracle/_ref) on all host cores; each step is a bounded 2-tile sample of the workload."""
+    """--impl reference: the reference's own CPU implementation of the path (the unmodified modules staged into oracle/_ref by
+    build(); the oracle port if they are absent) on all host cores, the FULL step (all tiles of the batch) per timed step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import synth
+    from tpu_superresolution_b200 import synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample_tiles = 2
-    cfg, sd, _, oracle_fwd = _build(W["family"], W["cfg"])
-    lr = synth.make_lr_batch(sample_tiles, TILE, TILE, seed=2)
+    tiles = W["tiles"]
+    cfg, sd, _ = _build(W["family"], W["cfg"])
+    fwd, kind = reference_forward(W["family"], cfg, sd)
+    lr = synth.make_lr_batch(tiles, TILE, TILE, seed=2)
     with torch.no_grad():
         for _ in range(args.warmup):
-            oracle_fwd(lr, sd, cfg)
+            fwd(lr)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            oracle_fwd(lr, sd, cfg)
+            fwd(lr)
         dt = time.perf_counter() - t0
-    mpix = sample_tiles * (TILE * W['scale']) ** 2 / 1e6
+    mpix = tiles * (TILE * W['scale']) ** 2 / 1e6
     value = mpix * args.steps / dt
-    sample = f"{sample_tiles} of the {W['tiles']} tiles of one step per timed step, fp32, torch CPU ops, {cores} threads"
+    sample = f"all {tiles} tiles of one step per timed step, fp32, {'unmodified reference modules (oracle/_ref)' if kind == 'reference' else 'oracle port'}, torch CPU ops, {cores} threads"
     print(json.dumps({
         "impl": "reference", "metric": W["metric"], "value": value, "unit": "Mpix/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": W["workload"], "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": shared_config(),
+        "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
+def reference_gpu_rates(dev, lr_dev, steps):
+    """The unmodified reference's EAGER CUDA forward on this GPU (what the reference does today: ~850 launches per SwinIR
+    forward), fp32 and under bf16 autocast (finetune_swinir.py:194), same weights and inputs, CUDA events."""
+    cfg, sd, _ = _build(W["family"], W["cfg"])
+    fwd, kind = reference_forward(W["family"], cfg, sd, device=dev)
+    if fwd is None:
+        return {"unavailable": "oracle/_ref not staged (build() runs where /root/reference exists)"}
+    out = {"kind": "unmodified reference modules (oracle/_ref), eager PyTorch CUDA forward, same weights / inputs / batch", "steps": steps}
+    mpix = lr_dev.shape[0] * (TILE * W['scale']) ** 2 / 1e6
+    stream = torch.cuda.current_stream()
+    for name, ctx in (("fp32", torch.autocast("cuda", enabled=False)), ("bf16_autocast", torch.autocast("cuda", dtype=torch.bfloat16))):
+        with torch.no_grad(), ctx:
+            for _ in range(2):
+                fwd(lr_dev)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(steps):
+                fwd(lr_dev)
+            e1.record(stream)
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out[name] = {"value": mpix / (ms * 1e-3), "unit": "Mpix/s", "ms_per_step": ms}
+    return out
+
+
+def run_tiled(model, dev, world, rank, steps, warmup):
+    """BASELINE.json configs[4]: strong scaling of the tiled 4096x4096 image over `world` ranks (tiling.TiledSuperResolver).
+    value: LR resident on every rank's device -> stitched fp32 image resident on rank 0, gather included (CUDA events, max over
+    ranks).  e2e: pinned host uint8 LR -> each rank copies its rows -> uint8 stitched image in pinned host memory on rank 0."""
+    from tpu_superresolution_b200 import synth, tiling
+    H, Wd = TILED["height"], TILED["width"]
+    lr = synth.make_lr_batch(1, H, Wd, seed=0)
+    lr_dev = lr.to(dev)
+    res = tiling.TiledSuperResolver(model, scale=4, tile=TILE, overlap=TILED["overlap"], batch=TILED["batch"])
+    res8 = tiling.TiledSuperResolver(model, scale=4, tile=TILE, overlap=TILED["overlap"], batch=TILED["batch"], out_dtype=torch.uint8)
+    res8.run_tiles = res.run_tiles                      # share the captured graph
+    stream = torch.cuda.current_stream()
+    plan = res.plan(H, Wd, rank, world, dev)
+
+    def timed(fn, n):
+        ts = []
+        for _ in range(n):
+            _barrier(world)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            _barrier(world)
+            ts.append(_max_over_ranks(e0.elapsed_time(e1) * 1e-3, world))
+        return ts
+
+    with torch.no_grad():
+        for _ in range(warmup):
+            out = res(lr_dev, rank=rank, world=world)
+            del out
+        t_full = timed(lambda: res(lr_dev, rank=rank, world=world), steps)
+        t_band = timed(lambda: res(lr_dev, rank=rank, world=world, gather=False), max(1, min(steps, 2)))      # no gather: its cost by difference
+        # end to end: host uint8 LR -> uint8 HR image in pinned host memory on rank 0
+        lr8 = (lr * 255).round().to(torch.uint8).pin_memory()
+        host_out = torch.empty(1, 3, H * 4, Wd * 4, dtype=torch.uint8).pin_memory() if rank == 0 else None
+
+        def e2e_step():
+            o = res8(lr8, rank=rank, world=world, device=dev)
+            if rank == 0:
+                host_out.copy_(o, non_blocking=True)
+        e2e_step()
+        t_e2e = timed(e2e_step, max(1, min(steps, 2)))
+    t = sum(t_full) / len(t_full)
+    tb = sum(t_band) / len(t_band)
+    te = sum(t_e2e) / len(t_e2e)
+    gather_bytes = 3 * (H * 4) * (Wd * 4) * 4 * (world - 1) / world
+    band_rows = plan.band[1] - plan.band[0]
+    return {
+        "workload": TILED["workload"], "scaling": "strong", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "value": TILED["unique_mpix"] / t, "unit": "unique output Mpix/s", "ms_per_step": t * 1e3,
+        "tiles_total": TILED["tiles"], "tiles_rank0": plan.n_tiles, "lr_rows_rank0": band_rows,
+        "seam_recompute_fraction": tiling.seam_recompute_fraction(H, Wd, TILE, TILED["overlap"], world),
+        "compute_and_stitch_ms": tb * 1e3, "gather_ms": max(0.0, (t - tb)) * 1e3,
+        "gather_bytes_into_rank0": gather_bytes, "gather_gbs": (gather_bytes / max(t - tb, 1e-9) / 1e9) if world > 1 else None,
+        "frac_of_sustained_bf16_peak": TILED["tiles"] * W["gflop_per_tile"] / t / 1e3 / _peaks()[0] / world,
+        "e2e": {"value": TILED["unique_mpix"] / te, "unit": "unique output Mpix/s", "ms_per_step": te * 1e3,
+                "h2d_bytes_per_step": 3 * H * Wd, "d2h_bytes_per_step": 3 * H * 4 * Wd * 4,
+                "mode": "pinned host uint8 LR -> per-rank H2D of its rows -> uint8 stitched image -> pinned host on rank 0"},
+        "timed": "CUDA events per step on every rank, barrier + synchronize both sides, max over ranks; LR resident, output resident on rank 0",
+    }
+
+
 def run_ours(args):
-    from oracle import synth                      # synthetic weights / inputs only (numpy RNG), not the checker
-    import tpu_superresolution_b200 as srk
+    from tpu_superresolution_b200 import synth    # synthetic weights / inputs (numpy RNG)
     from tpu_superresolution_b200 import _lib as L
 
     world, rank, local = _dist_setup(args.gpus)
@@ -223,10 +358,34 @@ def run_ours(args):
     torch.backends.cudnn.benchmark = True
 
     TILES_PER_STEP = W["tiles"]
-    cfg, sd, model_cls, _ = _build(W["family"], W["cfg"])
+    cfg, sd, model_cls = _build(W["family"], W["cfg"])
     model = model_cls(**cfg.as_kwargs()).eval()
     model.load_state_dict(sd, strict=True)
     model.to(dev)
+
+    if args.workload == "tiled_4096":                   # configs[4] as the main metric
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        l0 = L.launch_count()
+        tiled = run_tiled(model, dev, world, rank, args.steps, args.warmup)
+        launches = L.launch_count() - l0
+        clocks = sampler.stop() if rank == 0 else None
+        if rank == 0:
+            print(json.dumps({
+                "metric": W["metric"], "value": tiled["value"], "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": tiled["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic", "config": {"workload": TILED["workload"], "tiles_per_step": TILED["tiles"],
+                                                "l2": "inputs larger than L2 (201 MB LR, 3.2 GB output per step)"},
+                "e2e": tiled["e2e"], "gpu_launches": int(launches), "clocks": clocks, "tiled_4096": tiled,
+                "roofline": {"kernel": "whole step", "bound": "tensor", "achieved": tiled["frac_of_sustained_bf16_peak"] * _peaks()[0],
+                             "peak": _peaks()[0], "unit": "TFLOP/s", "frac": tiled["frac_of_sustained_bf16_peak"], "traffic": None},
+                "cpu_baseline": None}))
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return
+
     # one cudaGraphLaunch per step instead of ~1000 kernel launches: at this batch size the eager forward is bound by the
     # host's launch rate (tpu_superresolution_b200/graphs.py); --eager times the plain module instead
     from tpu_superresolution_b200.graphs import GraphedModel
@@ -327,6 +486,12 @@ def run_ours(args):
     L.PROFILE = None
     kstats = {k: (sum(a.elapsed_time(b) for a, b in v) / len(v), len(v)) for k, v in prof.items()}
 
+    # ---- BASELINE.json configs[4] beside the replica number (SwinIR x4 only): a few steps of the tiled 4096x4096 image
+    tiled = None
+    if W["cfg"] == "swinir_x4" and not args.no_tiled:
+        flush = None
+        tiled = run_tiled(model, dev, world, rank, steps=max(1, min(args.steps, 3)), warmup=1)
+
     if rank != 0:
         if world > 1:
             import torch.distributed as dist
@@ -349,12 +514,14 @@ def run_ours(args):
         with open(tpath) as f:
             traffic = json.load(f).get(W["kernel_name"] + "_dram_bytes_per_launch")
 
-    cpu_tiles = TILES_PER_STEP if (os.cpu_count() or 1) >= 16 else 4
-    cpu_baseline = None                         # reported at N = 1 only (driver contract)
+    cpu_baseline, ref_gpu = None, None          # reported at N = 1 only (driver contract)
     if world == 1:
-        cpu_val, cores, cpu_s = cpu_oracle_rate(tiles=cpu_tiles)
-        cpu_baseline = {"value": cpu_val, "unit": "Mpix/s", "cores": cores, "kind": "port",
-                        "sample": f"{cpu_tiles} of the {TILES_PER_STEP} tiles of one step, fp32 oracle port (torch CPU ops), {cpu_s:.1f} s"}
+        cpu_tiles = TILES_PER_STEP if (os.cpu_count() or 1) >= 16 else 4
+        cpu_val, cores, cpu_s, kind = cpu_reference_rate(tiles=cpu_tiles)
+        cpu_baseline = {"value": cpu_val, "unit": "Mpix/s", "cores": cores, "kind": kind,
+                        "sample": f"{cpu_tiles} of the {TILES_PER_STEP} tiles of one step, fp32, "
+                                  f"{'unmodified reference modules (oracle/_ref)' if kind == 'reference' else 'oracle port'} (torch CPU ops), {cpu_s:.1f} s"}
+        ref_gpu = reference_gpu_rates(dev, dev_in[0], steps=max(2, min(args.steps, 10)))
 
     ms_step = t_res / args.steps * 1e3
     value = world * mpix_step * args.steps / t_res
@@ -363,10 +530,10 @@ def run_ours(args):
         "metric": W["metric"], "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": W["workload"], "tiles_per_step_per_gpu": TILES_PER_STEP, "parallelism": f"tile-sharded x{world}, no collective",
-                   "precision": "bf16 MMA operands, fp32 accumulate, fp32 residual stream; convs cuDNN TF32",
+        "config": shared_config(),
+        "detail": {"parallelism": f"tile-sharded x{world}, no collective",
+                   "precision": "bf16 MMA operands, fp32 accumulate, fp32 residual stream",
                    "launch": "eager" if args.eager else "one CUDA graph replay per step",
-                   "l2": "flushed between steps (256 MiB memset outside the timed events)",
                    "whole_model_tflops": model_tf, "whole_model_frac_of_peak": model_tf / world / peak_tf},
         "e2e": {"value": world * mpix_step * args.steps / t_e2e, "unit": "Mpix/s",
                 "h2d_bytes_per_step": host_in[0].numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4,
@@ -376,10 +543,15 @@ def run_ours(args):
         "roofline": {"kernel": W["kernel_name"], "bound": "tensor", "achieved": dom["achieved"], "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src,
                      "avg_launch_ms": dom["avg_launch_ms"], "launches_timed": dom["launches_timed"],
+                     "avg_launch_ms_note": "eager pass with CUDA events around every launch: no programmatic-dependent-launch / progress-counter "
+                                           "overlap between kernels, so this is a conservative (upper) launch time",
                      "algorithmic_flop_per_launch": dom["algorithmic_flop_per_launch"],
-                     "other_kernels": {k: kstat(k) for k in W["kernels"] if k != W["dominant"]},
-                     "libsrk_ms_per_step": sum(v[0] * v[1] for v in kstats.values()) / 3.0},
+                     "other_kernels": {k: kstat(k) for k in W["kernels"] if k != W["dominant"] and k in kstats},
+                     "libsrk_ms_per_step": sum(v[0] * v[1] for v in kstats.values()) / 3.0,
+                     "per_kernel_ms_per_step": {k: v[0] * v[1] / 3.0 for k, v in sorted(kstats.items())}},
         "cpu_baseline": cpu_baseline,
+        "reference_gpu": ref_gpu,
+        "tiled_4096": tiled,
     }
     print(json.dumps(out))
     if world > 1:
@@ -390,11 +562,12 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="swinir_x4", choices=sorted(WORKLOADS))
     ap.add_argument("--eager", action="store_true", help="time the plain module instead of the CUDA-graph replay")
+    ap.add_argument("--no-tiled", action="store_true", help="skip the tiled_4096 object of the default line")
     args = ap.parse_args()
     global W
     W = WORKLOADS[args.workload]

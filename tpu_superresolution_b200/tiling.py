@@ -211,7 +211,12 @@ class TiledSuperResolver:
         r0, r1 = p.band
         th, tw = p.tile_hw
         # the LR rows this rank reads; a host image is copied band-wise (pinned memory: asynchronously)
-        slab = lr[0, :, p.rows[0]:p.rows[1], :].to(device, non_blocking=True)
+        if lr.device == device:
+            slab = lr[0, :, p.rows[0]:p.rows[1], :]
+        else:                                   # one contiguous (rows x W) copy per channel plane: asynchronous from pinned memory
+            slab = torch.empty(C, p.rows[1] - p.rows[0], W, device=device, dtype=lr.dtype)
+            for c in range(C):
+                slab[c].copy_(lr[0, c, p.rows[0]:p.rows[1], :], non_blocking=True)
         if slab.dtype == torch.uint8:
             slab = slab.float().div_(255.0)
         slab = slab.float().contiguous()
