@@ -255,6 +255,42 @@ int srk_stitch_accumulate_strided(const float* tiles, int64_t stride_n, int64_t 
 int srk_stitch_finalize(const float* E, int64_t e_channel_stride, const float* cnt_y, const float* cnt_x, void* out, int64_t out_channel_stride,
                         int32_t out_dtype, int32_t channels, int32_t out_h, int32_t out_w, void* stream);
 
+/* 3x3 convolution, stride 1, zero padding 1, as a tcgen05 implicit GEMM with the conv's tail fused (csrc/conv_kernel.cu).
+ * Replaces F.conv2d / nn.Conv2d(…, 3, 1, 1) at network_swinir.py:465 (RSTB), :720 (conv_first), :729 (conv_after_body), :742-745
+ * (conv_before_upsample, Upsample, conv_last), hat_arch.py:67-72 (CAB) and the same layers of hat_arch.py / dat_arch.py.
+ *   in       fp16 NHWC (batch, height, width, 64 * k_atoms), channels zero-padded (written by srk_rows_to_f16 /
+ *            srk_image_to_f16_split or by a previous srk_conv3x3_fwd in an fp16 output mode)
+ *   wstream  packing.pack_conv3x3: k_atoms x 3 x 3 slabs of np rows x 128 B;  bias: np floats
+ *   out      SRK_CONV_OUT_ROWS_F32:     fp32 (pixels, ld_out), out = act(conv + bias) [+ residual]; residual may alias out
+ *            SRK_CONV_OUT_NHWC_F16:     fp16 (pixels, ld_out) with ld_out >= np (the next convolution's input)
+ *            SRK_CONV_OUT_SHUFFLE2_F16: np = 256: fp16 (batch, 2 height, 2 width, 64) = nn.PixelShuffle(2) of the conv output
+ *                                       (network_swinir.py:584-585; pack_conv3x3(pixel_shuffle=True) permutes the weight rows)
+ *            SRK_CONV_OUT_IMAGE:        cout <= 4, np = 16: fp32 (pixels, ld_out = cout)
+ * fp16 operands (11-bit significand, as the TF32 library path had), fp32 accumulation. */
+#define SRK_CONV_OUT_ROWS_F32 0
+#define SRK_CONV_OUT_NHWC_F16 1
+#define SRK_CONV_OUT_SHUFFLE2_F16 2
+#define SRK_CONV_OUT_IMAGE 3
+typedef struct SrkConvDesc {
+    int32_t batch, height, width;
+    int32_t k_atoms;        /* padded input channels / 64: 1..4 */
+    int32_t np;             /* padded output channels: multiple of 32 (16 for SRK_CONV_OUT_IMAGE), <= 256 */
+    int32_t cout;           /* real output channels (multiple of 4 for SRK_CONV_OUT_ROWS_F32) */
+    int32_t out_mode;
+    int32_t ld_out;
+    int32_t act;            /* SRK_ACT_* */
+    float slope;
+} SrkConvDesc;
+int srk_conv3x3_fwd(const SrkConvDesc* desc, const void* in_f16, const void* wstream, const float* bias, const float* residual, void* out,
+                    void* stream);
+/* fp32 token rows (pixels, ld_in) with `channels` channels -> fp16 NHWC (pixels, cp), cp = 64 * k_atoms, zero padded. */
+int srk_rows_to_f16(const float* x, int32_t ld_in, int32_t channels, void* out_f16, int32_t cp, int64_t pixels, void* stream);
+/* network input (batch, channels <= 3, height, width) fp32 with element strides (sb, sc, sy, sx) -> fp16 NHWC (pixels, 64) holding
+ * [hi(v), v - hi(v), hi(v)] of v = (x - mean[c]) * range (network_swinir.py:803-804): conv_first's input with the fp16 rounding
+ * compensated (pack_conv3x3(split_first=True) packs [hi(w), hi(w), w - hi(w)]).  mean3: 3 floats in HOST memory. */
+int srk_image_to_f16_split(const float* x, int64_t sb, int64_t sc, int64_t sy, int64_t sx, int32_t channels, int32_t batch, int32_t height,
+                           int32_t width, const float* mean3, float range, void* out_f16, void* stream);
+
 int srk_abi_version(void);
 const char* srk_last_error_string(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */

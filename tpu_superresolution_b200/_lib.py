@@ -43,6 +43,13 @@ class LinearDesc(Structure):
                [("plane_phase_mask", ctypes.c_uint32)]
 
 
+class ConvDesc(Structure):
+    _fields_ = [(n, c_int32) for n in ("batch", "height", "width", "k_atoms", "np", "cout", "out_mode", "ld_out", "act")] + [("slope", ctypes.c_float)]
+
+
+CONV_OUT_ROWS_F32, CONV_OUT_NHWC_F16, CONV_OUT_SHUFFLE2_F16, CONV_OUT_IMAGE = 0, 1, 2, 3
+
+
 class WinAttnDesc(Structure):
     _fields_ = [(n, c_int32) for n in ("kind", "batch", "height", "width", "shift_y", "shift_x", "mask_shift", "n_heads",
                                        "emask_nw", "out_mode", "out_ld", "out_col0")]
@@ -126,6 +133,10 @@ def load():
     lib.srk_stitch_accumulate.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                           c_int32, c_int32, c_void_p]
     lib.srk_stitch_normalize.argtypes = [c_void_p, c_void_p, c_int32, c_int64, c_void_p]
+    lib.srk_conv3x3_fwd.argtypes = [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.srk_rows_to_f16.argtypes = [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int64, c_void_p]
+    lib.srk_image_to_f16_split.argtypes = [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32,
+                                           POINTER(ctypes.c_float), ctypes.c_float, c_void_p, c_void_p]
     lib.srk_gather_tiles.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]
     lib.srk_stitch_accumulate_strided.argtypes = [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int32, c_int32,
                                                   c_int32, c_int32, c_int32, c_int32, c_void_p]
@@ -155,7 +166,7 @@ def load():
     lib.srk_debug_set_pdl.restype = None
     for f in ("srk_swin_attn_fwd", "srk_swin_mlp_fwd", "srk_swin_attn_fwd_sync", "srk_swin_mlp_fwd_sync", "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd", "srk_pixelshuffle_nhwc_bias_fwd", "srk_bias_act_add_nhwc",
               "srk_stitch_accumulate", "srk_stitch_normalize", "srk_gather_tiles", "srk_stitch_accumulate_strided", "srk_stitch_finalize",
-              "srk_linear_fwd", "srk_window_attention_fwd",
+              "srk_conv3x3_fwd", "srk_rows_to_f16", "srk_image_to_f16_split", "srk_linear_fwd", "srk_window_attention_fwd",
               "srk_window_attention_table_floats", "srk_cab_gate_add", "srk_dwconv3x3_rows_fwd", "srk_row_stats_fwd", "srk_dat_mix_fwd",
               "srk_dat_channel_gram_fwd", "srk_dat_channel_apply_fwd", "srk_dat_channel_gram_ws_floats", "srk_cab_ws_floats", "srk_token_mean_fwd"):
         getattr(lib, f).restype = c_int32
@@ -168,7 +179,7 @@ def load():
 EXPORTS = ("srk_abi_version", "srk_last_error_string", "srk_launch_count", "srk_swin_attn_fwd", "srk_swin_mlp_fwd",
            "srk_swin_attn_fwd_sync", "srk_swin_mlp_fwd_sync",
            "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd", "srk_pixelshuffle_nhwc_bias_fwd", "srk_bias_act_add_nhwc", "srk_stitch_accumulate", "srk_stitch_normalize", "srk_gather_tiles", "srk_stitch_accumulate_strided", "srk_stitch_finalize",
-           "srk_debug_set_timeline", "srk_debug_set_stagger",
+           "srk_conv3x3_fwd", "srk_rows_to_f16", "srk_image_to_f16_split", "srk_debug_set_timeline", "srk_debug_set_stagger",
            "srk_linear_fwd", "srk_window_attention_fwd", "srk_window_attention_table_floats", "srk_debug_set_winattn_stagger", "srk_debug_set_pdl",
            "srk_cab_gate_add", "srk_dwconv3x3_rows_fwd", "srk_row_stats_fwd", "srk_dat_mix_fwd", "srk_dat_channel_gram_fwd",
            "srk_dat_channel_apply_fwd", "srk_dat_channel_gram_ws_floats", "srk_cab_ws_floats", "srk_token_mean_fwd")
@@ -312,6 +323,48 @@ def stitch_finalize(E, cnt_y, cnt_x, out) -> None:
     with _launch("stitch_finalize", E, cnt_y, cnt_x, out) as st:
         _check(lib.srk_stitch_finalize(E.data_ptr(), E.stride(0), cnt_y.data_ptr(), cnt_x.data_ptr(), out.data_ptr(), out.stride(0),
                                        OUT_DTYPES[out.dtype], E.shape[0], E.shape[1], E.shape[2], st), lib)
+
+
+def conv3x3(x16, wstream, bias, out, *, batch, height, width, k_atoms, np_, cout, out_mode, ld_out, act=ACT_NONE, slope=0.0,
+            residual=None) -> None:
+    """srk_conv3x3_fwd (include/srk.h): x16 = fp16 NHWC (batch, height, width, 64 k_atoms); out per out_mode."""
+    lib = load()
+    if x16.dtype != torch.float16 or x16.numel() != batch * height * width * 64 * k_atoms or not x16.is_contiguous():
+        raise RuntimeError("conv3x3: input must be a contiguous fp16 NHWC tensor of batch * height * width * 64 * k_atoms elements")
+    want = torch.float32 if out_mode in (CONV_OUT_ROWS_F32, CONV_OUT_IMAGE) else torch.float16
+    if out.dtype != want or not out.is_contiguous():
+        raise RuntimeError(f"conv3x3: output must be contiguous {want}")
+    if wstream.numel() != 9 * k_atoms * np_ * 128 or bias.numel() != np_:
+        raise RuntimeError("conv3x3: weight stream / bias size does not match k_atoms, np")
+    _require_cuda_f32(bias, residual)
+    d = ConvDesc(batch, height, width, k_atoms, np_, cout, out_mode, ld_out, act, float(slope))
+    label = "conv3x3" if PROFILE is None else f"conv3x3_c{64 * k_atoms}_n{np_}"
+    with _launch(label, x16, wstream, bias, out, residual) as st:
+        _check(lib.srk_conv3x3_fwd(ctypes.byref(d), x16.data_ptr(), wstream.data_ptr(), bias.data_ptr(), _ptr(residual), out.data_ptr(), st), lib)
+
+
+def rows_to_f16(x, out16, *, channels, ld_in, pixels) -> None:
+    """srk_rows_to_f16: fp32 rows (pixels, ld_in) -> fp16 NHWC (pixels, cp), cp = out16.shape[-1] (multiple of 64), zero padded."""
+    lib = load()
+    _require_cuda_f32(x)
+    cp = out16.shape[-1]
+    if out16.dtype != torch.float16 or not out16.is_contiguous() or out16.numel() != pixels * cp:
+        raise RuntimeError("rows_to_f16: output must be a contiguous fp16 (pixels, cp) tensor")
+    with _launch("rows_to_f16", x, out16) as st:
+        _check(lib.srk_rows_to_f16(x.data_ptr(), ld_in, channels, out16.data_ptr(), cp, pixels, st), lib)
+
+
+def image_to_f16_split(x, out16, mean, img_range) -> None:
+    """srk_image_to_f16_split: (B, C <= 3, H, W) fp32 (any strides) -> fp16 NHWC (B * H * W, 64) of (x - mean) * range, hi / lo split."""
+    lib = load()
+    _require_cuda_f32(x)
+    B, C, H, W = x.shape
+    if out16.dtype != torch.float16 or not out16.is_contiguous() or out16.numel() != B * H * W * 64:
+        raise RuntimeError("image_to_f16_split: output must be a contiguous fp16 (B * H * W, 64) tensor")
+    m = (ctypes.c_float * 3)(*([float(v) for v in mean] + [0.0] * 3)[:3])
+    sb, sc, sy, sx = x.stride()
+    with _launch("image_to_f16", x, out16) as st:
+        _check(lib.srk_image_to_f16_split(x.data_ptr(), sb, sc, sy, sx, C, B, H, W, m, float(img_range), out16.data_ptr(), st), lib)
 
 
 _ZERO_PAGES = {}

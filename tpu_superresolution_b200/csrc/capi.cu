@@ -363,6 +363,61 @@ int srk_stitch_finalize(const float* E, int64_t e_channel_stride, const float* c
                                              static_cast<cudaStream_t>(stream)), "srk_stitch_finalize");
 }
 
+int srk_conv3x3_fwd(const SrkConvDesc* d, const void* in_f16, const void* wstream, const float* bias, const float* residual, void* out,
+                    void* stream) {
+    if (!d || !in_f16 || !wstream || !bias || !out) return fail("srk_conv3x3_fwd: null argument");
+    if (d->batch <= 0 || d->height <= 0 || d->width <= 0) return fail("srk_conv3x3_fwd: bad image shape");
+    if (d->k_atoms < 1 || d->k_atoms > 4) return fail("srk_conv3x3_fwd: k_atoms must be 1..4 (got %d)", d->k_atoms);
+    if (!aligned16(in_f16) || !aligned16(wstream) || !aligned16(out) || (residual && !aligned16(residual)))
+        return fail("srk_conv3x3_fwd: pointers must be 16-byte aligned");
+    if (static_cast<int64_t>(d->batch) * d->height * d->width * 4 >= (int64_t(1) << 31)) return fail("srk_conv3x3_fwd: too many pixels");
+    srk::ConvArgs a{};
+    a.in = static_cast<const __half*>(in_f16); a.wstream = static_cast<const uint8_t*>(wstream); a.bias = bias; a.residual = residual;
+    a.B = d->batch; a.H = d->height; a.W = d->width; a.k_atoms = d->k_atoms; a.np = d->np; a.cout = d->cout;
+    a.out_mode = d->out_mode; a.ld_out = d->ld_out; a.act = d->act; a.slope = d->slope;
+    switch (d->out_mode) {
+        case SRK_CONV_OUT_ROWS_F32:
+            if (d->np % 32 || d->np < 32 || d->np > 256 || d->cout > d->np || d->cout % 4 || d->cout <= 0 || d->ld_out < d->cout || d->ld_out % 4)
+                return fail("srk_conv3x3_fwd: rows output needs np %% 32 == 0 <= 256, cout %% 4 == 0 <= np, ld_out %% 4 == 0 >= cout");
+            a.out_f32 = static_cast<float*>(out);
+            break;
+        case SRK_CONV_OUT_NHWC_F16:
+            if (d->np % 32 || d->np < 32 || d->np > 256 || d->ld_out < d->np || d->ld_out % 8 || residual)
+                return fail("srk_conv3x3_fwd: fp16 NHWC output needs np %% 32 == 0 <= 256, ld_out %% 8 == 0 >= np, no residual");
+            a.out_f16 = static_cast<__half*>(out);
+            break;
+        case SRK_CONV_OUT_SHUFFLE2_F16:
+            if (d->np != 256 || residual) return fail("srk_conv3x3_fwd: pixel-shuffle output needs np == 256 (4 x 64 channels), no residual");
+            a.out_f16 = static_cast<__half*>(out);
+            break;
+        case SRK_CONV_OUT_IMAGE:
+            if (d->np != 16 || d->cout < 1 || d->cout > 4 || d->ld_out < d->cout) return fail("srk_conv3x3_fwd: image output needs np == 16, cout <= 4");
+            a.out_f32 = static_cast<float*>(out);
+            break;
+        default:
+            return fail("srk_conv3x3_fwd: unknown out_mode %d", d->out_mode);
+    }
+    if (d->act < SRK_ACT_NONE || d->act > SRK_ACT_GELU) return fail("srk_conv3x3_fwd: unknown activation %d", d->act);
+    cudaError_t e = srk::launch_conv3x3(a, static_cast<cudaStream_t>(stream));
+    if (e == cudaErrorNotSupported) return fail("srk_conv3x3_fwd: cuTensorMapEncodeTiled is not available from this driver");
+    return check(e, "srk_conv3x3_fwd");
+}
+
+int srk_rows_to_f16(const float* x, int32_t ld_in, int32_t channels, void* out_f16, int32_t cp, int64_t pixels, void* stream) {
+    if (!x || !out_f16) return fail("srk_rows_to_f16: null argument");
+    if (channels <= 0 || ld_in < channels || (ld_in & 3) || cp < channels || cp % 64 || !aligned16(x) || !aligned16(out_f16))
+        return fail("srk_rows_to_f16: need ld_in %% 4 == 0 >= channels, cp %% 64 == 0 >= channels, 16-byte aligned pointers");
+    return check(srk::launch_rows_to_f16(x, ld_in, channels, static_cast<__half*>(out_f16), cp, pixels, static_cast<cudaStream_t>(stream)), "srk_rows_to_f16");
+}
+
+int srk_image_to_f16_split(const float* x, int64_t sb, int64_t sc, int64_t sy, int64_t sx, int32_t channels, int32_t batch, int32_t height,
+                           int32_t width, const float* mean3, float range, void* out_f16, void* stream) {
+    if (!x || !mean3 || !out_f16) return fail("srk_image_to_f16_split: null argument");
+    if (channels < 1 || channels > 3 || batch <= 0 || height <= 0 || width <= 0 || !aligned16(out_f16)) return fail("srk_image_to_f16_split: bad arguments");
+    return check(srk::launch_image_to_f16_split(x, sb, sc, sy, sx, channels, batch, height, width, mean3, range, static_cast<__half*>(out_f16),
+                                                static_cast<cudaStream_t>(stream)), "srk_image_to_f16_split");
+}
+
 int srk_stitch_normalize(float* E, const float* Wt, int32_t channels, int64_t pixels, void* stream) {
     if (!E || !Wt) return fail("srk_stitch_normalize: null argument");
     return check(srk::launch_stitch_normalize(E, Wt, channels, pixels, static_cast<cudaStream_t>(stream)), "srk_stitch_normalize");

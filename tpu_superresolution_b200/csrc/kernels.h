@@ -1,5 +1,6 @@
 // Internal launch interface between capi.cu and the kernel translation units.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -164,6 +165,22 @@ cudaError_t launch_dat_mix(const float* att, const float* conv, const float* cma
 cudaError_t launch_channel_gram(const float* qkv, float* gram, float* ws, int batch, int tokens_per_image, cudaStream_t stream);
 cudaError_t launch_channel_apply(const float* qkv, const float* attn, float* out, int batch, int tokens_per_image, cudaStream_t stream);
 cudaError_t launch_stitch_normalize(float* E, const float* Wt, int channels, int64_t pixels, cudaStream_t stream);
+
+// conv_kernel.cu
+struct ConvArgs {
+    const ::__half* in;          // fp16 NHWC (B, H, W, 64 * k_atoms)
+    const uint8_t* wstream;      // packing.pack_conv3x3
+    const float* bias;           // np floats
+    const float* residual;       // fp32 rows like out_f32 (may alias it) or nullptr
+    float* out_f32;
+    ::__half* out_f16;
+    int B, H, W, k_atoms, np, cout, out_mode, ld_out, act;
+    float slope;
+};
+cudaError_t launch_conv3x3(const ConvArgs& a, cudaStream_t stream);
+cudaError_t launch_rows_to_f16(const float* x, int ld_in, int C, ::__half* out, int cp, int64_t pixels, cudaStream_t stream);
+cudaError_t launch_image_to_f16_split(const float* x, int64_t sb, int64_t sc, int64_t sy, int64_t sx, int C, int B, int H, int W,
+                                      const float* mean3, float range, ::__half* out, cudaStream_t stream);
 cudaError_t launch_gather_tiles(const float* slab, int64_t slab_cstride, int slab_w, const int32_t* src_yx, int num_tiles, int channels,
                                 int tile_h, int tile_w, float* out, cudaStream_t stream);
 cudaError_t launch_stitch_accumulate2(const float* tiles, int64_t sn, int64_t sc, int64_t sy, int64_t sx, float* E, int64_t e_cstride,

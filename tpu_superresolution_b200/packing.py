@@ -316,3 +316,59 @@ def pack_bias_table_rect(pos: torch.Tensor, hs: int, ws: int, sy: int) -> torch.
     out = torch.zeros(4, 2 * hs - 1, sy)
     out[:nh, :, :2 * ws - 1] = t
     return out.reshape(4, -1).contiguous().to(pos.device)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# 3x3 convolutions (csrc/conv_kernel.cu)
+# ---------------------------------------------------------------------------------------------------------------
+def swizzle_slab_any(mat: torch.Tensor) -> torch.Tensor:
+    """swizzle_slab for any 2-byte dtype (the conv slabs are fp16)."""
+    return swizzle_slab(mat.view(torch.int16)).view(mat.dtype)
+
+
+@torch.no_grad()
+def pack_conv3x3(weight, bias, *, split_first: bool = False, pixel_shuffle: bool = False, out_scale: float = 1.0, out_shift=None):
+    """nn.Conv2d(C_in, C_out, 3, 1, 1) -> (wstream uint8, bias fp32 [np], meta) for srk_conv3x3_fwd.
+
+    wstream = k_atoms x 3 (dx) x 3 (dy) slabs of np rows x 64 input channels, fp16, 128-byte swizzled, in the order the kernel's
+    weight producer streams them.  np = C_out rounded up to 32 (16 when C_out <= 4).
+    split_first (conv_first, C_in <= 3): input channels [hi(w), hi(w), w - hi(w)] against srk_image_to_f16_split's
+        [hi(v), v - hi(v), hi(v)], so the fp16 roundings of the image and of the weights cancel to second order.
+    pixel_shuffle (Upsample: conv + nn.PixelShuffle(2), network_swinir.py:584-585): output row (2i + j) * C_out/4 + c <- original
+        row 4c + 2i + j, so the kernel's SRK_CONV_OUT_SHUFFLE2_F16 epilogue writes whole 64-channel pixels.
+    out_scale / out_shift: y = conv(x) * out_scale + out_shift folded into weights and bias (conv_last: x / img_range + mean).
+    """
+    dev = weight.device
+    w = weight.detach().cpu().double() * out_scale
+    cout, cin = w.shape[:2]
+    b = torch.zeros(cout, dtype=torch.float64) if bias is None else bias.detach().cpu().double() * out_scale
+    if out_shift is not None:
+        b = b + torch.as_tensor(out_shift, dtype=torch.float64).reshape(-1)
+    if tuple(w.shape[2:]) != (3, 3):
+        raise RuntimeError(f"pack_conv3x3: 3x3 kernels only, got {tuple(w.shape)}")
+    w = w.float()
+    if split_first:
+        if 3 * cin > 64:
+            raise RuntimeError("pack_conv3x3(split_first): at most 21 input channels")
+        hi = w.half().float()
+        w = torch.cat([hi, hi, w - hi], dim=1)
+        cin = 3 * cin
+    if pixel_shuffle:
+        if cout % 4 or cout != 256:
+            raise RuntimeError("pack_conv3x3(pixel_shuffle): C_out must be 4 x 64")
+        c4 = cout // 4
+        perm = torch.tensor([4 * c + s for s in range(4) for c in range(c4)])       # new row s * c4 + c <- old row 4c + s
+        w, b = w[perm], b[perm]
+    k_atoms = (cin + 63) // 64
+    np_ = 16 if cout <= 4 else ((cout + 31) // 32) * 32
+    if np_ > 256 or k_atoms > 4:
+        raise RuntimeError(f"pack_conv3x3: unsupported geometry C_in {cin} C_out {cout}")
+    wp = torch.zeros(np_, 64 * k_atoms, 3, 3)
+    wp[:cout, :cin] = w
+    wp = wp.half()
+    slabs = [swizzle_slab_any(wp[:, 64 * ka:64 * ka + 64, dy, dx].contiguous())
+             for ka in range(k_atoms) for dx in range(3) for dy in range(3)]
+    wstream = torch.cat([s.reshape(-1) for s in slabs]).contiguous().view(torch.uint8)
+    bp = torch.zeros(np_, dtype=torch.float32)
+    bp[:cout] = b.float()
+    return wstream.to(dev), bp.to(dev), {"k_atoms": k_atoms, "np": np_, "cout": cout}
