@@ -173,6 +173,11 @@ int srk_window_attention_table_floats(int32_t kind);
  * network_swinir.py:526-527, :800). */
 int srk_layernorm_fwd(const float* x, float* y, const float* w, const float* b, int64_t num_tokens, int32_t ld_in,
                       int32_t ld_out, void* stream);
+/* The same with the result (also) written as fp16 NHWC rows of SRK_DIM_PAD channels, zero padded: the input layout of
+ * srk_conv3x3_fwd (norm1 in front of HAT's CAB, hat_arch.py:276-278; the final norm in front of conv_after_body,
+ * network_swinir.py:800, :829).  y may be NULL (fp16 only). */
+int srk_layernorm_f16_fwd(const float* x, float* y, void* y16, const float* w, const float* b, int64_t num_tokens, int32_t ld_in,
+                          int32_t ld_out, void* stream);
 
 /* HAT CAB tail: out[b, t, c] += scale * y[b, t, c] * sigmoid(W2 relu(W1 mean_t(y[b, :, c]) + b1) + b2)[c] on channels-last
  * (batch, tokens_per_image, 180) fp32 tensors -- ChannelAttention (hat_arch.py:41-59) fused with `+ conv_x * conv_scale`

@@ -59,7 +59,7 @@ with torch.no_grad():
         ref = lambda: F.conv2d(xin, wcl, None, padding=1)
         gf = 2 * 9 * cin * cout * B * H * W / 1e9
         t, tf, tc = timeit(fn), timeit(fn, do_flush=True), timeit(ref)
-        print(f"{name:26s} {gf:7.1f} GF  srk {t:7.1f} us ({gf / t * 1e-3:6.1f} TF/s)  flushed {tf:7.1f} us   cuDNN tf32 {tc:7.1f} us")
+        print(f"{name:26s} {gf:7.1f} GF  srk {t:7.1f} us ({gf / t * 1e3:6.1f} TF/s)  flushed {tf:7.1f} us   cuDNN tf32 {tc:7.1f} us")
     # the fp32 rows -> fp16 NHWC conversion in front of the body convolutions
     x = torch.randn(16 * 4096, 180, device=dev)
     o = torch.empty(16 * 4096, 192, dtype=torch.float16, device=dev)

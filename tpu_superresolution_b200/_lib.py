@@ -127,6 +127,7 @@ def load():
     lib.srk_swin_attn_fwd_sync.argtypes = [POINTER(SwinAttnDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(BlockSync), c_void_p]
     lib.srk_swin_mlp_fwd_sync.argtypes = [POINTER(MlpDesc), c_void_p, c_void_p, c_void_p, c_void_p, POINTER(BlockSync), c_void_p]
     lib.srk_layernorm_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]
+    lib.srk_layernorm_f16_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]
     lib.srk_pixelshuffle_nhwc_fwd.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
     lib.srk_pixelshuffle_nhwc_bias_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
     lib.srk_bias_act_add_nhwc.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, ctypes.c_float, c_void_p]
@@ -164,7 +165,7 @@ def load():
     lib.srk_debug_set_winattn_stagger.restype = None
     lib.srk_debug_set_pdl.argtypes = [c_int32]
     lib.srk_debug_set_pdl.restype = None
-    for f in ("srk_swin_attn_fwd", "srk_swin_mlp_fwd", "srk_swin_attn_fwd_sync", "srk_swin_mlp_fwd_sync", "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd", "srk_pixelshuffle_nhwc_bias_fwd", "srk_bias_act_add_nhwc",
+    for f in ("srk_swin_attn_fwd", "srk_swin_mlp_fwd", "srk_swin_attn_fwd_sync", "srk_swin_mlp_fwd_sync", "srk_layernorm_fwd", "srk_layernorm_f16_fwd", "srk_pixelshuffle_nhwc_fwd", "srk_pixelshuffle_nhwc_bias_fwd", "srk_bias_act_add_nhwc",
               "srk_stitch_accumulate", "srk_stitch_normalize", "srk_gather_tiles", "srk_stitch_accumulate_strided", "srk_stitch_finalize",
               "srk_conv3x3_fwd", "srk_rows_to_f16", "srk_image_to_f16_split", "srk_linear_fwd", "srk_window_attention_fwd",
               "srk_window_attention_table_floats", "srk_cab_gate_add", "srk_dwconv3x3_rows_fwd", "srk_row_stats_fwd", "srk_dat_mix_fwd",
@@ -178,7 +179,7 @@ def load():
 
 EXPORTS = ("srk_abi_version", "srk_last_error_string", "srk_launch_count", "srk_swin_attn_fwd", "srk_swin_mlp_fwd",
            "srk_swin_attn_fwd_sync", "srk_swin_mlp_fwd_sync",
-           "srk_layernorm_fwd", "srk_pixelshuffle_nhwc_fwd", "srk_pixelshuffle_nhwc_bias_fwd", "srk_bias_act_add_nhwc", "srk_stitch_accumulate", "srk_stitch_normalize", "srk_gather_tiles", "srk_stitch_accumulate_strided", "srk_stitch_finalize",
+           "srk_layernorm_fwd", "srk_layernorm_f16_fwd", "srk_pixelshuffle_nhwc_fwd", "srk_pixelshuffle_nhwc_bias_fwd", "srk_bias_act_add_nhwc", "srk_stitch_accumulate", "srk_stitch_normalize", "srk_gather_tiles", "srk_stitch_accumulate_strided", "srk_stitch_finalize",
            "srk_conv3x3_fwd", "srk_rows_to_f16", "srk_image_to_f16_split", "srk_debug_set_timeline", "srk_debug_set_stagger",
            "srk_linear_fwd", "srk_window_attention_fwd", "srk_window_attention_table_floats", "srk_debug_set_winattn_stagger", "srk_debug_set_pdl",
            "srk_cab_gate_add", "srk_dwconv3x3_rows_fwd", "srk_row_stats_fwd", "srk_dat_mix_fwd", "srk_dat_channel_gram_fwd",
@@ -242,6 +243,16 @@ def layernorm(x, y, w, b, *, num_tokens, ld_in, ld_out) -> None:
     _require_cuda_f32(x, y, w, b)
     with _launch("layernorm", x, y, w, b) as st:
         _check(lib.srk_layernorm_fwd(x.data_ptr(), y.data_ptr(), w.data_ptr(), b.data_ptr(), num_tokens, ld_in, ld_out, st), lib)
+
+
+def layernorm_f16(x, y16, w, b, *, num_tokens, ld_in, y=None, ld_out=0) -> None:
+    """srk_layernorm_f16_fwd: LayerNorm(x) as fp16 NHWC rows (num_tokens, 192) in y16 (and, optionally, fp32 rows in y)."""
+    lib = load()
+    _require_cuda_f32(x, w, b, y)
+    if y16.dtype != torch.float16 or not y16.is_contiguous() or y16.numel() != num_tokens * DIM_PAD:
+        raise RuntimeError("layernorm_f16: y16 must be a contiguous fp16 (num_tokens, 192) tensor")
+    with _launch("layernorm", x, y16, w, b, y) as st:
+        _check(lib.srk_layernorm_f16_fwd(x.data_ptr(), _ptr(y), y16.data_ptr(), w.data_ptr(), b.data_ptr(), num_tokens, ld_in, ld_out, st), lib)
 
 
 def pixelshuffle_nhwc(x, y, *, batch, height, width, out_channels, r, bias=None) -> None:

@@ -1,6 +1,7 @@
 // HBM-bound helper kernels: row LayerNorm, channels-last PixelShuffle, tile stitcher.
 // All are pure streaming kernels: 128-bit coalesced loads/stores, grid-stride, no shared memory.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -10,7 +11,9 @@ namespace srk {
 
 // ---- LayerNorm over 180 channels (patch_embed.norm / final norm, network_swinir.py:526-527, :800)
 // half-warp per token, 3 float4 per lane (45 float4 = 180 floats)
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, float* __restrict__ y,
+// x and y may be the same buffer (the final norm runs in place): no __restrict__ / read-only path on them.  y16 (optional): the
+// result as fp16 NHWC rows of SRK_DIM_PAD channels, zero padded -- the input layout of the 3x3 convolution (conv_kernel.cu).
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* x, float* y, __half* __restrict__ y16,
                                                         const float* __restrict__ w, const float* __restrict__ b,
                                                         int64_t num_tokens, int ld_in, int ld_out) {
     const int l16 = threadIdx.x & 15;
@@ -22,8 +25,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 #pragma unroll
         for (int jj = 0; jj < 3; ++jj) {
             const int f = l16 + 16 * jj;
-            v[jj] = (live && f < SRK_DIM / 4) ? __ldg(reinterpret_cast<const float4*>(x + tok * ld_in) + f)
-                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[jj] = (live && f < SRK_DIM / 4) ? reinterpret_cast<const float4*>(x + tok * ld_in)[f] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         float s = 0.f;
 #pragma unroll
@@ -52,19 +54,25 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                     float4 o;
                     o.x = v[jj].x * rstd * g.x + bb.x; o.y = v[jj].y * rstd * g.y + bb.y;
                     o.z = v[jj].z * rstd * g.z + bb.z; o.w = v[jj].w * rstd * g.w + bb.w;
-                    reinterpret_cast<float4*>(y + tok * ld_out)[f] = o;
+                    if (y) reinterpret_cast<float4*>(y + tok * ld_out)[f] = o;
+                    if (y16) {
+                        const __half2 lo = __floats2half2_rn(o.x, o.y), hi = __floats2half2_rn(o.z, o.w);
+                        reinterpret_cast<uint2*>(y16 + tok * SRK_DIM_PAD)[f] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+                    }
+                } else if (y16) {
+                    reinterpret_cast<uint2*>(y16 + tok * SRK_DIM_PAD)[f] = make_uint2(0u, 0u);      // channels 180..191
                 }
             }
         }
     }
 }
 
-cudaError_t launch_layernorm(const float* x, float* y, const float* w, const float* b, int64_t num_tokens, int ld_in,
+cudaError_t launch_layernorm(const float* x, float* y, __half* y16, const float* w, const float* b, int64_t num_tokens, int ld_in,
                              int ld_out, cudaStream_t stream) {
     if (num_tokens <= 0) return cudaSuccess;
     const int64_t blocks = (num_tokens * 16 + 255) / 256;
     const int grid = static_cast<int>(blocks < 148 * 16 ? blocks : 148 * 16);
-    layernorm_kernel<<<grid, 256, 0, stream>>>(x, y, w, b, num_tokens, ld_in, ld_out);
+    layernorm_kernel<<<grid, 256, 0, stream>>>(x, y, y16, w, b, num_tokens, ld_in, ld_out);
     return cudaGetLastError();
 }
 

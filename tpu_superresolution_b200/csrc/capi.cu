@@ -234,7 +234,17 @@ int srk_layernorm_fwd(const float* x, float* y, const float* w, const float* b, 
     if (ld_in < SRK_DIM || ld_out < SRK_DIM || (ld_in & 3) || (ld_out & 3)) return fail("srk_layernorm_fwd: bad ld");
     if (!aligned16(x) || !aligned16(y) || !aligned16(w) || !aligned16(b)) return fail("srk_layernorm_fwd: pointers must be 16-byte aligned");
     if (num_tokens < 0) return fail("srk_layernorm_fwd: bad num_tokens");
-    return check(srk::launch_layernorm(x, y, w, b, num_tokens, ld_in, ld_out, static_cast<cudaStream_t>(stream)), "srk_layernorm_fwd");
+    return check(srk::launch_layernorm(x, y, nullptr, w, b, num_tokens, ld_in, ld_out, static_cast<cudaStream_t>(stream)), "srk_layernorm_fwd");
+}
+
+int srk_layernorm_f16_fwd(const float* x, float* y, void* y16, const float* w, const float* b, int64_t num_tokens, int32_t ld_in,
+                          int32_t ld_out, void* stream) {
+    if (!x || !y16 || !w || !b) return fail("srk_layernorm_f16_fwd: null argument");
+    if (ld_in < SRK_DIM || (ld_in & 3) || (y && (ld_out < SRK_DIM || (ld_out & 3)))) return fail("srk_layernorm_f16_fwd: bad ld");
+    if (!aligned16(x) || !aligned16(y16) || !aligned16(w) || !aligned16(b) || (y && !aligned16(y))) return fail("srk_layernorm_f16_fwd: pointers must be 16-byte aligned");
+    if (num_tokens < 0) return fail("srk_layernorm_f16_fwd: bad num_tokens");
+    return check(srk::launch_layernorm(x, y, static_cast<__half*>(y16), w, b, num_tokens, ld_in, ld_out, static_cast<cudaStream_t>(stream)),
+                 "srk_layernorm_f16_fwd");
 }
 
 int srk_cab_gate_add(const float* y, const float* y_bias, float* out, float* sums_ws, const float* w1, const float* b1, const float* w2, const float* b2,

@@ -62,7 +62,9 @@ struct ConvParams {
     float slope;
     uint32_t idesc, box_bytes, slab_bytes;
     int n_wstages;
+    unsigned long long* dbg;        // optional timeline buffer (srk_debug_set_timeline): CTA 0's clock64() stamps of its first patches
 };
+#define CV_TL(it, id) do { if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && (it) < 8) p.dbg[(it) * 64 + (id)] = clock64(); } while (0)
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
@@ -156,17 +158,25 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_kernel(const __grid_c
     } else if (warp == 2) {
         // ===================================================== MMA issuer (whole warp, uniform operands: umma.cuh)
         uint32_t as = 0, aph = 0, ws = 0, wph = 0, acc_ph = 0;
-        for (int patch = blockIdx.x; patch < p.n_patches; patch += gridDim.x) {
+        int it = 0;
+        for (int patch = blockIdx.x; patch < p.n_patches; patch += gridDim.x, ++it) {
+            CV_TL(it, 0);
             mbar_wait(&bars[CB_ACCEMPTY], acc_ph ^ 1);            // the epilogue has drained the previous patch's accumulators
             tc_fence_after();
+            CV_TL(it, 1);
+            long long wwait = 0;
             for (int s = 0; s < n_steps; ++s) {
+                if (s < 12) CV_TL(it, 2 + 2 * s);
                 mbar_wait(&bars[CB_AFULL + as], aph);
                 tc_fence_after();
+                if (s < 12) CV_TL(it, 3 + 2 * s);
                 const uint32_t box = sbase + CV_A + as * CV_ABOX;
 #pragma unroll 1
                 for (int dy = 0; dy < 3; ++dy) {
+                    const long long w0 = p.dbg ? clock64() : 0;
                     mbar_wait(&bars[CB_WFULL + ws], wph);
                     tc_fence_after();
+                    if (p.dbg) wwait += clock64() - w0;
                     const uint64_t bd = umma_desc_sw128(sbase + CV_W + ws * p.slab_bytes);
                     const uint32_t a0 = box + static_cast<uint32_t>(dy * TW) * 128u;
                     const uint32_t accum = (s | dy) != 0;
@@ -181,6 +191,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_kernel(const __grid_c
             }
             umma_commit_w(&bars[CB_ACCFULL]);
             acc_ph ^= 1;
+            CV_TL(it, 30);
+            if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && it < 8) p.dbg[it * 64 + 31] = static_cast<unsigned long long>(wwait);
         }
         __syncwarp();
     } else if (warp >= 4) {
@@ -190,8 +202,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_kernel(const __grid_c
         uint8_t* stg = sm + CV_STAGE + (warp - 4) * 4096;
         const uint32_t stg_u = sbase + CV_STAGE + (warp - 4) * 4096;
         uint32_t ph = 0;
+        int it = 0;
         pdl_wait();                                   // residual / output buffers may still be in use by the previous kernel
-        for (int patch = blockIdx.x; patch < p.n_patches; patch += gridDim.x) {
+        for (int patch = blockIdx.x; patch < p.n_patches; patch += gridDim.x, ++it) {
             int b, y0, x0;
             patch_geom(patch, b, y0, x0);
             const int R = 128 * mt + 32 * q + lane;
@@ -201,6 +214,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_kernel(const __grid_c
             const int pix2 = valid ? (b * 2 * p.H + 2 * y) * 2 * p.W + 2 * x : -1;          // (2y, 2x) of the pixel-shuffled image
             mbar_wait(&bars[CB_ACCFULL], ph); ph ^= 1;
             tc_fence_after();
+            if (warp == 4) CV_TL(it, 40);
             if (p.out_mode == SRK_CONV_OUT_IMAGE) {
                 // ---- C_out <= 4 (conv_last): the row's lane stores its pixel directly (consecutive lanes = consecutive pixels)
                 uint32_t v[16];
@@ -225,8 +239,24 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_kernel(const __grid_c
                     tmem_ld32(acc + 32 * c, v);
                     tmem_ld_wait();
                     float f[32];
+                    {   // bias as eight 16-byte broadcasts; the activation switch sits OUTSIDE the element loops (a per-element
+                        // runtime switch serialised 32 dependent LDS + branches per chunk: 3.8 K cycles per chunk, measured)
+                        const float4* b4 = reinterpret_cast<const float4*>(s_bias + 32 * c);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) f[i] = conv_act(__uint_as_float(v[i]) + s_bias[32 * c + i], p.act, p.slope);
+                        for (int k = 0; k < 8; ++k) {
+                            const float4 bb = b4[k];
+                            f[4 * k] = __uint_as_float(v[4 * k]) + bb.x;         f[4 * k + 1] = __uint_as_float(v[4 * k + 1]) + bb.y;
+                            f[4 * k + 2] = __uint_as_float(v[4 * k + 2]) + bb.z; f[4 * k + 3] = __uint_as_float(v[4 * k + 3]) + bb.w;
+                        }
+                        if (p.act == SRK_ACT_LEAKY_RELU) {
+                            const float sl = p.slope;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) f[i] = f[i] > 0.f ? f[i] : f[i] * sl;
+                        } else if (p.act == SRK_ACT_GELU) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) f[i] = 0.5f * f[i] * (1.0f + erff(f[i] * 0.70710678118654752f));      // nn.GELU() (exact), hat_arch.py:68
+                        }
+                    }
                     if (p.out_mode == SRK_CONV_OUT_ROWS_F32) {
                         // transpose: lane = row -> 8 lanes per row, 128 B (32 floats) contiguous per row
 #pragma unroll
@@ -277,6 +307,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_kernel(const __grid_c
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[CB_ACCEMPTY]);
+            if (warp == 4) CV_TL(it, 41);
         }
     }
     tc_fence_before();
@@ -381,6 +412,7 @@ cudaError_t launch_conv3x3(const ConvArgs& a, cudaStream_t stream) {
     p.idesc = (1u << 4) | (static_cast<uint32_t>(a.np >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);      // kind::f16, A = B = fp16, D = fp32, K-major
     p.box_bytes = static_cast<uint32_t>((p.th + 2) * TW * 128);
     p.slab_bytes = static_cast<uint32_t>(a.np * 128);
+    p.dbg = g_timeline;
     p.n_wstages = static_cast<int>(CV_WBYTES / p.slab_bytes) < 4 ? static_cast<int>(CV_WBYTES / p.slab_bytes) : 4;
     static bool configured[SRK_MAX_DEVICES] = {};
     if (cudaError_t e = configure_smem_once(configured, conv3x3_kernel, CONV_SMEM); e != cudaSuccess) return e;

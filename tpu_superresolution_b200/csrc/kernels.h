@@ -143,7 +143,7 @@ cudaError_t launch_swin_mlp(const MlpParams& p, cudaStream_t stream);
 cudaError_t launch_token_linear(const LinearParams& p, cudaStream_t stream);
 cudaError_t launch_winattn(int kind, const WinAttnParams& p, cudaStream_t stream);
 int winattn_table_floats(int kind);
-cudaError_t launch_layernorm(const float* x, float* y, const float* w, const float* b, int64_t num_tokens, int ld_in,
+cudaError_t launch_layernorm(const float* x, float* y, ::__half* y16, const float* w, const float* b, int64_t num_tokens, int ld_in,
                              int ld_out, cudaStream_t stream);
 cudaError_t launch_pixelshuffle_nhwc(const float* x, const float* bias, float* y, int batch, int height, int width, int out_channels,
                                      int r, cudaStream_t stream);
