@@ -114,3 +114,49 @@ class PixelShuffleTail:
         y = torch.empty(B, H, W, self.out_ch, dtype=torch.float32, device=dev)
         self.last(t, B, H, W, out=y, mode=L.CONV_OUT_IMAGE, ld_out=self.out_ch)
         return y.permute(0, 3, 1, 2)
+
+
+def group_conv_residual(module: nn.Module, conv: nn.Conv2d, t: torch.Tensor, x: torch.Tensor, x_size) -> torch.Tensor:
+    """The tail of RSTB / RHAG / ResidualGroup (network_swinir.py:482, hat_arch.py:620, dat_arch.py:649-651):
+    ``x + conv(t)`` with t, x fp32 token rows (B, H*W, C); the result is written over t."""
+    B, Ltok, C = t.shape
+    t = t.contiguous()
+    if not hasattr(module, "_fconv"):
+        object.__setattr__(module, "_fconv", FusedConv3x3(conv))
+    return module._fconv(rows_to_f16(t, C), B, x_size[0], x_size[1], out=t, mode=L.CONV_OUT_ROWS_F32, ld_out=C, residual=x.contiguous())
+
+
+def fused_ok(model: nn.Module) -> bool:
+    """Whole-model fused-conv forward: the pixelshuffle tail with 2^n scale, '1conv' residual connections, <= 3 input channels."""
+    return (USE_FUSED_CONV and getattr(model, "upsampler", None) == 'pixelshuffle' and isinstance(model.conv_after_body, nn.Conv2d)
+            and model.upscale in (2, 4, 8) and model.embed_dim == L.DIM and model.conv_first.in_channels <= 3)
+
+
+def fused_forward(model: nn.Module, x: torch.Tensor, first_norm: Optional[nn.LayerNorm], run_layers) -> torch.Tensor:
+    """SwinIR.forward / HAT.forward / DAT.forward (network_swinir.py:800-840, hat_arch.py:971-994, dat_arch.py:839-858) with every
+    3x3 convolution on the implicit-GEMM kernel.  x: (B, C_in, H, W) fp32, already padded to the model's window multiple.
+    run_layers(tokens (B, H*W, C), (H, W)) -> tokens runs the residual groups.  Returns the (B, C_out, H*s, W*s) image."""
+    B, Cin, H, W = x.shape
+    C = model.embed_dim
+    dev = x.device
+    if not hasattr(model, "_f_first"):
+        object.__setattr__(model, "_f_first", FusedConv3x3(model.conv_first, split_first=True))
+        object.__setattr__(model, "_f_after", FusedConv3x3(model.conv_after_body))
+        object.__setattr__(model, "_f_tail", PixelShuffleTail(model.conv_before_upsample, model.upsample, model.conv_last,
+                                                               model.img_range, model.mean))
+        object.__setattr__(model, "_mean_vals", [float(v) for v in model.mean.detach().cpu().reshape(-1)])
+    x16 = torch.empty(B * H * W, 64, dtype=torch.float16, device=dev)
+    L.image_to_f16_split(x, x16, model._mean_vals, model.img_range)                    # (x - mean) * img_range
+    feat0 = torch.empty(B, H * W, C, dtype=torch.float32, device=dev)
+    model._f_first(x16, B, H, W, out=feat0, mode=L.CONV_OUT_ROWS_F32, ld_out=C)
+    t = feat0
+    if first_norm is not None:
+        t = torch.empty_like(feat0)
+        L.layernorm(feat0, t, first_norm.weight, first_norm.bias, num_tokens=B * H * W, ld_in=C, ld_out=C)
+    t = run_layers(t, (H, W))
+    t16 = torch.empty(B * H * W, L.DIM_PAD, dtype=torch.float16, device=dev)
+    L.layernorm_f16(t.contiguous(), t16, model.norm.weight, model.norm.bias, num_tokens=B * H * W, ld_in=C)   # final norm, straight to the conv's layout
+    if t.data_ptr() == feat0.data_ptr():
+        t = torch.empty_like(feat0)
+    model._f_after(t16, B, H, W, out=t, mode=L.CONV_OUT_ROWS_F32, ld_out=C, residual=feat0)      # conv_after_body(...) + x
+    return model._f_tail(rows_to_f16(t, C), B, H, W)

@@ -263,20 +263,25 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_kernel(const __grid_c
                         for (int k = 0; k < 8; ++k)
                             *reinterpret_cast<float4*>(stg + lane * 128 + ((k ^ (lane & 7)) << 4)) = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
                         __syncwarp();
+                        // all residual loads of the chunk first, then the stores: `residual` may alias `out` (in-place += ), and a
+                        // load behind each store would serialise eight global round trips per chunk.  Every lane reads exactly the
+                        // addresses it writes, so the order between lanes does not matter.
+                        const int k = lane & 7, col = 32 * c + 4 * k;
+                        int64_t addr[8];
+                        float4 res[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const int rr = 4 * i + (lane >> 3), k = lane & 7;
+                            const int pr = __shfl_sync(0xffffffffu, pix, 4 * i + (lane >> 3));
+                            addr[i] = (pr >= 0 && col < p.cout) ? static_cast<int64_t>(pr) * p.ld_out + col : static_cast<int64_t>(-1);
+                            res[i] = (p.residual != nullptr && addr[i] >= 0) ? *reinterpret_cast<const float4*>(p.residual + addr[i])
+                                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int rr = 4 * i + (lane >> 3);
                             float4 o = *reinterpret_cast<const float4*>(stg + rr * 128 + ((k ^ (rr & 7)) << 4));
-                            const int pr = __shfl_sync(0xffffffffu, pix, rr);
-                            const int col = 32 * c + 4 * k;
-                            if (pr >= 0 && col < p.cout) {
-                                const int64_t a = static_cast<int64_t>(pr) * p.ld_out + col;
-                                if (p.residual) {
-                                    const float4 r = *reinterpret_cast<const float4*>(p.residual + a);
-                                    o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-                                }
-                                *reinterpret_cast<float4*>(p.out_f32 + a) = o;
-                            }
+                            o.x += res[i].x; o.y += res[i].y; o.z += res[i].z; o.w += res[i].w;
+                            if (addr[i] >= 0) *reinterpret_cast<float4*>(p.out_f32 + addr[i]) = o;
                         }
                         __syncwarp();
                     } else {

@@ -28,6 +28,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib as L
+from . import convs
 from . import packing
 from .swinir import Upsample, UpsampleOneStep, _PackedCache, _conv_tail, _inference_only
 
@@ -460,6 +461,8 @@ class ResidualGroup(nn.Module):
         for blk in self.blocks:          # first block out of place (x is the group's residual), the rest in place
             blk.forward_into(src, x_size, out)
             src = out
+        if isinstance(self.conv, nn.Conv2d) and convs.USE_FUSED_CONV and C == L.DIM:
+            return convs.group_conv_residual(self, self.conv, out, x, x_size)   # '1conv' on the tcgen05 implicit-GEMM kernel (:649-651)
         img = out.view(B, H, W, C).permute(0, 3, 1, 2)
         if isinstance(self.conv, nn.Conv2d):      # '1conv': bias + the group's residual in one pass behind the bias-free conv
             return _conv_tail(self.conv, img, residual=x).permute(0, 2, 3, 1).reshape(B, Ltok, C)
@@ -542,6 +545,13 @@ class DAT(nn.Module):
         if self.training:
             raise RuntimeError("DAT: eval mode required")
         _inference_only(self.conv_first)
+        if convs.fused_ok(self) and x.dtype == torch.float32:
+            def run_layers(t, x_size):
+                for layer in self.layers:
+                    t = layer(t, list(x_size))
+                return t
+
+            return convs.fused_forward(self, x, self.before_RG[1], run_layers)
         self._prepare(x.device)
         self.mean = self.mean.type_as(x)
         x = ((x - self.mean) * self.img_range).contiguous(memory_format=torch.channels_last)

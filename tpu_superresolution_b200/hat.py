@@ -26,6 +26,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib as L
+from . import convs
 from . import packing
 from .swinir import (Mlp, PatchEmbed, PatchUnEmbed, Upsample, _PackedCache, _conv_tail, _inference_only, _to_2tuple,
                      calculate_mask as _calculate_mask)
@@ -221,9 +222,25 @@ class HAB(nn.Module):
         self.attn._check_rpi(rpi_sa)
         tokens = B * Ltok
         # conv branch on the un-shifted LN1 output (:276-278)
-        xn = torch.empty_like(x)
-        L.layernorm(x, xn, self.norm1.weight, self.norm1.bias, num_tokens=tokens, ld_in=C, ld_out=C)
-        y, y_bias = self.conv_block.body_nobias(xn.view(B, H, W, C).permute(0, 3, 1, 2))     # channels-last views
+        fused_cab = convs.USE_FUSED_CONV and C == L.DIM and getattr(self.conv_block.cab[1], "approximate", "none") == "none"
+        if fused_cab:
+            # LN1 straight into the conv's fp16 NHWC layout; conv (180 -> 60) + GELU -> fp16; conv (60 -> 180) + bias -> fp32 rows
+            cb = self.conv_block
+            if not hasattr(cb, "_f1"):
+                object.__setattr__(cb, "_f1", convs.FusedConv3x3(cb.cab[0]))
+                object.__setattr__(cb, "_f2", convs.FusedConv3x3(cb.cab[2]))
+            xn16 = torch.empty(tokens, L.DIM_PAD, dtype=torch.float16, device=x.device)
+            L.layernorm_f16(x, xn16, self.norm1.weight, self.norm1.bias, num_tokens=tokens, ld_in=C)
+            mid_cp = cb._f2.cin_pad
+            mid = torch.empty(tokens, mid_cp, dtype=torch.float16, device=x.device)
+            cb._f1(xn16, B, H, W, out=mid, mode=L.CONV_OUT_NHWC_F16, ld_out=mid_cp, act=L.ACT_GELU)
+            y_tok = torch.empty(B, Ltok, C, dtype=torch.float32, device=x.device)
+            cb._f2(mid, B, H, W, out=y_tok, mode=L.CONV_OUT_ROWS_F32, ld_out=C)
+            y_bias = None
+        else:
+            xn = torch.empty_like(x)
+            L.layernorm(x, xn, self.norm1.weight, self.norm1.bias, num_tokens=tokens, ld_in=C, ld_out=C)
+            y, y_bias = self.conv_block.body_nobias(xn.view(B, H, W, C).permute(0, 3, 1, 2))     # channels-last views
         # attention branch (reads x before `out` is touched)
         src = x
         mw, mv = self.mlp._packed(self.norm2)
@@ -238,7 +255,8 @@ class HAB(nn.Module):
             out.copy_(x)
         L.linear(o, pw, pb, out, num_tokens=tokens, a_mode=L.LIN_A_PLANES, n_chunks=1, out_mode=L.LIN_OUT_ROWS, ld_out=C,
                  add_residual=True)                                                           # out = shortcut + attn
-        y_tok = y.permute(0, 2, 3, 1).reshape(B, Ltok, C).contiguous()                        # a view when y is channels-last
+        if not fused_cab:
+            y_tok = y.permute(0, 2, 3, 1).reshape(B, Ltok, C).contiguous()                    # a view when y is channels-last
         ca = self.conv_block.cab[3].attention                                                 # squeeze-excite gate + `+ conv_x * conv_scale` (:307)
         L.cab_gate_add(y_tok, out, ca[1].weight.reshape(ca[1].weight.shape[0], C), ca[1].bias, ca[3].weight.reshape(C, -1), ca[3].bias,
                        scale=self.conv_scale, batch=B, tokens_per_image=Ltok, y_bias=y_bias)
@@ -380,7 +398,10 @@ class RHAG(nn.Module):
         self.patch_unembed = PatchUnEmbed(img_size=img_size, patch_size=patch_size, in_chans=0, embed_dim=dim, norm_layer=None)
 
     def forward(self, x, x_size, params):
-        y = self.patch_unembed(self.residual_group(x, x_size, params), x_size)
+        t = self.residual_group(x, x_size, params)
+        if isinstance(self.conv, nn.Conv2d) and convs.USE_FUSED_CONV and t.shape[-1] == L.DIM:
+            return convs.group_conv_residual(self, self.conv, t, x, x_size)     # '1conv' on the tcgen05 implicit-GEMM kernel (:620)
+        y = self.patch_unembed(t, x_size)
         if isinstance(self.conv, nn.Conv2d):
             return self.patch_embed(_conv_tail(self.conv, y, residual=x))
         return self.patch_embed(self.conv(y)) + x
@@ -487,6 +508,17 @@ class HAT(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("HAT: CUDA input required (no CPU fallback)")
         _inference_only(self.conv_first)
+        if convs.fused_ok(self) and not self.ape and x.dtype == torch.float32:
+            H0, W0 = x.shape[2:]
+            params = {'attn_mask': None, 'rpi_sa': self.relative_position_index_SA, 'rpi_oca': self.relative_position_index_OCA}
+
+            def run_layers(t, x_size):
+                for layer in self.layers:
+                    t = layer(t, x_size, params)
+                return t
+
+            y = convs.fused_forward(self, self.check_image_size(x), self.patch_embed.norm, run_layers)
+            return y[:, :, :H0 * self.upscale, :W0 * self.upscale]
         self._prepare(x.device)
         H, W = x.shape[2:]
         x = self.check_image_size(x)

@@ -331,14 +331,8 @@ class RSTB(nn.Module):
 
     def forward(self, x, x_size):
         t = self.residual_group(x, x_size)
-        if isinstance(self.conv, nn.Conv2d) and convs.USE_FUSED_CONV and t.is_cuda and t.dtype == torch.float32:
-            # '1conv' on the tcgen05 implicit-GEMM kernel: out = x + conv(t) + bias in one pass, written over t (:482)
-            B, Ltok, C = t.shape
-            t = t.contiguous()
-            if not hasattr(self, "_fconv"):
-                object.__setattr__(self, "_fconv", convs.FusedConv3x3(self.conv))
-            t16 = convs.rows_to_f16(t, C)
-            return self._fconv(t16, B, x_size[0], x_size[1], out=t, mode=L.CONV_OUT_ROWS_F32, ld_out=C, residual=x.contiguous())
+        if isinstance(self.conv, nn.Conv2d) and convs.USE_FUSED_CONV and t.is_cuda and t.dtype == torch.float32 and t.shape[-1] == L.DIM:
+            return convs.group_conv_residual(self, self.conv, t, x, x_size)     # '1conv' on the tcgen05 implicit-GEMM kernel (:482)
         y = self.patch_unembed(t, x_size)
         if isinstance(self.conv, nn.Conv2d):        # '1conv': bias + residual fused behind the (library) conv
             return self.patch_embed(_conv_tail(self.conv, y, residual=x))
@@ -503,46 +497,24 @@ class SwinIR(nn.Module):
         and ``.to()`` are detected without it.  A ``GraphedModel`` around this model must be ``reset()`` as well."""
         convs.invalidate_all()
 
-    def _fused_convs_ok(self) -> bool:
-        return (convs.USE_FUSED_CONV and self.upsampler == 'pixelshuffle' and isinstance(self.conv_after_body, nn.Conv2d)
-                and self.upscale in (2, 4, 8) and self.embed_dim == L.DIM and self.conv_first.in_channels <= 3 and not self.ape)
-
     def _forward_fused(self, x):
-        """The whole forward with every 3x3 convolution on the tcgen05 implicit-GEMM kernel (convs.py)."""
+        """The whole forward with every 3x3 convolution on the tcgen05 implicit-GEMM kernel (convs.fused_forward)."""
         H0, W0 = x.shape[2:]
         x = self.check_image_size(x)
-        B, Cin, H, W = x.shape
-        C = self.embed_dim
-        dev = x.device
-        if not hasattr(self, "_f_first"):
-            object.__setattr__(self, "_f_first", convs.FusedConv3x3(self.conv_first, split_first=True))
-            object.__setattr__(self, "_f_after", convs.FusedConv3x3(self.conv_after_body))
-            object.__setattr__(self, "_f_tail", convs.PixelShuffleTail(self.conv_before_upsample, self.upsample, self.conv_last,
-                                                                      self.img_range, self.mean))
-            object.__setattr__(self, "_mean_vals", [float(v) for v in self.mean.detach().cpu().reshape(-1)])
-        x16 = torch.empty(B * H * W, 64, dtype=torch.float16, device=dev)
-        L.image_to_f16_split(x, x16, self._mean_vals, self.img_range)      # (x - mean) * img_range (:803-804)
-        feat0 = torch.empty(B, H * W, C, dtype=torch.float32, device=dev)
-        self._f_first(x16, B, H, W, out=feat0, mode=L.CONV_OUT_ROWS_F32, ld_out=C)
-        t = feat0
-        if self.patch_embed.norm is not None:
-            t = torch.empty_like(feat0)
-            L.layernorm(feat0, t, self.patch_embed.norm.weight, self.patch_embed.norm.bias, num_tokens=B * H * W, ld_in=C, ld_out=C)
-        for layer in self.layers:
-            t = layer(t, (H, W))
-        t16 = torch.empty(B * H * W, L.DIM_PAD, dtype=torch.float16, device=dev)
-        L.layernorm_f16(t, t16, self.norm.weight, self.norm.bias, num_tokens=B * H * W, ld_in=C)      # :800, straight to the conv's layout
-        if t.data_ptr() == feat0.data_ptr():
-            t = torch.empty_like(feat0)
-        self._f_after(t16, B, H, W, out=t, mode=L.CONV_OUT_ROWS_F32, ld_out=C, residual=feat0)       # conv_after_body(...) + x (:829)
-        y = self._f_tail(convs.rows_to_f16(t, C), B, H, W)
+
+        def run_layers(t, x_size):
+            for layer in self.layers:
+                t = layer(t, x_size)
+            return t
+
+        y = convs.fused_forward(self, x, self.patch_embed.norm, run_layers)
         return y[:, :, :H0 * self.upscale, :W0 * self.upscale]
 
     def forward(self, x):
         if not x.is_cuda:
             raise RuntimeError("SwinIR: CUDA input required (no CPU fallback)")
         _inference_only(self.conv_first)
-        if self._fused_convs_ok() and x.dtype == torch.float32:
+        if convs.fused_ok(self) and not self.ape and x.dtype == torch.float32:
             return self._forward_fused(x)
         self._prepare(x.device)
         H, W = x.shape[2:]
