@@ -108,6 +108,26 @@ int srk_swin_attn_fwd_sync(const SrkSwinAttnDesc* desc, const float* x, float* y
 int srk_swin_mlp_fwd_sync(const SrkMlpDesc* desc, const float* x, float* y, const void* wstream, const float* vec,
                           const SrkBlockSync* sync /* or NULL */, void* stream);
 
+/* All blocks of one BasicLayer (network_swinir.py:349-416: `depth` SwinTransformerBlocks alternating shift 0 / 4) in ONE persistent
+ * launch: y = blocks(y) in place.  The attention and MLP halves of every block are work items walked in global order by one CTA
+ * per SM and ordered per image through `progress` (2 * batch int32 counters, zeroed by this call), see swin_layer_kernel.
+ * Needs height * width %% 128 == 0 (and multiples of 8); n_blocks <= SRK_LAYER_MAX_BLOCKS; masks in closed form only. */
+#define SRK_LAYER_MAX_BLOCKS 8
+typedef struct SrkLayerBlock {
+    const void* attn_wstream;   /* SRK_ATTN_WSTREAM_BYTES (LayerNorm 1 folded in) */
+    const float* attn_vec;      /* SRK_ATTN_VEC_FLOATS */
+    const void* mlp_wstream;    /* SRK_MLP_WSTREAM_BYTES (LayerNorm 2 folded in) */
+    const float* mlp_vec;       /* SRK_MLP_VEC_FLOATS */
+    int32_t shift;              /* 0 or 4 */
+    int32_t reserved;
+} SrkLayerBlock;
+typedef struct SrkLayerDesc {
+    int32_t batch, height, width;
+    int32_t ld;                 /* floats per token row of y */
+    int32_t n_blocks;
+} SrkLayerDesc;
+int srk_swin_layer_fwd(const SrkLayerDesc* desc, float* y, const SrkLayerBlock* blocks /* host array */, int32_t* progress, void* stream);
+
 /* Token-wise linear layer on tcgen05 for the HAT / DAT paths:  out[tok, :] = act(A[tok, :] W^T + b), N in chunks of 192
  * columns.  Replaces the nn.Linear call sites hat_arch.py:179, :195, :401, :436 and dat_arch.py:371, :435, :483, :526, :79-88.
  *   A  SRK_LIN_A_ROWS  : fp32 token rows [tok][ld_in] (180 valid), optional LayerNorm (affine folded into W, b at pack time)

@@ -285,6 +285,32 @@ def test_block_sync_progress_counters_bit_identical():
         swinir.USE_BLOCK_SYNC = old
 
 
+@pytest.mark.parametrize("B,h,w", [(16, 64, 64), (1, 64, 64), (3, 16, 32), (1, 16, 8), (2, 8, 16), (5, 48, 32)])
+def test_layer_kernel_bit_identical_to_per_block_kernels(B, h, w):
+    """srk_swin_layer_fwd (one persistent launch per BasicLayer: attention and MLP halves of all blocks as work items ordered by the
+    image progress counters) must reproduce the one-launch-per-half-block path bit for bit, run after run -- including the
+    degenerate grids where every CTA changes phase at every item (one tile per phase) and the last, ragged round of items."""
+    from tpu_superresolution_b200 import swinir
+    cfg = synth.CONFIGS["swinir_x4_d2"]
+    m = srk.SwinIR(**cfg.as_kwargs()).eval()
+    m.load_state_dict(synth.make_swinir_state_dict(cfg, seed=77, kind="stress"), strict=True)
+    m.cuda()
+    layer = m.layers[1].residual_group
+    x = synth.make_tokens(B, h, w, 180, seed=B + h).cuda()
+    old = swinir.USE_LAYER_KERNEL
+    try:
+        swinir.USE_LAYER_KERNEL = False
+        ref = layer(x, (h, w)).clone()
+        swinir.USE_LAYER_KERNEL = True
+        before = L.launch_count()
+        for _ in range(5):
+            y = layer(x, (h, w))
+            assert torch.equal(y, ref)
+        assert L.launch_count() - before == 5           # one launch per call
+    finally:
+        swinir.USE_LAYER_KERNEL = old
+
+
 def test_pipelined_runner_matches_direct_forward():
     """srk.PipelinedRunner (host-to-host loop with the D2H copy on a side stream) returns exactly the model's outputs, in order."""
     cfg = synth.CONFIGS["swinir_x2_d2"]

@@ -32,6 +32,18 @@ class BlockSync(Structure):
     _fields_ = [("progress", c_void_p), ("batch", c_int32), ("tokens_per_image", c_int32), ("wait_target", c_int32)]
 
 
+class LayerBlock(Structure):
+    _fields_ = [("attn_wstream", c_void_p), ("attn_vec", c_void_p), ("mlp_wstream", c_void_p), ("mlp_vec", c_void_p),
+                ("shift", c_int32), ("reserved", c_int32)]
+
+
+class LayerDesc(Structure):
+    _fields_ = [(n, c_int32) for n in ("batch", "height", "width", "ld", "n_blocks")]
+
+
+LAYER_MAX_BLOCKS = 8
+
+
 class MlpDesc(Structure):
     _fields_ = [("num_tokens", c_int64), ("ld_in", c_int32), ("ld_out", c_int32), ("apply_ln", c_int32),
                 ("add_residual", c_int32)]
@@ -126,6 +138,7 @@ def load():
     lib.srk_swin_mlp_fwd.argtypes = [POINTER(MlpDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.srk_swin_attn_fwd_sync.argtypes = [POINTER(SwinAttnDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(BlockSync), c_void_p]
     lib.srk_swin_mlp_fwd_sync.argtypes = [POINTER(MlpDesc), c_void_p, c_void_p, c_void_p, c_void_p, POINTER(BlockSync), c_void_p]
+    lib.srk_swin_layer_fwd.argtypes = [POINTER(LayerDesc), c_void_p, POINTER(LayerBlock), c_void_p, c_void_p]
     lib.srk_layernorm_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]
     lib.srk_layernorm_f16_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]
     lib.srk_pixelshuffle_nhwc_fwd.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
@@ -165,7 +178,7 @@ def load():
     lib.srk_debug_set_winattn_stagger.restype = None
     lib.srk_debug_set_pdl.argtypes = [c_int32]
     lib.srk_debug_set_pdl.restype = None
-    for f in ("srk_swin_attn_fwd", "srk_swin_mlp_fwd", "srk_swin_attn_fwd_sync", "srk_swin_mlp_fwd_sync", "srk_layernorm_fwd", "srk_layernorm_f16_fwd", "srk_pixelshuffle_nhwc_fwd", "srk_pixelshuffle_nhwc_bias_fwd", "srk_bias_act_add_nhwc",
+    for f in ("srk_swin_attn_fwd", "srk_swin_mlp_fwd", "srk_swin_attn_fwd_sync", "srk_swin_mlp_fwd_sync", "srk_swin_layer_fwd", "srk_layernorm_fwd", "srk_layernorm_f16_fwd", "srk_pixelshuffle_nhwc_fwd", "srk_pixelshuffle_nhwc_bias_fwd", "srk_bias_act_add_nhwc",
               "srk_stitch_accumulate", "srk_stitch_normalize", "srk_gather_tiles", "srk_stitch_accumulate_strided", "srk_stitch_finalize",
               "srk_conv3x3_fwd", "srk_rows_to_f16", "srk_image_to_f16_split", "srk_linear_fwd", "srk_window_attention_fwd",
               "srk_window_attention_table_floats", "srk_cab_gate_add", "srk_dwconv3x3_rows_fwd", "srk_row_stats_fwd", "srk_dat_mix_fwd",
@@ -178,7 +191,7 @@ def load():
 
 
 EXPORTS = ("srk_abi_version", "srk_last_error_string", "srk_launch_count", "srk_swin_attn_fwd", "srk_swin_mlp_fwd",
-           "srk_swin_attn_fwd_sync", "srk_swin_mlp_fwd_sync",
+           "srk_swin_attn_fwd_sync", "srk_swin_mlp_fwd_sync", "srk_swin_layer_fwd",
            "srk_layernorm_fwd", "srk_layernorm_f16_fwd", "srk_pixelshuffle_nhwc_fwd", "srk_pixelshuffle_nhwc_bias_fwd", "srk_bias_act_add_nhwc", "srk_stitch_accumulate", "srk_stitch_normalize", "srk_gather_tiles", "srk_stitch_accumulate_strided", "srk_stitch_finalize",
            "srk_conv3x3_fwd", "srk_rows_to_f16", "srk_image_to_f16_split", "srk_debug_set_timeline", "srk_debug_set_stagger",
            "srk_linear_fwd", "srk_window_attention_fwd", "srk_window_attention_table_floats", "srk_debug_set_winattn_stagger", "srk_debug_set_pdl",
@@ -235,6 +248,26 @@ def swin_mlp(x, y, wstream, vec, *, num_tokens, ld_in, ld_out, apply_ln=True, ad
     with _launch("swin_mlp", x, y, wstream, vec, progress) as st:
         _check(lib.srk_swin_mlp_fwd_sync(ctypes.byref(d), x.data_ptr(), y.data_ptr(), wstream.data_ptr(), vec.data_ptr(),
                                          None if sync is None else ctypes.byref(sync), st), lib)
+
+
+def swin_layer(y, blocks, progress, *, batch, height, width, ld) -> None:
+    """srk_swin_layer_fwd: y = blocks(y) in place for all blocks of a BasicLayer in one persistent launch.
+    blocks: list of (attn_wstream, attn_vec, mlp_wstream, mlp_vec, shift); progress: int32 CUDA tensor of >= 2 * batch elements."""
+    lib = load()
+    _require_cuda_f32(y)
+    if len(blocks) > LAYER_MAX_BLOCKS:
+        raise RuntimeError(f"swin_layer: at most {LAYER_MAX_BLOCKS} blocks per launch")
+    if not (progress.is_cuda and progress.dtype == torch.int32 and progress.is_contiguous() and progress.numel() >= 2 * batch):
+        raise RuntimeError("progress must be a contiguous CUDA int32 tensor of at least 2 * batch elements")
+    arr = (LayerBlock * len(blocks))()
+    tensors = [y, progress]
+    for k, (aw, av, mw, mv, shift) in enumerate(blocks):
+        _require_cuda_f32(av, mv)
+        arr[k] = LayerBlock(aw.data_ptr(), av.data_ptr(), mw.data_ptr(), mv.data_ptr(), int(shift), 0)
+        tensors += [aw, av, mw, mv]
+    d = LayerDesc(batch, height, width, ld, len(blocks))
+    with _launch("swin_layer", *tensors) as st:
+        _check(lib.srk_swin_layer_fwd(ctypes.byref(d), y.data_ptr(), arr, progress.data_ptr(), st), lib)
 
 
 def layernorm(x, y, w, b, *, num_tokens, ld_in, ld_out) -> None:

@@ -144,6 +144,37 @@ int srk_swin_mlp_fwd_sync(const SrkMlpDesc* d, const float* x, float* y, const v
     return check(srk::launch_swin_mlp(p, static_cast<cudaStream_t>(stream)), "srk_swin_mlp_fwd");
 }
 
+int srk_swin_layer_fwd(const SrkLayerDesc* d, float* y, const SrkLayerBlock* blocks, int32_t* progress, void* stream) {
+    if (!d || !y || !blocks || !progress) return fail("srk_swin_layer_fwd: null argument");
+    if (d->batch <= 0 || d->height <= 0 || d->width <= 0 || d->height % SRK_WINDOW || d->width % SRK_WINDOW)
+        return fail("srk_swin_layer_fwd: height/width must be positive multiples of %d (got %d x %d)", SRK_WINDOW, d->height, d->width);
+    const int64_t tokens_img = static_cast<int64_t>(d->height) * d->width;
+    if (tokens_img % 128) return fail("srk_swin_layer_fwd: height * width must be a multiple of 128 (got %lld)", static_cast<long long>(tokens_img));
+    if (d->n_blocks < 1 || d->n_blocks > SRK_LAYER_MAX_BLOCKS) return fail("srk_swin_layer_fwd: n_blocks must be 1..%d", SRK_LAYER_MAX_BLOCKS);
+    if (d->ld < SRK_DIM || (d->ld & 3) || !aligned16(y)) return fail("srk_swin_layer_fwd: ld must be >= %d and a multiple of 4, y 16-byte aligned", SRK_DIM);
+    const int64_t T = d->batch * tokens_img / 128;
+    if (T * 2 * d->n_blocks >= (int64_t(1) << 30)) return fail("srk_swin_layer_fwd: too many tiles");
+    srk::LayerParams p{};
+    p.y = y; p.ld = d->ld; p.B = d->batch; p.H = d->height; p.W = d->width;
+    p.nwx = d->width / SRK_WINDOW; p.nw_img = (d->height / SRK_WINDOW) * p.nwx;
+    p.T = static_cast<int>(T); p.tiles_per_image = static_cast<int>(tokens_img / 128);
+    p.n_blocks = d->n_blocks; p.n_items = static_cast<int>(T * 2 * d->n_blocks);
+    p.progress = progress;
+    for (int b = 0; b < d->n_blocks; ++b) {
+        const SrkLayerBlock& k = blocks[b];
+        if (!k.attn_wstream || !k.attn_vec || !k.mlp_wstream || !k.mlp_vec) return fail("srk_swin_layer_fwd: block %d has a null pointer", b);
+        if (!aligned16(k.attn_wstream) || !aligned16(k.attn_vec) || !aligned16(k.mlp_wstream) || !aligned16(k.mlp_vec))
+            return fail("srk_swin_layer_fwd: block %d: pointers must be 16-byte aligned", b);
+        if (k.shift != 0 && k.shift != SRK_WINDOW / 2) return fail("srk_swin_layer_fwd: block %d: shift must be 0 or %d", b, SRK_WINDOW / 2);
+        p.blk[b].attn_w = static_cast<const uint8_t*>(k.attn_wstream); p.blk[b].attn_vec = k.attn_vec;
+        p.blk[b].mlp_w = static_cast<const uint8_t*>(k.mlp_wstream); p.blk[b].mlp_vec = k.mlp_vec; p.blk[b].shift = k.shift;
+    }
+    p.dbg = srk::g_timeline;
+    cudaError_t e = cudaMemsetAsync(progress, 0, sizeof(int32_t) * 2 * d->batch, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail("srk_swin_layer_fwd: %s", cudaGetErrorString(e));
+    return check(srk::launch_swin_layer(p, static_cast<cudaStream_t>(stream)), "srk_swin_layer_fwd");
+}
+
 int srk_linear_fwd(const SrkLinearDesc* d, const void* a, const void* wstream, const float* bias, void* out, void* stream) {
     if (!d || !a || !wstream || !bias || !out) return fail("srk_linear_fwd: null argument");
     if (!aligned16(a) || !aligned16(wstream) || !aligned16(bias) || !aligned16(out)) return fail("srk_linear_fwd: pointers must be 16-byte aligned");

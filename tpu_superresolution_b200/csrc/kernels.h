@@ -44,6 +44,28 @@ struct MlpParams {
     int tokens_per_image;      // tile -> image (a multiple of 128 when the counters are used)
 };
 
+// swin_layer_kernel (swin_kernels.cu): all blocks of one BasicLayer in one persistent launch
+constexpr int SRK_LAYER_MAX_BLOCKS_K = 8;
+struct LayerBlockW {
+    const uint8_t* attn_w;
+    const float* attn_vec;
+    const uint8_t* mlp_w;
+    const float* mlp_vec;
+    int shift, pad;
+};
+struct LayerParams {
+    float* y;                  // residual stream (B, H*W, ld) fp32, updated in place
+    int ld;
+    int B, H, W, nwx, nw_img;
+    int T;                     // tiles per half-block = B * H * W / 128
+    int tiles_per_image;
+    int n_blocks, n_items;     // n_items = n_blocks * 2 * T
+    int* progress;             // 2 * B counters, zeroed: [0, B) windows finished by attention, [B, 2B) tiles finished by the MLP
+    LayerBlockW blk[SRK_LAYER_MAX_BLOCKS_K];
+    unsigned long long* dbg;
+};
+cudaError_t launch_swin_layer(const LayerParams& p, cudaStream_t stream);
+
 // token_linear_kernel (linear_kernel.cu)
 struct LinearParams {
     const float* x;              // SRK_LIN_A_ROWS: fp32 token rows

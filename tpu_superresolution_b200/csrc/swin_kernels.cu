@@ -861,6 +861,518 @@ __global__ void __launch_bounds__(LNW ? NTHREADS : 320, 1) swin_mlp_kernel(const
 }
 
 // ------------------------------------------------------------------------------------------------
+// KL: one persistent kernel per BasicLayer (network_swinir.py:349-416): the attention and MLP halves of ALL blocks of the group
+// ------------------------------------------------------------------------------------------------
+// Work items in global order: for block b: [attention tile 0 .. T-1][MLP tile 0 .. T-1], T = tokens / 128.  CTA c processes items
+// c, c + G, c + 2G, ... (G = grid).  An item waits, per tile, for the image it belongs to (the image progress counters of the
+// two-kernel form, umma.cuh) -- every wait is on items earlier in the global order, every CTA walks its items in order and all CTAs
+// are resident (grid <= #SMs, one CTA per SM), so the smallest unfinished item can always proceed.
+// Why: with one launch per half-block, each of the 12 launches of a 6-block group pays a prologue, a cold first tile (LayerNorm of the
+// first tile exposed, empty weight ring) and the quantisation of 3.46 tiles per CTA to 4 rounds -- measured: swin_attn_kernel 61 us
+// back to back against 37 us of steady-state tile time.  Here the pipelines never drain: the next item's LayerNorm (utility + LayerNorm
+// warps), its weights (producer) and its first GEMMs (MMA warp) overlap the current item whatever the two item types are.
+// The roles are swin_attn_kernel's (16 warps).  MLP items reuse them: the utility warps (no q|k epilogues to do) and the LayerNorm
+// warps build the next item's x image, the row warps run the GELU epilogues and the store.  TMEM of an MLP item is remapped
+// (fc1 buffers at columns 192 / 320, fc2 accumulator at 0) so that the first GEMMs of either item type never touch columns [0, 192),
+// which the row warps may still be draining for the previous item (proj / fc2 accumulator).
+constexpr uint32_t L_VECA = A_RING + RING_N * RING_STAGE;
+constexpr uint32_t L_VECM = L_VECA + ((SRK_ATTN_VEC_FLOATS * 4 + 127) / 128) * 128;
+constexpr uint32_t L_TAIL = L_VECM + ((SRK_MLP_VEC_FLOATS * 4 + 127) / 128) * 128;
+constexpr uint32_t L_BAR = L_TAIL + 16 * 720;
+constexpr uint32_t L_END = L_BAR + 512;
+constexpr uint32_t KL_SMEM = L_END + 1024;
+static_assert(KL_SMEM <= 232448, "KL shared memory exceeds 227 KB");
+constexpr uint32_t TL_F1A = 192, TL_F1B = 320, TL_F2 = 0;          // MLP items (see above)
+enum { LB_F1A = B_COUNT, LB_F1B, LB_HR0, LB_HR1, LB_HR2, LB_F2, LB_COUNT };
+
+struct LayerItem { int type, blk, tile; };
+__device__ __forceinline__ LayerItem layer_item(const LayerParams& p, int i) {
+    const int ph = i / p.T;
+    LayerItem it;
+    it.type = ph & 1; it.blk = ph >> 1; it.tile = i - ph * p.T;
+    return it;
+}
+// per-item view of the geometry helpers' parameter block
+__device__ __forceinline__ void layer_attn_params(const LayerParams& p, const LayerItem& it, AttnParams& a) {
+    a.H = p.H; a.W = p.W; a.nwx = p.nwx; a.nw_img = p.nw_img; a.ld_in = p.ld; a.ld_out = p.ld; a.apply_ln = 1; a.add_residual = 1;
+    a.total_windows = 2 * p.T; a.n_tiles = p.T; a.mask = nullptr; a.mask_nw = 1;
+    if (it.type == 0) { a.mode = SRK_MODE_IMAGE; a.shift = p.blk[it.blk].shift; a.mask_mode = a.shift > 0 ? SRK_MASK_SHIFT : SRK_MASK_NONE; }
+    else              { a.mode = SRK_MODE_WINDOWS; a.shift = 0; a.mask_mode = SRK_MASK_NONE; }        // rows = tokens 128 tile + r
+}
+// whole warp: the residual stream's base once everything item `it` reads has been written (block 0's attention: nothing to wait for)
+__device__ __forceinline__ const float* layer_item_ready(const LayerParams& p, const LayerItem& it) {
+    const int img = it.tile / p.tiles_per_image;
+    const int* ctr = it.type == 0 ? p.progress + p.B + img : p.progress + img;
+    const int target = it.type == 0 ? it.blk * p.tiles_per_image : (it.blk + 1) * p.nw_img;
+    return p.y + progress_wait(target > 0 ? ctr : nullptr, target);
+}
+static __device__ __noinline__ void layer_load_vec(float* dst, const float* src, int n, int lane_in_group, int group_threads) {
+    for (int i = lane_in_group; i < n; i += group_threads) dst[i] = __ldg(src + i);
+}
+static __device__ __noinline__ uint32_t kl_fc1_chunk(uint64_t* bars, uint32_t ring, uint32_t cur, uint32_t acc, uint32_t xa, uint64_t* done_bar) {
+    uint32_t stage = cur & 0xffu, phase = cur >> 8;
+#pragma unroll 1
+    for (int ka = 0; ka < 3; ++ka) {
+        mbar_wait(&bars[B_FULL + stage], phase);
+        tc_fence_after();
+        umma_ss_w4(acc, umma_desc_sw128(xa + ka * ATOM_A), umma_desc_sw128(ring + stage * RING_STAGE), IDESC_128x128, ka != 0);
+        umma_commit_w(&bars[B_EMPTY + stage]);
+        if (++stage == RING_N) { stage = 0; phase ^= 1; }
+    }
+    umma_commit_w(done_bar);
+    return stage | (phase << 8);
+}
+static __device__ __noinline__ uint32_t kl_fc2_chunk(uint64_t* bars, uint32_t ring, uint32_t cur, uint32_t acc, uint32_t h_tmem, uint32_t first) {
+    uint32_t stage = cur & 0xffu, phase = cur >> 8;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        mbar_wait(&bars[B_FULL + stage], phase);
+        tc_fence_after();
+        umma_ts_w4(acc, h_tmem + 64 * half, umma_desc_sw128(ring + stage * RING_STAGE), IDESC_128x192, !(first && half == 0));
+        umma_commit_w(&bars[B_EMPTY + stage]);
+        if (++stage == RING_N) { stage = 0; phase ^= 1; }
+    }
+    return stage | (phase << 8);
+}
+
+__global__ void __launch_bounds__(K1_THREADS, 1) swin_layer_kernel(const LayerParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t sbase = (raw + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (sbase - raw);
+    float* s_veca = reinterpret_cast<float*>(sm + L_VECA);
+    float* s_vecm = reinterpret_cast<float*>(sm + L_VECM);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + LB_COUNT + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int G = gridDim.x, first = blockIdx.x;
+
+    pdl_launch_dependents();
+    // constants of the first attention and MLP items (block 0); later blocks: reloaded by the utility warps (see there)
+    for (int i = threadIdx.x; i < SRK_ATTN_VEC_FLOATS; i += blockDim.x) s_veca[i] = p.blk[0].attn_vec[i];
+    for (int i = threadIdx.x; i < SRK_MLP_VEC_FLOATS; i += blockDim.x) s_vecm[i] = p.blk[0].mlp_vec[i];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < RING_N; ++i) { mbar_init(&bars[B_FULL + i], 1); mbar_init(&bars[B_EMPTY + i], 1); }
+        mbar_init(&bars[B_XA], 192); mbar_init(&bars[B_XAFREE], 1);        mbar_init(&bars[B_VTF], 1);    mbar_init(&bars[B_VTD], NROWTHREADS);
+        mbar_init(&bars[B_QKF0], 1);         mbar_init(&bars[B_QKF1], 1);   mbar_init(&bars[B_QKR0], 128); mbar_init(&bars[B_QKR1], 128);
+        mbar_init(&bars[B_SF0], 1);          mbar_init(&bars[B_SF1], 1);
+        mbar_init(&bars[B_PR0], 128);        mbar_init(&bars[B_PR1], 128);  mbar_init(&bars[B_OF], 1);
+        mbar_init(&bars[B_OR], NROWTHREADS); mbar_init(&bars[B_PJF], 1);    mbar_init(&bars[B_DRAIN], 128);
+        mbar_init(&bars[LB_F1A], 1);         mbar_init(&bars[LB_F1B], 1);   mbar_init(&bars[LB_F2], 1);
+        mbar_init(&bars[LB_HR0], NROWTHREADS); mbar_init(&bars[LB_HR1], NROWTHREADS); mbar_init(&bars[LB_HR2], NROWTHREADS);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    if (warp != 0) pdl_wait();          // (the weight producer streams constant slabs either way)
+
+    if (warp == 0) {
+        // ===================================================== weight producer
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int i = first; i < p.n_items; i += G) {
+                const LayerItem it = layer_item(p, i);
+                const uint8_t* w = it.type == 0 ? p.blk[it.blk].attn_w : p.blk[it.blk].mlp_w;
+                uint32_t off = 0;
+                for (int s = 0; s < 15; ++s) {      // slab sizes in MMA order: see swin_attn_kernel / swin_mlp_kernel
+                    const uint32_t bytes = it.type == 0 ? ((s < 3 || s >= 12) ? 24576u : 16384u) : ((s < 6 || (s >= 8 && s < 11)) ? 16384u : 24576u);
+                    mbar_wait(&bars[B_EMPTY + stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&bars[B_FULL + stage], bytes);
+                    bulk_g2s(sm + A_RING + stage * RING_STAGE, w + off, bytes, &bars[B_FULL + stage]);
+                    off += bytes;
+                    if (++stage == RING_N) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer (warp-uniform: see umma_ss_w)
+        uint32_t ph_xa = 0, ph_vtd = 0, ph_qkr[2] = {0, 0}, ph_pr[2] = {0, 0}, ph_or = 0, ph_hr[3] = {0, 0, 0}, nchunk = 0;
+        const uint32_t xa = sbase + A_XA, vt = sbase + A_VT, qki = sbase + A_QKI, ring = sbase + A_RING;
+        uint32_t cur = 0;                   // weight ring cursor (stage | phase << 8)
+        auto gemm_k192 = [&](uint32_t d_tmem, uint32_t img, bool img_is_a, uint32_t idesc) {
+            cur = k1_gemm_k192(bars, ring, cur, d_tmem, img, img_is_a ? 1u : 0u, idesc);
+        };
+        auto gemm_qk_pair = [&]() {
+            gemm_k192(tmem + TC_QK0, xa, true, IDESC_128x128);
+            umma_commit_w(&bars[B_QKF0]);
+            umma_commit_w(&bars[B_QKF1]);
+        };
+        auto issue_s = [&](int h) {
+            const uint32_t img = qki + (h & 1) * ATOM_A;
+            const uint32_t scol = tmem + ((h & 1) ? TC_S1 : TC_S0);
+#pragma unroll
+            for (int w = 0; w < 2; ++w)
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)
+                    umma_ss_w(scol + w * LANE16, umma_desc_sw128(img + w * 8192 + ks * 32), umma_desc_sw128(img + w * 8192 + 64 + ks * 32),
+                              IDESC_64x64, ks != 0);
+            umma_commit_w(&bars[B_SF0 + (h & 1)]);
+        };
+        auto issue_pv = [&](int h) {
+            const uint32_t pcol = tmem + ((h & 1) ? TC_S1 : TC_S0);
+#pragma unroll
+            for (int w = 0; w < 2; ++w)
+                umma_ts_w4<128>(tmem + TC_O + 32 * h + w * LANE16, pcol + w * LANE16,
+                                umma_desc_sw128(vt + (h >> 1) * ATOM_A + w * 8192 + (h & 1) * 64), IDESC_64x32_BMN, 0);
+        };
+        for (int i = first; i < p.n_items; i += G) {
+            const LayerItem it = layer_item(p, i);
+            mbar_wait(&bars[B_XA], ph_xa); ph_xa ^= 1;
+            tc_fence_after();
+            if (it.type == 0) {
+                gemm_k192(tmem + TC_V, xa, true, IDESC_128x192);
+                umma_commit_w(&bars[B_VTF]);
+                gemm_qk_pair();
+                mbar_wait(&bars[B_VTD], ph_vtd); ph_vtd ^= 1;
+                tc_fence_after();
+#pragma unroll 1
+                for (int h = 0; h < 6; ++h) {
+                    mbar_wait(&bars[B_QKR0 + (h & 1)], ph_qkr[h & 1]); ph_qkr[h & 1] ^= 1;
+                    tc_fence_after();
+                    issue_s(h);
+                    if ((h & 1) && h < 5) gemm_qk_pair();
+                    if (h == 3) umma_commit_w(&bars[B_XAFREE]);
+                    if (h >= 1) {
+                        mbar_wait(&bars[B_PR0 + ((h - 1) & 1)], ph_pr[(h - 1) & 1]); ph_pr[(h - 1) & 1] ^= 1;
+                        tc_fence_after();
+                        issue_pv(h - 1);
+                    }
+                }
+                mbar_wait(&bars[B_PR1], ph_pr[1]); ph_pr[1] ^= 1;
+                tc_fence_after();
+                issue_pv(5);
+                umma_commit_w(&bars[B_OF]);
+                mbar_wait(&bars[B_OR], ph_or); ph_or ^= 1;
+                tc_fence_after();
+                gemm_k192(tmem + TC_PROJ, vt, true, IDESC_128x192);
+                umma_commit_w(&bars[B_PJF]);
+            } else {
+                const uint32_t b0 = nchunk & 1;
+                auto f1buf = [&](uint32_t buf) { return tmem + (buf ? TL_F1B : TL_F1A); };
+                auto fc1 = [&]() {
+                    const uint32_t buf = nchunk & 1;
+                    cur = kl_fc1_chunk(bars, ring, cur, f1buf(buf), xa, &bars[buf ? LB_F1B : LB_F1A]);
+                    ++nchunk;
+                };
+                fc1();                                                           // chunk 0 -> buffer b0
+                fc1();                                                           // chunk 1 -> buffer b0 ^ 1
+                mbar_wait(&bars[LB_HR0], ph_hr[0]); ph_hr[0] ^= 1;               // H of chunk 0 written over its accumulators;
+                tc_fence_after();                                                // (the row warps are past the previous item: columns [0,192) are free)
+                cur = kl_fc2_chunk(bars, ring, cur, tmem + TL_F2, f1buf(b0), 1u);
+                fc1();                                                           // chunk 2 -> buffer b0
+                umma_commit_w(&bars[B_XAFREE]);                                  // all fc1 GEMMs issued: the x image is free once they complete
+                mbar_wait(&bars[LB_HR1], ph_hr[1]); ph_hr[1] ^= 1;
+                tc_fence_after();
+                cur = kl_fc2_chunk(bars, ring, cur, tmem + TL_F2, f1buf(b0 ^ 1), 0u);
+                mbar_wait(&bars[LB_HR2], ph_hr[2]); ph_hr[2] ^= 1;
+                tc_fence_after();
+                cur = kl_fc2_chunk(bars, ring, cur, tmem + TL_F2, f1buf(b0), 0u);
+                umma_commit_w(&bars[LB_F2]);
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 14) {
+        // ===================================================== 2 LayerNorm warps: rows [64, 128) of the NEXT item's x image
+        const int lw = warp - 14;
+        const uint32_t xa = sbase + A_XA;
+        uint32_t ph_free = 0;
+        TileGeom geo;
+        AttnParams pa{};
+        if (first < p.n_items) mbar_arrive(&bars[B_XA]);        // first item: the row warps build all of it
+        for (int i = first; i + G < p.n_items; i += G) {
+            const LayerItem nx = layer_item(p, i + G);
+            layer_attn_params(p, nx, pa);
+            const float* xb = layer_item_ready(p, nx);
+            set_tile_geom(pa, nx.tile, geo);
+            uint2 hb[8][3];
+            {
+                const RowSrc16 rs = make_row_src16(pa, xb, geo, 64 + 32 * lw, lane);
+                ln_rows_hold_p<8>(1, lane, [&](int pass) { return rs.ptr(pass); }, hb);
+            }
+            mbar_wait(&bars[B_XAFREE], ph_free); ph_free ^= 1;
+            ln_rows_dump<8>(xa, 64 + 32 * lw, lane, hb);
+            k1_ln16(pa, xb, geo, xa, 4 + 2 * lw + 1, lane);
+            fence_proxy_async_smem();
+            mbar_arrive(&bars[B_XA]);
+        }
+    } else if (warp >= 10) {
+        // ===================================================== 128 utility threads: q|k epilogues (attention items), rows [0, 64) of the
+        //                                                       next item's x image, reload of the per-block constants
+        const int cwu = warp - 10;
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t lanebase = static_cast<uint32_t>(q * 32) << 16;
+        const uint32_t xa = sbase + A_XA, qki = sbase + A_QKI;
+        uint32_t ph_qkf[2] = {0, 0};
+        TileGeom geo;
+        AttnParams pa{};
+        int n = 0, blk_a = 0, blk_m = 0;            // blocks whose constants are in s_veca / s_vecm
+        for (int i = first; i < p.n_items; i += G, ++n) {
+            const LayerItem it = layer_item(p, i);
+            const bool has_next = i + G < p.n_items;
+            const LayerItem nx = layer_item(p, has_next ? i + G : i);
+            if (it.type == 0) {
+                // the previous item's output rows (staged over the V^T / q|k images) have left shared memory: phase n - 1 of B_DRAIN
+                if (n > 0) mbar_wait(&bars[B_DRAIN], static_cast<uint32_t>((n - 1) & 1));
+#pragma unroll 1
+                for (int h = 0; h < 6; ++h) {
+                    mbar_wait(&bars[B_QKF0 + (h & 1)], ph_qkf[h & 1]); ph_qkf[h & 1] ^= 1;
+                    tc_fence_after();
+                    const uint32_t img = qki + (h & 1) * ATOM_A;
+                    const uint32_t acc = tmem + lanebase + ((h & 1) ? TC_QK1 : TC_QK0);
+                    uint32_t v[32];
+                    tmem_ld32(acc, v);
+                    tmem_ld_wait();
+                    store_row_chunks<true, false>(img, row, 0, v, s_veca + SRK_AV_BIAS_Q + 32 * h, 1.0f);
+                    tmem_ld32(acc + 32, v);
+                    tmem_ld_wait();
+                    store_row_chunks<false, false>(img, row, 4, v, nullptr, 1.0f);
+                    tc_fence_before();
+                    fence_proxy_async_smem();
+                    mbar_arrive(&bars[B_QKR0 + (h & 1)]);
+                }
+                // the q|k GEMM of head 5 is complete, so nothing reads the x image any more
+                if (has_next) {
+                    layer_attn_params(p, nx, pa);
+                    const float* xb = layer_item_ready(p, nx);
+                    set_tile_geom(pa, nx.tile, geo);
+                    k1_ln16(pa, xb, geo, xa, cwu, lane);
+                }
+            } else if (has_next) {
+                // MLP item: nothing else to do -- load and normalise the next item's rows into registers right away, dump them once the
+                // fc1 GEMMs have read the x image (phase n of B_XAFREE: one completion per item)
+                layer_attn_params(p, nx, pa);
+                const float* xb = layer_item_ready(p, nx);
+                set_tile_geom(pa, nx.tile, geo);
+                uint2 hb[8][3];
+                {
+                    const RowSrc16 rs = make_row_src16(pa, xb, geo, 16 * cwu, lane);
+                    ln_rows_hold_p<8>(1, lane, [&](int pass) { return rs.ptr(pass); }, hb);
+                }
+                mbar_wait(&bars[B_XAFREE], static_cast<uint32_t>(n & 1));
+                ln_rows_dump<8>(xa, 16 * cwu, lane, hb);
+            }
+            if (has_next) {
+                // constants of the next item's block: its type's previous user is an EARLIER item of this CTA (items of one type are
+                // separated by the row warps' sequential order), and its first reader waits behind B_XA, which this arrive releases
+                if (nx.type == 0 && nx.blk != blk_a) { layer_load_vec(s_veca, p.blk[nx.blk].attn_vec, SRK_ATTN_VEC_FLOATS, threadIdx.x - 320, 128); blk_a = nx.blk; }
+                if (nx.type == 1 && nx.blk != blk_m) { layer_load_vec(s_vecm, p.blk[nx.blk].mlp_vec, SRK_MLP_VEC_FLOATS, threadIdx.x - 320, 128); blk_m = nx.blk; }
+                fence_proxy_async_smem();
+                mbar_arrive(&bars[B_XA]);
+            }
+        }
+    } else {
+        // ===================================================== 256 row threads (two groups)
+        const int cw8 = warp - 2;
+        const int g = cw8 >> 2;
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t lanebase = static_cast<uint32_t>(q * 32) << 16;
+        const uint32_t vt = sbase + A_VT;
+        const int half = lane >> 4, t = 16 * q + (lane & 15);
+        const int srow = 64 * half + t;
+        const int rpb_base = (t >> 3) * 15 + (t & 7) + 112;
+        uint32_t ph_vtf = 0, ph_sf = 0, ph_of = 0, ph_pjf = 0, ph_f1[2] = {0, 0}, ph_f2 = 0, nchunk = 0;
+        uint64_t* const bar_sf = &bars[B_SF0 + g];
+        uint64_t* const bar_pr = &bars[B_PR0 + g];
+        const uint32_t scol = g ? TC_S1 : TC_S0;
+        TileGeom geo;
+        AttnParams pa{};
+
+        if (first < p.n_items) {            // first item's x image (later ones: the utility / LayerNorm warps, one item ahead)
+            const LayerItem it0 = layer_item(p, first);
+            layer_attn_params(p, it0, pa);
+            const float* xb = layer_item_ready(p, it0);
+            set_tile_geom(pa, it0.tile, geo);
+            k1_ln16(pa, xb, geo, sbase + A_XA, cw8, lane);
+            fence_proxy_async_smem();
+            named_bar_sync(1, NROWTHREADS);
+            if (g == 0) mbar_arrive(&bars[B_XA]);
+        }
+        struct RowState { TileGeom geo; uint32_t mh, mw; };
+        auto prep = [&](const LayerItem& it, RowState& st) {           // window geometry / mask bits of this row for an attention item
+            AttnParams a{};
+            layer_attn_params(p, it, a);
+            set_tile_geom(a, it.tile, st.geo);
+            const int gw_row = it.tile * 2 + half;
+            st.mh = 0xffu; st.mw = 0xffu;
+            if (a.mask_mode == SRK_MASK_SHIFT) {
+                const int w = gw_row % p.nw_img;
+                const int wy = w / p.nwx, wx = w - wy * p.nwx;
+                auto reg = [&](int pos, int Ln) { return (pos >= Ln - 8 ? 1 : 0) + (pos >= Ln - a.shift ? 1 : 0); };
+                const int rh = reg(wy * 8 + (t >> 3), p.H), rw = reg(wx * 8 + (t & 7), p.W);
+                st.mh = 0; st.mw = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    st.mh |= (reg(wy * 8 + k, p.H) == rh ? 1u : 0u) << k;
+                    st.mw |= (reg(wx * 8 + k, p.W) == rw ? 1u : 0u) << k;
+                }
+            }
+        };
+        RowState nxt;
+        if (first < p.n_items) prep(layer_item(p, first), nxt);
+        // progress report of a finished item by group 0 (the threads that issued its bulk stores): deferred to the middle of the next
+        // item (its copies are long done by then, nothing stalls) unless the next item of this CTA is in another phase -- it might
+        // depend on this very item -- or there is none
+        int* pend_ctr = nullptr;
+        int pend_add = 0;
+        auto flush_signal = [&]() {
+            if (pend_ctr != nullptr) { signal_progress(pend_ctr, pend_add); pend_ctr = nullptr; }
+        };
+
+        int n = 0;
+        unsigned long long* dbg = threadIdx.x == 64 ? p.dbg : nullptr;
+        for (int i = first; i < p.n_items; i += G, ++n) {
+            const LayerItem it = layer_item(p, i);
+            const bool has_next = i + G < p.n_items;
+            const LayerItem nx = layer_item(p, has_next ? i + G : i);
+            SRK_TL(dbg, n, 0);
+            if (it.type == 0) {
+                // ------------------------------------------------------------------ attention item (swin_attn_kernel's row loop)
+                layer_attn_params(p, it, pa);
+                geo = nxt.geo;
+                const uint32_t mh = nxt.mh, mw = nxt.mw;
+                const bool masked = (mh & mw) != 0xffu;
+                auto tok_of_row = [&](int r) -> int64_t { return tile_tok(pa, geo, r); };
+                mbar_wait(&bars[B_VTF], ph_vtf); ph_vtf ^= 1;
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const int d0 = 96 * g + 32 * c;
+                    uint32_t v[32];
+                    tmem_ld32(tmem + lanebase + TC_V + d0, v);
+                    tmem_ld_wait();
+                    store_row_chunks<false, false>(vt + (d0 >> 6) * ATOM_A, row, (d0 & 63) >> 3, v, nullptr, 1.0f);
+                }
+                tc_fence_before();
+                fence_proxy_async_smem();
+                mbar_arrive(&bars[B_VTD]);
+                float inv_sum0 = 0.f, inv_sum1 = 0.f, inv_sum2 = 0.f;
+#pragma unroll 1
+                for (int hh = 0; hh < 3; ++hh) {
+                    const int h = 2 * hh + g;
+                    mbar_wait(bar_sf, ph_sf); ph_sf ^= 1;
+                    tc_fence_after();
+                    uint32_t v0[32], v1[32];
+                    tmem_ld32(tmem + lanebase + scol, v0);
+                    tmem_ld32(tmem + lanebase + scol + 32, v1);
+                    tmem_ld_wait();
+                    const float* rpb = s_veca + SRK_AV_RPB + h * SRK_AV_RPB_STRIDE + rpb_base;
+                    float s[64];
+#pragma unroll
+                    for (int jx = 0; jx < 64; ++jx)
+                        s[jx] = __uint_as_float(jx < 32 ? v0[jx] : v1[jx - 32]) + rpb[-(15 * (jx >> 3) + (jx & 7))];
+                    if (masked) {
+#pragma unroll
+                        for (int jx = 0; jx < 64; ++jx)
+                            if (!(((mh >> (jx >> 3)) & (mw >> (jx & 7))) & 1u)) s[jx] += -100.0f * LOG2E;
+                    }
+                    float mx = s[0];
+#pragma unroll
+                    for (int jx = 1; jx < 64; ++jx) mx = fmaxf(mx, s[jx]);
+                    float sum0 = 0.f, sum1 = 0.f;
+                    uint32_t pw[32];
+#pragma unroll
+                    for (int jx = 0; jx < 64; jx += 2) {
+                        const float e0 = ex2_approx(s[jx] - mx), e1 = ex2_approx(s[jx + 1] - mx);
+                        sum0 += e0; sum1 += e1;
+                        pw[jx >> 1] = pack_bf16x2(e0, e1);
+                    }
+                    {
+                        const float is = __frcp_rn(sum0 + sum1);
+                        if (hh == 0) inv_sum0 = is; else if (hh == 1) inv_sum1 = is; else inv_sum2 = is;
+                    }
+                    tmem_st32(tmem + lanebase + scol, pw);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(bar_pr);
+                    if (g == 0 && hh == 0) flush_signal();
+                }
+                mbar_wait(&bars[B_OF], ph_of); ph_of ^= 1;
+                tc_fence_after();
+#pragma unroll 1
+                for (int hh = 0; hh < 3; ++hh) {
+                    const int h = 2 * hh + g;
+                    uint32_t v[32];
+                    tmem_ld32(tmem + lanebase + TC_O + 32 * h, v);
+                    tmem_ld_wait();
+                    store_row_chunks<false, true>(vt + (h >> 1) * ATOM_A, srow, (h & 1) * 4, v, nullptr, hh == 0 ? inv_sum0 : (hh == 1 ? inv_sum1 : inv_sum2));
+                }
+                tc_fence_before();
+                fence_proxy_async_smem();
+                mbar_arrive(&bars[B_OR]);
+                if (has_next && nx.type == 0) prep(nx, nxt);          // ~300 dependent scalar instructions, under the proj GEMM
+                mbar_wait(&bars[B_PJF], ph_pjf); ph_pjf ^= 1;
+                tc_fence_after();
+                stage_rows_and_bulk_store(tmem + TC_PROJ, lanebase, sm + A_VT, sm + L_TAIL, 28, s_veca + SRK_AV_BIAS_PROJ, p.y, p.ld,
+                                          1, q, g, lane, tok_of_row);
+                tc_fence_before();
+                if (g == 0) { pend_ctr = p.progress + (it.tile * 2) / p.nw_img; pend_add = 2; }
+            } else {
+                // ------------------------------------------------------------------ MLP item (swin_mlp_kernel's row loop)
+                const int tile = it.tile;
+                auto tok_of_row = [&](int r) -> int64_t { return static_cast<int64_t>(tile) * 128 + r; };
+#pragma unroll 1
+                for (int c = 0; c < 3; ++c) {
+                    const uint32_t buf = nchunk & 1;
+                    ++nchunk;
+                    mbar_wait(&bars[buf ? LB_F1B : LB_F1A], ph_f1[buf]); ph_f1[buf] ^= 1;
+                    tc_fence_after();
+                    {
+                        const uint32_t col = (buf ? TL_F1B : TL_F1A) + 64 * g;
+                        uint32_t v0[32], v1[32];
+                        tmem_ld32(tmem + lanebase + col, v0);
+                        tmem_ld32(tmem + lanebase + col + 32, v1);
+                        tmem_ld_wait();
+                        const float4* b1 = reinterpret_cast<const float4*>(s_vecm + SRK_MV_B1 + 128 * c + 64 * g);
+                        uint32_t hw[32];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const float4 b = b1[k];
+                            hw[2 * k] = pack_bf16x2(gelu_fast(__uint_as_float(v0[4 * k + 0]) + b.x), gelu_fast(__uint_as_float(v0[4 * k + 1]) + b.y));
+                            hw[2 * k + 1] = pack_bf16x2(gelu_fast(__uint_as_float(v0[4 * k + 2]) + b.z), gelu_fast(__uint_as_float(v0[4 * k + 3]) + b.w));
+                        }
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const float4 b = b1[8 + k];
+                            hw[16 + 2 * k] = pack_bf16x2(gelu_fast(__uint_as_float(v1[4 * k + 0]) + b.x), gelu_fast(__uint_as_float(v1[4 * k + 1]) + b.y));
+                            hw[16 + 2 * k + 1] = pack_bf16x2(gelu_fast(__uint_as_float(v1[4 * k + 2]) + b.z), gelu_fast(__uint_as_float(v1[4 * k + 3]) + b.w));
+                        }
+                        tmem_st32(tmem + lanebase + col, hw);
+                        tmem_st_wait();
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&bars[LB_HR0 + c]);
+                }
+                if (g == 0) flush_signal();
+                if (has_next && nx.type == 0) prep(nx, nxt);
+                mbar_wait(&bars[LB_F2], ph_f2); ph_f2 ^= 1;
+                tc_fence_after();
+                stage_rows_and_bulk_store(tmem + TL_F2, lanebase, sm + A_VT, sm + L_TAIL, 28, s_vecm + SRK_MV_B2, p.y, p.ld, 1, q, g, lane, tok_of_row);
+                tc_fence_before();
+                if (g == 0) { pend_ctr = p.progress + p.B + tile / p.tiles_per_image; pend_add = 1; }
+            }
+            // the copies drain while the next item's first GEMMs run; nobody may write the V^T / q|k regions before that
+            if (g == 0) {
+                bulk_wait_read0();
+                mbar_arrive(&bars[B_DRAIN]);            // -> utility warps (q|k images of the next attention item)
+            }
+            named_bar_sync(1, NROWTHREADS);             // -> both groups (V^T image / store staging of the next item)
+            // no next item, or the next item of this CTA is in another phase (it may depend on this very item): report now
+            if (g == 0 && (!has_next || (i + G) / p.T != i / p.T)) flush_signal();
+            SRK_TL(dbg, n, 63);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
 static int num_sms() { return device_num_sms(); }
@@ -879,6 +1391,13 @@ cudaError_t launch_swin_mlp(const MlpParams& p, cudaStream_t stream) {
     const int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
     if (p.n_tiles > 2 * grid) return launch_pdl(swin_mlp_kernel<true>, grid, NTHREADS, K2_SMEM, stream, p);
     return launch_pdl(swin_mlp_kernel<false>, grid, 320, K2_SMEM, stream, p);
+}
+
+cudaError_t launch_swin_layer(const LayerParams& p, cudaStream_t stream) {
+    static bool configured[SRK_MAX_DEVICES] = {};
+    if (cudaError_t e = configure_smem_once(configured, swin_layer_kernel, KL_SMEM); e != cudaSuccess) return e;
+    const int grid = p.T < num_sms() ? p.T : num_sms();
+    return launch_pdl(swin_layer_kernel, grid, K1_THREADS, KL_SMEM, stream, p);
 }
 
 }  // namespace srk

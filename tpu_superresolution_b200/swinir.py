@@ -214,6 +214,8 @@ class SwinTransformerBlock(nn.Module):
 
 # image progress counters between the kernels of a BasicLayer (include/srk.h: SrkBlockSync); SRK_BLOCK_SYNC=0 disables them
 USE_BLOCK_SYNC = os.environ.get("SRK_BLOCK_SYNC", "1") != "0"
+# one persistent launch per BasicLayer (include/srk.h: srk_swin_layer_fwd); SRK_LAYER_KERNEL=0 selects one launch per half-block
+USE_LAYER_KERNEL = os.environ.get("SRK_LAYER_KERNEL", "1") != "0"
 
 
 class BasicLayer(nn.Module):
@@ -234,8 +236,25 @@ class BasicLayer(nn.Module):
             raise RuntimeError("BasicLayer: downsample (PatchMerging) is never used by SwinIR and is not implemented")
         self.downsample = None
 
+    def _layer_kernel_ok(self, x, x_size) -> bool:
+        H, W = x_size
+        return (USE_LAYER_KERNEL and 1 <= len(self.blocks) <= L.LAYER_MAX_BLOCKS and x.is_cuda and x.dtype == torch.float32
+                and H % L.WINDOW == 0 and W % L.WINDOW == 0 and (H * W) % 128 == 0 and x.shape[-1] == L.DIM
+                and all(b.shift_size in (0, L.WINDOW // 2) and b.window_size == L.WINDOW for b in self.blocks))
+
     def forward(self, x, x_size):
         x = x.contiguous()
+        if self._layer_kernel_ok(x, x_size):
+            # all blocks in ONE persistent launch (srk_swin_layer_fwd), in place on a copy of x (x stays the group's residual)
+            _inference_only(self.blocks[0])
+            B, Ltok, C = x.shape
+            if Ltok != x_size[0] * x_size[1]:
+                raise RuntimeError("input feature has wrong size")
+            out = x.clone()
+            packed = [blk.attn._packed(blk.norm1) + blk.mlp._packed(blk.norm2) + (blk.shift_size,) for blk in self.blocks]
+            progress = torch.empty(2 * B, dtype=torch.int32, device=x.device)
+            L.swin_layer(out, packed, progress, batch=B, height=x_size[0], width=x_size[1], ld=C)
+            return out
         out = torch.empty_like(x)
         src = x
         progress = torch.zeros(2 * x.shape[0], dtype=torch.int32, device=x.device) if USE_BLOCK_SYNC else None
