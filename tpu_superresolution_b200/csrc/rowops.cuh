@@ -217,7 +217,8 @@ constexpr uint32_t ROW_BYTES = SRK_DIM * 4;     // 720
 template <typename TokFn>
 __device__ __forceinline__ void stage_rows_and_bulk_store(uint32_t tmem_acc, uint32_t lanebase, uint8_t* stage_main, uint8_t* stage_tail,
                                                           int main_rows, const float* s_bias, float* __restrict__ y, int ld_out,
-                                                          int add_residual, int q, int g, int lane, TokFn tok_of_row, int act_gelu = 0) {
+                                                          int add_residual, int q, int g, int lane, TokFn tok_of_row, int act_gelu = 0,
+                                                          unsigned long long* tl = nullptr) {
     uint8_t* const my_row = lane < main_rows ? stage_main + (q * main_rows + lane) * ROW_BYTES
                                              : stage_tail + (q * (32 - main_rows) + lane - main_rows) * ROW_BYTES;
     float* dst = reinterpret_cast<float*>(my_row);
@@ -241,8 +242,10 @@ __device__ __forceinline__ void stage_rows_and_bulk_store(uint32_t tmem_acc, uin
             }
         }
     }
+    if (tl) tl[50] = clock64();
     fence_proxy_async_smem();                   // generic-proxy smem writes -> visible to the bulk copy engine
     named_bar_sync(2 + q, 64);                  // both groups of this lane quadrant have written their columns
+    if (tl) tl[51] = clock64();
     if (g == 0) {
         // one bulk copy per maximal run of tokens that are contiguous in memory (and in the staging buffer)
         const int64_t tok = tok_of_row(q * 32 + lane);
@@ -251,14 +254,28 @@ __device__ __forceinline__ void stage_rows_and_bulk_store(uint32_t tmem_acc, uin
         const bool start = valid && (lane == 0 || lane == main_rows || ld_out != SRK_DIM || prev < 0 || tok != prev + 1);
         const uint32_t m_start = __ballot_sync(0xffffffffu, start);
         const uint32_t m_stop = m_start | ~__ballot_sync(0xffffffffu, valid);      // next start or first invalid row ends a run
-        if (start) {
-            const uint32_t after = lane == 31 ? 0u : (m_stop >> (lane + 1));
-            const int len = after ? __ffs(after) : (32 - lane);
-            float* gdst = y + tok * ld_out;
-            if (add_residual) bulk_s2g_add_f32(gdst, smem_u32(my_row), len * ROW_BYTES);
-            else              bulk_s2g(gdst, smem_u32(my_row), len * ROW_BYTES);
-            bulk_commit();
+        // Issue from CONVERGENT code with warp-uniform operands: inside `if (start)` the compiler wraps the bulk-copy instruction
+        // (its operands live in uniform registers) in an ELECT / R2UR.BROADCAST waterfall loop, one trip per run.  Here every lane
+        // computes its run, then the warp walks the run starts; the values of the run's first lane are broadcast and one elected
+        // lane issues the copy (all copies of a warp therefore belong to that lane's bulk groups).
+        const uint32_t after = lane == 31 ? 0u : (m_stop >> (lane + 1));
+        const int len = after ? __ffs(after) : (32 - lane);
+        const uint32_t my_bytes = static_cast<uint32_t>(len) * ROW_BYTES;
+        const uint32_t my_src = smem_u32(my_row);
+        float* const my_dst = y + (valid ? tok : 0) * ld_out;
+        for (uint32_t m = m_start; m != 0; m &= m - 1) {
+            const int l = __ffs(m) - 1;
+            const uint32_t bytes = __shfl_sync(0xffffffffu, my_bytes, l);
+            const uint32_t src = __shfl_sync(0xffffffffu, my_src, l);
+            const uint64_t dst = __shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(my_dst), l);
+            if (add_residual)
+                asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                             "@e cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;\n\t}" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+            else
+                asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                             "@e cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n\t}" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
         }
+        bulk_commit();
         __syncwarp();
     }
 }

@@ -579,7 +579,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
             tc_fence_after();
             SRK_TL(dbg, it, 26);
             stage_rows_and_bulk_store(tmem + TC_PROJ, lanebase, sm + A_VT, sm + A_TAIL, 28, s_vec + SRK_AV_BIAS_PROJ, p.y, p.ld_out,
-                                      p.add_residual, q, g, lane, tok_of_row);
+                                      p.add_residual, q, g, lane, tok_of_row, 0, (dbg != nullptr && blockIdx.x == 0 && it < 8) ? dbg + it * 64 : nullptr);
             tc_fence_before();
             SRK_TL(dbg, it, 28);
             // the copies drain while the next tile's V^T / q|k GEMMs run; nobody may write the V^T or q|k images before that
@@ -1308,9 +1308,11 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_layer_kernel(const LayerPa
                 if (has_next && nx.type == 0) prep(nx, nxt);          // ~300 dependent scalar instructions, under the proj GEMM
                 mbar_wait(&bars[B_PJF], ph_pjf); ph_pjf ^= 1;
                 tc_fence_after();
+                SRK_TL(dbg, n, 26);
                 stage_rows_and_bulk_store(tmem + TC_PROJ, lanebase, sm + A_VT, sm + L_TAIL, 28, s_veca + SRK_AV_BIAS_PROJ, p.y, p.ld,
-                                          1, q, g, lane, tok_of_row);
+                                          1, q, g, lane, tok_of_row, 0, (dbg != nullptr && blockIdx.x == 0 && n < 8) ? dbg + n * 64 : nullptr);
                 tc_fence_before();
+                SRK_TL(dbg, n, 28);
                 if (g == 0) { pend_ctr = p.progress + (it.tile * 2) / p.nw_img; pend_add = 2; }
             } else {
                 // ------------------------------------------------------------------ MLP item (swin_mlp_kernel's row loop)

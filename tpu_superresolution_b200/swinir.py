@@ -214,8 +214,11 @@ class SwinTransformerBlock(nn.Module):
 
 # image progress counters between the kernels of a BasicLayer (include/srk.h: SrkBlockSync); SRK_BLOCK_SYNC=0 disables them
 USE_BLOCK_SYNC = os.environ.get("SRK_BLOCK_SYNC", "1") != "0"
-# one persistent launch per BasicLayer (include/srk.h: srk_swin_layer_fwd); SRK_LAYER_KERNEL=0 selects one launch per half-block
-USE_LAYER_KERNEL = os.environ.get("SRK_LAYER_KERNEL", "1") != "0"
+# SRK_LAYER_KERNEL=1: one persistent launch per BasicLayer (include/srk.h: srk_swin_layer_fwd) instead of one launch per half-block.
+# Bit-identical and tested, but measured 2 % SLOWER at the BASELINE shape (4.47 vs 4.39 ms/step: inside the merged kernel an
+# attention item takes 25 K cycles against 21 K in swin_attn_kernel and an MLP item 17.5 K against 12.8 K -- DESIGN.md 3.6c), so
+# the default stays one launch per half-block ordered by the image progress counters.
+USE_LAYER_KERNEL = os.environ.get("SRK_LAYER_KERNEL", "0") == "1"
 
 
 class BasicLayer(nn.Module):
