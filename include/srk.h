@@ -75,7 +75,7 @@ typedef struct SrkSwinAttnDesc {
 int srk_swin_attn_fwd(const SrkSwinAttnDesc* desc, const float* x, float* y, const void* wstream /* SRK_ATTN_WSTREAM_BYTES */,
                       const float* vec /* SRK_ATTN_VEC_FLOATS */, const float* mask /* or NULL */, void* stream);
 
-/* MLP half:  y = x + fc2(gelu(fc1(LN2(x)))), gelu = the exact-erf form evaluated to 2.6e-5 (see swin_kernels.cu).  Replaces network_swinir.py:277 + Mlp.forward :24-30. */
+/* MLP half:  y = x + fc2(gelu(fc1(LN2(x)))), gelu = nn.GELU() (erf form) evaluated by a tanh-form polynomial fit, |error| <= 2.6e-5 before the bf16 rounding (rowops.cuh: gelu_fast).  Replaces network_swinir.py:277 + Mlp.forward :24-30. */
 typedef struct SrkMlpDesc {
     int64_t num_tokens;
     int32_t ld_in, ld_out;

@@ -120,15 +120,27 @@ def _spatial_interaction(x_img: Tensor, p: Dict[str, Tensor], pre: str) -> Tenso
 
 def adaptive_spatial_attention(x: Tensor, H: int, W: int, p: Dict[str, Tensor], pre: str, heads: int,
                                split: Sequence[int], shifted: bool) -> Tensor:
-    """Adaptive_Spatial_Attention.forward, dat_arch.py:363-438 (H, W multiples of max(split): no padding)."""
+    """Adaptive_Spatial_Attention.forward, dat_arch.py:363-438, including the zero padding of the PROJECTED q, k, v to a multiple
+    of max(split) (:376-385: the qkv bias is not re-added on the pad), masks for the padded size (:396-399) and the crop (:406-407)."""
     B, L, C = x.shape
-    assert H % max(split) == 0 and W % max(split) == 0, "oracle restates the un-padded case"
     qkv = x @ p[pre + "qkv.weight"].T + p[pre + "qkv.bias"]
     q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
     h2, c2 = heads // 2, C // 2
     s0, s1 = split[0] // 2, split[1] // 2
-    x1 = spatial_branch(q[..., :c2], k[..., :c2], v[..., :c2], H, W, split[0], split[1], s0, s1, h2, p, pre + "attns.0.", shifted)
-    x2 = spatial_branch(q[..., c2:], k[..., c2:], v[..., c2:], H, W, split[1], split[0], s1, s0, h2, p, pre + "attns.1.", shifted)
+    m = max(split)
+    Hp, Wp = H + (m - H % m) % m, W + (m - W % m) % m
+
+    def padded(t):          # (B, H*W, c) -> (B, Hp*Wp, c), zeros at the bottom / right
+        if (Hp, Wp) == (H, W):
+            return t
+        return F.pad(t.reshape(B, H, W, -1), (0, 0, 0, Wp - W, 0, Hp - H)).reshape(B, Hp * Wp, -1)
+
+    def cropped(t):         # (B, Hp, Wp, c) -> (B, H*W, c)
+        return t[:, :H, :W, :].reshape(B, H * W, -1)
+
+    qp, kp, vp = padded(q), padded(k), padded(v)
+    x1 = cropped(spatial_branch(qp[..., :c2], kp[..., :c2], vp[..., :c2], Hp, Wp, split[0], split[1], s0, s1, h2, p, pre + "attns.0.", shifted).reshape(B, Hp, Wp, c2))
+    x2 = cropped(spatial_branch(qp[..., c2:], kp[..., c2:], vp[..., c2:], Hp, Wp, split[1], split[0], s1, s0, h2, p, pre + "attns.1.", shifted).reshape(B, Hp, Wp, c2))
     att = torch.cat([x1, x2], dim=2)
     conv_x = _dwconv_bn_gelu(tokens_to_image(v, (H, W)), p, pre)
     channel_map = _channel_interaction(conv_x, p, pre).permute(0, 2, 3, 1).reshape(B, 1, C)

@@ -32,7 +32,9 @@ def main() -> None:
     print(f"dat_x2: {len(man)} state_dict entries, {sum(p.numel() for p in model.parameters())} params")
 
     # whole-model outputs (64x64 native; 32x96: x_size != img_size -> masks rebuilt per forward, dat_arch.py:396-399)
-    for name, kind, seed, B, h, w in [("dat_x2_d3", "init", 1234, 1, 64, 64), ("dat_x2_d3", "stress", 4321, 1, 32, 96)]:
+    # 40x72: neither side a multiple of 32 -> projected q, k, v zero-padded to 64x96, masks of the padded size, crop (:376-407)
+    for name, kind, seed, B, h, w in [("dat_x2_d3", "init", 1234, 1, 64, 64), ("dat_x2_d3", "stress", 4321, 1, 32, 96),
+                                      ("dat_x2_d3", "stress", 77, 1, 40, 72)]:
         cfg = synth.DAT_CONFIGS[name]
         model = dat.DAT(**cfg.as_kwargs()).eval()
         model.load_state_dict(synth.make_dat_state_dict(cfg, seed=seed, kind=kind), strict=True)
@@ -50,6 +52,8 @@ def main() -> None:
     xt = synth.make_tokens(1, H, W, 180, seed=11)
     blocks = model.layers[0].blocks
     _save("kat_dat_spatial", y_unshifted=blocks[0].attn(xt, H, W)[:, ::11], y_shifted=blocks[2].attn(xt, H, W)[:, ::11])
+    xp = synth.make_tokens(2, 40, 72, 180, seed=12)
+    _save("kat_dat_spatial_padded", y_unshifted=blocks[0].attn(xp, 40, 72)[:, ::7], y_shifted=blocks[2].attn(xp, 40, 72)[:, ::7])
     _save("kat_dat_channel", y=blocks[1].attn(xt, H, W)[:, ::11])
     _save("kat_dat_sgfn", y=blocks[0].ffn(xt, H, W)[:, ::11])
     _save("kat_dat_block", y0=blocks[0](xt, (H, W))[:, ::11], y1=blocks[1](xt, (H, W))[:, ::11], y2=blocks[2](xt, (H, W))[:, ::11])

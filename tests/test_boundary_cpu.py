@@ -166,3 +166,15 @@ def test_no_cpu_fallback():
         blk(torch.zeros(1, 256, 180), (16, 16))
     with torch.no_grad(), pytest.raises(RuntimeError):
         srk.WindowAttention(96, (7, 7), 3)._packed()
+
+
+@pytest.mark.parametrize("name", sorted(__import__("tpu_superresolution_b200").synth.SWINIR_VARIANTS))
+def test_constructor_variants_keep_the_reference_state_dict(name):
+    """Upsampler / resi_connection / ape variants of network_swinir.py (646-764): same keys and shapes as the unmodified reference
+    (recorded by oracle/make_golden_variants.py), strict load of name-keyed synthetic weights."""
+    import numpy as np
+    from tpu_superresolution_b200 import synth
+    m = srk.SwinIR(**synth.SWINIR_VARIANTS[name]).eval()
+    keys = str(np.load(os.path.join(ROOT, "tests", "golden", f"swinir_variant_{name}.npz"))["keys"]).split("\n")
+    assert list(m.state_dict().keys()) == keys
+    m.load_state_dict(synth.generic_state_dict(m.state_dict(), seed=7), strict=True)

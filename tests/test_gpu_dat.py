@@ -63,7 +63,8 @@ def test_channel_attention_sgfn_block_group_kats(model):
     assert _rel(model.layers[1](xt, (64, 64))[:, ::11], _g("kat_dat_rg")["y"]) < 1e-2
 
 
-@pytest.mark.parametrize("name,kind,seed,B,h,w", [("dat_x2_d3", "init", 1234, 1, 64, 64), ("dat_x2_d3", "stress", 4321, 1, 32, 96)])
+@pytest.mark.parametrize("name,kind,seed,B,h,w", [("dat_x2_d3", "init", 1234, 1, 64, 64), ("dat_x2_d3", "stress", 4321, 1, 32, 96),
+                                                   ("dat_x2_d3", "stress", 77, 1, 40, 72)])      # 40x72: the zero-padded path
 def test_whole_model_vs_reference_golden(name, kind, seed, B, h, w):
     cfg = synth.DAT_CONFIGS[name]
     m = srk.DAT(**cfg.as_kwargs()).eval()
@@ -79,10 +80,20 @@ def test_whole_model_vs_reference_golden(name, kind, seed, B, h, w):
     assert abs(O.batch_psnr(y, hr).item() - O.batch_psnr(ref, hr).item()) <= 0.01
 
 
-def test_unsupported_geometry_is_an_error(model):
+def test_spatial_attention_padded_path(model):
+    """dat_arch.py:376-407: H, W not multiples of 32 -> the projected q, k, v are zero-padded to 64 x 96, the windows and masks are
+    those of the padded size and the result is cropped; un-shifted and shifted blocks vs the unmodified reference."""
+    xp = synth.make_tokens(2, 40, 72, 180, seed=12).cuda()
+    g = _g("kat_dat_spatial_padded")
+    blocks = model.layers[0].blocks
+    assert _rel(blocks[0].attn(xp, 40, 72)[:, ::7], g["y_unshifted"]) < 2e-2
+    assert _rel(blocks[2].attn(xp, 40, 72)[:, ::7], g["y_shifted"]) < 2e-2
+
+
+def test_wrong_token_count_is_an_error(model):
     xt = synth.make_tokens(1, 48, 64, 180, seed=1).cuda()
     with pytest.raises(RuntimeError):
-        model.layers[0].blocks[0].attn(xt, 48, 64)            # H not a multiple of 32: the padded path is not implemented
+        model.layers[0].blocks[0].attn(xt, 48, 32)
 
 
 def test_determinism(model):

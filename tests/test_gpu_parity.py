@@ -311,6 +311,23 @@ def test_layer_kernel_bit_identical_to_per_block_kernels(B, h, w):
         swinir.USE_LAYER_KERNEL = old
 
 
+@pytest.mark.parametrize("name", sorted(synth.SWINIR_VARIANTS))
+def test_constructor_variants_vs_reference_golden(name):
+    """The constructor variants beyond BASELINE's configuration (pixelshuffledirect, nearest+conv, the denoising tail, '3conv', ape,
+    x3) against outputs of the unmodified reference.  Name-keyed synthetic weights of order-one logits; outputs reach +-10, so the
+    gate is relative: 1e-2 of the output range (bf16 attention / MLP operands; these tails run on library convolutions)."""
+    m = srk.SwinIR(**synth.SWINIR_VARIANTS[name]).eval()
+    m.load_state_dict(synth.generic_state_dict(m.state_dict(), seed=7), strict=True)
+    m.cuda()
+    lr = synth.make_lr_batch(2, 16, 16, seed=21)
+    before = L.launch_count()
+    y = m(lr.cuda()).cpu()
+    assert L.launch_count() > before
+    ref = torch.from_numpy(np.load(os.path.join(GOLDEN, f"swinir_variant_{name}.npz"))["y"])
+    assert y.shape == ref.shape
+    assert _rel(y, ref) < 1e-2
+
+
 def test_pipelined_runner_matches_direct_forward():
     """srk.PipelinedRunner (host-to-host loop with the D2H copy on a side stream) returns exactly the model's outputs, in order."""
     cfg = synth.CONFIGS["swinir_x2_d2"]
@@ -323,7 +340,9 @@ def test_pipelined_runner_matches_direct_forward():
     pr = srk.PipelinedRunner(srk.GraphedModel(m), depth=2)
     outs = [torch.empty_like(refs[0]).pin_memory() for _ in xs]
     for x, o in zip(xs, outs):
-        pr.submit(x, o)
+        ev = pr.submit(x, o)
+        assert ev is not None           # host input: the event after which the pinned buffer may be refilled
+        ev.synchronize()
     pr.drain()
     torch.cuda.synchronize()
     for o, r in zip(outs, refs):

@@ -64,7 +64,18 @@ def test_modules(stress):
     assert _err(DO.residual_group(xt, (H, W), sd, "layers.1.", 2, 6, cfg.split_size, 1)[:, ::11], _g("kat_dat_rg")["y"]) < 1e-4
 
 
-@pytest.mark.parametrize("name,kind,seed,B,h,w", [("dat_x2_d3", "init", 1234, 1, 64, 64), ("dat_x2_d3", "stress", 4321, 1, 32, 96)])
+def test_spatial_attention_padded(stress):
+    """dat_arch.py:376-407: H, W not multiples of 32 -> projected q, k, v zero-padded, masks of the padded size, crop."""
+    cfg, sd = stress
+    xp = synth.make_tokens(2, 40, 72, 180, seed=12)
+    g = _g("kat_dat_spatial_padded")
+    y0 = DO.adaptive_spatial_attention(xp, 40, 72, sd, "layers.0.blocks.0.attn.", 6, cfg.split_size, False)
+    y2 = DO.adaptive_spatial_attention(xp, 40, 72, sd, "layers.0.blocks.2.attn.", 6, cfg.split_size, True)
+    assert _err(y0[:, ::7], g["y_unshifted"]) < TOL and _err(y2[:, ::7], g["y_shifted"]) < TOL
+
+
+@pytest.mark.parametrize("name,kind,seed,B,h,w", [("dat_x2_d3", "init", 1234, 1, 64, 64), ("dat_x2_d3", "stress", 4321, 1, 32, 96),
+                                                   ("dat_x2_d3", "stress", 77, 1, 40, 72)])
 def test_whole_model(name, kind, seed, B, h, w):
     cfg = synth.DAT_CONFIGS[name]
     sd = synth.make_dat_state_dict(cfg, seed=seed, kind=kind)

@@ -307,34 +307,74 @@ class Adaptive_Spatial_Attention(_AIM):
         B, Ltok, C = x.shape
         if Ltok != H * W:
             raise RuntimeError("flatten img_tokens has wrong size")
-        if H % 32 or W % 32:
-            raise RuntimeError(f"Adaptive_Spatial_Attention: H, W ({H}, {W}) must be multiples of 32 (the padded case of "
-                               "dat_arch.py:376-385 is not implemented)")
         if self.training:
             raise RuntimeError("Adaptive_Spatial_Attention: eval mode required (BatchNorm running statistics)")
         tokens = B * Ltok
         (qw, qb), (vw, vb), (pw, pb), t0, t1 = self._packed(norm)
         ln = norm is not None
-        planes = torch.empty((12, tokens, 64), dtype=torch.bfloat16, device=x.device)
         # 32x8 windows shifted by 4 columns start 4 pixels off a multiple of 8: their planes use the (tok + 4) & 7 row phase
         phase = sum(1 << p for p in (2, 3, 6, 7, 10, 11)) if self.shifted else 0
-        L.linear(x, qw, qb, planes, num_tokens=tokens, a_mode=L.LIN_A_ROWS, ld_in=C, apply_ln=ln, n_chunks=4,
-                 out_mode=L.LIN_OUT_PLANES, plane_phase_mask=phase)
+        Hp, Wp = H + (-H) % 32, W + (-W) % 32
+        padded = (Hp, Wp) != (H, W)
+        if padded:
+            # dat_arch.py:376-385: the PROJECTED q, k, v are zero-padded to a multiple of 32 (the qkv bias is not re-added on the pad),
+            # the windows / masks are those of the padded size (:396-399) and the result is cropped (:406-407).  Here: the token rows are
+            # embedded in a padded (B, Hp, Wp) grid, the qkv GEMM runs on that grid, and the plane rows of the pad tokens are then
+            # overwritten with the pad pattern (q = k = 0; v = 0 with the ones column that carries the softmax row sum).
+            xg = torch.zeros((B, Hp, Wp, C), dtype=torch.float32, device=x.device)
+            xg[:, :H, :W] = x.view(B, H, W, C)
+            tok_p = B * Hp * Wp
+            planes = torch.empty((12, tok_p, 64), dtype=torch.bfloat16, device=x.device)
+            L.linear(xg, qw, qb, planes, num_tokens=tok_p, a_mode=L.LIN_A_ROWS, ld_in=C, apply_ln=ln, n_chunks=4,
+                     out_mode=L.LIN_OUT_PLANES, plane_phase_mask=phase)
+            pad_idx, patt = self._pad_tables(B, H, W, Hp, Wp, phase, x.device)
+            planes[0:8, pad_idx] = 0
+            for j in range(4):
+                planes[8 + j, pad_idx] = patt[j]
+            att_p = torch.empty((B, Hp * Wp, C), dtype=torch.float32, device=x.device)
+        else:
+            planes = torch.empty((12, tokens, 64), dtype=torch.bfloat16, device=x.device)
+            L.linear(x, qw, qb, planes, num_tokens=tokens, a_mode=L.LIN_A_ROWS, ld_in=C, apply_ln=ln, n_chunks=4,
+                     out_mode=L.LIN_OUT_PLANES, plane_phase_mask=phase)
+            att_p = torch.empty((B, Ltok, C), dtype=torch.float32, device=x.device)
         v_rows = torch.empty((B, Ltok, C), dtype=torch.float32, device=x.device)
         L.linear(x, vw, vb, v_rows, num_tokens=tokens, a_mode=L.LIN_A_ROWS, ld_in=C, apply_ln=ln, n_chunks=1,
                  out_mode=L.LIN_OUT_ROWS, ld_out=C)
-        att = torch.empty((B, Ltok, C), dtype=torch.float32, device=x.device)
         s0, s1 = self.shift_size
         for i, (kind, tab, shift) in enumerate(((L.WA_DAT_8x32, t0, (s0, s1)), (L.WA_DAT_32x8, t1, (s1, s0)))):
-            L.window_attention(planes[2 * i:2 * i + 2], planes[4 + 2 * i:6 + 2 * i], planes[8 + 2 * i:10 + 2 * i], tab, att, kind=kind,
-                               batch=B, height=H, width=W, shift=shift if self.shifted else (0, 0), mask_shift=self.shifted,
+            L.window_attention(planes[2 * i:2 * i + 2], planes[4 + 2 * i:6 + 2 * i], planes[8 + 2 * i:10 + 2 * i], tab, att_p, kind=kind,
+                               batch=B, height=Hp, width=Wp, shift=shift if self.shifted else (0, 0), mask_shift=self.shifted,
                                n_heads=3, out_mode=1, out_ld=C, out_col0=(C // 2) * i)
+        att = att_p.view(B, Hp, Wp, C)[:, :H, :W].reshape(B, Ltok, C) if padded else att_p
         # convolution branch + adaptive interaction module (dat_arch.py:418-431)
         conv_x = self._conv_branch(v_rows, C, 0, B, H, W)
         mix = self._mix(att, conv_x, self._channel_map(conv_x), 0)
         L.linear(mix, pw, pb, out, num_tokens=tokens, a_mode=L.LIN_A_ROWS, ld_in=C, apply_ln=False, n_chunks=1,
                  out_mode=L.LIN_OUT_ROWS, ld_out=C, add_residual=add_residual)
         return out
+
+    def _pad_tables(self, B, H, W, Hp, Wp, phase_mask, device):
+        """Indices of the pad tokens in the padded (B, Hp, Wp) grid and, per v plane, their rows: zeros with bf16 1.0 in the ones
+        column (padded dim 30) of every real head slot, 16-byte chunks permuted by chunk ^ ((token + phase) & 7) like the planes."""
+        key = (B, H, W, Hp, Wp, phase_mask, str(device))
+        cache = self.__dict__.setdefault("_pad_cache", {})
+        if key not in cache:
+            yy, xx = torch.meshgrid(torch.arange(Hp), torch.arange(Wp), indexing="ij")
+            pad = ((yy >= H) | (xx >= W)).reshape(-1).nonzero().reshape(-1)
+            idx = (torch.arange(B)[:, None] * (Hp * Wp) + pad[None, :]).reshape(-1)
+            patt = []
+            for j in range(4):                                   # v planes 8..11: head slots (0, 1) (2, -) (3, 4) (5, -)
+                row = torch.zeros(64, dtype=torch.bfloat16)
+                row[L.HEAD_DIM] = 1.0
+                if j % 2 == 0:
+                    row[L.HEAD_PAD + L.HEAD_DIM] = 1.0
+                ph = 4 if (phase_mask >> (8 + j)) & 1 else 0
+                keyr = (idx + ph) & 7
+                chunk = (torch.arange(8)[None, :] ^ keyr[:, None])                     # stored chunk position c holds logical chunk c ^ key
+                rows = row.view(8, 8)[chunk.reshape(-1)].reshape(idx.numel(), 64)
+                patt.append(rows.to(device))
+            cache[key] = (idx.to(device), patt)
+        return cache[key]
 
     def forward(self, x, H, W):
         x = x.contiguous()

@@ -26,6 +26,7 @@ class GraphedModel(nn.Module):
         self.model = model
         self.warmup = warmup
         self._graphs: Dict[Tuple, Tuple[torch.cuda.CUDAGraph, torch.Tensor, torch.Tensor]] = {}
+        self.h2d_done = None            # event recorded after the last host -> device input copy (None: the last input was on the device)
 
     def reset(self) -> None:
         self._graphs.clear()
@@ -56,7 +57,11 @@ class GraphedModel(nn.Module):
             entry = self._capture(x.to(dev))
             self._graphs[key] = entry
         graph, static_in, static_out = entry
-        static_in.copy_(x, non_blocking=True)
+        static_in.copy_(x, non_blocking=True)       # any strides / memory format of x: copy_ converts into the captured buffer's layout
+        if not x.is_cuda:
+            # a pinned host source is read asynchronously: it may be refilled only after this event (PipelinedRunner.submit returns it)
+            self.h2d_done = torch.cuda.Event()
+            self.h2d_done.record(torch.cuda.current_stream(dev))
         graph.replay()
         return static_out
 
@@ -79,8 +84,12 @@ class PipelinedRunner:
         self._i = 0
 
     @torch.no_grad()
-    def submit(self, host_in: torch.Tensor, host_out: torch.Tensor) -> None:
+    def submit(self, host_in: torch.Tensor, host_out: torch.Tensor):
+        """Returns the event after which `host_in` has been read (None for a device input): a serving loop that reuses one pinned
+        input buffer must `event.synchronize()` before refilling it -- the H2D copy is asynchronous, and only the D2H side is
+        covered by `drain()`.  (Rotating `depth + 1` input buffers, as bench.py does, needs no wait.)"""
         y = self.graphed(host_in)                                   # H2D into the static input + replay, current stream
+        h2d_done = self.graphed.h2d_done if not host_in.is_cuda else None
         cur = torch.cuda.current_stream(y.device)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=y.device)
@@ -99,6 +108,7 @@ class PipelinedRunner:
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
             self._done[b] = ev
+        return h2d_done
 
     def drain(self) -> None:
         """Make the current stream wait for every copy in flight (then synchronise the stream / an event as usual)."""

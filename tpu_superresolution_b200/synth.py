@@ -447,3 +447,44 @@ def _hat_configs():
 
 HAT_CONFIGS = _hat_configs()
 DAT_CONFIGS = _dat_configs()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# generic synthetic weights for the constructor variants (upsamplers, '3conv', ape): keyed by parameter NAME, so the
+# reference model and the drop-in model get the same tensors whatever their registration order
+# ---------------------------------------------------------------------------------------------------------------
+VARIANT_KW = dict(img_size=16, window_size=8, img_range=1.0, depths=[2], embed_dim=180, num_heads=[6], mlp_ratio=2.0, in_chans=3)
+SWINIR_VARIANTS = {
+    "pixelshuffledirect_x2": dict(VARIANT_KW, upscale=2, upsampler="pixelshuffledirect", resi_connection="1conv"),
+    "nearestconv_x4": dict(VARIANT_KW, upscale=4, upsampler="nearest+conv", resi_connection="1conv"),
+    "denoise_x1": dict(VARIANT_KW, upscale=1, upsampler="", resi_connection="1conv"),
+    "pixelshuffle_3conv_x2": dict(VARIANT_KW, upscale=2, upsampler="pixelshuffle", resi_connection="3conv"),
+    "pixelshuffle_ape_x2": dict(VARIANT_KW, upscale=2, upsampler="pixelshuffle", resi_connection="1conv", ape=True),
+    "pixelshuffle_x3": dict(VARIANT_KW, upscale=3, upsampler="pixelshuffle", resi_connection="1conv"),
+}
+
+
+def generic_state_dict(template: Dict[str, torch.Tensor], seed: int = 7) -> Dict[str, torch.Tensor]:
+    """Fill every floating-point PARAMETER of `template` (a model's state_dict) from a numpy RNG seeded by (seed, key name):
+    weights ~ N(0, 0.06) (attention logits of order one), biases ~ N(0, 0.05), norm weights 1 + N(0, 0.1), bias tables ~ N(0, 0.5).
+    Integer buffers and masks (relative_position_index, attn_mask) keep the template's values."""
+    import zlib
+    out = {}
+    for k, v in template.items():
+        if not v.is_floating_point() or k.endswith("attn_mask"):
+            out[k] = v.clone()
+            continue
+        rng = np.random.default_rng([seed, zlib.crc32(k.encode())])
+        if "relative_position_bias_table" in k:
+            a = rng.normal(0, 0.5, size=tuple(v.shape))
+        elif "absolute_pos_embed" in k:
+            a = rng.normal(0, 0.1, size=tuple(v.shape))
+        elif "norm" in k and k.endswith("weight"):
+            a = 1.0 + rng.normal(0, 0.1, size=tuple(v.shape))
+        elif k.endswith("bias"):
+            a = rng.normal(0, 0.05, size=tuple(v.shape))
+        else:
+            fan_in = int(np.prod(v.shape[1:])) if v.dim() > 1 else int(v.shape[0])
+            a = rng.normal(0, min(0.06, 1.5 / np.sqrt(fan_in)), size=tuple(v.shape))
+        out[k] = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    return out
