@@ -10,7 +10,7 @@ W = bench.WORKLOADS[name]
 from tpu_superresolution_b200 import synth
 torch.backends.cudnn.allow_tf32 = True
 torch.backends.cudnn.benchmark = True
-cfg, sd, cls, _ = bench._build(W["family"], W["cfg"])
+cfg, sd, cls = bench._build(W["family"], W["cfg"])
 m = cls(**cfg.as_kwargs()).eval()
 m.load_state_dict(sd, strict=True)
 m.cuda()
