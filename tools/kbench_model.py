@@ -11,7 +11,7 @@ torch.backends.cudnn.allow_tf32 = True
 torch.backends.cudnn.benchmark = True
 name = sys.argv[1] if len(sys.argv) > 1 else "dat_x2"
 W = bench.WORKLOADS[name]
-cfg, sd, cls, _ = bench._build(W["family"], W["cfg"])
+cfg, sd, cls = bench._build(W["family"], W["cfg"])
 m = cls(**cfg.as_kwargs()).eval()
 m.load_state_dict(sd, strict=True)
 m.cuda()
