@@ -55,4 +55,5 @@ for k in range(len(st) - 1):
     ph0, ph1 = (k * G) // (B * 32), ((k + 1) * G) // (B * 32)
     line.append(f"{st[k + 1] - st[k]}{' |' if ph1 != ph0 else ''}")
 print(" ".join(line))
-print(f"total {st[-1] - st[0]} cycles over {len(st) - 1} items")
+if len(st) > 1:
+    print(f"total {st[-1] - st[0]} cycles over {len(st) - 1} items")

@@ -1107,7 +1107,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_layer_kernel(const LayerPa
         const int row = q * 32 + lane;
         const uint32_t lanebase = static_cast<uint32_t>(q * 32) << 16;
         const uint32_t xa = sbase + A_XA, qki = sbase + A_QKI;
-        uint32_t ph_qkf[2] = {0, 0};
+        uint32_t ph_qkf[2] = {0, 0}, ph_drain = 0;
         TileGeom geo;
         AttnParams pa{};
         int n = 0, blk_a = 0, blk_m = 0;            // blocks whose constants are in s_veca / s_vecm
@@ -1116,8 +1116,10 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_layer_kernel(const LayerPa
             const bool has_next = i + G < p.n_items;
             const LayerItem nx = layer_item(p, has_next ? i + G : i);
             if (it.type == 0) {
-                // the previous item's output rows (staged over the V^T / q|k images) have left shared memory: phase n - 1 of B_DRAIN
-                if (n > 0) mbar_wait(&bars[B_DRAIN], static_cast<uint32_t>((n - 1) & 1));
+                // the previous item's output rows (staged over the V^T / q|k images) have left shared memory.  B_DRAIN completes once per
+                // item transition (`drain` of the row warps); every phase is consumed in order (attention items: here, MLP items: at
+                // their end), so a parity wait can never be two phases ahead of the barrier
+                if (n > 0) { mbar_wait(&bars[B_DRAIN], ph_drain); ph_drain ^= 1; }
 #pragma unroll 1
                 for (int h = 0; h < 6; ++h) {
                     mbar_wait(&bars[B_QKF0 + (h & 1)], ph_qkf[h & 1]); ph_qkf[h & 1] ^= 1;
@@ -1164,6 +1166,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_layer_kernel(const LayerPa
                 fence_proxy_async_smem();
                 mbar_arrive(&bars[B_XA]);
             }
+            if (it.type == 1 && n > 0) { mbar_wait(&bars[B_DRAIN], ph_drain); ph_drain ^= 1; }
         }
     } else {
         // ===================================================== 256 row threads (two groups)
@@ -1220,6 +1223,21 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_layer_kernel(const LayerPa
         // depend on this very item -- or there is none
         int* pend_ctr = nullptr;
         int pend_add = 0;
+        // The previous item's bulk copies may still read the staging region (V^T + q|k images + tail).  They are waited for lazily, right
+        // before the region is written again -- the V epilogue of an attention item, the second GELU chunk of an MLP item (by then the
+        // copies, 2.5 - 4 K cycles, are long done; not later: the utility warps count B_DRAIN phases item by item) -- instead of at the
+        // end of the item, where the wait was exposed (an MLP item: 3 K of 17.5 K cycles).
+        bool drain_pending = false;
+        auto drain = [&]() {
+            if (drain_pending) {
+                if (g == 0) {
+                    bulk_wait_read0();
+                    mbar_arrive(&bars[B_DRAIN]);        // -> utility warps (q|k images of the next attention item)
+                }
+                named_bar_sync(1, NROWTHREADS);         // -> both groups
+                drain_pending = false;
+            }
+        };
         auto flush_signal = [&]() {
             if (pend_ctr != nullptr) { signal_progress(pend_ctr, pend_add); pend_ctr = nullptr; }
         };
@@ -1231,6 +1249,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_layer_kernel(const LayerPa
             const bool has_next = i + G < p.n_items;
             const LayerItem nx = layer_item(p, has_next ? i + G : i);
             SRK_TL(dbg, n, 0);
+            if (dbg != nullptr && blockIdx.x == 0 && n == 0) dbg[1024] = clock64();
             if (it.type == 0) {
                 // ------------------------------------------------------------------ attention item (swin_attn_kernel's row loop)
                 layer_attn_params(p, it, pa);
@@ -1240,6 +1259,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_layer_kernel(const LayerPa
                 auto tok_of_row = [&](int r) -> int64_t { return tile_tok(pa, geo, r); };
                 mbar_wait(&bars[B_VTF], ph_vtf); ph_vtf ^= 1;
                 tc_fence_after();
+                drain();                                 // the V image is written over the previous item's staged rows
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const int d0 = 96 * g + 32 * c;
@@ -1349,6 +1369,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_layer_kernel(const LayerPa
                     }
                     tc_fence_before();
                     mbar_arrive(&bars[LB_HR0 + c]);
+                    if (c == 1) drain();
                 }
                 if (g == 0) flush_signal();
                 if (has_next && nx.type == 0) prep(nx, nxt);
@@ -1358,16 +1379,13 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_layer_kernel(const LayerPa
                 tc_fence_before();
                 if (g == 0) { pend_ctr = p.progress + p.B + tile / p.tiles_per_image; pend_add = 1; }
             }
-            // the copies drain while the next item's first GEMMs run; nobody may write the V^T / q|k regions before that
-            if (g == 0) {
-                bulk_wait_read0();
-                mbar_arrive(&bars[B_DRAIN]);            // -> utility warps (q|k images of the next attention item)
-            }
-            named_bar_sync(1, NROWTHREADS);             // -> both groups (V^T image / store staging of the next item)
+            drain_pending = true;                       // (see `drain`)
             // no next item, or the next item of this CTA is in another phase (it may depend on this very item): report now
             if (g == 0 && (!has_next || (i + G) / p.T != i / p.T)) flush_signal();
             SRK_TL(dbg, n, 63);
+            if (dbg != nullptr && blockIdx.x == 0 && n < 127) dbg[1025 + n] = clock64();      // (tools/timeline_layer.py allocates 2048 entries)
         }
+        if (g == 0) bulk_wait_read0();      // shared memory must outlive the bulk copies that read it
     }
     tc_fence_before();
     __syncthreads();
