@@ -716,24 +716,35 @@ __global__ void __launch_bounds__(LNW ? NTHREADS : 320, 1) swin_mlp_kernel(const
             auto fc2_chunk = [&](uint32_t buf, bool first) {    // K = 128 hidden units of one chunk: A = H (TMEM), B = two W2 slabs
                 cur = k2_fc2_chunk(bars, ring, cur, tmem + TC_F2, tmem + (buf ? TC_F1B : TC_F1A), first ? 1u : 0u);
             };
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            unsigned long long* mdbg = lane == 0 ? p.dbg : nullptr;
+            int mit = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++mit) {
+                SRK_TL(mdbg, mit, 32);
                 mbar_wait(&bars[MB_XA], ph_xa); ph_xa ^= 1;
                 tc_fence_after();
+                SRK_TL(mdbg, mit, 33);
                 const uint32_t b0 = nchunk & 1;
                 fc1_chunk();                                                   // chunk 0 -> buffer b0
                 fc1_chunk();                                                   // chunk 1 -> buffer b0 ^ 1
+                SRK_TL(mdbg, mit, 34);
                 mbar_wait(&bars[MB_HR0], ph_hr[0]); ph_hr[0] ^= 1;             // H of chunk 0 written over its accumulators
                 tc_fence_after();
+                SRK_TL(mdbg, mit, 35);
                 fc2_chunk(b0, true);
                 fc1_chunk();                                                   // chunk 2 -> buffer b0 (after fc2 consumed H of chunk 0)
                 umma_commit_w(&bars[MB_XAFREE]);                               // all fc1 GEMMs issued: the x image is free once they complete
+                SRK_TL(mdbg, mit, 36);
                 mbar_wait(&bars[MB_HR1], ph_hr[1]); ph_hr[1] ^= 1;
                 tc_fence_after();
+                SRK_TL(mdbg, mit, 37);
                 fc2_chunk(b0 ^ 1, false);
+                SRK_TL(mdbg, mit, 38);
                 mbar_wait(&bars[MB_HR2], ph_hr[2]); ph_hr[2] ^= 1;
                 tc_fence_after();
+                SRK_TL(mdbg, mit, 39);
                 fc2_chunk(b0, false);
                 umma_commit_w(&bars[MB_F2]);
+                SRK_TL(mdbg, mit, 40);
             }
         }
         __syncwarp();
@@ -1019,10 +1030,14 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_layer_kernel(const LayerPa
                 umma_ts_w4<128>(tmem + TC_O + 32 * h + w * LANE16, pcol + w * LANE16,
                                 umma_desc_sw128(vt + (h >> 1) * ATOM_A + w * 8192 + (h & 1) * 64), IDESC_64x32_BMN, 0);
         };
-        for (int i = first; i < p.n_items; i += G) {
+        unsigned long long* mdbg = lane == 0 ? p.dbg : nullptr;
+        int mit = 0;
+        for (int i = first; i < p.n_items; i += G, ++mit) {
             const LayerItem it = layer_item(p, i);
+            SRK_TL(mdbg, mit, 32);
             mbar_wait(&bars[B_XA], ph_xa); ph_xa ^= 1;
             tc_fence_after();
+            SRK_TL(mdbg, mit, 33);
             if (it.type == 0) {
                 gemm_k192(tmem + TC_V, xa, true, IDESC_128x192);
                 umma_commit_w(&bars[B_VTF]);
@@ -1060,18 +1075,25 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_layer_kernel(const LayerPa
                 };
                 fc1();                                                           // chunk 0 -> buffer b0
                 fc1();                                                           // chunk 1 -> buffer b0 ^ 1
+                SRK_TL(mdbg, mit, 34);
                 mbar_wait(&bars[LB_HR0], ph_hr[0]); ph_hr[0] ^= 1;               // H of chunk 0 written over its accumulators;
                 tc_fence_after();                                                // (the row warps are past the previous item: columns [0,192) are free)
+                SRK_TL(mdbg, mit, 35);
                 cur = kl_fc2_chunk(bars, ring, cur, tmem + TL_F2, f1buf(b0), 1u);
                 fc1();                                                           // chunk 2 -> buffer b0
                 umma_commit_w(&bars[B_XAFREE]);                                  // all fc1 GEMMs issued: the x image is free once they complete
+                SRK_TL(mdbg, mit, 36);
                 mbar_wait(&bars[LB_HR1], ph_hr[1]); ph_hr[1] ^= 1;
                 tc_fence_after();
+                SRK_TL(mdbg, mit, 37);
                 cur = kl_fc2_chunk(bars, ring, cur, tmem + TL_F2, f1buf(b0 ^ 1), 0u);
+                SRK_TL(mdbg, mit, 38);
                 mbar_wait(&bars[LB_HR2], ph_hr[2]); ph_hr[2] ^= 1;
                 tc_fence_after();
+                SRK_TL(mdbg, mit, 39);
                 cur = kl_fc2_chunk(bars, ring, cur, tmem + TL_F2, f1buf(b0), 0u);
                 umma_commit_w(&bars[LB_F2]);
+                SRK_TL(mdbg, mit, 40);
             }
         }
         __syncwarp();
@@ -1344,6 +1366,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_layer_kernel(const LayerPa
                     ++nchunk;
                     mbar_wait(&bars[buf ? LB_F1B : LB_F1A], ph_f1[buf]); ph_f1[buf] ^= 1;
                     tc_fence_after();
+                    SRK_TL(dbg, n, 1 + 2 * c);
                     {
                         const uint32_t col = (buf ? TL_F1B : TL_F1A) + 64 * g;
                         uint32_t v0[32], v1[32];
@@ -1369,14 +1392,17 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_layer_kernel(const LayerPa
                     }
                     tc_fence_before();
                     mbar_arrive(&bars[LB_HR0 + c]);
+                    SRK_TL(dbg, n, 2 + 2 * c);
                     if (c == 1) drain();
                 }
                 if (g == 0) flush_signal();
                 if (has_next && nx.type == 0) prep(nx, nxt);
                 mbar_wait(&bars[LB_F2], ph_f2); ph_f2 ^= 1;
                 tc_fence_after();
+                SRK_TL(dbg, n, 8);
                 stage_rows_and_bulk_store(tmem + TL_F2, lanebase, sm + A_VT, sm + L_TAIL, 28, s_vecm + SRK_MV_B2, p.y, p.ld, 1, q, g, lane, tok_of_row);
                 tc_fence_before();
+                SRK_TL(dbg, n, 9);
                 if (g == 0) { pend_ctr = p.progress + p.B + tile / p.tiles_per_image; pend_add = 1; }
             }
             drain_pending = true;                       // (see `drain`)
