@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SRK_ABI_VERSION 1
+#define SRK_ABI_VERSION 2
 
 /* Fixed geometry of the SwinIR/HAT/DAT "M" family served by these kernels. */
 #define SRK_DIM 180        /* embed_dim                      (finetune_swinir.py:276) */
@@ -58,6 +58,11 @@ extern "C" {
  * with mode = SRK_MODE_WINDOWS, network_swinir.py:114-145 (WindowAttention.forward). */
 enum { SRK_MODE_IMAGE = 0, SRK_MODE_WINDOWS = 1 };
 enum { SRK_MASK_NONE = 0, SRK_MASK_SHIFT = 1, SRK_MASK_EXPLICIT = 2 };
+/* GEMM operand type of the fused Swin kernels.  BF16: the default path (gate: max abs <= 2e-3 on [0,1] pixels, measured 1.6 - 4.4e-4).
+ * F16: the "tight" mode -- operand images and packed weights in fp16, which has TF32's 11-bit significand (gate <= 2e-4); every
+ * GEMM input of these kernels is LayerNorm output, a softmax probability or a projection of those, so fp16's range is safe.
+ * The weight stream must have been packed for the same type (packing.py: operands=...). */
+enum { SRK_OPERANDS_BF16 = 0, SRK_OPERANDS_F16 = 1 };
 
 typedef struct SrkSwinAttnDesc {
     int32_t mode;          /* SRK_MODE_IMAGE: x is (batch, height*width, ld); SRK_MODE_WINDOWS: x is (num_windows, 64, ld) */
@@ -70,6 +75,7 @@ typedef struct SrkSwinAttnDesc {
     int32_t add_residual;  /* 1: y = x + attn (network_swinir.py:276); 0: y = attn */
     int32_t mask_mode;     /* SRK_MASK_SHIFT: closed form of calculate_mask (network_swinir.py:216-237) */
     int32_t mask_nw;       /* SRK_MASK_EXPLICIT: mask is (mask_nw, 64, 64) fp32, window w uses mask[w % mask_nw] */
+    int32_t operands;      /* SRK_OPERANDS_BF16 / SRK_OPERANDS_F16 */
 } SrkSwinAttnDesc;
 
 int srk_swin_attn_fwd(const SrkSwinAttnDesc* desc, const float* x, float* y, const void* wstream /* SRK_ATTN_WSTREAM_BYTES */,
@@ -81,6 +87,7 @@ typedef struct SrkMlpDesc {
     int32_t ld_in, ld_out;
     int32_t apply_ln;      /* 1: LayerNorm first */
     int32_t add_residual;  /* 1: y = x + mlp(LN(x)); 0: y = mlp(LN(x)) */
+    int32_t operands;      /* SRK_OPERANDS_BF16 / SRK_OPERANDS_F16 */
 } SrkMlpDesc;
 
 int srk_swin_mlp_fwd(const SrkMlpDesc* desc, const float* x, float* y, const void* wstream /* SRK_MLP_WSTREAM_BYTES */,
@@ -320,7 +327,7 @@ int srk_abi_version(void);
 const char* srk_last_error_string(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t srk_launch_count(void);
-/* debug: device buffer of >= 512 uint64 receiving CTA 0's clock64() timeline of later launches (NULL = off) */
+/* debug: device buffer of >= 2048 uint64 receiving CTA 0's clock64() timeline of later launches (NULL = off) */
 void srk_debug_set_timeline(void* device_buf);
 /* tuning: start skew (cycles per CTA index mod 4) of the attention / MLP kernels, see stagger_start() */
 void srk_debug_set_stagger(int attn_cycles, int mlp_cycles);

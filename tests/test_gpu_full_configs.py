@@ -71,6 +71,34 @@ def test_full_depth_vs_reference_golden(name, kind, seed):
     assert _dpsnr(y, ref, lr, cfg.upscale) <= 0.01
 
 
+@pytest.mark.parametrize("cfg_name", ["swinir_x2", "swinir_x4"])
+@pytest.mark.parametrize("kind,seed", [("init", 1234), ("stress", 4321)])
+def test_tight_mode_fp16_operands_vs_reference_golden(cfg_name, kind, seed):
+    """north star: "tighter for a TF32 mode".  set_precision("fp16"): operand images and weights of the fused attention / MLP
+    kernels in fp16 (TF32's 11-bit significand), everything else unchanged.  BASELINE configs[0] (SwinIR x2, 1x3x64x64) and the x4
+    model at full depth against the unmodified reference's fp32 output; gate max abs <= 2e-4, and the result must be
+    closer to the reference than the bf16 path's."""
+    cfg = synth.CONFIGS[cfg_name]
+    sd = synth.make_swinir_state_dict(cfg, seed=seed, kind=kind)
+    m = srk.SwinIR(**cfg.as_kwargs()).eval()
+    m.load_state_dict(sd, strict=True)
+    m.cuda()
+    lr = synth.make_lr_batch(1, 64, 64, seed=seed + 1)
+    ref = torch.from_numpy(np.load(os.path.join(GOLDEN, f"{cfg_name}_{kind}_1x64x64.npz"))["y"])
+    err_bf16 = (m(lr.cuda()).cpu() - ref).abs().max().item()
+    m.set_precision("fp16")
+    before = L.launch_count()
+    y = m(lr.cuda()).cpu()
+    assert L.launch_count() > before
+    err = (y - ref).abs().max().item()
+    print(f"{cfg_name} {kind}: full depth max|cuda - reference|: fp16 operands {err:.3e}, bf16 operands {err_bf16:.3e}")
+    assert err <= 2e-4
+    assert err < err_bf16
+    assert _dpsnr(y, ref, lr, cfg.upscale) <= 0.001
+    m.set_precision("bf16")
+    assert abs((m(lr.cuda()).cpu() - ref).abs().max().item() - err_bf16) == 0.0      # switching back repacks
+
+
 @pytest.mark.parametrize("name", ["hat_x4", "dat_x2"])
 def test_baseline_config_batch_vs_oracle_sample(name):
     """configs[2] (HAT x4, B = 8) and configs[3] (DAT x2, B = 16) at full depth, like

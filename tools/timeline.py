@@ -19,7 +19,7 @@ y = torch.empty_like(x)
 for _ in range(3):
     blk.forward_into(x, (64, 64), y)
 lib = L.load()
-buf = torch.zeros(512, dtype=torch.int64, device="cuda")
+buf = torch.zeros(2048, dtype=torch.int64, device="cuda")
 aw, av = blk.attn._packed(blk.norm1)
 mw, mv = blk.mlp._packed(blk.norm2)
 names1 = {0: "tile start", 2: "VTF seen", 3: "VT epi done", 23: "OF seen", 24: "O epi done", 25: "LN(next) done", 26: "PJF seen",
@@ -42,7 +42,21 @@ for which, names in (("attn", names1), ("mlp", names2)):
         L.swin_mlp(y, y, mw, mv, num_tokens=16 * 4096, ld_in=180, ld_out=180)
     torch.cuda.synchronize()
     lib.srk_debug_set_timeline(0)
-    t = buf.cpu().view(8, 64)
+    t = buf.cpu()[:512].view(8, 64)
+    if which == "attn":
+        w = buf.cpu()[1600:1700].tolist()
+        if w[8]:
+            nt = max(w[9], 1)
+            print(f"--- attn CTA0 wait profile (cycles per tile, averaged over {w[9]} tiles incl. the first)")
+            lab = ["wait XA", "GEMM issue (V, q|k, proj: incl. weight-slab waits)", "wait VTD", "wait QKA/QKB free", "wait OALL"]
+            print("  GEMM issuer : loop %d | " % (w[8] // nt) + ", ".join(f"{lab[c]} {w[c] // nt}" for c in range(5)))
+            lab = ["wait VTD", "wait QKR (6)", "wait PR (6)", "wait OR (2)", "issue S (6)", "issue PV (6)"]
+            print("  attn issuer : loop %d | " % (w[88] // nt) + ", ".join(f"{lab[c]} {w[80 + c] // nt}" for c in range(6)))
+            lab = ["wait VTF", "wait SF (3)", "wait OF (3)", "wait PJF", "store drain + bar"]
+            for name, o in (("group 0     ", 20), ("group 1     ", 40)):
+                print(f"  {name}: loop %d | " % (w[o + 8] // nt) + ", ".join(f"{lab[c]} {w[o + c] // nt}" for c in range(5)))
+            lab = ["wait DRAIN", "wait QKF (3)", "wait SF (6)", "LN next tile"]
+            print("  utility     : loop %d | " % (w[68] // nt) + ", ".join(f"{lab[c]} {w[60 + c] // nt}" for c in range(4)))
     for it in range(4):
         ev = sorted((int(t[it, i]), i) for i in names if int(t[it, i]) != 0)
         if not ev:

@@ -18,12 +18,12 @@ run = lambda: L.conv3x3(x16, ws, bp, out, batch=B, height=H, width=W, k_atoms=me
 for _ in range(3):
     run()
 torch.cuda.synchronize()
-buf = torch.zeros(512, dtype=torch.int64, device="cuda")
+buf = torch.zeros(2048, dtype=torch.int64, device="cuda")
 lib.srk_debug_set_timeline(buf.data_ptr())
 run()
 torch.cuda.synchronize()
 lib.srk_debug_set_timeline(0)
-t = buf.cpu().view(8, 64)
+t = buf.cpu()[:512].view(8, 64)
 base = int(t[0, 0])
 for it in range(4):
     if int(t[it, 0]) == 0:

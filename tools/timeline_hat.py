@@ -38,12 +38,12 @@ for st in (0, 1500, 3000, 4000, 5000, 7000):
     e1.record(); torch.cuda.synchronize()
     print(f"kind={kind} shift={shift} stagger={st}: {e0.elapsed_time(e1) / 10 * 1e3:.1f} us per launch")
 lib.srk_debug_set_winattn_stagger(4000)
-buf = torch.zeros(512, dtype=torch.int64, device="cuda")
+buf = torch.zeros(2048, dtype=torch.int64, device="cuda")
 lib.srk_debug_set_timeline(buf.data_ptr())
 run()
 torch.cuda.synchronize()
 lib.srk_debug_set_timeline(0)
-t = buf.cpu().view(8, 64)
+t = buf.cpu()[:512].view(8, 64)
 names = {0: "step start", 1: "SF seen c0", 2: "sweep1 c0 done", 3: "sweep2 c0 done (PR)", 5: "SF seen c1", 6: "sweep1 c1", 7: "PR c1", 9: "SF c2", 10: "sweep1 c2", 11: "PR c2",
          20: "OF seen", 21: "drain done"}
 t0 = min(int(v) for v in t.flatten() if int(v) != 0)

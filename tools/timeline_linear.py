@@ -30,12 +30,12 @@ for name, fn in (("qkv", qkv_run), ("proj", proj_run)):
         fn()
     e1.record(); torch.cuda.synchronize()
     print(f"{name} T={T}: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us per launch")
-    buf = torch.zeros(512, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(2048, dtype=torch.int64, device="cuda")
     lib.srk_debug_set_timeline(buf.data_ptr())
     fn()
     torch.cuda.synchronize()
     lib.srk_debug_set_timeline(0)
-    t = buf.cpu().view(8, 64)
+    t = buf.cpu()[:512].view(8, 64)
     t0 = int(t[0, 62])
     print(f"  kernel-body start -> first LN done: {int(t[0, 63]) - t0}")
     for it in range(8):
@@ -58,12 +58,12 @@ for _ in range(20):
     rows_run()
 e1.record(); torch.cuda.synchronize()
 print(f"rows->rows+res T={T}: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us per launch")
-buf = torch.zeros(512, dtype=torch.int64, device="cuda")
+buf = torch.zeros(2048, dtype=torch.int64, device="cuda")
 lib.srk_debug_set_timeline(buf.data_ptr())
 rows_run()
 torch.cuda.synchronize()
 lib.srk_debug_set_timeline(0)
-t = buf.cpu().view(8, 64)
+t = buf.cpu()[:512].view(8, 64)
 t0 = int(t[0, 62])
 print(f"  kernel-body start -> first LN done: {int(t[0, 63]) - t0}")
 for it in range(8):

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libsrk.so")
 
 # mirrors of the #defines in include/srk.h
-ABI_VERSION = 1
+ABI_VERSION = 2
 DIM, DIM_PAD, HEADS, HEAD_DIM, HEAD_PAD, WINDOW, HIDDEN, HIDDEN_PAD = 180, 192, 6, 30, 32, 8, 360, 384
 ATTN_WSTREAM_BYTES = 3 * 24576 + 9 * 16384 + 3 * 24576
 MLP_WSTREAM_BYTES = 9 * 16384 + 6 * 24576
@@ -20,11 +20,12 @@ ATTN_VEC_FLOATS = 1216 + 6 * 232
 MV_B1, MV_B2, MLP_VEC_FLOATS = 384, 768, 960
 MODE_IMAGE, MODE_WINDOWS = 0, 1
 MASK_NONE, MASK_SHIFT, MASK_EXPLICIT = 0, 1, 2
+OPERANDS = {"bf16": 0, "fp16": 1}      # include/srk.h: SRK_OPERANDS_* ("fp16" = the tight precision mode)
 
 
 class SwinAttnDesc(Structure):
     _fields_ = [(n, c_int32) for n in ("mode", "batch", "height", "width", "num_windows", "ld_in", "ld_out", "shift",
-                                       "apply_ln", "add_residual", "mask_mode", "mask_nw")]
+                                       "apply_ln", "add_residual", "mask_mode", "mask_nw", "operands")]
 
 
 class BlockSync(Structure):
@@ -46,7 +47,7 @@ LAYER_MAX_BLOCKS = 8
 
 class MlpDesc(Structure):
     _fields_ = [("num_tokens", c_int64), ("ld_in", c_int32), ("ld_out", c_int32), ("apply_ln", c_int32),
-                ("add_residual", c_int32)]
+                ("add_residual", c_int32), ("operands", c_int32)]
 
 
 class LinearDesc(Structure):
@@ -227,12 +228,12 @@ def _block_sync(progress, batch, tokens_per_image, wait_target):
 
 
 def swin_attn(x, y, wstream, vec, *, mode, batch=0, height=0, width=0, num_windows=0, ld_in, ld_out, shift=0,
-              apply_ln=True, add_residual=True, mask_mode=MASK_NONE, mask=None, progress=None, wait_target=0) -> None:
+              apply_ln=True, add_residual=True, mask_mode=MASK_NONE, mask=None, progress=None, wait_target=0, operands="bf16") -> None:
     """progress / wait_target: image progress counters (include/srk.h: SrkBlockSync); None = whole-grid ordering."""
     lib = load()
     _require_cuda_f32(x, y, vec, mask)
     d = SwinAttnDesc(mode, batch, height, width, num_windows, ld_in, ld_out, shift, int(apply_ln), int(add_residual),
-                     mask_mode, 0 if mask is None else mask.shape[0])
+                     mask_mode, 0 if mask is None else mask.shape[0], OPERANDS[operands])
     sync = _block_sync(progress, batch, height * width, wait_target)
     with _launch("swin_attn", x, y, wstream, vec, mask, progress) as st:
         _check(lib.srk_swin_attn_fwd_sync(ctypes.byref(d), x.data_ptr(), y.data_ptr(), wstream.data_ptr(), vec.data_ptr(),
@@ -240,10 +241,10 @@ def swin_attn(x, y, wstream, vec, *, mode, batch=0, height=0, width=0, num_windo
 
 
 def swin_mlp(x, y, wstream, vec, *, num_tokens, ld_in, ld_out, apply_ln=True, add_residual=True, progress=None, batch=0,
-             tokens_per_image=0, wait_target=0) -> None:
+             tokens_per_image=0, wait_target=0, operands="bf16") -> None:
     lib = load()
     _require_cuda_f32(x, y, vec)
-    d = MlpDesc(num_tokens, ld_in, ld_out, int(apply_ln), int(add_residual))
+    d = MlpDesc(num_tokens, ld_in, ld_out, int(apply_ln), int(add_residual), OPERANDS[operands])
     sync = _block_sync(progress, batch, tokens_per_image, wait_target)
     with _launch("swin_mlp", x, y, wstream, vec, progress) as st:
         _check(lib.srk_swin_mlp_fwd_sync(ctypes.byref(d), x.data_ptr(), y.data_ptr(), wstream.data_ptr(), vec.data_ptr(),

@@ -76,11 +76,6 @@ __device__ __forceinline__ float conv_act(float v, int act, float slope) {
     if (act == SRK_ACT_GELU) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));      // nn.GELU() (exact), hat_arch.py:68
     return v;
 }
-__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
-    uint32_t r;
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));          // .x (low half) = lo
-    return r;
-}
 
 __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ uint8_t smem_raw[];

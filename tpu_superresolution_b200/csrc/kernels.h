@@ -162,6 +162,8 @@ inline cudaError_t launch_pdl(void (*kern)(const P), int grid, int threads, size
 }
 cudaError_t launch_swin_attn(const AttnParams& p, cudaStream_t stream);
 cudaError_t launch_swin_mlp(const MlpParams& p, cudaStream_t stream);
+cudaError_t launch_swin_attn_f16(const AttnParams& p, cudaStream_t stream);      // swin_kernels_f16.cu: fp16 operand images / weights
+cudaError_t launch_swin_mlp_f16(const MlpParams& p, cudaStream_t stream);
 cudaError_t launch_token_linear(const LinearParams& p, cudaStream_t stream);
 cudaError_t launch_winattn(int kind, const WinAttnParams& p, cudaStream_t stream);
 int winattn_table_floats(int kind);

@@ -80,7 +80,7 @@ __device__ __forceinline__ void ln_rows_to_image_p(int apply_ln, uint32_t xa, in
         const uint32_t off = xa + sw128_off(r, l16 >> 1) + (l16 & 1) * 8;
 #pragma unroll
         for (int jj = 0; jj < 3; ++jj)      // channel 4f = 64*jj + 4*l16 -> atom jj, chunk l16>>1, byte (l16&1)*8
-            st_shared_v2(off + jj * ATOM_A, pack_bf16x2(w[jj].x, w[jj].y), pack_bf16x2(w[jj].z, w[jj].w));
+            st_shared_v2(off + jj * ATOM_A, pack_op2(w[jj].x, w[jj].y), pack_op2(w[jj].z, w[jj].w));
     }
 }
 template <typename TokFn>
@@ -149,7 +149,7 @@ __device__ __forceinline__ void ln_rows_hold_p(int apply_ln, int lane, PtrFn row
             if (!live2) w[2] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int jj = 0; jj < 3; ++jj) held[pass][jj] = make_uint2(pack_bf16x2(w[jj].x, w[jj].y), pack_bf16x2(w[jj].z, w[jj].w));
+        for (int jj = 0; jj < 3; ++jj) held[pass][jj] = make_uint2(pack_op2(w[jj].x, w[jj].y), pack_op2(w[jj].z, w[jj].w));
     }
 }
 template <int NPASS, typename TokFn>
@@ -189,8 +189,8 @@ __device__ __forceinline__ void store_row_chunks(uint32_t img_atom, uint32_t row
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[e] *= scale;
         }
-        st_shared_v4(img_atom + sw128_off(row, c16base + k), pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                     pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+        st_shared_v4(img_atom + sw128_off(row, c16base + k), pack_op2(f[0], f[1]), pack_op2(f[2], f[3]),
+                     pack_op2(f[4], f[5]), pack_op2(f[6], f[7]));
     }
 }
 

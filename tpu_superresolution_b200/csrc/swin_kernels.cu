@@ -22,8 +22,18 @@
 
 #include "kernels.h"
 #define SRK_OOL_TIMEOUT 1      // see umma.cuh: mbar_wait
+#define SRK_OOL_WAIT 1         // spin loop of mbar_wait out of line (instruction-cache footprint)
 #include "umma.cuh"
 #include "rowops.cuh"
+
+// swin_kernels_f16.cu compiles this file a second time with fp16 GEMM operands (umma.cuh: umma_idesc_op / pack_op2): same kernels
+// under other names, without the layer kernel and the process-wide debug / tuning globals.
+#ifdef SRK_F16_OPERANDS
+#define swin_attn_kernel swin_attn_kernel_f16
+#define swin_mlp_kernel swin_mlp_kernel_f16
+#define launch_swin_attn launch_swin_attn_f16
+#define launch_swin_mlp launch_swin_mlp_f16
+#endif
 
 namespace srk {
 
@@ -34,10 +44,10 @@ constexpr uint32_t VT_ATOM = 24576;     // 192 rows x 128 B: one k-atom (64 keys
 constexpr uint32_t RING_STAGE = 24576;  // largest weight slab (192 rows x 64 k)
 constexpr int RING_N = 3;
 
-constexpr uint32_t IDESC_128x128 = umma_idesc_bf16(128, 128);
-constexpr uint32_t IDESC_128x192 = umma_idesc_bf16(128, 192);
-constexpr uint32_t IDESC_64x64 = umma_idesc_bf16(64, 64);
-constexpr uint32_t IDESC_64x32_BMN = umma_idesc_bf16(64, 32) | (1u << 16);     // B (= V) MN-major: [key][dim] rows
+constexpr uint32_t IDESC_128x128 = umma_idesc_op(128, 128);
+constexpr uint32_t IDESC_128x192 = umma_idesc_op(128, 192);
+constexpr uint32_t IDESC_64x64 = umma_idesc_op(64, 64);
+constexpr uint32_t IDESC_64x32_BMN = umma_idesc_op(64, 32) | (1u << 16);     // B (= V) MN-major: [key][dim] rows
 constexpr float LOG2E = 1.4426950408889634f;
 
 // Optional per-CTA timeline (debug): CTA 0 writes clock64() at event `id` of its `it`-th tile.
@@ -47,9 +57,11 @@ constexpr float LOG2E = 1.4426950408889634f;
 #define SRK_TL(dbgptr, it, id) do { if ((dbgptr) != nullptr && blockIdx.x == 0 && (it) < 8) (dbgptr)[(it) * 64 + (id)] = clock64(); } while (0)
 #endif
 #define SRK_TL0(dbgptr, id) do { if (threadIdx.x == 64) SRK_TL(dbgptr, 0, id); } while (0)
+#ifndef SRK_F16_OPERANDS
 unsigned long long* g_timeline = nullptr;
 int g_stagger_attn = 0, g_stagger_mlp = 0, g_stagger_winattn = 1500;
 int g_pdl = 1;
+#endif
 
 // All CTAs of a launch run the same phase sequence; started together they hit their memory phases (tile load, tile
 // store) at the same time and leave HBM / L2 idle in between.  Skewing the start of CTA i by (i mod 4) * `cycles`
@@ -541,7 +553,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
                 for (int jx = 0; jx < 64; jx += 2) {
                     const float e0 = ex2_approx(s[jx] - mx), e1 = ex2_approx(s[jx + 1] - mx);
                     sum0 += e0; sum1 += e1;
-                    pw[jx >> 1] = pack_bf16x2(e0, e1);
+                    pw[jx >> 1] = pack_op2(e0, e1);
                 }
                 {
                     const float is = __frcp_rn(sum0 + sum1);
@@ -819,14 +831,14 @@ __global__ void __launch_bounds__(LNW ? NTHREADS : 320, 1) swin_mlp_kernel(const
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float4 b = b1[i];
-                        hw[2 * i] = pack_bf16x2(gelu_fast(__uint_as_float(v0[4 * i + 0]) + b.x), gelu_fast(__uint_as_float(v0[4 * i + 1]) + b.y));
-                        hw[2 * i + 1] = pack_bf16x2(gelu_fast(__uint_as_float(v0[4 * i + 2]) + b.z), gelu_fast(__uint_as_float(v0[4 * i + 3]) + b.w));
+                        hw[2 * i] = pack_op2(gelu_fast(__uint_as_float(v0[4 * i + 0]) + b.x), gelu_fast(__uint_as_float(v0[4 * i + 1]) + b.y));
+                        hw[2 * i + 1] = pack_op2(gelu_fast(__uint_as_float(v0[4 * i + 2]) + b.z), gelu_fast(__uint_as_float(v0[4 * i + 3]) + b.w));
                     }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float4 b = b1[8 + i];
-                        hw[16 + 2 * i] = pack_bf16x2(gelu_fast(__uint_as_float(v1[4 * i + 0]) + b.x), gelu_fast(__uint_as_float(v1[4 * i + 1]) + b.y));
-                        hw[16 + 2 * i + 1] = pack_bf16x2(gelu_fast(__uint_as_float(v1[4 * i + 2]) + b.z), gelu_fast(__uint_as_float(v1[4 * i + 3]) + b.w));
+                        hw[16 + 2 * i] = pack_op2(gelu_fast(__uint_as_float(v1[4 * i + 0]) + b.x), gelu_fast(__uint_as_float(v1[4 * i + 1]) + b.y));
+                        hw[16 + 2 * i + 1] = pack_op2(gelu_fast(__uint_as_float(v1[4 * i + 2]) + b.z), gelu_fast(__uint_as_float(v1[4 * i + 3]) + b.w));
                     }
                     tmem_st32(tmem + lanebase + col, hw);          // H aliases the first half of this thread's own accumulator columns
                     tmem_st_wait();
@@ -871,6 +883,7 @@ __global__ void __launch_bounds__(LNW ? NTHREADS : 320, 1) swin_mlp_kernel(const
     if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
+#ifndef SRK_F16_OPERANDS
 // ------------------------------------------------------------------------------------------------
 // KL: one persistent kernel per BasicLayer (network_swinir.py:349-416): the attention and MLP halves of ALL blocks of the group
 // ------------------------------------------------------------------------------------------------
@@ -1322,7 +1335,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_layer_kernel(const LayerPa
                     for (int jx = 0; jx < 64; jx += 2) {
                         const float e0 = ex2_approx(s[jx] - mx), e1 = ex2_approx(s[jx + 1] - mx);
                         sum0 += e0; sum1 += e1;
-                        pw[jx >> 1] = pack_bf16x2(e0, e1);
+                        pw[jx >> 1] = pack_op2(e0, e1);
                     }
                     {
                         const float is = __frcp_rn(sum0 + sum1);
@@ -1378,14 +1391,14 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_layer_kernel(const LayerPa
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             const float4 b = b1[k];
-                            hw[2 * k] = pack_bf16x2(gelu_fast(__uint_as_float(v0[4 * k + 0]) + b.x), gelu_fast(__uint_as_float(v0[4 * k + 1]) + b.y));
-                            hw[2 * k + 1] = pack_bf16x2(gelu_fast(__uint_as_float(v0[4 * k + 2]) + b.z), gelu_fast(__uint_as_float(v0[4 * k + 3]) + b.w));
+                            hw[2 * k] = pack_op2(gelu_fast(__uint_as_float(v0[4 * k + 0]) + b.x), gelu_fast(__uint_as_float(v0[4 * k + 1]) + b.y));
+                            hw[2 * k + 1] = pack_op2(gelu_fast(__uint_as_float(v0[4 * k + 2]) + b.z), gelu_fast(__uint_as_float(v0[4 * k + 3]) + b.w));
                         }
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             const float4 b = b1[8 + k];
-                            hw[16 + 2 * k] = pack_bf16x2(gelu_fast(__uint_as_float(v1[4 * k + 0]) + b.x), gelu_fast(__uint_as_float(v1[4 * k + 1]) + b.y));
-                            hw[16 + 2 * k + 1] = pack_bf16x2(gelu_fast(__uint_as_float(v1[4 * k + 2]) + b.z), gelu_fast(__uint_as_float(v1[4 * k + 3]) + b.w));
+                            hw[16 + 2 * k] = pack_op2(gelu_fast(__uint_as_float(v1[4 * k + 0]) + b.x), gelu_fast(__uint_as_float(v1[4 * k + 1]) + b.y));
+                            hw[16 + 2 * k + 1] = pack_op2(gelu_fast(__uint_as_float(v1[4 * k + 2]) + b.z), gelu_fast(__uint_as_float(v1[4 * k + 3]) + b.w));
                         }
                         tmem_st32(tmem + lanebase + col, hw);
                         tmem_st_wait();
@@ -1418,6 +1431,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_layer_kernel(const LayerPa
     if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
+#endif  // !SRK_F16_OPERANDS (layer kernel)
+
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
@@ -1439,11 +1454,13 @@ cudaError_t launch_swin_mlp(const MlpParams& p, cudaStream_t stream) {
     return launch_pdl(swin_mlp_kernel<false>, grid, 320, K2_SMEM, stream, p);
 }
 
+#ifndef SRK_F16_OPERANDS
 cudaError_t launch_swin_layer(const LayerParams& p, cudaStream_t stream) {
     static bool configured[SRK_MAX_DEVICES] = {};
     if (cudaError_t e = configure_smem_once(configured, swin_layer_kernel, KL_SMEM); e != cudaSuccess) return e;
     const int grid = p.T < num_sms() ? p.T : num_sms();
     return launch_pdl(swin_layer_kernel, grid, K1_THREADS, KL_SMEM, stream, p);
 }
+#endif
 
 }  // namespace srk

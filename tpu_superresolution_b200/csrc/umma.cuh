@@ -75,8 +75,31 @@ static __device__ __noinline__ void mbar_timeout_trap(uint32_t bar, uint32_t par
     printf("srk: mbarrier wait timeout (block %d thread %d bar@%u parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
     __trap();
 }
+#ifdef SRK_OOL_TIMEOUT
+// the whole spin loop out of line: ~12 instructions less at each of the ~60 waits of a fused kernel (instruction-cache footprint)
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+    const long long t0 = clock64();
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!ok && clock64() - t0 > SRK_WAIT_TIMEOUT_CYCLES) mbar_timeout_trap(bar, parity);
+    }
+}
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
+#ifdef SRK_OOL_WAIT
+    mbar_wait_slow(smem_u32(bar), parity);
+    return;
+#endif
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
 #ifndef SRK_OOL_TIMEOUT
@@ -187,6 +210,18 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
            (static_cast<uint32_t>(M >> 4) << 24);
 }
+// ... A = B = fp16 (a_format = b_format = 0)
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+    return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+// Operand type of the translation unit: bf16 (default), or fp16 with SRK_F16_OPERANDS -- the "tight" precision mode: an 11-bit
+// significand like TF32's; safe in range because every GEMM input here is LayerNorm output, a softmax probability or a
+// weight-bounded projection of those (swin_kernels_f16.cu compiles swin_kernels.cu a second time with it).
+#ifdef SRK_F16_OPERANDS
+__host__ __device__ constexpr uint32_t umma_idesc_op(int M, int N) { return umma_idesc_f16(M, N); }
+#else
+__host__ __device__ constexpr uint32_t umma_idesc_op(int M, int N) { return umma_idesc_bf16(M, N); }
+#endif
 // byte offset of 16-byte chunk c16 of row r inside one SW128 k-atom
 __device__ __forceinline__ uint32_t sw128_off(uint32_t r, uint32_t c16) { return r * 128u + ((c16 ^ (r & 7u)) << 4); }
 
@@ -355,6 +390,18 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);   // .x = lo (low 16 bits), .y = hi
     return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));      // (first source -> upper half)
+    return r;
+}
+__device__ __forceinline__ uint32_t pack_op2(float lo, float hi) {          // two GEMM-operand elements, see umma_idesc_op
+#ifdef SRK_F16_OPERANDS
+    return pack_f16x2(lo, hi);
+#else
+    return pack_bf16x2(lo, hi);
+#endif
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");

@@ -41,9 +41,14 @@ def unswizzle_slab(slab: torch.Tensor) -> torch.Tensor:
     return swizzle_slab(slab)
 
 
-def _slabs(mat: torch.Tensor) -> list:
-    """(R, K) with K % 64 == 0 -> list of K/64 swizzled bf16 slabs in k order."""
-    mat = mat.to(torch.bfloat16)
+OPERAND_DTYPES = {"bf16": torch.bfloat16, "fp16": torch.float16}      # include/srk.h: SRK_OPERANDS_*
+
+
+def _slabs(mat: torch.Tensor, operands: str = "bf16") -> list:
+    """(R, K) with K % 64 == 0 -> list of K/64 swizzled bf16 (or fp16) slabs in k order."""
+    if operands == "fp16" and bool((mat.abs() > 65504.0).any()):
+        raise RuntimeError("packing: a weight exceeds the fp16 range; use operands='bf16'")
+    mat = mat.to(OPERAND_DTYPES[operands])
     return [swizzle_slab(mat[:, k:k + 64].contiguous()) for k in range(0, mat.shape[1], 64)]
 
 
@@ -61,7 +66,7 @@ def _pad_cols(w: torch.Tensor, cols: int) -> torch.Tensor:
 
 
 @torch.no_grad()
-def pack_attention(qkv_w, qkv_b, proj_w, proj_b, rpb_table, ln_w=None, ln_b=None, scale=None
+def pack_attention(qkv_w, qkv_b, proj_w, proj_b, rpb_table, ln_w=None, ln_b=None, scale=None, operands: str = "bf16"
                    ) -> Tuple[torch.Tensor, torch.Tensor]:
     """-> (wstream uint8[ATTN_WSTREAM_BYTES], vec float32[ATTN_VEC_FLOATS]) on qkv_w's device.
 
@@ -89,16 +94,16 @@ def pack_attention(qkv_w, qkv_b, proj_w, proj_b, rpb_table, ln_w=None, ln_b=None
     bq = _pad_heads((qkv_b[:C] * (scale * LOG2E)).float())
     proj_b_eff = (proj_b.detach().double() + proj_w.detach().double() @ qkv_b[2 * C:]).float()   # v bias -> proj bias
 
-    slabs = _slabs(wv)                                   # V = xhat Wv^T: B operand, N = 192 padded v-dims (3 k-atoms x 24 KB)
+    slabs = _slabs(wv, operands)                         # V = xhat Wv^T: B operand, N = 192 padded v-dims (3 k-atoms x 24 KB)
     for h in range(0, L.HEADS, 2):                       # heads h, h+1: [q_h | k_h | q_h+1 | k_h+1] rows (B operand, N = 128)
         rows = torch.cat([wq[32 * h:32 * h + 32], wk[32 * h:32 * h + 32],
                           wq[32 * h + 32:32 * h + 64], wk[32 * h + 32:32 * h + 64]], 0)
-        slabs += _slabs(rows)
+        slabs += _slabs(rows, operands)
     # proj: K index is the padded head layout of O
     wp = proj_w.detach().float().view(C, L.HEADS, L.HEAD_DIM)
     wp_pad = wp.new_zeros(L.DIM_PAD, L.HEADS, L.HEAD_PAD)
     wp_pad[:C, :, :L.HEAD_DIM] = wp
-    slabs += _slabs(wp_pad.reshape(L.DIM_PAD, L.DIM_PAD))
+    slabs += _slabs(wp_pad.reshape(L.DIM_PAD, L.DIM_PAD), operands)
     wstream = torch.cat([s.reshape(-1) for s in slabs]).contiguous().view(torch.uint8)
     assert wstream.numel() == L.ATTN_WSTREAM_BYTES
 
@@ -111,7 +116,7 @@ def pack_attention(qkv_w, qkv_b, proj_w, proj_b, rpb_table, ln_w=None, ln_b=None
 
 
 @torch.no_grad()
-def pack_mlp(fc1_w, fc1_b, fc2_w, fc2_b, ln_w=None, ln_b=None) -> Tuple[torch.Tensor, torch.Tensor]:
+def pack_mlp(fc1_w, fc1_b, fc2_w, fc2_b, ln_w=None, ln_b=None, operands: str = "bf16") -> Tuple[torch.Tensor, torch.Tensor]:
     """fc1 (360,180), fc2 (180,360) -> (wstream uint8[MLP_WSTREAM_BYTES], vec float32[MLP_VEC_FLOATS])."""
     dev = fc1_w.device
     fc1_w, fc1_b, fc2_w, fc2_b, ln_w, ln_b = [None if t is None else t.detach().cpu() for t in
@@ -130,8 +135,8 @@ def pack_mlp(fc1_w, fc1_b, fc2_w, fc2_b, ln_w=None, ln_b=None) -> Tuple[torch.Te
     w1[:Hd, :C] = f1.float()
     w2 = fc2_w.new_zeros(L.DIM_PAD, L.HIDDEN_PAD, dtype=torch.float32)
     w2[:C, :Hd] = fc2_w.detach().float()
-    f1 = [_slabs(w1[128 * c:128 * (c + 1)]) for c in range(3)]     # fc1 in three 128-unit hidden chunks (3 k-atoms each)
-    f2 = _slabs(w2)                                                  # fc2: 6 k-atoms of 64 hidden units
+    f1 = [_slabs(w1[128 * c:128 * (c + 1)], operands) for c in range(3)]     # fc1 in three 128-unit hidden chunks (3 k-atoms each)
+    f2 = _slabs(w2, operands)                                        # fc2: 6 k-atoms of 64 hidden units
     slabs = f1[0] + f1[1] + f2[0:2] + f1[2] + f2[2:6]               # the order the MMA warp consumes them
     wstream = torch.cat([s.reshape(-1) for s in slabs]).contiguous().view(torch.uint8)
     assert wstream.numel() == L.MLP_WSTREAM_BYTES

@@ -37,6 +37,16 @@ def _to_2tuple(v):
     return tuple(v) if isinstance(v, (tuple, list)) else (v, v)
 
 
+def set_precision(model: nn.Module, precision: str = "bf16") -> None:
+    """Set the GEMM operand type ("bf16" | "fp16") of every fused Mlp / WindowAttention module under `model`."""
+    if precision not in L.OPERANDS:
+        raise ValueError(f"precision must be one of {sorted(L.OPERANDS)}, got {precision!r}")
+    for m in model.modules():
+        if isinstance(m, (Mlp, WindowAttention)):
+            m.operands = precision
+    convs.invalidate_all()
+
+
 def _inference_only(mod: nn.Module) -> None:
     if torch.is_grad_enabled() and any(p.requires_grad for p in mod.parameters(recurse=False)):
         # the kernels have no backward; refuse silently-wrong training instead of detaching
@@ -59,6 +69,7 @@ class Mlp(nn.Module):
         self.act = act_layer()
         self.fc2 = nn.Linear(hidden_features, out_features)
         self.drop = nn.Dropout(drop)
+        self.operands = "bf16"           # GEMM operand type ("fp16" = tight mode), see set_precision()
         self._cache = _PackedCache()
 
     def _packed(self, norm: Optional[nn.LayerNorm] = None):
@@ -66,7 +77,7 @@ class Mlp(nn.Module):
              ([norm.weight, norm.bias] if norm is not None else [])
         return self._cache.get(ps, lambda: packing.pack_mlp(
             self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias,
-            None if norm is None else norm.weight, None if norm is None else norm.bias))
+            None if norm is None else norm.weight, None if norm is None else norm.bias, operands=self.operands))
 
     def forward(self, x):
         _inference_only(self)
@@ -75,7 +86,7 @@ class Mlp(nn.Module):
         y = torch.empty_like(x2)
         w, v = self._packed()
         L.swin_mlp(x2, y, w, v, num_tokens=x2.shape[0], ld_in=x2.shape[1], ld_out=x2.shape[1], apply_ln=False,
-                   add_residual=False)
+                   add_residual=False, operands=self.operands)
         return y.reshape(shape)
 
 
@@ -100,6 +111,7 @@ class WindowAttention(nn.Module):
         self.proj_drop = nn.Dropout(proj_drop)
         nn.init.trunc_normal_(self.relative_position_bias_table, std=.02)
         self.softmax = nn.Softmax(dim=-1)
+        self.operands = "bf16"           # GEMM operand type ("fp16" = tight mode), see set_precision()
         self._cache = _PackedCache()
 
     def _packed(self, norm: Optional[nn.LayerNorm] = None):
@@ -110,7 +122,7 @@ class WindowAttention(nn.Module):
              ([norm.weight, norm.bias] if norm is not None else [])
         return self._cache.get(ps, lambda: packing.pack_attention(
             self.qkv.weight, self.qkv.bias, self.proj.weight, self.proj.bias, self.relative_position_bias_table,
-            None if norm is None else norm.weight, None if norm is None else norm.bias, self.scale))
+            None if norm is None else norm.weight, None if norm is None else norm.bias, self.scale, operands=self.operands))
 
     def forward(self, x, mask=None):
         _inference_only(self)
@@ -125,7 +137,7 @@ class WindowAttention(nn.Module):
                 raise RuntimeError("WindowAttention: B_ must be a multiple of mask.shape[0]")
             mask = mask.to(device=x.device, dtype=torch.float32).contiguous()
         L.swin_attn(x, y, w, v, mode=L.MODE_WINDOWS, num_windows=B_, ld_in=C, ld_out=C, apply_ln=False,
-                    add_residual=False, mask_mode=L.MASK_NONE if mask is None else L.MASK_EXPLICIT, mask=mask)
+                    add_residual=False, mask_mode=L.MASK_NONE if mask is None else L.MASK_EXPLICIT, mask=mask, operands=self.operands)
         return y
 
     def extra_repr(self) -> str:
@@ -198,9 +210,10 @@ class SwinTransformerBlock(nn.Module):
         L.swin_attn(x, out, aw, av, mode=L.MODE_IMAGE, batch=B, height=H, width=W, ld_in=C, ld_out=C,
                     shift=self.shift_size, apply_ln=True, add_residual=True,
                     mask_mode=L.MASK_SHIFT if self.shift_size > 0 else L.MASK_NONE, progress=progress,
-                    wait_target=block_index * (Ltok // 128) if (progress is not None and in_place) else 0)
+                    wait_target=block_index * (Ltok // 128) if (progress is not None and in_place) else 0, operands=self.attn.operands)
         L.swin_mlp(out, out, mw, mv, num_tokens=B * Ltok, ld_in=C, ld_out=C, apply_ln=True, add_residual=True, progress=progress,
-                   batch=B, tokens_per_image=Ltok, wait_target=(block_index + 1) * nw_img if progress is not None else 0)
+                   batch=B, tokens_per_image=Ltok, wait_target=(block_index + 1) * nw_img if progress is not None else 0,
+                   operands=self.mlp.operands)
         return out
 
     def forward(self, x, x_size):
@@ -243,7 +256,8 @@ class BasicLayer(nn.Module):
         H, W = x_size
         return (USE_LAYER_KERNEL and 1 <= len(self.blocks) <= L.LAYER_MAX_BLOCKS and x.is_cuda and x.dtype == torch.float32
                 and H % L.WINDOW == 0 and W % L.WINDOW == 0 and (H * W) % 128 == 0 and x.shape[-1] == L.DIM
-                and all(b.shift_size in (0, L.WINDOW // 2) and b.window_size == L.WINDOW for b in self.blocks))
+                and all(b.shift_size in (0, L.WINDOW // 2) and b.window_size == L.WINDOW and b.attn.operands == "bf16"
+                        and b.mlp.operands == "bf16" for b in self.blocks))
 
     def forward(self, x, x_size):
         x = x.contiguous()
@@ -513,6 +527,15 @@ class SwinIR(nn.Module):
         L.layernorm(x, x, self.norm.weight, self.norm.bias, num_tokens=B * Ltok, ld_in=C, ld_out=C)   # :800, in place
         return self.patch_unembed(x, x_size)
 
+    def set_precision(self, precision: str = "bf16") -> "SwinIR":
+        """GEMM operand type of the fused attention / MLP kernels: "bf16" (default; gate max abs <= 2e-3 vs the reference's fp32
+        forward) or "fp16" -- the tight mode (include/srk.h: SRK_OPERANDS_F16; fp16 has TF32's 11-bit significand; gate <= 2e-4).
+        In the tight mode the 3x3 convolutions run in fp32 on the library path (slower; the default mode's tcgen05 convolution has
+        fp16 operands, which alone would exceed the tight gate).  A ``GraphedModel`` around this model must be ``reset()``."""
+        set_precision(self, precision)
+        self.precision = precision
+        return self
+
     def invalidate_packed(self) -> None:
         """Forget all packed weight images.  Needed only after parameters were edited in place through ``.data`` (EMA, weight
         surgery): such edits change neither ``_version`` nor ``data_ptr``, which is what the caches key on.  ``load_state_dict``
@@ -536,6 +559,15 @@ class SwinIR(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("SwinIR: CUDA input required (no CPU fallback)")
         _inference_only(self.conv_first)
+        if getattr(self, "precision", "bf16") == "fp16" and convs.USE_FUSED_CONV:
+            # tight mode: the fused attention / MLP kernels with fp16 operands; the 3x3 convolutions in fp32 on the library path
+            # (the tcgen05 convolution's fp16 operands alone cost 1.7 - 2.6e-4 max abs, like cuDNN's TF32: tools/probe_precision.py)
+            tf32 = torch.backends.cudnn.allow_tf32
+            convs.USE_FUSED_CONV, torch.backends.cudnn.allow_tf32 = False, False
+            try:
+                return self.forward(x)
+            finally:
+                convs.USE_FUSED_CONV, torch.backends.cudnn.allow_tf32 = True, tf32
         if convs.fused_ok(self) and not self.ape and x.dtype == torch.float32:
             return self._forward_fused(x)
         self._prepare(x.device)
