@@ -62,7 +62,9 @@ enum { SRK_MASK_NONE = 0, SRK_MASK_SHIFT = 1, SRK_MASK_EXPLICIT = 2 };
  * F16: the "tight" mode -- operand images and packed weights in fp16, which has TF32's 11-bit significand (gate <= 2e-4); every
  * GEMM input of these kernels is LayerNorm output, a softmax probability or a projection of those, so fp16's range is safe.
  * The weight stream must have been packed for the same type (packing.py: operands=...). */
-enum { SRK_OPERANDS_BF16 = 0, SRK_OPERANDS_F16 = 1 };
+enum { SRK_OPERANDS_BF16 = 0, SRK_OPERANDS_F16 = 1,
+       SRK_OPERANDS_F16_HALF_GELU = 2 /* srk_swin_mlp_fwd only: fp16 operands (weights packed as for F16) and the GELU evaluated on packed
+                                         halves -- faster and still closer to the exact GELU than the bf16 variant; the modules' default MLP */ };
 
 typedef struct SrkSwinAttnDesc {
     int32_t mode;          /* SRK_MODE_IMAGE: x is (batch, height*width, ld); SRK_MODE_WINDOWS: x is (num_windows, 64, ld) */

@@ -295,6 +295,7 @@ def test_layer_kernel_bit_identical_to_per_block_kernels(B, h, w):
     m = srk.SwinIR(**cfg.as_kwargs()).eval()
     m.load_state_dict(synth.make_swinir_state_dict(cfg, seed=77, kind="stress"), strict=True)
     m.cuda()
+    m.set_precision("bf16_strict")                      # the layer kernel implements bf16 operands only
     layer = m.layers[1].residual_group
     x = synth.make_tokens(B, h, w, 180, seed=B + h).cuda()
     old = swinir.USE_LAYER_KERNEL

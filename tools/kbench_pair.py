@@ -25,8 +25,11 @@ def attn(x, shift):
                 mask_mode=L.MASK_SHIFT if shift else L.MASK_NONE)
 
 
+OPS = os.environ.get("SRK_OPS", "bf16")
+
+
 def mlp(x):
-    L.swin_mlp(x, x, mw, mv, num_tokens=B * 4096, ld_in=180, ld_out=180)
+    L.swin_mlp(x, x, mw, mv, num_tokens=B * 4096, ld_in=180, ld_out=180, operands=OPS)
 
 
 def timed(fn, n=40):

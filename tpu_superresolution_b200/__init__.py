@@ -1,7 +1,7 @@
 """B200-native (sm_100a) fused window-attention super-resolution: drop-in modules for the reference's
 SwinIR / HAT / DAT blocks (ViacheslavTimofeev/tpu_superresolution, modules/network_swinir.py, hat_arch.py, dat_arch.py) backed by libsrk.so."""
 from .swinir import (Mlp, WindowAttention, SwinTransformerBlock, BasicLayer, RSTB, PatchEmbed, PatchUnEmbed,
-                     PixelShuffle, Upsample, UpsampleOneStep, SwinIR, calculate_mask)
+                     PixelShuffle, Upsample, UpsampleOneStep, SwinIR, calculate_mask, set_precision)
 from . import hat
 from .hat import HAT, HAB, OCAB, RHAG, CAB, ChannelAttention, AttenBlocks
 from . import dat
@@ -12,4 +12,4 @@ __all__ = ["Mlp", "WindowAttention", "SwinTransformerBlock", "BasicLayer", "RSTB
            "PixelShuffle", "Upsample", "UpsampleOneStep", "SwinIR", "calculate_mask",
            "hat", "HAT", "HAB", "OCAB", "RHAG", "CAB", "ChannelAttention", "AttenBlocks",
            "dat", "DAT", "DATB", "ResidualGroup", "Adaptive_Spatial_Attention", "Adaptive_Channel_Attention", "SGFN", "SpatialGate",
-           "DynamicPosBias", "GraphedModel", "PipelinedRunner"]
+           "DynamicPosBias", "GraphedModel", "PipelinedRunner", "set_precision"]

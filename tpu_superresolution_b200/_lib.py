@@ -20,7 +20,7 @@ ATTN_VEC_FLOATS = 1216 + 6 * 232
 MV_B1, MV_B2, MLP_VEC_FLOATS = 384, 768, 960
 MODE_IMAGE, MODE_WINDOWS = 0, 1
 MASK_NONE, MASK_SHIFT, MASK_EXPLICIT = 0, 1, 2
-OPERANDS = {"bf16": 0, "fp16": 1}      # include/srk.h: SRK_OPERANDS_* ("fp16" = the tight precision mode)
+OPERANDS = {"bf16": 0, "fp16": 1, "fp16_fast": 2}      # include/srk.h: SRK_OPERANDS_* ("fp16" = the tight mode; "fp16_fast": MLP only)
 
 
 class SwinAttnDesc(Structure):

@@ -144,6 +144,7 @@ int srk_swin_mlp_fwd_sync(const SrkMlpDesc* d, const float* x, float* y, const v
     p.dbg = srk::g_timeline;
     p.stagger = p.n_tiles >= 2 * 148 ? srk::g_stagger_mlp : 0;
     if (d->operands == SRK_OPERANDS_F16) return check(srk::launch_swin_mlp_f16(p, static_cast<cudaStream_t>(stream)), "srk_swin_mlp_fwd");
+    if (d->operands == SRK_OPERANDS_F16_HALF_GELU) return check(srk::launch_swin_mlp_f16h(p, static_cast<cudaStream_t>(stream)), "srk_swin_mlp_fwd");
     if (d->operands != SRK_OPERANDS_BF16) return fail("srk_swin_mlp_fwd: unknown operands %d", d->operands);
     return check(srk::launch_swin_mlp(p, static_cast<cudaStream_t>(stream)), "srk_swin_mlp_fwd");
 }

@@ -1,5 +1,6 @@
 // Internal launch interface between capi.cu and the kernel translation units.
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -25,6 +26,7 @@ struct AttnParams {
     int* prog_sig;
     const int* prog_wait;
     int wait_target;
+    int use_tmap;              // swin_attn_kernel: the output tensor map (second kernel argument) is valid
 };
 
 struct MlpParams {
@@ -85,6 +87,10 @@ struct LinearParams {
     float* y;                    // SRK_LIN_OUT_ROWS
     int ld_out, add_residual;
     unsigned long long* dbg;     // optional timeline buffer (srk_debug_set_timeline)
+    // SRK_LIN_OUT_ROWS with ld_out != 180 (a chunk's 180 columns are then 720-byte pieces of wider rows): the output as a 2-D
+    // tensor (ld_out x num_tokens fp32), box 180 x 32 -- one tensor-map TMA store per lane quadrant instead of one bulk copy per row
+    int use_tmap;
+    alignas(64) CUtensorMap tmap_out;
 };
 
 // winattn_kernel (winattn_kernel.cu)
@@ -160,10 +166,25 @@ inline cudaError_t launch_pdl(void (*kern)(const P), int grid, int threads, size
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, p);
 }
+template <typename P, typename Q>
+inline cudaError_t launch_pdl2(void (*kern)(const P, const Q), int grid, int threads, size_t smem, cudaStream_t stream, const P& p, const Q& q) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, p, q);
+}
 cudaError_t launch_swin_attn(const AttnParams& p, cudaStream_t stream);
 cudaError_t launch_swin_mlp(const MlpParams& p, cudaStream_t stream);
 cudaError_t launch_swin_attn_f16(const AttnParams& p, cudaStream_t stream);      // swin_kernels_f16.cu: fp16 operand images / weights
 cudaError_t launch_swin_mlp_f16(const MlpParams& p, cudaStream_t stream);
+cudaError_t launch_swin_mlp_f16h(const MlpParams& p, cudaStream_t stream);       // swin_kernels_f16h.cu: + GELU on packed halves
 cudaError_t launch_token_linear(const LinearParams& p, cudaStream_t stream);
 cudaError_t launch_winattn(int kind, const WinAttnParams& p, cudaStream_t stream);
 int winattn_table_floats(int kind);

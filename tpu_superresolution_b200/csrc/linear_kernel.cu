@@ -53,7 +53,7 @@ enum { LB_FULL = 0, LB_EMPTY = 3, LB_AFULL = 6, LB_AEMPTY = 7, LB_ACCF = 8, LB_A
 
 }  // namespace
 
-__global__ void __launch_bounds__(LIN_THREADS, 1) token_linear_kernel(const LinearParams p) {
+__global__ void __launch_bounds__(LIN_THREADS, 1) token_linear_kernel(const __grid_constant__ LinearParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t sbase = (raw + 1023u) & ~1023u;
@@ -253,7 +253,8 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) token_linear_kernel(const Line
                     }
                     // chunk c = output columns [180 c, 180 c + 180) of the ld_out-wide rows
                     stage_rows_and_bulk_store(acc, 0u, stage, stage, 32, s_vec + c * LIN_NC, p.y + c * SRK_DIM, p.ld_out, p.add_residual, q, g,
-                                              lane, tok_of_row, p.act == SRK_LIN_ACT_GELU);
+                                              lane, tok_of_row, p.act == SRK_LIN_ACT_GELU, nullptr, p.use_tmap ? &p.tmap_out : nullptr,
+                                              c * SRK_DIM, tile * 128);
                     if (stage_alias && g == 0) {
                         bulk_wait_read0();
                         mbar_arrive(&bars[LB_DRAIN]);
@@ -272,7 +273,34 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) token_linear_kernel(const Line
     if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
-cudaError_t launch_token_linear(const LinearParams& p, cudaStream_t stream) {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn lin_encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(f);
+    }
+    return fn;
+}
+
+cudaError_t launch_token_linear(const LinearParams& p_in, cudaStream_t stream) {
+    LinearParams p = p_in;
+    p.use_tmap = 0;
+    if (p.out_mode == SRK_LIN_OUT_ROWS && p.ld_out != SRK_DIM && p.num_tokens < (1ll << 31)) {
+        // (a failed encode just keeps the per-row copies)
+        if (EncodeTiledFn enc = lin_encode_tiled_fn()) {
+            const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(p.ld_out), static_cast<cuuint64_t>(p.num_tokens)};
+            const cuuint64_t gstr[1] = {static_cast<cuuint64_t>(p.ld_out) * sizeof(float)};
+            const cuuint32_t box[2] = {SRK_DIM, 32};
+            const cuuint32_t estr[2] = {1, 1};
+            if (enc(&p.tmap_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, p.y, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+                p.use_tmap = 1;
+        }
+    }
     static bool configured[SRK_MAX_DEVICES] = {};
     if (cudaError_t e = configure_smem_once(configured, token_linear_kernel, 232448); e != cudaSuccess) return e;
     const int sms = device_num_sms();

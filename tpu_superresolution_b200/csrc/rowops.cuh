@@ -2,6 +2,7 @@
 // LayerNorm -> bf16 operand image, accumulator -> image chunks, accumulator -> staged fp32 rows -> bulk (reduce-add) store, GELU.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -205,20 +206,77 @@ __device__ __forceinline__ float gelu_fast(float x) {
 }
 
 
+// Two GELU results as a packed operand pair.  With SRK_HALF_GELU (fp16 operands only) the whole evaluation runs on packed halves:
+// 9 instructions and ONE MUFU per PAIR instead of 8 + 1 MUFU per element.  The fp16 arithmetic costs accuracy (max abs 2.3e-3 near
+// x = 2.8, rms 4e-4 on |x| < 3), but the bf16 operand path rounds the fp32 result to 8 bits right after (rms 2e-3), so this is still
+// five times closer to the exact GELU than the bf16 path; the tight mode keeps the fp32 evaluation.
+__device__ __forceinline__ uint32_t gelu_pack2(float x0, float x1) {
+#if defined(SRK_HALF_GELU) && defined(SRK_F16_OPERANDS)
+    const uint32_t xu = pack_f16x2(x0, x1);
+    const __half2 x = *reinterpret_cast<const __half2*>(&xu);
+    const __half2 u2 = __hmin2(__hmul2(x, x), __float2half2_rn(64.0f));
+    const __half2 pl = __hfma2(u2, __hfma2(u2, __float2half2_rn(-3.51517176e-04f), __float2half2_rn(3.70056486e-02f)), __float2half2_rn(7.97507881e-01f));
+    const __half2 q = __hmul2(x, pl);
+    uint32_t tu;
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(tu) : "r"(*reinterpret_cast<const uint32_t*>(&q)));
+    const __half2 t = *reinterpret_cast<const __half2*>(&tu);
+    const __half2 hx = __hmul2(x, __float2half2_rn(0.5f));
+    const __half2 r = __hfma2(hx, t, hx);
+    return *reinterpret_cast<const uint32_t*>(&r);
+#else
+    return pack_op2(gelu_fast(x0), gelu_fast(x1));
+#endif
+}
+
+constexpr uint32_t ROW_BYTES = SRK_DIM * 4;     // 720
+// Bulk copies of the 32 staged rows of lane quadrant q (this lane's row at `my_row`): one copy per maximal run of tokens that are
+// contiguous in memory (and in the staging buffer).  Whole warp; the caller commits the bulk group.
+template <typename TokFn>
+__device__ __forceinline__ void issue_row_runs(uint8_t* my_row, int main_rows, float* __restrict__ y, int ld_out, int add_residual, int q,
+                                               int lane, TokFn tok_of_row) {
+    const int64_t tok = tok_of_row(q * 32 + lane);
+    const int64_t prev = __shfl_up_sync(0xffffffffu, tok, 1);
+    const bool valid = tok >= 0;
+    const bool start = valid && (lane == 0 || lane == main_rows || ld_out != SRK_DIM || prev < 0 || tok != prev + 1);
+    const uint32_t m_start = __ballot_sync(0xffffffffu, start);
+    const uint32_t m_stop = m_start | ~__ballot_sync(0xffffffffu, valid);      // next start or first invalid row ends a run
+    // Issue from CONVERGENT code with warp-uniform operands: inside `if (start)` the compiler wraps the bulk-copy instruction
+    // (its operands live in uniform registers) in an ELECT / R2UR.BROADCAST waterfall loop, one trip per run.  Here every lane
+    // computes its run, then the warp walks the run starts; the values of the run's first lane are broadcast and one elected
+    // lane issues the copy (all copies of a warp therefore belong to that lane's bulk groups).
+    const uint32_t after = lane == 31 ? 0u : (m_stop >> (lane + 1));
+    const int len = after ? __ffs(after) : (32 - lane);
+    const uint32_t my_bytes = static_cast<uint32_t>(len) * ROW_BYTES;
+    const uint32_t my_src = smem_u32(my_row);
+    float* const my_dst = y + (valid ? tok : 0) * ld_out;
+    for (uint32_t m = m_start; m != 0; m &= m - 1) {
+        const int l = __ffs(m) - 1;
+        const uint32_t bytes = __shfl_sync(0xffffffffu, my_bytes, l);
+        const uint32_t src = __shfl_sync(0xffffffffu, my_src, l);
+        const uint64_t dst = __shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(my_dst), l);
+        if (add_residual)
+            asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                         "@e cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;\n\t}" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+        else
+            asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                         "@e cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n\t}" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+    }
+}
+
 // Final epilogue shared by K1/K2: accumulator (+bias) -> fp32 rows staged in shared memory in the exact global row
 // layout (720 B per token row) -> the TMA engine writes them out with one bulk copy per contiguous run of tokens.
 // With add_residual the copy is `cp.reduce.async.bulk ... add.f32`: the residual stream is updated in place
 // (y += delta), so the shortcut is never loaded into the SM.  Thread = accumulator row; the two groups fill columns
 // [96 g, 96 g + 96) of the same rows.  `half` / `nhalf` let a caller with < 92 KB of staging do the 32 rows of each
 // lane quadrant in two passes of 16.
-constexpr uint32_t ROW_BYTES = SRK_DIM * 4;     // 720
 // Staging geometry: rows 0 .. main_rows-1 of every lane quadrant live at stage_main + (q * main_rows + r) * 720, the
 // remaining rows at stage_tail + (q * (32 - main_rows) + r - main_rows) * 720 (K1 has no single 92 KB hole).
 template <typename TokFn>
 __device__ __forceinline__ void stage_rows_and_bulk_store(uint32_t tmem_acc, uint32_t lanebase, uint8_t* stage_main, uint8_t* stage_tail,
                                                           int main_rows, const float* s_bias, float* __restrict__ y, int ld_out,
                                                           int add_residual, int q, int g, int lane, TokFn tok_of_row, int act_gelu = 0,
-                                                          unsigned long long* tl = nullptr) {
+                                                          unsigned long long* tl = nullptr, const void* tmap = nullptr, int tcol = 0,
+                                                          int trow = 0, bool issue = true) {
     uint8_t* const my_row = lane < main_rows ? stage_main + (q * main_rows + lane) * ROW_BYTES
                                              : stage_tail + (q * (32 - main_rows) + lane - main_rows) * ROW_BYTES;
     float* dst = reinterpret_cast<float*>(my_row);
@@ -244,37 +302,27 @@ __device__ __forceinline__ void stage_rows_and_bulk_store(uint32_t tmem_acc, uin
     }
     if (tl) tl[50] = clock64();
     fence_proxy_async_smem();                   // generic-proxy smem writes -> visible to the bulk copy engine
+    if (!issue) return;                         // the caller synchronises and issues the copies (swin_attn_kernel: one box per window)
     named_bar_sync(2 + q, 64);                  // both groups of this lane quadrant have written their columns
     if (tl) tl[51] = clock64();
-    if (g == 0) {
-        // one bulk copy per maximal run of tokens that are contiguous in memory (and in the staging buffer)
-        const int64_t tok = tok_of_row(q * 32 + lane);
-        const int64_t prev = __shfl_up_sync(0xffffffffu, tok, 1);
-        const bool valid = tok >= 0;
-        const bool start = valid && (lane == 0 || lane == main_rows || ld_out != SRK_DIM || prev < 0 || tok != prev + 1);
-        const uint32_t m_start = __ballot_sync(0xffffffffu, start);
-        const uint32_t m_stop = m_start | ~__ballot_sync(0xffffffffu, valid);      // next start or first invalid row ends a run
-        // Issue from CONVERGENT code with warp-uniform operands: inside `if (start)` the compiler wraps the bulk-copy instruction
-        // (its operands live in uniform registers) in an ELECT / R2UR.BROADCAST waterfall loop, one trip per run.  Here every lane
-        // computes its run, then the warp walks the run starts; the values of the run's first lane are broadcast and one elected
-        // lane issues the copy (all copies of a warp therefore belong to that lane's bulk groups).
-        const uint32_t after = lane == 31 ? 0u : (m_stop >> (lane + 1));
-        const int len = after ? __ffs(after) : (32 - lane);
-        const uint32_t my_bytes = static_cast<uint32_t>(len) * ROW_BYTES;
-        const uint32_t my_src = smem_u32(my_row);
-        float* const my_dst = y + (valid ? tok : 0) * ld_out;
-        for (uint32_t m = m_start; m != 0; m &= m - 1) {
-            const int l = __ffs(m) - 1;
-            const uint32_t bytes = __shfl_sync(0xffffffffu, my_bytes, l);
-            const uint32_t src = __shfl_sync(0xffffffffu, my_src, l);
-            const uint64_t dst = __shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(my_dst), l);
-            if (add_residual)
-                asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
-                             "@e cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;\n\t}" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-            else
-                asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
-                             "@e cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n\t}" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-        }
+    if (g == 0 && tmap != nullptr) {
+        // rows wider than the 180 staged columns: ONE tensor-map TMA store of this quadrant's 32 x 180 box at (column tcol, row trow +
+        // 32 q) of the 2-D output (rows past the last token are clipped by the copy engine); main_rows must be 32.  Per-row bulk
+        // copies (720 B each, ~600 cycles of issue per copy) made the 180 -> 720 layer of DAT's SGFN cost 119 us per launch.
+        const uint32_t src = smem_u32(stage_main + q * 32 * ROW_BYTES);
+        const int r0 = trow + 32 * q;
+        if (add_residual)
+            asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                         "@e cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%1, %2}], [%3];\n\t}" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+                         "r"(tcol), "r"(r0), "r"(src) : "memory");
+        else
+            asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                         "@e cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];\n\t}" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+                         "r"(tcol), "r"(r0), "r"(src) : "memory");
+        bulk_commit();
+        __syncwarp();
+    } else if (g == 0) {
+        issue_row_runs(my_row, main_rows, y, ld_out, add_residual, q, lane, tok_of_row);
         bulk_commit();
         __syncwarp();
     }

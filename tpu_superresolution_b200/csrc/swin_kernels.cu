@@ -19,6 +19,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "kernels.h"
 #define SRK_OOL_TIMEOUT 1      // see umma.cuh: mbar_wait
@@ -28,12 +29,8 @@
 
 // swin_kernels_f16.cu compiles this file a second time with fp16 GEMM operands (umma.cuh: umma_idesc_op / pack_op2): same kernels
 // under other names, without the layer kernel and the process-wide debug / tuning globals.
-#ifdef SRK_F16_OPERANDS
-#define swin_attn_kernel swin_attn_kernel_f16
-#define swin_mlp_kernel swin_mlp_kernel_f16
-#define launch_swin_attn launch_swin_attn_f16
-#define launch_swin_mlp launch_swin_mlp_f16
-#endif
+// (the variant translation units rename swin_attn_kernel / swin_mlp_kernel / launch_swin_attn / launch_swin_mlp before including
+//  this file; SRK_ONLY_MLP leaves the attention kernel out)
 
 namespace srk {
 
@@ -52,7 +49,7 @@ constexpr float LOG2E = 1.4426950408889634f;
 
 // Optional per-CTA timeline (debug): CTA 0 writes clock64() at event `id` of its `it`-th tile.
 #ifdef SRK_NO_TIMELINE
-#define SRK_TL(dbgptr, it, id) do { } while (0)
+#define SRK_TL(dbgptr, it, id) do { (void)(dbgptr); } while (0)
 #else
 #define SRK_TL(dbgptr, it, id) do { if ((dbgptr) != nullptr && blockIdx.x == 0 && (it) < 8) (dbgptr)[(it) * 64 + (id)] = clock64(); } while (0)
 #endif
@@ -81,13 +78,17 @@ constexpr uint32_t A_XA = 0;                          // normalised x image [128
 constexpr uint32_t A_VT = A_XA + 3 * ATOM_A;          // V image [128 tokens x 192 dims]; then the O image; then the store staging
 constexpr uint32_t A_QKI = A_VT + 2 * VT_ATOM;        // 2 x [q_h | k_h] images [128 x (32+32)] (one per softmax group)
 constexpr uint32_t A_RING = A_QKI + 2 * ATOM_A;       // weight ring
-constexpr uint32_t A_VEC = A_RING + RING_N * RING_STAGE;
-constexpr uint32_t A_TAIL = A_VEC + ((SRK_ATTN_VEC_FLOATS * 4 + 127) / 128) * 128;   // staging rows 28..31 of each quadrant
-constexpr uint32_t A_BAR = A_TAIL + 16 * 720;
+// swin_attn_kernel: the store staging (128 rows x 720 B, tile-row order = two windows of 64 tokens) is ONE contiguous region -- the V^T
+// and q|k images plus a 12 KB tail right behind them -- so that a whole 8 x 8 window leaves with one tensor-map TMA store (below);
+// the weight ring follows the tail.  (The layer kernel keeps the older map: A_RING, rows 28..31 of each quadrant in a separate tail.)
+constexpr uint32_t K_TAIL = A_QKI + 2 * ATOM_A;
+constexpr uint32_t K_RING = K_TAIL + 12 * 1024;
+constexpr uint32_t A_VEC = K_RING + RING_N * RING_STAGE;
+constexpr uint32_t A_BAR = A_VEC + ((SRK_ATTN_VEC_FLOATS * 4 + 127) / 128) * 128;
 constexpr uint32_t A_END = A_BAR + 256;
 constexpr uint32_t K1_SMEM = A_END + 1024;            // + alignment slack
 static_assert(K1_SMEM <= 232448, "K1 shared memory exceeds 227 KB");
-static_assert(112 * 720 <= 2 * VT_ATOM + 2 * ATOM_A && 3 * ATOM_A <= 2 * VT_ATOM, "O image / store staging must fit");
+static_assert(128 * 720 <= 2 * VT_ATOM + 2 * ATOM_A + 12 * 1024 && 3 * ATOM_A <= 2 * VT_ATOM, "O image / store staging must fit");
 
 // TMEM columns (fp32, 128 lanes).  S and P v run as two M = 64 UMMAs per head, one per window: an M = 64 accumulator
 // occupies lanes {0-15, 32-47, 64-79, 96-111} and the second window's interleaves at lane offset 16, so both windows of
@@ -116,9 +117,10 @@ static __device__ __noinline__ void signal_progress(int* counter, int add) {
     }
 }
 
+#ifndef SRK_ONLY_MLP
 struct TileGeom {
     int64_t base[2];
-    int y0[2], x0[2];
+    int y0[2], x0[2], img[2];
     bool valid[2];
 };
 __device__ __forceinline__ void set_tile_geom(const AttnParams& p, int tile, TileGeom& geo) {
@@ -127,10 +129,11 @@ __device__ __forceinline__ void set_tile_geom(const AttnParams& p, int tile, Til
         const int gw = tile * 2 + hf;
         geo.valid[hf] = gw < p.total_windows;
         if (p.mode == SRK_MODE_WINDOWS) {
-            geo.base[hf] = static_cast<int64_t>(gw) * 64; geo.y0[hf] = 0; geo.x0[hf] = 0;
+            geo.base[hf] = static_cast<int64_t>(gw) * 64; geo.y0[hf] = 0; geo.x0[hf] = 0; geo.img[hf] = 0;
         } else {
             const int b = gw / p.nw_img, w = gw - b * p.nw_img;
             const int wy = w / p.nwx, wx = w - wy * p.nwx;
+            geo.img[hf] = b;
             geo.base[hf] = static_cast<int64_t>(b) * p.H * p.W;
             geo.y0[hf] = wy * 8 + p.shift; geo.x0[hf] = wx * 8 + p.shift;
         }
@@ -221,7 +224,19 @@ static __device__ __noinline__ uint32_t k1_gemm_k192(uint64_t* bars, uint32_t ri
     }
     return stage | (phase << 8);
 }
-__global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnParams p) {
+// 4-D tensor-map TMA store (plain or fp32 reduce-add) of one staged 8 x 8 x 180 window box at (x, y) of image b; whole warp, one lane issues
+__device__ __forceinline__ void k1_store_window(const CUtensorMap* tmap, uint32_t src, int x, int y, int b, int add) {
+    if (add)
+        asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                     "@e cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.bulk_group [%0, {%1, %2, %3, %4}], [%5];\n\t}" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+                     "r"(0), "r"(x), "r"(y), "r"(b), "r"(src) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                     "@e cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];\n\t}" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+                     "r"(0), "r"(x), "r"(y), "r"(b), "r"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnParams p, const __grid_constant__ CUtensorMap tmap_y) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t sbase = (raw + 1023u) & ~1023u;
@@ -269,7 +284,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
                     const uint32_t bytes = (s < 3 || s >= 12) ? 24576u : 16384u;
                     mbar_wait(&bars[B_EMPTY + stage], phase ^ 1);
                     mbar_arrive_expect_tx(&bars[B_FULL + stage], bytes);
-                    bulk_g2s(sm + A_RING + stage * RING_STAGE, p.wstream + off, bytes, &bars[B_FULL + stage]);
+                    bulk_g2s(sm + K_RING + stage * RING_STAGE, p.wstream + off, bytes, &bars[B_FULL + stage]);
                     off += bytes;
                     if (++stage == RING_N) { stage = 0; phase ^= 1; }
                 }
@@ -281,7 +296,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
         {
             unsigned long long* mdbg = lane == 0 ? p.dbg : nullptr;
             uint32_t ph_xa = 0, ph_vtd = 0, ph_qkr[2] = {0, 0}, ph_pr[2] = {0, 0}, ph_or = 0;
-            const uint32_t xa = sbase + A_XA, vt = sbase + A_VT, qki = sbase + A_QKI, ring = sbase + A_RING;
+            const uint32_t xa = sbase + A_XA, vt = sbase + A_VT, qki = sbase + A_QKI, ring = sbase + K_RING;
             uint32_t cur = 0;                   // weight ring cursor (stage | phase << 8)
             auto gemm_k192 = [&](uint32_t d_tmem, uint32_t img, bool img_is_a, uint32_t idesc) {
                 cur = k1_gemm_k192(bars, ring, cur, d_tmem, img, img_is_a ? 1u : 0u, idesc);
@@ -590,8 +605,30 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
             mbar_wait(&bars[B_PJF], ph_pjf); ph_pjf ^= 1;
             tc_fence_after();
             SRK_TL(dbg, it, 26);
-            stage_rows_and_bulk_store(tmem + TC_PROJ, lanebase, sm + A_VT, sm + A_TAIL, 28, s_vec + SRK_AV_BIAS_PROJ, p.y, p.ld_out,
-                                      p.add_residual, q, g, lane, tok_of_row, 0, (dbg != nullptr && blockIdx.x == 0 && it < 8) ? dbg + it * 64 : nullptr);
+            if (p.use_tmap) {
+                // SRK_MODE_IMAGE: a window's 64 staged rows are an 8 x 8 x 180 box of the (B, H, W, ld) output: ONE tensor-map store per
+                // window (a bulk copy per 8-token window row cost ~600 cycles of issue each, 16+ per tile: 2 - 3 K of a 21 K cycle tile).
+                stage_rows_and_bulk_store(tmem + TC_PROJ, lanebase, sm + A_VT, sm + A_VT, 32, s_vec + SRK_AV_BIAS_PROJ, p.y, p.ld_out,
+                                          p.add_residual, q, g, lane, tok_of_row, 0, nullptr, nullptr, 0, 0, false);
+                named_bar_sync(2 + (q >> 1), 128);          // both lane quadrants (and both column groups) of this window are staged
+                if (g == 0) {
+                    const int w = q >> 1;
+                    const int x0 = w ? geo.x0[1] : geo.x0[0], y0 = w ? geo.y0[1] : geo.y0[0];
+                    if (x0 + 8 > p.W || y0 + 8 > p.H) {
+                        // a shifted window that wraps around the image edge: the copy engine rejects negative start coordinates for
+                        // stores, so its rows leave as before (a bulk copy per contiguous run: 2 x 8 pieces per wrapped window)
+                        issue_row_runs(sm + A_VT + (q * 32 + lane) * ROW_BYTES, 32, p.y, p.ld_out, p.add_residual, q, lane, tok_of_row);
+                    } else if ((q & 1) == 0 && (w ? geo.valid[1] : geo.valid[0])) {
+                        k1_store_window(&tmap_y, sbase + A_VT + static_cast<uint32_t>(w) * 64u * ROW_BYTES, x0, y0, w ? geo.img[1] : geo.img[0],
+                                        p.add_residual);
+                    }
+                    bulk_commit();
+                    __syncwarp();
+                }
+            } else {
+                stage_rows_and_bulk_store(tmem + TC_PROJ, lanebase, sm + A_VT, sm + A_VT, 32, s_vec + SRK_AV_BIAS_PROJ, p.y, p.ld_out,
+                                          p.add_residual, q, g, lane, tok_of_row, 0, (dbg != nullptr && blockIdx.x == 0 && it < 8) ? dbg + it * 64 : nullptr);
+            }
             tc_fence_before();
             SRK_TL(dbg, it, 28);
             // the copies drain while the next tile's V^T / q|k GEMMs run; nobody may write the V^T or q|k images before that
@@ -611,6 +648,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
     SRK_TL0(p.dbg, 17);
     if (warp == 1) tmem_dealloc(tmem, 512);
 }
+
+#endif  // !SRK_ONLY_MLP
 
 // ------------------------------------------------------------------------------------------------
 // K2: MLP half
@@ -831,14 +870,14 @@ __global__ void __launch_bounds__(LNW ? NTHREADS : 320, 1) swin_mlp_kernel(const
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float4 b = b1[i];
-                        hw[2 * i] = pack_op2(gelu_fast(__uint_as_float(v0[4 * i + 0]) + b.x), gelu_fast(__uint_as_float(v0[4 * i + 1]) + b.y));
-                        hw[2 * i + 1] = pack_op2(gelu_fast(__uint_as_float(v0[4 * i + 2]) + b.z), gelu_fast(__uint_as_float(v0[4 * i + 3]) + b.w));
+                        hw[2 * i] = gelu_pack2(__uint_as_float(v0[4 * i + 0]) + b.x, __uint_as_float(v0[4 * i + 1]) + b.y);
+                        hw[2 * i + 1] = gelu_pack2(__uint_as_float(v0[4 * i + 2]) + b.z, __uint_as_float(v0[4 * i + 3]) + b.w);
                     }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float4 b = b1[8 + i];
-                        hw[16 + 2 * i] = pack_op2(gelu_fast(__uint_as_float(v1[4 * i + 0]) + b.x), gelu_fast(__uint_as_float(v1[4 * i + 1]) + b.y));
-                        hw[16 + 2 * i + 1] = pack_op2(gelu_fast(__uint_as_float(v1[4 * i + 2]) + b.z), gelu_fast(__uint_as_float(v1[4 * i + 3]) + b.w));
+                        hw[16 + 2 * i] = gelu_pack2(__uint_as_float(v1[4 * i + 0]) + b.x, __uint_as_float(v1[4 * i + 1]) + b.y);
+                        hw[16 + 2 * i + 1] = gelu_pack2(__uint_as_float(v1[4 * i + 2]) + b.z, __uint_as_float(v1[4 * i + 3]) + b.w);
                     }
                     tmem_st32(tmem + lanebase + col, hw);          // H aliases the first half of this thread's own accumulator columns
                     tmem_st_wait();
@@ -1391,14 +1430,14 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_layer_kernel(const LayerPa
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             const float4 b = b1[k];
-                            hw[2 * k] = pack_op2(gelu_fast(__uint_as_float(v0[4 * k + 0]) + b.x), gelu_fast(__uint_as_float(v0[4 * k + 1]) + b.y));
-                            hw[2 * k + 1] = pack_op2(gelu_fast(__uint_as_float(v0[4 * k + 2]) + b.z), gelu_fast(__uint_as_float(v0[4 * k + 3]) + b.w));
+                            hw[2 * k] = gelu_pack2(__uint_as_float(v0[4 * k + 0]) + b.x, __uint_as_float(v0[4 * k + 1]) + b.y);
+                            hw[2 * k + 1] = gelu_pack2(__uint_as_float(v0[4 * k + 2]) + b.z, __uint_as_float(v0[4 * k + 3]) + b.w);
                         }
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             const float4 b = b1[8 + k];
-                            hw[16 + 2 * k] = pack_op2(gelu_fast(__uint_as_float(v1[4 * k + 0]) + b.x), gelu_fast(__uint_as_float(v1[4 * k + 1]) + b.y));
-                            hw[16 + 2 * k + 1] = pack_op2(gelu_fast(__uint_as_float(v1[4 * k + 2]) + b.z), gelu_fast(__uint_as_float(v1[4 * k + 3]) + b.w));
+                            hw[16 + 2 * k] = gelu_pack2(__uint_as_float(v1[4 * k + 0]) + b.x, __uint_as_float(v1[4 * k + 1]) + b.y);
+                            hw[16 + 2 * k + 1] = gelu_pack2(__uint_as_float(v1[4 * k + 2]) + b.z, __uint_as_float(v1[4 * k + 3]) + b.w);
                         }
                         tmem_st32(tmem + lanebase + col, hw);
                         tmem_st_wait();
@@ -1437,13 +1476,46 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_layer_kernel(const LayerPa
 // launchers
 // ------------------------------------------------------------------------------------------------
 static int num_sms() { return device_num_sms(); }
+#ifndef SRK_ONLY_MLP
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(f);
+    }
+    return fn;
+}
+#endif
 
-cudaError_t launch_swin_attn(const AttnParams& p, cudaStream_t stream) {
+#ifndef SRK_ONLY_MLP
+cudaError_t launch_swin_attn(const AttnParams& p_in, cudaStream_t stream) {
     static bool configured[SRK_MAX_DEVICES] = {};
     if (cudaError_t e = configure_smem_once(configured, swin_attn_kernel, K1_SMEM); e != cudaSuccess) return e;
+    AttnParams p = p_in;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    p.use_tmap = 0;
+    if (p.mode == SRK_MODE_IMAGE) {
+        // the output as a 4-D fp32 tensor (180 x W x H x B, row pitch ld_out), box = one window (a failed encode keeps the bulk copies)
+        const int B = p.total_windows / p.nw_img;
+        const cuuint64_t ld = static_cast<cuuint64_t>(p.ld_out) * sizeof(float);
+        const cuuint64_t gdim[4] = {SRK_DIM, static_cast<cuuint64_t>(p.W), static_cast<cuuint64_t>(p.H), static_cast<cuuint64_t>(B)};
+        const cuuint64_t gstr[3] = {ld, ld * p.W, ld * p.W * p.H};
+        const cuuint32_t box[4] = {SRK_DIM, 8, 8, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        if (EncodeTiledFn enc = encode_tiled_fn())
+            if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.y, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+                p.use_tmap = 1;
+    }
     const int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
-    return launch_pdl(swin_attn_kernel, grid, K1_THREADS, K1_SMEM, stream, p);
+    return launch_pdl2(swin_attn_kernel, grid, K1_THREADS, K1_SMEM, stream, p, tmap);
 }
+#endif
 
 cudaError_t launch_swin_mlp(const MlpParams& p, cudaStream_t stream) {
     static bool configured_a[SRK_MAX_DEVICES] = {}, configured_b[SRK_MAX_DEVICES] = {};

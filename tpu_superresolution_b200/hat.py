@@ -260,7 +260,7 @@ class HAB(nn.Module):
         ca = self.conv_block.cab[3].attention                                                 # squeeze-excite gate + `+ conv_x * conv_scale` (:307)
         L.cab_gate_add(y_tok, out, ca[1].weight.reshape(ca[1].weight.shape[0], C), ca[1].bias, ca[3].weight.reshape(C, -1), ca[3].bias,
                        scale=self.conv_scale, batch=B, tokens_per_image=Ltok, y_bias=y_bias)
-        L.swin_mlp(out, out, mw, mv, num_tokens=tokens, ld_in=C, ld_out=C, apply_ln=True, add_residual=True)
+        L.swin_mlp(out, out, mw, mv, num_tokens=tokens, ld_in=C, ld_out=C, apply_ln=True, add_residual=True, operands=self.mlp.operands)
         return out
 
     def forward(self, x, x_size, rpi_sa=None, attn_mask=None):
@@ -333,7 +333,7 @@ class OCAB(nn.Module):
             out.copy_(x)
         L.linear(o, pw, pb, out, num_tokens=tokens, a_mode=L.LIN_A_PLANES, n_chunks=1, out_mode=L.LIN_OUT_ROWS, ld_out=C,
                  add_residual=True)                                                           # proj(x) + shortcut (:436)
-        L.swin_mlp(out, out, mw, mv, num_tokens=tokens, ld_in=C, ld_out=C, apply_ln=True, add_residual=True)
+        L.swin_mlp(out, out, mw, mv, num_tokens=tokens, ld_in=C, ld_out=C, apply_ln=True, add_residual=True, operands=self.mlp.operands)
         return out
 
     def forward(self, x, x_size, rpi=None):

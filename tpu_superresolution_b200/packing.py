@@ -41,12 +41,12 @@ def unswizzle_slab(slab: torch.Tensor) -> torch.Tensor:
     return swizzle_slab(slab)
 
 
-OPERAND_DTYPES = {"bf16": torch.bfloat16, "fp16": torch.float16}      # include/srk.h: SRK_OPERANDS_*
+OPERAND_DTYPES = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp16_fast": torch.float16}      # include/srk.h: SRK_OPERANDS_*
 
 
 def _slabs(mat: torch.Tensor, operands: str = "bf16") -> list:
     """(R, K) with K % 64 == 0 -> list of K/64 swizzled bf16 (or fp16) slabs in k order."""
-    if operands == "fp16" and bool((mat.abs() > 65504.0).any()):
+    if operands != "bf16" and bool((mat.abs() > 65504.0).any()):
         raise RuntimeError("packing: a weight exceeds the fp16 range; use operands='bf16'")
     mat = mat.to(OPERAND_DTYPES[operands])
     return [swizzle_slab(mat[:, k:k + 64].contiguous()) for k in range(0, mat.shape[1], 64)]

@@ -37,13 +37,22 @@ def _to_2tuple(v):
     return tuple(v) if isinstance(v, (tuple, list)) else (v, v)
 
 
+PRECISIONS = {           # mode -> (WindowAttention operands, Mlp operands)
+    "bf16": ("bf16", "fp16_fast"),          # default: bf16 attention operands; the MLP's fp16 variant is both faster and more accurate
+    "bf16_strict": ("bf16", "bf16"),        # bf16 operands everywhere (what the one-launch-per-layer kernel implements)
+    "fp16": ("fp16", "fp16"),               # tight mode: 11-bit significands, GELU in fp32
+}
+
+
 def set_precision(model: nn.Module, precision: str = "bf16") -> None:
-    """Set the GEMM operand type ("bf16" | "fp16") of every fused Mlp / WindowAttention module under `model`."""
-    if precision not in L.OPERANDS:
-        raise ValueError(f"precision must be one of {sorted(L.OPERANDS)}, got {precision!r}")
+    """Set the GEMM operand types of every fused Mlp / WindowAttention module under `model` (PRECISIONS)."""
+    if precision not in PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {precision!r}")
     for m in model.modules():
-        if isinstance(m, (Mlp, WindowAttention)):
-            m.operands = precision
+        if isinstance(m, WindowAttention):
+            m.operands = PRECISIONS[precision][0]
+        elif isinstance(m, Mlp):
+            m.operands = PRECISIONS[precision][1]
     convs.invalidate_all()
 
 
@@ -69,7 +78,9 @@ class Mlp(nn.Module):
         self.act = act_layer()
         self.fc2 = nn.Linear(hidden_features, out_features)
         self.drop = nn.Dropout(drop)
-        self.operands = "bf16"           # GEMM operand type ("fp16" = tight mode), see set_precision()
+        # GEMM operand type, see set_precision().  Default: fp16 operands + GELU on packed halves (srk.h: SRK_OPERANDS_F16_HALF_GELU)
+        # -- faster than the bf16 variant and closer to the exact GELU
+        self.operands = "fp16_fast"
         self._cache = _PackedCache()
 
     def _packed(self, norm: Optional[nn.LayerNorm] = None):
@@ -528,8 +539,9 @@ class SwinIR(nn.Module):
         return self.patch_unembed(x, x_size)
 
     def set_precision(self, precision: str = "bf16") -> "SwinIR":
-        """GEMM operand type of the fused attention / MLP kernels: "bf16" (default; gate max abs <= 2e-3 vs the reference's fp32
-        forward) or "fp16" -- the tight mode (include/srk.h: SRK_OPERANDS_F16; fp16 has TF32's 11-bit significand; gate <= 2e-4).
+        """GEMM operand types of the fused attention / MLP kernels (PRECISIONS): "bf16" (default; gate max abs <= 2e-3 vs the
+        reference's fp32 forward), "bf16_strict", or "fp16" -- the tight mode (include/srk.h: SRK_OPERANDS_F16; fp16 has TF32's
+        11-bit significand; gate <= 2e-4).
         In the tight mode the 3x3 convolutions run in fp32 on the library path (slower; the default mode's tcgen05 convolution has
         fp16 operands, which alone would exceed the tight gate).  A ``GraphedModel`` around this model must be ``reset()``."""
         set_precision(self, precision)
