@@ -217,6 +217,10 @@ int srk_cab_ws_floats(int32_t batch, int32_t tokens_per_image);
  * AdaptiveAvgPool2d(1) in front of DAT's channel interaction (dat_arch.py:305-310).  sums_ws: srk_cab_ws_floats() floats
  * (per-chunk partial sums, reduced in a fixed order). */
 int srk_token_mean_fwd(const float* x, float* mean, float* sums_ws, int32_t batch, int32_t tokens_per_image, void* stream);
+/* ... and the rest of that channel interaction in the same call: out[b] = w2 gelu(w1 mean[b] + b1) + b2 (the two 1x1 convolutions of
+ * dat_arch.py:305-310 with the eval BatchNorm folded into w1 / b1, exact GELU).  w1 (hidden, 180), w2 (180, hidden), hidden <= 64. */
+int srk_token_mean_mlp_fwd(const float* x, float* out, float* sums_ws, const float* w1, const float* b1, const float* w2, const float* b2,
+                           int32_t hidden, int32_t batch, int32_t tokens_per_image, void* stream);
 int srk_cab_gate_add(const float* y, const float* y_bias /* bias of the conv that produced y, or NULL: y + y_bias is used */, float* out, float* sums_ws, const float* w1, const float* b1, const float* w2, const float* b2,
                      int32_t hidden, float scale, int32_t batch, int32_t tokens_per_image, void* stream);
 

@@ -387,6 +387,43 @@ __global__ void __launch_bounds__(192) token_mean_reduce_kernel(const float* __r
     mean[b * SRK_DIM + c] = s / static_cast<float>(tokens_per_image);
 }
 
+// ---- ... followed by the squeeze MLP of DAT's channel interaction (dat_arch.py:305-310): out[b] = W2 gelu(W1 mean[b] + b1) + b2 with the
+//      eval BatchNorm folded into W1 / b1 and the exact (erf) GELU; one block per image, a few thousand MACs.
+__global__ void __launch_bounds__(192) token_mean_mlp_kernel(const float* __restrict__ sums, const float* __restrict__ w1,
+                                                             const float* __restrict__ b1, const float* __restrict__ w2,
+                                                             const float* __restrict__ b2, int hidden, float* __restrict__ out, int chunks,
+                                                             int tokens_per_image) {
+    __shared__ float s_mean[SRK_DIM];
+    __shared__ float s_h[64];
+    const int b = blockIdx.x, c = threadIdx.x;
+    if (c < SRK_DIM) {
+        float s = 0.f;
+        for (int k = 0; k < chunks; ++k) s += __ldg(sums + (static_cast<int64_t>(b) * chunks + k) * SRK_DIM + c);
+        s_mean[c] = s / static_cast<float>(tokens_per_image);
+    }
+    __syncthreads();
+    if (c < hidden) {
+        float a = __ldg(b1 + c);
+        for (int k = 0; k < SRK_DIM; ++k) a = fmaf(__ldg(w1 + c * SRK_DIM + k), s_mean[k], a);
+        s_h[c] = 0.5f * a * (1.0f + erff(a * 0.70710678118654752440f));
+    }
+    __syncthreads();
+    if (c < SRK_DIM) {
+        float a = __ldg(b2 + c);
+        for (int j = 0; j < hidden; ++j) a = fmaf(__ldg(w2 + c * hidden + j), s_h[j], a);
+        out[b * SRK_DIM + c] = a;
+    }
+}
+
+cudaError_t launch_token_mean_mlp(const float* x, float* out, float* sums, const float* w1, const float* b1, const float* w2, const float* b2,
+                                  int hidden, int batch, int tokens_per_image, cudaStream_t stream) {
+    if (batch <= 0 || tokens_per_image <= 0) return cudaSuccess;
+    const int chunks = (tokens_per_image + CAB_TOK_PER_BLOCK - 1) / CAB_TOK_PER_BLOCK;
+    cab_pool_kernel<<<dim3(chunks, batch), 192, 0, stream>>>(x, sums, tokens_per_image);
+    token_mean_mlp_kernel<<<batch, 192, 0, stream>>>(sums, w1, b1, w2, b2, hidden, out, chunks, tokens_per_image);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_token_mean(const float* x, float* mean, float* sums, int batch, int tokens_per_image, cudaStream_t stream) {
     if (batch <= 0 || tokens_per_image <= 0) return cudaSuccess;
     const int chunks = (tokens_per_image + CAB_TOK_PER_BLOCK - 1) / CAB_TOK_PER_BLOCK;

@@ -330,6 +330,15 @@ int srk_dat_mix_fwd(const float* att, const float* conv, const float* cmap, cons
                                      static_cast<cudaStream_t>(stream)), "srk_dat_mix_fwd");
 }
 
+int srk_token_mean_mlp_fwd(const float* x, float* out, float* sums_ws, const float* w1, const float* b1, const float* w2, const float* b2,
+                           int32_t hidden, int32_t batch, int32_t tokens_per_image, void* stream) {
+    if (!x || !out || !sums_ws || !w1 || !b1 || !w2 || !b2) return fail("srk_token_mean_mlp_fwd: null argument");
+    if (batch < 0 || batch > 65535 || tokens_per_image < 0 || hidden < 1 || hidden > 64) return fail("srk_token_mean_mlp_fwd: bad shape");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return check(srk::launch_token_mean_mlp(x, out, sums_ws, w1, b1, w2, b2, hidden, batch, tokens_per_image, static_cast<cudaStream_t>(stream)),
+                 "srk_token_mean_mlp_fwd");
+}
+
 int srk_token_mean_fwd(const float* x, float* mean, float* sums_ws, int32_t batch, int32_t tokens_per_image, void* stream) {
     if (!x || !mean || !sums_ws) return fail("srk_token_mean_fwd: null argument");
     if (batch < 0 || batch > 65535 || tokens_per_image < 0) return fail("srk_token_mean_fwd: bad shape");

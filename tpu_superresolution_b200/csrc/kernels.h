@@ -198,6 +198,8 @@ cudaError_t launch_stitch_accumulate(const float* tiles, float* E, float* Wt, co
                                      int channels, int tile_h, int tile_w, int out_h, int out_w, cudaStream_t stream);
 int cab_ws_floats(int batch, int tokens_per_image);
 cudaError_t launch_token_mean(const float* x, float* mean, float* sums, int batch, int tokens_per_image, cudaStream_t stream);
+cudaError_t launch_token_mean_mlp(const float* x, float* out, float* sums, const float* w1, const float* b1, const float* w2, const float* b2,
+                                  int hidden, int batch, int tokens_per_image, cudaStream_t stream);
 int channel_gram_ws_floats(int batch, int tokens_per_image);
 cudaError_t launch_cab_gate_add(const float* y, const float* y_bias, float* out, float* sums, const float* w1, const float* b1, const float* w2,
                                 const float* b2, int hidden, float scale, int batch, int tokens_per_image, cudaStream_t stream);

@@ -239,8 +239,19 @@ class _AIM(nn.Module):
     def _channel_map(self, rows):
         """channel_interaction (dat_arch.py:305-310) on (B, N, C) rows -> (B, C) map before the sigmoid; a few hundred MACs per image."""
         B, N, C = rows.shape
-        pooled = L.token_mean(rows.contiguous(), batch=B, tokens_per_image=N)        # AdaptiveAvgPool2d(1), deterministic
-        return self.channel_interaction[1:](pooled.view(B, C, 1, 1)).reshape(B, C).contiguous()
+        c1, bn1, c4 = self.channel_interaction[1], self.channel_interaction[2], self.channel_interaction[4]
+        ps = [c1.weight, c1.bias, bn1.weight, bn1.bias, bn1.running_mean, bn1.running_var, c4.weight, c4.bias]
+
+        def build():
+            s1 = bn1.weight.detach() / torch.sqrt(bn1.running_var + bn1.eps)
+            w1 = (c1.weight.detach().reshape(c1.weight.shape[0], C) * s1[:, None]).contiguous()
+            b1 = ((c1.bias.detach() - bn1.running_mean) * s1 + bn1.bias.detach()).contiguous()
+            return w1, b1, c4.weight.detach().reshape(C, -1).contiguous(), c4.bias.detach().contiguous()
+        if not hasattr(self, "_cmap_cache"):
+            self._cmap_cache = _PackedCache()
+        w1, b1, w2, b2 = self._cmap_cache.get(ps, build)
+        # AdaptiveAvgPool2d(1) (deterministic) + conv1x1 + BatchNorm + GELU + conv1x1 in one call
+        return L.token_mean_mlp(rows.contiguous(), w1, b1, w2, b2, batch=B, tokens_per_image=N)
 
     def _mix(self, att, conv_x, cmap, mode):
         w1, b1, w2, b2 = self._aim_packed()[3:]
