@@ -246,6 +246,9 @@ int srk_dat_mix_fwd(const float* att, const float* conv, const float* cmap, cons
 int srk_dat_channel_gram_fwd(const float* qkv, float* gram, float* ws /* srk_dat_channel_gram_ws_floats() */, int32_t batch,
                              int32_t tokens_per_image, void* stream);
 int srk_dat_channel_gram_ws_floats(int32_t batch, int32_t tokens_per_image);
+/* attn[b][h][d1][:] = softmax(gram[d1][:] / (max(sqrt(sum q_d1^2), 1e-12) max(sqrt(sum k_d2^2), 1e-12)) * temperature[h]): F.normalize
+ * over the tokens, the temperature and the softmax of dat_arch.py:497-503 on the output of srk_dat_channel_gram_fwd; temperature (6). */
+int srk_dat_channel_softmax_fwd(const float* gram, const float* temperature, float* attn, int32_t batch, void* stream);
 int srk_dat_channel_apply_fwd(const float* qkv, const float* attn, float* out, int32_t batch, int32_t tokens_per_image, void* stream);
 
 /* PixelShuffle(r) on channels-last activations, optional fused LeakyReLU:

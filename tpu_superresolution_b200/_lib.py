@@ -169,6 +169,7 @@ def load():
     lib.srk_dat_channel_gram_ws_floats.argtypes = [c_int32, c_int32]
     lib.srk_cab_ws_floats.argtypes = [c_int32, c_int32]
     lib.srk_token_mean_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]
+    lib.srk_dat_channel_softmax_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_void_p]
     lib.srk_token_mean_mlp_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]
     lib.srk_dat_channel_apply_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]
     lib.srk_cab_gate_add.argtypes = [c_void_p] * 8 + [c_int32, ctypes.c_float, c_int32, c_int32, c_void_p]
@@ -184,7 +185,7 @@ def load():
               "srk_stitch_accumulate", "srk_stitch_normalize", "srk_gather_tiles", "srk_stitch_accumulate_strided", "srk_stitch_finalize",
               "srk_conv3x3_fwd", "srk_rows_to_f16", "srk_image_to_f16_split", "srk_linear_fwd", "srk_window_attention_fwd",
               "srk_window_attention_table_floats", "srk_cab_gate_add", "srk_dwconv3x3_rows_fwd", "srk_row_stats_fwd", "srk_dat_mix_fwd",
-              "srk_dat_channel_gram_fwd", "srk_dat_channel_apply_fwd", "srk_dat_channel_gram_ws_floats", "srk_cab_ws_floats", "srk_token_mean_fwd", "srk_token_mean_mlp_fwd"):
+              "srk_dat_channel_gram_fwd", "srk_dat_channel_apply_fwd", "srk_dat_channel_gram_ws_floats", "srk_cab_ws_floats", "srk_token_mean_fwd", "srk_token_mean_mlp_fwd", "srk_dat_channel_softmax_fwd"):
         getattr(lib, f).restype = c_int32
     if lib.srk_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libsrk.so ABI {lib.srk_abi_version()} != expected {ABI_VERSION}; rebuild")
@@ -198,7 +199,7 @@ EXPORTS = ("srk_abi_version", "srk_last_error_string", "srk_launch_count", "srk_
            "srk_conv3x3_fwd", "srk_rows_to_f16", "srk_image_to_f16_split", "srk_debug_set_timeline", "srk_debug_set_stagger",
            "srk_linear_fwd", "srk_window_attention_fwd", "srk_window_attention_table_floats", "srk_debug_set_winattn_stagger", "srk_debug_set_pdl",
            "srk_cab_gate_add", "srk_dwconv3x3_rows_fwd", "srk_row_stats_fwd", "srk_dat_mix_fwd", "srk_dat_channel_gram_fwd",
-           "srk_dat_channel_apply_fwd", "srk_dat_channel_gram_ws_floats", "srk_cab_ws_floats", "srk_token_mean_fwd", "srk_token_mean_mlp_fwd")
+           "srk_dat_channel_apply_fwd", "srk_dat_channel_gram_ws_floats", "srk_cab_ws_floats", "srk_token_mean_fwd", "srk_token_mean_mlp_fwd", "srk_dat_channel_softmax_fwd")
 
 
 def _check(rc: int, lib) -> None:
@@ -484,6 +485,16 @@ def token_mean_mlp(x, w1, b1, w2, b2, *, batch, tokens_per_image):
         _check(lib.srk_token_mean_mlp_fwd(x.data_ptr(), out.data_ptr(), ws.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
                                           w1.shape[0], batch, tokens_per_image, st), lib)
     return out
+
+
+def dat_channel_softmax(gram, temperature, *, batch):
+    """srk_dat_channel_softmax_fwd: (batch, 6, 960) gram -> (batch, 6, 30, 30) attention (normalisation, temperature, softmax)."""
+    lib = load()
+    _require_cuda_f32(gram, temperature)
+    attn = torch.empty((batch, HEADS, HEAD_DIM, HEAD_DIM), dtype=torch.float32, device=gram.device)
+    with _launch("dat_channel_softmax", gram, temperature) as st:
+        _check(lib.srk_dat_channel_softmax_fwd(gram.data_ptr(), temperature.data_ptr(), attn.data_ptr(), batch, st), lib)
+    return attn
 
 
 def _ptr(t):

@@ -402,14 +402,18 @@ __global__ void __launch_bounds__(192) token_mean_mlp_kernel(const float* __rest
         s_mean[c] = s / static_cast<float>(tokens_per_image);
     }
     __syncthreads();
-    if (c < hidden) {
-        float a = __ldg(b1 + c);
-        for (int k = 0; k < SRK_DIM; ++k) a = fmaf(__ldg(w1 + c * SRK_DIM + k), s_mean[k], a);
-        s_h[c] = 0.5f * a * (1.0f + erff(a * 0.70710678118654752440f));
+    for (int j = c >> 5; j < hidden; j += 6) {             // warp per hidden unit: lane-strided dot product, butterfly sum
+        float a = 0.f;
+        for (int k = c & 31; k < SRK_DIM; k += 32) a = fmaf(__ldg(w1 + j * SRK_DIM + k), s_mean[k], a);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        a += __ldg(b1 + j);
+        if ((c & 31) == 0) s_h[j] = 0.5f * a * (1.0f + erff(a * 0.70710678118654752440f));
     }
     __syncthreads();
     if (c < SRK_DIM) {
         float a = __ldg(b2 + c);
+#pragma unroll 8
         for (int j = 0; j < hidden; ++j) a = fmaf(__ldg(w2 + c * hidden + j), s_h[j], a);
         out[b * SRK_DIM + c] = a;
     }

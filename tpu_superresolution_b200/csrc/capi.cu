@@ -355,6 +355,12 @@ int srk_dat_channel_gram_fwd(const float* qkv, float* gram, float* ws, int32_t b
     return check(srk::launch_channel_gram(qkv, gram, ws, batch, tokens_per_image, static_cast<cudaStream_t>(stream)), "srk_dat_channel_gram_fwd");
 }
 
+int srk_dat_channel_softmax_fwd(const float* gram, const float* temperature, float* attn, int32_t batch, void* stream) {
+    if (!gram || !temperature || !attn) return fail("srk_dat_channel_softmax_fwd: null argument");
+    if (batch < 0 || batch > 65535) return fail("srk_dat_channel_softmax_fwd: bad shape");
+    return check(srk::launch_channel_softmax(gram, temperature, attn, batch, static_cast<cudaStream_t>(stream)), "srk_dat_channel_softmax_fwd");
+}
+
 int srk_dat_channel_apply_fwd(const float* qkv, const float* attn, float* out, int32_t batch, int32_t tokens_per_image, void* stream) {
     if (!qkv || !attn || !out) return fail("srk_dat_channel_apply_fwd: null argument");
     if (batch < 0 || batch > 65535 || tokens_per_image <= 0) return fail("srk_dat_channel_apply_fwd: bad shape");

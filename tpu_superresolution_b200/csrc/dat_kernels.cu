@@ -472,6 +472,38 @@ cudaError_t launch_channel_gram(const float* qkv, float* gram, float* ws, int ba
     return cudaGetLastError();
 }
 
+// ---- attn[b][h] = softmax_d2( gram[d1][d2] / (max(|q_d1|, eps) max(|k_d2|, eps)) * temperature[h] ): the F.normalize of q and k over
+//      the tokens folded into the 30 x 30 logits (dat_arch.py:497-503).  One warp per (image, head), lane = row d1.
+__global__ void __launch_bounds__(32) channel_softmax_kernel(const float* __restrict__ gram, const float* __restrict__ temperature,
+                                                             float* __restrict__ attn) {
+    constexpr int D = SRK_HEAD_DIM;
+    const int h = blockIdx.x, b = blockIdx.y, i = threadIdx.x;
+    const float* g = gram + (static_cast<int64_t>(b) * SRK_HEADS + h) * (D * D + 2 * D);
+    __shared__ float s_nk[D];
+    if (i < D) s_nk[i] = fmaxf(sqrtf(g[D * D + D + i]), 1e-12f);
+    __syncwarp();
+    if (i >= D) return;
+    const float nq = fmaxf(sqrtf(g[D * D + i]), 1e-12f), t = __ldg(temperature + h);
+    float l[D], mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        l[j] = g[i * D + j] / (nq * s_nk[j]) * t;
+        mx = fmaxf(mx, l[j]);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < D; ++j) { l[j] = expf(l[j] - mx); sum += l[j]; }
+    float* o = attn + ((static_cast<int64_t>(b) * SRK_HEADS + h) * D + i) * D;
+#pragma unroll
+    for (int j = 0; j < D; ++j) o[j] = l[j] / sum;
+}
+
+cudaError_t launch_channel_softmax(const float* gram, const float* temperature, float* attn, int batch, cudaStream_t stream) {
+    if (batch <= 0) return cudaSuccess;
+    channel_softmax_kernel<<<dim3(SRK_HEADS, batch), 32, 0, stream>>>(gram, temperature, attn);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_channel_apply(const float* qkv, const float* attn, float* out, int batch, int tokens_per_image, cudaStream_t stream) {
     if (batch <= 0 || tokens_per_image <= 0) return cudaSuccess;
     dim3 grid((tokens_per_image + APPLY_TOK - 1) / APPLY_TOK, batch);

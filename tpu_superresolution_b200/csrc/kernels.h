@@ -211,6 +211,7 @@ cudaError_t launch_dat_mix(const float* att, const float* conv, const float* cma
                            float b2, int hidden, int mode, float* mix, int64_t tokens, int tokens_per_image, cudaStream_t stream);
 cudaError_t launch_channel_gram(const float* qkv, float* gram, float* ws, int batch, int tokens_per_image, cudaStream_t stream);
 cudaError_t launch_channel_apply(const float* qkv, const float* attn, float* out, int batch, int tokens_per_image, cudaStream_t stream);
+cudaError_t launch_channel_softmax(const float* gram, const float* temperature, float* attn, int batch, cudaStream_t stream);
 cudaError_t launch_stitch_normalize(float* E, const float* Wt, int channels, int64_t pixels, cudaStream_t stream);
 
 // conv_kernel.cu

@@ -432,9 +432,8 @@ class Adaptive_Channel_Attention(_AIM):
         # values (torch); then attn @ v per token (srk_dat_channel_apply_fwd)
         gram = torch.empty((B, nh, d * d + 2 * d), dtype=torch.float32, device=x.device)
         L.dat_channel_gram(qkv, gram, batch=B, tokens_per_image=N)
-        nq = gram[..., d * d:d * d + d].sqrt().clamp_min(1e-12)                                # F.normalize over the tokens (:497-498)
-        nk = gram[..., d * d + d:].sqrt().clamp_min(1e-12)
-        attn = (gram[..., :d * d].view(B, nh, d, d) / (nq[..., :, None] * nk[..., None, :]) * self.temperature).softmax(dim=-1).contiguous()
+        # F.normalize over the tokens (:497-498), temperature, softmax: srk_dat_channel_softmax_fwd
+        attn = L.dat_channel_softmax(gram, self.temperature.reshape(-1).contiguous(), batch=B)
         att = torch.empty((B, N, C), dtype=torch.float32, device=x.device)
         L.dat_channel_apply(qkv, attn, att, batch=B, tokens_per_image=N)
         conv_x = self._conv_branch(qkv, 3 * C, 2 * C, B, H, W)
