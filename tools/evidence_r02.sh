@@ -1,19 +1,33 @@
+# Final evidence of round 2 (one B200): run under gpurun from the repo root, e.g.
+#   gpurun --timeout 1500 -- 'bash tools/evidence_r02.sh r02j'
+# Everything lands in gpurun_out/<tag>_*; copy what should be judged into profiles/.
 set -x
-cd $GRAFT_REPO_ROOT
-timeout 300 python -m pytest tests/test_validate_tool.py -q -m gpu 2>&1 | tail -3
+T=${1:-r02j}
+cd ${GRAFT_REPO_ROOT:-.}
+O=gpurun_out
+timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -15 > $O/${T}_pytest_gpu.log
+tail -1 $O/${T}_pytest_gpu.log
+# ---- bench lines (never under a profiler)
+timeout 400 python bench.py --steps 50 --warmup 5 > $O/${T}_bench_swinir_x4.json 2> $O/${T}_bench.err
+for w in hat_x4 dat_x2; do timeout 300 python bench.py --workload $w --steps 20 --warmup 5 > $O/${T}_bench_$w.json 2>> $O/${T}_bench.err; done
+timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > $O/${T}_bench_reference.json 2>> $O/${T}_bench.err
+timeout 120 python tools/kbench_pair.py > $O/${T}_kbench_pair.log 2>&1
+timeout 120 python tools/kbench_conv.py > $O/${T}_kbench_conv.log 2>&1
+SRK_LIB=$PWD/tpu_superresolution_b200/lib/libsrk_dbg.so timeout 120 python tools/timeline.py > $O/${T}_timeline.log 2>&1
+# ---- ncu launch lists of one steady-state forward per family (after the plain run has exited 0)
 for w in swinir_x4 hat_x4 dat_x2; do
-  python tools/run_forward_any.py $w 3 > gpurun_out/plain_$w.log 2>&1 && \
-  ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/r02_${w}_ncu_launches.csv python tools/run_forward_any.py $w 3 > gpurun_out/ncu_$w.log 2>&1
-  tail -1 gpurun_out/ncu_$w.log
+  python tools/run_forward_any.py $w 3 > $O/plain_$w.log 2>&1 && \
+  ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $O/${T}_${w}_ncu_launches.csv python tools/run_forward_any.py $w 3 > $O/ncu_$w.log 2>&1
+  python tools/ncu_launch_summary.py $O/${T}_${w}_ncu_launches.csv > $O/${T}_${w}_ncu_launch_summary.txt
 done
-python tools/run_forward_any.py swinir_x4 3 > gpurun_out/plain_full.log 2>&1 && \
-ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:conv3x3_kernel -s 1 -c 1 -o gpurun_out/r02_prof_conv python tools/run_forward_any.py swinir_x4 3 > gpurun_out/ncu_full1.log 2>&1
-python tools/run_forward_any.py swinir_x4 3 > gpurun_out/plain_full.log 2>&1 && \
-ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:swin_attn_kernel -s 2 -c 1 -o gpurun_out/r02_prof_attn python tools/run_forward_any.py swinir_x4 3 > gpurun_out/ncu_full2.log 2>&1
-python tools/run_forward_any.py swinir_x4 3 > gpurun_out/plain_full.log 2>&1 && \
-ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:swin_mlp_kernel -s 2 -c 1 -o gpurun_out/r02_prof_mlp python tools/run_forward_any.py swinir_x4 3 > gpurun_out/ncu_full3.log 2>&1
-python tools/run_forward_any.py hat_x4 3 > gpurun_out/plain_full.log 2>&1 && \
-ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:winattn_kernel -s 2 -c 1 -o gpurun_out/r02_prof_winattn python tools/run_forward_any.py hat_x4 3 > gpurun_out/ncu_full4.log 2>&1
-python tools/run_forward_any.py dat_x2 3 > gpurun_out/plain_full.log 2>&1 && \
-ncu --set full --clock-control none --profile-from-start off -k "regex:dwconv3x3_rows|dat_mix|channel_gram|channel_apply|token_linear|row_stats|rows_to_f16|cab_gate" -s 8 -c 12 -o gpurun_out/r02_prof_dat_aux python tools/run_forward_any.py dat_x2 3 > gpurun_out/ncu_full5.log 2>&1
-ls -la gpurun_out/*.ncu-rep
+# ---- ncu --set full of the top kernels (one launch each)
+full() {  # name, kernel regex, workload, skip
+  python tools/run_forward_any.py $3 3 > $O/plain_full.log 2>&1 && \
+  ncu --set full --clock-control none --import-source on --profile-from-start off -k "regex:$2" -s $4 -c 1 -o $O/${T}_prof_$1 -f python tools/run_forward_any.py $3 3 > $O/ncu_full_$1.log 2>&1
+}
+full attn swin_attn_kernel swinir_x4 2
+full mlp swin_mlp_kernel swinir_x4 2
+full conv conv3x3_kernel swinir_x4 1
+full winattn winattn_kernel hat_x4 2
+full linear token_linear_kernel dat_x2 3
+ls -la $O/${T}_*

@@ -8,7 +8,7 @@ from ctypes import c_int32, c_int64, c_void_p, c_char_p, POINTER, Structure
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsrk.so")
+LIB_PATH = os.environ.get("SRK_LIB") or os.path.join(_HERE, "lib", "libsrk.so")      # SRK_LIB: the debug build (__graft_entry__.build_debug)
 
 # mirrors of the #defines in include/srk.h
 ABI_VERSION = 2
