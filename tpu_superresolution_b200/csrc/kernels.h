@@ -27,6 +27,7 @@ struct AttnParams {
     const int* prog_wait;
     int wait_target;
     int use_tmap;              // swin_attn_kernel: the output tensor map (second kernel argument) is valid
+    uint32_t div_img_m, div_img_s, div_nwx_m, div_nwx_s;      // multiply-high constants of / nw_img and / nwx (launch_swin_attn sets them)
 };
 
 struct MlpParams {

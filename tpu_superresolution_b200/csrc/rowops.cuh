@@ -27,61 +27,68 @@ template <typename PtrFn>
 __device__ __forceinline__ void ln_rows_to_image_p(int apply_ln, uint32_t xa, int cw8, int lane, PtrFn row_ptr) {
     const int l16 = lane & 15;
     const bool live2 = l16 < 13;            // float4 index l16 + 32 < 45
-    float4 v[8][3];
+    // Two rolled halves of four passes (8 rows each): half the straight-line code of an 8-pass body.  This routine runs once per tile
+    // and role, so its instructions are fetched cold every time (ncu: the kernel's no-instruction stalls concentrate here; the first
+    // tile of a launch spent ~14 K cycles in it) -- the second half now hits the instruction cache, at the price of two exposed
+    // memory latencies (12 loads in flight per lane) instead of one.
+#pragma unroll 1
+    for (int hb = 0; hb < 2; ++hb) {
+        float4 v[4][3];
 #pragma unroll
-    for (int pass = 0; pass < 8; ++pass) {
-        const float* rp = row_ptr(pass);
-        const float4* src = reinterpret_cast<const float4*>(rp) + l16;
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        v[pass][0] = rp ? ld_cg_f4(src) : z;              // through L2 (see umma.cuh: image progress counters)
-        v[pass][1] = rp ? ld_cg_f4(src + 16) : z;
-        v[pass][2] = (rp && live2) ? ld_cg_f4(src + 32) : z;
-    }
-    // statistics of all 8 passes first, then the 4 butterfly rounds over all passes at once: the 16 shuffles of a
-    // round are independent, so their latency overlaps instead of serialising 8 x 4 dependent steps
-    float s[8], q[8];
-#pragma unroll
-    for (int pass = 0; pass < 8; ++pass) {
-        float4(&w)[3] = v[pass];
-        s[pass] = 0.f; q[pass] = 0.f;
-#pragma unroll
-        for (int jj = 0; jj < 3; ++jj) {
-            s[pass] += (w[jj].x + w[jj].y) + (w[jj].z + w[jj].w);
-            q[pass] = fmaf(w[jj].x, w[jj].x, q[pass]); q[pass] = fmaf(w[jj].y, w[jj].y, q[pass]);
-            q[pass] = fmaf(w[jj].z, w[jj].z, q[pass]); q[pass] = fmaf(w[jj].w, w[jj].w, q[pass]);
+        for (int pp = 0; pp < 4; ++pp) {
+            const float* rp = row_ptr(4 * hb + pp);
+            const float4* src = reinterpret_cast<const float4*>(rp) + l16;
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            v[pp][0] = rp ? ld_cg_f4(src) : z;              // through L2 (see umma.cuh: image progress counters)
+            v[pp][1] = rp ? ld_cg_f4(src + 16) : z;
+            v[pp][2] = (rp && live2) ? ld_cg_f4(src + 32) : z;
         }
-    }
-    if (apply_ln) {
+        // statistics of all passes first, then the 4 butterfly rounds over all passes at once: the shuffles of a round are
+        // independent, so their latency overlaps instead of serialising dependent steps
+        float s[4], q[4];
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {
-#pragma unroll
-            for (int pass = 0; pass < 8; ++pass) {
-                s[pass] += __shfl_xor_sync(0xffffffffu, s[pass], o);
-                q[pass] += __shfl_xor_sync(0xffffffffu, q[pass], o);
-            }
-        }
-    }
-    const uint32_t r0 = cw8 * 16 + (lane >> 4);
-#pragma unroll
-    for (int pass = 0; pass < 8; ++pass) {
-        float4(&w)[3] = v[pass];
-        if (apply_ln) {
-            const float mean = s[pass] * (1.0f / SRK_DIM);
-            const float var = fmaxf(fmaf(-mean, mean, q[pass] * (1.0f / SRK_DIM)), 0.f);
-            const float rstd = rsqrtf(var + 1e-5f);
-            const float nm = -mean * rstd;
+        for (int pp = 0; pp < 4; ++pp) {
+            float4(&w)[3] = v[pp];
+            s[pp] = 0.f; q[pp] = 0.f;
 #pragma unroll
             for (int jj = 0; jj < 3; ++jj) {
-                w[jj].x = fmaf(w[jj].x, rstd, nm); w[jj].y = fmaf(w[jj].y, rstd, nm);
-                w[jj].z = fmaf(w[jj].z, rstd, nm); w[jj].w = fmaf(w[jj].w, rstd, nm);
+                s[pp] += (w[jj].x + w[jj].y) + (w[jj].z + w[jj].w);
+                q[pp] = fmaf(w[jj].x, w[jj].x, q[pp]); q[pp] = fmaf(w[jj].y, w[jj].y, q[pp]);
+                q[pp] = fmaf(w[jj].z, w[jj].z, q[pp]); q[pp] = fmaf(w[jj].w, w[jj].w, q[pp]);
             }
-            if (!live2) w[2] = make_float4(0.f, 0.f, 0.f, 0.f);      // padded channels 180..191 stay exactly zero
         }
-        const uint32_t r = r0 + 2 * pass;
-        const uint32_t off = xa + sw128_off(r, l16 >> 1) + (l16 & 1) * 8;
+        if (apply_ln) {
 #pragma unroll
-        for (int jj = 0; jj < 3; ++jj)      // channel 4f = 64*jj + 4*l16 -> atom jj, chunk l16>>1, byte (l16&1)*8
-            st_shared_v2(off + jj * ATOM_A, pack_op2(w[jj].x, w[jj].y), pack_op2(w[jj].z, w[jj].w));
+            for (int o = 8; o > 0; o >>= 1) {
+#pragma unroll
+                for (int pp = 0; pp < 4; ++pp) {
+                    s[pp] += __shfl_xor_sync(0xffffffffu, s[pp], o);
+                    q[pp] += __shfl_xor_sync(0xffffffffu, q[pp], o);
+                }
+            }
+        }
+        const uint32_t r0 = cw8 * 16 + 8 * hb + (lane >> 4);
+#pragma unroll
+        for (int pp = 0; pp < 4; ++pp) {
+            float4(&w)[3] = v[pp];
+            if (apply_ln) {
+                const float mean = s[pp] * (1.0f / SRK_DIM);
+                const float var = fmaxf(fmaf(-mean, mean, q[pp] * (1.0f / SRK_DIM)), 0.f);
+                const float rstd = rsqrtf(var + 1e-5f);
+                const float nm = -mean * rstd;
+#pragma unroll
+                for (int jj = 0; jj < 3; ++jj) {
+                    w[jj].x = fmaf(w[jj].x, rstd, nm); w[jj].y = fmaf(w[jj].y, rstd, nm);
+                    w[jj].z = fmaf(w[jj].z, rstd, nm); w[jj].w = fmaf(w[jj].w, rstd, nm);
+                }
+                if (!live2) w[2] = make_float4(0.f, 0.f, 0.f, 0.f);      // padded channels 180..191 stay exactly zero
+            }
+            const uint32_t r = r0 + 2 * pp;
+            const uint32_t off = xa + sw128_off(r, l16 >> 1) + (l16 & 1) * 8;
+#pragma unroll
+            for (int jj = 0; jj < 3; ++jj)      // channel 4f = 64*jj + 4*l16 -> atom jj, chunk l16>>1, byte (l16&1)*8
+                st_shared_v2(off + jj * ATOM_A, pack_op2(w[jj].x, w[jj].y), pack_op2(w[jj].z, w[jj].w));
+        }
     }
 }
 template <typename TokFn>

@@ -140,6 +140,28 @@ __device__ __forceinline__ void set_tile_geom(const AttnParams& p, int tile, Til
     }
 }
 
+// swin_attn_kernel: the same with the two divisions by launch constants done as multiply-high (host-computed magic numbers,
+// AttnParams::div_*): set_tile_geom is inlined at four places of the kernel and an integer division is ~40 instructions.
+__device__ __forceinline__ int fast_div(int n, uint32_t magic, uint32_t shift) {       // n / d for 0 <= n < 2^31, see div_magic()
+    return static_cast<int>((__umulhi(static_cast<uint32_t>(n), magic) + static_cast<uint32_t>(n)) >> shift);
+}
+__device__ __forceinline__ void set_tile_geom_k1(const AttnParams& p, int tile, TileGeom& geo) {
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+        const int gw = tile * 2 + hf;
+        geo.valid[hf] = gw < p.total_windows;
+        if (p.mode == SRK_MODE_WINDOWS) {
+            geo.base[hf] = static_cast<int64_t>(gw) * 64; geo.y0[hf] = 0; geo.x0[hf] = 0; geo.img[hf] = 0;
+        } else {
+            const int b = fast_div(gw, p.div_img_m, p.div_img_s), w = gw - b * p.nw_img;
+            const int wy = fast_div(w, p.div_nwx_m, p.div_nwx_s), wx = w - wy * p.nwx;
+            geo.img[hf] = b;
+            geo.base[hf] = static_cast<int64_t>(b) * p.H * p.W;
+            geo.y0[hf] = wy * 8 + p.shift; geo.x0[hf] = wx * 8 + p.shift;
+        }
+    }
+}
+
 // token index of tile row r (-1: padding window).  Selects instead of geo.x[hf]: a runtime index would put geo in local memory.
 __device__ __forceinline__ int64_t tile_tok(const AttnParams& p, const TileGeom& geo, int r) {
     const bool hi = r >= 64;
@@ -271,7 +293,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
     SRK_TL0(p.dbg, 15);
     // whole warp: returns the residual stream's base once the image of `tile` has been finished by the previous kernel
     auto tile_ready = [&](int tile) -> const float* {
-        return p.x + progress_wait(flag_wait ? p.prog_wait + (tile * 2) / p.nw_img : nullptr, p.wait_target);
+        return p.x + progress_wait(flag_wait ? p.prog_wait + fast_div(tile * 2, p.div_img_m, p.div_img_s) : nullptr, p.wait_target);
     };
 
     if (warp == 0) {
@@ -379,7 +401,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
         if (static_cast<int>(blockIdx.x) < p.n_tiles) mbar_arrive(&bars[B_XA]);      // first tile: the row warps do all of it
         for (int tile = blockIdx.x; tile + static_cast<int>(gridDim.x) < p.n_tiles; tile += gridDim.x) {
             const float* xb = tile_ready(tile + gridDim.x);
-            set_tile_geom(p, tile + gridDim.x, geo);
+            set_tile_geom_k1(p, tile + gridDim.x, geo);
             uint2 hb[8][3];
             {
                 const RowSrc16 rs = make_row_src16(p, xb, geo, 64 + 32 * lw, lane);
@@ -404,7 +426,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
         unsigned long long* udbg = threadIdx.x == 320 ? p.dbg : nullptr;
         auto ln_tile = [&](int tile) {               // gather + normalise rows [0, 64) of the next tile -> x image (16 rows per warp)
             const float* xb = tile_ready(tile);
-            set_tile_geom(p, tile, geo);
+            set_tile_geom_k1(p, tile, geo);
             k1_ln16(p, xb, geo, xa, cwu, lane);
             fence_proxy_async_smem();
             mbar_arrive(&bars[B_XA]);
@@ -465,7 +487,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
         stagger_start(p.stagger);
         if (static_cast<int>(blockIdx.x) < p.n_tiles) {      // first tile's x image (later ones: the utility warps, one tile ahead)
             const float* xb = tile_ready(blockIdx.x);
-            set_tile_geom(p, blockIdx.x, geo);
+            set_tile_geom_k1(p, blockIdx.x, geo);
             k1_ln16(p, xb, geo, sbase + A_XA, cw8, lane);
             fence_proxy_async_smem();
             named_bar_sync(1, NROWTHREADS);
@@ -477,16 +499,16 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
         // runs (the row warps would only wait), not between the store and the next tile's first epilogue.
         struct RowState { TileGeom geo; uint32_t mh, mw; const float* emask; };
         auto prep = [&](int tile, RowState& st) {
-            set_tile_geom(p, tile, st.geo);
+            set_tile_geom_k1(p, tile, st.geo);
             const int gw_row = tile * 2 + half;
             st.mh = 0xffu; st.mw = 0xffu;
             if (p.mask_mode == SRK_MASK_SHIFT) {
-                const int w = gw_row % p.nw_img;
-                const int wy = w / p.nwx, wx = w - wy * p.nwx;
+                const int w = gw_row - fast_div(gw_row, p.div_img_m, p.div_img_s) * p.nw_img;
+                const int wy = fast_div(w, p.div_nwx_m, p.div_nwx_s), wx = w - wy * p.nwx;
                 auto reg = [&](int pos, int L) { return (pos >= L - 8 ? 1 : 0) + (pos >= L - p.shift ? 1 : 0); };
                 const int rh = reg(wy * 8 + (t >> 3), p.H), rw = reg(wx * 8 + (t & 7), p.W);
                 st.mh = 0; st.mw = 0;
-#pragma unroll
+#pragma unroll 1
                 for (int a = 0; a < 8; ++a) {
                     st.mh |= (reg(wy * 8 + a, p.H) == rh ? 1u : 0u) << a;
                     st.mw |= (reg(wx * 8 + a, p.W) == rw ? 1u : 0u) << a;
@@ -500,7 +522,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
         if (static_cast<int>(blockIdx.x) < p.n_tiles) prep(blockIdx.x, nxt);
         // progress counters: group 0 (the threads that issue the bulk stores) reports a tile once its writes have completed --
         // not right after the store but after the next tile's first softmax, when the copies are long done and nothing stalls
-        auto signal_tile = [&](int tile) { signal_progress(p.prog_sig + (tile * 2) / p.nw_img, min(2, p.total_windows - 2 * tile)); };
+        auto signal_tile = [&](int tile) { signal_progress(p.prog_sig + fast_div(tile * 2, p.div_img_m, p.div_img_s), min(2, p.total_windows - 2 * tile)); };
 
         int it = 0;
         unsigned long long* dbg = threadIdx.x == 64 ? p.dbg : nullptr;
@@ -1496,6 +1518,13 @@ cudaError_t launch_swin_attn(const AttnParams& p_in, cudaStream_t stream) {
     static bool configured[SRK_MAX_DEVICES] = {};
     if (cudaError_t e = configure_smem_once(configured, swin_attn_kernel, K1_SMEM); e != cudaSuccess) return e;
     AttnParams p = p_in;
+    auto div_magic = [](int d, uint32_t& m, uint32_t& sh) {      // n / d == (umulhi(n, m) + n) >> sh for 0 <= n < 2^31 (round-up method)
+        sh = 0;
+        while ((1ll << sh) < d) ++sh;
+        m = static_cast<uint32_t>(((1ull << 32) * ((1ull << sh) - static_cast<uint64_t>(d))) / static_cast<uint64_t>(d) + 1);
+    };
+    div_magic(p.nw_img, p.div_img_m, p.div_img_s);
+    div_magic(p.nwx, p.div_nwx_m, p.div_nwx_s);
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     p.use_tmap = 0;
