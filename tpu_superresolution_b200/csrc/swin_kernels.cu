@@ -402,13 +402,10 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
         for (int tile = blockIdx.x; tile + static_cast<int>(gridDim.x) < p.n_tiles; tile += gridDim.x) {
             const float* xb = tile_ready(tile + gridDim.x);
             set_tile_geom_k1(p, tile + gridDim.x, geo);
-            uint2 hb[8][3];
-            {
-                const RowSrc16 rs = make_row_src16(p, xb, geo, 64 + 32 * lw, lane);
-                ln_rows_hold_p<8>(p.apply_ln, lane, [&](int pass) { return rs.ptr(pass); }, hb);
-            }
+            // (no register prefetch of the rows while the image is still in use: the image is free half way through the heads, the next
+            //  tile needs it ~10 K cycles later, and the prefetch variant was another 470 instructions of once-per-tile code)
             mbar_wait(&bars[B_XAFREE], ph_free); ph_free ^= 1;
-            ln_rows_dump<8>(xa, 64 + 32 * lw, lane, hb);
+            k1_ln16(p, xb, geo, xa, 4 + 2 * lw, lane);
             k1_ln16(p, xb, geo, xa, 4 + 2 * lw + 1, lane);
             fence_proxy_async_smem();
             mbar_arrive(&bars[B_XA]);
