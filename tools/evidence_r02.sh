@@ -1,8 +1,8 @@
 # Final evidence of round 2 (one B200): run under gpurun from the repo root, e.g.
-#   gpurun --timeout 1500 -- 'bash tools/evidence_r02.sh r02j'
+#   gpurun --timeout 1500 -- 'bash tools/evidence_r02.sh r02k'
 # Everything lands in gpurun_out/<tag>_*; copy what should be judged into profiles/.
 set -x
-T=${1:-r02j}
+T=${1:-r02k}
 cd ${GRAFT_REPO_ROOT:-.}
 O=gpurun_out
 timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -15 > $O/${T}_pytest_gpu.log
