@@ -51,62 +51,103 @@ __device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, ui
 
 // ---- sweep 1 of the softmax: logits (exp2 domain, already scaled) + position bias (+ mask) -> running max; the biased
 //      logits are written back in place.  The TMEM load of piece pc + 1 is in flight while piece pc is processed.
-//      MASKED (shifted-window mask) is a separate instantiation so un-masked windows pay nothing for it.
+//      MASKED (shifted-window mask, or an explicit mask `emrow`) is a separate instantiation so un-masked windows pay nothing
+//      for it -- not even its code: the explicit-mask adds live in the MASKED variant only.
+//      The un-masked variant is ROLLED (two 32-key pieces per iteration; the double-buffered register arrays stay static):
+//      a quarter of the straight-line code.  ncu on the unrolled kernel: instruction-cache hit rate 82.7 %, 1.1 warp-cycles of
+//      no-instruction stall per issued instruction -- this kernel's row threads run ~3 K instructions per head step.
+//      Rolling needs a piece to cover whole key rows (32 % KW == 0: not OCAB's KW = 24), so that the bias pointer moves by a constant.
 template <int KH, int KW, int SY, int NCH, bool MASKED>
 __device__ __forceinline__ float softmax_sweep1(uint32_t tacc, const float* rp, int c, const uint32_t (&rowmask)[KH],
                                                 const float* emrow, float mx) {
     constexpr int NP = NCH / 32;
+    constexpr bool ROLL = !MASKED && (32 % KW == 0) && (NP % 2 == 0);
     uint32_t va[32], vb[32];
     tmem_ld32(tacc, va);
+    if constexpr (ROLL) {
+        // piece pc covers columns c NCH + 32 pc + e: key row yj = col / KW, xj = col % KW; the bias pointer moves by a constant per piece
+        constexpr int STEP = SY * (32 / KW);                            // 32 / KW key rows per piece
+        const float* rq = rp - SY * ((c * NCH) / KW);                  // (c NCH is a multiple of KW for these shapes)
+        auto piece = [&](uint32_t (&v)[32], const float* r) {
 #pragma unroll
-    for (int pc = 0; pc < NP; ++pc) {
-        uint32_t(&v)[32] = (pc & 1) ? vb : va;
-        tmem_ld_wait();
-        if (pc + 1 < NP) tmem_ld32(tacc + 32 * (pc + 1), (pc & 1) ? va : vb);
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-            const int col = c * NCH + 32 * pc + e, yj = col / KW, xj = col - yj * KW;
-            float sv = __uint_as_float(v[e]) + rp[-(SY * yj + xj)];
-            if (MASKED) {
-                if (!((rowmask[yj] >> xj) & 1u)) sv -= 100.0f * WA_LOG2E;
+            for (int e = 0; e < 32; ++e) {
+                const int yj = e / KW, xj = e - yj * KW;
+                const float sv = __uint_as_float(v[e]) + r[-(SY * yj + xj)];
+                v[e] = __float_as_uint(sv);
+                mx = fmaxf(mx, sv);
             }
-            v[e] = __float_as_uint(sv);
+        };
+#pragma unroll 1
+        for (int pp = 0; pp < NP; pp += 2) {
+            tmem_ld_wait();
+            tmem_ld32(tacc + 32 * (pp + 1), vb);
+            piece(va, rq - STEP * pp);
+            tmem_st32(tacc + 32 * pp, va);
+            tmem_ld_wait();
+            if (pp + 2 < NP) tmem_ld32(tacc + 32 * (pp + 2), va);
+            piece(vb, rq - STEP * (pp + 1));
+            tmem_st32(tacc + 32 * (pp + 1), vb);
         }
-        if (emrow) {
+        tmem_st_wait();
+        return mx;
+    } else {
 #pragma unroll
-            for (int e = 0; e < 32; e += 4) {
-                const float4 mk = __ldg(reinterpret_cast<const float4*>(emrow + c * NCH + 32 * pc + e));
-                v[e] = __float_as_uint(fmaf(mk.x, WA_LOG2E, __uint_as_float(v[e])));
-                v[e + 1] = __float_as_uint(fmaf(mk.y, WA_LOG2E, __uint_as_float(v[e + 1])));
-                v[e + 2] = __float_as_uint(fmaf(mk.z, WA_LOG2E, __uint_as_float(v[e + 2])));
-                v[e + 3] = __float_as_uint(fmaf(mk.w, WA_LOG2E, __uint_as_float(v[e + 3])));
+        for (int pc = 0; pc < NP; ++pc) {
+            uint32_t(&v)[32] = (pc & 1) ? vb : va;
+            tmem_ld_wait();
+            if (pc + 1 < NP) tmem_ld32(tacc + 32 * (pc + 1), (pc & 1) ? va : vb);
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+                const int col = c * NCH + 32 * pc + e, yj = col / KW, xj = col - yj * KW;
+                float sv = __uint_as_float(v[e]) + rp[-(SY * yj + xj)];
+                if (MASKED) {
+                    if (!((rowmask[yj] >> xj) & 1u)) sv -= 100.0f * WA_LOG2E;
+                }
+                v[e] = __float_as_uint(sv);
             }
-        }
+            if (MASKED && emrow) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
-        tmem_st32(tacc + 32 * pc, v);
+                for (int e = 0; e < 32; e += 4) {
+                    const float4 mk = __ldg(reinterpret_cast<const float4*>(emrow + c * NCH + 32 * pc + e));
+                    v[e] = __float_as_uint(fmaf(mk.x, WA_LOG2E, __uint_as_float(v[e])));
+                    v[e + 1] = __float_as_uint(fmaf(mk.y, WA_LOG2E, __uint_as_float(v[e + 1])));
+                    v[e + 2] = __float_as_uint(fmaf(mk.z, WA_LOG2E, __uint_as_float(v[e + 2])));
+                    v[e + 3] = __float_as_uint(fmaf(mk.w, WA_LOG2E, __uint_as_float(v[e + 3])));
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
+            tmem_st32(tacc + 32 * pc, v);
+        }
+        tmem_st_wait();
+        return mx;
     }
-    tmem_st_wait();
-    return mx;
 }
 
 // ---- sweep 2: p = exp2(s - max) as bf16 pairs written over the S columns already consumed.  The row sum is not
 //      accumulated here: padded dim 30 of every V head is 1, so the P v GEMM delivers sum_j p_ij in column 30 of O.
+//      Rolled like sweep 1 (two pieces per iteration).
 template <int NCH>
 __device__ __forceinline__ void softmax_sweep2(uint32_t tacc, float mx) {
     constexpr int NP = NCH / 32;
+    static_assert(NP % 2 == 0, "two pieces per iteration");
     uint32_t va[32], vb[32];
     tmem_ld32(tacc, va);
-#pragma unroll
-    for (int pc = 0; pc < NP; ++pc) {
-        uint32_t(&v)[32] = (pc & 1) ? vb : va;
-        tmem_ld_wait();
-        if (pc + 1 < NP) tmem_ld32(tacc + 32 * (pc + 1), (pc & 1) ? va : vb);
+    auto piece = [&](const uint32_t (&v)[32], uint32_t dst) {
         uint32_t pw[16];
 #pragma unroll
         for (int e = 0; e < 32; e += 2)
             pw[e >> 1] = pack_bf16x2(ex2_approx(__uint_as_float(v[e]) - mx), ex2_approx(__uint_as_float(v[e + 1]) - mx));
-        tmem_st16(tacc + 16 * pc, pw);
+        tmem_st16(dst, pw);
+    };
+#pragma unroll 1
+    for (int pp = 0; pp < NP; pp += 2) {
+        tmem_ld_wait();
+        tmem_ld32(tacc + 32 * (pp + 1), vb);
+        piece(va, tacc + 16 * pp);
+        tmem_ld_wait();
+        if (pp + 2 < NP) tmem_ld32(tacc + 32 * (pp + 2), va);
+        piece(vb, tacc + 16 * (pp + 1));
     }
     tmem_st_wait();
 }
@@ -344,7 +385,10 @@ __global__ void __launch_bounds__(320, 1) winattn_kernel(const WinAttnParams p) 
                 for (int a = 0; a < KH; ++a) rowmask[a] = 0xffffffffu;
             }
             const float* emrow = nullptr;
-            if (p.emask) emrow = p.emask + (static_cast<int64_t>(wg % p.emask_nw) * C::NQ + qi) * NK;
+            if (p.emask) {                                  // explicit mask: handled by the MASKED sweep variant
+                emrow = p.emask + (static_cast<int64_t>(wg % p.emask_nw) * C::NQ + qi) * NK;
+                masked = true;
+            }
 
             mbar_wait(&bars[W_FULL + s], ph);               // the pair's bias tables have landed
             if (g == 1 && (first_item || NSETS == 1) && p.stagger > 0) {
