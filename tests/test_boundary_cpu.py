@@ -178,3 +178,38 @@ def test_constructor_variants_keep_the_reference_state_dict(name):
     keys = str(np.load(os.path.join(ROOT, "tests", "golden", f"swinir_variant_{name}.npz"))["keys"]).split("\n")
     assert list(m.state_dict().keys()) == keys
     m.load_state_dict(synth.generic_state_dict(m.state_dict(), seed=7), strict=True)
+
+
+def test_fp16_operand_packing_and_precision_table():
+    """Tight mode / default MLP (include/srk.h: SRK_OPERANDS_*): the same slab stream with fp16 elements, closer to the fp32 weights
+    than the bf16 one; weights outside the fp16 range are an error; set_precision() maps the three modes onto the modules."""
+    cfg = synth.CONFIGS["swinir_x2_d2"]
+    sd = synth.make_swinir_state_dict(cfg, seed=99, kind="stress")
+    pre = "layers.0.residual_group.blocks.0.mlp."
+    args = (sd[pre + "fc1.weight"], sd[pre + "fc1.bias"], sd[pre + "fc2.weight"], sd[pre + "fc2.bias"])
+    w16, v16 = packing.pack_mlp(*args, operands="fp16")
+    wbf, vbf = packing.pack_mlp(*args, operands="bf16")
+    wfast, _ = packing.pack_mlp(*args, operands="fp16_fast")
+    assert w16.numel() == wbf.numel() == L.MLP_WSTREAM_BYTES and torch.equal(v16, vbf) and torch.equal(w16, wfast)
+    first16 = packing.unswizzle_slab(w16.view(torch.float16)[:128 * 64].reshape(128, 64)).float()       # fc1 rows 0..127, k 0..63
+    firstbf = packing.unswizzle_slab(wbf.view(torch.bfloat16)[:128 * 64].reshape(128, 64)).float()
+    ref = sd[pre + "fc1.weight"][:128, :64].float()
+    assert (first16 - ref).abs().max() < (firstbf - ref).abs().max() and (first16 - ref).abs().max() <= 2.0 ** -11 * ref.abs().max()
+    big = [a.clone() for a in args]
+    big[0][0, 0] = 1.0e5
+    with pytest.raises(RuntimeError):
+        packing.pack_mlp(*big, operands="fp16")
+    packing.pack_mlp(*big, operands="bf16")                                                              # bf16 has the range
+
+    m = srk.SwinIR(**cfg.as_kwargs()).eval()
+    blk = m.layers[0].residual_group.blocks[0]
+    assert (blk.attn.operands, blk.mlp.operands) == ("bf16", "fp16_fast")                               # the default mode
+    for mode, want in srk.swinir.PRECISIONS.items():
+        m.set_precision(mode)
+        assert all((b.attn.operands, b.mlp.operands) == want for layer in m.layers for b in layer.residual_group.blocks)
+    with pytest.raises(ValueError):
+        m.set_precision("fp8")
+    assert set(L.OPERANDS) == {"bf16", "fp16", "fp16_fast"}
+    hdr = open(os.path.join(ROOT, "include", "srk.h")).read()
+    for name, val in (("SRK_OPERANDS_BF16", 0), ("SRK_OPERANDS_F16", 1), ("SRK_OPERANDS_F16_HALF_GELU", 2)):
+        assert re.search(name + r"\s*=\s*" + str(val), hdr), name
