@@ -18,8 +18,8 @@ constexpr uint32_t ATOM_A = 16384;      // 128 rows x 128 B: one k-atom of a 128
 // ------------------------------------------------------------------------------------------------
 // (x - mean) * rstd of 16 token rows per warp -> bf16 SW128 image at `xa` (3 k-atoms).  LayerNorm's affine
 // (gamma, beta) is folded into the following GEMM's weights / bias at pack time (packing.py).
-// Half-warp per token: 16 lanes x 3 float4 cover the 180 channels (45 float4) fully coalesced.  All 24 loads
-// of a lane are issued before the first use (one exposed memory latency per tile).
+// Half-warp per token: 16 lanes x 3 float4 cover the 180 channels (45 float4) fully coalesced.  The 12 loads of a
+// lane for 8 rows are issued before their first use; two such halves per call (see below).
 // Core form: `row_ptr(pass)` returns the global address of the token row this lane's half-warp handles in `pass`
 // (image row cw8 * 16 + 2 * pass + (lane >> 4)), or nullptr for a padding row.  A single warp runs dependent scalar
 // code at one instruction per ~6 cycles, so callers keep the per-pass address arithmetic to an add or two.

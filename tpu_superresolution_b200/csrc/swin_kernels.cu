@@ -6,16 +6,19 @@
 //                      Replaces network_swinir.py:244-276 (and :114-145 in SRK_MODE_WINDOWS).
 //   swin_mlp_kernel  : LN2 -> fc1 -> GELU -> fc2 -> + shortcut.  Replaces :277, :24-30.
 //
-// One CTA per SM, persistent over 128-token tiles (= two 8x8 windows).  320 threads:
-//   warp 0 lane 0 : weight producer -- streams the pre-swizzled bf16 weight slabs (packing.py) from
-//                   L2 into a 3-stage shared-memory ring with 1-D bulk TMA;
-//   warp 1 lane 0 : tcgen05.mma issuer (all GEMMs accumulate in TMEM); runs ahead of the row threads,
+// One CTA per SM, persistent over 128-token tiles (= two 8x8 windows).  swin_attn_kernel: 512 threads, swin_mlp_kernel: 448 (or 320):
+//   warp 0 lane 0 : weight producer -- streams the pre-swizzled weight slabs (packing.py: bf16, or fp16 in the variant translation
+//                   units swin_kernels_f16.cu / _f16h.cu) from L2 into a 3-stage shared-memory ring with 1-D bulk TMA;
+//   warp 1        : tcgen05.mma issuer (warp-uniform issue, all GEMMs accumulate in TMEM); runs ahead of the row threads,
 //                   ordered only by mbarriers, so GEMMs of head h+1 overlap the softmax of head h;
-//   warps 2..9    : 256 "row" threads in two groups g = 0,1.  Thread <-> TMEM lane <-> token row; the two
-//                   groups split the accumulator columns of every epilogue (a TMEM lane quadrant is only
-//                   reachable from warps with the same warp_id % 4).  LayerNorm, operand images (bf16,
-//                   128-byte swizzle), softmax (32 keys per thread, row max/sum merged across the two
-//                   groups through shared memory), epilogues.
+//   warps 2..9    : 256 "row" threads in two groups g = 0,1.  Thread <-> TMEM lane <-> token row; the two groups split the
+//                   accumulator columns of every epilogue (a TMEM lane quadrant is only reachable from warps with the same
+//                   warp_id % 4) and the heads of the softmax (group g: heads g, g + 2, g + 4; one window row = 64 keys per thread);
+//   warps 10..13  : swin_attn_kernel: utility warps (q|k epilogues, rows 0-63 of the next tile's LayerNorm);
+//                   swin_mlp_kernel: LayerNorm warps one tile ahead;
+//   warps 14, 15  : swin_attn_kernel: LayerNorm of rows 64-127 of the next tile.
+// Code size matters here: the roles' loop bodies together exceed the instruction cache, so code that runs once per
+// tile is kept small (rolled halves, shared out-of-line routines) and the clock64() timeline stamps exist only in the debug build.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
