@@ -233,6 +233,13 @@ int srk_dwconv3x3_rows_fwd(const float* in, int32_t ld_in, int32_t c_in, const f
                            const float* ln_stats, const float* ln_gamma, const float* ln_beta, const float* gate, int32_t ld_gate,
                            int32_t c_gate, float* out, int32_t ld_out, int32_t channels, int32_t batch, int32_t height, int32_t width,
                            int32_t act_gelu, void* stream);
+/* The same with the result as bf16 planes [channel / 64][token][64 channels] (plane_stride bytes apart, 16-byte chunks permuted by
+ * chunk ^ (token & 7)): the SRK_LIN_A_PLANES input of srk_linear_fwd -- DAT's SpatialGate output feeds fc2 (K = 360 as six k-atoms)
+ * in ONE launch this way.  Channels past `channels` in the last plane are not written: zero them once. */
+int srk_dwconv3x3_rows_planes_fwd(const float* in, int32_t ld_in, int32_t c_in, const float* w9c, const float* scale, const float* shift,
+                                  const float* ln_stats, const float* ln_gamma, const float* ln_beta, const float* gate, int32_t ld_gate,
+                                  int32_t c_gate, void* out_planes, int64_t plane_stride, int32_t channels, int32_t batch, int32_t height,
+                                  int32_t width, int32_t act_gelu, void* stream);
 /* stats[tok] = (mean, rstd) over the channel slice (nn.LayerNorm statistics, biased variance). */
 int srk_row_stats_fwd(const float* in, int32_t ld_in, int32_t c_in, int32_t channels, int64_t tokens, float eps, float* stats, void* stream);
 /* Adaptive interaction module (dat_arch.py:420-433 mode 0, :510-523 mode 1) on (tokens, 180) rows: s = w2 . gelu(W1 src + b1) + b2

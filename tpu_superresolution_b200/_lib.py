@@ -170,6 +170,8 @@ def load():
     lib.srk_cab_ws_floats.argtypes = [c_int32, c_int32]
     lib.srk_token_mean_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]
     lib.srk_dat_channel_softmax_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_void_p]
+    lib.srk_dwconv3x3_rows_planes_fwd.argtypes = [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                  c_int32, c_int32, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
     lib.srk_token_mean_mlp_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]
     lib.srk_dat_channel_apply_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]
     lib.srk_cab_gate_add.argtypes = [c_void_p] * 8 + [c_int32, ctypes.c_float, c_int32, c_int32, c_void_p]
@@ -185,7 +187,7 @@ def load():
               "srk_stitch_accumulate", "srk_stitch_normalize", "srk_gather_tiles", "srk_stitch_accumulate_strided", "srk_stitch_finalize",
               "srk_conv3x3_fwd", "srk_rows_to_f16", "srk_image_to_f16_split", "srk_linear_fwd", "srk_window_attention_fwd",
               "srk_window_attention_table_floats", "srk_cab_gate_add", "srk_dwconv3x3_rows_fwd", "srk_row_stats_fwd", "srk_dat_mix_fwd",
-              "srk_dat_channel_gram_fwd", "srk_dat_channel_apply_fwd", "srk_dat_channel_gram_ws_floats", "srk_cab_ws_floats", "srk_token_mean_fwd", "srk_token_mean_mlp_fwd", "srk_dat_channel_softmax_fwd"):
+              "srk_dat_channel_gram_fwd", "srk_dat_channel_apply_fwd", "srk_dat_channel_gram_ws_floats", "srk_cab_ws_floats", "srk_token_mean_fwd", "srk_token_mean_mlp_fwd", "srk_dat_channel_softmax_fwd", "srk_dwconv3x3_rows_planes_fwd"):
         getattr(lib, f).restype = c_int32
     if lib.srk_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libsrk.so ABI {lib.srk_abi_version()} != expected {ABI_VERSION}; rebuild")
@@ -201,7 +203,7 @@ EXPORTS = ("srk_abi_version", "srk_last_error_string", "srk_launch_count", "srk_
            "srk_conv3x3_fwd", "srk_rows_to_f16", "srk_image_to_f16_split", "srk_debug_set_timeline", "srk_debug_set_stagger",
            "srk_linear_fwd", "srk_window_attention_fwd", "srk_window_attention_table_floats", "srk_debug_set_winattn_stagger", "srk_debug_set_pdl",
            "srk_cab_gate_add", "srk_dwconv3x3_rows_fwd", "srk_row_stats_fwd", "srk_dat_mix_fwd", "srk_dat_channel_gram_fwd",
-           "srk_dat_channel_apply_fwd", "srk_dat_channel_gram_ws_floats", "srk_cab_ws_floats", "srk_token_mean_fwd", "srk_token_mean_mlp_fwd", "srk_dat_channel_softmax_fwd")
+           "srk_dat_channel_apply_fwd", "srk_dat_channel_gram_ws_floats", "srk_cab_ws_floats", "srk_token_mean_fwd", "srk_token_mean_mlp_fwd", "srk_dat_channel_softmax_fwd", "srk_dwconv3x3_rows_planes_fwd")
 
 
 def _check(rc: int, lib) -> None:
@@ -512,6 +514,20 @@ def dwconv3x3_rows(inp, w9c, scale, shift, out, *, ld_in, c_in, ld_out, channels
         _check(lib.srk_dwconv3x3_rows_fwd(inp.data_ptr(), ld_in, c_in, w9c.data_ptr(), scale.data_ptr(), shift.data_ptr(), _ptr(ln_stats),
                                           _ptr(ln_gamma), _ptr(ln_beta), _ptr(gate), ld_gate, c_gate, out.data_ptr(), ld_out, channels, batch,
                                           height, width, int(act_gelu), st), lib)
+
+
+def dwconv3x3_rows_planes(inp, w9c, scale, shift, planes, *, ld_in, c_in, channels, batch, height, width, act_gelu=False, ln_stats=None,
+                          ln_gamma=None, ln_beta=None, gate=None, ld_gate=0, c_gate=0) -> None:
+    """srk_dwconv3x3_rows_planes_fwd: like dwconv3x3_rows, output as bf16 planes (P, tokens, 64) for linear(a_mode=LIN_A_PLANES)."""
+    lib = load()
+    _require_cuda_f32(inp, w9c, scale, shift, ln_stats, ln_gamma, ln_beta, gate)
+    if planes.dtype != torch.bfloat16 or planes.dim() != 3 or planes.shape[2] != 64 or not planes.is_contiguous() or \
+            planes.shape[0] * 64 < channels or planes.shape[1] != batch * height * width:
+        raise RuntimeError("dwconv3x3_rows_planes: planes must be a contiguous bf16 (P, tokens, 64) buffer covering the channels")
+    with _launch("dwconv3x3_rows", inp, w9c, scale, shift, planes, ln_stats, ln_gamma, ln_beta, gate) as st:
+        _check(lib.srk_dwconv3x3_rows_planes_fwd(inp.data_ptr(), ld_in, c_in, w9c.data_ptr(), scale.data_ptr(), shift.data_ptr(), _ptr(ln_stats),
+                                                 _ptr(ln_gamma), _ptr(ln_beta), _ptr(gate), ld_gate, c_gate, planes.data_ptr(),
+                                                 planes.shape[1] * 128, channels, batch, height, width, int(act_gelu), st), lib)
 
 
 def row_stats(inp, stats, *, ld_in, c_in, channels, tokens, eps) -> None:

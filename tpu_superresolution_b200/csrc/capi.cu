@@ -313,6 +313,26 @@ int srk_dwconv3x3_rows_fwd(const float* in, int32_t ld_in, int32_t c_in, const f
                  "srk_dwconv3x3_rows_fwd");
 }
 
+int srk_dwconv3x3_rows_planes_fwd(const float* in, int32_t ld_in, int32_t c_in, const float* w9c, const float* scale, const float* shift,
+                                  const float* ln_stats, const float* ln_gamma, const float* ln_beta, const float* gate, int32_t ld_gate,
+                                  int32_t c_gate, void* out_planes, int64_t plane_stride, int32_t channels, int32_t batch, int32_t height,
+                                  int32_t width, int32_t act_gelu, void* stream) {
+    if (!in || !w9c || !scale || !shift || !out_planes) return fail("srk_dwconv3x3_rows_planes_fwd: null argument");
+    if (ln_stats && (!ln_gamma || !ln_beta)) return fail("srk_dwconv3x3_rows_planes_fwd: LayerNorm input needs gamma and beta");
+    if (channels <= 0 || (channels & 3) || (ld_in & 3) || (c_in & 3) || c_in + channels > ld_in)
+        return fail("srk_dwconv3x3_rows_planes_fwd: channels / ld / offsets must be multiples of 4 and consistent");
+    if (gate && ((ld_gate & 3) || (c_gate & 3) || c_gate + channels > ld_gate)) return fail("srk_dwconv3x3_rows_planes_fwd: bad gate slice");
+    if (!aligned16(in) || !aligned16(w9c) || !aligned16(scale) || !aligned16(shift) || !aligned16(out_planes) || (gate && !aligned16(gate)) ||
+        (ln_stats && (!aligned16(ln_gamma) || !aligned16(ln_beta))) || (plane_stride & 127))
+        return fail("srk_dwconv3x3_rows_planes_fwd: pointers must be 16-byte aligned, plane_stride a multiple of 128");
+    if (batch < 0 || height <= 0 || width <= 0 || plane_stride < static_cast<int64_t>(batch) * height * width * 128)
+        return fail("srk_dwconv3x3_rows_planes_fwd: bad shape");
+    return check(srk::launch_dwconv3x3_rows(in, ld_in, c_in, w9c, scale, shift, ln_stats, ln_gamma, ln_beta, gate, ld_gate, c_gate, nullptr, 0,
+                                            channels, batch, height, width, act_gelu, static_cast<cudaStream_t>(stream),
+                                            static_cast<uint8_t*>(out_planes), plane_stride),
+                 "srk_dwconv3x3_rows_planes_fwd");
+}
+
 int srk_row_stats_fwd(const float* in, int32_t ld_in, int32_t c_in, int32_t channels, int64_t tokens, float eps, float* stats, void* stream) {
     if (!in || !stats) return fail("srk_row_stats_fwd: null argument");
     if (channels <= 0 || (channels & 3) || (ld_in & 3) || (c_in & 3) || c_in + channels > ld_in || !aligned16(in))

@@ -11,6 +11,7 @@
 //   channel_apply_kernel    out[tok, h*30+d1] = sum_d2 A[b, h, d1, d2] v[tok, h*30+d2]      (dat_arch.py:505)
 // 128-bit accesses where the layout allows, grid-stride or one block per token chunk, no tensor cores: these are
 // streaming kernels whose bound is bytes moved.
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -56,7 +57,8 @@ __global__ void __launch_bounds__(DW_SLAB * DW_XL, 2) dwconv3x3_rows_kernel(cons
                                                                          const float* __restrict__ shift, const float* __restrict__ stats,
                                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                          const float* __restrict__ gate, int ld_gate, int c_gate,
-                                                                         float* __restrict__ out, int ld_out, int C, int H, int W, int act_gelu) {
+                                                                         float* __restrict__ out, int ld_out, int C, int H, int W, int act_gelu,
+                                                                         uint8_t* __restrict__ out_planes, long long plane_stride) {
     extern __shared__ float4 dw_smem[];                      // [4][WC + 2][DW_SLAB]: ring of input rows
     const int C4 = C >> 2;
     const int c = threadIdx.x % DW_SLAB, xl = threadIdx.x / DW_SLAB;
@@ -150,7 +152,16 @@ __global__ void __launch_bounds__(DW_SLAB * DW_XL, 2) dwconv3x3_rows_kernel(cons
                 float4 o = make_float4(fmaf(acc.x, sc.x, sh.x), fmaf(acc.y, sc.y, sh.y), fmaf(acc.z, sc.z, sh.z), fmaf(acc.w, sc.w, sh.w));
                 if (act_gelu) { o.x = gelu_erf_fast(o.x); o.y = gelu_erf_fast(o.y); o.z = gelu_erf_fast(o.z); o.w = gelu_erf_fast(o.w); }
                 if (HAS_GATE) { o.x *= gv[k].x; o.y *= gv[k].y; o.z *= gv[k].z; o.w *= gv[k].w; }
-                reinterpret_cast<float4*>(out + tok * ld_out)[c4] = o;
+                if (out_planes != nullptr) {
+                    // bf16 planes [channel / 64][token][128 B], 16-byte chunks permuted by chunk ^ (token & 7): the A-operand layout
+                    // token_linear_kernel reads with one bulk copy per k-atom (SRK_LIN_A_PLANES); this thread's 4 channels = 8 bytes
+                    const int ch = 4 * c4, pl = ch >> 6, chunk = (ch & 63) >> 3;
+                    uint8_t* dst = out_planes + pl * plane_stride + tok * 128 + (((chunk ^ static_cast<int>(tok & 7)) << 4) | ((ch & 4) << 1));
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+                    *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+                } else {
+                    reinterpret_cast<float4*>(out + tok * ld_out)[c4] = o;
+                }
             }
         }
         if (more) {
@@ -423,7 +434,8 @@ static int grid_for(int64_t threads_needed) {
 
 cudaError_t launch_dwconv3x3_rows(const float* in, int ld_in, int c_in, const float* w, const float* scale, const float* shift,
                                   const float* stats, const float* gamma, const float* beta, const float* gate, int ld_gate, int c_gate,
-                                  float* out, int ld_out, int C, int batch, int H, int W, int act_gelu, cudaStream_t stream) {
+                                  float* out, int ld_out, int C, int batch, int H, int W, int act_gelu, cudaStream_t stream,
+                                  uint8_t* out_planes, long long plane_stride) {
     if (batch <= 0) return cudaSuccess;
     const int C4 = C >> 2;
     const size_t smem = static_cast<size_t>(4) * (DW_XC + 2) * DW_SLAB * sizeof(float4);
@@ -432,7 +444,7 @@ cudaError_t launch_dwconv3x3_rows(const float* in, int ld_in, int c_in, const fl
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
         kern<<<grid, DW_SLAB * DW_XL, smem, stream>>>(in, ld_in, c_in, w, scale, shift, stats, gamma, beta, gate, ld_gate, c_gate, out, ld_out, C, H,
-                                                    W, act_gelu);
+                                                    W, act_gelu, out_planes, plane_stride);
         return cudaSuccess;
     };
     cudaError_t e;

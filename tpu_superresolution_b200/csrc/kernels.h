@@ -206,7 +206,7 @@ cudaError_t launch_cab_gate_add(const float* y, const float* y_bias, float* out,
                                 const float* b2, int hidden, float scale, int batch, int tokens_per_image, cudaStream_t stream);
 cudaError_t launch_dwconv3x3_rows(const float* in, int ld_in, int c_in, const float* w, const float* scale, const float* shift,
                                   const float* stats, const float* gamma, const float* beta, const float* gate, int ld_gate, int c_gate,
-                                  float* out, int ld_out, int C, int batch, int H, int W, int act_gelu, cudaStream_t stream);
+                                  float* out, int ld_out, int C, int batch, int H, int W, int act_gelu, cudaStream_t stream, uint8_t* out_planes = nullptr, long long plane_stride = 0);
 cudaError_t launch_row_stats(const float* in, int ld_in, int c_in, int C, int64_t tokens, float eps, float* stats, cudaStream_t stream);
 cudaError_t launch_dat_mix(const float* att, const float* conv, const float* cmap, const float* w1, const float* b1, const float* w2,
                            float b2, int hidden, int mode, float* mix, int64_t tokens, int tokens_per_image, cudaStream_t stream);

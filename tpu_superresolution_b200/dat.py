@@ -85,8 +85,31 @@ class SpatialGate(nn.Module):
                          ln_gamma=self.norm.weight, ln_beta=self.norm.bias, gate=x, ld_gate=C, c_gate=0)
         return out
 
+    def gate_planes(self, x, H, W):
+        """The same, result as bf16 planes (ceil(Ch / 64), B * N, 64) -- the A-operand layout of srk_linear_fwd(a_mode = PLANES), so fc2
+        (K = Ch = 360) is ONE launch over six k-atoms instead of two K = 180 launches on fp32 rows, and the gated tensor moves half the
+        bytes.  One zero-initialised buffer per (device, tokens, planes) is shared by all blocks (they run one after the other on one
+        stream); the kernel never writes the padded channels of the last plane."""
+        B, N, C = x.shape
+        Ch = C // 2
+        w9c, one, bias = self._packed()
+        stats = torch.empty((B * N, 2), dtype=torch.float32, device=x.device)
+        L.row_stats(x, stats, ld_in=C, c_in=Ch, channels=Ch, tokens=B * N, eps=self.norm.eps)
+        key = (str(x.device), B * N, 3 if Ch <= 192 else 6)            # K padded to 192 or 384 (packing.pack_planes_linear)
+        planes = _GATE_PLANES.get(key)
+        if planes is None:
+            if len(_GATE_PLANES) >= 4:
+                _GATE_PLANES.clear()
+            planes = _GATE_PLANES[key] = torch.zeros((key[2], B * N, 64), dtype=torch.bfloat16, device=x.device)
+        L.dwconv3x3_rows_planes(x, w9c, one, bias, planes, ld_in=C, c_in=Ch, channels=Ch, batch=B, height=H, width=W, ln_stats=stats,
+                                ln_gamma=self.norm.weight, ln_beta=self.norm.bias, gate=x, ld_gate=C, c_gate=0)
+        return planes
+
     def forward(self, x, H, W):
         return self.gate_rows(x.contiguous(), H, W)
+
+
+_GATE_PLANES = {}        # SpatialGate.gate_planes: shared zero-initialised plane buffers
 
 
 class SGFN(nn.Module):
@@ -117,7 +140,9 @@ class SGFN(nn.Module):
             halves = []
             for i in range(hid // 2 // L.DIM):      # fc2's K = hidden / 2 in slices of 180: y += x[:, 180 i : 180 i + 180] W[:, slice]^T
                 halves.append(packing.pack_rows_linear(self.fc2.weight[:, L.DIM * i:L.DIM * (i + 1)], self.fc2.bias if i == 0 else None))
-            return f1, halves
+            # ... or, for hidden / 2 <= 384, all of K at once from bf16 planes (SpatialGate.gate_planes)
+            whole = packing.pack_planes_linear(self.fc2.weight, self.fc2.bias) if hid // 2 <= 384 else None
+            return f1, halves, whole
         return self._cache.get(ps, build)
 
     def run(self, x, out, H, W, norm: Optional[nn.LayerNorm], add_residual: bool):
@@ -125,10 +150,15 @@ class SGFN(nn.Module):
         _inference_only(self)
         B, N, C = x.shape
         hid = self.fc1.weight.shape[0]
-        (f1w, f1b), halves = self._packed(norm)
+        (f1w, f1b), halves, whole = self._packed(norm)
         h = torch.empty((B, N, hid), device=x.device, dtype=torch.float32)
         L.linear(x, f1w, f1b, h, num_tokens=B * N, a_mode=L.LIN_A_ROWS, ld_in=C, apply_ln=norm is not None, n_chunks=hid // L.DIM,
                  act=L.LIN_ACT_GELU, out_mode=L.LIN_OUT_ROWS, ld_out=hid)
+        if whole is not None:                                                   # x1 * dwconv(LayerNorm(x2)) as bf16 planes, fc2 in one launch
+            planes = self.sg.gate_planes(h, H, W)
+            L.linear(planes, whole[0], whole[1], out, num_tokens=B * N, a_mode=L.LIN_A_PLANES, k_atoms=planes.shape[0], n_chunks=1,
+                     out_mode=L.LIN_OUT_ROWS, ld_out=C, add_residual=add_residual)
+            return out
         g = self.sg.gate_rows(h, H, W)                                          # (B, N, hid / 2): x1 * dwconv(LayerNorm(x2))
         for i, (w2, b2) in enumerate(halves):
             L.linear(g[..., L.DIM * i:], w2, b2, out, num_tokens=B * N, a_mode=L.LIN_A_ROWS, ld_in=hid // 2, apply_ln=False,

@@ -285,6 +285,23 @@ def pack_rows_linear(w, b, ln_w=None, ln_b=None) -> Tuple[torch.Tensor, torch.Te
 
 
 @torch.no_grad()
+def pack_planes_linear(w, b) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Linear (180, K), K <= 384, consuming bf16 planes in plain channel order (plane = 64 channels; K padded with zero columns to a
+    whole number of planes: 3 or 6) -> (wstream, bias[192]) for srk_linear_fwd(a_mode = PLANES, fp32 row output, one chunk)."""
+    dev = w.device
+    N, K = w.shape
+    if N != L.DIM or K > 384:
+        raise RuntimeError(f"unsupported linear geometry {tuple(w.shape)}: N must be 180 and K <= 384")
+    kp = 192 if K <= 192 else 384
+    w_pad = torch.zeros(192, kp)
+    w_pad[:N, :K] = w.detach().cpu().float()
+    b_pad = torch.zeros(192)
+    if b is not None:
+        b_pad[:N] = b.detach().cpu().float()
+    return pack_linear_stream(w_pad).to(dev), b_pad.to(dev)
+
+
+@torch.no_grad()
 def pack_dat_qkv_planes(qkv_w, qkv_b, ln_w=None, ln_b=None, scale=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """DAT spatial block qkv (540, 180) -> (wstream, bias[768]) producing 12 planes: for each of q, k, v the head pairs
     (h0, h1) (h2, -) of the first channel half (8x32 windows) and (h3, h4) (h5, -) of the second (32x8 windows),
