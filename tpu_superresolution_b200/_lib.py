@@ -191,6 +191,8 @@ def load():
         getattr(lib, f).restype = c_int32
     if lib.srk_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libsrk.so ABI {lib.srk_abi_version()} != expected {ABI_VERSION}; rebuild")
+    if os.environ.get("SRK_WINATTN_STAGGER"):       # experiment switch: start skew of the second softmax group of winattn_kernel (cycles)
+        lib.srk_debug_set_winattn_stagger(int(os.environ["SRK_WINATTN_STAGGER"]))
     if os.environ.get("SRK_PDL") == "0":            # experiment switch: no programmatic dependent launch (include/srk.h: srk_debug_set_pdl)
         lib.srk_debug_set_pdl(0)
     _lib = lib
