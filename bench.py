@@ -551,7 +551,7 @@ def run_ours(args):
     tight = None
     if world == 1 and hasattr(model, "set_precision"):
         # the tight precision mode (north star: "tighter for a TF32 mode"): fp16 operands in the fused attention / MLP kernels,
-        # fp32 library convolutions; eager launches, inputs resident, CUDA events
+        # hi / lo split convolutions on the same tcgen05 kernel; eager launches, inputs resident, CUDA events
         model.set_precision("fp16")
         with torch.no_grad():
             for i in range(2):
@@ -565,7 +565,7 @@ def run_ours(args):
             torch.cuda.synchronize()
         ms_t = e0.elapsed_time(e1) / n_t
         tight = {"value": mpix_step / (ms_t * 1e-3), "unit": "Mpix/s", "ms_per_step": ms_t, "steps": n_t,
-                 "precision": "fp16 MMA operands (11-bit significand) in the fused attention / MLP kernels, fp32 accumulate; 3x3 convolutions fp32 (cuDNN, TF32 off)",
+                 "precision": "fp16 MMA operands (11-bit significand) in the fused attention / MLP kernels, fp32 accumulate; 3x3 convolutions as hi/lo fp16 pairs on the tcgen05 kernel (3 products per layer, ~22-bit operands)",
                  "gate": "max abs <= 2e-4 vs the reference fp32 forward (tests/test_gpu_full_configs.py::test_tight_mode_fp16_operands_vs_reference_golden)"}
         model.set_precision("bf16")
 

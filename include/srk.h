@@ -333,6 +333,15 @@ int srk_conv3x3_fwd(const SrkConvDesc* desc, const void* in_f16, const void* wst
                     void* stream);
 /* fp32 token rows (pixels, ld_in) with `channels` channels -> fp16 NHWC (pixels, cp), cp = 64 * k_atoms, zero padded. */
 int srk_rows_to_f16(const float* x, int32_t ld_in, int32_t channels, void* out_f16, int32_t cp, int64_t pixels, void* stream);
+/* Tight mode (fp32-class convolutions out of the fp16 tensor-core kernel): fp32 rows -> the fp16 pair hi = fp16(v), lo = fp16(v - hi),
+ * v = act(x), as NHWC images with row pitch ld_out and cp = 64 * k_atoms zero-padded channels each; hi2 (may be NULL) receives a
+ * second copy of hi.  conv(x, w) = srk_conv3x3_fwd(hi, hi(w)) + (lo, hi(w)) + (hi, lo(w)), either as three accumulating launches
+ * (SRK_CONV_OUT_ROWS_F32 with residual == out) or, for C_in = 64, as ONE launch with k_atoms = 3 over the interleaved image
+ * hi = base, lo = base + 64, hi2 = base + 128, ld_out = 192 against weights packed [hi(w) | hi(w) | lo(w)].
+ * shuffle_h, shuffle_w > 0: x holds the 4 x 64 output channels of a conv + nn.PixelShuffle(2) stage at shuffle_h x shuffle_w pixels
+ * per image (channels == 256, cp == 64; network_swinir.py:584-585); the pair is written at the 2x resolution. */
+int srk_rows_to_f16_split(const float* x, int32_t ld_in, int32_t channels, void* hi_f16, void* lo_f16, void* hi2_f16, int32_t ld_out, int32_t cp,
+                          int64_t pixels, int32_t act, float slope, int32_t shuffle_h, int32_t shuffle_w, void* stream);
 /* network input (batch, channels <= 3, height, width) fp32 with element strides (sb, sc, sy, sx) -> fp16 NHWC (pixels, 64) holding
  * [hi(v), v - hi(v), hi(v)] of v = (x - mean[c]) * range (network_swinir.py:803-804): conv_first's input with the fp16 rounding
  * compensated (pack_conv3x3(split_first=True) packs [hi(w), hi(w), w - hi(w)]).  mean3: 3 floats in HOST memory. */

@@ -114,6 +114,41 @@ def test_conv_first_split_is_near_fp32():
     assert _rel(out, ref) < 2e-5
 
 
+def test_split_convs_are_fp32_grade():
+    """Tight mode (convs.SplitConv3x3 / SplitPixelShuffleTail): hi / lo fp16 pairs of activations and weights on the same kernel.
+    Reference: torch float64 convolutions; gate 3e-6 of the output's max magnitude for one layer, 2e-5 for the four-layer tail
+    (plain fp16 operands: ~5e-4 per layer)."""
+    import torch.nn as nn
+    from tpu_superresolution_b200 import convs
+    B, H, W = 2, 24, 40
+    dev = "cuda"
+    g = torch.Generator().manual_seed(3)
+    body = nn.Conv2d(180, 180, 3, 1, 1)
+    before = nn.Sequential(nn.Conv2d(180, 64, 3, 1, 1), nn.LeakyReLU(0.01))
+    ups = nn.Sequential(nn.Conv2d(64, 256, 3, 1, 1), nn.PixelShuffle(2), nn.Conv2d(64, 256, 3, 1, 1), nn.PixelShuffle(2))
+    last = nn.Conv2d(64, 3, 3, 1, 1)
+    for mod in (body, before, ups, last):
+        for prm in mod.parameters():
+            prm.data = torch.randn(prm.shape, generator=g) * (0.03 if prm.dim() == 4 else 0.1)
+    x, res = _rand((B, 180, H, W), 31), _rand((B, H * W, 180), 32)
+    mean = torch.tensor([0.4488, 0.4371, 0.4040])
+    with torch.no_grad():
+        d = lambda m: m.double()
+        ref_body = d(body)(x.double()).permute(0, 2, 3, 1).reshape(B, H * W, 180) + res.double()
+        ref_tail = d(last)(d(ups)(d(before)(x.double()))) / 2.0 + mean.double().view(1, 3, 1, 1)
+        for mod in (body, before, ups, last):
+            mod.float().to(dev)
+    rows = x.permute(0, 2, 3, 1).reshape(B * H * W, 180).contiguous().to(dev)
+    xs = convs.rows_split(rows, 180)
+    assert xs.shape == (2, B * H * W, 192) and torch.equal(xs[:, :, 180:], torch.zeros_like(xs[:, :, 180:]))
+    assert _rel(xs[0].float() + xs[1].float(), F.pad(rows, (0, 12)).cpu()) < 1e-6
+    out = res.to(dev).clone()
+    convs.SplitConv3x3(body)(xs, B, H, W, out=out, mode=L.CONV_OUT_ROWS_F32, ld_out=180, residual=out)        # in place += like the RSTB tail
+    assert _rel(out, ref_body) < 3e-6
+    y = convs.SplitPixelShuffleTail(before, ups, last, 2.0, mean)(xs, B, H, W)
+    assert y.shape == (B, 3, 4 * H, 4 * W) and _rel(y, ref_tail) < 2e-5            # four layers deep (measured 8e-6)
+
+
 def test_cab_pair_with_gelu():
     """hat_arch.py:67-72: conv 180 -> 60, GELU, conv 60 -> 180."""
     B, H, W = 1, 32, 48

@@ -150,6 +150,8 @@ def load():
     lib.srk_stitch_normalize.argtypes = [c_void_p, c_void_p, c_int32, c_int64, c_void_p]
     lib.srk_conv3x3_fwd.argtypes = [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.srk_rows_to_f16.argtypes = [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int64, c_void_p]
+    lib.srk_rows_to_f16_split.argtypes = [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int64, c_int32,
+                                          ctypes.c_float, c_int32, c_int32, c_void_p]
     lib.srk_image_to_f16_split.argtypes = [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32,
                                            POINTER(ctypes.c_float), ctypes.c_float, c_void_p, c_void_p]
     lib.srk_gather_tiles.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]
@@ -185,7 +187,7 @@ def load():
     lib.srk_debug_set_pdl.restype = None
     for f in ("srk_swin_attn_fwd", "srk_swin_mlp_fwd", "srk_swin_attn_fwd_sync", "srk_swin_mlp_fwd_sync", "srk_swin_layer_fwd", "srk_layernorm_fwd", "srk_layernorm_f16_fwd", "srk_pixelshuffle_nhwc_fwd", "srk_pixelshuffle_nhwc_bias_fwd", "srk_bias_act_add_nhwc",
               "srk_stitch_accumulate", "srk_stitch_normalize", "srk_gather_tiles", "srk_stitch_accumulate_strided", "srk_stitch_finalize",
-              "srk_conv3x3_fwd", "srk_rows_to_f16", "srk_image_to_f16_split", "srk_linear_fwd", "srk_window_attention_fwd",
+              "srk_conv3x3_fwd", "srk_rows_to_f16", "srk_rows_to_f16_split", "srk_image_to_f16_split", "srk_linear_fwd", "srk_window_attention_fwd",
               "srk_window_attention_table_floats", "srk_cab_gate_add", "srk_dwconv3x3_rows_fwd", "srk_row_stats_fwd", "srk_dat_mix_fwd",
               "srk_dat_channel_gram_fwd", "srk_dat_channel_apply_fwd", "srk_dat_channel_gram_ws_floats", "srk_cab_ws_floats", "srk_token_mean_fwd", "srk_token_mean_mlp_fwd", "srk_dat_channel_softmax_fwd", "srk_dwconv3x3_rows_planes_fwd"):
         getattr(lib, f).restype = c_int32
@@ -202,7 +204,7 @@ def load():
 EXPORTS = ("srk_abi_version", "srk_last_error_string", "srk_launch_count", "srk_swin_attn_fwd", "srk_swin_mlp_fwd",
            "srk_swin_attn_fwd_sync", "srk_swin_mlp_fwd_sync", "srk_swin_layer_fwd",
            "srk_layernorm_fwd", "srk_layernorm_f16_fwd", "srk_pixelshuffle_nhwc_fwd", "srk_pixelshuffle_nhwc_bias_fwd", "srk_bias_act_add_nhwc", "srk_stitch_accumulate", "srk_stitch_normalize", "srk_gather_tiles", "srk_stitch_accumulate_strided", "srk_stitch_finalize",
-           "srk_conv3x3_fwd", "srk_rows_to_f16", "srk_image_to_f16_split", "srk_debug_set_timeline", "srk_debug_set_stagger",
+           "srk_conv3x3_fwd", "srk_rows_to_f16", "srk_rows_to_f16_split", "srk_image_to_f16_split", "srk_debug_set_timeline", "srk_debug_set_stagger",
            "srk_linear_fwd", "srk_window_attention_fwd", "srk_window_attention_table_floats", "srk_debug_set_winattn_stagger", "srk_debug_set_pdl",
            "srk_cab_gate_add", "srk_dwconv3x3_rows_fwd", "srk_row_stats_fwd", "srk_dat_mix_fwd", "srk_dat_channel_gram_fwd",
            "srk_dat_channel_apply_fwd", "srk_dat_channel_gram_ws_floats", "srk_cab_ws_floats", "srk_token_mean_fwd", "srk_token_mean_mlp_fwd", "srk_dat_channel_softmax_fwd", "srk_dwconv3x3_rows_planes_fwd")
@@ -405,6 +407,28 @@ def rows_to_f16(x, out16, *, channels, ld_in, pixels) -> None:
         raise RuntimeError("rows_to_f16: output must be a contiguous fp16 (pixels, cp) tensor")
     with _launch("rows_to_f16", x, out16) as st:
         _check(lib.srk_rows_to_f16(x.data_ptr(), ld_in, channels, out16.data_ptr(), cp, pixels, st), lib)
+
+
+def rows_to_f16_split(x, out16, *, channels, ld_in, pixels, act=ACT_NONE, slope=0.0, shuffle=None) -> None:
+    """srk_rows_to_f16_split: fp32 rows (pixels, ld_in) -> the fp16 pair hi = fp16(act(x)), lo = fp16(act(x) - hi) of the tight mode.
+    out16 (2, P, cp): two NHWC images (hi, lo).  out16 (P, 3 * 64): the interleaved [hi | lo | hi] image of a C_in = 64 layer.
+    shuffle = (H, W): x holds the 256 channels of a conv + PixelShuffle(2) stage at H x W pixels per image; P = 4 * pixels."""
+    lib = load()
+    _require_cuda_f32(x)
+    if out16.dtype != torch.float16 or not out16.is_contiguous():
+        raise RuntimeError("rows_to_f16_split: output must be a contiguous fp16 tensor")
+    opix = pixels * (4 if shuffle else 1)
+    if out16.dim() == 3 and out16.shape[0] == 2 and out16.shape[1] == opix:
+        cp = ld_out = out16.shape[2]
+        hi, lo, hi2 = out16.data_ptr(), out16[1].data_ptr(), None
+    elif out16.dim() == 2 and out16.shape == (opix, 192):
+        cp, ld_out = 64, 192
+        hi, lo, hi2 = out16.data_ptr(), out16.data_ptr() + 128, out16.data_ptr() + 256
+    else:
+        raise RuntimeError(f"rows_to_f16_split: output must be (2, {opix}, cp) or ({opix}, 192), got {tuple(out16.shape)}")
+    sh, sw = shuffle if shuffle else (0, 0)
+    with _launch("rows_to_f16_split", x, out16) as st:
+        _check(lib.srk_rows_to_f16_split(x.data_ptr(), ld_in, channels, hi, lo, hi2, ld_out, cp, pixels, act, slope, sh, sw, st), lib)
 
 
 def image_to_f16_split(x, out16, mean, img_range) -> None:

@@ -25,6 +25,9 @@ from . import _lib as L
 from . import packing
 
 USE_FUSED_CONV = os.environ.get("SRK_CONV", "fused") != "cudnn"
+# Tight mode (SwinIR.set_precision("fp16")): every convolution as hi / lo fp16 pairs on the same kernel (SplitConv3x3), set by the
+# model around its forward.
+SPLIT = False
 
 
 class _Cache:
@@ -84,6 +87,85 @@ def rows_to_f16(rows: torch.Tensor, channels: int) -> torch.Tensor:
     return out
 
 
+def rows_split(rows: torch.Tensor, channels: int, *, interleaved: bool = False, act: int = L.ACT_NONE, slope: float = 0.0,
+               shuffle=None) -> torch.Tensor:
+    """fp32 token rows (..., C) -> the tight mode's fp16 pair (srk_rows_to_f16_split): (2, P, 64 * ceil(C / 64)) = (hi, lo) images,
+    or with interleaved=True (C = 64) the (P, 192) image [hi | lo | hi].  shuffle=(H, W): rows are a conv + PixelShuffle(2)
+    stage's 256 channels at H x W; the pair comes out at 2H x 2W (P = 4 x pixels)."""
+    pixels = rows.numel() // rows.shape[-1]
+    opix = 4 * pixels if shuffle else pixels
+    cp = 64 if shuffle else (channels + 63) // 64 * 64
+    if interleaved and cp != 64:
+        raise RuntimeError("rows_split: the interleaved layout is for 64-channel layers")
+    out = torch.empty((opix, 192) if interleaved else (2, opix, cp), dtype=torch.float16, device=rows.device)
+    L.rows_to_f16_split(rows, out, channels=channels, ld_in=rows.shape[-1], pixels=pixels, act=act, slope=slope, shuffle=shuffle)
+    return out
+
+
+class SplitConv3x3:
+    """FusedConv3x3 for the tight mode: fp32-class accuracy out of the fp16 tensor-core kernel.  Activations and weights are fp16
+    pairs (x = hi + lo to 22 bits) and conv(x, w) = hi(x) * hi(w) + lo(x) * hi(w) + hi(x) * lo(w), accumulated in fp32:
+    C_in = 64 layers in ONE launch over the interleaved image (k_atoms = 3), wider layers as three launches accumulating into the
+    fp32 output rows (smallest terms first)."""
+
+    def __init__(self, conv: nn.Conv2d, *, pixel_shuffle: bool = False, out_scale: float = 1.0, out_shift=None):
+        FusedConv3x3(conv)                 # geometry check
+        self.conv = conv
+        self.interleaved = conv.in_channels <= 64
+        self.kw = dict(pixel_shuffle=pixel_shuffle, out_scale=out_scale, out_shift=out_shift,
+                       split="interleaved" if self.interleaved else "pair")
+        self._cache = _Cache()
+
+    def packed(self):
+        c = self.conv
+
+        def build():
+            ws, bias, meta = packing.pack_conv3x3(c.weight, c.bias, **self.kw)
+            return ws, bias, torch.zeros_like(bias), meta
+        return self._cache.get([c.weight, c.bias], build)
+
+    def __call__(self, xs: torch.Tensor, B: int, H: int, W: int, *, out: torch.Tensor, mode: int, ld_out: int,
+                 residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """xs: rows_split(...) of the input.  The activation of the layer (if any) is applied by the NEXT rows_split."""
+        ws, bias, zero, meta = self.packed()
+        kw = dict(batch=B, height=H, width=W, k_atoms=meta["k_atoms"], np_=meta["np"], cout=meta["cout"], out_mode=mode, ld_out=ld_out)
+        if self.interleaved:
+            L.conv3x3(xs, ws, bias, out, residual=residual, **kw)
+            return out
+        if mode != L.CONV_OUT_ROWS_F32:
+            raise RuntimeError("SplitConv3x3: layers wider than 64 input channels accumulate in fp32 rows (CONV_OUT_ROWS_F32)")
+        L.conv3x3(xs[1], ws[0], zero, out, residual=residual, **kw)          # lo(x) * hi(w)  (+ residual)
+        L.conv3x3(xs[0], ws[1], zero, out, residual=out, **kw)               # + hi(x) * lo(w)
+        L.conv3x3(xs[0], ws[0], bias, out, residual=out, **kw)               # + hi(x) * hi(w) + bias
+        return out
+
+
+class SplitPixelShuffleTail:
+    """PixelShuffleTail for the tight mode: every intermediate stays fp32 rows, re-split into fp16 pairs between the layers (the
+    LeakyReLU and the PixelShuffle(2) permutation ride on that pass)."""
+
+    def __init__(self, conv_before_upsample: nn.Sequential, upsample: nn.Sequential, conv_last: nn.Conv2d, img_range: float, mean):
+        ref = PixelShuffleTail(conv_before_upsample, upsample, conv_last, img_range, mean)      # structure checks
+        self.slope, self.out_ch = ref.slope, ref.out_ch
+        self.before = SplitConv3x3(conv_before_upsample[0])
+        self.ups = [SplitConv3x3(u.conv, pixel_shuffle=True) for u in ref.ups]
+        self.last = SplitConv3x3(conv_last, **{k: ref.last.kw[k] for k in ("out_scale", "out_shift")})
+
+    def __call__(self, xs: torch.Tensor, B: int, H: int, W: int) -> torch.Tensor:
+        dev = xs.device
+        t = torch.empty(B * H * W, 64, dtype=torch.float32, device=dev)
+        self.before(xs, B, H, W, out=t, mode=L.CONV_OUT_ROWS_F32, ld_out=64)
+        ts = rows_split(t, 64, interleaved=True, act=L.ACT_LEAKY_RELU, slope=self.slope)
+        for up in self.ups:
+            u = torch.empty(B * H * W, 256, dtype=torch.float32, device=dev)
+            up(ts, B, H, W, out=u, mode=L.CONV_OUT_ROWS_F32, ld_out=256)
+            ts = rows_split(u, 256, interleaved=True, shuffle=(H, W))
+            H, W = 2 * H, 2 * W
+        y = torch.empty(B, H, W, self.out_ch, dtype=torch.float32, device=dev)
+        self.last(ts, B, H, W, out=y, mode=L.CONV_OUT_IMAGE, ld_out=self.out_ch)
+        return y.permute(0, 3, 1, 2)
+
+
 class PixelShuffleTail:
     """conv_before_upsample (+ LeakyReLU) -> Upsample([conv, PixelShuffle(2)] x n) -> conv_last -> x / img_range + mean
     (network_swinir.py:742-745, :816-817, :838; identical in hat_arch.py:864-869, :989-992 and dat_arch.py:806-811, :848-858)."""
@@ -121,6 +203,10 @@ def group_conv_residual(module: nn.Module, conv: nn.Conv2d, t: torch.Tensor, x: 
     ``x + conv(t)`` with t, x fp32 token rows (B, H*W, C); the result is written over t."""
     B, Ltok, C = t.shape
     t = t.contiguous()
+    if SPLIT:
+        if not hasattr(module, "_sconv"):
+            object.__setattr__(module, "_sconv", SplitConv3x3(conv))
+        return module._sconv(rows_split(t, C), B, x_size[0], x_size[1], out=t, mode=L.CONV_OUT_ROWS_F32, ld_out=C, residual=x.contiguous())
     if not hasattr(module, "_fconv"):
         object.__setattr__(module, "_fconv", FusedConv3x3(conv))
     return module._fconv(rows_to_f16(t, C), B, x_size[0], x_size[1], out=t, mode=L.CONV_OUT_ROWS_F32, ld_out=C, residual=x.contiguous())
@@ -154,6 +240,16 @@ def fused_forward(model: nn.Module, x: torch.Tensor, first_norm: Optional[nn.Lay
         t = torch.empty_like(feat0)
         L.layernorm(feat0, t, first_norm.weight, first_norm.bias, num_tokens=B * H * W, ld_in=C, ld_out=C)
     t = run_layers(t, (H, W))
+    if SPLIT:
+        if not hasattr(model, "_s_after"):
+            object.__setattr__(model, "_s_after", SplitConv3x3(model.conv_after_body))
+            object.__setattr__(model, "_s_tail", SplitPixelShuffleTail(model.conv_before_upsample, model.upsample, model.conv_last,
+                                                                        model.img_range, model.mean))
+        t = t.contiguous()
+        tn = torch.empty_like(feat0)
+        L.layernorm(t, tn, model.norm.weight, model.norm.bias, num_tokens=B * H * W, ld_in=C, ld_out=C)
+        model._s_after(rows_split(tn, C), B, H, W, out=tn, mode=L.CONV_OUT_ROWS_F32, ld_out=C, residual=feat0)
+        return model._s_tail(rows_split(tn, C), B, H, W)
     t16 = torch.empty(B * H * W, L.DIM_PAD, dtype=torch.float16, device=dev)
     L.layernorm_f16(t.contiguous(), t16, model.norm.weight, model.norm.bias, num_tokens=B * H * W, ld_in=C)   # final norm, straight to the conv's layout
     if t.data_ptr() == feat0.data_ptr():

@@ -491,6 +491,24 @@ int srk_rows_to_f16(const float* x, int32_t ld_in, int32_t channels, void* out_f
     return check(srk::launch_rows_to_f16(x, ld_in, channels, static_cast<__half*>(out_f16), cp, pixels, static_cast<cudaStream_t>(stream)), "srk_rows_to_f16");
 }
 
+int srk_rows_to_f16_split(const float* x, int32_t ld_in, int32_t channels, void* hi_f16, void* lo_f16, void* hi2_f16, int32_t ld_out, int32_t cp,
+                          int64_t pixels, int32_t act, float slope, int32_t shuffle_h, int32_t shuffle_w, void* stream) {
+    if (!x || !hi_f16 || !lo_f16) return fail("srk_rows_to_f16_split: null argument");
+    if (channels <= 0 || ld_in < channels || (ld_in & 3) || cp % 64 || cp <= 0 || ld_out < cp || ld_out % 8 || !aligned16(x) || !aligned16(hi_f16) ||
+        !aligned16(lo_f16) || (hi2_f16 && !aligned16(hi2_f16)))
+        return fail("srk_rows_to_f16_split: need ld_in %% 4 == 0 >= channels, cp %% 64 == 0, ld_out %% 8 == 0 >= cp, 16-byte aligned pointers");
+    if (shuffle_h > 0 || shuffle_w > 0) {
+        if (shuffle_h <= 0 || shuffle_w <= 0 || channels != 256 || cp != 64 || pixels % (static_cast<int64_t>(shuffle_h) * shuffle_w))
+            return fail("srk_rows_to_f16_split: pixel-shuffle input needs channels == 256, cp == 64, pixels a multiple of shuffle_h * shuffle_w");
+    } else if (cp < channels) {
+        return fail("srk_rows_to_f16_split: cp must cover the channels");
+    }
+    if (act < SRK_ACT_NONE || act > SRK_ACT_GELU) return fail("srk_rows_to_f16_split: unknown activation %d", act);
+    return check(srk::launch_rows_to_f16_split(x, ld_in, channels, static_cast<__half*>(hi_f16), static_cast<__half*>(lo_f16),
+                                               static_cast<__half*>(hi2_f16), ld_out, cp, pixels, act, slope, shuffle_h, shuffle_w,
+                                               static_cast<cudaStream_t>(stream)), "srk_rows_to_f16_split");
+}
+
 int srk_image_to_f16_split(const float* x, int64_t sb, int64_t sc, int64_t sy, int64_t sx, int32_t channels, int32_t batch, int32_t height,
                            int32_t width, const float* mean3, float range, void* out_f16, void* stream) {
     if (!x || !mean3 || !out_f16) return fail("srk_image_to_f16_split: null argument");

@@ -336,6 +336,56 @@ __global__ void __launch_bounds__(256) rows_to_f16_kernel(const float* __restric
     }
 }
 
+// ---- fp32 token rows -> the fp16 PAIR hi = fp16(v), lo = fp16(v - hi) of the tight mode's split convolutions (v = act(x)):
+// conv(x, w) ~= hi(x) * hi(w) + lo(x) * hi(w) + hi(x) * lo(w) on the fp16 tensor-core kernel, fp32 accumulation; the dropped
+// lo * lo term is 2^-22 relative.  `hi`, `lo` and (optionally) `hi2` are NHWC images with row pitch ld_out; a C_in = 64 layer
+// passes hi = base, lo = base + 64, hi2 = base + 128, ld_out = 192, so that ONE launch of conv3x3_kernel with k_atoms = 3 does
+// all three products against weights packed [hi(w) | hi(w) | lo(w)]; wider layers pass two images and launch three times.
+// The activation of the PREVIOUS layer (conv_before_upsample's LeakyReLU, network_swinir.py:743) is applied on the way in, and
+// with shuffle_h > 0 the rows are the 4 x 64 channels of a conv + nn.PixelShuffle(2) stage (weights packed pixel_shuffle=True,
+// network_swinir.py:584-585): group s = 2 i + j of input pixel (y, x) goes to output pixel (2 y + i, 2 x + j).
+__global__ void __launch_bounds__(256) rows_to_f16_split_kernel(const float* __restrict__ x, int ld_in, int C, __half* __restrict__ hi,
+                                                                __half* __restrict__ lo, __half* __restrict__ hi2, int ld_out, int cp, int64_t pixels,
+                                                                int act, float slope, int sh, int sw) {
+    const int groups = (sh > 0 ? 256 : cp) >> 3;
+    const int64_t total = pixels * groups;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t pix = i / groups;
+        int c0 = static_cast<int>(i - pix * groups) * 8;
+        float v[8];
+        const float* src = x + pix * ld_in + c0;
+        if (c0 + 8 <= C) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = c0 + k < C ? __ldg(src + k) : 0.f;
+        }
+        int64_t opix = pix;
+        if (sh > 0) {
+            const int sub = c0 >> 6;
+            c0 &= 63;
+            const int64_t b = pix / (static_cast<int64_t>(sh) * sw);
+            const int r = static_cast<int>(pix - b * sh * sw), y = r / sw, xx = r - y * sw;
+            opix = (b * 2 * sh + 2 * y + (sub >> 1)) * 2 * sw + 2 * xx + (sub & 1);
+        }
+        float l[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (act == SRK_ACT_LEAKY_RELU) v[k] = v[k] > 0.f ? v[k] : v[k] * slope;
+            else if (act == SRK_ACT_GELU) v[k] = 0.5f * v[k] * (1.0f + erff(v[k] * 0.70710678118654752f));
+            const float h = __half2float(__float2half_rn(v[k]));
+            l[k] = v[k] - h;
+        }
+        const uint4 H = make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]), pack_f16x2(v[6], v[7]));
+        const uint4 Lo = make_uint4(pack_f16x2(l[0], l[1]), pack_f16x2(l[2], l[3]), pack_f16x2(l[4], l[5]), pack_f16x2(l[6], l[7]));
+        const int64_t o = opix * ld_out + c0;
+        *reinterpret_cast<uint4*>(hi + o) = H;
+        *reinterpret_cast<uint4*>(lo + o) = Lo;
+        if (hi2 != nullptr) *reinterpret_cast<uint4*>(hi2 + o) = H;
+    }
+}
+
 // ---- network input (B, C <= 3, H, W) fp32, any strides -> fp16 NHWC (P, 64) for conv_first (network_swinir.py:720, :803-804):
 // v = (x - mean[c]) * range; channels [0, C) = hi(v), [C, 2C) = v - hi(v), [2C, 3C) = hi(v) again, rest 0.  With the weights packed
 // as [hi(w), hi(w), w - hi(w)] the fp16 MMA computes hi*hi + lo*hi + hi*lo: the input and weight roundings cancel to second
@@ -427,6 +477,16 @@ cudaError_t launch_rows_to_f16(const float* x, int ld_in, int C, __half* out, in
     const int64_t blocks = (total + 255) / 256;
     const int grid = static_cast<int>(blocks < 148 * 16 ? blocks : 148 * 16);
     rows_to_f16_kernel<<<grid, 256, 0, stream>>>(x, ld_in, C, out, cp, pixels);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rows_to_f16_split(const float* x, int ld_in, int C, __half* hi, __half* lo, __half* hi2, int ld_out, int cp, int64_t pixels,
+                                     int act, float slope, int shuffle_h, int shuffle_w, cudaStream_t stream) {
+    if (pixels <= 0) return cudaSuccess;
+    const int64_t total = pixels * ((shuffle_h > 0 ? 256 : cp) >> 3);
+    const int64_t blocks = (total + 255) / 256;
+    const int grid = static_cast<int>(blocks < 148 * 16 ? blocks : 148 * 16);
+    rows_to_f16_split_kernel<<<grid, 256, 0, stream>>>(x, ld_in, C, hi, lo, hi2, ld_out, cp, pixels, act, slope, shuffle_h, shuffle_w);
     return cudaGetLastError();
 }
 

@@ -228,6 +228,8 @@ struct ConvArgs {
 };
 cudaError_t launch_conv3x3(const ConvArgs& a, cudaStream_t stream);
 cudaError_t launch_rows_to_f16(const float* x, int ld_in, int C, ::__half* out, int cp, int64_t pixels, cudaStream_t stream);
+cudaError_t launch_rows_to_f16_split(const float* x, int ld_in, int C, ::__half* hi, ::__half* lo, ::__half* hi2, int ld_out, int cp, int64_t pixels,
+                                     int act, float slope, int shuffle_h, int shuffle_w, cudaStream_t stream);
 cudaError_t launch_image_to_f16_split(const float* x, int64_t sb, int64_t sc, int64_t sy, int64_t sx, int C, int B, int H, int W,
                                       const float* mean3, float range, ::__half* out, cudaStream_t stream);
 cudaError_t launch_gather_tiles(const float* slab, int64_t slab_cstride, int slab_w, const int32_t* src_yx, int num_tiles, int channels,

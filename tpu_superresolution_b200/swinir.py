@@ -542,8 +542,9 @@ class SwinIR(nn.Module):
         """GEMM operand types of the fused attention / MLP kernels (PRECISIONS): "bf16" (default; gate max abs <= 2e-3 vs the
         reference's fp32 forward), "bf16_strict", or "fp16" -- the tight mode (include/srk.h: SRK_OPERANDS_F16; fp16 has TF32's
         11-bit significand; gate <= 2e-4).
-        In the tight mode the 3x3 convolutions run in fp32 on the library path (slower; the default mode's tcgen05 convolution has
-        fp16 operands, which alone would exceed the tight gate).  A ``GraphedModel`` around this model must be ``reset()``."""
+        In the tight mode the 3x3 convolutions run as hi / lo fp16 pairs on the same tcgen05 kernel (convs.SplitConv3x3: three
+        products per layer; plain fp16 operands alone would exceed the tight gate).  A ``GraphedModel`` around this model must be
+        ``reset()``."""
         set_precision(self, precision)
         self.precision = precision
         return self
@@ -571,9 +572,16 @@ class SwinIR(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("SwinIR: CUDA input required (no CPU fallback)")
         _inference_only(self.conv_first)
-        if getattr(self, "precision", "bf16") == "fp16" and convs.USE_FUSED_CONV:
-            # tight mode: the fused attention / MLP kernels with fp16 operands; the 3x3 convolutions in fp32 on the library path
-            # (the tcgen05 convolution's fp16 operands alone cost 1.7 - 2.6e-4 max abs, like cuDNN's TF32: tools/probe_precision.py)
+        if getattr(self, "precision", "bf16") == "fp16" and convs.USE_FUSED_CONV and not convs.SPLIT:
+            # tight mode: the fused attention / MLP kernels with fp16 operands, and the 3x3 convolutions as hi / lo fp16 pairs on
+            # the tcgen05 kernel (convs.SplitConv3x3; plain fp16 operands alone cost 1.7 - 2.6e-4 max abs, like cuDNN's TF32:
+            # tools/probe_precision.py).  SRK_TIGHT_CONV=library: fp32 library convolutions instead (the earlier tight mode, A/B).
+            if convs.fused_ok(self) and not self.ape and x.dtype == torch.float32 and os.environ.get("SRK_TIGHT_CONV", "split") != "library":
+                convs.SPLIT = True
+                try:
+                    return self._forward_fused(x)
+                finally:
+                    convs.SPLIT = False
             tf32 = torch.backends.cudnn.allow_tf32
             convs.USE_FUSED_CONV, torch.backends.cudnn.allow_tf32 = False, False
             try:
