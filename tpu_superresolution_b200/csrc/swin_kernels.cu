@@ -305,6 +305,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) swin_attn_kernel(const AttnPara
             uint32_t stage = 0, phase = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                 uint32_t off = 0;
+#pragma unroll 1
                 for (int s = 0; s < 15; ++s) {      // 3 x 24 KB (Wv k-atoms), 9 x 16 KB (3 head pairs x 3 k-atoms of [q|k|q|k]), 3 x 24 KB (proj)
                     const uint32_t bytes = (s < 3 || s >= 12) ? 24576u : 16384u;
                     mbar_wait(&bars[B_EMPTY + stage], phase ^ 1);
@@ -764,6 +765,7 @@ __global__ void __launch_bounds__(LNW ? NTHREADS : 320, 1) swin_mlp_kernel(const
             uint32_t stage = 0, phase = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                 uint32_t off = 0;
+#pragma unroll 1
                 for (int s = 0; s < 15; ++s) {      // MMA order: fc1 c0, c1 (6 x 16 KB) | fc2 k-atoms 0,1 (2 x 24 KB) | fc1 c2 (3 x 16 KB) | fc2 k-atoms 2..5
                     const uint32_t bytes = (s < 6 || (s >= 8 && s < 11)) ? 16384u : 24576u;
                     mbar_wait(&bars[MB_EMPTY + stage], phase ^ 1);
