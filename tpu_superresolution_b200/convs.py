@@ -11,6 +11,10 @@ tail fused into the epilogue:
     one kernel each, conv_last with ``/ img_range + mean`` (:838) folded into its weights -> the fp32 image;
   * HAT's CAB (hat_arch.py:67-72): conv -> GELU -> conv.
 
+Tight mode (``SwinIR.set_precision("fp16")``, module flag ``SPLIT``): the same layers through ``SplitConv3x3`` /
+``SplitPixelShuffleTail`` -- activations and weights as hi / lo fp16 pairs, three products per layer accumulated in fp32
+(fp32-class accuracy from the fp16 tensor-core kernel; intermediates stay fp32 rows).
+
 ``SRK_CONV=cudnn`` selects the round-1 path (library convolutions + separate bias / activation / shuffle passes) for A/B runs.
 """
 from __future__ import annotations
