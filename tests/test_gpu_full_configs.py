@@ -99,6 +99,35 @@ def test_tight_mode_fp16_operands_vs_reference_golden(cfg_name, kind, seed):
     assert abs((m(lr.cuda()).cpu() - ref).abs().max().item() - err_bf16) == 0.0      # switching back repacks
 
 
+@pytest.mark.parametrize("shape", [(2, 40, 56), (1, 21, 30), (3, 64, 72)])
+def test_tight_mode_split_convolutions_vs_fp32_library_convolutions(shape, monkeypatch):
+    """The tight mode's convolutions (convs.SplitConv3x3: hi / lo fp16 pairs on the tcgen05 kernel, three products per layer) against
+    the same mode with fp32 library convolutions (SRK_TIGHT_CONV=library), at image sizes that need window padding and leave
+    partial patches; x4 tail (two PixelShuffle stages).  Both are fp32-class computations of the same network; with the stress weights
+    their rounding differences are amplified to ~2e-5 (measured; 6e-6 with init weights at the bench size), a geometry error would
+    show as >= 1e-2: gate 1e-4 max abs on [0, 1] pixels."""
+    cfg = synth.CONFIGS["swinir_x4_d2"]
+    sd = synth.make_swinir_state_dict(cfg, seed=77, kind="stress")
+    m = srk.SwinIR(**cfg.as_kwargs()).eval()
+    m.load_state_dict(sd, strict=True)
+    m.cuda().set_precision("fp16")
+    lr = synth.make_lr_batch(*shape, seed=5).cuda()
+    monkeypatch.setenv("SRK_TIGHT_CONV", "split")
+    before = L.launch_count()
+    y = m(lr)
+    n_split = L.launch_count() - before
+    monkeypatch.setenv("SRK_TIGHT_CONV", "library")
+    before = L.launch_count()
+    ref = m(lr)
+    assert n_split > L.launch_count() - before                      # the split path is all ours: more of our launches
+    assert y.shape == ref.shape == (shape[0], 3, 4 * shape[1], 4 * shape[2])
+    err = (y - ref).abs().max().item()
+    print(f"tight mode {shape}: split vs fp32 library convolutions max abs {err:.3e}")
+    assert err <= 1e-4
+    monkeypatch.setenv("SRK_TIGHT_CONV", "split")
+    assert torch.equal(m(lr), y)                                    # deterministic
+
+
 @pytest.mark.parametrize("name", ["hat_x4", "dat_x2"])
 def test_baseline_config_batch_vs_oracle_sample(name):
     """configs[2] (HAT x4, B = 8) and configs[3] (DAT x2, B = 16) at full depth, like
