@@ -619,6 +619,11 @@ class DAT(nn.Module):
         L.layernorm(y, y, self.norm.weight, self.norm.bias, num_tokens=B * H * W, ld_in=C, ld_out=C)
         return y.view(B, H, W, C).permute(0, 3, 1, 2)
 
+    def invalidate_packed(self) -> None:
+        """Forget all packed weight images: needed only after parameters were edited in place through ``.data`` (EMA, weight surgery),
+        which changes neither ``_version`` nor ``data_ptr`` (the cache keys).  A ``GraphedModel`` around the model must be ``reset()``."""
+        convs.invalidate_all()
+
     def forward(self, x):
         if not x.is_cuda:
             raise RuntimeError("DAT: CUDA input required (no CPU fallback)")

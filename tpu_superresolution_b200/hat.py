@@ -504,6 +504,11 @@ class HAT(nn.Module):
         L.layernorm(x, x, self.norm.weight, self.norm.bias, num_tokens=B * Ltok, ld_in=C, ld_out=C)
         return self.patch_unembed(x, x_size)
 
+    def invalidate_packed(self) -> None:
+        """Forget all packed weight images: needed only after parameters were edited in place through ``.data`` (EMA, weight surgery),
+        which changes neither ``_version`` nor ``data_ptr`` (the cache keys).  A ``GraphedModel`` around the model must be ``reset()``."""
+        convs.invalidate_all()
+
     def forward(self, x):
         if not x.is_cuda:
             raise RuntimeError("HAT: CUDA input required (no CPU fallback)")
