@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SRK_ABI_VERSION 2
+#define SRK_ABI_VERSION 3
 
 /* Fixed geometry of the SwinIR/HAT/DAT "M" family served by these kernels. */
 #define SRK_DIM 180        /* embed_dim                      (finetune_swinir.py:276) */
@@ -306,7 +306,7 @@ int srk_stitch_finalize(const float* E, int64_t e_channel_stride, const float* c
 /* 3x3 convolution, stride 1, zero padding 1, as a tcgen05 implicit GEMM with the conv's tail fused (csrc/conv_kernel.cu).
  * Replaces F.conv2d / nn.Conv2d(…, 3, 1, 1) at network_swinir.py:465 (RSTB), :720 (conv_first), :729 (conv_after_body), :742-745
  * (conv_before_upsample, Upsample, conv_last), hat_arch.py:67-72 (CAB) and the same layers of hat_arch.py / dat_arch.py.
- *   in       fp16 NHWC (batch, height, width, 64 * k_atoms), channels zero-padded (written by srk_rows_to_f16 /
+ *   in       fp16 NHWC (batch, height, width, 64 * a_atoms), channels zero-padded (written by srk_rows_to_f16 /
  *            srk_image_to_f16_split or by a previous srk_conv3x3_fwd in an fp16 output mode)
  *   wstream  packing.pack_conv3x3: k_atoms x 3 x 3 slabs of np rows x 128 B;  bias: np floats
  *   out      SRK_CONV_OUT_ROWS_F32:     fp32 (pixels, ld_out), out = act(conv + bias) [+ residual]; residual may alias out
@@ -321,26 +321,30 @@ int srk_stitch_finalize(const float* E, int64_t e_channel_stride, const float* c
 #define SRK_CONV_OUT_IMAGE 3
 typedef struct SrkConvDesc {
     int32_t batch, height, width;
-    int32_t k_atoms;        /* padded input channels / 64: 1..4 */
+    int32_t k_atoms;        /* k-steps of 64 channels: 1..12; normally = a_atoms = padded input channels / 64 */
     int32_t np;             /* padded output channels: multiple of 32 (16 for SRK_CONV_OUT_IMAGE), <= 256 */
     int32_t cout;           /* real output channels (multiple of 4 for SRK_CONV_OUT_ROWS_F32) */
     int32_t out_mode;
     int32_t ld_out;
     int32_t act;            /* SRK_ACT_* */
     float slope;
+    int32_t a_atoms;        /* 64-channel atoms of the input image, 1..8 (0: = k_atoms).  With k_atoms > a_atoms the last k_atoms - a_atoms
+                             * k-steps re-read the image's last atoms: the tight mode's convolution is ONE launch over the image
+                             * [lo(x) | hi(x)] (a_atoms = 2 C/64) against the weights [hi(w) | lo(w) | hi(w)] (k_atoms = 3 C/64):
+                             * lo*hi + hi*lo + hi*hi, small terms first, see srk_rows_to_f16_split */
 } SrkConvDesc;
 int srk_conv3x3_fwd(const SrkConvDesc* desc, const void* in_f16, const void* wstream, const float* bias, const float* residual, void* out,
                     void* stream);
 /* fp32 token rows (pixels, ld_in) with `channels` channels -> fp16 NHWC (pixels, cp), cp = 64 * k_atoms, zero padded. */
 int srk_rows_to_f16(const float* x, int32_t ld_in, int32_t channels, void* out_f16, int32_t cp, int64_t pixels, void* stream);
 /* Tight mode (fp32-class convolutions out of the fp16 tensor-core kernel): fp32 rows -> the fp16 pair hi = fp16(v), lo = fp16(v - hi),
- * v = act(x), as NHWC images with row pitch ld_out and cp = 64 * k_atoms zero-padded channels each; hi2 (may be NULL) receives a
- * second copy of hi.  conv(x, w) = srk_conv3x3_fwd(hi, hi(w)) + (lo, hi(w)) + (hi, lo(w)), either as three accumulating launches
- * (SRK_CONV_OUT_ROWS_F32 with residual == out) or, for C_in = 64, as ONE launch with k_atoms = 3 over the interleaved image
- * hi = base, lo = base + 64, hi2 = base + 128, ld_out = 192 against weights packed [hi(w) | hi(w) | lo(w)].
+ * v = act(x) (22 bits together), as two NHWC images with row pitch ld_out and cp = 64 * ceil(C / 64) zero-padded channels each.
+ * conv(x, w) = lo * hi(w) + hi * lo(w) + hi * hi(w), accumulated in fp32 in that order, is ONE srk_conv3x3_fwd launch over the
+ * image [lo | hi] (lo = base, hi = base + cp, ld_out = 2 cp; SrkConvDesc.a_atoms = 2 cp / 64, k_atoms = 3 cp / 64) against weights
+ * packed [hi(w) | lo(w) | hi(w)] (packing.pack_conv3x3(split=True)); the dropped lo * lo term is 2^-22 relative.
  * shuffle_h, shuffle_w > 0: x holds the 4 x 64 output channels of a conv + nn.PixelShuffle(2) stage at shuffle_h x shuffle_w pixels
  * per image (channels == 256, cp == 64; network_swinir.py:584-585); the pair is written at the 2x resolution. */
-int srk_rows_to_f16_split(const float* x, int32_t ld_in, int32_t channels, void* hi_f16, void* lo_f16, void* hi2_f16, int32_t ld_out, int32_t cp,
+int srk_rows_to_f16_split(const float* x, int32_t ld_in, int32_t channels, void* hi_f16, void* lo_f16, int32_t ld_out, int32_t cp,
                           int64_t pixels, int32_t act, float slope, int32_t shuffle_h, int32_t shuffle_w, void* stream);
 /* network input (batch, channels <= 3, height, width) fp32 with element strides (sb, sc, sy, sx) -> fp16 NHWC (pixels, 64) holding
  * [hi(v), v - hi(v), hi(v)] of v = (x - mean[c]) * range (network_swinir.py:803-804): conv_first's input with the fp16 rounding

@@ -181,14 +181,17 @@ def test_constructor_variants_keep_the_reference_state_dict(name):
 
 
 def test_split_conv_packing():
-    """Tight-mode convolution weights (packing.pack_conv3x3(split=...)): hi(w) + lo(w) reproduces w to 2^-22; the interleaved stream
-    is [hi | hi | lo] over three 64-channel k-atoms; pair streams are two streams of the plain size."""
+    """Tight-mode convolution weights (packing.pack_conv3x3(split=True)): the stream is the k-atoms [hi(w) | lo(w) | hi(w)], with
+    hi(w) + lo(w) reproducing w to 2^-22, for one launch of 3 C/64 k-steps over the [lo(x) | hi(x)] image (2 C/64 atoms)."""
     g = torch.Generator().manual_seed(5)
     w, b = torch.randn(180, 180, 3, 3, generator=g) * 0.03, torch.randn(180, generator=g)
     plain, bias, meta = packing.pack_conv3x3(w, b)
-    (hi, lo), bias2, meta2 = packing.pack_conv3x3(w, b, split="pair")
-    assert meta2 == meta == {"k_atoms": 3, "np": 192, "cout": 180} and torch.equal(bias, bias2)
-    assert torch.equal(hi, plain) and lo.numel() == plain.numel()
+    split, bias2, meta2 = packing.pack_conv3x3(w, b, split=True)
+    assert meta == {"k_atoms": 3, "np": 192, "cout": 180} and meta2 == {"k_atoms": 9, "a_atoms": 6, "np": 192, "cout": 180}
+    n = plain.numel()
+    assert torch.equal(bias, bias2) and split.numel() == 3 * n
+    hi, lo, hi2 = split[:n], split[n:2 * n], split[2 * n:]
+    assert torch.equal(hi, plain) and torch.equal(hi2, plain)
     h, l = hi.view(torch.float16).float(), lo.view(torch.float16).float()
     assert l.abs().max() <= 2.0 ** -11 * h.abs().max() and l.abs().max() > 0
     # first slab = output rows x input channels 0..63 at (dy, dx) = (0, 0): hi + lo against the fp32 weights
@@ -196,15 +199,11 @@ def test_split_conv_packing():
     err = (first(hi)[:180] + first(lo)[:180] - w[:, :64, 0, 0]).abs().max()
     assert err <= 2.0 ** -21 * w.abs().max()
     w64 = torch.randn(256, 64, 3, 3, generator=g) * 0.05
-    il, _, m3 = packing.pack_conv3x3(w64, None, split="interleaved", pixel_shuffle=True)
+    s64, _, m3 = packing.pack_conv3x3(w64, None, split=True, pixel_shuffle=True)
     one, _, m1 = packing.pack_conv3x3(w64, None, pixel_shuffle=True)
-    assert m3 == {"k_atoms": 3, "np": 256, "cout": 256} and m1["k_atoms"] == 1 and il.numel() == 3 * one.numel()
-    n = one.numel()
-    assert torch.equal(il[:n], one) and torch.equal(il[n:2 * n], one) and not torch.equal(il[2 * n:], one)
+    assert m3 == {"k_atoms": 3, "a_atoms": 2, "np": 256, "cout": 256} and m1["k_atoms"] == 1 and s64.numel() == 3 * one.numel()
     with pytest.raises(RuntimeError):
-        packing.pack_conv3x3(w, b, split="interleaved")               # 180 input channels do not fit one k-atom
-    with pytest.raises(RuntimeError):
-        packing.pack_conv3x3(torch.randn(180, 3, 3, 3), None, split_first=True, split="pair")
+        packing.pack_conv3x3(torch.randn(180, 3, 3, 3), None, split_first=True, split=True)
 
 
 def test_fp16_operand_packing_and_precision_table():

@@ -140,8 +140,8 @@ def test_split_convs_are_fp32_grade():
             mod.float().to(dev)
     rows = x.permute(0, 2, 3, 1).reshape(B * H * W, 180).contiguous().to(dev)
     xs = convs.rows_split(rows, 180)
-    assert xs.shape == (2, B * H * W, 192) and torch.equal(xs[:, :, 180:], torch.zeros_like(xs[:, :, 180:]))
-    assert _rel(xs[0].float() + xs[1].float(), F.pad(rows, (0, 12)).cpu()) < 1e-6
+    assert xs.shape == (B * H * W, 384) and not xs[:, 180:192].any() and not xs[:, 372:].any()          # [lo | hi], zero padded
+    assert _rel(xs[:, :192].float() + xs[:, 192:].float(), F.pad(rows, (0, 12)).cpu()) < 1e-6
     out = res.to(dev).clone()
     convs.SplitConv3x3(body)(xs, B, H, W, out=out, mode=L.CONV_OUT_ROWS_F32, ld_out=180, residual=out)        # in place += like the RSTB tail
     assert _rel(out, ref_body) < 3e-6
@@ -176,3 +176,6 @@ def test_bad_arguments_are_errors():
         L.conv3x3(x16, ws, bp, out, batch=1, height=64, width=64, k_atoms=3, np_=192, cout=180, out_mode=L.CONV_OUT_ROWS_F32, ld_out=178)
     with pytest.raises(RuntimeError):
         L.conv3x3(x16.float(), ws, bp, out, batch=1, height=64, width=64, k_atoms=3, np_=192, cout=180, out_mode=L.CONV_OUT_ROWS_F32, ld_out=180)
+    with pytest.raises(RuntimeError):      # k-steps may wrap over the input atoms once only (a_atoms <= k_atoms <= 2 a_atoms)
+        L.conv3x3(x16[:, :64].contiguous(), ws, bp, out, batch=1, height=64, width=64, k_atoms=3, a_atoms=1, np_=192, cout=180,
+                  out_mode=L.CONV_OUT_ROWS_F32, ld_out=180)

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SRK_LIB") or os.path.join(_HERE, "lib", "libsrk.so")      # SRK_LIB: the debug build (__graft_entry__.build_debug)
 
 # mirrors of the #defines in include/srk.h
-ABI_VERSION = 2
+ABI_VERSION = 3
 DIM, DIM_PAD, HEADS, HEAD_DIM, HEAD_PAD, WINDOW, HIDDEN, HIDDEN_PAD = 180, 192, 6, 30, 32, 8, 360, 384
 ATTN_WSTREAM_BYTES = 3 * 24576 + 9 * 16384 + 3 * 24576
 MLP_WSTREAM_BYTES = 9 * 16384 + 6 * 24576
@@ -57,7 +57,8 @@ class LinearDesc(Structure):
 
 
 class ConvDesc(Structure):
-    _fields_ = [(n, c_int32) for n in ("batch", "height", "width", "k_atoms", "np", "cout", "out_mode", "ld_out", "act")] + [("slope", ctypes.c_float)]
+    _fields_ = [(n, c_int32) for n in ("batch", "height", "width", "k_atoms", "np", "cout", "out_mode", "ld_out", "act")] + \
+               [("slope", ctypes.c_float), ("a_atoms", c_int32)]
 
 
 CONV_OUT_ROWS_F32, CONV_OUT_NHWC_F16, CONV_OUT_SHUFFLE2_F16, CONV_OUT_IMAGE = 0, 1, 2, 3
@@ -150,7 +151,7 @@ def load():
     lib.srk_stitch_normalize.argtypes = [c_void_p, c_void_p, c_int32, c_int64, c_void_p]
     lib.srk_conv3x3_fwd.argtypes = [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.srk_rows_to_f16.argtypes = [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int64, c_void_p]
-    lib.srk_rows_to_f16_split.argtypes = [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int64, c_int32,
+    lib.srk_rows_to_f16_split.argtypes = [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_int64, c_int32,
                                           ctypes.c_float, c_int32, c_int32, c_void_p]
     lib.srk_image_to_f16_split.argtypes = [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32,
                                            POINTER(ctypes.c_float), ctypes.c_float, c_void_p, c_void_p]
@@ -381,18 +382,20 @@ def stitch_finalize(E, cnt_y, cnt_x, out) -> None:
 
 
 def conv3x3(x16, wstream, bias, out, *, batch, height, width, k_atoms, np_, cout, out_mode, ld_out, act=ACT_NONE, slope=0.0,
-            residual=None) -> None:
-    """srk_conv3x3_fwd (include/srk.h): x16 = fp16 NHWC (batch, height, width, 64 k_atoms); out per out_mode."""
+            residual=None, a_atoms=0) -> None:
+    """srk_conv3x3_fwd (include/srk.h): x16 = fp16 NHWC (batch, height, width, 64 a_atoms), a_atoms = k_atoms unless given (the
+    tight mode's [lo | hi] image: a_atoms = 2/3 k_atoms); out per out_mode."""
     lib = load()
-    if x16.dtype != torch.float16 or x16.numel() != batch * height * width * 64 * k_atoms or not x16.is_contiguous():
-        raise RuntimeError("conv3x3: input must be a contiguous fp16 NHWC tensor of batch * height * width * 64 * k_atoms elements")
+    in_atoms = a_atoms or k_atoms
+    if x16.dtype != torch.float16 or x16.numel() != batch * height * width * 64 * in_atoms or not x16.is_contiguous():
+        raise RuntimeError("conv3x3: input must be a contiguous fp16 NHWC tensor of batch * height * width * 64 * a_atoms elements")
     want = torch.float32 if out_mode in (CONV_OUT_ROWS_F32, CONV_OUT_IMAGE) else torch.float16
     if out.dtype != want or not out.is_contiguous():
         raise RuntimeError(f"conv3x3: output must be contiguous {want}")
     if wstream.numel() != 9 * k_atoms * np_ * 128 or bias.numel() != np_:
         raise RuntimeError("conv3x3: weight stream / bias size does not match k_atoms, np")
     _require_cuda_f32(bias, residual)
-    d = ConvDesc(batch, height, width, k_atoms, np_, cout, out_mode, ld_out, act, float(slope))
+    d = ConvDesc(batch, height, width, k_atoms, np_, cout, out_mode, ld_out, act, float(slope), a_atoms)
     label = "conv3x3" if PROFILE is None else f"conv3x3_c{64 * k_atoms}_n{np_}"
     with _launch(label, x16, wstream, bias, out, residual) as st:
         _check(lib.srk_conv3x3_fwd(ctypes.byref(d), x16.data_ptr(), wstream.data_ptr(), bias.data_ptr(), _ptr(residual), out.data_ptr(), st), lib)
@@ -410,25 +413,19 @@ def rows_to_f16(x, out16, *, channels, ld_in, pixels) -> None:
 
 
 def rows_to_f16_split(x, out16, *, channels, ld_in, pixels, act=ACT_NONE, slope=0.0, shuffle=None) -> None:
-    """srk_rows_to_f16_split: fp32 rows (pixels, ld_in) -> the fp16 pair hi = fp16(act(x)), lo = fp16(act(x) - hi) of the tight mode.
-    out16 (2, P, cp): two NHWC images (hi, lo).  out16 (P, 3 * 64): the interleaved [hi | lo | hi] image of a C_in = 64 layer.
-    shuffle = (H, W): x holds the 256 channels of a conv + PixelShuffle(2) stage at H x W pixels per image; P = 4 * pixels."""
+    """srk_rows_to_f16_split: fp32 rows (pixels, ld_in) -> the tight mode's fp16 pair image out16 (P, 2 cp) = [lo | hi],
+    hi = fp16(act(x)), lo = fp16(act(x) - hi), cp = 64 * ceil(channels / 64) zero-padded channels each.
+    shuffle = (H, W): x holds the 256 channels of a conv + PixelShuffle(2) stage at H x W pixels per image; P = 4 * pixels, cp = 64."""
     lib = load()
     _require_cuda_f32(x)
-    if out16.dtype != torch.float16 or not out16.is_contiguous():
-        raise RuntimeError("rows_to_f16_split: output must be a contiguous fp16 tensor")
     opix = pixels * (4 if shuffle else 1)
-    if out16.dim() == 3 and out16.shape[0] == 2 and out16.shape[1] == opix:
-        cp = ld_out = out16.shape[2]
-        hi, lo, hi2 = out16.data_ptr(), out16[1].data_ptr(), None
-    elif out16.dim() == 2 and out16.shape == (opix, 192):
-        cp, ld_out = 64, 192
-        hi, lo, hi2 = out16.data_ptr(), out16.data_ptr() + 128, out16.data_ptr() + 256
-    else:
-        raise RuntimeError(f"rows_to_f16_split: output must be (2, {opix}, cp) or ({opix}, 192), got {tuple(out16.shape)}")
+    if out16.dtype != torch.float16 or not out16.is_contiguous() or out16.dim() != 2 or out16.shape[0] != opix or out16.shape[1] % 128:
+        raise RuntimeError(f"rows_to_f16_split: output must be a contiguous fp16 ({opix}, 2 cp) tensor, got {tuple(out16.shape)}")
+    cp = out16.shape[1] // 2
     sh, sw = shuffle if shuffle else (0, 0)
     with _launch("rows_to_f16_split", x, out16) as st:
-        _check(lib.srk_rows_to_f16_split(x.data_ptr(), ld_in, channels, hi, lo, hi2, ld_out, cp, pixels, act, slope, sh, sw, st), lib)
+        _check(lib.srk_rows_to_f16_split(x.data_ptr(), ld_in, channels, out16.data_ptr() + 2 * cp, out16.data_ptr(), 2 * cp, cp, pixels, act, slope,
+                                         sh, sw, st), lib)
 
 
 def image_to_f16_split(x, out16, mean, img_range) -> None:

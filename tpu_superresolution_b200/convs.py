@@ -12,8 +12,8 @@ tail fused into the epilogue:
   * HAT's CAB (hat_arch.py:67-72): conv -> GELU -> conv.
 
 Tight mode (``SwinIR.set_precision("fp16")``, module flag ``SPLIT``): the same layers through ``SplitConv3x3`` /
-``SplitPixelShuffleTail`` -- activations and weights as hi / lo fp16 pairs, three products per layer accumulated in fp32
-(fp32-class accuracy from the fp16 tensor-core kernel; intermediates stay fp32 rows).
+``SplitPixelShuffleTail`` -- activations and weights as hi / lo fp16 pairs, three products per layer accumulated in fp32 in one
+launch (fp32-class accuracy from the fp16 tensor-core kernel; intermediates stay fp32 rows).
 
 ``SRK_CONV=cudnn`` selects the round-1 path (library convolutions + separate bias / activation / shuffle passes) for A/B runs.
 """
@@ -91,56 +91,40 @@ def rows_to_f16(rows: torch.Tensor, channels: int) -> torch.Tensor:
     return out
 
 
-def rows_split(rows: torch.Tensor, channels: int, *, interleaved: bool = False, act: int = L.ACT_NONE, slope: float = 0.0,
-               shuffle=None) -> torch.Tensor:
-    """fp32 token rows (..., C) -> the tight mode's fp16 pair (srk_rows_to_f16_split): (2, P, 64 * ceil(C / 64)) = (hi, lo) images,
-    or with interleaved=True (C = 64) the (P, 192) image [hi | lo | hi].  shuffle=(H, W): rows are a conv + PixelShuffle(2)
-    stage's 256 channels at H x W; the pair comes out at 2H x 2W (P = 4 x pixels)."""
+def rows_split(rows: torch.Tensor, channels: int, *, act: int = L.ACT_NONE, slope: float = 0.0, shuffle=None) -> torch.Tensor:
+    """fp32 token rows (..., C) -> the tight mode's fp16 pair image (P, 2 cp) = [lo | hi], cp = 64 * ceil(C / 64)
+    (srk_rows_to_f16_split).  shuffle=(H, W): rows are a conv + PixelShuffle(2) stage's 256 channels at H x W; the pair comes out at
+    2H x 2W (P = 4 x pixels, cp = 64)."""
     pixels = rows.numel() // rows.shape[-1]
     opix = 4 * pixels if shuffle else pixels
     cp = 64 if shuffle else (channels + 63) // 64 * 64
-    if interleaved and cp != 64:
-        raise RuntimeError("rows_split: the interleaved layout is for 64-channel layers")
-    out = torch.empty((opix, 192) if interleaved else (2, opix, cp), dtype=torch.float16, device=rows.device)
+    out = torch.empty(opix, 2 * cp, dtype=torch.float16, device=rows.device)
     L.rows_to_f16_split(rows, out, channels=channels, ld_in=rows.shape[-1], pixels=pixels, act=act, slope=slope, shuffle=shuffle)
     return out
 
 
 class SplitConv3x3:
     """FusedConv3x3 for the tight mode: fp32-class accuracy out of the fp16 tensor-core kernel.  Activations and weights are fp16
-    pairs (x = hi + lo to 22 bits) and conv(x, w) = hi(x) * hi(w) + lo(x) * hi(w) + hi(x) * lo(w), accumulated in fp32:
-    C_in = 64 layers in ONE launch over the interleaved image (k_atoms = 3), wider layers as three launches accumulating into the
-    fp32 output rows (smallest terms first)."""
+    pairs (x = hi + lo to 22 bits) and conv(x, w) = lo(x) * hi(w) + hi(x) * lo(w) + hi(x) * hi(w), accumulated in fp32 in ONE
+    launch, small terms first: 3 C/64 k-steps over the [lo | hi] image against the weight stream [hi(w) | lo(w) | hi(w)]
+    (srk.h: SrkConvDesc.a_atoms)."""
 
     def __init__(self, conv: nn.Conv2d, *, pixel_shuffle: bool = False, out_scale: float = 1.0, out_shift=None):
         FusedConv3x3(conv)                 # geometry check
         self.conv = conv
-        self.interleaved = conv.in_channels <= 64
-        self.kw = dict(pixel_shuffle=pixel_shuffle, out_scale=out_scale, out_shift=out_shift,
-                       split="interleaved" if self.interleaved else "pair")
+        self.kw = dict(pixel_shuffle=pixel_shuffle, out_scale=out_scale, out_shift=out_shift, split=True)
         self._cache = _Cache()
 
     def packed(self):
         c = self.conv
-
-        def build():
-            ws, bias, meta = packing.pack_conv3x3(c.weight, c.bias, **self.kw)
-            return ws, bias, torch.zeros_like(bias), meta
-        return self._cache.get([c.weight, c.bias], build)
+        return self._cache.get([c.weight, c.bias], lambda: packing.pack_conv3x3(c.weight, c.bias, **self.kw))
 
     def __call__(self, xs: torch.Tensor, B: int, H: int, W: int, *, out: torch.Tensor, mode: int, ld_out: int,
                  residual: Optional[torch.Tensor] = None) -> torch.Tensor:
         """xs: rows_split(...) of the input.  The activation of the layer (if any) is applied by the NEXT rows_split."""
-        ws, bias, zero, meta = self.packed()
-        kw = dict(batch=B, height=H, width=W, k_atoms=meta["k_atoms"], np_=meta["np"], cout=meta["cout"], out_mode=mode, ld_out=ld_out)
-        if self.interleaved:
-            L.conv3x3(xs, ws, bias, out, residual=residual, **kw)
-            return out
-        if mode != L.CONV_OUT_ROWS_F32:
-            raise RuntimeError("SplitConv3x3: layers wider than 64 input channels accumulate in fp32 rows (CONV_OUT_ROWS_F32)")
-        L.conv3x3(xs[1], ws[0], zero, out, residual=residual, **kw)          # lo(x) * hi(w)  (+ residual)
-        L.conv3x3(xs[0], ws[1], zero, out, residual=out, **kw)               # + hi(x) * lo(w)
-        L.conv3x3(xs[0], ws[0], bias, out, residual=out, **kw)               # + hi(x) * hi(w) + bias
+        ws, bias, meta = self.packed()
+        L.conv3x3(xs, ws, bias, out, batch=B, height=H, width=W, k_atoms=meta["k_atoms"], a_atoms=meta["a_atoms"], np_=meta["np"],
+                  cout=meta["cout"], out_mode=mode, ld_out=ld_out, residual=residual)
         return out
 
 
@@ -159,11 +143,11 @@ class SplitPixelShuffleTail:
         dev = xs.device
         t = torch.empty(B * H * W, 64, dtype=torch.float32, device=dev)
         self.before(xs, B, H, W, out=t, mode=L.CONV_OUT_ROWS_F32, ld_out=64)
-        ts = rows_split(t, 64, interleaved=True, act=L.ACT_LEAKY_RELU, slope=self.slope)
+        ts = rows_split(t, 64, act=L.ACT_LEAKY_RELU, slope=self.slope)
         for up in self.ups:
             u = torch.empty(B * H * W, 256, dtype=torch.float32, device=dev)
             up(ts, B, H, W, out=u, mode=L.CONV_OUT_ROWS_F32, ld_out=256)
-            ts = rows_split(u, 256, interleaved=True, shuffle=(H, W))
+            ts = rows_split(u, 256, shuffle=(H, W))
             H, W = 2 * H, 2 * W
         y = torch.empty(B, H, W, self.out_ch, dtype=torch.float32, device=dev)
         self.last(ts, B, H, W, out=y, mode=L.CONV_OUT_IMAGE, ld_out=self.out_ch)

@@ -448,14 +448,16 @@ int srk_conv3x3_fwd(const SrkConvDesc* d, const void* in_f16, const void* wstrea
                     void* stream) {
     if (!d || !in_f16 || !wstream || !bias || !out) return fail("srk_conv3x3_fwd: null argument");
     if (d->batch <= 0 || d->height <= 0 || d->width <= 0) return fail("srk_conv3x3_fwd: bad image shape");
-    if (d->k_atoms < 1 || d->k_atoms > 4) return fail("srk_conv3x3_fwd: k_atoms must be 1..4 (got %d)", d->k_atoms);
+    const int a_atoms = d->a_atoms > 0 ? d->a_atoms : d->k_atoms;
+    if (d->k_atoms < 1 || d->k_atoms > 12 || a_atoms > 8 || a_atoms > d->k_atoms || d->k_atoms > 2 * a_atoms)
+        return fail("srk_conv3x3_fwd: need 1 <= a_atoms <= 8 and a_atoms <= k_atoms <= min(12, 2 a_atoms) (got k_atoms %d, a_atoms %d)", d->k_atoms, d->a_atoms);
     if (!aligned16(in_f16) || !aligned16(wstream) || !aligned16(out) || (residual && !aligned16(residual)))
         return fail("srk_conv3x3_fwd: pointers must be 16-byte aligned");
     if (static_cast<int64_t>(d->batch) * d->height * d->width * 4 >= (int64_t(1) << 31)) return fail("srk_conv3x3_fwd: too many pixels");
     srk::ConvArgs a{};
     a.in = static_cast<const __half*>(in_f16); a.wstream = static_cast<const uint8_t*>(wstream); a.bias = bias; a.residual = residual;
     a.B = d->batch; a.H = d->height; a.W = d->width; a.k_atoms = d->k_atoms; a.np = d->np; a.cout = d->cout;
-    a.out_mode = d->out_mode; a.ld_out = d->ld_out; a.act = d->act; a.slope = d->slope;
+    a.out_mode = d->out_mode; a.ld_out = d->ld_out; a.act = d->act; a.slope = d->slope; a.a_atoms = a_atoms;
     switch (d->out_mode) {
         case SRK_CONV_OUT_ROWS_F32:
             if (d->np % 32 || d->np < 32 || d->np > 256 || d->cout > d->np || d->cout % 4 || d->cout <= 0 || d->ld_out < d->cout || d->ld_out % 4)
@@ -491,11 +493,11 @@ int srk_rows_to_f16(const float* x, int32_t ld_in, int32_t channels, void* out_f
     return check(srk::launch_rows_to_f16(x, ld_in, channels, static_cast<__half*>(out_f16), cp, pixels, static_cast<cudaStream_t>(stream)), "srk_rows_to_f16");
 }
 
-int srk_rows_to_f16_split(const float* x, int32_t ld_in, int32_t channels, void* hi_f16, void* lo_f16, void* hi2_f16, int32_t ld_out, int32_t cp,
+int srk_rows_to_f16_split(const float* x, int32_t ld_in, int32_t channels, void* hi_f16, void* lo_f16, int32_t ld_out, int32_t cp,
                           int64_t pixels, int32_t act, float slope, int32_t shuffle_h, int32_t shuffle_w, void* stream) {
     if (!x || !hi_f16 || !lo_f16) return fail("srk_rows_to_f16_split: null argument");
     if (channels <= 0 || ld_in < channels || (ld_in & 3) || cp % 64 || cp <= 0 || ld_out < cp || ld_out % 8 || !aligned16(x) || !aligned16(hi_f16) ||
-        !aligned16(lo_f16) || (hi2_f16 && !aligned16(hi2_f16)))
+        !aligned16(lo_f16))
         return fail("srk_rows_to_f16_split: need ld_in %% 4 == 0 >= channels, cp %% 64 == 0, ld_out %% 8 == 0 >= cp, 16-byte aligned pointers");
     if (shuffle_h > 0 || shuffle_w > 0) {
         if (shuffle_h <= 0 || shuffle_w <= 0 || channels != 256 || cp != 64 || pixels % (static_cast<int64_t>(shuffle_h) * shuffle_w))
@@ -504,9 +506,8 @@ int srk_rows_to_f16_split(const float* x, int32_t ld_in, int32_t channels, void*
         return fail("srk_rows_to_f16_split: cp must cover the channels");
     }
     if (act < SRK_ACT_NONE || act > SRK_ACT_GELU) return fail("srk_rows_to_f16_split: unknown activation %d", act);
-    return check(srk::launch_rows_to_f16_split(x, ld_in, channels, static_cast<__half*>(hi_f16), static_cast<__half*>(lo_f16),
-                                               static_cast<__half*>(hi2_f16), ld_out, cp, pixels, act, slope, shuffle_h, shuffle_w,
-                                               static_cast<cudaStream_t>(stream)), "srk_rows_to_f16_split");
+    return check(srk::launch_rows_to_f16_split(x, ld_in, channels, static_cast<__half*>(hi_f16), static_cast<__half*>(lo_f16), ld_out, cp, pixels,
+                                               act, slope, shuffle_h, shuffle_w, static_cast<cudaStream_t>(stream)), "srk_rows_to_f16_split");
 }
 
 int srk_image_to_f16_split(const float* x, int64_t sb, int64_t sc, int64_t sy, int64_t sx, int32_t channels, int32_t batch, int32_t height,

@@ -57,7 +57,7 @@ struct ConvParams {
     int H, W, B;
     int tw_log2, th;                // patch = th rows x (1 << tw_log2) columns = 256 pixels
     int patches_x, patches_y, n_patches;
-    int k_atoms, np, cout;
+    int k_atoms, a_atoms, np, cout;     // k_atoms k-steps of 64 channels over an image of a_atoms atoms (hi/lo split convolutions)
     int out_mode, ld_out, act;
     float slope;
     uint32_t idesc, box_bytes, slab_bytes;
@@ -124,9 +124,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_kernel(const __grid_c
                 patch_geom(patch, b, y0, x0);
                 for (int s = 0; s < n_steps; ++s) {
                     const int ka = s / 3, dx = s - 3 * ka;
+                    // input atom: the last k_atoms - a_atoms steps re-read the image's last atoms ([lo | hi] x [hi(w) | lo(w) | hi(w)])
+                    const int ia = ka >= p.a_atoms ? ka - (p.k_atoms - p.a_atoms) : ka;
                     mbar_wait(&bars[CB_AEMPTY + stage], phase ^ 1);
                     mbar_arrive_expect_tx(&bars[CB_AFULL + stage], p.box_bytes);
-                    tma_load_4d(sbase + CV_A + stage * CV_ABOX, &p.tmap, 64 * ka, x0 + dx - 1, y0 - 1, b, &bars[CB_AFULL + stage]);
+                    tma_load_4d(sbase + CV_A + stage * CV_ABOX, &p.tmap, 64 * ia, x0 + dx - 1, y0 - 1, b, &bars[CB_AFULL + stage]);
                     stage ^= 1;
                     if (stage == 0) phase ^= 1;
                 }
@@ -338,14 +340,15 @@ __global__ void __launch_bounds__(256) rows_to_f16_kernel(const float* __restric
 
 // ---- fp32 token rows -> the fp16 PAIR hi = fp16(v), lo = fp16(v - hi) of the tight mode's split convolutions (v = act(x)):
 // conv(x, w) ~= hi(x) * hi(w) + lo(x) * hi(w) + hi(x) * lo(w) on the fp16 tensor-core kernel, fp32 accumulation; the dropped
-// lo * lo term is 2^-22 relative.  `hi`, `lo` and (optionally) `hi2` are NHWC images with row pitch ld_out; a C_in = 64 layer
-// passes hi = base, lo = base + 64, hi2 = base + 128, ld_out = 192, so that ONE launch of conv3x3_kernel with k_atoms = 3 does
-// all three products against weights packed [hi(w) | hi(w) | lo(w)]; wider layers pass two images and launch three times.
+// lo * lo term is 2^-22 relative.  `hi` and `lo` are NHWC images with row pitch ld_out: the callers pass lo = base, hi = base + cp,
+// ld_out = 2 cp, and ONE launch of conv3x3_kernel walks k_atoms = 3 cp / 64 k-steps over that image's a_atoms = 2 cp / 64 atoms
+// (the last cp / 64 steps re-read the hi atoms) against weights packed [hi(w) | lo(w) | hi(w)]: the two small products are
+// accumulated first, the large one on top (the order matters: the tensor core's fp32 accumulation truncates).
 // The activation of the PREVIOUS layer (conv_before_upsample's LeakyReLU, network_swinir.py:743) is applied on the way in, and
 // with shuffle_h > 0 the rows are the 4 x 64 channels of a conv + nn.PixelShuffle(2) stage (weights packed pixel_shuffle=True,
 // network_swinir.py:584-585): group s = 2 i + j of input pixel (y, x) goes to output pixel (2 y + i, 2 x + j).
 __global__ void __launch_bounds__(256) rows_to_f16_split_kernel(const float* __restrict__ x, int ld_in, int C, __half* __restrict__ hi,
-                                                                __half* __restrict__ lo, __half* __restrict__ hi2, int ld_out, int cp, int64_t pixels,
+                                                                __half* __restrict__ lo, int ld_out, int cp, int64_t pixels,
                                                                 int act, float slope, int sh, int sw) {
     const int groups = (sh > 0 ? 256 : cp) >> 3;
     const int64_t total = pixels * groups;
@@ -382,7 +385,6 @@ __global__ void __launch_bounds__(256) rows_to_f16_split_kernel(const float* __r
         const int64_t o = opix * ld_out + c0;
         *reinterpret_cast<uint4*>(hi + o) = H;
         *reinterpret_cast<uint4*>(lo + o) = Lo;
-        if (hi2 != nullptr) *reinterpret_cast<uint4*>(hi2 + o) = H;
     }
 }
 
@@ -444,7 +446,8 @@ cudaError_t launch_conv3x3(const ConvArgs& a, cudaStream_t stream) {
     ConvParams p{};
     pick_patch(a.H, a.W, p.tw_log2, p.th);
     const int TW = 1 << p.tw_log2;
-    const cuuint64_t cp = 64ull * a.k_atoms;
+    const int a_atoms = a.a_atoms > 0 ? a.a_atoms : a.k_atoms;
+    const cuuint64_t cp = 64ull * a_atoms;
     const cuuint64_t gdim[4] = {cp, static_cast<cuuint64_t>(a.W), static_cast<cuuint64_t>(a.H), static_cast<cuuint64_t>(a.B)};
     const cuuint64_t gstr[3] = {cp * 2, cp * 2 * a.W, cp * 2 * a.W * a.H};
     const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(TW), static_cast<cuuint32_t>(p.th + 2), 1};
@@ -457,7 +460,7 @@ cudaError_t launch_conv3x3(const ConvArgs& a, cudaStream_t stream) {
     p.patches_x = (a.W + TW - 1) / TW;
     p.patches_y = (a.H + p.th - 1) / p.th;
     p.n_patches = a.B * p.patches_x * p.patches_y;
-    p.k_atoms = a.k_atoms; p.np = a.np; p.cout = a.cout;
+    p.k_atoms = a.k_atoms; p.a_atoms = a_atoms; p.np = a.np; p.cout = a.cout;
     p.out_mode = a.out_mode; p.ld_out = a.ld_out; p.act = a.act; p.slope = a.slope;
     p.idesc = (1u << 4) | (static_cast<uint32_t>(a.np >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);      // kind::f16, A = B = fp16, D = fp32, K-major
     p.box_bytes = static_cast<uint32_t>((p.th + 2) * TW * 128);
@@ -480,13 +483,13 @@ cudaError_t launch_rows_to_f16(const float* x, int ld_in, int C, __half* out, in
     return cudaGetLastError();
 }
 
-cudaError_t launch_rows_to_f16_split(const float* x, int ld_in, int C, __half* hi, __half* lo, __half* hi2, int ld_out, int cp, int64_t pixels,
+cudaError_t launch_rows_to_f16_split(const float* x, int ld_in, int C, __half* hi, __half* lo, int ld_out, int cp, int64_t pixels,
                                      int act, float slope, int shuffle_h, int shuffle_w, cudaStream_t stream) {
     if (pixels <= 0) return cudaSuccess;
     const int64_t total = pixels * ((shuffle_h > 0 ? 256 : cp) >> 3);
     const int64_t blocks = (total + 255) / 256;
     const int grid = static_cast<int>(blocks < 148 * 16 ? blocks : 148 * 16);
-    rows_to_f16_split_kernel<<<grid, 256, 0, stream>>>(x, ld_in, C, hi, lo, hi2, ld_out, cp, pixels, act, slope, shuffle_h, shuffle_w);
+    rows_to_f16_split_kernel<<<grid, 256, 0, stream>>>(x, ld_in, C, hi, lo, ld_out, cp, pixels, act, slope, shuffle_h, shuffle_w);
     return cudaGetLastError();
 }
 

@@ -217,7 +217,7 @@ cudaError_t launch_stitch_normalize(float* E, const float* Wt, int channels, int
 
 // conv_kernel.cu
 struct ConvArgs {
-    const ::__half* in;          // fp16 NHWC (B, H, W, 64 * k_atoms)
+    const ::__half* in;          // fp16 NHWC (B, H, W, 64 * a_atoms)
     const uint8_t* wstream;      // packing.pack_conv3x3
     const float* bias;           // np floats
     const float* residual;       // fp32 rows like out_f32 (may alias it) or nullptr
@@ -225,10 +225,11 @@ struct ConvArgs {
     ::__half* out_f16;
     int B, H, W, k_atoms, np, cout, out_mode, ld_out, act;
     float slope;
+    int a_atoms;                 // 64-channel atoms of the input image (0: k_atoms); the last k_atoms - a_atoms k-steps re-read its last atoms
 };
 cudaError_t launch_conv3x3(const ConvArgs& a, cudaStream_t stream);
 cudaError_t launch_rows_to_f16(const float* x, int ld_in, int C, ::__half* out, int cp, int64_t pixels, cudaStream_t stream);
-cudaError_t launch_rows_to_f16_split(const float* x, int ld_in, int C, ::__half* hi, ::__half* lo, ::__half* hi2, int ld_out, int cp, int64_t pixels,
+cudaError_t launch_rows_to_f16_split(const float* x, int ld_in, int C, ::__half* hi, ::__half* lo, int ld_out, int cp, int64_t pixels,
                                      int act, float slope, int shuffle_h, int shuffle_w, cudaStream_t stream);
 cudaError_t launch_image_to_f16_split(const float* x, int64_t sb, int64_t sc, int64_t sy, int64_t sx, int C, int B, int H, int W,
                                       const float* mean3, float range, ::__half* out, cudaStream_t stream);

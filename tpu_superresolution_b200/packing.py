@@ -350,7 +350,7 @@ def swizzle_slab_any(mat: torch.Tensor) -> torch.Tensor:
 
 @torch.no_grad()
 def pack_conv3x3(weight, bias, *, split_first: bool = False, pixel_shuffle: bool = False, out_scale: float = 1.0, out_shift=None,
-                 split: Optional[str] = None):
+                 split: bool = False):
     """nn.Conv2d(C_in, C_out, 3, 1, 1) -> (wstream uint8, bias fp32 [np], meta) for srk_conv3x3_fwd.
 
     wstream = k_atoms x 3 (dx) x 3 (dy) slabs of np rows x 64 input channels, fp16, 128-byte swizzled, in the order the kernel's
@@ -360,10 +360,10 @@ def pack_conv3x3(weight, bias, *, split_first: bool = False, pixel_shuffle: bool
     pixel_shuffle (Upsample: conv + nn.PixelShuffle(2), network_swinir.py:584-585): output row (2i + j) * C_out/4 + c <- original
         row 4c + 2i + j, so the kernel's SRK_CONV_OUT_SHUFFLE2_F16 epilogue writes whole 64-channel pixels.
     out_scale / out_shift: y = conv(x) * out_scale + out_shift folded into weights and bias (conv_last: x / img_range + mean).
-    split (tight mode, srk_rows_to_f16_split): the weights as the fp16 pair hi(w), lo(w) = w - hi(w).
-        "pair": wstream = (stream of hi(w), stream of lo(w)) for three accumulating launches (any C_in <= 256);
-        "interleaved" (C_in <= 64): one stream over the input channels [hi(w) | hi(w) | lo(w)], 64 each, against the
-        activations [hi(x) | lo(x) | hi(x)]: one launch with k_atoms = 3.
+    split (tight mode, srk_rows_to_f16_split): the weights as the fp16 pair hi(w), lo(w) = w - hi(w), streamed as the k-atoms
+        [hi(w) | lo(w) | hi(w)] (each part padded to whole k-atoms) against the activation image [lo(x) | hi(x)]: ONE launch with
+        k_atoms = 3 * ceil(C_in / 64) k-steps over a_atoms = 2 * ceil(C_in / 64) input atoms (the last third re-reads hi(x)); the
+        two small products come first.
     """
     dev = weight.device
     w = weight.detach().cpu().double() * out_scale
@@ -390,8 +390,8 @@ def pack_conv3x3(weight, bias, *, split_first: bool = False, pixel_shuffle: bool
     np_ = 16 if cout <= 4 else ((cout + 31) // 32) * 32
     if np_ > 256 or k_atoms > 4:
         raise RuntimeError(f"pack_conv3x3: unsupported geometry C_in {cin} C_out {cout}")
-    if split not in (None, "pair", "interleaved") or (split and split_first) or (split == "interleaved" and k_atoms != 1):
-        raise RuntimeError(f"pack_conv3x3: split={split!r} is not available for this layer (C_in {cin}, split_first {split_first})")
+    if split and split_first:
+        raise RuntimeError("pack_conv3x3: split_first already is a hi / lo split")
     wp = torch.zeros(np_, 64 * k_atoms, 3, 3)
     wp[:cout, :cin] = w
 
@@ -404,11 +404,8 @@ def pack_conv3x3(weight, bias, *, split_first: bool = False, pixel_shuffle: bool
     bp = torch.zeros(np_, dtype=torch.float32)
     bp[:cout] = b.float()
     meta = {"k_atoms": k_atoms, "np": np_, "cout": cout}
-    if split is None:
+    if not split:
         return stream(wp), bp.to(dev), meta
     hi = wp.half().float()
-    lo = wp - hi
-    if split == "pair":
-        return (stream(hi), stream(lo)), bp.to(dev), meta
-    meta["k_atoms"] = 3
-    return stream(torch.cat([hi, hi, lo], dim=1)), bp.to(dev), meta
+    meta.update(k_atoms=3 * k_atoms, a_atoms=2 * k_atoms)
+    return stream(torch.cat([hi, wp - hi, hi], dim=1)), bp.to(dev), meta
