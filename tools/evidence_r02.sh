@@ -1,8 +1,8 @@
 # Final evidence of round 2 (one B200): run under gpurun from the repo root, e.g.
-#   gpurun --timeout 1500 -- 'bash tools/evidence_r02.sh r02k'
+#   gpurun --timeout 1500 -- 'bash tools/evidence_r02.sh r02m'
 # Everything lands in gpurun_out/<tag>_*; copy what should be judged into profiles/.
 set -x
-T=${1:-r02k}
+T=${1:-r02m}
 cd ${GRAFT_REPO_ROOT:-.}
 O=gpurun_out
 timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -15 > $O/${T}_pytest_gpu.log
@@ -13,6 +13,8 @@ for w in hat_x4 dat_x2; do timeout 300 python bench.py --workload $w --steps 20 
 timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > $O/${T}_bench_reference.json 2>> $O/${T}_bench.err
 timeout 120 python tools/kbench_pair.py > $O/${T}_kbench_pair.log 2>&1
 timeout 120 python tools/kbench_conv.py > $O/${T}_kbench_conv.log 2>&1
+timeout 150 python tools/tight_bench.py 10 > $O/${T}_tight_bench.log 2>&1
+timeout 200 python tools/step_bench.py > $O/${T}_step_bench.log 2>&1
 SRK_LIB=$PWD/tpu_superresolution_b200/lib/libsrk_dbg.so timeout 120 python tools/timeline.py > $O/${T}_timeline.log 2>&1
 # ---- ncu launch lists of one steady-state forward per family (after the plain run has exited 0)
 for w in swinir_x4 hat_x4 dat_x2; do
