@@ -312,6 +312,28 @@ cudaError_t launch_stitch_finalize(const float* E, int64_t e_cstride, const floa
 // (1) per-(image, channel) sums; (2) the 180 -> hidden -> 180 squeeze-excite gate (recomputed by every block: 2 x 180 x hidden
 // MACs) fused with the scaled residual add.  Replaces five torch launches (mean, two 1x1 convs, ReLU / sigmoid, addcmul).
 constexpr int CAB_TOK_PER_BLOCK = 64;
+// Sum of the per-chunk partial sums of one image -> s_out[180], by 45 float4 channel groups x KG chunk groups of threads (a serial
+// loop over the 64 chunks per channel cost every block ~5 us of dependent L2 round trips).  Fixed order: run-to-run identical.
+template <int KG>
+__device__ __forceinline__ void sum_partials(const float* __restrict__ sums, int chunks, float* s_out, float4 (*s_part)[SRK_DIM / 4]) {
+    const int cg = threadIdx.x % (SRK_DIM / 4), kg = threadIdx.x / (SRK_DIM / 4);
+    if (kg < KG) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = kg; k < chunks; k += KG) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(sums + static_cast<int64_t>(k) * SRK_DIM) + cg);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        s_part[kg][cg] = a;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < SRK_DIM; c += blockDim.x) {
+        float s = 0.f;
+#pragma unroll
+        for (int g = 0; g < KG; ++g) s += reinterpret_cast<const float*>(s_part[g])[c];
+        s_out[c] = s;
+    }
+    __syncthreads();
+}
 __global__ void __launch_bounds__(192) cab_pool_kernel(const float* __restrict__ y, float* __restrict__ sums, int tokens_per_image) {
     const int b = blockIdx.y, c = threadIdx.x;
     const int t0 = blockIdx.x * CAB_TOK_PER_BLOCK;
@@ -336,13 +358,13 @@ __global__ void __launch_bounds__(256) cab_gate_add_kernel(const float* __restri
                                                            int tokens_per_image) {
     __shared__ float s_mean[SRK_DIM], s_hid[32];
     __shared__ __align__(16) float s_gate[SRK_DIM], s_yb[SRK_DIM];      // s_yb: the bias of the conv that produced y (or 0)
+    __shared__ float4 s_part[5][SRK_DIM / 4];
     const int b = blockIdx.y;
+    sum_partials<5>(sums + static_cast<int64_t>(b) * gridDim.x * SRK_DIM, gridDim.x, s_mean, s_part);
     for (int c = threadIdx.x; c < SRK_DIM; c += blockDim.x) {
-        float s = 0.f;
-        for (int k = 0; k < static_cast<int>(gridDim.x); ++k) s += __ldg(sums + (static_cast<int64_t>(b) * gridDim.x + k) * SRK_DIM + c);
         const float yb = y_bias ? __ldg(y_bias + c) : 0.f;
         s_yb[c] = yb;
-        s_mean[c] = s / static_cast<float>(tokens_per_image) + yb;      // mean(y + bias) = mean(y) + bias
+        s_mean[c] = s_mean[c] / static_cast<float>(tokens_per_image) + yb;      // mean(y + bias) = mean(y) + bias
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -361,6 +383,8 @@ __global__ void __launch_bounds__(256) cab_gate_add_kernel(const float* __restri
     }
     __syncthreads();
     // 64 tokens x 45 float4 per block
+    // 64 tokens x 45 float4 per block (a plain block-stride loop: a (channel group, row phase) thread mapping with gate / bias in
+    // registers and four rows in flight was SLOWER, 7.47 vs 7.24 ms per HAT step)
     const int t0 = blockIdx.x * CAB_TOK_PER_BLOCK;
     const int nt = min(CAB_TOK_PER_BLOCK, tokens_per_image - t0);
     const int64_t base = (static_cast<int64_t>(b) * tokens_per_image + t0) * (SRK_DIM / 4);
@@ -395,12 +419,10 @@ __global__ void __launch_bounds__(192) token_mean_mlp_kernel(const float* __rest
                                                              int tokens_per_image) {
     __shared__ float s_mean[SRK_DIM];
     __shared__ float s_h[64];
+    __shared__ float4 s_part[4][SRK_DIM / 4];
     const int b = blockIdx.x, c = threadIdx.x;
-    if (c < SRK_DIM) {
-        float s = 0.f;
-        for (int k = 0; k < chunks; ++k) s += __ldg(sums + (static_cast<int64_t>(b) * chunks + k) * SRK_DIM + c);
-        s_mean[c] = s / static_cast<float>(tokens_per_image);
-    }
+    sum_partials<4>(sums + static_cast<int64_t>(b) * chunks * SRK_DIM, chunks, s_mean, s_part);
+    if (c < SRK_DIM) s_mean[c] = s_mean[c] / static_cast<float>(tokens_per_image);
     __syncthreads();
     for (int j = c >> 5; j < hidden; j += 6) {             // warp per hidden unit: lane-strided dot product, butterfly sum
         float a = 0.f;
