@@ -378,11 +378,18 @@ __global__ void __launch_bounds__(224) channel_gram_kernel(const float* __restri
 }
 
 __global__ void __launch_bounds__(256) channel_gram_reduce_kernel(const float* __restrict__ part, float* __restrict__ gram, int nblk, int per_image) {
+    // one element per thread, four independent partial sums (k mod 4) so that the loads of a thread overlap; fixed order
     const int b = blockIdx.y;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < per_image; e += gridDim.x * blockDim.x) {
-        float s = 0.f;
-        for (int k = 0; k < nblk; ++k) s += __ldg(part + (static_cast<int64_t>(b) * nblk + k) * per_image + e);
-        gram[static_cast<int64_t>(b) * per_image + e] = s;
+        const float* src = part + static_cast<int64_t>(b) * nblk * per_image + e;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int k = 0;
+        for (; k + 4 <= nblk; k += 4) {
+            s0 += __ldg(src + static_cast<int64_t>(k) * per_image);     s1 += __ldg(src + static_cast<int64_t>(k + 1) * per_image);
+            s2 += __ldg(src + static_cast<int64_t>(k + 2) * per_image); s3 += __ldg(src + static_cast<int64_t>(k + 3) * per_image);
+        }
+        for (; k < nblk; ++k) s0 += __ldg(src + static_cast<int64_t>(k) * per_image);
+        gram[static_cast<int64_t>(b) * per_image + e] = (s0 + s1) + (s2 + s3);
     }
 }
 
@@ -480,7 +487,7 @@ cudaError_t launch_channel_gram(const float* qkv, float* gram, float* ws, int ba
     if (batch <= 0 || tokens_per_image <= 0) return cudaSuccess;
     const int nblk = gram_blocks(tokens_per_image);
     channel_gram_kernel<<<dim3(nblk, batch), 224, 0, stream>>>(qkv, ws, tokens_per_image);
-    channel_gram_reduce_kernel<<<dim3(6, batch), 256, 0, stream>>>(ws, gram, nblk, SRK_HEADS * GRAM_STRIDE);
+    channel_gram_reduce_kernel<<<dim3((SRK_HEADS * GRAM_STRIDE + 255) / 256, batch), 256, 0, stream>>>(ws, gram, nblk, SRK_HEADS * GRAM_STRIDE);
     return cudaGetLastError();
 }
 
