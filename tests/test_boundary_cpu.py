@@ -233,6 +233,8 @@ def test_fp16_operand_packing_and_precision_table():
     for mode, want in srk.swinir.PRECISIONS.items():
         m.set_precision(mode)
         assert all((b.attn.operands, b.mlp.operands) == want for layer in m.layers for b in layer.residual_group.blocks)
+        # tight mode only: the 3x3 convolutions as hi / lo fp16 pairs (a flag on the model and on every RSTB, no global state)
+        assert m.split_conv == (mode == "fp16") and all(layer.split_conv == (mode == "fp16") for layer in m.layers)
     with pytest.raises(ValueError):
         m.set_precision("fp8")
     assert set(L.OPERANDS) == {"bf16", "fp16", "fp16_fast"}

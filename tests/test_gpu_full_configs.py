@@ -110,13 +110,17 @@ def test_tight_mode_split_convolutions_vs_fp32_library_convolutions(shape, monke
     sd = synth.make_swinir_state_dict(cfg, seed=77, kind="stress")
     m = srk.SwinIR(**cfg.as_kwargs()).eval()
     m.load_state_dict(sd, strict=True)
-    m.cuda().set_precision("fp16")
+    m.cuda()
     lr = synth.make_lr_batch(*shape, seed=5).cuda()
-    monkeypatch.setenv("SRK_TIGHT_CONV", "split")
+    monkeypatch.setenv("SRK_TIGHT_CONV", "split")               # read by set_precision()
+    m.set_precision("fp16")
+    assert m.split_conv and all(layer.split_conv for layer in m.layers)
     before = L.launch_count()
     y = m(lr)
     n_split = L.launch_count() - before
     monkeypatch.setenv("SRK_TIGHT_CONV", "library")
+    m.set_precision("fp16")
+    assert not m.split_conv
     before = L.launch_count()
     ref = m(lr)
     assert n_split > L.launch_count() - before                      # the split path is all ours: more of our launches
@@ -125,7 +129,10 @@ def test_tight_mode_split_convolutions_vs_fp32_library_convolutions(shape, monke
     print(f"tight mode {shape}: split vs fp32 library convolutions max abs {err:.3e}")
     assert err <= 1e-4
     monkeypatch.setenv("SRK_TIGHT_CONV", "split")
+    m.set_precision("fp16")
     assert torch.equal(m(lr), y)                                    # deterministic
+    m.set_precision("bf16")
+    assert not m.split_conv and not any(layer.split_conv for layer in m.layers)
 
 
 @pytest.mark.parametrize("name", ["hat_x4", "dat_x2"])

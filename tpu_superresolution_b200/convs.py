@@ -11,7 +11,7 @@ tail fused into the epilogue:
     one kernel each, conv_last with ``/ img_range + mean`` (:838) folded into its weights -> the fp32 image;
   * HAT's CAB (hat_arch.py:67-72): conv -> GELU -> conv.
 
-Tight mode (``SwinIR.set_precision("fp16")``, module flag ``SPLIT``): the same layers through ``SplitConv3x3`` /
+Tight mode (``SwinIR.set_precision("fp16")`` marks the model and its RSTBs with ``split_conv``): the same layers through ``SplitConv3x3`` /
 ``SplitPixelShuffleTail`` -- activations and weights as hi / lo fp16 pairs, three products per layer accumulated in fp32 in one
 launch (fp32-class accuracy from the fp16 tensor-core kernel; intermediates stay fp32 rows).
 
@@ -29,9 +29,6 @@ from . import _lib as L
 from . import packing
 
 USE_FUSED_CONV = os.environ.get("SRK_CONV", "fused") != "cudnn"
-# Tight mode (SwinIR.set_precision("fp16")): every convolution as hi / lo fp16 pairs on the same kernel (SplitConv3x3), set by the
-# model around its forward.
-SPLIT = False
 
 
 class _Cache:
@@ -191,7 +188,7 @@ def group_conv_residual(module: nn.Module, conv: nn.Conv2d, t: torch.Tensor, x: 
     ``x + conv(t)`` with t, x fp32 token rows (B, H*W, C); the result is written over t."""
     B, Ltok, C = t.shape
     t = t.contiguous()
-    if SPLIT:
+    if getattr(module, "split_conv", False):      # tight mode (set_precision): hi / lo fp16 pairs on the same kernel
         if not hasattr(module, "_sconv"):
             object.__setattr__(module, "_sconv", SplitConv3x3(conv))
         return module._sconv(rows_split(t, C), B, x_size[0], x_size[1], out=t, mode=L.CONV_OUT_ROWS_F32, ld_out=C, residual=x.contiguous())
@@ -228,7 +225,7 @@ def fused_forward(model: nn.Module, x: torch.Tensor, first_norm: Optional[nn.Lay
         t = torch.empty_like(feat0)
         L.layernorm(feat0, t, first_norm.weight, first_norm.bias, num_tokens=B * H * W, ld_in=C, ld_out=C)
     t = run_layers(t, (H, W))
-    if SPLIT:
+    if getattr(model, "split_conv", False):
         if not hasattr(model, "_s_after"):
             object.__setattr__(model, "_s_after", SplitConv3x3(model.conv_after_body))
             object.__setattr__(model, "_s_tail", SplitPixelShuffleTail(model.conv_before_upsample, model.upsample, model.conv_last,

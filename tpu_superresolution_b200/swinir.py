@@ -53,6 +53,9 @@ def set_precision(model: nn.Module, precision: str = "bf16") -> None:
             m.operands = PRECISIONS[precision][0]
         elif isinstance(m, Mlp):
             m.operands = PRECISIONS[precision][1]
+        elif isinstance(m, (RSTB, SwinIR)):
+            # tight mode: the 3x3 convolutions as hi / lo fp16 pairs (convs.SplitConv3x3); a per-module flag, no global state
+            m.split_conv = precision == "fp16" and os.environ.get("SRK_TIGHT_CONV", "split") != "library"
     convs.invalidate_all()
 
 
@@ -572,23 +575,18 @@ class SwinIR(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("SwinIR: CUDA input required (no CPU fallback)")
         _inference_only(self.conv_first)
-        if getattr(self, "precision", "bf16") == "fp16" and convs.USE_FUSED_CONV and not convs.SPLIT:
-            # tight mode: the fused attention / MLP kernels with fp16 operands, and the 3x3 convolutions as hi / lo fp16 pairs on
-            # the tcgen05 kernel (convs.SplitConv3x3; plain fp16 operands alone cost 1.7 - 2.6e-4 max abs, like cuDNN's TF32:
-            # tools/probe_precision.py).  SRK_TIGHT_CONV=library: fp32 library convolutions instead (the earlier tight mode, A/B).
-            if convs.fused_ok(self) and not self.ape and x.dtype == torch.float32 and os.environ.get("SRK_TIGHT_CONV", "split") != "library":
-                convs.SPLIT = True
-                try:
-                    return self._forward_fused(x)
-                finally:
-                    convs.SPLIT = False
+        fused = convs.fused_ok(self) and not self.ape and x.dtype == torch.float32
+        if getattr(self, "precision", "bf16") == "fp16" and convs.USE_FUSED_CONV and not (fused and getattr(self, "split_conv", False)):
+            # tight mode (set_precision) where the split convolutions (convs.SplitConv3x3) do not apply -- an upsampler / residual
+            # connection outside the fused forward, or SRK_TIGHT_CONV=library (the earlier tight mode, kept for A/B runs): fp32 library
+            # convolutions with cuDNN's TF32 paths off (a TF32-class convolution alone costs 1.7 - 2.6e-4: tools/probe_precision.py)
             tf32 = torch.backends.cudnn.allow_tf32
             convs.USE_FUSED_CONV, torch.backends.cudnn.allow_tf32 = False, False
             try:
                 return self.forward(x)
             finally:
                 convs.USE_FUSED_CONV, torch.backends.cudnn.allow_tf32 = True, tf32
-        if convs.fused_ok(self) and not self.ape and x.dtype == torch.float32:
+        if fused:
             return self._forward_fused(x)
         self._prepare(x.device)
         H, W = x.shape[2:]
