@@ -360,6 +360,17 @@ __global__ void __launch_bounds__(256) cab_gate_add_kernel(const float* __restri
     __shared__ __align__(16) float s_gate[SRK_DIM], s_yb[SRK_DIM];      // s_yb: the bias of the conv that produced y (or 0)
     __shared__ float4 s_part[5][SRK_DIM / 4];
     const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // hidden <= 8 (HAT: 180 / 30 = 6): this thread's squeeze / excite weights are fetched before the partial sums, so the three
+    // dependent global round trips of the prologue (partial sums -> W1 -> W2) become one
+    const bool small = hidden <= 8;
+    float w1r[6], w2r[8], b1r = 0.f, b2r = 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) w1r[k] = (small && warp < hidden && lane + 32 * k < SRK_DIM) ? __ldg(w1 + warp * SRK_DIM + lane + 32 * k) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w2r[j] = (small && threadIdx.x < SRK_DIM && j < hidden) ? __ldg(w2 + threadIdx.x * hidden + j) : 0.f;
+    if (small && warp < hidden) b1r = __ldg(b1 + warp);
+    if (small && threadIdx.x < SRK_DIM) b2r = __ldg(b2 + threadIdx.x);
     sum_partials<5>(sums + static_cast<int64_t>(b) * gridDim.x * SRK_DIM, gridDim.x, s_mean, s_part);
     for (int c = threadIdx.x; c < SRK_DIM; c += blockDim.x) {
         const float yb = y_bias ? __ldg(y_bias + c) : 0.f;
@@ -367,22 +378,38 @@ __global__ void __launch_bounds__(256) cab_gate_add_kernel(const float* __restri
         s_mean[c] = s_mean[c] / static_cast<float>(tokens_per_image) + yb;      // mean(y + bias) = mean(y) + bias
     }
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int j = warp; j < hidden; j += 8) {                 // hidden unit j: one warp, lanes stride over the 180 inputs
-        float a = 0.f;
-        for (int c = lane; c < SRK_DIM; c += 32) a = fmaf(w1[j * SRK_DIM + c], s_mean[c], a);
+    if (small) {
+        if (warp < hidden) {                                 // hidden unit `warp`: lanes stride over the 180 inputs (same order as below)
+            float a = 0.f;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) s_hid[j] = fmaxf(a + b1[j], 0.f);
+            for (int k = 0; k < 6; ++k) if (lane + 32 * k < SRK_DIM) a = fmaf(w1r[k], s_mean[lane + 32 * k], a);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) s_hid[warp] = fmaxf(a + b1r, 0.f);
+        }
+        __syncthreads();
+        if (threadIdx.x < SRK_DIM) {
+            float a = b2r;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (j < hidden) a = fmaf(w2r[j], s_hid[j], a);
+            s_gate[threadIdx.x] = scale / (1.0f + __expf(-a));
+        }
+    } else {
+        for (int j = warp; j < hidden; j += 8) {             // hidden unit j: one warp, lanes stride over the 180 inputs
+            float a = 0.f;
+            for (int c = lane; c < SRK_DIM; c += 32) a = fmaf(w1[j * SRK_DIM + c], s_mean[c], a);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) s_hid[j] = fmaxf(a + b1[j], 0.f);
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < SRK_DIM; c += blockDim.x) {
+            float a = b2[c];
+            for (int j = 0; j < hidden; ++j) a = fmaf(w2[c * hidden + j], s_hid[j], a);
+            s_gate[c] = scale / (1.0f + __expf(-a));
+        }
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < SRK_DIM; c += blockDim.x) {
-        float a = b2[c];
-        for (int j = 0; j < hidden; ++j) a = fmaf(w2[c * hidden + j], s_hid[j], a);
-        s_gate[c] = scale / (1.0f + __expf(-a));
-    }
-    __syncthreads();
-    // 64 tokens x 45 float4 per block
     // 64 tokens x 45 float4 per block (a plain block-stride loop: a (channel group, row phase) thread mapping with gate / bias in
     // registers and four rows in flight was SLOWER, 7.47 vs 7.24 ms per HAT step)
     const int t0 = blockIdx.x * CAB_TOK_PER_BLOCK;
