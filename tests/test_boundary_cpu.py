@@ -206,6 +206,58 @@ def test_split_conv_packing():
         packing.pack_conv3x3(torch.randn(180, 3, 3, 3), None, split_first=True, split=True)
 
 
+def _emulate_conv_from_stream(x_atoms, wstream, bias, meta):
+    """Host model of conv3x3_kernel's data path (csrc/conv_kernel.cu): k-step ka multiplies input atom
+    ia = ka if ka < a_atoms else ka - (k_atoms - a_atoms) with the slabs (ka, dx, dy) of the stream; float64 accumulation.
+    x_atoms: (B, a_atoms * 64, H, W) fp16 values as float64.  Returns (B, np, H, W)."""
+    k_atoms, np_ = meta["k_atoms"], meta["np"]
+    a_atoms = meta.get("a_atoms", k_atoms)
+    slabs = wstream.view(torch.float16).reshape(k_atoms, 3, 3, np_, 64)                       # [ka][dx][dy][row][k]
+    out = bias.double().view(1, np_, 1, 1).repeat(x_atoms.shape[0], 1, x_atoms.shape[2], x_atoms.shape[3])
+    for ka in range(k_atoms):
+        ia = ka if ka < a_atoms else ka - (k_atoms - a_atoms)
+        w = torch.zeros(np_, 64, 3, 3, dtype=torch.float64)
+        for dx in range(3):
+            for dy in range(3):
+                w[:, :, dy, dx] = packing.unswizzle_slab(slabs[ka, dx, dy].view(torch.int16)).view(torch.float16).double()
+        out += torch.nn.functional.conv2d(x_atoms[:, 64 * ia:64 * ia + 64], w, padding=1)
+    return out
+
+
+@pytest.mark.parametrize("cin,cout,kw", [(180, 180, {}), (64, 256, {"pixel_shuffle": True}),
+                                          (64, 3, {"out_scale": 0.5, "out_shift": [0.4488, 0.4371, 0.4040]})])
+def test_split_conv_stream_reproduces_the_fp32_convolution(cin, cout, kw):
+    """The tight mode's algebra end to end on the host: activations as the [lo | hi] fp16 pair image (what srk_rows_to_f16_split
+    writes), weights as the packed [hi(w) | lo(w) | hi(w)] stream, the kernel's k-step -> input-atom rule -- against the float64
+    convolution of the original weights (incl. the pixel-shuffle row permutation and the folded output scale / shift).  Exact
+    accumulation here, so what remains is the dropped lo * lo term and the fp16 rounding of lo: <= 1e-6 of the output's magnitude;
+    the same stream without the lo parts (plain fp16 operands) is ~1e-4."""
+    g = torch.Generator().manual_seed(cin + cout)
+    B, H, W = 1, 9, 11
+    x = torch.randn(B, cin, H, W, generator=g)
+    w, b = torch.randn(cout, cin, 3, 3, generator=g) * 0.05, torch.randn(cout, generator=g) * 0.1
+    ws, bias, meta = packing.pack_conv3x3(w, b, split=True, **kw)
+    cp = 64 * ((cin + 63) // 64)
+    assert meta["k_atoms"] == 3 * cp // 64 and meta["a_atoms"] == 2 * cp // 64
+    hi = x.half().float()
+    lo = (x - hi).half().float()
+    img = torch.zeros(B, 2 * cp, H, W, dtype=torch.float64)
+    img[:, :cin], img[:, cp:cp + cin] = lo.double(), hi.double()                  # [lo | hi], zero padded
+    y = _emulate_conv_from_stream(img, ws, bias, meta)[:, :cout]
+    ref = torch.nn.functional.conv2d(x.double(), w.double(), b.double(), padding=1)
+    if kw.get("pixel_shuffle"):                                                   # packed row s * 64 + c <- original row 4 c + s
+        ref = ref.reshape(B, cout // 4, 4, H, W).transpose(1, 2).reshape(B, cout, H, W)
+    if "out_scale" in kw:
+        ref = ref * kw["out_scale"] + torch.tensor(kw["out_shift"], dtype=torch.float64).view(1, -1, 1, 1)
+    scale = ref.abs().max()
+    assert (y - ref).abs().max() <= 1e-6 * scale
+    plain_ws, plain_bias, plain_meta = packing.pack_conv3x3(w, b, **kw)
+    img_hi = torch.zeros(B, cp, H, W, dtype=torch.float64)
+    img_hi[:, :cin] = hi.double()
+    y16 = _emulate_conv_from_stream(img_hi, plain_ws, plain_bias, plain_meta)[:, :cout]
+    assert (y16 - ref).abs().max() > 20 * (y - ref).abs().max()                   # what the split buys
+
+
 def test_fp16_operand_packing_and_precision_table():
     """Tight mode / default MLP (include/srk.h: SRK_OPERANDS_*): the same slab stream with fp16 elements, closer to the fp32 weights
     than the bf16 one; weights outside the fp16 range are an error; set_precision() maps the three modes onto the modules."""
