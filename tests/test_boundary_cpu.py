@@ -258,6 +258,22 @@ def test_split_conv_stream_reproduces_the_fp32_convolution(cin, cout, kw):
     assert (y16 - ref).abs().max() > 20 * (y - ref).abs().max()                   # what the split buys
 
 
+def test_conv_first_split_stream_reproduces_the_fp32_convolution():
+    """conv_first (network_swinir.py:720): the image as [hi(v), v - hi(v), hi(v)] inside one 64-channel atom (srk_image_to_f16_split)
+    against weights packed [hi(w), hi(w), w - hi(w)] (pack_conv3x3(split_first=True)), through the same host model."""
+    g = torch.Generator().manual_seed(3)
+    v = torch.rand(2, 3, 10, 12, generator=g) - 0.45
+    w, b = torch.randn(180, 3, 3, 3, generator=g) * 0.2, torch.randn(180, generator=g) * 0.1
+    ws, bias, meta = packing.pack_conv3x3(w, b, split_first=True)
+    assert meta == {"k_atoms": 1, "np": 192, "cout": 180}
+    hi = v.half().float()
+    img = torch.zeros(2, 64, 10, 12, dtype=torch.float64)
+    img[:, 0:3], img[:, 3:6], img[:, 6:9] = hi.double(), (v - hi).half().double(), hi.double()
+    y = _emulate_conv_from_stream(img, ws, bias, meta)[:, :180]
+    ref = torch.nn.functional.conv2d(v.double(), w.double(), b.double(), padding=1)
+    assert (y - ref).abs().max() <= 2e-6 * ref.abs().max()
+
+
 def test_fp16_operand_packing_and_precision_table():
     """Tight mode / default MLP (include/srk.h: SRK_OPERANDS_*): the same slab stream with fp16 elements, closer to the fp32 weights
     than the bf16 one; weights outside the fp16 range are an error; set_precision() maps the three modes onto the modules."""
