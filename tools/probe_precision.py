@@ -19,8 +19,10 @@ for cfg_name in ("swinir_x2", "swinir_x4"):
         ref = torch.from_numpy(np.load(os.path.join(GOLDEN, f"{cfg_name}_{kind}_1x64x64.npz"))["y"])
         for ops in ("bf16", "fp16"):
             m.set_precision(ops)
-            for conv in ("fused", "cudnn-fp32", "cudnn-tf32"):
-                convs.USE_FUSED_CONV = conv == "fused"
+            for conv in ("fused", "split", "cudnn-fp32", "cudnn-tf32"):      # fused: plain fp16 operands; split: hi / lo pairs (tight mode)
+                convs.USE_FUSED_CONV = conv in ("fused", "split")
+                for mod in [m] + list(m.layers):
+                    mod.split_conv = conv == "split"
                 torch.backends.cudnn.allow_tf32 = conv == "cudnn-tf32"
                 torch.backends.cuda.matmul.allow_tf32 = False
                 y = m(lr).cpu()
