@@ -19,6 +19,7 @@ for cfg_name in ("swinir_x2", "swinir_x4"):
         ref = torch.from_numpy(np.load(os.path.join(GOLDEN, f"{cfg_name}_{kind}_1x64x64.npz"))["y"])
         for ops in ("bf16", "fp16"):
             m.set_precision(ops)
+            m.precision = "probe"          # the flags below pick the convolution path, not SwinIR.forward's tight-mode branch
             for conv in ("fused", "split", "cudnn-fp32", "cudnn-tf32"):      # fused: plain fp16 operands; split: hi / lo pairs (tight mode)
                 convs.USE_FUSED_CONV = conv in ("fused", "split")
                 for mod in [m] + list(m.layers):
